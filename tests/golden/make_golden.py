@@ -1,0 +1,197 @@
+#!/usr/bin/env python
+"""Generate golden vectors from the LIVE reference modules.
+
+Run in the build container only (the reference tree is not shipped to the GPU
+box):
+
+    python tests/golden/make_golden.py [--ref /root/reference]
+
+It imports the reference's decoders from `--ref` (read-only, nothing is copied
+into this repo), builds each with small dimensions, runs forward + the training
+loss glue + backward and beam search on seeded inputs, and writes the inputs,
+the `state_dict` and every output to `tests/golden/<case>.pt`.
+
+Two harness-side restatements are applied to the imported modules, both
+documented in SURVEY.md §8c:
+  * the module-global `device` is forced to CPU;
+  * for `sample`, the module source is re-executed with the parent-index
+    division `top_k_words / vocab_size` spelled `//` (true division makes the
+    upstream code raise IndexError on torch >= 1.5).
+The reference is otherwise untouched.
+"""
+import argparse
+import importlib
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_reference(ref_root):
+    sys.path.insert(0, ref_root)
+    mods = {}
+    for kind, cls in (("attention_scn", "AttentionSCN"), ("pure_scn", "PureSCN"),
+                      ("pure_attention", "PureAttention")):
+        m = importlib.import_module("models.decoders." + kind)
+        m.device = torch.device("cpu")
+        with open(m.__file__) as fh:
+            src = fh.read()
+        assert "top_k_words / vocab_size" in src
+        patched = {}
+        ns = dict(m.__dict__)
+        exec(compile(src.replace("top_k_words / vocab_size", "top_k_words // vocab_size"),
+                     m.__file__, "exec"), ns)
+        ns["device"] = torch.device("cpu")
+        patched["cls_fixed"] = ns[cls]
+        # the class object exec'd above looks up `device` in ns
+        mods[kind] = (getattr(m, cls), patched["cls_fixed"], ns)
+    import trains  # noqa: F401  (package only; trains/*.py need h5py/nltk and are not imported)
+    return mods
+
+
+def loss_glue(scores, caps_sorted, decode_lengths, alphas, alpha_c=1.0):
+    # the five lines of trains/attention_scn.py:219-235, stock torch ops
+    from torch.nn.utils.rnn import pack_padded_sequence
+    targets = caps_sorted[:, 1:]
+    s = pack_padded_sequence(scores, decode_lengths, batch_first=True).data
+    t = pack_padded_sequence(targets, decode_lengths, batch_first=True).data
+    loss = torch.nn.CrossEntropyLoss()(s, t)
+    if alphas is not None:
+        loss = loss + alpha_c * ((1. - alphas.sum(dim=1)) ** 2).mean()
+    return loss
+
+
+def build(kind, cls, dims):
+    torch.manual_seed(0)
+    if kind == "attention_scn":
+        return cls(dims["A"], dims["M"], dims["D"], dims["F"], dims["S"], dims["V"],
+                   encoder_dim=dims["E"], dropout=0.5)
+    if kind == "pure_scn":
+        return cls(dims["M"], dims["D"], dims["F"], dims["S"], dims["V"],
+                   encoder_dim=dims["E"], dropout=0.5)
+    return cls(dims["A"], dims["M"], dims["D"], dims["V"], encoder_dim=dims["E"], dropout=0.5)
+
+
+def make_inputs(dims, B, lengths, seed):
+    g = torch.Generator().manual_seed(seed)
+    V = dims["V"]
+    enc = torch.randn(B, dims["side"], dims["side"], dims["E"], generator=g).relu_()
+    tags = torch.rand(B, dims["S"], generator=g)
+    L = dims["L"]
+    caps = torch.zeros(B, L, dtype=torch.long)
+    for b, n in enumerate(lengths):
+        caps[b, 0] = V - 2
+        if n > 2:
+            caps[b, 1:n - 1] = torch.randint(1, V - 3, (n - 2,), generator=g)
+        caps[b, n - 1] = V - 1
+    caplens = torch.tensor(lengths).unsqueeze(1)
+    return enc, tags, caps, caplens
+
+
+def train_case(mods, kind, name, dims, B, lengths, seed, scale=None):
+    cls = mods[kind][0]
+    dec = build(kind, cls, dims).eval()      # eval: dropout off (mask RNG cannot be matched)
+    if scale:
+        with torch.no_grad():
+            for n, p in dec.named_parameters():
+                for key, f in scale.items():
+                    if n.startswith(key):
+                        p.mul_(f)
+    enc, tags, caps, caplens = make_inputs(dims, B, lengths, seed)
+    if kind == "pure_attention":
+        out = dec(enc, caps, caplens)
+    else:
+        out = dec(enc, tags, caps, caplens)
+    if kind == "pure_scn":
+        scores, caps_sorted, dl, sort_ind = out
+        alphas = None
+    else:
+        scores, caps_sorted, dl, alphas, sort_ind = out
+    loss = loss_glue(scores, caps_sorted, dl, alphas)
+    dec.zero_grad()
+    loss.backward()
+    blob = {
+        "kind": kind, "dims": dims,
+        "state_dict": {k: v.detach().clone() for k, v in dec.state_dict().items()},
+        "encoder_out": enc, "tags": tags, "captions": caps, "caption_lengths": caplens,
+        "predictions": scores.detach(), "caps_sorted": caps_sorted, "decode_lengths": dl,
+        "alphas": None if alphas is None else alphas.detach(), "sort_ind": sort_ind,
+        "loss": loss.detach(),
+        "grads": {n: p.grad.detach().clone() for n, p in dec.named_parameters()},
+    }
+    torch.save(blob, os.path.join(HERE, name + ".pt"))
+    print("wrote", name, "loss=%.6f" % loss.item(), "T=%d" % max(dl))
+
+
+def beam_case(mods, kind, name, dims, n_images, beams, seed, scale):
+    cls = mods[kind][1]                      # `//`-restated class
+    dec = build(kind, cls, dims).eval()
+    with torch.no_grad():
+        for n, p in dec.named_parameters():
+            for key, f in scale.items():
+                if n.startswith(key):
+                    p.mul_(f)
+    V = dims["V"]
+    word_map = {"w%d" % i: i for i in range(1, V - 3)}
+    word_map.update({"<pad>": 0, "<unk>": V - 3, "<start>": V - 2, "<end>": V - 1})
+    assert len(word_map) == V
+    g = torch.Generator().manual_seed(seed)
+    images = []
+    for i in range(n_images):
+        enc = torch.randn(1, dims["side"], dims["side"], dims["E"], generator=g).relu_()
+        tags = torch.rand(1, dims["S"], generator=g)
+        per_beam = {}
+        for k in beams:
+            try:
+                with torch.no_grad():
+                    if kind == "pure_attention":
+                        res = dec.sample(k, word_map, enc)
+                    else:
+                        res = dec.sample(k, word_map, enc, tags)
+                if kind == "pure_scn":
+                    seq, al = res, None
+                else:
+                    seq, al = res
+                per_beam[k] = {"completed": True, "seq": seq,
+                               "alphas": None if al is None else torch.tensor(al)}
+            except ValueError as e:          # no beam ever emitted <end> (App. C-4)
+                per_beam[k] = {"completed": False, "error": str(e)}
+        images.append({"encoder_out": enc, "tags": tags, "results": per_beam})
+    lens = [len(r["seq"]) for im in images for r in im["results"].values() if r["completed"]]
+    blob = {"kind": kind, "dims": dims, "start_id": V - 2, "end_id": V - 1,
+            "state_dict": {k: v.detach().clone() for k, v in dec.state_dict().items()},
+            "images": images}
+    torch.save(blob, os.path.join(HERE, name + ".pt"))
+    n_fail = sum(1 for im in images for r in im["results"].values() if not r["completed"])
+    print("wrote", name, "completed lengths", sorted(lens), "no-completion", n_fail)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    args = ap.parse_args()
+    torch.set_num_threads(1)                 # deterministic reductions for bit-level replay
+    mods = load_reference(args.ref)
+    small = dict(A=24, M=16, D=32, F=24, S=12, V=37, E=40, side=3, L=14)
+    lengths = [9, 3, 14, 6, 11, 4]
+    for kind in ("attention_scn", "pure_scn", "pure_attention"):
+        train_case(mods, kind, "train_%s_small" % kind, small, 6, lengths, seed=11)
+    # medium: real pixel count (14x14), dims in multiples of 8, ties in the lengths
+    med = dict(A=64, M=48, D=64, F=56, S=100, V=203, E=128, side=14, L=20)
+    lengths_m = [20, 7, 13, 5, 18, 9, 3, 16]
+    for kind in ("attention_scn", "pure_scn", "pure_attention"):
+        train_case(mods, kind, "train_%s_medium" % kind, med, 8, lengths_m, seed=12)
+    # hot weights so the gradients / gates are far from the linear regime
+    train_case(mods, "attention_scn", "train_attention_scn_hot", small, 6, lengths, seed=13,
+               scale={"decode_step.": 4.0, "fc.weight": 10.0, "embedding.weight": 5.0})
+    # beam search: "hot weights" recipe of SURVEY.md §8c so beams really finish at varied lengths
+    bdims = dict(A=32, M=32, D=64, F=64, S=100, V=64, E=256, side=4, L=52)
+    hot = {"decode_step.": 8.0, "fc.weight": 30.0, "embedding.weight": 10.0}
+    for kind in ("attention_scn", "pure_scn", "pure_attention"):
+        beam_case(mods, kind, "beam_%s" % kind, bdims, 6, (1, 3, 5), seed=21, scale=hot)
+
+
+if __name__ == "__main__":
+    main()
