@@ -1,0 +1,104 @@
+"""Shared host logic of the three drop-in decoder modules (models/decoders/*.py).
+
+Mirrors the reference call contract (attention_scn.py:95-158 forward, :160-296 sample):
+sorting by caption length, the returned tuple, the un-permuted tag quirk (App. C-1, handled
+inside capdec_forward_train by passing tags as given) -- while the tensor math is ONE C call
+per forward and one per backward.
+"""
+import torch
+from torch import nn
+
+from . import functional as CF
+from .config import get_precision
+
+
+class CaptionDecoderBase(nn.Module):
+    kind = None          # "attention_scn" | "pure_scn" | "pure_attention"
+
+    # ------------------------------------------------------------------ helpers
+    def _param_list(self):
+        sd = dict(self.named_parameters())
+        return [sd[n] for n in CF.param_names(self.kind)]
+
+    def _dims_kw(self):
+        return {"A": getattr(self, "attention_dim", 0), "M": self.embed_dim, "D": self.decoder_dim,
+                "F": getattr(self, "factored_dim", 0), "S": getattr(self, "semantic_dim", 0),
+                "V": self.vocab_size}
+
+    def init_weights(self):
+        r"""Uniform init of embedding / fc as the reference (attention_scn.py:58-63)."""
+        self.embedding.weight.data.uniform_(-0.1, 0.1)
+        self.fc.bias.data.fill_(0)
+        self.fc.weight.data.uniform_(-0.1, 0.1)
+
+    def load_pretrained_embeddings(self, embeddings):
+        self.embedding.weight = nn.Parameter(embeddings)
+
+    def fine_tune_embeddings(self, fine_tune=True):
+        for p in self.embedding.parameters():
+            p.requires_grad = fine_tune
+
+    def init_hidden_state(self, encoder_out):
+        r"""h0, c0 from the mean encoder feature (attention_scn.py:82-93), on the GEMM engine."""
+        prec = get_precision()
+        ft = torch.bfloat16 if prec == "bf16" else torch.float32
+        m = encoder_out.detach().float().mean(dim=1).to(ft).contiguous()
+        h = CF.gemm(m, self.init_h.weight.detach().to(ft).contiguous(), bias=self.init_h.bias.detach())
+        c = CF.gemm(m, self.init_c.weight.detach().to(ft).contiguous(), bias=self.init_c.bias.detach())
+        return h, c
+
+    # ------------------------------------------------------------------ teacher-forced forward
+    def _forward_impl(self, encoder_out, semantic_input, encoded_captions, caption_lengths):
+        batch_size = encoder_out.size(0)
+        encoder_dim = encoder_out.size(-1)
+        enc = encoder_out.view(batch_size, -1, encoder_dim)        # strided views are fine (App. C-22)
+        if enc.dtype != torch.float32:
+            enc = enc.float()
+        lens, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True)   # same op as :117-118
+        caps_sorted = encoded_captions[sort_ind].contiguous()
+        decode_lengths = (lens - 1).tolist()                       # host sync, as upstream (:131)
+        tags = None
+        if self.kind != "pure_attention":
+            tags = semantic_input.detach().float().contiguous()    # NOT permuted (App. C-1)
+        p = self.dropout.p if self.training else 0.0
+        seed = int(torch.empty((), dtype=torch.int64).random_().item()) if p > 0 else 0
+        out, meta = CF.decoder_forward(self.kind, self._param_list(), enc.detach(), tags, caps_sorted,
+                                       sort_ind, decode_lengths, dims_kw=self._dims_kw(), dropout_p=p,
+                                       seed=seed)
+        if self.kind == "pure_scn":
+            predictions, alphas = out, None
+        else:
+            predictions, alphas = out
+        predictions._capdec_meta = meta
+        if alphas is None:
+            return predictions, caps_sorted, decode_lengths, sort_ind
+        return predictions, caps_sorted, decode_lengths, alphas, sort_ind
+
+    def loss(self, scores, caps_sorted, decode_lengths, alphas=None, alpha_c=1.0, n_tokens=None):
+        r"""Fused loss glue of trains/attention_scn.py:219-235; returns (loss, [total, ce, reg])."""
+        return CF.caption_loss(scores, caps_sorted, decode_lengths, alphas, alpha_c,
+                               meta=getattr(scores, "_capdec_meta", None), n_tokens=n_tokens)
+
+    # ------------------------------------------------------------------ beam search
+    def sample_batch(self, beam_size, start_id, end_id, encoder_out, tag_out=None, max_steps=50,
+                     want_alphas=True, want_trace=False):
+        r"""Independent beam searches for G images in one device-side loop (no per-step host sync)."""
+        from . import beam
+        return beam.beam_search_batch(self, beam_size, start_id, end_id, encoder_out, tag_out,
+                                      max_steps=max_steps, want_alphas=want_alphas,
+                                      want_trace=want_trace)
+
+    def _sample_one(self, beam_size, word_map, encoder_out, tag_out):
+        if len(word_map) != self.vocab_size:
+            raise ValueError("len(word_map)=%d != vocab_size=%d" % (len(word_map), self.vocab_size))
+        res = self.sample_batch(beam_size, word_map['<start>'], word_map['<end>'], encoder_out, tag_out,
+                                want_alphas=self.kind != "pure_scn")
+        n = int(res["len"][0])
+        seq = res["seq"][0, :n].tolist()
+        self.last_sample_completed = bool(res["completed"][0])
+        self.last_sample_score = float(res["score"][0])
+        if self.kind == "pure_scn":
+            return seq
+        side = encoder_out.size(1)
+        alphas = res["alpha"][0, :n].view(n, side, side).tolist()
+        return seq, alphas

@@ -1,0 +1,582 @@
+// decoder.cu -- host orchestration of the teacher-forced decoder forward and the
+// reverse-time backward (one call = one mini-batch; every launch goes to the caller's
+// stream; no allocation, no synchronisation).
+//
+// Reference: models/decoders/attention_scn.py:95-158 (AttentionSCN.forward),
+// pure_scn.py:87-140, pure_attention.py:90-151, models/scn_cell.py:52-154,
+// models/attention.py:26-44; backward = SURVEY.md App. A.2.
+//
+// Structure of one decode step (attention_scn), each line one kernel:
+//   G1   [att2 | beta_pre | p] = h_{t-1} . [W_d ; W_beta ; W_ha^T]^T + [b_d ; b_beta ; 0]
+//   ATT  alpha, awe, z = sigmoid(beta_pre) * awe                       (attention.cu)
+//   P3   u = U_emb[t] + z . W_ia[M:]            (U_emb = Emb[caps] . W_ia[:M], batched over t)
+//   FM   m_g = [u_g * v_g | p_g * q_g]          (v = s W_ib, q = s W_hb: hoisted, App. C-7)
+//   P4   pre_g = m_g . [W_ic_g | W_hc_g]^T      (4 gates = 4 GEMM batches)
+//   CELL i,f,o,g~ -> c_t, h_t (+ dropout copy for fc)
+// The time-invariant products (att1, v, q, U_emb, h0/c0) and the vocabulary projection
+// over all (b,t) rows are batched GEMMs outside the loop.
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace capdec {
+
+namespace {
+
+inline int64_t pad8(int64_t x) { return round_up(x, 8); }
+
+struct Plan {
+  CapdecDims d;
+  bool att, scn, bwd;
+  int X, NQ, NG1, fsz;             // fsz = sizeof(feature type)
+  int64_t ldE, ldD, ldX, ldS, ld2F, ldV, ldNQ, ldEA, ldM, ldR, ldB, ldBP, ldA;
+  // byte offsets into the workspace
+  struct Off {
+    // packed weights (feature type) + fp32 bias vectors
+    size_t Wp_e, Wp_cat1, b_cat1, Wp_xq, Wp_ibT, Wp_hbT, Wp_c, Wp_init, Wp_fc;
+    size_t Wp_fcT, Wp_cT, Wp_hq, Wp_xin, Wp_b6;
+    // forward activations
+    size_t enc_s, att1, mean, meanF, tagsF, v, q, Xe, U, g1, awe, z, m, pre, gates, C, H0, Hall,
+        Hd, lenD;
+    // backward buffers
+    size_t dlogF, dHfc, dh_rec, dc, dpre, wr, du, dp, dv_acc, dq_acc, dz, dba, dAtt1, dwf, dbf, dXe;
+    size_t tA, tB, tC;             // transposed-operand scratch
+    size_t total;
+  } o;
+};
+
+int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
+  CAPDEC_REQUIRE(d.kind >= 0 && d.kind <= 2 && (d.precision == 0 || d.precision == 1),
+                 CAPDEC_ERR_BAD_ARG, "bad kind/precision");
+  CAPDEC_REQUIRE(d.B > 0 && d.T > 0 && d.V > 1 && d.L > d.T && d.M > 0 && d.D > 0 && d.E > 0,
+                 CAPDEC_ERR_BAD_SHAPE, "bad dims B=%d T=%d V=%d L=%d", d.B, d.T, d.V, d.L);
+  p->d = d;
+  p->att = d.kind != CAPDEC_PURE_SCN;
+  p->scn = d.kind != CAPDEC_PURE_ATTENTION;
+  p->bwd = with_bwd;
+  CAPDEC_REQUIRE(d.D % 8 == 0 && d.M % 8 == 0 && d.E % 8 == 0, CAPDEC_ERR_BAD_SHAPE,
+                 "decoder_dim, embed_dim, encoder_dim must be multiples of 8 (D=%d M=%d E=%d)", d.D,
+                 d.M, d.E);
+  if (p->scn)
+    CAPDEC_REQUIRE(d.F > 0 && d.F % 8 == 0 && d.S > 0, CAPDEC_ERR_BAD_SHAPE,
+                   "factored_dim must be a multiple of 8 (F=%d S=%d)", d.F, d.S);
+  if (p->att)
+    CAPDEC_REQUIRE(d.A > 0 && d.A % 8 == 0 && d.P > 0, CAPDEC_ERR_BAD_SHAPE,
+                   "attention_dim must be a multiple of 8 (A=%d P=%d)", d.A, d.P);
+  p->X = p->att ? d.M + d.E : d.M;
+  p->NQ = p->scn ? 4 * d.F : 4 * d.D;
+  p->NG1 = (p->att ? d.A + d.E : 0) + p->NQ;
+  p->fsz = d.precision == CAPDEC_BF16 ? 2 : 4;
+  p->ldE = pad8(d.E); p->ldD = pad8(d.D); p->ldX = pad8(p->X); p->ldS = pad8(d.S);
+  p->ld2F = pad8(2 * d.F); p->ldV = pad8(d.V); p->ldNQ = pad8(p->NQ); p->ldEA = pad8(d.E + d.A);
+  p->ldM = pad8(d.M); p->ldR = pad8((int64_t)d.B * d.T); p->ldB = pad8(d.B);
+  p->ldBP = pad8((int64_t)d.B * d.P); p->ldA = pad8(d.A);
+
+  const size_t f = p->fsz;
+  const int64_t B = d.B, T = d.T, P = d.P, E = d.E, A = d.A, M = d.M, D = d.D, F = d.F, S = d.S,
+                V = d.V, X = p->X, NQ = p->NQ, NG1 = p->NG1, R = B * T;
+  size_t cur = 0;
+  auto take = [&](size_t bytes) { size_t at = cur; cur += (size_t)round_up((int64_t)bytes, 256); return at; };
+  Plan::Off& o = p->o;
+  memset(&o, 0, sizeof o);
+  // ---- packed weights ----
+  if (p->att) o.Wp_e = take(A * p->ldE * f);
+  o.Wp_cat1 = take(NG1 * p->ldD * f);
+  o.b_cat1 = take(NG1 * 4);
+  o.Wp_xq = take(NQ * p->ldX * f);                  // SCN: W_ia^T [4F][X] ; LSTM: W_ih [4D][X]
+  if (p->scn) {
+    o.Wp_ibT = take(NQ * p->ldS * f);
+    o.Wp_hbT = take(NQ * p->ldS * f);
+    o.Wp_c = take(4 * D * p->ld2F * f);
+  }
+  o.Wp_init = take(2 * D * p->ldE * f);
+  o.Wp_fc = take(V * p->ldD * f);
+  if (with_bwd) {
+    o.Wp_fcT = take(D * p->ldV * f);
+    if (p->scn) o.Wp_cT = take(4 * 2 * F * p->ldD * f);
+    o.Wp_hq = take(D * p->ldNQ * f);                // SCN: W_ha [D][4F] ; LSTM: W_hh^T [D][4D]
+    o.Wp_xin = take(X * p->ldNQ * f);               // SCN: W_ia [X][4F] ; LSTM: W_ih^T [X][4D]
+    if (p->att) o.Wp_b6 = take(D * p->ldEA * f);
+  }
+  // ---- forward activations ----
+  o.enc_s = take(B * P * E * f);
+  if (p->att) o.att1 = take(B * P * A * f);
+  o.mean = take(B * E * 4);
+  o.meanF = take(B * p->ldE * f);
+  if (p->scn) {
+    o.tagsF = take(B * p->ldS * f);
+    o.v = take(B * NQ * 4);
+    o.q = take(B * NQ * 4);
+  }
+  o.Xe = take(R * p->ldM * f);
+  o.U = take(R * NQ * 4);
+  o.g1 = take(R * NG1 * 4);
+  if (p->att) {
+    o.awe = take(R * E * 4);
+    o.z = take(R * E * f);
+  }
+  if (p->scn) {
+    o.m = take(T * 4 * B * 2 * F * f);
+    o.pre = take(B * 4 * D * 4);
+  }
+  o.gates = take(R * 4 * D * 4);
+  o.C = take((T + 1) * B * D * 4);
+  o.H0 = take(B * p->ldD * f);
+  o.Hall = take(R * D * f);
+  o.Hd = take(R * D * f);
+  o.lenD = take(B * 4);
+  if (with_bwd) {
+    o.dlogF = take(R * p->ldV * f);
+    o.dHfc = take(R * D * 4);
+    o.dh_rec = take(B * D * 4);
+    o.dc = take(B * D * 4);
+    o.dpre = take(R * 4 * D * f);
+    if (p->scn) {
+      o.wr = take(4 * B * 2 * F * 4);
+      o.du = take(R * NQ * f);
+      o.dp = take(R * NQ * f);
+      o.dv_acc = take(B * NQ * 4);
+      o.dq_acc = take(B * NQ * 4);
+    }
+    if (p->att) {
+      o.dz = take(B * E * 4);
+      o.dba = take(R * p->ldEA * f);
+      o.dAtt1 = take(B * P * A * 4);
+      o.dwf = take(R * A * 4);
+      o.dbf = take(R * 4);
+    }
+    o.dXe = take(R * M * 4);
+    // transposed operands for the weight-gradient GEMMs (K = rows).  tA/tB are sized for
+    // the largest pair used together, tC for the shared H_prev^T.
+    int64_t widest = V;
+    if (NQ > widest) widest = NQ;
+    if (4 * D > widest) widest = 4 * D;
+    if (E + A > widest) widest = E + A;
+    if (X > widest) widest = X;
+    int64_t kmax = p->ldR;
+    size_t tA = (size_t)widest * kmax * f;
+    size_t tB = (size_t)(NQ > 4 * D ? NQ : 4 * D) * kmax * f;
+    auto grow = [](size_t& x, size_t v) { if (v > x) x = v; };
+    grow(tB, (size_t)M * kmax * f);
+    grow(tB, (size_t)E * kmax * f);
+    grow(tB, (size_t)D * kmax * f);
+    if (p->scn) grow(tB, (size_t)(8 * F) * kmax * f);
+    grow(tA, (size_t)S * p->ldB * f);
+    grow(tA, (size_t)D * p->ldB * f);
+    grow(tB, (size_t)NQ * p->ldB * f);
+    grow(tB, (size_t)E * p->ldB * f);
+    if (p->att) {
+      grow(tA, (size_t)A * p->ldBP * f);
+      grow(tB, (size_t)E * p->ldBP * f);
+    }
+    o.tA = take(tA);
+    o.tB = take(tB);
+    o.tC = take((size_t)D * kmax * f);
+  }
+  o.total = cur;
+  return CAPDEC_OK;
+}
+
+struct Ctx {
+  Plan p;
+  uint8_t* ws;
+  cudaStream_t st;
+  int prec;
+  template <typename T = void> T* at(size_t off) const { return (T*)(ws + off); }
+  // element offset inside a feature-type buffer
+  void* ft(size_t off, int64_t elem) const { return ws + off + (size_t)elem * p.fsz; }
+};
+
+int G(const Ctx& c, const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo,
+      int out_ft, const float* bias, const float* addm, int64_t ldadd, int rows, int N, int K,
+      int rows_alloc = 0, int batch = 1, int64_t sX = 0, int64_t sW = 0, int64_t sO = 0) {
+  GemmArgs a;
+  a.X = X; a.ldx = ldx; a.W = W; a.ldw = ldw; a.out = out; a.ldo = ldo; a.out_ft = out_ft;
+  a.bias = bias; a.addm = addm; a.ldadd = ldadd; a.rows = rows; a.N = N; a.K = K;
+  a.rows_alloc = rows_alloc; a.batch = batch; a.sX = sX; a.sW = sW; a.sO = sO;
+  return gemm(c.prec, a, c.st);
+}
+
+// fp32 master weights -> packed feature-type operands ([N_out][K] , K contiguous)
+int pack_weights(const Ctx& c, const CapdecParams& w) {
+  const Plan& p = c.p;
+  const CapdecDims& d = p.d;
+  const int pr = c.prec;
+  cudaStream_t st = c.st;
+  const int D = d.D, E = d.E, A = d.A, M = d.M, F = d.F, S = d.S, V = d.V, X = p.X, NQ = p.NQ;
+  int row = 0;     // row cursor inside Wp_cat1
+  if (p.att) {
+    CAPDEC_TRY(copy_cast(pr, w.enc_att_w, 0, E, c.at(p.o.Wp_e), 1, p.ldE, A, E, st));
+    CAPDEC_TRY(copy_cast(pr, w.dec_att_w, 0, D, c.ft(p.o.Wp_cat1, 0), 1, p.ldD, A, D, st));
+    CAPDEC_TRY(copy_cast(pr, w.f_beta_w, 0, D, c.ft(p.o.Wp_cat1, (int64_t)A * p.ldD), 1, p.ldD, E, D, st));
+    row = A + E;
+    CAPDEC_TRY(concat_bias(c.at<float>(p.o.b_cat1), w.dec_att_b, A, w.f_beta_b, E, NQ, st));
+  } else {
+    CAPDEC_TRY(concat_bias(c.at<float>(p.o.b_cat1), nullptr, 0, nullptr, 0, NQ, st));
+  }
+  if (p.scn) {
+    // W_ha (D,4F) -> rows [row, row+4F) of cat1 as W_ha^T
+    CAPDEC_TRY(transpose_cast(pr, w.w_ha, 0, c.ft(p.o.Wp_cat1, (int64_t)row * p.ldD), 1, 1, D, NQ, 0, NQ,
+                              p.ldD, 0, 1, st));
+    CAPDEC_TRY(transpose_cast(pr, w.w_ia, 0, c.at(p.o.Wp_xq), 1, 1, X, NQ, 0, NQ, p.ldX, 0, 1, st));
+    CAPDEC_TRY(transpose_cast(pr, w.w_ib, 0, c.at(p.o.Wp_ibT), 1, 1, S, NQ, 0, NQ, p.ldS, 0, 1, st));
+    CAPDEC_TRY(transpose_cast(pr, w.w_hb, 0, c.at(p.o.Wp_hbT), 1, 1, S, NQ, 0, NQ, p.ldS, 0, 1, st));
+    for (int g = 0; g < 4; ++g) {
+      // Wp_c[g] = [ W_ic[:, gF:(g+1)F] | W_hc[:, gF:(g+1)F] ]   (D x 2F)
+      CAPDEC_TRY(copy_cast(pr, w.w_ic + g * F, 0, NQ, c.ft(p.o.Wp_c, (int64_t)g * D * p.ld2F), 1,
+                           p.ld2F, D, F, st));
+      CAPDEC_TRY(copy_cast(pr, w.w_hc + g * F, 0, NQ, c.ft(p.o.Wp_c, (int64_t)g * D * p.ld2F + F), 1,
+                           p.ld2F, D, F, st));
+    }
+  } else {
+    // LSTM: weight_hh (4D,D) and weight_ih (4D,X) are already [N_out][K]
+    CAPDEC_TRY(copy_cast(pr, w.w_ha, 0, D, c.ft(p.o.Wp_cat1, (int64_t)row * p.ldD), 1, p.ldD, NQ, D, st));
+    CAPDEC_TRY(copy_cast(pr, w.w_ia, 0, X, c.at(p.o.Wp_xq), 1, p.ldX, NQ, X, st));
+  }
+  CAPDEC_TRY(copy_cast(pr, w.init_h_w, 0, E, c.ft(p.o.Wp_init, 0), 1, p.ldE, D, E, st));
+  CAPDEC_TRY(copy_cast(pr, w.init_c_w, 0, E, c.ft(p.o.Wp_init, (int64_t)D * p.ldE), 1, p.ldE, D, E, st));
+  CAPDEC_TRY(copy_cast(pr, w.fc_w, 0, D, c.at(p.o.Wp_fc), 1, p.ldD, V, D, st));
+  if (p.bwd) {
+    CAPDEC_TRY(transpose_cast(pr, w.fc_w, 0, c.at(p.o.Wp_fcT), 1, 1, V, D, 0, D, p.ldV, 0, 1, st));
+    if (p.scn) {
+      for (int g = 0; g < 4; ++g) {
+        // Wp_cT[g] = [ W_ic_g^T ; W_hc_g^T ]  (2F x D)
+        CAPDEC_TRY(transpose_cast(pr, w.w_ic + g * F, 0, c.ft(p.o.Wp_cT, (int64_t)g * 2 * F * p.ldD), 1,
+                                  1, D, F, 0, NQ, p.ldD, 0, 1, st));
+        CAPDEC_TRY(transpose_cast(pr, w.w_hc + g * F, 0,
+                                  c.ft(p.o.Wp_cT, ((int64_t)g * 2 * F + F) * p.ldD), 1, 1, D, F, 0, NQ,
+                                  p.ldD, 0, 1, st));
+      }
+      CAPDEC_TRY(copy_cast(pr, w.w_ha, 0, NQ, c.at(p.o.Wp_hq), 1, p.ldNQ, D, NQ, st));
+      CAPDEC_TRY(copy_cast(pr, w.w_ia, 0, NQ, c.at(p.o.Wp_xin), 1, p.ldNQ, X, NQ, st));
+    } else {
+      CAPDEC_TRY(transpose_cast(pr, w.w_ha, 0, c.at(p.o.Wp_hq), 1, 1, NQ, D, 0, D, p.ldNQ, 0, 1, st));
+      CAPDEC_TRY(transpose_cast(pr, w.w_ia, 0, c.at(p.o.Wp_xin), 1, 1, NQ, X, 0, X, p.ldNQ, 0, 1, st));
+    }
+    if (p.att) {
+      // Wp_b6 = [ W_beta^T | W_d^T ]   (D x (E+A))
+      CAPDEC_TRY(transpose_cast(pr, w.f_beta_w, 0, c.ft(p.o.Wp_b6, 0), 1, 1, E, D, 0, D, p.ldEA, 0, 1, st));
+      CAPDEC_TRY(transpose_cast(pr, w.dec_att_w, 0, c.ft(p.o.Wp_b6, E), 1, 1, A, D, 0, D, p.ldEA, 0, 1, st));
+    }
+  }
+  return CAPDEC_OK;
+}
+
+}  // namespace
+
+size_t workspace_bytes(const CapdecDims& d, int with_bwd) {
+  Plan p;
+  if (make_plan(d, with_bwd != 0, &p) != CAPDEC_OK) return 0;
+  return p.o.total;
+}
+
+int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, int64_t sb, int64_t sp,
+                  int64_t se, const int64_t* sort_ind, const float* tags, const int64_t* caps,
+                  const int32_t* len_h, float dropout_p, uint64_t seed, int save_bwd,
+                  float* predictions, float* alphas, void* workspace, size_t ws_bytes,
+                  cudaStream_t st) {
+  Ctx c;
+  CAPDEC_TRY(make_plan(d, save_bwd != 0, &c.p));
+  CAPDEC_REQUIRE(ws_bytes >= c.p.o.total, CAPDEC_ERR_WORKSPACE, "workspace %zu < %zu", ws_bytes,
+                 c.p.o.total);
+  CAPDEC_REQUIRE(((uintptr_t)workspace % 256) == 0, CAPDEC_ERR_BAD_ARG, "workspace must be 256-B aligned");
+  CAPDEC_REQUIRE(len_h[0] == d.T, CAPDEC_ERR_BAD_SHAPE, "decode_len[0]=%d != T=%d", len_h[0], d.T);
+  for (int b = 1; b < d.B; ++b)
+    CAPDEC_REQUIRE(len_h[b] <= len_h[b - 1] && len_h[b] >= 1, CAPDEC_ERR_BAD_SHAPE,
+                   "decode lengths must be sorted descending and >= 1");
+  c.ws = (uint8_t*)workspace;
+  c.st = st;
+  c.prec = d.precision;
+  const Plan& p = c.p;
+  const Plan::Off& o = p.o;
+  const int pr = c.prec;
+  const int B = d.B, T = d.T, P = d.P, E = d.E, A = d.A, M = d.M, D = d.D, F = d.F, S = d.S, V = d.V,
+            NQ = p.NQ, NG1 = p.NG1;
+  const int64_t R = (int64_t)B * T;
+  const bool ragged = len_h[B - 1] != T;
+
+  std::vector<int> bt(T);
+  for (int t = 0; t < T; ++t) {
+    int n = 0;
+    while (n < B && len_h[n] > t) ++n;
+    bt[t] = n;
+  }
+  CAPDEC_CUDA_OK(cudaMemcpyAsync(c.at(o.lenD), len_h, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+
+  CAPDEC_TRY(pack_weights(c, w));
+
+  // ---------------- prologue: time-invariant products ----------------
+  CAPDEC_TRY(gather_features(pr, enc, sb, sp, se, sort_ind, c.at(o.enc_s), c.at<float>(o.mean),
+                             c.at(o.meanF), p.ldE, B, P, E, st));
+  if (p.att)   // att1 = enc . W_e^T + b_e      (attention.py:35, hoisted)
+    CAPDEC_TRY(G(c, c.at(o.enc_s), E, c.at(o.Wp_e), p.ldE, c.at(o.att1), A, 1, w.enc_att_b, nullptr, 0,
+                 B * P, A, E));
+  // h0 -> H0 (feature type), c0 -> C[0] (fp32)   (attention_scn.py:90-92)
+  CAPDEC_TRY(G(c, c.at(o.meanF), p.ldE, c.ft(o.Wp_init, 0), p.ldE, c.at(o.H0), p.ldD, 1, w.init_h_b,
+               nullptr, 0, B, D, E));
+  CAPDEC_TRY(G(c, c.at(o.meanF), p.ldE, c.ft(o.Wp_init, (int64_t)D * p.ldE), p.ldE, c.at(o.C), D, 0,
+               w.init_c_b, nullptr, 0, B, D, E));
+  if (p.scn) {   // v = s W_ib, q = s W_hb   (scn_cell.py:78-81, 134-143; tags NOT permuted, App. C-1)
+    CAPDEC_TRY(copy_cast(pr, tags, 0, S, c.at(o.tagsF), 1, p.ldS, B, S, st));
+    CAPDEC_TRY(G(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_ibT), p.ldS, c.at(o.v), NQ, 0, nullptr, nullptr, 0, B,
+                 NQ, S));
+    CAPDEC_TRY(G(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_hbT), p.ldS, c.at(o.q), NQ, 0, nullptr, nullptr, 0, B,
+                 NQ, S));
+  }
+  // embeddings of the teacher tokens and their input-side projection, all (t,b) rows at once
+  CAPDEC_TRY(embedding_gather(pr, w.emb, caps, d.L, c.at(o.Xe), p.ldM, B, T, M, V, st));
+  CAPDEC_TRY(G(c, c.at(o.Xe), p.ldM, c.at(o.Wp_xq), p.ldX, c.at(o.U), NQ, 0, nullptr, nullptr, 0, (int)R,
+               NQ, M));
+  if (alphas) CAPDEC_CUDA_OK(cudaMemsetAsync(alphas, 0, (size_t)R * P * 4, st));
+  if (ragged) {
+    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.Hall), 0, (size_t)R * D * p.fsz, st));
+    if (dropout_p > 0.f) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.Hd), 0, (size_t)R * D * p.fsz, st));
+  }
+
+  const bool drop = dropout_p > 0.f;
+  // ---------------- the recurrence ----------------
+  for (int t = 0; t < T; ++t) {
+    const int n = bt[t];
+    const void* hprev = t == 0 ? c.at(o.H0) : c.ft(o.Hall, (int64_t)(t - 1) * D);
+    const int64_t ldh = t == 0 ? p.ldD : (int64_t)T * D;
+    float* g1 = c.at<float>(o.g1) + (int64_t)t * B * NG1;
+    float* U = c.at<float>(o.U) + (int64_t)t * B * NQ;
+    CAPDEC_TRY(G(c, hprev, ldh, c.at(o.Wp_cat1), p.ldD, g1, NG1, 0, c.at<float>(o.b_cat1), nullptr, 0, n,
+                 NG1, D, B));
+    const float* pcol = g1 + (p.att ? A + E : 0);
+    if (p.att) {
+      void* z = c.ft(o.z, (int64_t)t * B * E);
+      float* awe = save_bwd ? c.at<float>(o.awe) + (int64_t)t * B * E : nullptr;
+      CAPDEC_TRY(attention_fwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w, w.full_att_b,
+                               alphas + (int64_t)t * P, (int64_t)T * P, z, E, awe, n, 1, P, E, A, st));
+      // u (in place over U_emb[t]) += z . W_x[:, M:]^T
+      CAPDEC_TRY(G(c, z, E, c.ft(o.Wp_xq, M), p.ldX, U, NQ, 0, nullptr, U, NQ, n, NQ, E, B));
+    }
+    const float* c_prev = c.at<float>(o.C) + (int64_t)t * B * D;
+    float* c_new = c.at<float>(o.C) + (int64_t)(t + 1) * B * D;
+    float* gates = c.at<float>(o.gates) + (int64_t)t * B * 4 * D;
+    void* hout = c.ft(o.Hall, (int64_t)t * D);
+    void* hdout = drop ? c.ft(o.Hd, (int64_t)t * D) : nullptr;
+    if (p.scn) {
+      void* m = c.ft(o.m, (int64_t)t * 4 * B * 2 * F);
+      CAPDEC_TRY(scn_form_m(pr, U, NQ, pcol, NG1, c.at<float>(o.v), c.at<float>(o.q), m, n, B, F, st));
+      CAPDEC_TRY(G(c, m, 2 * F, c.at(o.Wp_c), p.ld2F, c.at(o.pre), 4 * D, 0, nullptr, nullptr, 0, n, D,
+                   2 * F, B, 4, (int64_t)B * 2 * F, (int64_t)D * p.ld2F, D));
+      CAPDEC_TRY(cell_fwd(pr, c.at<float>(o.pre), 4 * D, nullptr, 0, w.b_ih, w.b_hh, 0, c_prev, c_new,
+                          gates, hout, (int64_t)T * D, hdout, dropout_p, seed, t, T, n, D, st));
+    } else {
+      CAPDEC_TRY(cell_fwd(pr, U, NQ, pcol, NG1, w.b_ih, w.b_hh, 1, c_prev, c_new, gates, hout,
+                          (int64_t)T * D, hdout, dropout_p, seed, t, T, n, D, st));
+    }
+  }
+  // ---------------- vocabulary projection over all (b,t) rows ----------------
+  CAPDEC_TRY(G(c, drop ? c.at(o.Hd) : c.at(o.Hall), D, c.at(o.Wp_fc), p.ldD, predictions, V, 0, w.fc_b,
+               nullptr, 0, (int)R, V, D));
+  if (ragged)
+    CAPDEC_TRY(zero_rows_beyond_len(predictions, c.at<int32_t>(o.lenD), B, T, V, st));
+  return CAPDEC_OK;
+}
+
+int backward(const CapdecDims& d, const CapdecParams& w, const float* tags, const int64_t* caps,
+             const int32_t* len_h, float dropout_p, uint64_t seed, const float* d_pred,
+             const void* d_logits_ft, const float* d_alphas, const float* alphas,
+             const CapdecParams& g, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  Ctx c;
+  CAPDEC_TRY(make_plan(d, true, &c.p));
+  CAPDEC_REQUIRE(ws_bytes >= c.p.o.total, CAPDEC_ERR_WORKSPACE, "workspace %zu < %zu", ws_bytes,
+                 c.p.o.total);
+  CAPDEC_REQUIRE(d_pred || d_logits_ft, CAPDEC_ERR_BAD_ARG, "backward: no logits gradient");
+  c.ws = (uint8_t*)workspace;
+  c.st = st;
+  c.prec = d.precision;
+  const Plan& p = c.p;
+  const Plan::Off& o = p.o;
+  const int pr = c.prec;
+  const int B = d.B, T = d.T, P = d.P, E = d.E, A = d.A, M = d.M, D = d.D, F = d.F, S = d.S, V = d.V,
+            X = p.X, NQ = p.NQ, NG1 = p.NG1;
+  const int64_t R = (int64_t)B * T;
+  const bool ragged = len_h[B - 1] != T;
+  const bool drop = dropout_p > 0.f;
+  std::vector<int> bt(T);
+  for (int t = 0; t < T; ++t) {
+    int n = 0;
+    while (n < B && len_h[n] > t) ++n;
+    bt[t] = n;
+  }
+
+  // ---- gradient wrt the logits in the GEMM operand type ----
+  const void* dlog;
+  int64_t lddl;
+  if (d_logits_ft) { dlog = d_logits_ft; lddl = p.ldV; }
+  else if (pr == CAPDEC_FP32) { dlog = d_pred; lddl = V; }
+  else {
+    CAPDEC_TRY(copy_cast(pr, d_pred, 0, V, c.at(o.dlogF), 1, p.ldV, (int)R, V, st));
+    dlog = c.at(o.dlogF); lddl = p.ldV;
+  }
+  // dH_fc[(b,t), :] = dlogits . W_fc
+  CAPDEC_TRY(G(c, dlog, lddl, c.at(o.Wp_fcT), p.ldV, c.at(o.dHfc), D, 0, nullptr, nullptr, 0, (int)R, D, V));
+  // fc.weight.grad = dlogits^T . dropout(H) ; fc.bias.grad = colsum(dlogits)     (rows in (b,t) order)
+  CAPDEC_TRY(transpose_cast(pr, dlog, 1, c.at(o.tA), 1, 1, (int)R, V, 0, lddl, p.ldR, 0, 1, st));
+  CAPDEC_TRY(transpose_cast(pr, drop ? c.at(o.Hd) : c.at(o.Hall), 1, c.at(o.tB), 1, 1, (int)R, D, 0, D,
+                            p.ldR, 0, 1, st));
+  CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.fc_w, D, 0, nullptr, nullptr, 0, V, D, (int)R));
+  CAPDEC_TRY(colsum(pr, dlog, 1, lddl, (int)R, V, g.fc_b, 0, st));
+
+  CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dh_rec), 0, (size_t)B * D * 4, st));
+  CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dc), 0, (size_t)B * D * 4, st));
+  if (p.scn) {
+    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dv_acc), 0, (size_t)B * NQ * 4, st));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dq_acc), 0, (size_t)B * NQ * 4, st));
+  }
+  if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dAtt1), 0, (size_t)B * P * A * 4, st));
+  if (ragged) {
+    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dpre), 0, (size_t)R * 4 * D * p.fsz, st));
+    if (p.scn) {
+      CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.du), 0, (size_t)R * NQ * p.fsz, st));
+      CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dp), 0, (size_t)R * NQ * p.fsz, st));
+    }
+    if (p.att) {
+      CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dba), 0, (size_t)R * p.ldEA * p.fsz, st));
+      CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dwf), 0, (size_t)R * A * 4, st));
+      CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dbf), 0, (size_t)R * 4, st));
+    }
+  }
+
+  // ---------------- reverse-time recurrence ----------------
+  for (int t = T - 1; t >= 0; --t) {
+    const int n = bt[t];
+    float* g1 = c.at<float>(o.g1) + (int64_t)t * B * NG1;
+    const float* pcol = g1 + (p.att ? A + E : 0);
+    const float* U = c.at<float>(o.U) + (int64_t)t * B * NQ;
+    const float* c_prev = c.at<float>(o.C) + (int64_t)t * B * D;
+    const float* c_new = c.at<float>(o.C) + (int64_t)(t + 1) * B * D;
+    const float* gates = c.at<float>(o.gates) + (int64_t)t * B * 4 * D;
+    void* dpre = c.ft(o.dpre, (int64_t)t * B * 4 * D);
+    float* dh_rec = c.at<float>(o.dh_rec);
+    CAPDEC_TRY(cell_bwd(pr, c.at<float>(o.dHfc) + (int64_t)t * D, (int64_t)T * D, dh_rec, c.at<float>(o.dc),
+                        gates, c_prev, c_new, p.scn ? 0 : 1, dropout_p, seed, t, T, dpre, nullptr, n, D, st));
+    const void* du;      // gradient wrt u (input-side pre-products) and wrt p (recurrent side)
+    const void* dpp;
+    if (p.scn) {
+      // [w_g | r_g] = dpre_g . [W_ic_g | W_hc_g]
+      CAPDEC_TRY(G(c, dpre, 4 * D, c.at(o.Wp_cT), p.ldD, c.at(o.wr), 2 * F, 0, nullptr, nullptr, 0, n, 2 * F,
+                   D, B, 4, D, (int64_t)2 * F * p.ldD, (int64_t)B * 2 * F));
+      void* du_t = c.ft(o.du, (int64_t)t * B * NQ);
+      void* dp_t = c.ft(o.dp, (int64_t)t * B * NQ);
+      CAPDEC_TRY(scn_bwd_products(pr, c.at<float>(o.wr), U, NQ, pcol, NG1, c.at<float>(o.v),
+                                  c.at<float>(o.q), du_t, dp_t, c.at<float>(o.dv_acc),
+                                  c.at<float>(o.dq_acc), n, B, F, st));
+      du = du_t; dpp = dp_t;
+    } else {
+      du = dpre; dpp = dpre;
+    }
+    // dh_{t-1} (recurrent part) = dp . W_hq^T
+    CAPDEC_TRY(G(c, dpp, NQ, c.at(o.Wp_hq), p.ldNQ, dh_rec, D, 0, nullptr, nullptr, 0, n, D, NQ, B));
+    if (p.att) {
+      // dz = du . W_x[M:, :]^T
+      CAPDEC_TRY(G(c, du, NQ, c.ft(o.Wp_xin, (int64_t)M * p.ldNQ), p.ldNQ, c.at(o.dz), E, 0, nullptr,
+                   nullptr, 0, n, E, NQ, B));
+      void* dba = c.ft(o.dba, (int64_t)t * B * p.ldEA);
+      CAPDEC_TRY(attention_bwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w,
+                               alphas + (int64_t)t * P, (int64_t)T * P,
+                               d_alphas ? d_alphas + (int64_t)t * P : nullptr, (int64_t)T * P,
+                               c.at<float>(o.dz), E, c.at<float>(o.awe) + (int64_t)t * B * E, dba, p.ldEA,
+                               c.at<float>(o.dAtt1), c.at<float>(o.dwf) + (int64_t)t * B * A,
+                               c.at<float>(o.dbf) + (int64_t)t * B, n, P, E, A, st));
+      // dh_{t-1} += [dbeta_pre | datt2] . [W_beta^T | W_d^T]^T
+      CAPDEC_TRY(G(c, dba, p.ldEA, c.at(o.Wp_b6), p.ldEA, dh_rec, D, 0, nullptr, dh_rec, D, n, D, E + A, B));
+    }
+  }
+
+  // ---------------- weight gradients: batched GEMMs over all (t,b) rows ----------------
+  // X-side operand = (d out-feature)^T [N_out][R], W-side = (input)^T [K_in][R]; K = R rows.
+  const int Ri = (int)R;
+  // H_prev^T [D][R]: column (t,b) = h_{t-1}[b]  (t=0 -> H0, else Hall[b][t-1])
+  CAPDEC_TRY(transpose_cast(pr, c.at(o.H0), 1, c.at(o.tC), 1, 1, B, D, 0, p.ldD, p.ldR, 0, 1, st));
+  if (T > 1)
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.Hall), 1, c.ft(o.tC, B), 1, T - 1, B, D, D, (int64_t)T * D, p.ldR,
+                              B, 1, st));
+  // bias_ih.grad == bias_hh.grad = colsum(dpre)
+  CAPDEC_TRY(colsum(pr, c.at(o.dpre), 1, 4 * D, Ri, 4 * D, g.b_ih, 0, st));
+  CAPDEC_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * D * 4, cudaMemcpyDeviceToDevice, st));
+  // dpre^T [4D][R]
+  CAPDEC_TRY(transpose_cast(pr, c.at(o.dpre), 1, c.at(o.tA), 1, 1, Ri, 4 * D, 0, 4 * D, p.ldR, 0, 1, st));
+  if (p.scn) {
+    // m^T: per gate [2F][R]
+    for (int gg = 0; gg < 4; ++gg)
+      CAPDEC_TRY(transpose_cast(pr, c.ft(o.m, (int64_t)gg * B * 2 * F), 1,
+                                c.ft(o.tB, (int64_t)gg * 2 * F * p.ldR), 1, T, B, 2 * F,
+                                (int64_t)4 * B * 2 * F, 2 * F, p.ldR, B, 1, st));
+    // weight_ic.grad[:, gF:(g+1)F] = dpre_g^T . (u_g*v_g) ; weight_hc.grad likewise with (p_g*q_g)
+    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ic, NQ, 0, nullptr, nullptr, 0, D, F, Ri, 0, 4,
+                 (int64_t)D * p.ldR, (int64_t)2 * F * p.ldR, F));
+    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.ft(o.tB, (int64_t)F * p.ldR), p.ldR, g.w_hc, NQ, 0, nullptr, nullptr,
+                 0, D, F, Ri, 0, 4, (int64_t)D * p.ldR, (int64_t)2 * F * p.ldR, F));
+    // weight_ha.grad [D][4F] = H_prev^T . dp
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.dp), 1, c.at(o.tB), 1, 1, Ri, NQ, 0, NQ, p.ldR, 0, 1, st));
+    CAPDEC_TRY(G(c, c.at(o.tC), p.ldR, c.at(o.tB), p.ldR, g.w_ha, NQ, 0, nullptr, nullptr, 0, D, NQ, Ri));
+    // weight_ia.grad [X][4F] = [Xe | z]^T . du
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.du), 1, c.at(o.tB), 1, 1, Ri, NQ, 0, NQ, p.ldR, 0, 1, st));
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.Xe), 1, c.at(o.tA), 1, 1, Ri, M, 0, p.ldM, p.ldR, 0, 1, st));
+    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia, NQ, 0, nullptr, nullptr, 0, M, NQ, Ri));
+    if (p.att) {
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.z), 1, c.at(o.tA), 1, 1, Ri, E, 0, E, p.ldR, 0, 1, st));
+      CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia + (int64_t)M * NQ, NQ, 0, nullptr,
+                   nullptr, 0, E, NQ, Ri));
+    }
+    // embedding.weight.grad: dXe = du . W_ia[:M]^T, scattered to the consumed token rows
+    CAPDEC_TRY(G(c, c.at(o.du), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
+    // weight_ib.grad [S][4F] = s^T . sum_t dv ; weight_hb.grad = s^T . sum_t dq
+    CAPDEC_TRY(transpose_cast(pr, tags, 0, c.at(o.tA), 1, 1, B, S, 0, S, p.ldB, 0, 1, st));
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.dv_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
+    CAPDEC_TRY(G(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_ib, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.dq_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
+    CAPDEC_TRY(G(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_hb, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
+  } else {
+    // LSTM: weight_hh.grad [4D][D] = dpre^T . H_prev ; weight_ih.grad [4D][X] = dpre^T . [Xe | z]
+    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tC), p.ldR, g.w_ha, D, 0, nullptr, nullptr, 0, NQ, D, Ri));
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.Xe), 1, c.at(o.tB), 1, 1, Ri, M, 0, p.ldM, p.ldR, 0, 1, st));
+    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia, X, 0, nullptr, nullptr, 0, NQ, M, Ri));
+    if (p.att) {
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.z), 1, c.at(o.tB), 1, 1, Ri, E, 0, E, p.ldR, 0, 1, st));
+      CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia + M, X, 0, nullptr, nullptr, 0, NQ, E, Ri));
+    }
+    CAPDEC_TRY(G(c, c.at(o.dpre), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
+  }
+  if (g.emb) {
+    CAPDEC_CUDA_OK(cudaMemsetAsync(g.emb, 0, (size_t)V * M * 4, st));
+    CAPDEC_TRY(embedding_scatter_add(c.at<float>(o.dXe), M, caps, d.L, c.at<int32_t>(o.lenD), g.emb, B, T,
+                                     M, V, st));
+  }
+
+  if (p.att) {
+    // f_beta / decoder_att: [dbeta_pre | datt2]^T . H_prev
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.dba), 1, c.at(o.tA), 1, 1, Ri, E + A, 0, p.ldEA, p.ldR, 0, 1, st));
+    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tC), p.ldR, g.f_beta_w, D, 0, nullptr, nullptr, 0, E, D, Ri));
+    CAPDEC_TRY(G(c, c.ft(o.tA, (int64_t)E * p.ldR), p.ldR, c.at(o.tC), p.ldR, g.dec_att_w, D, 0, nullptr,
+                 nullptr, 0, A, D, Ri));
+    CAPDEC_TRY(colsum(pr, c.at(o.dba), 1, p.ldEA, Ri, E, g.f_beta_b, 0, st));
+    CAPDEC_TRY(colsum(pr, c.ft(o.dba, E), 1, p.ldEA, Ri, A, g.dec_att_b, 0, st));
+    // full_att: per-row partials reduced over all (t,b)
+    CAPDEC_TRY(colsum(pr, c.at(o.dwf), 0, A, Ri, A, g.full_att_w, 0, st));
+    CAPDEC_TRY(colsum(pr, c.at(o.dbf), 0, 1, Ri, 1, g.full_att_b, 0, st));
+    // encoder_att: dAtt1^T . enc  (K = B*P pixel rows)
+    const int BP = B * P;
+    CAPDEC_TRY(colsum(pr, c.at(o.dAtt1), 0, A, BP, A, g.enc_att_b, 0, st));
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.dAtt1), 0, c.at(o.tA), 1, 1, BP, A, 0, A, p.ldBP, 0, 1, st));
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.enc_s), 1, c.at(o.tB), 1, 1, BP, E, 0, E, p.ldBP, 0, 1, st));
+    CAPDEC_TRY(G(c, c.at(o.tA), p.ldBP, c.at(o.tB), p.ldBP, g.enc_att_w, E, 0, nullptr, nullptr, 0, A, E, BP));
+  }
+  // init_h / init_c: dh0 = dh_rec, dc0 = dc after the last reverse step
+  CAPDEC_TRY(transpose_cast(pr, c.at(o.mean), 0, c.at(o.tB), 1, 1, B, E, 0, E, p.ldB, 0, 1, st));
+  CAPDEC_TRY(transpose_cast(pr, c.at(o.dh_rec), 0, c.at(o.tA), 1, 1, B, D, 0, D, p.ldB, 0, 1, st));
+  CAPDEC_TRY(G(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.init_h_w, E, 0, nullptr, nullptr, 0, D, E, B));
+  CAPDEC_TRY(colsum(pr, c.at(o.dh_rec), 0, D, B, D, g.init_h_b, 0, st));
+  CAPDEC_TRY(transpose_cast(pr, c.at(o.dc), 0, c.at(o.tA), 1, 1, B, D, 0, D, p.ldB, 0, 1, st));
+  CAPDEC_TRY(G(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.init_c_w, E, 0, nullptr, nullptr, 0, D, E, B));
+  CAPDEC_TRY(colsum(pr, c.at(o.dc), 0, D, B, D, g.init_c_b, 0, st));
+  return CAPDEC_OK;
+}
+
+}  // namespace capdec

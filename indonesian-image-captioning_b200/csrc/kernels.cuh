@@ -1,0 +1,87 @@
+// kernels.cuh -- host-callable launchers shared between the translation units of libcapdec.
+#pragma once
+#include "common.cuh"
+
+namespace capdec {
+
+// ---- attention.cu ----
+int attention_init();
+int attention_fwd(int precision, const void* att1, const void* enc, const float* g1, int64_t ldg,
+                  int beta_col, const float* w_f, const float* b_f, float* alpha_out,
+                  int64_t alpha_stride, void* z_out, int64_t ldz, float* awe_out, int rows,
+                  int rows_per_map, int P, int E, int A, cudaStream_t st);
+int attention_bwd(int precision, const void* att1, const void* enc, const float* g1, int64_t ldg,
+                  int beta_col, const float* w_f, const float* alpha, int64_t alpha_stride,
+                  const float* dalpha_ext, int64_t dalpha_stride, const float* dz, int64_t lddz,
+                  const float* awe, void* dba, int64_t lddba, float* dAtt1, float* dwf_part,
+                  float* dbf_part, int rows, int P, int E, int A, cudaStream_t st);
+
+// ---- pointwise.cu ----
+// dst[c*ldd + i*d_i + j*d_j] = src[i*s_i + j*s_j + c]   for i<ni, j<nj, c<C   (transpose + cast)
+// src_ft/dst_ft: 0 = fp32, 1 = the feature type of `precision`
+int transpose_cast(int precision, const void* src, int src_ft, void* dst, int dst_ft, int ni, int nj,
+                   int C, int64_t s_i, int64_t s_j, int64_t ldd, int64_t d_i, int64_t d_j,
+                   cudaStream_t st);
+// dst[r*ldd + c] = src[r*lds + c]  (cast), r<R, c<C
+int copy_cast(int precision, const void* src, int src_ft, int64_t lds, void* dst, int dst_ft,
+              int64_t ldd, int R, int C, cudaStream_t st);
+// out[n] (=|+=) sum_r X[r*ld + n]
+int colsum(int precision, const void* X, int x_ft, int64_t ld, int R, int N, float* out,
+           int accumulate, cudaStream_t st);
+// gather rows by sort_ind, convert to the feature type, and mean over pixels
+int gather_features(int precision, const float* enc, int64_t sb, int64_t sp, int64_t se,
+                    const int64_t* sort_ind, void* enc_s, float* mean_f32, void* mean_ft,
+                    int64_t ld_mean_ft, int B, int P, int E, cudaStream_t st);
+// Xe[(t*B + b)*ldx + :] = emb[caps[b*L + t]]
+int embedding_gather(int precision, const float* emb, const int64_t* caps, int L, void* Xe,
+                     int64_t ldx, int B, int T, int M, int V, cudaStream_t st);
+// dEmb[caps[b][t]] += dXe[(t*B+b)] for t < len[b]
+int embedding_scatter_add(const float* dXe, int64_t ldx, const int64_t* caps, int L,
+                          const int32_t* len_d, float* dEmb, int B, int T, int M, int V,
+                          cudaStream_t st);
+// SCN: m[g][b][0:F] = u*v, m[g][b][F:2F] = p*q
+int scn_form_m(int precision, const float* u, int64_t ldu, const float* p, int64_t ldp,
+               const float* v, const float* q, void* m, int rows, int B, int F, cudaStream_t st);
+// LSTM pointwise.  pre = preA + preB + b1 + b2 ; lstm_order: 0 = (i,f,o,c) SCN, 1 = (i,f,g,o) torch
+int cell_fwd(int precision, const float* preA, int64_t ldA, const float* preB, int64_t ldB,
+             const float* b1, const float* b2, int lstm_order, const float* c_prev, float* c_new,
+             float* gates, void* h_out, int64_t ldh, void* hd_out, float dropout_p, uint64_t seed,
+             int t, int T, int rows, int D, cudaStream_t st);
+int cell_bwd(int precision, const float* dh_fc, int64_t ld_dhfc, const float* dh_rec, float* dc,
+             const float* gates, const float* c_prev, const float* c_new, int lstm_order,
+             float dropout_p, uint64_t seed, int t, int T, void* dpre, float* dpre_f32, int rows,
+             int D, cudaStream_t st);
+// SCN backward pointwise: du = w*v, dp = r*q, dv_acc += w*u, dq_acc += r*p ; wr = [g][b][w(F)|r(F)]
+int scn_bwd_products(int precision, const float* wr, const float* u, int64_t ldu, const float* p,
+                     int64_t ldp, const float* v, const float* q, void* du, void* dp,
+                     float* dv_acc, float* dq_acc, int rows, int B, int F, cudaStream_t st);
+// out[i] = a[i] (+ b[i]) ; small helpers
+int concat_bias(float* dst, const float* a, int na, const float* b, int nb, int nzero,
+                cudaStream_t st);
+int zero_rows_beyond_len(float* x, const int32_t* len_d, int B, int T, int64_t row_elems,
+                         cudaStream_t st);
+
+// ---- loss.cu ----
+int loss_fwd(const CapdecDims& d, const float* pred, const float* alphas, const int64_t* caps,
+             const int32_t* len_d, int n_tokens, float alpha_c, float* loss_out, float* lse_out,
+             cudaStream_t st);
+int loss_bwd(const CapdecDims& d, const float* pred, const float* alphas, const int64_t* caps,
+             const int32_t* len_d, int n_tokens, float alpha_c, float gscale, const float* gscale_dev,
+             const float* lse, float* d_pred, void* d_logits_ft, int64_t ldq, float* d_alphas,
+             cudaStream_t st);
+
+}  // namespace capdec
+
+// ---- decoder.cu ----
+namespace capdec {
+size_t workspace_bytes(const CapdecDims& d, int with_bwd);
+int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, int64_t sb, int64_t sp,
+                  int64_t se, const int64_t* sort_ind, const float* tags, const int64_t* caps,
+                  const int32_t* len_h, float dropout_p, uint64_t seed, int save_bwd,
+                  float* predictions, float* alphas, void* workspace, size_t ws_bytes,
+                  cudaStream_t st);
+int backward(const CapdecDims& d, const CapdecParams& w, const float* tags, const int64_t* caps,
+             const int32_t* len_h, float dropout_p, uint64_t seed, const float* d_pred,
+             const void* d_logits_ft, const float* d_alphas, const float* alphas,
+             const CapdecParams& g, void* workspace, size_t ws_bytes, cudaStream_t st);
+}  // namespace capdec

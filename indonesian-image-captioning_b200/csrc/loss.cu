@@ -1,0 +1,196 @@
+// loss.cu -- the loss glue of the training loop as two fused kernels + a finaliser.
+//
+// Reference: trains/attention_scn.py:219-235
+//   targets = caps_sorted[:, 1:] ; pack_padded_sequence(scores/targets, decode_lengths)
+//   loss = CrossEntropyLoss(mean over N = sum(decode_lengths))
+//        + alpha_c * mean_{b,p} (1 - sum_t alphas[b,t,p])^2
+// The packing is only a row selection: row (b,t) takes part iff t < decode_len[b].
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace capdec {
+
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = -INFINITY;
+  for (int i = 0; i < NT / 32; ++i) r = fmaxf(r, sh[i]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < NT / 32; ++i) r += sh[i];
+  __syncthreads();
+  return r;
+}
+
+// one CTA per (b,t) row: log-sum-exp and the target's negative log-likelihood
+__global__ void __launch_bounds__(NT)
+ce_fwd_kernel(const float* __restrict__ pred, const int64_t* __restrict__ caps,
+              const int32_t* __restrict__ len_d, int T, int V, int L, float* __restrict__ lse_out,
+              float* __restrict__ nll_out) {
+  __shared__ float sh[NT / 32];
+  const int r = blockIdx.x;
+  const int b = r / T, t = r - b * T;
+  if (t >= len_d[b]) {
+    if (threadIdx.x == 0) { lse_out[r] = 0.f; nll_out[r] = 0.f; }
+    return;
+  }
+  const float* x = pred + (int64_t)r * V;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += NT) m = fmaxf(m, x[i]);
+  m = block_max(m, sh);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += NT) s += expf(x[i] - m);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) {
+    const float lse = logf(s) + m;
+    int64_t tgt = caps[(int64_t)b * L + t + 1];
+    if (tgt < 0) tgt = 0;
+    if (tgt >= V) tgt = V - 1;
+    lse_out[r] = lse;
+    nll_out[r] = lse - x[tgt];
+  }
+}
+
+// one CTA per caption b: sum_p (1 - sum_t alpha[b,t,p])^2
+__global__ void __launch_bounds__(NT)
+alpha_reg_fwd_kernel(const float* __restrict__ alphas, int T, int P, float* __restrict__ regpart) {
+  __shared__ float sh[NT / 32];
+  const int b = blockIdx.x;
+  const float* a = alphas + (int64_t)b * T * P;
+  float acc = 0.f;
+  for (int p = threadIdx.x; p < P; p += NT) {
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += a[(int64_t)t * P + p];
+    const float d = 1.f - s;
+    acc += d * d;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) regpart[b] = acc;
+}
+
+__global__ void __launch_bounds__(NT)
+loss_finalize_kernel(const float* __restrict__ nll, int n_rows, const float* __restrict__ regpart,
+                     int B, int P, int n_tokens, float alpha_c, float* __restrict__ loss_out) {
+  __shared__ float sh[NT / 32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n_rows; i += NT) s += nll[i];
+  s = block_sum(s, sh);
+  float r = 0.f;
+  if (regpart)
+    for (int i = threadIdx.x; i < B; i += NT) r += regpart[i];
+  r = block_sum(r, sh);
+  if (threadIdx.x == 0) {
+    const float ce = s / (float)n_tokens;
+    const float reg = regpart ? alpha_c * r / ((float)B * (float)P) : 0.f;
+    loss_out[0] = ce + reg;
+    loss_out[1] = ce;
+    loss_out[2] = reg;
+  }
+}
+
+// d logits = g/N (softmax - onehot) for active rows, 0 otherwise
+template <typename FT>
+__global__ void __launch_bounds__(NT)
+ce_bwd_kernel(const float* __restrict__ pred, const int64_t* __restrict__ caps,
+              const int32_t* __restrict__ len_d, const float* __restrict__ lse, int T, int V, int L,
+              float scale, const float* __restrict__ gscale_dev, float* __restrict__ d_pred,
+              FT* __restrict__ d_ft, int64_t ldq) {
+  if (gscale_dev) scale *= gscale_dev[0];
+  const int r = blockIdx.x;
+  const int b = r / T, t = r - b * T;
+  const bool active = t < len_d[b];
+  const float* x = pred + (int64_t)r * V;
+  float* dp = d_pred ? d_pred + (int64_t)r * V : nullptr;
+  FT* dq = d_ft ? d_ft + (int64_t)r * ldq : nullptr;
+  if (!active) {
+    for (int i = threadIdx.x; i < V; i += NT) {
+      if (dp) dp[i] = 0.f;
+      if (dq) dq[i] = from_f<FT>(0.f);
+    }
+    return;
+  }
+  const float l = lse[r];
+  int64_t tgt = caps[(int64_t)b * L + t + 1];
+  if (tgt < 0) tgt = 0;
+  if (tgt >= V) tgt = V - 1;
+  for (int i = threadIdx.x; i < V; i += NT) {
+    float g = expf(x[i] - l);
+    if (i == (int)tgt) g -= 1.f;
+    g *= scale;
+    if (dp) dp[i] = g;
+    if (dq) dq[i] = from_f<FT>(g);
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+alpha_reg_bwd_kernel(const float* __restrict__ alphas, const int32_t* __restrict__ len_d, int T,
+                     int P, float scale, const float* __restrict__ gscale_dev,
+                     float* __restrict__ d_alphas) {
+  if (gscale_dev) scale *= gscale_dev[0];
+  const int b = blockIdx.x;
+  const float* a = alphas + (int64_t)b * T * P;
+  float* d = d_alphas + (int64_t)b * T * P;
+  const int len = len_d[b];
+  for (int p = threadIdx.x; p < P; p += NT) {
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) s += a[(int64_t)t * P + p];
+    const float g = -2.f * (1.f - s) * scale;
+    for (int t = 0; t < T; ++t) d[(int64_t)t * P + p] = t < len ? g : 0.f;
+  }
+}
+
+}  // namespace
+
+int loss_fwd(const CapdecDims& d, const float* pred, const float* alphas, const int64_t* caps,
+             const int32_t* len_d, int n_tokens, float alpha_c, float* loss_out, float* lse_out,
+             cudaStream_t st) {
+  const int R = d.B * d.T;
+  float* nll = lse_out + R;
+  float* regpart = alphas ? lse_out + 2 * R : nullptr;
+  ce_fwd_kernel<<<R, NT, 0, st>>>(pred, caps, len_d, d.T, d.V, d.L, lse_out, nll);
+  CAPDEC_LAUNCH_OK();
+  if (alphas) {
+    alpha_reg_fwd_kernel<<<d.B, NT, 0, st>>>(alphas, d.T, d.P, regpart);
+    CAPDEC_LAUNCH_OK();
+  }
+  loss_finalize_kernel<<<1, NT, 0, st>>>(nll, R, regpart, d.B, d.P, n_tokens, alpha_c, loss_out);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int loss_bwd(const CapdecDims& d, const float* pred, const float* alphas, const int64_t* caps,
+             const int32_t* len_d, int n_tokens, float alpha_c, float gscale, const float* gscale_dev,
+             const float* lse, float* d_pred, void* d_logits_ft, int64_t ldq, float* d_alphas,
+             cudaStream_t st) {
+  const int R = d.B * d.T;
+  const float scale = gscale / (float)n_tokens;
+  if (d_pred || d_logits_ft) {
+    if (d.precision == CAPDEC_BF16)
+      ce_bwd_kernel<bf16><<<R, NT, 0, st>>>(pred, caps, len_d, lse, d.T, d.V, d.L, scale, gscale_dev,
+                                            d_pred, (bf16*)d_logits_ft, ldq);
+    else
+      ce_bwd_kernel<float><<<R, NT, 0, st>>>(pred, caps, len_d, lse, d.T, d.V, d.L, scale, gscale_dev,
+                                             d_pred, (float*)d_logits_ft, ldq);
+    CAPDEC_LAUNCH_OK();
+  }
+  if (alphas && d_alphas) {
+    alpha_reg_bwd_kernel<<<d.B, NT, 0, st>>>(alphas, len_d, d.T, d.P,
+                                             gscale * alpha_c / ((float)d.B * (float)d.P), gscale_dev,
+                                             d_alphas);
+    CAPDEC_LAUNCH_OK();
+  }
+  return CAPDEC_OK;
+}
+
+}  // namespace capdec

@@ -1,0 +1,459 @@
+// pointwise.cu -- layout/packing, gather/scatter and LSTM/SCN pointwise kernels.
+//
+// Reference math (paths relative to the reference root):
+//   cell_fwd / cell_bwd       models/scn_cell.py:146-152 (gate order i,f,o,c) and
+//                             torch.nn.LSTMCell as used by pure_attention.py:143-146 (i,f,g,o)
+//   scn_form_m                models/scn_cell.py:83-86, 134-143: (x W_ia) * (s W_ib), (h W_ha) * (s W_hb)
+//   gather_features           attention_scn.py:113-120 (view, sort permutation) + :90 (pixel mean)
+//   embedding_gather          attention_scn.py:124
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace capdec {
+
+namespace {
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p) { return to_f(*p); }
+
+// ------------------------------------------------------------------------------------
+// transpose + cast through a 32x33 shared tile
+// ------------------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int ni, int nj,
+                                 int C, int64_t s_i, int64_t s_j, int64_t ldd, int64_t d_i,
+                                 int64_t d_j) {
+  __shared__ float tile[32][33];
+  const int R = ni * nj;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < R && c < C) {
+      const int i = r / nj, j = r - i * nj;
+      v = ldf(src + (int64_t)i * s_i + (int64_t)j * s_j + c);
+    }
+    tile[k][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int c = c0 + k, r = r0 + threadIdx.x;
+    if (r < R && c < C) {
+      const int i = r / nj, j = r - i * nj;
+      dst[(int64_t)c * ldd + (int64_t)i * d_i + (int64_t)j * d_j] = from_f<TD>(tile[threadIdx.x][k]);
+    }
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void copy_cast_kernel(const TS* __restrict__ src, int64_t lds, TD* __restrict__ dst,
+                                 int64_t ldd, int R, int C) {
+  const int64_t total = (int64_t)R * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i - (int64_t)r * C);
+    dst[(int64_t)r * ldd + c] = from_f<TD>(ldf(src + (int64_t)r * lds + c));
+  }
+}
+
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ X, int64_t ld, int R, int N, float* out,
+                              int accumulate) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (n < N)
+    for (int r = threadIdx.y; r < R; r += 8) s += ldf(X + (int64_t)r * ld + n);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    out[n] = accumulate ? out[n] + t : t;
+  }
+}
+
+template <typename FT>
+__global__ void gather_features_kernel(const float* __restrict__ enc, int64_t sb, int64_t sp,
+                                       int64_t se, const int64_t* __restrict__ sort_ind,
+                                       FT* __restrict__ enc_s, float* __restrict__ mean_f32,
+                                       FT* __restrict__ mean_ft, int64_t ld_mean_ft, int B, int P,
+                                       int E) {
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t src_b = sort_ind ? sort_ind[b] : b;
+  const float* src = enc + src_b * sb + (int64_t)e * se;
+  FT* dst = enc_s + (int64_t)b * P * E + e;
+  float s = 0.f;
+  int p = 0;
+  for (; p + 3 < P; p += 4) {
+    const float v0 = src[(int64_t)p * sp], v1 = src[(int64_t)(p + 1) * sp];
+    const float v2 = src[(int64_t)(p + 2) * sp], v3 = src[(int64_t)(p + 3) * sp];
+    dst[(int64_t)p * E] = from_f<FT>(v0);
+    dst[(int64_t)(p + 1) * E] = from_f<FT>(v1);
+    dst[(int64_t)(p + 2) * E] = from_f<FT>(v2);
+    dst[(int64_t)(p + 3) * E] = from_f<FT>(v3);
+    s += v0; s += v1; s += v2; s += v3;
+  }
+  for (; p < P; ++p) {
+    const float v0 = src[(int64_t)p * sp];
+    dst[(int64_t)p * E] = from_f<FT>(v0);
+    s += v0;
+  }
+  const float m = s / (float)P;
+  if (mean_f32) mean_f32[(int64_t)b * E + e] = m;
+  if (mean_ft) mean_ft[(int64_t)b * ld_mean_ft + e] = from_f<FT>(m);
+}
+
+template <typename FT>
+__global__ void embedding_gather_kernel(const float* __restrict__ emb,
+                                        const int64_t* __restrict__ caps, int L, FT* __restrict__ Xe,
+                                        int64_t ldx, int B, int T, int M, int V) {
+  const int r = blockIdx.x;          // r = t*B + b
+  const int t = r / B, b = r - t * B;
+  int64_t w = caps[(int64_t)b * L + t];
+  if (w < 0) w = 0;
+  if (w >= V) w = V - 1;
+  const float* src = emb + w * M;
+  FT* dst = Xe + (int64_t)r * ldx;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) dst[i] = from_f<FT>(src[i]);
+}
+
+__global__ void embedding_scatter_add_kernel(const float* __restrict__ dXe, int64_t ldx,
+                                             const int64_t* __restrict__ caps, int L,
+                                             const int32_t* __restrict__ len_d, float* dEmb, int B,
+                                             int T, int M, int V) {
+  const int r = blockIdx.x;
+  const int t = r / B, b = r - t * B;
+  if (t >= len_d[b]) return;
+  int64_t w = caps[(int64_t)b * L + t];
+  if (w < 0 || w >= V) return;
+  const float* src = dXe + (int64_t)r * ldx;
+  float* dst = dEmb + w * M;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) atomicAdd(dst + i, src[i]);
+}
+
+template <typename FT>
+__global__ void scn_form_m_kernel(const float* __restrict__ u, int64_t ldu,
+                                  const float* __restrict__ p, int64_t ldp,
+                                  const float* __restrict__ v, const float* __restrict__ q,
+                                  FT* __restrict__ m, int rows, int B, int F) {
+  const int64_t total = (int64_t)rows * 4 * F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / (4 * F));
+    const int n = (int)(i - (int64_t)b * 4 * F);     // n = g*F + f
+    const int g = n / F, f = n - g * F;
+    const float uv = u[(int64_t)b * ldu + n] * v[(int64_t)b * 4 * F + n];
+    const float pq = p[(int64_t)b * ldp + n] * q[(int64_t)b * 4 * F + n];
+    FT* dst = m + ((int64_t)g * B + b) * 2 * F;
+    dst[f] = from_f<FT>(uv);
+    dst[F + f] = from_f<FT>(pq);
+  }
+}
+
+// gate slots in the pre-activation buffer for the two orders
+__device__ __forceinline__ void gate_slots(int lstm_order, int& si, int& sf, int& so, int& sg) {
+  si = 0; sf = 1;
+  if (lstm_order) { sg = 2; so = 3; } else { so = 2; sg = 3; }
+}
+
+template <typename FT>
+__global__ void cell_fwd_kernel(const float* __restrict__ preA, int64_t ldA,
+                                const float* __restrict__ preB, int64_t ldB,
+                                const float* __restrict__ b1, const float* __restrict__ b2,
+                                int lstm_order, const float* __restrict__ c_prev,
+                                float* __restrict__ c_new, float* __restrict__ gates,
+                                FT* __restrict__ h_out, int64_t ldh, FT* __restrict__ hd_out,
+                                float dropout_p, uint64_t seed, int t, int T, int rows, int D) {
+  int si, sf, so, sg;
+  gate_slots(lstm_order, si, sf, so, sg);
+  const int64_t total = (int64_t)rows * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / D), d = (int)(i - (int64_t)b * D);
+    float pre[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float x = preA[(int64_t)b * ldA + g * D + d];
+      if (preB) x += preB[(int64_t)b * ldB + g * D + d];
+      if (b1) x += b1[g * D + d];
+      if (b2) x += b2[g * D + d];
+      pre[g] = x;
+    }
+    const float ig = sigmoidf_(pre[si]), fg = sigmoidf_(pre[sf]), og = sigmoidf_(pre[so]);
+    const float gg = tanhf(pre[sg]);
+    const float c = fg * c_prev[i] + ig * gg;
+    const float h = og * tanhf(c);
+    c_new[i] = c;
+    if (gates) {
+      float* gp = gates + (int64_t)b * 4 * D + d;       // stored as [i | f | o | g~]
+      gp[0] = ig; gp[D] = fg; gp[2 * D] = og; gp[3 * D] = gg;
+    }
+    h_out[(int64_t)b * ldh + d] = from_f<FT>(h);
+    if (hd_out) {
+      const float sc = dropout_scale(seed, ((uint64_t)b * T + t) * D + d, dropout_p);
+      hd_out[(int64_t)b * ldh + d] = from_f<FT>(h * sc);
+    }
+  }
+}
+
+template <typename FT>
+__global__ void cell_bwd_kernel(const float* __restrict__ dh_fc, int64_t ld_dhfc,
+                                const float* __restrict__ dh_rec, float* __restrict__ dc,
+                                const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                const float* __restrict__ c_new, int lstm_order, float dropout_p,
+                                uint64_t seed, int t, int T, FT* __restrict__ dpre,
+                                float* __restrict__ dpre_f32, int rows, int D) {
+  int si, sf, so, sg;
+  gate_slots(lstm_order, si, sf, so, sg);
+  const int64_t total = (int64_t)rows * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / D), d = (int)(i - (int64_t)b * D);
+    float dh = dh_rec[i];
+    if (dh_fc) {
+      float g = dh_fc[(int64_t)b * ld_dhfc + d];
+      if (dropout_p > 0.f) g *= dropout_scale(seed, ((uint64_t)b * T + t) * D + d, dropout_p);
+      dh += g;
+    }
+    const float* gp = gates + (int64_t)b * 4 * D + d;
+    const float ig = gp[0], fg = gp[D], og = gp[2 * D], gg = gp[3 * D];
+    const float tc = tanhf(c_new[i]);
+    const float dcn = dc[i] + dh * og * (1.f - tc * tc);
+    const float dpo = dh * tc * og * (1.f - og);
+    const float dpi = dcn * gg * ig * (1.f - ig);
+    const float dpf = dcn * c_prev[i] * fg * (1.f - fg);
+    const float dpg = dcn * ig * (1.f - gg * gg);
+    dc[i] = dcn * fg;
+    const int64_t o = (int64_t)b * 4 * D + d;
+    dpre[o + (int64_t)si * D] = from_f<FT>(dpi);
+    dpre[o + (int64_t)sf * D] = from_f<FT>(dpf);
+    dpre[o + (int64_t)so * D] = from_f<FT>(dpo);
+    dpre[o + (int64_t)sg * D] = from_f<FT>(dpg);
+    if (dpre_f32) {
+      dpre_f32[o + (int64_t)si * D] = dpi;
+      dpre_f32[o + (int64_t)sf * D] = dpf;
+      dpre_f32[o + (int64_t)so * D] = dpo;
+      dpre_f32[o + (int64_t)sg * D] = dpg;
+    }
+  }
+}
+
+template <typename FT>
+__global__ void scn_bwd_products_kernel(const float* __restrict__ wr, const float* __restrict__ u,
+                                        int64_t ldu, const float* __restrict__ p, int64_t ldp,
+                                        const float* __restrict__ v, const float* __restrict__ q,
+                                        FT* __restrict__ du, FT* __restrict__ dp,
+                                        float* __restrict__ dv_acc, float* __restrict__ dq_acc,
+                                        int rows, int B, int F) {
+  const int64_t total = (int64_t)rows * 4 * F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / (4 * F));
+    const int n = (int)(i - (int64_t)b * 4 * F);
+    const int g = n / F, f = n - g * F;
+    const float* src = wr + ((int64_t)g * B + b) * 2 * F;
+    const float w = src[f], r = src[F + f];
+    const int64_t k = (int64_t)b * 4 * F + n;
+    du[k] = from_f<FT>(w * v[k]);
+    dp[k] = from_f<FT>(r * q[k]);
+    dv_acc[k] += w * u[(int64_t)b * ldu + n];
+    dq_acc[k] += r * p[(int64_t)b * ldp + n];
+  }
+}
+
+__global__ void concat_bias_kernel(float* dst, const float* a, int na, const float* b, int nb,
+                                   int nzero) {
+  const int n = na + nb + nzero;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < na) v = a[i];
+    else if (i < na + nb) v = b[i - na];
+    dst[i] = v;
+  }
+}
+
+__global__ void zero_rows_kernel(float* x, const int32_t* __restrict__ len_d, int B, int T,
+                                 int64_t row_elems) {
+  const int r = blockIdx.x;       // r = b*T + t
+  const int b = r / T, t = r - b * T;
+  if (t < len_d[b]) return;
+  float* p = x + (int64_t)r * row_elems;
+  for (int64_t i = threadIdx.x; i < row_elems; i += blockDim.x) p[i] = 0.f;
+}
+
+inline int grid_for(int64_t total, int threads) {
+  int64_t g = (total + threads - 1) / threads;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+#define DISPATCH_2FT(precision, src_ft, dst_ft, CALL)                                  \
+  do {                                                                                 \
+    const bool s_h = (src_ft) && (precision) == CAPDEC_BF16;                           \
+    const bool d_h = (dst_ft) && (precision) == CAPDEC_BF16;                           \
+    if (s_h && d_h) { CALL(bf16, bf16); }                                              \
+    else if (s_h && !d_h) { CALL(bf16, float); }                                       \
+    else if (!s_h && d_h) { CALL(float, bf16); }                                       \
+    else { CALL(float, float); }                                                       \
+  } while (0)
+
+int transpose_cast(int precision, const void* src, int src_ft, void* dst, int dst_ft, int ni, int nj,
+                   int C, int64_t s_i, int64_t s_j, int64_t ldd, int64_t d_i, int64_t d_j,
+                   cudaStream_t st) {
+  const int R = ni * nj;
+  if (R <= 0 || C <= 0) return CAPDEC_OK;
+  dim3 grid(ceil_div(C, 32), ceil_div(R, 32)), block(32, 8);
+#define CALL(TS, TD)                                                                          \
+  transpose_kernel<TS, TD><<<grid, block, 0, st>>>((const TS*)src, (TD*)dst, ni, nj, C, s_i, s_j, \
+                                                   ldd, d_i, d_j)
+  DISPATCH_2FT(precision, src_ft, dst_ft, CALL);
+#undef CALL
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int copy_cast(int precision, const void* src, int src_ft, int64_t lds, void* dst, int dst_ft,
+              int64_t ldd, int R, int C, cudaStream_t st) {
+  if (R <= 0 || C <= 0) return CAPDEC_OK;
+  const int g = grid_for((int64_t)R * C, 256);
+#define CALL(TS, TD) \
+  copy_cast_kernel<TS, TD><<<g, 256, 0, st>>>((const TS*)src, lds, (TD*)dst, ldd, R, C)
+  DISPATCH_2FT(precision, src_ft, dst_ft, CALL);
+#undef CALL
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int colsum(int precision, const void* X, int x_ft, int64_t ld, int R, int N, float* out,
+           int accumulate, cudaStream_t st) {
+  if (N <= 0) return CAPDEC_OK;
+  dim3 grid(ceil_div(N, 32)), block(32, 8);
+  if (x_ft && precision == CAPDEC_BF16)
+    colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)X, ld, R, N, out, accumulate);
+  else
+    colsum_kernel<float><<<grid, block, 0, st>>>((const float*)X, ld, R, N, out, accumulate);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int gather_features(int precision, const float* enc, int64_t sb, int64_t sp, int64_t se,
+                    const int64_t* sort_ind, void* enc_s, float* mean_f32, void* mean_ft,
+                    int64_t ld_mean_ft, int B, int P, int E, cudaStream_t st) {
+  dim3 grid(ceil_div(E, 128), B);
+  if (precision == CAPDEC_BF16)
+    gather_features_kernel<bf16><<<grid, 128, 0, st>>>(enc, sb, sp, se, sort_ind, (bf16*)enc_s,
+                                                       mean_f32, (bf16*)mean_ft, ld_mean_ft, B, P, E);
+  else
+    gather_features_kernel<float><<<grid, 128, 0, st>>>(enc, sb, sp, se, sort_ind, (float*)enc_s,
+                                                        mean_f32, (float*)mean_ft, ld_mean_ft, B, P, E);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int embedding_gather(int precision, const float* emb, const int64_t* caps, int L, void* Xe,
+                     int64_t ldx, int B, int T, int M, int V, cudaStream_t st) {
+  if (B * T <= 0) return CAPDEC_OK;
+  if (precision == CAPDEC_BF16)
+    embedding_gather_kernel<bf16><<<B * T, 128, 0, st>>>(emb, caps, L, (bf16*)Xe, ldx, B, T, M, V);
+  else
+    embedding_gather_kernel<float><<<B * T, 128, 0, st>>>(emb, caps, L, (float*)Xe, ldx, B, T, M, V);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int embedding_scatter_add(const float* dXe, int64_t ldx, const int64_t* caps, int L,
+                          const int32_t* len_d, float* dEmb, int B, int T, int M, int V,
+                          cudaStream_t st) {
+  if (B * T <= 0) return CAPDEC_OK;
+  embedding_scatter_add_kernel<<<B * T, 128, 0, st>>>(dXe, ldx, caps, L, len_d, dEmb, B, T, M, V);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int scn_form_m(int precision, const float* u, int64_t ldu, const float* p, int64_t ldp,
+               const float* v, const float* q, void* m, int rows, int B, int F, cudaStream_t st) {
+  if (rows <= 0) return CAPDEC_OK;
+  const int g = grid_for((int64_t)rows * 4 * F, 256);
+  if (precision == CAPDEC_BF16)
+    scn_form_m_kernel<bf16><<<g, 256, 0, st>>>(u, ldu, p, ldp, v, q, (bf16*)m, rows, B, F);
+  else
+    scn_form_m_kernel<float><<<g, 256, 0, st>>>(u, ldu, p, ldp, v, q, (float*)m, rows, B, F);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int cell_fwd(int precision, const float* preA, int64_t ldA, const float* preB, int64_t ldB,
+             const float* b1, const float* b2, int lstm_order, const float* c_prev, float* c_new,
+             float* gates, void* h_out, int64_t ldh, void* hd_out, float dropout_p, uint64_t seed,
+             int t, int T, int rows, int D, cudaStream_t st) {
+  if (rows <= 0) return CAPDEC_OK;
+  const int g = grid_for((int64_t)rows * D, 128);
+  if (precision == CAPDEC_BF16)
+    cell_fwd_kernel<bf16><<<g, 128, 0, st>>>(preA, ldA, preB, ldB, b1, b2, lstm_order, c_prev, c_new,
+                                             gates, (bf16*)h_out, ldh, (bf16*)hd_out, dropout_p, seed,
+                                             t, T, rows, D);
+  else
+    cell_fwd_kernel<float><<<g, 128, 0, st>>>(preA, ldA, preB, ldB, b1, b2, lstm_order, c_prev, c_new,
+                                              gates, (float*)h_out, ldh, (float*)hd_out, dropout_p,
+                                              seed, t, T, rows, D);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int cell_bwd(int precision, const float* dh_fc, int64_t ld_dhfc, const float* dh_rec, float* dc,
+             const float* gates, const float* c_prev, const float* c_new, int lstm_order,
+             float dropout_p, uint64_t seed, int t, int T, void* dpre, float* dpre_f32, int rows,
+             int D, cudaStream_t st) {
+  if (rows <= 0) return CAPDEC_OK;
+  const int g = grid_for((int64_t)rows * D, 128);
+  if (precision == CAPDEC_BF16)
+    cell_bwd_kernel<bf16><<<g, 128, 0, st>>>(dh_fc, ld_dhfc, dh_rec, dc, gates, c_prev, c_new,
+                                             lstm_order, dropout_p, seed, t, T, (bf16*)dpre, dpre_f32,
+                                             rows, D);
+  else
+    cell_bwd_kernel<float><<<g, 128, 0, st>>>(dh_fc, ld_dhfc, dh_rec, dc, gates, c_prev, c_new,
+                                              lstm_order, dropout_p, seed, t, T, (float*)dpre,
+                                              dpre_f32, rows, D);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int scn_bwd_products(int precision, const float* wr, const float* u, int64_t ldu, const float* p,
+                     int64_t ldp, const float* v, const float* q, void* du, void* dp,
+                     float* dv_acc, float* dq_acc, int rows, int B, int F, cudaStream_t st) {
+  if (rows <= 0) return CAPDEC_OK;
+  const int g = grid_for((int64_t)rows * 4 * F, 256);
+  if (precision == CAPDEC_BF16)
+    scn_bwd_products_kernel<bf16><<<g, 256, 0, st>>>(wr, u, ldu, p, ldp, v, q, (bf16*)du, (bf16*)dp,
+                                                     dv_acc, dq_acc, rows, B, F);
+  else
+    scn_bwd_products_kernel<float><<<g, 256, 0, st>>>(wr, u, ldu, p, ldp, v, q, (float*)du,
+                                                      (float*)dp, dv_acc, dq_acc, rows, B, F);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int concat_bias(float* dst, const float* a, int na, const float* b, int nb, int nzero,
+                cudaStream_t st) {
+  const int n = na + nb + nzero;
+  if (n <= 0) return CAPDEC_OK;
+  concat_bias_kernel<<<grid_for(n, 256), 256, 0, st>>>(dst, a, na, b, nb, nzero);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int zero_rows_beyond_len(float* x, const int32_t* len_d, int B, int T, int64_t row_elems,
+                         cudaStream_t st) {
+  if (B * T <= 0) return CAPDEC_OK;
+  zero_rows_kernel<<<B * T, 256, 0, st>>>(x, len_d, B, T, row_elems);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+}  // namespace capdec

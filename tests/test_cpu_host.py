@@ -1,0 +1,100 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the drop-in
+modules expose the reference's state_dict layout, and nothing silently computes on the CPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import capdec_oracle as O
+from conftest import ROOT, PKG
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "capdec.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(capdec_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from capdec import _lib
+    lib = _lib.load()
+    names = _header_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in _lib.SIGNATURES, "ctypes signature missing for " + n
+    assert lib.capdec_version() == 100
+
+
+def test_workspace_query_is_host_only():
+    from capdec import _lib, functional as CF
+    lib = _lib.load()
+    d = CF.make_dims("attention_scn", "bf16", 32, 50, 196, 2048, 512, 512, 512, 512, 1000, 10000, 52)
+    fwd = lib.capdec_workspace_bytes(ctypes.byref(d), 0)
+    both = lib.capdec_workspace_bytes(ctypes.byref(d), 1)
+    assert 0 < fwd < both < 4 << 30
+    bad = CF.make_dims("attention_scn", "bf16", 32, 50, 196, 2048, 512, 512, 510, 512, 1000, 10000, 52)
+    assert lib.capdec_workspace_bytes(ctypes.byref(bad), 0) == 0
+    assert b"multiples of 8" in lib.capdec_last_error()
+
+
+@pytest.mark.parametrize("kind", O.KINDS)
+def test_state_dict_layout_matches_reference(kind):
+    from gpu_util import build_decoder
+    dims = dict(A=24, M=16, D=32, F=24, S=12, V=37, E=40)
+    dec = build_decoder(kind, dims, device="cpu")
+    want = O.param_shapes(kind, attention_dim=24, embed_dim=16, decoder_dim=32, factored_dim=24,
+                          semantic_dim=12, vocab_size=37, encoder_dim=40)
+    got = {k: tuple(v.shape) for k, v in dec.state_dict().items()}
+    assert got == want
+    assert list(got) == list(want)           # same order as the reference modules register them
+    from capdec import functional as CF
+    assert sorted(CF.param_names(kind)) == sorted(want)
+
+
+def test_no_cpu_fallback():
+    from gpu_util import build_decoder
+    from capdec._lib import CapdecError
+    dims = dict(A=24, M=16, D=32, F=24, S=12, V=37, E=40)
+    dec = build_decoder(O.ATTENTION_SCN, dims, device="cpu").eval()
+    enc, tags, caps, caplens = O.synthetic_batch(3, 37, side=3, E=40, S=12, max_len=14,
+                                                 lengths=[5, 9, 3])
+    with pytest.raises(CapdecError):
+        dec(enc, tags, caps, caplens)
+
+
+def test_product_never_imports_oracle():
+    for base, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(base, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not present")
+@pytest.mark.parametrize("kind,cls", [("attention_scn", "AttentionSCN"), ("pure_scn", "PureSCN"),
+                                      ("pure_attention", "PureAttention")])
+def test_same_seed_same_init_as_reference(kind, cls, tmp_path):
+    """Construction order mirrors the reference, so torch.manual_seed(k) gives identical weights."""
+    out = tmp_path / "ref_sd.pt"
+    code = (
+        "import sys, torch; sys.path.insert(0, '/root/reference');"
+        "from models.decoders.%s import %s as C;"
+        "torch.manual_seed(7);"
+        "m = C(24,16,32,24,12,37,encoder_dim=40) if '%s'=='attention_scn' else "
+        "(C(16,32,24,12,37,encoder_dim=40) if '%s'=='pure_scn' else C(24,16,32,37,encoder_dim=40));"
+        "torch.save(m.state_dict(), r'%s')" % (kind, cls, kind, kind, out))
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=str(tmp_path),
+                   env={k: v for k, v in os.environ.items() if k != "PYTHONPATH"})
+    ref = torch.load(out)
+    from gpu_util import build_decoder
+    torch.manual_seed(7)
+    dec = build_decoder(kind, dict(A=24, M=16, D=32, F=24, S=12, V=37, E=40), device="cpu")
+    mine = dec.state_dict()
+    assert list(mine) == list(ref)
+    for k in ref:
+        assert torch.equal(mine[k], ref[k]), k

@@ -1,0 +1,193 @@
+"""GPU parity tests of the drop-in decoder modules through the C ABI.
+
+fp32 mode: logits / alphas / loss / every parameter gradient within 1e-4 (max-norm relative,
+BASELINE.json north_star) of the golden vectors produced by the live reference and of the
+fp64 oracle.  bf16 mode: logits within 2e-2.
+"""
+import pytest
+import torch
+
+import capdec
+from oracle import capdec_oracle as O
+from conftest import load_golden
+from gpu_util import build_decoder, call_forward, torch_loss_glue, rel_err, oracle_run
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+GOLDEN = ["train_attention_scn_small", "train_pure_scn_small", "train_pure_attention_small",
+          "train_attention_scn_medium", "train_pure_scn_medium", "train_pure_attention_medium",
+          "train_attention_scn_hot"]
+
+
+def _load(blob):
+    kind = blob["kind"]
+    dec = build_decoder(kind, blob["dims"])
+    dec.load_state_dict(blob["state_dict"], strict=True)
+    dec.eval()
+    args = [blob[k].cuda() for k in ("encoder_out", "tags", "captions", "caption_lengths")]
+    return kind, dec, args
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("loss_path", ["torch_glue", "fused"])
+def test_fp32_matches_reference_golden(name, loss_path):
+    blob = load_golden(name)
+    with capdec.precision_scope("fp32"):
+        kind, dec, (enc, tags, caps, caplens) = _load(blob)
+        scores, caps_sorted, dl, alphas, sort_ind = call_forward(dec, kind, enc, tags, caps, caplens)
+        assert dl == blob["decode_lengths"]
+        assert torch.equal(sort_ind.cpu(), blob["sort_ind"])
+        assert torch.equal(caps_sorted.cpu(), blob["caps_sorted"])
+        assert rel_err(scores, blob["predictions"]) < FP32_TOL
+        if alphas is not None:
+            assert rel_err(alphas, blob["alphas"]) < FP32_TOL
+        # rows beyond each caption's length stay exactly zero (reference zero-inits the buffers)
+        for i, L in enumerate(dl):
+            assert scores[i, L:].abs().max().item() == 0 if L < scores.shape[1] else True
+        if loss_path == "fused":
+            loss, parts = dec.loss(scores, caps_sorted, dl, alphas, alpha_c=1.0)
+        else:
+            loss = torch_loss_glue(scores, caps_sorted, dl, alphas)
+        assert abs(loss.item() - blob["loss"].item()) < FP32_TOL * max(1.0, abs(blob["loss"].item()))
+        dec.zero_grad()
+        loss.backward()
+        worst = ("", 0.0)
+        for n, p in dec.named_parameters():
+            ref = blob["grads"][n]
+            assert p.grad is not None, n
+            if ref.abs().max().item() < 1e-7:      # full_att.bias: mathematically zero
+                assert p.grad.abs().max().item() < 1e-5, n
+                continue
+            e = rel_err(p.grad, ref)
+            if e > worst[1]:
+                worst = (n, e)
+        assert worst[1] < 2 * FP32_TOL, worst
+        assert torch.equal(dec.decode_step.bias_ih.grad, dec.decode_step.bias_hh.grad)
+
+
+@pytest.mark.parametrize("name", ["train_attention_scn_medium", "train_pure_scn_medium",
+                                  "train_pure_attention_medium"])
+def test_bf16_within_tolerance(name):
+    blob = load_golden(name)
+    with capdec.precision_scope("bf16"):
+        kind, dec, (enc, tags, caps, caplens) = _load(blob)
+        scores, caps_sorted, dl, alphas, sort_ind = call_forward(dec, kind, enc, tags, caps, caplens)
+        assert rel_err(scores, blob["predictions"]) < BF16_TOL
+        if alphas is not None:
+            assert rel_err(alphas, blob["alphas"]) < BF16_TOL
+        loss, _ = dec.loss(scores, caps_sorted, dl, alphas)
+        assert abs(loss.item() - blob["loss"].item()) < BF16_TOL * abs(blob["loss"].item())
+        dec.zero_grad()
+        loss.backward()
+        for n, p in dec.named_parameters():
+            ref = blob["grads"][n]
+            if ref.abs().max().item() < 1e-7:
+                continue
+            assert rel_err(p.grad, ref) < 0.1, n     # loose: bf16 operands through T steps
+
+
+@pytest.mark.parametrize("kind", [O.ATTENTION_SCN, O.PURE_SCN, O.PURE_ATTENTION])
+def test_fp32_full_width_matches_oracle(kind):
+    """Reference dims (512/2048/1000, V=10k) at a batch the CPU oracle finishes in seconds."""
+    dims = dict(A=512, M=512, D=512, F=512, S=1000, V=10000, E=2048)
+    B = 4
+    lengths = [9, 5, 12, 3]
+    enc, tags, caps, caplens = O.synthetic_batch(B, dims["V"], seed=3, lengths=lengths)
+    with capdec.precision_scope("fp32"):
+        torch.manual_seed(0)
+        dec = build_decoder(kind, dims).eval()
+        sd = {k: v.detach().cpu() for k, v in dec.state_dict().items()}
+        scores, caps_sorted, dl, alphas, sort_ind = call_forward(dec, kind, enc.cuda(), tags.cuda(),
+                                                                 caps.cuda(), caplens.cuda())
+        ref = oracle_run(kind, sd, enc, tags, caps, caplens, sort_ind=sort_ind)
+        assert dl == ref["decode_lengths"]
+        assert rel_err(scores, ref["scores"]) < FP32_TOL
+        if alphas is not None:
+            assert rel_err(alphas, ref["alphas"]) < FP32_TOL
+        loss, _ = dec.loss(scores, caps_sorted, dl, alphas)
+        assert abs(loss.item() - ref["loss"].item()) < FP32_TOL * abs(ref["loss"].item())
+        loss.backward()
+        for n, p in dec.named_parameters():
+            g = ref["grads"][n]
+            if g.abs().max().item() < 1e-9:
+                continue
+            assert rel_err(p.grad, g) < 2 * FP32_TOL, n
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_properties(precision):
+    """BASELINE config 3 per-GPU shape (B=32, T=50, V=10k): size-independent properties."""
+    dims = dict(A=512, M=512, D=512, F=512, S=1000, V=10000, E=2048)
+    B = 32
+    lengths = O.tie_free_lengths(B)
+    enc, tags, caps, caplens = O.synthetic_batch(B, dims["V"], seed=5, lengths=lengths)
+    with capdec.precision_scope(precision):
+        torch.manual_seed(0)
+        dec = build_decoder(O.ATTENTION_SCN, dims).eval()
+        args = [t.cuda() for t in (enc, tags, caps, caplens)]
+        scores, caps_sorted, dl, alphas, sort_ind = dec(*args)
+        assert dl == sorted([l - 1 for l in lengths], reverse=True)
+        for i, L in enumerate(dl):
+            if L < scores.shape[1]:
+                assert scores[i, L:].abs().max().item() == 0
+                assert alphas[i, L:].abs().max().item() == 0
+            assert (alphas[i, :L].sum(-1) - 1).abs().max().item() < 1e-4
+        assert torch.isfinite(scores).all()
+        # tags are NOT permuted with the captions (reference quirk)
+        scores2 = dec(args[0], args[1][sort_ind], args[2], args[3])[0]
+        assert (scores2 - scores).abs().max().item() > 0
+        # determinism of the whole forward
+        scores3 = dec(*args)[0]
+        assert torch.equal(scores3, scores)
+        loss, parts = dec.loss(scores, caps_sorted, dl, alphas)
+        loss.backward()
+        assert torch.equal(dec.decode_step.bias_ih.grad, dec.decode_step.bias_hh.grad)
+        emb_g = dec.embedding.weight.grad
+        used = torch.zeros(dims["V"], dtype=torch.bool, device="cuda")
+        for i, L in enumerate(dl):
+            used[caps_sorted[i, :L]] = True
+        assert emb_g[~used].abs().max().item() == 0      # SURVEY §4 invariant 5
+        assert emb_g[used].abs().sum().item() > 0
+        for n, p in dec.named_parameters():
+            assert torch.isfinite(p.grad).all(), n
+
+
+def test_dropout_training_mode_runs_and_is_seeded():
+    dims = dict(A=64, M=48, D=64, F=56, S=100, V=203, E=128)
+    enc, tags, caps, caplens = O.synthetic_batch(8, dims["V"], seed=9, side=14, E=dims["E"], S=dims["S"],
+                                                 max_len=20, lengths=[20, 7, 13, 5, 18, 9, 3, 16])
+    with capdec.precision_scope("fp32"):
+        torch.manual_seed(0)
+        dec = build_decoder(O.ATTENTION_SCN, dims).train()
+        args = [t.cuda() for t in (enc, tags, caps, caplens)]
+        torch.manual_seed(1)
+        s1 = dec(*args)[0]
+        torch.manual_seed(1)
+        s2 = dec(*args)[0]
+        torch.manual_seed(2)
+        s3 = dec(*args)[0]
+        assert torch.equal(s1, s2) and not torch.equal(s1, s3)
+        dec.eval()
+        s_eval = dec(*args)[0]
+        assert not torch.equal(s_eval, s1)
+        dec.train()
+        out = dec(*args)
+        loss, _ = dec.loss(out[0], out[1], out[2], out[3])
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() for p in dec.parameters())
+
+
+def test_state_dict_round_trip_and_strided_encoder_features():
+    """state_dict keys/shapes are the reference's; NCHW-physical encoder views are accepted (App. C-22)."""
+    blob = load_golden("train_attention_scn_medium")
+    with capdec.precision_scope("fp32"):
+        kind, dec, (enc, tags, caps, caplens) = _load(blob)
+        assert list(dec.state_dict().keys()) == list(blob["state_dict"].keys())
+        ref_scores = dec(enc, tags, caps, caplens)[0]
+        nchw = enc.permute(0, 3, 1, 2).contiguous()          # what the ResNet trunk really produces
+        view = nchw.permute(0, 2, 3, 1)                      # the reference encoder's permuted view
+        assert not view.is_contiguous()
+        got = dec(view, tags, caps, caplens)[0]
+        assert torch.equal(got, ref_scores)

@@ -1,0 +1,135 @@
+"""GPU parity tests of the single kernels behind the C ABI (GEMM engines, attention step,
+SCN cell step) against torch / the oracle."""
+import pytest
+import torch
+
+from oracle import capdec_oracle as O
+from gpu_util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_gemm(X, W, bias=None, addm=None):
+    out = X.double().cpu() @ W.double().cpu().transpose(-1, -2)
+    if bias is not None:
+        out = out + bias.double().cpu()
+    if addm is not None:
+        out = out + addm.double().cpu()
+    return out
+
+
+SHAPES = [(32, 128, 64), (5, 37, 40), (32, 2048, 512), (70, 300, 1000), (200, 130, 72), (1, 8, 8),
+          (1600, 1000, 512), (33, 4608, 512)]
+
+
+@pytest.mark.parametrize("rows,N,K", SHAPES)
+def test_gemm_simt_fp32(rows, N, K):
+    from capdec import functional as CF
+    g = torch.Generator(device="cuda").manual_seed(rows * 7 + N)
+    X = torch.randn(rows, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    addm = torch.randn(rows, N, device="cuda", generator=g)
+    out = CF.gemm(X, W, bias=bias, addm=addm, precision="fp32")
+    assert rel_err(out, _ref_gemm(X, W, bias, addm)) < 2e-6
+
+
+def _pad_k(t, mult=8):
+    """bf16 operand with a pitch that is a multiple of 8 elements (16 bytes) as TMA needs."""
+    K = t.shape[-1]
+    Kp = (K + mult - 1) // mult * mult
+    buf = torch.zeros(*t.shape[:-1], Kp, dtype=torch.bfloat16, device=t.device)
+    buf[..., :K] = t.to(torch.bfloat16)
+    return buf[..., :K]
+
+
+@pytest.mark.parametrize("rows,N,K", SHAPES)
+def test_gemm_tc_bf16(rows, N, K):
+    from capdec import functional as CF
+    g = torch.Generator(device="cuda").manual_seed(rows * 11 + N)
+    X = _pad_k(torch.randn(rows, K, device="cuda", generator=g))
+    W = _pad_k(torch.randn(N, K, device="cuda", generator=g))
+    bias = torch.randn(N, device="cuda", generator=g)
+    addm = torch.randn(rows, N, device="cuda", generator=g)
+    out = CF.gemm(X, W, bias=bias, addm=addm, precision="bf16")
+    # inputs are exactly representable; only the fp32 accumulation order differs
+    assert rel_err(out, _ref_gemm(X.float(), W.float(), bias, addm)) < 1e-5
+    out_h = CF.gemm(X, W, bias=bias, precision="bf16", out_ft=True)
+    assert out_h.dtype == torch.bfloat16
+    assert rel_err(out_h.float(), _ref_gemm(X.float(), W.float(), bias)) < 1e-2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gemm_batched(precision):
+    from capdec import functional as CF
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ft = torch.float32 if precision == "fp32" else torch.bfloat16
+    X = torch.randn(4, 24, 96, device="cuda", generator=g).to(ft)
+    W = torch.randn(4, 64, 96, device="cuda", generator=g).to(ft)
+    out = CF.gemm(X, W, precision=precision)
+    assert out.shape == (4, 24, 64)
+    assert rel_err(out, _ref_gemm(X.float(), W.float())) < 1e-5
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("rows,P,E,A", [(32, 196, 2048, 512), (3, 9, 40, 24), (7, 196, 128, 64),
+                                        (130, 49, 256, 128)])
+def test_attention_step_matches_oracle(precision, tol, rows, P, E, A):
+    from capdec import functional as CF
+    D = 32
+    g = torch.Generator().manual_seed(rows + P)
+    p = {"attention.encoder_att.weight": torch.randn(A, E, generator=g) / E ** 0.5,
+         "attention.encoder_att.bias": torch.randn(A, generator=g) * 0.1,
+         "attention.decoder_att.weight": torch.randn(A, D, generator=g) / D ** 0.5,
+         "attention.decoder_att.bias": torch.randn(A, generator=g) * 0.1,
+         "attention.full_att.weight": torch.randn(1, A, generator=g) / A ** 0.5 * 4,
+         "attention.full_att.bias": torch.randn(1, generator=g)}
+    enc = torch.randn(rows, P, E, generator=g).relu_()
+    h = torch.randn(rows, D, generator=g)
+    beta_pre = torch.randn(rows, E, generator=g)
+    ft = torch.float32 if precision == "fp32" else torch.bfloat16
+    if precision == "bf16":      # compare against the oracle on the rounded features
+        enc = enc.to(ft).float()
+    awe_ref, alpha_ref = O.soft_attention({k: v.double() for k, v in p.items()}, enc.double(), h.double())
+    att1 = torch.nn.functional.linear(enc, p["attention.encoder_att.weight"],
+                                      p["attention.encoder_att.bias"])
+    att2 = torch.nn.functional.linear(h, p["attention.decoder_att.weight"],
+                                      p["attention.decoder_att.bias"])
+    g1 = torch.cat([att2, beta_pre], dim=1).cuda().contiguous()
+    z, alpha, awe = CF.attention_step(att1.to(ft).cuda().contiguous(), enc.to(ft).cuda().contiguous(), g1, A,
+                                      p["attention.full_att.weight"].reshape(-1).cuda().contiguous(),
+                                      p["attention.full_att.bias"].cuda(), precision=precision)
+    assert rel_err(alpha, alpha_ref) < tol
+    assert rel_err(awe, awe_ref) < tol
+    z_ref = torch.sigmoid(beta_pre.double()) * awe_ref
+    assert rel_err(z.float(), z_ref) < max(tol, 1e-5 if precision == "fp32" else 1e-2)
+    assert (alpha.sum(dim=1) - 1).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("rows,X,D,F,S", [(32, 2560, 512, 512, 1000), (5, 56, 32, 24, 12)])
+def test_scn_cell_step_matches_oracle(precision, tol, rows, X, D, F, S):
+    from capdec import functional as CF
+    g = torch.Generator().manual_seed(rows)
+    bound = 1.0 / D ** 0.5
+    names = ["weight_ia", "weight_ib", "weight_ic", "weight_ha", "weight_hb", "weight_hc", "bias_ih",
+             "bias_hh"]
+    shapes = [(X, 4 * F), (S, 4 * F), (D, 4 * F), (D, 4 * F), (S, 4 * F), (D, 4 * F), (4 * D,), (4 * D,)]
+    p = {"c." + n: (torch.rand(s, generator=g) * 2 - 1) * bound for n, s in zip(names, shapes)}
+    x = torch.randn(rows, X, generator=g) * 0.5
+    s = torch.rand(rows, S, generator=g)
+    h = torch.randn(rows, D, generator=g) * 0.5
+    c = torch.randn(rows, D, generator=g)
+    pd = {k: v.double() for k, v in p.items()}
+    h_ref, c_ref = O.scn_cell(pd, "c.", x.double(), s.double(), h.double(), c.double())
+    weights = [p["c." + n].cuda() for n in names]
+    h_out, c_out = CF.scn_cell_step(weights, x.cuda(), s.cuda(), h.cuda(), c.cuda(), precision=precision)
+    assert rel_err(h_out, h_ref) < tol
+    assert rel_err(c_out, c_ref) < tol
+
+
+def test_ops_refuse_cpu_tensors():
+    from capdec import functional as CF
+    from capdec._lib import CapdecError
+    with pytest.raises(CapdecError):
+        CF.gemm(torch.zeros(4, 8), torch.zeros(4, 8), precision="fp32")
