@@ -88,6 +88,8 @@ typedef struct CapdecParams {
 
 int capdec_version(void);
 const char* capdec_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py `gpu_launches`). */
+unsigned long long capdec_launch_count(void);
 
 /* One-time per-process/device setup (function attributes, driver entry points).
  * Idempotent and thread-safe.  Returns CAPDEC_ERR_UNSUPPORTED off sm_100. */
@@ -168,12 +170,14 @@ int capdec_beam_search(const CapdecDims* dims, const CapdecParams* params,
 
 /* out[rows,N] (ldo) = X[rows,K] (ldx) . W[N,K]^T (ldw) (+ bias[N]) (+ addm[rows,N] (ldadd)).
  * precision FP32: X,W fp32, SIMT FFMA engine.  BF16: X,W bf16, tcgen05+TMA engine.
- * out_ft != 0: out is written in the feature type, else fp32.  batch>1: element strides. */
+ * out_ft != 0: out is written in the feature type, else fp32.  batch>1: element strides.
+ * splitk (tcgen05 engine only): 0 = off, -1 = auto, n = n K-slices reduced with fp32 atomics
+ * into `out`, which the caller must then have PRE-INITIALISED (zeros, or addm aliased to out). */
 int capdec_gemm(int precision, const void* X, int64_t ldx, const void* W, int64_t ldw,
                 void* out, int64_t ldo, int out_ft, const float* bias,
                 const float* addm, int64_t ldadd,
                 int rows, int N, int K, int batch, int64_t sX, int64_t sW, int64_t sO,
-                void* stream);
+                int splitk, void* stream);
 
 /* Attention.forward on prepared features: att1 (G,P,A) / enc (G,P,E) in the feature type,
  * g1 (rows, ldg) fp32 with att2 at column 0 and the f_beta pre-activation at column

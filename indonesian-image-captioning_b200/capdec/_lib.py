@@ -36,6 +36,7 @@ SIGNATURES = {
     "capdec_version": (_i, []),
     "capdec_last_error": (C.c_char_p, []),
     "capdec_init": (_i, []),
+    "capdec_launch_count": (C.c_ulonglong, []),
     "capdec_workspace_bytes": (_sz, [C.POINTER(Dims), _i]),
     "capdec_forward_train": (_i, [C.POINTER(Dims), C.POINTER(Params), _vp, _i64, _i64, _i64, _vp, _vp,
                                   _vp, _vp, _f, _u64, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -48,7 +49,7 @@ SIGNATURES = {
     "capdec_beam_search": (_i, [C.POINTER(Dims), C.POINTER(Params), _vp, _vp, _i, _i, _i, C.c_int32,
                                 C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "capdec_gemm": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i64,
-                         _i64, _i64, _vp]),
+                         _i64, _i64, _i, _vp]),
     "capdec_attention_step": (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i,
                                    _i, _i, _i, _vp]),
     "capdec_scn_cell_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),

@@ -109,7 +109,13 @@ class DecoderTrainFn(torch.autograd.Function):
         tags, caps_sorted, alphas = ctx.saved_tensors
         dev = caps_sorted.device
         params = ctx.param_tensors
-        grads = [torch.empty_like(p) for p in params]
+        # one flat buffer, per-parameter views: the data-parallel helper all-reduces it in place
+        flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+        grads, off = [], 0
+        for p in params:
+            grads.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        meta["flat_grads"] = flat
         fused = meta.get("fused_dlogits")      # set by FusedLossFn: gradient already in feature type
         d_logits_ft = None
         if fused is not None and fused.get("buf") is not None:
@@ -238,7 +244,7 @@ def _ft_dtype(precision):
     return torch.bfloat16 if precision_code(precision) == 1 else torch.float32
 
 
-def gemm(X, W, bias=None, addm=None, out_ft=False, precision=None):
+def gemm(X, W, bias=None, addm=None, out_ft=False, precision=None, splitk=0, out=None):
     """out[r,n] = sum_k X[r,k] W[n,k] (+bias[n]) (+addm[r,n]) through the selected engine.
     X (rows,K) / W (N,K) must already be in the engine's operand type with 16-byte pitch."""
     lib = _lib.load()
@@ -249,8 +255,10 @@ def gemm(X, W, bias=None, addm=None, out_ft=False, precision=None):
     batch = X.shape[0] if X.dim() == 3 else 1
     rows, K = X.shape[-2], X.shape[-1]
     N = W.shape[-2]
-    out = torch.empty((batch, rows, N) if X.dim() == 3 else (rows, N),
-                      dtype=ft if out_ft else torch.float32, device=X.device)
+    if out is None:
+        make = torch.zeros if splitk else torch.empty      # split-K accumulates into the output
+        out = make((batch, rows, N) if X.dim() == 3 else (rows, N),
+                   dtype=ft if out_ft else torch.float32, device=X.device)
     sX = X.stride(0) if X.dim() == 3 else 0
     sW = W.stride(0) if W.dim() == 3 else 0
     sO = out.stride(0) if X.dim() == 3 else 0
@@ -258,7 +266,7 @@ def gemm(X, W, bias=None, addm=None, out_ft=False, precision=None):
         rc = lib.capdec_gemm(precision_code(prec), _lib.ptr(X), X.stride(-2), _lib.ptr(W), W.stride(-2),
                              _lib.ptr(out), out.stride(-2), 1 if out_ft else 0, _lib.ptr(bias),
                              _lib.ptr(addm), addm.stride(-2) if addm is not None else 0, rows, N, K,
-                             batch, sX, sW, sO, _stream())
+                             batch, sX, sW, sO, splitk, _stream())
     _lib.check(rc, "capdec_gemm")
     return out
 

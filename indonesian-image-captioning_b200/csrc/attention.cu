@@ -12,10 +12,12 @@
 // enc[b] (P*E) once per step.  One thread-block CLUSTER handles one row: the CL CTAs of
 // the cluster split the P pixels for the score phase and the E channels for the weighted
 // sum; the 196 scores are exchanged through distributed shared memory (push model, one
-// cluster barrier), so a row's features are read exactly once while B*CL CTAs keep the
-// 148 SMs busy even at B = 32.  All global feature loads are 16-byte, coalesced,
-// L1-bypassing; reductions over the attention dim and the softmax use warp shuffles.
+// cluster barrier), so a row's features are read exactly once while B*CL CTAs (>= 2 per SM
+// at B = 32) keep enough 16-byte loads in flight to cover the L2/HBM latency.  All global
+// feature loads are coalesced and L1-bypassing; reductions over the attention dim and the
+// softmax use warp shuffles.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -28,9 +30,8 @@ namespace {
 
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
-constexpr int NCH = 4;        // max 16-byte chunks per lane along A (score phase)
-constexpr int NCE = 4;        // max 16-byte chunks per lane along the CTA's E slice (bwd)
 constexpr int CL_MAX = 8;
+constexpr int PXB = 4;        // pixels a warp keeps in flight per iteration
 
 struct FwdArgs {
   const void* att1; const void* enc; const float* g1; int64_t ldg; int beta_col;
@@ -38,7 +39,8 @@ struct FwdArgs {
   void* z_out; int64_t ldz; float* awe_out; int rows, rows_per_map, P, E, A;
 };
 
-template <typename FT>
+// NCH = 16-byte chunks per lane along the attention dim: A <= 32 * VEC * NCH
+template <typename FT, int NCH>
 __global__ void __launch_bounds__(NTHREADS)
 attn_fwd_kernel(FwdArgs a) {
   constexpr int VEC = FTraits<FT>::VEC;
@@ -76,37 +78,31 @@ attn_fwd_kernel(FwdArgs a) {
     }
   }
   const float bf = a.b_f[0];
-  for (int p = p_begin + warp; p < p_end; p += 2 * NWARPS) {
-    const int p2 = p + NWARPS;
-    const bool has2 = p2 < p_end;
-    uint4 v1[NCH], v2[NCH];
+  for (int p = p_begin + warp; p < p_end; p += PXB * NWARPS) {
+    uint4 v[PXB][NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int a0 = (c * 32 + lane) * VEC;
-      v1[c] = make_uint4(0, 0, 0, 0);
-      v2[c] = make_uint4(0, 0, 0, 0);
-      if (a0 < A) {
-        v1[c] = ld_stream16(att1 + (int64_t)p * A + a0);
-        if (has2) v2[c] = ld_stream16(att1 + (int64_t)p2 * A + a0);
+    for (int i = 0; i < PXB; ++i) {
+      const int pi = p + i * NWARPS;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int a0 = (c * 32 + lane) * VEC;
+        v[i][c] = make_uint4(0, 0, 0, 0);
+        if (a0 < A && pi < p_end) v[i][c] = ld_stream16(att1 + (int64_t)pi * A + a0);
       }
     }
-    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      float f1[VEC], f2[VEC];
-      unpack16(v1[c], f1, FT());
-      unpack16(v2[c], f2, FT());
+    for (int i = 0; i < PXB; ++i) {
+      const int pi = p + i * NWARPS;
+      float s = 0.f;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        s1 = fmaf(wf[c][v], fmaxf(f1[v] + att2[c][v], 0.f), s1);
-        s2 = fmaf(wf[c][v], fmaxf(f2[v] + att2[c][v], 0.f), s2);
+      for (int c = 0; c < NCH; ++c) {
+        float f[VEC];
+        unpack16(v[i][c], f, FT());
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s = fmaf(wf[c][k], fmaxf(f[k] + att2[c][k], 0.f), s);
       }
-    }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) {
-      sc[p] = s1 + bf;
-      if (has2) sc[p2] = s2 + bf;
+      s = warp_sum(s);
+      if (lane == 0 && pi < p_end) sc[pi] = s + bf;
     }
   }
   __syncthreads();
@@ -150,6 +146,7 @@ attn_fwd_kernel(FwdArgs a) {
   const int groups = NTHREADS / ncolPass;
   const int grp = tid / ncolPass;
   const int cip = tid % ncolPass;
+  constexpr int UNR = 8;
   for (int cb = 0; cb < ncol; cb += ncolPass) {
     const int col = cb + cip;
     const bool active = grp < groups && col < ncol;
@@ -159,25 +156,18 @@ attn_fwd_kernel(FwdArgs a) {
     if (active) {
       const FT* src = enc + e_begin + col * VEC;
       int p = grp;
-      for (; p + 3 * groups < P; p += 4 * groups) {
-        uint4 q0 = ld_stream16(src + (int64_t)p * E);
-        uint4 q1 = ld_stream16(src + (int64_t)(p + groups) * E);
-        uint4 q2 = ld_stream16(src + (int64_t)(p + 2 * groups) * E);
-        uint4 q3 = ld_stream16(src + (int64_t)(p + 3 * groups) * E);
-        const float w0 = al[p], w1 = al[p + groups], w2 = al[p + 2 * groups], w3 = al[p + 3 * groups];
-        float f[VEC];
-        unpack16(q0, f, FT());
+      for (; p + (UNR - 1) * groups < P; p += UNR * groups) {
+        uint4 q[UNR];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(w0, f[v], acc[v]);
-        unpack16(q1, f, FT());
+        for (int u = 0; u < UNR; ++u) q[u] = ld_stream16(src + (int64_t)(p + u * groups) * E);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(w1, f[v], acc[v]);
-        unpack16(q2, f, FT());
+        for (int u = 0; u < UNR; ++u) {
+          const float w = al[p + u * groups];
+          float f[VEC];
+          unpack16(q[u], f, FT());
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(w2, f[v], acc[v]);
-        unpack16(q3, f, FT());
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(w3, f[v], acc[v]);
+          for (int v = 0; v < VEC; ++v) acc[v] = fmaf(w, f[v], acc[v]);
+        }
       }
       for (; p < P; p += groups) {
         uint4 q0 = ld_stream16(src + (int64_t)p * E);
@@ -244,7 +234,8 @@ struct BwdArgs {
   int rows, P, E, A;
 };
 
-template <typename FT>
+// NCE = 16-byte chunks per lane along the CTA's channel slice: E/CL <= 32 * VEC * NCE
+template <typename FT, int NCH, int NCE>
 __global__ void __launch_bounds__(NTHREADS)
 attn_bwd_kernel(BwdArgs a) {
   constexpr int VEC = FTraits<FT>::VEC;
@@ -299,37 +290,31 @@ attn_bwd_kernel(BwdArgs a) {
 
   // ---- phase B: partial dalpha_p = enc[p, slice] . dawe[slice]  (warp per pixel) ----
   float* my_part = part + rank * Ppad;
-  for (int p = warp; p < P; p += 2 * NWARPS) {
-    const int p2 = p + NWARPS;
-    const bool has2 = p2 < P;
-    uint4 v1[NCE], v2[NCE];
+  for (int p = warp; p < P; p += PXB * NWARPS) {
+    uint4 v[PXB][NCE];
 #pragma unroll
-    for (int c = 0; c < NCE; ++c) {
-      const int col = c * 32 + lane;
-      v1[c] = make_uint4(0, 0, 0, 0);
-      v2[c] = make_uint4(0, 0, 0, 0);
-      if (col < ncol) {
-        v1[c] = ld_stream16(enc + (int64_t)p * E + e_begin + col * VEC);
-        if (has2) v2[c] = ld_stream16(enc + (int64_t)p2 * E + e_begin + col * VEC);
+    for (int i = 0; i < PXB; ++i) {
+      const int pi = p + i * NWARPS;
+#pragma unroll
+      for (int c = 0; c < NCE; ++c) {
+        const int col = c * 32 + lane;
+        v[i][c] = make_uint4(0, 0, 0, 0);
+        if (col < ncol && pi < P) v[i][c] = ld_stream16(enc + (int64_t)pi * E + e_begin + col * VEC);
       }
     }
-    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCE; ++c) {
-      float f1[VEC], f2[VEC];
-      unpack16(v1[c], f1, FT());
-      unpack16(v2[c], f2, FT());
+    for (int i = 0; i < PXB; ++i) {
+      const int pi = p + i * NWARPS;
+      float s = 0.f;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        s1 = fmaf(f1[v], dawe[c][v], s1);
-        s2 = fmaf(f2[v], dawe[c][v], s2);
+      for (int c = 0; c < NCE; ++c) {
+        float f[VEC];
+        unpack16(v[i][c], f, FT());
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s = fmaf(f[k], dawe[c][k], s);
       }
-    }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) {
-      my_part[p] = s1;
-      if (has2) my_part[p2] = s2;
+      s = warp_sum(s);
+      if (lane == 0 && pi < P) my_part[pi] = s;
     }
   }
   __syncthreads();
@@ -382,29 +367,46 @@ attn_bwd_kernel(BwdArgs a) {
     }
   }
   float* dA = a.dAtt1 + (int64_t)row * P * A;
-  for (int p = p_begin + warp; p < p_end; p += NWARPS) {
-    const float dep = de[p];
+  for (int p = p_begin + warp; p < p_end; p += 2 * NWARPS) {
+    const int p2 = p + NWARPS;
+    const bool has2 = p2 < p_end;
+    uint4 q1[NCH], q2[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int a0 = (c * 32 + lane) * VEC;
+      q1[c] = make_uint4(0, 0, 0, 0);
+      q2[c] = make_uint4(0, 0, 0, 0);
       if (a0 < A) {
-        uint4 q = ld_stream16(att1 + (int64_t)p * A + a0);
-        float f[VEC], dr[VEC];
-        unpack16(q, f, FT());
+        q1[c] = ld_stream16(att1 + (int64_t)p * A + a0);
+        if (has2) q2[c] = ld_stream16(att1 + (int64_t)p2 * A + a0);
+      }
+    }
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          const float pre = f[v] + att2[c][v];
-          const float on = pre > 0.f ? 1.f : 0.f;
-          dr[v] = dep * wf[c][v] * on;
-          dacc[c][v] += dr[v];
-          wacc[c][v] = fmaf(dep, pre * on, wacc[c][v]);
-        }
-        float* d = dA + (int64_t)p * A + a0;
+    for (int i = 0; i < 2; ++i) {
+      if (i == 1 && !has2) break;
+      const int pi = i == 0 ? p : p2;
+      const float dep = de[pi];
 #pragma unroll
-        for (int v = 0; v < VEC; v += 4) {
-          float4 o = *reinterpret_cast<float4*>(d + v);
-          o.x += dr[v]; o.y += dr[v + 1]; o.z += dr[v + 2]; o.w += dr[v + 3];
-          *reinterpret_cast<float4*>(d + v) = o;
+      for (int c = 0; c < NCH; ++c) {
+        const int a0 = (c * 32 + lane) * VEC;
+        if (a0 < A) {
+          float f[VEC], dr[VEC];
+          unpack16(i == 0 ? q1[c] : q2[c], f, FT());
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const float pre = f[v] + att2[c][v];
+            const float on = pre > 0.f ? 1.f : 0.f;
+            dr[v] = dep * wf[c][v] * on;
+            dacc[c][v] += dr[v];
+            wacc[c][v] = fmaf(dep, pre * on, wacc[c][v]);
+          }
+          float* d = dA + (int64_t)pi * A + a0;
+#pragma unroll
+          for (int v = 0; v < VEC; v += 4) {
+            float4 o = *reinterpret_cast<float4*>(d + v);
+            o.x += dr[v]; o.y += dr[v + 1]; o.z += dr[v + 2]; o.w += dr[v + 3];
+            *reinterpret_cast<float4*>(d + v) = o;
+          }
         }
       }
     }
@@ -466,23 +468,56 @@ int launch_cluster(KernelT kernel, const ArgsT& args, int rows, int CL, size_t s
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   CAPDEC_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, args));
+  count_launch();
   return CAPDEC_OK;
 }
 
-// cluster size: enough CTAs to cover the 148 SMs, bounded by divisibility / register budget
+int env_cluster() {
+  static int v = [] {
+    const char* s = getenv("CAPDEC_ATTN_CLUSTER");
+    return s ? atoi(s) : 0;
+  }();
+  return v;
+}
+
+// cluster size: >= 2 CTAs per SM over the 148 SMs when the batch is small, bounded by the
+// divisibility of the channel slice; CAPDEC_ATTN_CLUSTER overrides (tuning sweeps)
 int pick_cluster(int rows, int E, int vec, int min_cl) {
   int cl = min_cl;
-  while (cl < CL_MAX && rows * cl < 120 && (E % (2 * cl * vec)) == 0) cl *= 2;
+  const int want = env_cluster();
+  if (want > 0) {
+    while (cl < want && cl < CL_MAX && (E % (2 * cl * vec)) == 0) cl *= 2;
+    return cl;
+  }
+  while (cl < CL_MAX && rows * cl < 2 * 148 - 40 && (E % (2 * cl * vec)) == 0) cl *= 2;
   return cl;
+}
+
+template <typename FT, int NCH>
+int launch_bwd(const BwdArgs& a, int CL, int nce, size_t smem, cudaStream_t st) {
+  if (nce <= 1) return launch_cluster(attn_bwd_kernel<FT, NCH, 1>, a, a.rows, CL, smem, st);
+  if (nce <= 2) return launch_cluster(attn_bwd_kernel<FT, NCH, 2>, a, a.rows, CL, smem, st);
+  return launch_cluster(attn_bwd_kernel<FT, NCH, 4>, a, a.rows, CL, smem, st);
+}
+
+template <typename FT, int NCH>
+int set_bwd_attr() {
+  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<FT, NCH, 1>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<FT, NCH, 2>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<FT, NCH, 4>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  return CAPDEC_OK;
 }
 
 }  // namespace
 
 int attention_init() {
-  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<float>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<bf16>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CAPDEC_TRY((set_bwd_attr<float, 2>()));
+  CAPDEC_TRY((set_bwd_attr<float, 4>()));
+  CAPDEC_TRY((set_bwd_attr<bf16, 2>()));
+  CAPDEC_TRY((set_bwd_attr<bf16, 4>()));
   return CAPDEC_OK;
 }
 
@@ -492,14 +527,18 @@ int attention_fwd(int precision, const void* att1, const void* enc, const float*
                   int rows_per_map, int P, int E, int A, cudaStream_t st) {
   if (rows <= 0) return CAPDEC_OK;
   const int vec = precision == CAPDEC_BF16 ? 8 : 4;
-  CAPDEC_REQUIRE(E % vec == 0 && A % vec == 0 && A <= 32 * vec * NCH, CAPDEC_ERR_BAD_SHAPE,
-                 "attention: need E,A multiples of %d and A <= %d (E=%d A=%d)", vec, 32 * vec * NCH, E, A);
+  CAPDEC_REQUIRE(E % vec == 0 && A % vec == 0 && A <= 32 * vec * 4, CAPDEC_ERR_BAD_SHAPE,
+                 "attention: need E,A multiples of %d and A <= %d (E=%d A=%d)", vec, 32 * vec * 4, E, A);
   FwdArgs a{att1, enc, g1, ldg, beta_col, w_f, b_f, alpha_out, alpha_stride, z_out, ldz, awe_out,
             rows, rows_per_map, P, E, A};
   const int CL = pick_cluster(rows, E, vec, 1);
-  if (precision == CAPDEC_BF16)
-    return launch_cluster(attn_fwd_kernel<bf16>, a, rows, CL, fwd_smem(P), st);
-  return launch_cluster(attn_fwd_kernel<float>, a, rows, CL, fwd_smem(P), st);
+  const bool small = A <= 32 * vec * 2;
+  if (precision == CAPDEC_BF16) {
+    if (small) return launch_cluster(attn_fwd_kernel<bf16, 2>, a, rows, CL, fwd_smem(P), st);
+    return launch_cluster(attn_fwd_kernel<bf16, 4>, a, rows, CL, fwd_smem(P), st);
+  }
+  if (small) return launch_cluster(attn_fwd_kernel<float, 2>, a, rows, CL, fwd_smem(P), st);
+  return launch_cluster(attn_fwd_kernel<float, 4>, a, rows, CL, fwd_smem(P), st);
 }
 
 int attention_bwd(int precision, const void* att1, const void* enc, const float* g1, int64_t ldg,
@@ -509,21 +548,26 @@ int attention_bwd(int precision, const void* att1, const void* enc, const float*
                   float* dbf_part, int rows, int P, int E, int A, cudaStream_t st) {
   if (rows <= 0) return CAPDEC_OK;
   const int vec = precision == CAPDEC_BF16 ? 8 : 4;
-  CAPDEC_REQUIRE(E % vec == 0 && A % vec == 0 && A <= 32 * vec * NCH && beta_col >= 0,
+  CAPDEC_REQUIRE(E % vec == 0 && A % vec == 0 && A <= 32 * vec * 4 && beta_col >= 0,
                  CAPDEC_ERR_BAD_SHAPE, "attention bwd: unsupported dims E=%d A=%d", E, A);
-  // the E slice of one CTA must fit the per-lane register cache: E/CL/vec <= 32*NCE
+  // the E slice of one CTA must fit the per-lane register cache: E/CL/vec <= 32*4
   int min_cl = 1;
-  while (min_cl < CL_MAX && (E / min_cl) > 32 * NCE * vec) min_cl *= 2;
-  CAPDEC_REQUIRE((E / min_cl) <= 32 * NCE * vec && E % (min_cl * vec) == 0, CAPDEC_ERR_BAD_SHAPE,
+  while (min_cl < CL_MAX && (E / min_cl) > 32 * 4 * vec) min_cl *= 2;
+  CAPDEC_REQUIRE((E / min_cl) <= 32 * 4 * vec && E % (min_cl * vec) == 0, CAPDEC_ERR_BAD_SHAPE,
                  "attention bwd: E=%d too large / not divisible", E);
   BwdArgs a{att1, enc, g1, ldg, beta_col, w_f, alpha, alpha_stride, dalpha_ext, dalpha_stride,
             dz, lddz, awe, dba, lddba, dAtt1, dwf_part, dbf_part, rows, P, E, A};
   const int CL = pick_cluster(rows, E, vec, min_cl);
+  const int nce = ceil_div(E / CL / vec, 32);
   const size_t smem = bwd_smem(P, A);
   CAPDEC_REQUIRE(smem <= 160 * 1024, CAPDEC_ERR_BAD_SHAPE, "attention bwd: smem %zu too large", smem);
-  if (precision == CAPDEC_BF16)
-    return launch_cluster(attn_bwd_kernel<bf16>, a, rows, CL, smem, st);
-  return launch_cluster(attn_bwd_kernel<float>, a, rows, CL, smem, st);
+  const bool small = A <= 32 * vec * 2;
+  if (precision == CAPDEC_BF16) {
+    if (small) return launch_bwd<bf16, 2>(a, CL, nce, smem, st);
+    return launch_bwd<bf16, 4>(a, CL, nce, smem, st);
+  }
+  if (small) return launch_bwd<float, 2>(a, CL, nce, smem, st);
+  return launch_bwd<float, 4>(a, CL, nce, smem, st);
 }
 
 }  // namespace capdec

@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" surface of libcapdec.so (see include/capdec.h).
 #include <stdarg.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -17,6 +18,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static std::once_flag g_init_once;
 static int g_init_rc = CAPDEC_OK;
@@ -48,6 +52,8 @@ extern "C" {
 
 int capdec_version(void) { return CAPDEC_VERSION; }
 const char* capdec_last_error(void) { return get_error(); }
+
+unsigned long long capdec_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int capdec_init(void) {
   std::call_once(g_init_once, [] { g_init_rc = do_init(); });
@@ -132,9 +138,10 @@ int capdec_beam_search(const CapdecDims* dims, const CapdecParams* params, const
 
 int capdec_gemm(int precision, const void* X, int64_t ldx, const void* W, int64_t ldw, void* out,
                 int64_t ldo, int out_ft, const float* bias, const float* addm, int64_t ldadd, int rows,
-                int N, int K, int batch, int64_t sX, int64_t sW, int64_t sO, void* stream) {
+                int N, int K, int batch, int64_t sX, int64_t sW, int64_t sO, int splitk, void* stream) {
   CAPDEC_TRY(capdec_init());
   GemmArgs a;
+  a.splitk = splitk;
   a.X = X; a.ldx = ldx; a.W = W; a.ldw = ldw; a.out = out; a.ldo = ldo; a.out_ft = out_ft;
   a.bias = bias; a.addm = addm; a.ldadd = ldadd; a.rows = rows; a.N = N; a.K = K;
   a.batch = batch < 1 ? 1 : batch; a.sX = sX; a.sW = sW; a.sO = sO;

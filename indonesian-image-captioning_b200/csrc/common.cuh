@@ -17,6 +17,7 @@ typedef __nv_bfloat16 bf16;
 // ---------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 const char* get_error();
+void count_launch();          // process-wide kernel-launch counter (capdec_launch_count)
 
 #define CAPDEC_CUDA_OK(expr)                                                        \
   do {                                                                              \
@@ -36,6 +37,7 @@ const char* get_error();
                         cudaGetErrorString(_e));                                    \
       return CAPDEC_ERR_CUDA;                                                       \
     }                                                                               \
+    capdec::count_launch();                                                         \
   } while (0)
 
 #define CAPDEC_TRY(expr)                                                            \
@@ -145,6 +147,9 @@ struct GemmArgs {
   const float* addm = nullptr; int64_t ldadd = 0;  // fp32 [rows, N] added in the epilogue (may alias out)
   int rows = 0, N = 0, K = 0;
   int rows_alloc = 0;                            // rows physically present in X (>= rows); 0 -> rows
+  int splitk = 0;                                // tcgen05 engine: 0 = off, -1 = auto, n = n slices.  The
+                                                 // output must then be PRE-INITIALISED (zero or the in-place
+                                                 // addend); the SIMT engine ignores this and overwrites.
   int batch = 1;                                 // grid.z
   int64_t sX = 0, sW = 0, sO = 0, sBias = 0, sAdd = 0;   // element strides per batch index
 };

@@ -118,7 +118,7 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
   }
   if (p->scn) {
     o.m = take(T * 4 * B * 2 * F * f);
-    o.pre = take(B * 4 * D * 4);
+    o.pre = take(R * 4 * D * 4);                     // per step: split-K GEMMs accumulate into zeroed slots
   }
   o.gates = take(R * 4 * D * 4);
   o.C = take((T + 1) * B * D * 4);
@@ -129,18 +129,18 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
   if (with_bwd) {
     o.dlogF = take(R * p->ldV * f);
     o.dHfc = take(R * D * 4);
-    o.dh_rec = take(B * D * 4);
+    o.dh_rec = take((T + 1) * B * D * 4);            // dhs[t] = d loss / d h_{t-1} from step t ; dhs[T] = 0
     o.dc = take(B * D * 4);
     o.dpre = take(R * 4 * D * f);
     if (p->scn) {
-      o.wr = take(4 * B * 2 * F * 4);
+      o.wr = take(R * 4 * 2 * F * 4);
       o.du = take(R * NQ * f);
       o.dp = take(R * NQ * f);
       o.dv_acc = take(B * NQ * 4);
       o.dq_acc = take(B * NQ * 4);
     }
     if (p->att) {
-      o.dz = take(B * E * 4);
+      o.dz = take(R * E * 4);
       o.dba = take(R * p->ldEA * f);
       o.dAtt1 = take(B * P * A * 4);
       o.dwf = take(R * A * 4);
@@ -190,11 +190,11 @@ struct Ctx {
 
 int G(const Ctx& c, const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo,
       int out_ft, const float* bias, const float* addm, int64_t ldadd, int rows, int N, int K,
-      int rows_alloc = 0, int batch = 1, int64_t sX = 0, int64_t sW = 0, int64_t sO = 0) {
+      int rows_alloc = 0, int batch = 1, int64_t sX = 0, int64_t sW = 0, int64_t sO = 0, int splitk = 0) {
   GemmArgs a;
   a.X = X; a.ldx = ldx; a.W = W; a.ldw = ldw; a.out = out; a.ldo = ldo; a.out_ft = out_ft;
   a.bias = bias; a.addm = addm; a.ldadd = ldadd; a.rows = rows; a.N = N; a.K = K;
-  a.rows_alloc = rows_alloc; a.batch = batch; a.sX = sX; a.sW = sW; a.sO = sO;
+  a.rows_alloc = rows_alloc; a.batch = batch; a.sX = sX; a.sW = sW; a.sO = sO; a.splitk = splitk;
   return gemm(c.prec, a, c.st);
 }
 
@@ -330,8 +330,18 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
                NQ, M));
   if (alphas) CAPDEC_CUDA_OK(cudaMemsetAsync(alphas, 0, (size_t)R * P * 4, st));
   if (ragged) {
+    // rows beyond a caption's length are never written by the step kernels; the batched GEMMs over
+    // all (t,b) rows must see finite (zero) operands there
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.Hall), 0, (size_t)R * D * p.fsz, st));
     if (dropout_p > 0.f) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.Hd), 0, (size_t)R * D * p.fsz, st));
+    if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.z), 0, (size_t)R * E * p.fsz, st));
+    if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.m), 0, (size_t)R * 4 * 2 * F * p.fsz, st));
+  }
+  // split-K GEMMs of the tcgen05 engine accumulate with atomics into pre-zeroed outputs
+  const int SK = pr == CAPDEC_BF16 ? -1 : 0;
+  if (SK) {
+    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.g1), 0, (size_t)R * NG1 * 4, st));
+    if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.pre), 0, (size_t)R * 4 * D * 4, st));
   }
 
   const bool drop = dropout_p > 0.f;
@@ -343,7 +353,7 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     float* g1 = c.at<float>(o.g1) + (int64_t)t * B * NG1;
     float* U = c.at<float>(o.U) + (int64_t)t * B * NQ;
     CAPDEC_TRY(G(c, hprev, ldh, c.at(o.Wp_cat1), p.ldD, g1, NG1, 0, c.at<float>(o.b_cat1), nullptr, 0, n,
-                 NG1, D, B));
+                 NG1, D, B, 1, 0, 0, 0, SK));
     const float* pcol = g1 + (p.att ? A + E : 0);
     if (p.att) {
       void* z = c.ft(o.z, (int64_t)t * B * E);
@@ -351,7 +361,7 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
       CAPDEC_TRY(attention_fwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w, w.full_att_b,
                                alphas + (int64_t)t * P, (int64_t)T * P, z, E, awe, n, 1, P, E, A, st));
       // u (in place over U_emb[t]) += z . W_x[:, M:]^T
-      CAPDEC_TRY(G(c, z, E, c.ft(o.Wp_xq, M), p.ldX, U, NQ, 0, nullptr, U, NQ, n, NQ, E, B));
+      CAPDEC_TRY(G(c, z, E, c.ft(o.Wp_xq, M), p.ldX, U, NQ, 0, nullptr, U, NQ, n, NQ, E, B, 1, 0, 0, 0, SK));
     }
     const float* c_prev = c.at<float>(o.C) + (int64_t)t * B * D;
     float* c_new = c.at<float>(o.C) + (int64_t)(t + 1) * B * D;
@@ -361,9 +371,10 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     if (p.scn) {
       void* m = c.ft(o.m, (int64_t)t * 4 * B * 2 * F);
       CAPDEC_TRY(scn_form_m(pr, U, NQ, pcol, NG1, c.at<float>(o.v), c.at<float>(o.q), m, n, B, F, st));
-      CAPDEC_TRY(G(c, m, 2 * F, c.at(o.Wp_c), p.ld2F, c.at(o.pre), 4 * D, 0, nullptr, nullptr, 0, n, D,
-                   2 * F, B, 4, (int64_t)B * 2 * F, (int64_t)D * p.ld2F, D));
-      CAPDEC_TRY(cell_fwd(pr, c.at<float>(o.pre), 4 * D, nullptr, 0, w.b_ih, w.b_hh, 0, c_prev, c_new,
+      float* pre = c.at<float>(o.pre) + (int64_t)t * B * 4 * D;
+      CAPDEC_TRY(G(c, m, 2 * F, c.at(o.Wp_c), p.ld2F, pre, 4 * D, 0, nullptr, nullptr, 0, n, D, 2 * F, B, 4,
+                   (int64_t)B * 2 * F, (int64_t)D * p.ld2F, D, SK));
+      CAPDEC_TRY(cell_fwd(pr, pre, 4 * D, nullptr, 0, w.b_ih, w.b_hh, 0, c_prev, c_new,
                           gates, hout, (int64_t)T * D, hdout, dropout_p, seed, t, T, n, D, st));
     } else {
       CAPDEC_TRY(cell_fwd(pr, U, NQ, pcol, NG1, w.b_ih, w.b_hh, 1, c_prev, c_new, gates, hout,
@@ -423,7 +434,12 @@ int backward(const CapdecDims& d, const CapdecParams& w, const float* tags, cons
   CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.fc_w, D, 0, nullptr, nullptr, 0, V, D, (int)R));
   CAPDEC_TRY(colsum(pr, dlog, 1, lddl, (int)R, V, g.fc_b, 0, st));
 
-  CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dh_rec), 0, (size_t)B * D * 4, st));
+  const int SK = pr == CAPDEC_BF16 ? -1 : 0;
+  CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dh_rec), 0, (size_t)(T + 1) * B * D * 4, st));
+  if (SK) {
+    if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.wr), 0, (size_t)R * 4 * 2 * F * 4, st));
+    if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dz), 0, (size_t)R * E * 4, st));
+  }
   CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dc), 0, (size_t)B * D * 4, st));
   if (p.scn) {
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dv_acc), 0, (size_t)B * NQ * 4, st));
@@ -453,18 +469,22 @@ int backward(const CapdecDims& d, const CapdecParams& w, const float* tags, cons
     const float* c_new = c.at<float>(o.C) + (int64_t)(t + 1) * B * D;
     const float* gates = c.at<float>(o.gates) + (int64_t)t * B * 4 * D;
     void* dpre = c.ft(o.dpre, (int64_t)t * B * 4 * D);
-    float* dh_rec = c.at<float>(o.dh_rec);
-    CAPDEC_TRY(cell_bwd(pr, c.at<float>(o.dHfc) + (int64_t)t * D, (int64_t)T * D, dh_rec, c.at<float>(o.dc),
+    // dhs[t+1]: recurrent gradient flowing into h_t ; dhs[t]: what this step sends to h_{t-1}
+    const float* dh_in = c.at<float>(o.dh_rec) + (int64_t)(t + 1) * B * D;
+    float* dh_rec = c.at<float>(o.dh_rec) + (int64_t)t * B * D;
+    float* wr = p.scn ? c.at<float>(o.wr) + (int64_t)t * 4 * B * 2 * F : nullptr;
+    float* dz = p.att ? c.at<float>(o.dz) + (int64_t)t * B * E : nullptr;
+    CAPDEC_TRY(cell_bwd(pr, c.at<float>(o.dHfc) + (int64_t)t * D, (int64_t)T * D, dh_in, c.at<float>(o.dc),
                         gates, c_prev, c_new, p.scn ? 0 : 1, dropout_p, seed, t, T, dpre, nullptr, n, D, st));
     const void* du;      // gradient wrt u (input-side pre-products) and wrt p (recurrent side)
     const void* dpp;
     if (p.scn) {
       // [w_g | r_g] = dpre_g . [W_ic_g | W_hc_g]
-      CAPDEC_TRY(G(c, dpre, 4 * D, c.at(o.Wp_cT), p.ldD, c.at(o.wr), 2 * F, 0, nullptr, nullptr, 0, n, 2 * F,
-                   D, B, 4, D, (int64_t)2 * F * p.ldD, (int64_t)B * 2 * F));
+      CAPDEC_TRY(G(c, dpre, 4 * D, c.at(o.Wp_cT), p.ldD, wr, 2 * F, 0, nullptr, nullptr, 0, n, 2 * F,
+                   D, B, 4, D, (int64_t)2 * F * p.ldD, (int64_t)B * 2 * F, SK));
       void* du_t = c.ft(o.du, (int64_t)t * B * NQ);
       void* dp_t = c.ft(o.dp, (int64_t)t * B * NQ);
-      CAPDEC_TRY(scn_bwd_products(pr, c.at<float>(o.wr), U, NQ, pcol, NG1, c.at<float>(o.v),
+      CAPDEC_TRY(scn_bwd_products(pr, wr, U, NQ, pcol, NG1, c.at<float>(o.v),
                                   c.at<float>(o.q), du_t, dp_t, c.at<float>(o.dv_acc),
                                   c.at<float>(o.dq_acc), n, B, F, st));
       du = du_t; dpp = dp_t;
@@ -472,20 +492,21 @@ int backward(const CapdecDims& d, const CapdecParams& w, const float* tags, cons
       du = dpre; dpp = dpre;
     }
     // dh_{t-1} (recurrent part) = dp . W_hq^T
-    CAPDEC_TRY(G(c, dpp, NQ, c.at(o.Wp_hq), p.ldNQ, dh_rec, D, 0, nullptr, nullptr, 0, n, D, NQ, B));
+    CAPDEC_TRY(G(c, dpp, NQ, c.at(o.Wp_hq), p.ldNQ, dh_rec, D, 0, nullptr, nullptr, 0, n, D, NQ, B, 1, 0, 0, 0, SK));
     if (p.att) {
       // dz = du . W_x[M:, :]^T
-      CAPDEC_TRY(G(c, du, NQ, c.ft(o.Wp_xin, (int64_t)M * p.ldNQ), p.ldNQ, c.at(o.dz), E, 0, nullptr,
-                   nullptr, 0, n, E, NQ, B));
+      CAPDEC_TRY(G(c, du, NQ, c.ft(o.Wp_xin, (int64_t)M * p.ldNQ), p.ldNQ, dz, E, 0, nullptr,
+                   nullptr, 0, n, E, NQ, B, 1, 0, 0, 0, SK));
       void* dba = c.ft(o.dba, (int64_t)t * B * p.ldEA);
       CAPDEC_TRY(attention_bwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w,
                                alphas + (int64_t)t * P, (int64_t)T * P,
                                d_alphas ? d_alphas + (int64_t)t * P : nullptr, (int64_t)T * P,
-                               c.at<float>(o.dz), E, c.at<float>(o.awe) + (int64_t)t * B * E, dba, p.ldEA,
+                               dz, E, c.at<float>(o.awe) + (int64_t)t * B * E, dba, p.ldEA,
                                c.at<float>(o.dAtt1), c.at<float>(o.dwf) + (int64_t)t * B * A,
                                c.at<float>(o.dbf) + (int64_t)t * B, n, P, E, A, st));
       // dh_{t-1} += [dbeta_pre | datt2] . [W_beta^T | W_d^T]^T
-      CAPDEC_TRY(G(c, dba, p.ldEA, c.at(o.Wp_b6), p.ldEA, dh_rec, D, 0, nullptr, dh_rec, D, n, D, E + A, B));
+      CAPDEC_TRY(G(c, dba, p.ldEA, c.at(o.Wp_b6), p.ldEA, dh_rec, D, 0, nullptr, dh_rec, D, n, D, E + A, B, 1,
+                   0, 0, 0, SK));
     }
   }
 

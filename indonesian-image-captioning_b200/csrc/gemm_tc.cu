@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
                void* out, int64_t ldo, int out_ft, const float* __restrict__ bias,
                const float* addm, int64_t ldadd, int rows, int N, int K,
-               int64_t sO, int64_t sBias, int64_t sAdd) {
+               int64_t sO, int64_t sBias, int64_t sAdd, int splits) {
   using C = Cfg<BNR>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
@@ -139,8 +139,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BM;
   const int r0 = blockIdx.y * BNR;
-  const int z = blockIdx.z;
-  const int nkb = (K + BK - 1) / BK;
+  // grid.z = batch * splits: split-K slices of one output tile are reduced with fp32 atomics
+  // into an output the caller has pre-initialised (zero, or the in-place addend)
+  const int z = blockIdx.z / splits;
+  const int split = blockIdx.z - z * splits;
+  const int nkb_total = (K + BK - 1) / BK;
+  const int kb_begin = (int)(((int64_t)nkb_total * split) / splits);
+  const int kb_end = (int)(((int64_t)nkb_total * (split + 1)) / splits);
+  const int nkb = kb_end - kb_begin;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -174,8 +180,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         const uint32_t full = smem_u32(&bars[s]);
         mbar_expect_tx(full, C::STAGE_BYTES);
         const uint32_t ws = smem_u32(smem + s * C::STAGE_BYTES);
-        tma_load_3d(ws, &mapW, full, kb * BK, n0, z);
-        tma_load_3d(ws + C::W_BYTES, &mapX, full, kb * BK, r0, z);
+        tma_load_3d(ws, &mapW, full, (kb_begin + kb) * BK, n0, z);
+        tma_load_3d(ws + C::W_BYTES, &mapX, full, (kb_begin + kb) * BK, r0, z);
       }
     }
   } else if (warp == 1) {
@@ -210,10 +216,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     const int n = n0 + q * 32 + lane;       // output feature owned by this thread
     const bool n_ok = n < N;
     float bv = 0.f;
-    if (bias != nullptr && n_ok) bv = bias[(int64_t)z * sBias + n];
+    if (bias != nullptr && n_ok && split == 0) bv = bias[(int64_t)z * sBias + n];
     float* outf = (float*)out + (int64_t)z * sO;
     bf16* outh = (bf16*)out + (int64_t)z * sO;
     const float* add = addm ? addm + (int64_t)z * sAdd : nullptr;
+    // split-K: the addend is applied once (split 0) unless it IS the output (in-place accumulate)
+    if (splits > 1 && (split != 0 || (const void*)add == (const void*)outf)) add = nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < BNR; c0 += 32) {
       uint32_t v[32];
@@ -225,7 +233,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           if (r < rows) {
             float val = __uint_as_float(v[j]) + bv;
             if (add) val += add[(int64_t)r * ldadd + n];
-            if (out_ft) outh[(int64_t)r * ldo + n] = __float2bfloat16_rn(val);
+            if (splits > 1) atomicAdd(&outf[(int64_t)r * ldo + n], val);
+            else if (out_ft) outh[(int64_t)r * ldo + n] = __float2bfloat16_rn(val);
             else outf[(int64_t)r * ldo + n] = val;
           }
         }
@@ -310,10 +319,20 @@ int launch(const GemmArgs& a, cudaStream_t st) {
   CAPDEC_TRY(get_map(a.W, a.ldw, a.N, a.K, a.batch, a.sW, BM, &mW));
   const int xrows = a.rows_alloc > a.rows ? a.rows_alloc : a.rows;
   CAPDEC_TRY(get_map(a.X, a.ldx, xrows, a.K, a.batch, a.sX, BNR, &mX));
-  dim3 grid(ceil_div(a.N, BM), ceil_div(a.rows, BNR), a.batch);
+  // split-K only for fp32 outputs that the caller pre-initialised (GemmArgs::splitk)
+  const int nkb = ceil_div(a.K, BK);
+  int splits = 1;
+  if (a.splitk != 0 && !a.out_ft) {
+    const int tiles = ceil_div(a.N, BM) * ceil_div(a.rows, BNR) * a.batch;
+    splits = a.splitk > 0 ? a.splitk : (148 + tiles - 1) / tiles;     // auto: about one CTA per SM
+    if (splits > nkb / 2) splits = nkb / 2;                            // >= 2 k-blocks per CTA
+    if (splits > 16) splits = 16;
+    if (splits < 1) splits = 1;
+  }
+  dim3 grid(ceil_div(a.N, BM), ceil_div(a.rows, BNR), a.batch * splits);
   gemm_tc_kernel<BNR><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(
       mW, mX, a.out, a.ldo, a.out_ft, a.bias, a.addm, a.ldadd, a.rows, a.N, a.K, a.sO, a.sBias,
-      a.sAdd);
+      a.sAdd, splits);
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }

@@ -1,0 +1,83 @@
+"""world_size-2 gloo tests of the data-parallel host logic (CPU)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, PKG
+
+
+def _worker(rank, world, port, ret):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from capdec.parallel import GradReducer, shard_range
+        from oracle import capdec_oracle as O
+        torch.manual_seed(0)
+        dims = dict(attention_dim=24, embed_dim=16, decoder_dim=32, factored_dim=24, semantic_dim=12,
+                    vocab_size=37, encoder_dim=40)
+        params = O.random_params(O.ATTENTION_SCN, seed=0, **dims)
+        # two shards of a global batch of 6 captions
+        lengths = [[9, 3, 14], [6, 11, 4]]
+        shards = [O.synthetic_batch(3, 37, seed=50 + r, side=3, E=40, S=12, max_len=14, lengths=lengths[r])
+                  for r in range(world)]
+        n_global = sum(l - 1 for ls in lengths for l in ls)
+
+        def shard_loss(p, r):
+            enc, tags, caps, caplens = shards[r]
+            out = O.decoder_forward(O.ATTENTION_SCN, p, enc, tags, caps, caplens)
+            n_local = sum(out[2])
+            # global-denominator scaling used by CaptionDecoderBase.loss(n_tokens=..., alpha_c=1/world)
+            ce = O.caption_loss(out[0], out[1], out[2], None) * n_local / n_global
+            reg = ((1.0 - out[3].sum(dim=1)) ** 2).mean() / world
+            return ce + reg
+
+        class Holder(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.ps = torch.nn.ParameterList([torch.nn.Parameter(v.clone()) for v in params.values()])
+        h = Holder()
+        p_local = dict(zip(params.keys(), h.ps))
+        shard_loss(p_local, rank).backward()
+        red = GradReducer(h, dist)
+        red.allreduce(None)
+        # single-process truth: sum of both shard losses
+        p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        (shard_loss(p_ref, 0) + shard_loss(p_ref, 1)).backward()
+        err = max((p_local[k].grad - p_ref[k].grad).abs().max().item() for k in params)
+        # zero-copy path: grads that are views of one flat buffer
+        flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+        class Two(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.a = torch.nn.Parameter(torch.zeros(4))
+                self.b = torch.nn.Parameter(torch.zeros(2, 3))
+        m = Two()
+        m.a.grad = flat[:4]
+        m.b.grad = flat[4:].view(2, 3)
+        out = GradReducer(m, dist).allreduce({"flat_grads": flat})
+        ok_zero_copy = out.data_ptr() == flat.data_ptr() and torch.equal(flat, torch.arange(10.) * 3)
+        ret[rank] = (err, ok_zero_copy, shard_range(5000, rank, world))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dp_gradients_sum_to_global_gradient():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        err, ok, rng = ret[r]
+        assert err < 1e-6
+        assert ok
+    assert ret[0][2] == (0, 2500) and ret[1][2] == (2500, 5000)

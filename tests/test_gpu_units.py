@@ -133,3 +133,20 @@ def test_ops_refuse_cpu_tensors():
     from capdec._lib import CapdecError
     with pytest.raises(CapdecError):
         CF.gemm(torch.zeros(4, 8), torch.zeros(4, 8), precision="fp32")
+
+
+@pytest.mark.parametrize("rows,N,K,splitk", [(32, 2048, 2048, -1), (32, 512, 2560, 16), (32, 4608, 512, -1),
+                                             (20, 300, 1000, 3), (64, 512, 2048, -1)])
+def test_gemm_tc_splitk_atomics(rows, N, K, splitk):
+    """split-K slices reduced with fp32 atomics into a pre-initialised output (in-place addend)."""
+    from capdec import functional as CF
+    g = torch.Generator(device="cuda").manual_seed(rows + N + K)
+    X = _pad_k(torch.randn(rows, K, device="cuda", generator=g))
+    W = _pad_k(torch.randn(N, K, device="cuda", generator=g))
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = CF.gemm(X, W, bias=bias, precision="bf16", splitk=splitk)
+    assert rel_err(out, _ref_gemm(X.float(), W.float(), bias)) < 1e-5
+    acc = torch.randn(rows, N, device="cuda", generator=g)
+    ref = _ref_gemm(X.float(), W.float(), None, acc)
+    CF.gemm(X, W, addm=acc, out=acc, precision="bf16", splitk=splitk)      # acc += X W^T
+    assert rel_err(acc, ref) < 1e-5
