@@ -194,6 +194,7 @@ def workload_config(args, kind, dims, per_gpu_b, mode):
             "global_batch": per_gpu_b * args.gpus, "caption_len": CAP_LEN, "decode_steps": CAP_LEN - 1,
             "vocab": dims["V"], "dims": dims, "features": "14x14x%d" % dims["E"], "parallelism": "dp%d" % args.gpus,
             "precision": args.precision, "dropout": 0.5 if mode == "train" else 0.0,
+            "cuda_graphs": not getattr(args, "no_graphs", False),
             "l2": "flushed between timed steps by writing a 256 MiB buffer (outside the per-step event pairs)"}
 
 
@@ -227,6 +228,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     capdec.set_precision(args.precision)
+    capdec.set_graphs(not args.no_graphs)      # public switch: replay the step from CUDA graphs
     kind, dims, per_gpu_b, mode = WORKLOADS[args.workload]
     if args.batch:
         per_gpu_b = args.batch
@@ -450,6 +452,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -109,17 +109,24 @@ size_t capdec_workspace_bytes(const CapdecDims* dims, int with_backward);
  *   predictions    (B,T,V) fp32 out (rows beyond each length are zero)
  *   alphas         (B,T,P) fp32 out (NULL for pure_scn)
  *   workspace      capdec_workspace_bytes() bytes, 256-B aligned; holds the packed weights
- *                  and the per-step activations that capdec_backward consumes. */
+ *                  and the per-step activations that capdec_backward consumes.
+ *   phases         0 or 3 = everything.  1 = INPUT PHASE only: the launches that read the
+ *                  caller-owned input pointers (enc, sort_ind, tags, caps_sorted, lengths, seed)
+ *                  and stage them in the workspace.  2 = COMPUTE PHASE only: touches nothing but
+ *                  params, workspace, predictions and alphas, so with fixed pointers it can be
+ *                  captured ONCE into a CUDA graph (cudaStreamBeginCapture on `stream`) and
+ *                  replayed every iteration after a fresh phase-1 call. */
 int capdec_forward_train(const CapdecDims* dims, const CapdecParams* params,
                          const float* enc, int64_t enc_sb, int64_t enc_sp, int64_t enc_se,
                          const int64_t* sort_ind, const float* tags,
                          const int64_t* caps_sorted, const int32_t* decode_len_h,
-                         float dropout_p, uint64_t dropout_seed, int save_for_backward,
+                         float dropout_p, uint64_t dropout_seed, int save_for_backward, int phases,
                          float* predictions, float* alphas,
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* Reverse-time backward of capdec_forward_train (same dims / workspace, later on the same
- * stream).
+ * stream).  Reads only params, workspace (tags / captions / dropout seed were staged there by the
+ * forward), alphas and the d_* inputs -> graph-capturable like the compute phase.
  *   d_predictions  (B,T,V) fp32 gradient of the returned scores (may be NULL if d_logits_ft given)
  *   d_logits_ft    optional (B*T, ldq) gradient already in the GEMM feature type (bf16 when
  *                  precision==BF16, fp32 otherwise), ldq = V rounded up to 8; written by
@@ -129,8 +136,7 @@ int capdec_forward_train(const CapdecDims* dims, const CapdecParams* params,
  *   grads          every non-NULL member is OVERWRITTEN with the dense gradient of that
  *                  parameter (reference shapes; bias_ih.grad == bias_hh.grad). */
 int capdec_backward(const CapdecDims* dims, const CapdecParams* params,
-                    const float* tags, const int64_t* caps_sorted, const int32_t* decode_len_h,
-                    float dropout_p, uint64_t dropout_seed,
+                    const int32_t* decode_len_h, float dropout_p,
                     const float* d_predictions, const void* d_logits_ft, const float* d_alphas,
                     const float* alphas, const CapdecParams* grads,
                     void* workspace, size_t workspace_bytes, void* stream);
@@ -188,6 +194,19 @@ int capdec_attention_step(int precision, const void* att1, const void* enc,
                           float* alpha_out, int64_t alpha_stride,
                           void* z_out, float* awe_out,
                           int rows, int rows_per_map, int P, int E, int A, void* stream);
+
+/* Backward of capdec_attention_step for `rows` rows with one feature map each (training):
+ * inputs dz (rows,E) = d loss / d z, the saved awe (rows,E) and alpha (rows, alpha_stride),
+ * optional dalpha_ext (gradient arriving directly at alpha).  Outputs: dba (rows, lddba) in the
+ * feature type = [d beta_pre (E) | d att2 (A)], dAtt1 (rows,P,A) fp32 ACCUMULATED INTO,
+ * dwf_part (rows,A) and dbf_part (rows) per-row partials of the full_att gradients. */
+int capdec_attention_bwd_step(int precision, const void* att1, const void* enc,
+                              const float* g1, int64_t ldg, int beta_col, const float* w_f,
+                              const float* alpha, int64_t alpha_stride,
+                              const float* dalpha_ext, int64_t dalpha_stride,
+                              const float* dz, const float* awe,
+                              void* dba, int64_t lddba, float* dAtt1, float* dwf_part,
+                              float* dbf_part, int rows, int P, int E, int A, void* stream);
 
 /* SCNCell.forward for `rows` rows on fp32 master weights (packs them internally into
  * `workspace`): h_out/c_out (rows,D).  x (rows,X). */

@@ -39,8 +39,8 @@ SIGNATURES = {
     "capdec_launch_count": (C.c_ulonglong, []),
     "capdec_workspace_bytes": (_sz, [C.POINTER(Dims), _i]),
     "capdec_forward_train": (_i, [C.POINTER(Dims), C.POINTER(Params), _vp, _i64, _i64, _i64, _vp, _vp,
-                                  _vp, _vp, _f, _u64, _i, _vp, _vp, _vp, _sz, _vp]),
-    "capdec_backward": (_i, [C.POINTER(Dims), C.POINTER(Params), _vp, _vp, _vp, _f, _u64, _vp, _vp, _vp,
+                                  _vp, _vp, _f, _u64, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "capdec_backward": (_i, [C.POINTER(Dims), C.POINTER(Params), _vp, _f, _vp, _vp, _vp,
                              _vp, C.POINTER(Params), _vp, _sz, _vp]),
     "capdec_loss_fwd": (_i, [C.POINTER(Dims), _vp, _vp, _vp, _vp, C.c_int32, _f, _vp, _vp, _vp]),
     "capdec_loss_bwd": (_i, [C.POINTER(Dims), _vp, _vp, _vp, _vp, C.c_int32, _f, _f, _vp, _vp, _vp, _vp,
@@ -52,6 +52,8 @@ SIGNATURES = {
                          _i64, _i64, _i, _vp]),
     "capdec_attention_step": (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i,
                                    _i, _i, _i, _vp]),
+    "capdec_attention_bwd_step": (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp, _vp, _i64, _vp, _i64, _vp, _vp,
+                                       _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "capdec_scn_cell_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "capdec_scn_cell_step": (_i, [_i, _i, _i, _i, _i, _i] + [_vp] * 14 + [_vp, _sz, _vp]),
 }

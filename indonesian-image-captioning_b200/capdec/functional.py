@@ -1,8 +1,19 @@
 """Autograd wrappers around the C ABI (teacher-forced decoder, fused loss, unit ops).
 
 All tensors must live on a CUDA device; nothing here computes on the CPU.
+
+Two execution modes for the training step:
+  * eager (default): one C call per forward and per backward; each issues its ~400 kernel
+    launches on the current stream.
+  * graph replay (`capdec.set_graphs(True)` or CAPDEC_GRAPHS=1): per problem signature (dims,
+    decode lengths, parameter pointers) a plan owns static workspace/output/gradient buffers; the
+    compute phase of the forward and the whole backward are captured once into CUDA graphs and
+    replayed, so a step costs a handful of launches on the host.  Outputs are then views of the
+    plan's static buffers and stay valid until the next forward with the same signature.
 """
+import collections
 import ctypes as C
+import os
 
 import torch
 
@@ -28,6 +39,21 @@ PARAM_MAP = {
     "pure_scn": [("embedding.weight", "emb")] + _SCN + _COMMON_TAIL + _FC,
     "pure_attention": _ATT + [("embedding.weight", "emb")] + _LSTM + _COMMON_TAIL + _BETA + _FC,
 }
+
+_graphs_enabled = os.environ.get("CAPDEC_GRAPHS", "0") == "1"
+_MAX_PLANS = 4
+
+
+def set_graphs(flag):
+    """Enable / disable CUDA-graph replay of the training step (see module docstring)."""
+    global _graphs_enabled
+    _graphs_enabled = bool(flag)
+    if not flag:
+        _plans.clear()
+
+
+def graphs_enabled():
+    return _graphs_enabled
 
 
 def param_names(kind):
@@ -56,8 +82,92 @@ def make_dims(kind, precision, B, T, P, E, A, M, D, F, S, V, L):
     return _lib.Dims(_lib.KIND[kind], precision_code(precision), B, T, P, E, A, M, D, F, S, V, L)
 
 
+def _dims_key(d):
+    return tuple(getattr(d, n) for n, _ in _lib.Dims._fields_)
+
+
+class _Plan:
+    """Buffers (and, in graph mode, captured graphs) of one decoder problem signature."""
+
+    def __init__(self, kind, dims, decode_lengths, need_bwd, params, dev):
+        lib = _lib.load()
+        self.kind, self.dims, self.need_bwd, self.dev = kind, dims, need_bwd, dev
+        B, T, P, V = dims.B, dims.T, dims.P, dims.V
+        self.ws_bytes = lib.capdec_workspace_bytes(C.byref(dims), 1 if need_bwd else 0)
+        if self.ws_bytes == 0:
+            _lib.check(-1, "capdec_workspace_bytes")
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.predictions = torch.empty(B, T, V, dtype=torch.float32, device=dev)
+        self.alphas = None if kind == "pure_scn" else torch.empty(B, T, P, dtype=torch.float32, device=dev)
+        self.len_h = (C.c_int32 * B)(*decode_lengths)
+        self.params = params
+        self.pstruct = _params_struct(kind, params)
+        self.flat_grads = None
+        self.grads = None
+        self.gstruct = None
+        self.dlog = None          # d logits in the GEMM feature type (fused-loss path)
+        self.d_alphas = None
+        self.d_pred = None        # static copy of an autograd-provided gradient (generic path)
+        self.graphs = {}          # slot -> torch.cuda.CUDAGraph
+        self.calls = {}           # slot -> number of launches so far
+
+    def ensure_grad_buffers(self):
+        if self.flat_grads is None:
+            self.flat_grads = torch.empty(sum(p.numel() for p in self.params), dtype=torch.float32,
+                                          device=self.dev)
+            self.grads, off = [], 0
+            for p in self.params:
+                self.grads.append(self.flat_grads[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self.gstruct = _params_struct(self.kind, self.grads)
+
+    def ensure_dlog(self):
+        if self.dlog is None:
+            d = self.dims
+            ldq = (d.V + 7) // 8 * 8
+            esz = 2 if d.precision == 1 else 4
+            self.dlog = torch.empty(d.B * d.T * ldq * esz, dtype=torch.uint8, device=self.dev)
+        if self.d_alphas is None and self.alphas is not None:
+            self.d_alphas = torch.zeros_like(self.alphas)
+
+    def run(self, slot, launch):
+        """Graph mode: call #1 eager (also warms lazy state: tensor maps, function attributes),
+        call #2 capture + replay, later calls replay."""
+        g = self.graphs.get(slot)
+        n = self.calls.get(slot, 0)
+        if g is not None:
+            g.replay()
+        elif n == 0:
+            launch()
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                launch()
+            g.replay()
+            self.graphs[slot] = g
+        self.calls[slot] = n + 1
+
+
+_plans = collections.OrderedDict()
+
+
+def _get_plan(kind, dims, decode_lengths, need_bwd, params, dev, dropout_on):
+    key = (kind, _dims_key(dims), tuple(decode_lengths), need_bwd, dropout_on, dev.index,
+           tuple(p.data_ptr() for p in params))
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _Plan(kind, dims, decode_lengths, need_bwd, params, dev)
+        _plans[key] = plan
+        while len(_plans) > _MAX_PLANS:
+            _plans.popitem(last=False)
+    else:
+        _plans.move_to_end(key)
+    return plan
+
+
 class DecoderTrainFn(torch.autograd.Function):
-    """predictions, alphas = decoder(enc, tags, caps_sorted, sort_ind; params) -- one C call each way."""
+    """predictions, alphas = decoder(enc, tags, caps_sorted, sort_ind; params) -- one C call each way
+    (or one graph replay each way)."""
 
     @staticmethod
     def forward(ctx, meta, enc, tags, caps_sorted, sort_ind, *params):
@@ -65,77 +175,97 @@ class DecoderTrainFn(torch.autograd.Function):
         kind = meta["kind"]
         _require_cuda(enc, tags, caps_sorted, sort_ind, *params)
         dims = meta["dims"]
-        B, T, P, V = dims.B, dims.T, dims.P, dims.V
         dev = enc.device
-        params = [p.detach().contiguous() for p in params]
+        params = [p.detach() for p in params]
         for p in params:
-            if p.dtype != torch.float32:
-                raise _lib.CapdecError("decoder parameters must be float32 master weights")
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.CapdecError("decoder parameters must be contiguous float32 master weights")
         need_bwd = meta["need_bwd"]
-        ws_bytes = lib.capdec_workspace_bytes(C.byref(dims), 1 if need_bwd else 0)
-        if ws_bytes == 0:
-            _lib.check(-1, "capdec_workspace_bytes")
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        predictions = torch.empty(B, T, V, dtype=torch.float32, device=dev)
-        alphas = None if kind == "pure_scn" else torch.empty(B, T, P, dtype=torch.float32, device=dev)
-        len_h = (C.c_int32 * B)(*meta["decode_lengths"])
-        pstruct = _params_struct(kind, params)
+        use_graph = _graphs_enabled
+        if use_graph:
+            plan = _get_plan(kind, dims, meta["decode_lengths"], need_bwd, params, dev,
+                             meta["dropout_p"] > 0)
+        else:
+            plan = _Plan(kind, dims, meta["decode_lengths"], need_bwd, params, dev)
         sb, sp, se = enc.stride()
-        with torch.cuda.device(dev):
+
+        def call(phases):
             rc = lib.capdec_forward_train(
-                C.byref(dims), C.byref(pstruct), _lib.ptr(enc), sb, sp, se, _lib.ptr(sort_ind),
-                _lib.ptr(tags), _lib.ptr(caps_sorted), len_h, meta["dropout_p"], meta["seed"],
-                1 if need_bwd else 0, _lib.ptr(predictions), _lib.ptr(alphas), _lib.ptr(ws), ws_bytes,
-                _stream())
-        _lib.check(rc, "capdec_forward_train")
+                C.byref(dims), C.byref(plan.pstruct), _lib.ptr(enc), sb, sp, se, _lib.ptr(sort_ind),
+                _lib.ptr(tags), _lib.ptr(caps_sorted), plan.len_h, meta["dropout_p"], meta["seed"],
+                1 if need_bwd else 0, phases, _lib.ptr(plan.predictions), _lib.ptr(plan.alphas),
+                _lib.ptr(plan.ws), plan.ws_bytes, _stream())
+            _lib.check(rc, "capdec_forward_train")
+
+        with torch.cuda.device(dev):
+            if use_graph:
+                call(1)                                   # input phase: reads the caller's tensors
+                plan.run("fwd", lambda: call(2))
+            else:
+                call(3)
         ctx.meta = meta
-        ctx.len_h = len_h
-        ctx.ws = ws if need_bwd else None
-        ctx.param_tensors = params
-        ctx.save_for_backward(tags if tags is not None else torch.empty(0, device=dev), caps_sorted,
-                              alphas if alphas is not None else torch.empty(0, device=dev))
-        if alphas is None:
+        ctx.plan = plan
+        ctx.use_graph = use_graph
+        ctx.param_refs = meta.pop("param_refs", None)
+        meta["plan"] = plan
+        predictions = plan.predictions.detach() if use_graph else plan.predictions
+        if plan.alphas is None:
             return predictions
+        alphas = plan.alphas.detach() if use_graph else plan.alphas
         return predictions, alphas
 
     @staticmethod
     def backward(ctx, d_pred, d_alphas=None):
         lib = _lib.load()
-        meta = ctx.meta
-        kind = meta["kind"]
-        dims = meta["dims"]
-        if ctx.ws is None:
+        meta, plan = ctx.meta, ctx.plan
+        kind, dims, dev = plan.kind, plan.dims, plan.dev
+        if not plan.need_bwd:
             raise _lib.CapdecError("backward called but forward ran without save_for_backward")
-        tags, caps_sorted, alphas = ctx.saved_tensors
-        dev = caps_sorted.device
-        params = ctx.param_tensors
-        # one flat buffer, per-parameter views: the data-parallel helper all-reduces it in place
-        flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-        grads, off = [], 0
-        for p in params:
-            grads.append(flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
-        meta["flat_grads"] = flat
-        fused = meta.get("fused_dlogits")      # set by FusedLossFn: gradient already in feature type
-        d_logits_ft = None
-        if fused is not None and fused.get("buf") is not None:
-            d_logits_ft = fused["buf"]
-            d_pred_c = None
-            d_alphas = fused.get("d_alphas")
+        plan.ensure_grad_buffers()
+        fused = meta.pop("fused_dlogits", None)    # set by FusedLossFn: gradient already in plan.dlog
+        if fused:
+            slot, d_pred_p, dlog_p = "bwd_fused", None, plan.dlog
+            d_alphas_p = plan.d_alphas if kind != "pure_scn" else None
         else:
-            d_pred_c = torch.zeros(dims.B, dims.T, dims.V, device=dev) if d_pred is None \
-                else d_pred.contiguous().float()
-        d_alphas_c = None if (d_alphas is None or kind == "pure_scn") else d_alphas.contiguous().float()
-        pstruct = _params_struct(kind, params)
-        gstruct = _params_struct(kind, grads)
-        with torch.cuda.device(dev):
+            slot, dlog_p = "bwd_generic", None
+            if plan.d_pred is None:
+                plan.d_pred = torch.zeros(dims.B, dims.T, dims.V, dtype=torch.float32, device=dev)
+            if d_pred is None:
+                plan.d_pred.zero_()
+            else:
+                plan.d_pred.copy_(d_pred)
+            d_pred_p = plan.d_pred
+            d_alphas_p = None
+            if kind != "pure_scn":
+                if plan.d_alphas is None:
+                    plan.d_alphas = torch.zeros_like(plan.alphas)
+                if d_alphas is None:
+                    plan.d_alphas.zero_()
+                else:
+                    plan.d_alphas.copy_(d_alphas)
+                d_alphas_p = plan.d_alphas
+
+        def call():
             rc = lib.capdec_backward(
-                C.byref(dims), C.byref(pstruct), _lib.ptr(tags if tags.numel() else None),
-                _lib.ptr(caps_sorted), ctx.len_h, meta["dropout_p"], meta["seed"], _lib.ptr(d_pred_c),
-                _lib.ptr(d_logits_ft), _lib.ptr(d_alphas_c), _lib.ptr(alphas if alphas.numel() else None),
-                C.byref(gstruct), _lib.ptr(ctx.ws), ctx.ws.numel(), _stream())
-        _lib.check(rc, "capdec_backward")
-        ctx.ws = None
+                C.byref(dims), C.byref(plan.pstruct), plan.len_h, meta["dropout_p"], _lib.ptr(d_pred_p),
+                _lib.ptr(dlog_p), _lib.ptr(d_alphas_p), _lib.ptr(plan.alphas), C.byref(plan.gstruct),
+                _lib.ptr(plan.ws), plan.ws_bytes, _stream())
+            _lib.check(rc, "capdec_backward")
+
+        with torch.cuda.device(dev):
+            if ctx.use_graph:
+                plan.run(slot, call)
+            else:
+                call()
+        meta["flat_grads"] = plan.flat_grads
+        grads = plan.grads
+        if ctx.use_graph and ctx.param_refs is not None and \
+                any(p.grad is not None for p in ctx.param_refs):
+            # gradient accumulation into an existing .grad that may alias the static buffer
+            grads = [g.clone() for g in grads]
+        if not ctx.use_graph:
+            plan.ws = None          # eager plans are single-use: release the workspace early
+            plan.d_pred = None
         return (None, None, None, None, None) + tuple(grads)
 
 
@@ -149,7 +279,8 @@ def decoder_forward(kind, module_params, enc, tags, caps_sorted, sort_ind, decod
                      caps_sorted.shape[1])
     need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in module_params)
     meta = {"kind": kind, "dims": dims, "decode_lengths": [int(x) for x in decode_lengths],
-            "dropout_p": float(dropout_p), "seed": int(seed) & ((1 << 63) - 1), "need_bwd": need_bwd}
+            "dropout_p": float(dropout_p), "seed": int(seed) & ((1 << 63) - 1), "need_bwd": need_bwd,
+            "param_refs": list(module_params)}
     out = DecoderTrainFn.apply(meta, enc, tags, caps_sorted, sort_ind, *module_params)
     return out, meta
 
@@ -192,24 +323,24 @@ class FusedLossFn(torch.autograd.Function):
         alphas_p = alphas if ctx.has_alphas else None
         # upstream gradient stays on the device: no host sync in the training step
         g_dev = g_loss.detach().reshape(1).float().contiguous()
-        d_alphas = torch.empty_like(alphas) if ctx.has_alphas else None
-        if meta is not None and meta.get("need_bwd"):
-            ldq = (dims.V + 7) // 8 * 8
-            esz = 2 if dims.precision == 1 else 4
-            buf = torch.empty(dims.B * dims.T * ldq * esz, dtype=torch.uint8, device=dev)
+        plan = meta.get("plan") if meta is not None else None
+        if plan is not None and plan.need_bwd:
+            plan.ensure_dlog()
+            d_alphas = plan.d_alphas if ctx.has_alphas else None
             with torch.cuda.device(dev):
                 rc = lib.capdec_loss_bwd(C.byref(dims), _lib.ptr(scores), _lib.ptr(alphas_p),
                                          _lib.ptr(caps_sorted), _lib.ptr(len_d), ctx.n_tokens,
                                          ctx.alpha_c, 1.0, _lib.ptr(g_dev), _lib.ptr(lse), None,
-                                         _lib.ptr(buf), _lib.ptr(d_alphas), _stream())
+                                         _lib.ptr(plan.dlog), _lib.ptr(d_alphas), _stream())
             _lib.check(rc, "capdec_loss_bwd")
-            meta["fused_dlogits"] = {"buf": buf, "d_alphas": d_alphas}
-            # the decoder Function picks the buffers up from meta; autograd still needs
-            # tensors of the right shape to route the call, so hand it cheap expanded zeros
+            meta["fused_dlogits"] = True
+            # the decoder Function picks the buffers up from its plan; autograd still needs tensors of
+            # the right shape to route the call, so hand it cheap expanded zeros
             d_scores = torch.zeros((), device=dev).expand(scores.shape)
             d_al = None if not ctx.has_alphas else torch.zeros((), device=dev).expand(alphas.shape)
             return d_scores, d_al, None, None, None, None, None, None
         d_scores = torch.empty_like(scores)
+        d_alphas = torch.empty_like(alphas) if ctx.has_alphas else None
         with torch.cuda.device(dev):
             rc = lib.capdec_loss_bwd(C.byref(dims), _lib.ptr(scores), _lib.ptr(alphas_p),
                                      _lib.ptr(caps_sorted), _lib.ptr(len_d), ctx.n_tokens, ctx.alpha_c,
@@ -291,6 +422,33 @@ def attention_step(att1, enc, g1, beta_col, w_f, b_f, rows_per_map=1, precision=
                                        P, E, A, _stream())
     _lib.check(rc, "capdec_attention_step")
     return z, alpha, awe
+
+
+def attention_bwd_step(att1, enc, g1, beta_col, w_f, alpha, dz, awe, dalpha_ext=None, dAtt1=None,
+                       precision=None):
+    """Backward of attention_step (one feature map per row).  Returns (dbeta_pre, datt2, dAtt1,
+    dwf_part, dbf_part); dAtt1 is accumulated into when given."""
+    lib = _lib.load()
+    prec = precision or get_precision()
+    _require_cuda(att1, enc, g1, w_f, alpha, dz, awe)
+    rows, P, A = att1.shape
+    E = enc.shape[2]
+    ft = _ft_dtype(prec)
+    dev = enc.device
+    ld = (E + A + 7) // 8 * 8
+    dba = torch.zeros(rows, ld, dtype=ft, device=dev)
+    if dAtt1 is None:
+        dAtt1 = torch.zeros(rows, P, A, dtype=torch.float32, device=dev)
+    dwf = torch.empty(rows, A, dtype=torch.float32, device=dev)
+    dbf = torch.empty(rows, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.capdec_attention_bwd_step(
+            precision_code(prec), _lib.ptr(att1), _lib.ptr(enc), _lib.ptr(g1), g1.stride(0), beta_col,
+            _lib.ptr(w_f), _lib.ptr(alpha), alpha.stride(0), _lib.ptr(dalpha_ext),
+            dalpha_ext.stride(0) if dalpha_ext is not None else 0, _lib.ptr(dz), _lib.ptr(awe),
+            _lib.ptr(dba), ld, _lib.ptr(dAtt1), _lib.ptr(dwf), _lib.ptr(dbf), rows, P, E, A, _stream())
+    _lib.check(rc, "capdec_attention_bwd_step")
+    return dba[:, :E], dba[:, E:E + A], dAtt1, dwf, dbf
 
 
 def scn_cell_step(weights, x, s, h, c, precision=None):

@@ -68,7 +68,7 @@ size_t capdec_workspace_bytes(const CapdecDims* dims, int with_backward) {
 int capdec_forward_train(const CapdecDims* dims, const CapdecParams* params, const float* enc,
                          int64_t enc_sb, int64_t enc_sp, int64_t enc_se, const int64_t* sort_ind,
                          const float* tags, const int64_t* caps_sorted, const int32_t* decode_len_h,
-                         float dropout_p, uint64_t dropout_seed, int save_for_backward,
+                         float dropout_p, uint64_t dropout_seed, int save_for_backward, int phases,
                          float* predictions, float* alphas, void* workspace, size_t workspace_bytes,
                          void* stream) {
   CAPDEC_REQUIRE(dims && params && enc && caps_sorted && decode_len_h && predictions && workspace,
@@ -78,21 +78,21 @@ int capdec_forward_train(const CapdecDims* dims, const CapdecParams* params, con
   CAPDEC_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, CAPDEC_ERR_BAD_ARG, "dropout_p out of range");
   CAPDEC_TRY(capdec_init());
   return forward_train(*dims, *params, enc, enc_sb, enc_sp, enc_se, sort_ind, tags, caps_sorted,
-                       decode_len_h, dropout_p, dropout_seed, save_for_backward, predictions,
+                       decode_len_h, dropout_p, dropout_seed, save_for_backward, phases ? phases : 3, predictions,
                        dims->kind == CAPDEC_PURE_SCN ? nullptr : alphas, workspace, workspace_bytes,
                        (cudaStream_t)stream);
 }
 
-int capdec_backward(const CapdecDims* dims, const CapdecParams* params, const float* tags,
-                    const int64_t* caps_sorted, const int32_t* decode_len_h, float dropout_p,
-                    uint64_t dropout_seed, const float* d_predictions, const void* d_logits_ft,
+int capdec_backward(const CapdecDims* dims, const CapdecParams* params,
+                    const int32_t* decode_len_h, float dropout_p,
+                    const float* d_predictions, const void* d_logits_ft,
                     const float* d_alphas, const float* alphas, const CapdecParams* grads,
                     void* workspace, size_t workspace_bytes, void* stream) {
-  CAPDEC_REQUIRE(dims && params && caps_sorted && decode_len_h && grads && workspace,
+  CAPDEC_REQUIRE(dims && params && decode_len_h && grads && workspace,
                  CAPDEC_ERR_BAD_ARG, "capdec_backward: null argument");
   CAPDEC_REQUIRE(dims->kind == CAPDEC_PURE_SCN || alphas, CAPDEC_ERR_BAD_ARG, "alphas is NULL");
   CAPDEC_TRY(capdec_init());
-  return backward(*dims, *params, tags, caps_sorted, decode_len_h, dropout_p, dropout_seed,
+  return backward(*dims, *params, decode_len_h, dropout_p,
                   d_predictions, d_logits_ft, d_alphas, alphas, *grads, workspace, workspace_bytes,
                   (cudaStream_t)stream);
 }
@@ -157,6 +157,20 @@ int capdec_attention_step(int precision, const void* att1, const void* enc, cons
   CAPDEC_TRY(capdec_init());
   return attention_fwd(precision, att1, enc, g1, ldg, beta_col, w_f, b_f, alpha_out, alpha_stride, z_out,
                        E, awe_out, rows, rows_per_map, P, E, A, (cudaStream_t)stream);
+}
+
+int capdec_attention_bwd_step(int precision, const void* att1, const void* enc, const float* g1,
+                              int64_t ldg, int beta_col, const float* w_f, const float* alpha,
+                              int64_t alpha_stride, const float* dalpha_ext, int64_t dalpha_stride,
+                              const float* dz, const float* awe, void* dba, int64_t lddba, float* dAtt1,
+                              float* dwf_part, float* dbf_part, int rows, int P, int E, int A,
+                              void* stream) {
+  CAPDEC_REQUIRE(att1 && enc && g1 && w_f && alpha && dz && awe && dba && dAtt1 && dwf_part && dbf_part,
+                 CAPDEC_ERR_BAD_ARG, "capdec_attention_bwd_step: null argument");
+  CAPDEC_TRY(capdec_init());
+  return attention_bwd(precision, att1, enc, g1, ldg, beta_col, w_f, alpha, alpha_stride, dalpha_ext,
+                       dalpha_stride, dz, E, awe, dba, lddba, dAtt1, dwf_part, dbf_part, rows, P, E, A,
+                       (cudaStream_t)stream);
 }
 
 // ---- SCNCell.forward on fp32 master weights (unit entry; models/scn_cell.py:52-154) ----
@@ -237,7 +251,7 @@ int capdec_scn_cell_step(int precision, int rows, int X, int D, int F, int S, co
   CAPDEC_TRY(gm(ws + cp.m, 2 * F, ws + cp.Wc, cp.ld2F, ws + cp.pre, 4 * D, D, 2 * F, 4, (int64_t)n * 2 * F,
                 (int64_t)D * cp.ld2F, D));
   CAPDEC_TRY(cell_fwd(pr, (float*)(ws + cp.pre), 4 * D, nullptr, 0, b_ih, b_hh, 0, c, c_out, nullptr,
-                      ws + cp.hO, cp.ldD, nullptr, 0.f, 0, 0, 1, n, D, st));
+                      ws + cp.hO, cp.ldD, nullptr, 0.f, nullptr, 0, 1, n, D, st));
   CAPDEC_TRY(copy_cast(pr, ws + cp.hO, 1, cp.ldD, h_out, 0, D, n, D, st));
   return CAPDEC_OK;
 }

@@ -38,7 +38,7 @@ struct Plan {
     size_t Wp_fcT, Wp_cT, Wp_hq, Wp_xin, Wp_b6;
     // forward activations
     size_t enc_s, att1, mean, meanF, tagsF, v, q, Xe, U, g1, awe, z, m, pre, gates, C, H0, Hall,
-        Hd, lenD;
+        Hd, lenD, seedD, capsD;
     // backward buffers
     size_t dlogF, dHfc, dh_rec, dc, dpre, wr, du, dp, dv_acc, dq_acc, dz, dba, dAtt1, dwf, dbf, dXe;
     size_t tA, tB, tC;             // transposed-operand scratch
@@ -126,6 +126,8 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
   o.Hall = take(R * D * f);
   o.Hd = take(R * D * f);
   o.lenD = take(B * 4);
+  o.seedD = take(8);
+  o.capsD = take((size_t)B * d.L * 8);
   if (with_bwd) {
     o.dlogF = take(R * p->ldV * f);
     o.dHfc = take(R * D * 4);
@@ -273,9 +275,12 @@ size_t workspace_bytes(const CapdecDims& d, int with_bwd) {
 
 int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, int64_t sb, int64_t sp,
                   int64_t se, const int64_t* sort_ind, const float* tags, const int64_t* caps,
-                  const int32_t* len_h, float dropout_p, uint64_t seed, int save_bwd,
+                  const int32_t* len_h, float dropout_p, uint64_t seed, int save_bwd, int phases,
                   float* predictions, float* alphas, void* workspace, size_t ws_bytes,
                   cudaStream_t st) {
+  // phases: bit 0 = input phase (reads enc / tags / captions / lengths / seed into the workspace;
+  // the only part that touches caller-owned INPUT pointers), bit 1 = everything else (parameters,
+  // workspace and outputs only -> capturable once into a CUDA graph and replayed)
   Ctx c;
   CAPDEC_TRY(make_plan(d, save_bwd != 0, &c.p));
   CAPDEC_REQUIRE(ws_bytes >= c.p.o.total, CAPDEC_ERR_WORKSPACE, "workspace %zu < %zu", ws_bytes,
@@ -302,13 +307,22 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     while (n < B && len_h[n] > t) ++n;
     bt[t] = n;
   }
-  CAPDEC_CUDA_OK(cudaMemcpyAsync(c.at(o.lenD), len_h, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  if (phases & 1) {
+    CAPDEC_CUDA_OK(cudaMemcpyAsync(c.at(o.lenD), len_h, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    CAPDEC_CUDA_OK(cudaMemcpyAsync(c.at(o.seedD), &seed, 8, cudaMemcpyHostToDevice, st));
+    CAPDEC_CUDA_OK(cudaMemcpyAsync(c.at(o.capsD), caps, (size_t)B * d.L * 8, cudaMemcpyDeviceToDevice, st));
+    // sorted, converted features + pixel mean (attention_scn.py:113-120, :90)
+    CAPDEC_TRY(gather_features(pr, enc, sb, sp, se, sort_ind, c.at(o.enc_s), c.at<float>(o.mean),
+                               c.at(o.meanF), p.ldE, B, P, E, st));
+    if (p.scn)   // tags are NOT permuted (App. C-1): row i of the sorted batch uses tags[i]
+      CAPDEC_TRY(copy_cast(pr, tags, 0, S, c.at(o.tagsF), 1, p.ldS, B, S, st));
+  }
+  if (!(phases & 2)) return CAPDEC_OK;
+  const int64_t* capsD = c.at<int64_t>(o.capsD);
 
   CAPDEC_TRY(pack_weights(c, w));
 
   // ---------------- prologue: time-invariant products ----------------
-  CAPDEC_TRY(gather_features(pr, enc, sb, sp, se, sort_ind, c.at(o.enc_s), c.at<float>(o.mean),
-                             c.at(o.meanF), p.ldE, B, P, E, st));
   if (p.att)   // att1 = enc . W_e^T + b_e      (attention.py:35, hoisted)
     CAPDEC_TRY(G(c, c.at(o.enc_s), E, c.at(o.Wp_e), p.ldE, c.at(o.att1), A, 1, w.enc_att_b, nullptr, 0,
                  B * P, A, E));
@@ -317,15 +331,14 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
                nullptr, 0, B, D, E));
   CAPDEC_TRY(G(c, c.at(o.meanF), p.ldE, c.ft(o.Wp_init, (int64_t)D * p.ldE), p.ldE, c.at(o.C), D, 0,
                w.init_c_b, nullptr, 0, B, D, E));
-  if (p.scn) {   // v = s W_ib, q = s W_hb   (scn_cell.py:78-81, 134-143; tags NOT permuted, App. C-1)
-    CAPDEC_TRY(copy_cast(pr, tags, 0, S, c.at(o.tagsF), 1, p.ldS, B, S, st));
+  if (p.scn) {   // v = s W_ib, q = s W_hb   (scn_cell.py:78-81, 134-143)
     CAPDEC_TRY(G(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_ibT), p.ldS, c.at(o.v), NQ, 0, nullptr, nullptr, 0, B,
                  NQ, S));
     CAPDEC_TRY(G(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_hbT), p.ldS, c.at(o.q), NQ, 0, nullptr, nullptr, 0, B,
                  NQ, S));
   }
   // embeddings of the teacher tokens and their input-side projection, all (t,b) rows at once
-  CAPDEC_TRY(embedding_gather(pr, w.emb, caps, d.L, c.at(o.Xe), p.ldM, B, T, M, V, st));
+  CAPDEC_TRY(embedding_gather(pr, w.emb, capsD, d.L, c.at(o.Xe), p.ldM, B, T, M, V, st));
   CAPDEC_TRY(G(c, c.at(o.Xe), p.ldM, c.at(o.Wp_xq), p.ldX, c.at(o.U), NQ, 0, nullptr, nullptr, 0, (int)R,
                NQ, M));
   if (alphas) CAPDEC_CUDA_OK(cudaMemsetAsync(alphas, 0, (size_t)R * P * 4, st));
@@ -375,10 +388,10 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
       CAPDEC_TRY(G(c, m, 2 * F, c.at(o.Wp_c), p.ld2F, pre, 4 * D, 0, nullptr, nullptr, 0, n, D, 2 * F, B, 4,
                    (int64_t)B * 2 * F, (int64_t)D * p.ld2F, D, SK));
       CAPDEC_TRY(cell_fwd(pr, pre, 4 * D, nullptr, 0, w.b_ih, w.b_hh, 0, c_prev, c_new,
-                          gates, hout, (int64_t)T * D, hdout, dropout_p, seed, t, T, n, D, st));
+                          gates, hout, (int64_t)T * D, hdout, dropout_p, c.at<uint64_t>(o.seedD), t, T, n, D, st));
     } else {
       CAPDEC_TRY(cell_fwd(pr, U, NQ, pcol, NG1, w.b_ih, w.b_hh, 1, c_prev, c_new, gates, hout,
-                          (int64_t)T * D, hdout, dropout_p, seed, t, T, n, D, st));
+                          (int64_t)T * D, hdout, dropout_p, c.at<uint64_t>(o.seedD), t, T, n, D, st));
     }
   }
   // ---------------- vocabulary projection over all (b,t) rows ----------------
@@ -389,8 +402,8 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
   return CAPDEC_OK;
 }
 
-int backward(const CapdecDims& d, const CapdecParams& w, const float* tags, const int64_t* caps,
-             const int32_t* len_h, float dropout_p, uint64_t seed, const float* d_pred,
+int backward(const CapdecDims& d, const CapdecParams& w,
+             const int32_t* len_h, float dropout_p, const float* d_pred,
              const void* d_logits_ft, const float* d_alphas, const float* alphas,
              const CapdecParams& g, void* workspace, size_t ws_bytes, cudaStream_t st) {
   Ctx c;
@@ -475,7 +488,7 @@ int backward(const CapdecDims& d, const CapdecParams& w, const float* tags, cons
     float* wr = p.scn ? c.at<float>(o.wr) + (int64_t)t * 4 * B * 2 * F : nullptr;
     float* dz = p.att ? c.at<float>(o.dz) + (int64_t)t * B * E : nullptr;
     CAPDEC_TRY(cell_bwd(pr, c.at<float>(o.dHfc) + (int64_t)t * D, (int64_t)T * D, dh_in, c.at<float>(o.dc),
-                        gates, c_prev, c_new, p.scn ? 0 : 1, dropout_p, seed, t, T, dpre, nullptr, n, D, st));
+                        gates, c_prev, c_new, p.scn ? 0 : 1, dropout_p, c.at<uint64_t>(o.seedD), t, T, dpre, nullptr, n, D, st));
     const void* du;      // gradient wrt u (input-side pre-products) and wrt p (recurrent side)
     const void* dpp;
     if (p.scn) {
@@ -549,7 +562,8 @@ int backward(const CapdecDims& d, const CapdecParams& w, const float* tags, cons
     // embedding.weight.grad: dXe = du . W_ia[:M]^T, scattered to the consumed token rows
     CAPDEC_TRY(G(c, c.at(o.du), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
     // weight_ib.grad [S][4F] = s^T . sum_t dv ; weight_hb.grad = s^T . sum_t dq
-    CAPDEC_TRY(transpose_cast(pr, tags, 0, c.at(o.tA), 1, 1, B, S, 0, S, p.ldB, 0, 1, st));
+    // (the tag matrix as the forward saw it: the feature-type copy kept in the workspace)
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.tagsF), 1, c.at(o.tA), 1, 1, B, S, 0, p.ldS, p.ldB, 0, 1, st));
     CAPDEC_TRY(transpose_cast(pr, c.at(o.dv_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
     CAPDEC_TRY(G(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_ib, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
     CAPDEC_TRY(transpose_cast(pr, c.at(o.dq_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
@@ -567,7 +581,7 @@ int backward(const CapdecDims& d, const CapdecParams& w, const float* tags, cons
   }
   if (g.emb) {
     CAPDEC_CUDA_OK(cudaMemsetAsync(g.emb, 0, (size_t)V * M * 4, st));
-    CAPDEC_TRY(embedding_scatter_add(c.at<float>(o.dXe), M, caps, d.L, c.at<int32_t>(o.lenD), g.emb, B, T,
+    CAPDEC_TRY(embedding_scatter_add(c.at<float>(o.dXe), M, c.at<int64_t>(o.capsD), d.L, c.at<int32_t>(o.lenD), g.emb, B, T,
                                      M, V, st));
   }
 

@@ -91,6 +91,13 @@ gemm_simt_kernel(const float* __restrict__ X, int64_t ldx, const float* __restri
     }
     __syncthreads();
     if (k0 + BK < K) fetch(k0 + BK);
+    // two-level summation: each 16-wide k-tile is summed on its own and then added to the running
+    // total, which keeps the fp32 rounding error near that of a blocked BLAS instead of growing with K
+    float part[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[TM], b[TN];
@@ -101,8 +108,12 @@ gemm_simt_kernel(const float* __restrict__ X, int64_t ldx, const float* __restri
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] += part[i][j];
   }
 
 #pragma unroll

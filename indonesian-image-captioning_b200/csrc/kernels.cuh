@@ -45,11 +45,11 @@ int scn_form_m(int precision, const float* u, int64_t ldu, const float* p, int64
 // LSTM pointwise.  pre = preA + preB + b1 + b2 ; lstm_order: 0 = (i,f,o,c) SCN, 1 = (i,f,g,o) torch
 int cell_fwd(int precision, const float* preA, int64_t ldA, const float* preB, int64_t ldB,
              const float* b1, const float* b2, int lstm_order, const float* c_prev, float* c_new,
-             float* gates, void* h_out, int64_t ldh, void* hd_out, float dropout_p, uint64_t seed,
+             float* gates, void* h_out, int64_t ldh, void* hd_out, float dropout_p, const uint64_t* seed,
              int t, int T, int rows, int D, cudaStream_t st);
 int cell_bwd(int precision, const float* dh_fc, int64_t ld_dhfc, const float* dh_rec, float* dc,
              const float* gates, const float* c_prev, const float* c_new, int lstm_order,
-             float dropout_p, uint64_t seed, int t, int T, void* dpre, float* dpre_f32, int rows,
+             float dropout_p, const uint64_t* seed, int t, int T, void* dpre, float* dpre_f32, int rows,
              int D, cudaStream_t st);
 // SCN backward pointwise: du = w*v, dp = r*q, dv_acc += w*u, dq_acc += r*p ; wr = [g][b][w(F)|r(F)]
 int scn_bwd_products(int precision, const float* wr, const float* u, int64_t ldu, const float* p,
@@ -77,11 +77,11 @@ namespace capdec {
 size_t workspace_bytes(const CapdecDims& d, int with_bwd);
 int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, int64_t sb, int64_t sp,
                   int64_t se, const int64_t* sort_ind, const float* tags, const int64_t* caps,
-                  const int32_t* len_h, float dropout_p, uint64_t seed, int save_bwd,
+                  const int32_t* len_h, float dropout_p, uint64_t seed, int save_bwd, int phases,
                   float* predictions, float* alphas, void* workspace, size_t ws_bytes,
                   cudaStream_t st);
-int backward(const CapdecDims& d, const CapdecParams& w, const float* tags, const int64_t* caps,
-             const int32_t* len_h, float dropout_p, uint64_t seed, const float* d_pred,
+int backward(const CapdecDims& d, const CapdecParams& w,
+             const int32_t* len_h, float dropout_p, const float* d_pred,
              const void* d_logits_ft, const float* d_alphas, const float* alphas,
              const CapdecParams& g, void* workspace, size_t ws_bytes, cudaStream_t st);
 }  // namespace capdec

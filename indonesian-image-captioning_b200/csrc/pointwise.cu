@@ -166,7 +166,7 @@ __global__ void cell_fwd_kernel(const float* __restrict__ preA, int64_t ldA,
                                 int lstm_order, const float* __restrict__ c_prev,
                                 float* __restrict__ c_new, float* __restrict__ gates,
                                 FT* __restrict__ h_out, int64_t ldh, FT* __restrict__ hd_out,
-                                float dropout_p, uint64_t seed, int t, int T, int rows, int D) {
+                                float dropout_p, const uint64_t* __restrict__ seed_dev, int t, int T, int rows, int D) {
   int si, sf, so, sg;
   gate_slots(lstm_order, si, sf, so, sg);
   const int64_t total = (int64_t)rows * D;
@@ -193,7 +193,7 @@ __global__ void cell_fwd_kernel(const float* __restrict__ preA, int64_t ldA,
     }
     h_out[(int64_t)b * ldh + d] = from_f<FT>(h);
     if (hd_out) {
-      const float sc = dropout_scale(seed, ((uint64_t)b * T + t) * D + d, dropout_p);
+      const float sc = dropout_scale(seed_dev[0], ((uint64_t)b * T + t) * D + d, dropout_p);
       hd_out[(int64_t)b * ldh + d] = from_f<FT>(h * sc);
     }
   }
@@ -204,7 +204,7 @@ __global__ void cell_bwd_kernel(const float* __restrict__ dh_fc, int64_t ld_dhfc
                                 const float* __restrict__ dh_rec, float* __restrict__ dc,
                                 const float* __restrict__ gates, const float* __restrict__ c_prev,
                                 const float* __restrict__ c_new, int lstm_order, float dropout_p,
-                                uint64_t seed, int t, int T, FT* __restrict__ dpre,
+                                const uint64_t* __restrict__ seed_dev, int t, int T, FT* __restrict__ dpre,
                                 float* __restrict__ dpre_f32, int rows, int D) {
   int si, sf, so, sg;
   gate_slots(lstm_order, si, sf, so, sg);
@@ -215,7 +215,7 @@ __global__ void cell_bwd_kernel(const float* __restrict__ dh_fc, int64_t ld_dhfc
     float dh = dh_rec[i];
     if (dh_fc) {
       float g = dh_fc[(int64_t)b * ld_dhfc + d];
-      if (dropout_p > 0.f) g *= dropout_scale(seed, ((uint64_t)b * T + t) * D + d, dropout_p);
+      if (dropout_p > 0.f) g *= dropout_scale(seed_dev[0], ((uint64_t)b * T + t) * D + d, dropout_p);
       dh += g;
     }
     const float* gp = gates + (int64_t)b * 4 * D + d;
@@ -390,7 +390,7 @@ int scn_form_m(int precision, const float* u, int64_t ldu, const float* p, int64
 
 int cell_fwd(int precision, const float* preA, int64_t ldA, const float* preB, int64_t ldB,
              const float* b1, const float* b2, int lstm_order, const float* c_prev, float* c_new,
-             float* gates, void* h_out, int64_t ldh, void* hd_out, float dropout_p, uint64_t seed,
+             float* gates, void* h_out, int64_t ldh, void* hd_out, float dropout_p, const uint64_t* seed,
              int t, int T, int rows, int D, cudaStream_t st) {
   if (rows <= 0) return CAPDEC_OK;
   const int g = grid_for((int64_t)rows * D, 128);
@@ -408,7 +408,7 @@ int cell_fwd(int precision, const float* preA, int64_t ldA, const float* preB, i
 
 int cell_bwd(int precision, const float* dh_fc, int64_t ld_dhfc, const float* dh_rec, float* dc,
              const float* gates, const float* c_prev, const float* c_new, int lstm_order,
-             float dropout_p, uint64_t seed, int t, int T, void* dpre, float* dpre_f32, int rows,
+             float dropout_p, const uint64_t* seed, int t, int T, void* dpre, float* dpre_f32, int rows,
              int D, cudaStream_t st) {
   if (rows <= 0) return CAPDEC_OK;
   const int g = grid_for((int64_t)rows * D, 128);

@@ -119,6 +119,11 @@ def test_fp32_full_width_matches_oracle(kind):
             if g.abs().max().item() < 1e-9:
                 continue
             tol = max(2 * FP32_TOL, 4 * rel_err(ref32["grads"][n], g))
+            if n.startswith("attention.encoder_att") or n.startswith("attention.decoder_att"):
+                # downstream of the relu mask 1[att1+att2 > 0]: ONE mask that flips in the last ulp
+                # moves these sums by a full term (~1e-3 of the max here).  The kernel itself is pinned
+                # to 2e-5 by test_attention_bwd_step_matches_autograd on kink-free inputs.
+                tol = max(tol, 1e-2)
             e = rel_err(p.grad, g)
             if e >= tol:
                 bad.append((n, e, tol))
@@ -152,7 +157,7 @@ def test_full_size_properties(precision):
         if precision == "fp32":
             assert torch.equal(scores3, scores)
         else:       # split-K slices are reduced with fp32 atomics: order-dependent in the last bits
-            assert rel_err(scores3, scores) < 1e-3
+            assert rel_err(scores3, scores) < BF16_TOL
         loss, parts = dec.loss(scores, caps_sorted, dl, alphas)
         loss.backward()
         assert torch.equal(dec.decode_step.bias_ih.grad, dec.decode_step.bias_hh.grad)
@@ -203,3 +208,66 @@ def test_state_dict_round_trip_and_strided_encoder_features():
         assert not view.is_contiguous()
         got = dec(view, tags, caps, caplens)[0]
         assert torch.equal(got, ref_scores)
+
+
+@pytest.mark.parametrize("kind", [O.ATTENTION_SCN, O.PURE_SCN, O.PURE_ATTENTION])
+def test_graph_replay_matches_eager(kind):
+    """CUDA-graph replay of the compute phases gives the eager result bit for bit (fp32 mode is
+    deterministic), also when inputs, weights and the dropout seed change between replays."""
+    blob = load_golden("train_%s_medium" % kind)
+    with capdec.precision_scope("fp32"):
+        k, dec, (enc, tags, caps, caplens) = _load(blob)
+        dec.train()
+
+        def step(scale, seed):
+            torch.manual_seed(seed)
+            dec.zero_grad(set_to_none=True)
+            out = call_forward(dec, kind, enc * scale, tags, caps, caplens)
+            loss, _ = dec.loss(out[0], out[1], out[2], out[3])
+            loss.backward()
+            return out[0].clone(), loss.item(), [p.grad.clone() for p in dec.parameters()]
+
+        eager = [step(1.0, 1), step(0.5, 2), step(0.25, 3)]
+        capdec.set_graphs(True)
+        try:
+            for i, (scale, seed) in enumerate([(1.0, 1), (0.5, 2), (0.25, 3)]):   # eager, capture, replay
+                s, l, g = step(scale, seed)
+                assert torch.equal(s, eager[i][0])
+                assert l == eager[i][1]
+                for a, b in zip(g, eager[i][2]):
+                    assert torch.equal(a, b)
+            with torch.no_grad():          # weights change in place: the graph reads the new values
+                for p in dec.parameters():
+                    p.mul_(1.01)
+            s_graph, l_graph, _ = step(1.0, 4)
+        finally:
+            capdec.set_graphs(False)
+        s_eager, l_eager, _ = step(1.0, 4)
+        assert torch.equal(s_graph, s_eager) and l_graph == l_eager
+
+
+def test_bf16_full_width_matches_oracle():
+    """bf16 fast path at the reference dims against the fp64 oracle."""
+    dims = dict(A=512, M=512, D=512, F=512, S=1000, V=10000, E=2048)
+    lengths = [9, 5, 12, 3]
+    enc, tags, caps, caplens = O.synthetic_batch(4, dims["V"], seed=3, lengths=lengths)
+    with capdec.precision_scope("bf16"):
+        torch.manual_seed(0)
+        dec = build_decoder(O.ATTENTION_SCN, dims).eval()
+        sd = {k: v.detach().cpu() for k, v in dec.state_dict().items()}
+        scores, caps_sorted, dl, alphas, sort_ind = dec(enc.cuda(), tags.cuda(), caps.cuda(), caplens.cuda())
+        ref = oracle_run(O.ATTENTION_SCN, sd, enc, tags, caps, caplens, sort_ind=sort_ind)
+        assert rel_err(scores, ref["scores"]) < BF16_TOL
+        assert rel_err(alphas, ref["alphas"]) < BF16_TOL
+        loss, _ = dec.loss(scores, caps_sorted, dl, alphas)
+        assert abs(loss.item() - ref["loss"].item()) < BF16_TOL * abs(ref["loss"].item())
+        loss.backward()
+        bad = []
+        for n, p in dec.named_parameters():
+            g = ref["grads"][n]
+            if g.abs().max().item() < 1e-9:
+                continue
+            e = rel_err(p.grad, g)
+            if e > 0.08:
+                bad.append((n, e))
+        assert not bad, bad

@@ -150,3 +150,46 @@ def test_gemm_tc_splitk_atomics(rows, N, K, splitk):
     ref = _ref_gemm(X.float(), W.float(), None, acc)
     CF.gemm(X, W, addm=acc, out=acc, precision="bf16", splitk=splitk)      # acc += X W^T
     assert rel_err(acc, ref) < 1e-5
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("rows,P,E,A", [(32, 196, 2048, 512), (4, 196, 2048, 512), (3, 9, 40, 24),
+                                        (130, 49, 256, 128)])
+def test_attention_bwd_step_matches_autograd(precision, tol, rows, P, E, A):
+    """Backward kernel vs torch autograd (fp64) of the same math.  The pre-activations are kept
+    away from the relu kink (|att1+att2| > margin) so that no mask can flip between precisions."""
+    from capdec import functional as CF
+    g = torch.Generator().manual_seed(rows * 3 + P)
+    ft = torch.float32 if precision == "fp32" else torch.bfloat16
+    att2 = torch.randn(rows, A, generator=g) * 0.3
+    att1 = torch.randn(rows, P, A, generator=g)
+    att1 = (att1.sign() * (att1.abs() + 0.05)).to(ft).float()          # representable in ft
+    pre = att1 + att2.unsqueeze(1)
+    att1 = torch.where(pre.abs() < 0.02, att1 + 0.1 * pre.sign() + 0.1 * (pre == 0), att1).to(ft).float()
+    enc = torch.randn(rows, P, E, generator=g).relu_().to(ft).float()
+    beta_pre = torch.randn(rows, E, generator=g)
+    w_f = torch.randn(A, generator=g) / A ** 0.5 * 3
+    b_f = torch.randn(1, generator=g)
+    dz = torch.randn(rows, E, generator=g)
+    dal = torch.randn(rows, P, generator=g) * 0.1
+    # fp64 autograd reference
+    a1 = att1.double().requires_grad_(True)
+    a2 = att2.double().requires_grad_(True)
+    bp = beta_pre.double().requires_grad_(True)
+    wf = w_f.double().requires_grad_(True)
+    bf = b_f.double().requires_grad_(True)
+    e = torch.relu(a1 + a2.unsqueeze(1)) @ wf + bf
+    alpha = torch.softmax(e, dim=1)
+    awe = (enc.double() * alpha.unsqueeze(2)).sum(1)
+    z = torch.sigmoid(bp) * awe
+    ((z * dz.double()).sum() + (alpha * dal.double()).sum()).backward()
+    g1 = torch.cat([att2, beta_pre], dim=1).cuda().contiguous()
+    dbeta, datt2, dAtt1, dwf, dbf = CF.attention_bwd_step(
+        att1.to(ft).cuda().contiguous(), enc.to(ft).cuda().contiguous(), g1, A, w_f.cuda(),
+        alpha.float().cuda().contiguous(), dz.cuda(), awe.float().cuda().contiguous(),
+        dalpha_ext=dal.cuda(), precision=precision)
+    assert rel_err(dbeta.float(), bp.grad) < tol
+    assert rel_err(datt2.float(), a2.grad) < tol
+    assert rel_err(dAtt1, a1.grad) < tol
+    assert rel_err(dwf.sum(0), wf.grad) < tol
+    assert abs(dbf.sum().item() - bf.grad.item()) < 1e-4
