@@ -214,6 +214,7 @@ def run_b200(args):
     import capdec
     from capdec import _lib
     from capdec import parallel as cpar
+    from capdec import functional as CFm
     from oracle import capdec_oracle as O      # synthetic-input generator + CPU baseline only
 
     rank = int(os.environ.get("RANK", "0"))
@@ -296,9 +297,9 @@ def run_b200(args):
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        l0 = lib.capdec_launch_count()
+        l0 = CFm.launch_count()
         times = timed(step_resident, steps)
-        launches = lib.capdec_launch_count() - l0
+        launches = CFm.launch_count() - l0
         barrier()
         clocks = sampler.stop() if rank == 0 else None
         total_ms = sum(times)
@@ -350,9 +351,9 @@ def run_b200(args):
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        l0 = lib.capdec_launch_count()
+        l0 = CFm.launch_count()
         times = timed(step_resident, steps)
-        launches = lib.capdec_launch_count() - l0
+        launches = CFm.launch_count() - l0
         barrier()
         clocks = sampler.stop() if rank == 0 else None
         total_ms = sum(times)

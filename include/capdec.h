@@ -156,16 +156,21 @@ int capdec_loss_bwd(const CapdecDims* dims, const float* predictions, const floa
                     float alpha_c, float gscale, const float* gscale_dev, const float* lse,
                     float* d_predictions, void* d_logits_ft, float* d_alphas, void* stream);
 
-/* Batched beam search (reference `sample`, one independent search per image).
+/* Batched beam search (reference `sample`, one independent search per image; all G searches
+ * advance together and the host is not consulted inside the loop).
  *   enc (G,P,E) fp32 contiguous, tags (G,S) fp32 (NULL for pure_attention)
- *   k beams (<= 8), max_steps: reference stops after step > 50 -> 51 steps
- *   out_seq   (G, max_steps+1) int32 incl. <start>; out_len (G) int32; out_score (G) fp32;
- *   out_completed (G) int32: 1 if some beam emitted <end> (else best live beam)
- *   out_alpha (G, max_steps+1, P) fp32 or NULL
- *   trace_parent/word (G, max_steps, k) int32 and trace_score fp32, or NULL */
-size_t capdec_beam_workspace_bytes(const CapdecDims* dims, int G, int k, int max_steps);
+ *   k beams (<= 8); n_steps decode steps (<= 62): the reference breaks on `step > 50` AFTER
+ *   processing that step (attention_scn.py:288), i.e. n_steps = 51
+ *   out_seq   (G, n_steps+1) int32 incl. <start>, zero padded; out_len (G) int32; out_score (G) fp32
+ *   out_completed (G) int32: 1 if some beam emitted <end>; 0 -> the reference raises ValueError
+ *              and the result is the best LIVE beam (first maximum), DESIGN.md
+ *   out_alpha (G, n_steps+1, P) fp32 or NULL; entry 0 is all ones (attention_scn.py:204)
+ *   trace_parent/word (G, n_steps, k) int32 and trace_score fp32, or NULL: the top-k picks of every
+ *             step in torch.topk order (-1 / 0 once an image has finished)
+ *   dims->B, T, L are ignored. */
+size_t capdec_beam_workspace_bytes(const CapdecDims* dims, int G, int k, int n_steps);
 int capdec_beam_search(const CapdecDims* dims, const CapdecParams* params,
-                       const float* enc, const float* tags, int G, int k, int max_steps,
+                       const float* enc, const float* tags, int G, int k, int n_steps,
                        int32_t start_id, int32_t end_id,
                        int32_t* out_seq, int32_t* out_len, float* out_score, int32_t* out_completed,
                        float* out_alpha, int32_t* trace_parent, int32_t* trace_word,

@@ -88,6 +88,11 @@ class CaptionDecoderBase(nn.Module):
                                       max_steps=max_steps, want_alphas=want_alphas,
                                       want_trace=want_trace)
 
+    # The reference's `sample` dies with ValueError("max() arg is an empty sequence") when no beam
+    # emits <end> within 51 steps (attention_scn.py:292).  True keeps that error
+    # behaviour; False returns the best live beam instead (see `last_sample_completed`).
+    raise_on_incomplete = True
+
     def _sample_one(self, beam_size, word_map, encoder_out, tag_out):
         if len(word_map) != self.vocab_size:
             raise ValueError("len(word_map)=%d != vocab_size=%d" % (len(word_map), self.vocab_size))
@@ -97,6 +102,8 @@ class CaptionDecoderBase(nn.Module):
         seq = res["seq"][0, :n].tolist()
         self.last_sample_completed = bool(res["completed"][0])
         self.last_sample_score = float(res["score"][0])
+        if not self.last_sample_completed and self.raise_on_incomplete:
+            raise ValueError("max() arg is an empty sequence")
         if self.kind == "pure_scn":
             return seq
         side = encoder_out.size(1)

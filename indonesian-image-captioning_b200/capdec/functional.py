@@ -42,6 +42,13 @@ PARAM_MAP = {
 
 _graphs_enabled = os.environ.get("CAPDEC_GRAPHS", "0") == "1"
 _MAX_PLANS = 4
+_replayed_launches = 0
+
+
+def launch_count():
+    """Kernels of libcapdec launched by this process: direct launches counted by the library plus
+    the kernel nodes of every graph replay."""
+    return int(_lib.load().capdec_launch_count()) + _replayed_launches
 
 
 def set_graphs(flag):
@@ -109,6 +116,7 @@ class _Plan:
         self.d_alphas = None
         self.d_pred = None        # static copy of an autograd-provided gradient (generic path)
         self.graphs = {}          # slot -> torch.cuda.CUDAGraph
+        self.graph_nodes = {}     # slot -> kernels in the captured graph
         self.calls = {}           # slot -> number of launches so far
 
     def ensure_grad_buffers(self):
@@ -133,16 +141,22 @@ class _Plan:
     def run(self, slot, launch):
         """Graph mode: call #1 eager (also warms lazy state: tensor maps, function attributes),
         call #2 capture + replay, later calls replay."""
+        global _replayed_launches
         g = self.graphs.get(slot)
         n = self.calls.get(slot, 0)
         if g is not None:
             g.replay()
+            _replayed_launches += self.graph_nodes[slot]
         elif n == 0:
             launch()
         else:
+            lib = _lib.load()
+            before = lib.capdec_launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 launch()
+            # the capture call counted the kernels once without running them; this replay runs them
+            self.graph_nodes[slot] = lib.capdec_launch_count() - before
             g.replay()
             self.graphs[slot] = g
         self.calls[slot] = n + 1

@@ -190,7 +190,7 @@ struct Ctx {
   void* ft(size_t off, int64_t elem) const { return ws + off + (size_t)elem * p.fsz; }
 };
 
-int G(const Ctx& c, const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo,
+int G_(const Ctx& c, const void* X, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo,
       int out_ft, const float* bias, const float* addm, int64_t ldadd, int rows, int N, int K,
       int rows_alloc = 0, int batch = 1, int64_t sX = 0, int64_t sW = 0, int64_t sO = 0, int splitk = 0) {
   GemmArgs a;
@@ -324,22 +324,22 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
 
   // ---------------- prologue: time-invariant products ----------------
   if (p.att)   // att1 = enc . W_e^T + b_e      (attention.py:35, hoisted)
-    CAPDEC_TRY(G(c, c.at(o.enc_s), E, c.at(o.Wp_e), p.ldE, c.at(o.att1), A, 1, w.enc_att_b, nullptr, 0,
+    CAPDEC_TRY(G_(c, c.at(o.enc_s), E, c.at(o.Wp_e), p.ldE, c.at(o.att1), A, 1, w.enc_att_b, nullptr, 0,
                  B * P, A, E));
   // h0 -> H0 (feature type), c0 -> C[0] (fp32)   (attention_scn.py:90-92)
-  CAPDEC_TRY(G(c, c.at(o.meanF), p.ldE, c.ft(o.Wp_init, 0), p.ldE, c.at(o.H0), p.ldD, 1, w.init_h_b,
+  CAPDEC_TRY(G_(c, c.at(o.meanF), p.ldE, c.ft(o.Wp_init, 0), p.ldE, c.at(o.H0), p.ldD, 1, w.init_h_b,
                nullptr, 0, B, D, E));
-  CAPDEC_TRY(G(c, c.at(o.meanF), p.ldE, c.ft(o.Wp_init, (int64_t)D * p.ldE), p.ldE, c.at(o.C), D, 0,
+  CAPDEC_TRY(G_(c, c.at(o.meanF), p.ldE, c.ft(o.Wp_init, (int64_t)D * p.ldE), p.ldE, c.at(o.C), D, 0,
                w.init_c_b, nullptr, 0, B, D, E));
   if (p.scn) {   // v = s W_ib, q = s W_hb   (scn_cell.py:78-81, 134-143)
-    CAPDEC_TRY(G(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_ibT), p.ldS, c.at(o.v), NQ, 0, nullptr, nullptr, 0, B,
+    CAPDEC_TRY(G_(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_ibT), p.ldS, c.at(o.v), NQ, 0, nullptr, nullptr, 0, B,
                  NQ, S));
-    CAPDEC_TRY(G(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_hbT), p.ldS, c.at(o.q), NQ, 0, nullptr, nullptr, 0, B,
+    CAPDEC_TRY(G_(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_hbT), p.ldS, c.at(o.q), NQ, 0, nullptr, nullptr, 0, B,
                  NQ, S));
   }
   // embeddings of the teacher tokens and their input-side projection, all (t,b) rows at once
   CAPDEC_TRY(embedding_gather(pr, w.emb, capsD, d.L, c.at(o.Xe), p.ldM, B, T, M, V, st));
-  CAPDEC_TRY(G(c, c.at(o.Xe), p.ldM, c.at(o.Wp_xq), p.ldX, c.at(o.U), NQ, 0, nullptr, nullptr, 0, (int)R,
+  CAPDEC_TRY(G_(c, c.at(o.Xe), p.ldM, c.at(o.Wp_xq), p.ldX, c.at(o.U), NQ, 0, nullptr, nullptr, 0, (int)R,
                NQ, M));
   if (alphas) CAPDEC_CUDA_OK(cudaMemsetAsync(alphas, 0, (size_t)R * P * 4, st));
   if (ragged) {
@@ -365,7 +365,7 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     const int64_t ldh = t == 0 ? p.ldD : (int64_t)T * D;
     float* g1 = c.at<float>(o.g1) + (int64_t)t * B * NG1;
     float* U = c.at<float>(o.U) + (int64_t)t * B * NQ;
-    CAPDEC_TRY(G(c, hprev, ldh, c.at(o.Wp_cat1), p.ldD, g1, NG1, 0, c.at<float>(o.b_cat1), nullptr, 0, n,
+    CAPDEC_TRY(G_(c, hprev, ldh, c.at(o.Wp_cat1), p.ldD, g1, NG1, 0, c.at<float>(o.b_cat1), nullptr, 0, n,
                  NG1, D, B, 1, 0, 0, 0, SK));
     const float* pcol = g1 + (p.att ? A + E : 0);
     if (p.att) {
@@ -374,7 +374,7 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
       CAPDEC_TRY(attention_fwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w, w.full_att_b,
                                alphas + (int64_t)t * P, (int64_t)T * P, z, E, awe, n, 1, P, E, A, st));
       // u (in place over U_emb[t]) += z . W_x[:, M:]^T
-      CAPDEC_TRY(G(c, z, E, c.ft(o.Wp_xq, M), p.ldX, U, NQ, 0, nullptr, U, NQ, n, NQ, E, B, 1, 0, 0, 0, SK));
+      CAPDEC_TRY(G_(c, z, E, c.ft(o.Wp_xq, M), p.ldX, U, NQ, 0, nullptr, U, NQ, n, NQ, E, B, 1, 0, 0, 0, SK));
     }
     const float* c_prev = c.at<float>(o.C) + (int64_t)t * B * D;
     float* c_new = c.at<float>(o.C) + (int64_t)(t + 1) * B * D;
@@ -385,7 +385,7 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
       void* m = c.ft(o.m, (int64_t)t * 4 * B * 2 * F);
       CAPDEC_TRY(scn_form_m(pr, U, NQ, pcol, NG1, c.at<float>(o.v), c.at<float>(o.q), m, n, B, F, st));
       float* pre = c.at<float>(o.pre) + (int64_t)t * B * 4 * D;
-      CAPDEC_TRY(G(c, m, 2 * F, c.at(o.Wp_c), p.ld2F, pre, 4 * D, 0, nullptr, nullptr, 0, n, D, 2 * F, B, 4,
+      CAPDEC_TRY(G_(c, m, 2 * F, c.at(o.Wp_c), p.ld2F, pre, 4 * D, 0, nullptr, nullptr, 0, n, D, 2 * F, B, 4,
                    (int64_t)B * 2 * F, (int64_t)D * p.ld2F, D, SK));
       CAPDEC_TRY(cell_fwd(pr, pre, 4 * D, nullptr, 0, w.b_ih, w.b_hh, 0, c_prev, c_new,
                           gates, hout, (int64_t)T * D, hdout, dropout_p, c.at<uint64_t>(o.seedD), t, T, n, D, st));
@@ -395,7 +395,7 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     }
   }
   // ---------------- vocabulary projection over all (b,t) rows ----------------
-  CAPDEC_TRY(G(c, drop ? c.at(o.Hd) : c.at(o.Hall), D, c.at(o.Wp_fc), p.ldD, predictions, V, 0, w.fc_b,
+  CAPDEC_TRY(G_(c, drop ? c.at(o.Hd) : c.at(o.Hall), D, c.at(o.Wp_fc), p.ldD, predictions, V, 0, w.fc_b,
                nullptr, 0, (int)R, V, D));
   if (ragged)
     CAPDEC_TRY(zero_rows_beyond_len(predictions, c.at<int32_t>(o.lenD), B, T, V, st));
@@ -439,12 +439,12 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     dlog = c.at(o.dlogF); lddl = p.ldV;
   }
   // dH_fc[(b,t), :] = dlogits . W_fc
-  CAPDEC_TRY(G(c, dlog, lddl, c.at(o.Wp_fcT), p.ldV, c.at(o.dHfc), D, 0, nullptr, nullptr, 0, (int)R, D, V));
+  CAPDEC_TRY(G_(c, dlog, lddl, c.at(o.Wp_fcT), p.ldV, c.at(o.dHfc), D, 0, nullptr, nullptr, 0, (int)R, D, V));
   // fc.weight.grad = dlogits^T . dropout(H) ; fc.bias.grad = colsum(dlogits)     (rows in (b,t) order)
   CAPDEC_TRY(transpose_cast(pr, dlog, 1, c.at(o.tA), 1, 1, (int)R, V, 0, lddl, p.ldR, 0, 1, st));
   CAPDEC_TRY(transpose_cast(pr, drop ? c.at(o.Hd) : c.at(o.Hall), 1, c.at(o.tB), 1, 1, (int)R, D, 0, D,
                             p.ldR, 0, 1, st));
-  CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.fc_w, D, 0, nullptr, nullptr, 0, V, D, (int)R));
+  CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.fc_w, D, 0, nullptr, nullptr, 0, V, D, (int)R));
   CAPDEC_TRY(colsum(pr, dlog, 1, lddl, (int)R, V, g.fc_b, 0, st));
 
   const int SK = pr == CAPDEC_BF16 ? -1 : 0;
@@ -493,7 +493,7 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     const void* dpp;
     if (p.scn) {
       // [w_g | r_g] = dpre_g . [W_ic_g | W_hc_g]
-      CAPDEC_TRY(G(c, dpre, 4 * D, c.at(o.Wp_cT), p.ldD, wr, 2 * F, 0, nullptr, nullptr, 0, n, 2 * F,
+      CAPDEC_TRY(G_(c, dpre, 4 * D, c.at(o.Wp_cT), p.ldD, wr, 2 * F, 0, nullptr, nullptr, 0, n, 2 * F,
                    D, B, 4, D, (int64_t)2 * F * p.ldD, (int64_t)B * 2 * F, SK));
       void* du_t = c.ft(o.du, (int64_t)t * B * NQ);
       void* dp_t = c.ft(o.dp, (int64_t)t * B * NQ);
@@ -505,10 +505,10 @@ int backward(const CapdecDims& d, const CapdecParams& w,
       du = dpre; dpp = dpre;
     }
     // dh_{t-1} (recurrent part) = dp . W_hq^T
-    CAPDEC_TRY(G(c, dpp, NQ, c.at(o.Wp_hq), p.ldNQ, dh_rec, D, 0, nullptr, nullptr, 0, n, D, NQ, B, 1, 0, 0, 0, SK));
+    CAPDEC_TRY(G_(c, dpp, NQ, c.at(o.Wp_hq), p.ldNQ, dh_rec, D, 0, nullptr, nullptr, 0, n, D, NQ, B, 1, 0, 0, 0, SK));
     if (p.att) {
       // dz = du . W_x[M:, :]^T
-      CAPDEC_TRY(G(c, du, NQ, c.ft(o.Wp_xin, (int64_t)M * p.ldNQ), p.ldNQ, dz, E, 0, nullptr,
+      CAPDEC_TRY(G_(c, du, NQ, c.ft(o.Wp_xin, (int64_t)M * p.ldNQ), p.ldNQ, dz, E, 0, nullptr,
                    nullptr, 0, n, E, NQ, B, 1, 0, 0, 0, SK));
       void* dba = c.ft(o.dba, (int64_t)t * B * p.ldEA);
       CAPDEC_TRY(attention_bwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w,
@@ -518,7 +518,7 @@ int backward(const CapdecDims& d, const CapdecParams& w,
                                c.at<float>(o.dAtt1), c.at<float>(o.dwf) + (int64_t)t * B * A,
                                c.at<float>(o.dbf) + (int64_t)t * B, n, P, E, A, st));
       // dh_{t-1} += [dbeta_pre | datt2] . [W_beta^T | W_d^T]^T
-      CAPDEC_TRY(G(c, dba, p.ldEA, c.at(o.Wp_b6), p.ldEA, dh_rec, D, 0, nullptr, dh_rec, D, n, D, E + A, B, 1,
+      CAPDEC_TRY(G_(c, dba, p.ldEA, c.at(o.Wp_b6), p.ldEA, dh_rec, D, 0, nullptr, dh_rec, D, n, D, E + A, B, 1,
                    0, 0, 0, SK));
     }
   }
@@ -543,41 +543,41 @@ int backward(const CapdecDims& d, const CapdecParams& w,
                                 c.ft(o.tB, (int64_t)gg * 2 * F * p.ldR), 1, T, B, 2 * F,
                                 (int64_t)4 * B * 2 * F, 2 * F, p.ldR, B, 1, st));
     // weight_ic.grad[:, gF:(g+1)F] = dpre_g^T . (u_g*v_g) ; weight_hc.grad likewise with (p_g*q_g)
-    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ic, NQ, 0, nullptr, nullptr, 0, D, F, Ri, 0, 4,
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ic, NQ, 0, nullptr, nullptr, 0, D, F, Ri, 0, 4,
                  (int64_t)D * p.ldR, (int64_t)2 * F * p.ldR, F));
-    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.ft(o.tB, (int64_t)F * p.ldR), p.ldR, g.w_hc, NQ, 0, nullptr, nullptr,
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.ft(o.tB, (int64_t)F * p.ldR), p.ldR, g.w_hc, NQ, 0, nullptr, nullptr,
                  0, D, F, Ri, 0, 4, (int64_t)D * p.ldR, (int64_t)2 * F * p.ldR, F));
     // weight_ha.grad [D][4F] = H_prev^T . dp
     CAPDEC_TRY(transpose_cast(pr, c.at(o.dp), 1, c.at(o.tB), 1, 1, Ri, NQ, 0, NQ, p.ldR, 0, 1, st));
-    CAPDEC_TRY(G(c, c.at(o.tC), p.ldR, c.at(o.tB), p.ldR, g.w_ha, NQ, 0, nullptr, nullptr, 0, D, NQ, Ri));
+    CAPDEC_TRY(G_(c, c.at(o.tC), p.ldR, c.at(o.tB), p.ldR, g.w_ha, NQ, 0, nullptr, nullptr, 0, D, NQ, Ri));
     // weight_ia.grad [X][4F] = [Xe | z]^T . du
     CAPDEC_TRY(transpose_cast(pr, c.at(o.du), 1, c.at(o.tB), 1, 1, Ri, NQ, 0, NQ, p.ldR, 0, 1, st));
     CAPDEC_TRY(transpose_cast(pr, c.at(o.Xe), 1, c.at(o.tA), 1, 1, Ri, M, 0, p.ldM, p.ldR, 0, 1, st));
-    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia, NQ, 0, nullptr, nullptr, 0, M, NQ, Ri));
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia, NQ, 0, nullptr, nullptr, 0, M, NQ, Ri));
     if (p.att) {
       CAPDEC_TRY(transpose_cast(pr, c.at(o.z), 1, c.at(o.tA), 1, 1, Ri, E, 0, E, p.ldR, 0, 1, st));
-      CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia + (int64_t)M * NQ, NQ, 0, nullptr,
+      CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia + (int64_t)M * NQ, NQ, 0, nullptr,
                    nullptr, 0, E, NQ, Ri));
     }
     // embedding.weight.grad: dXe = du . W_ia[:M]^T, scattered to the consumed token rows
-    CAPDEC_TRY(G(c, c.at(o.du), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
+    CAPDEC_TRY(G_(c, c.at(o.du), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
     // weight_ib.grad [S][4F] = s^T . sum_t dv ; weight_hb.grad = s^T . sum_t dq
     // (the tag matrix as the forward saw it: the feature-type copy kept in the workspace)
     CAPDEC_TRY(transpose_cast(pr, c.at(o.tagsF), 1, c.at(o.tA), 1, 1, B, S, 0, p.ldS, p.ldB, 0, 1, st));
     CAPDEC_TRY(transpose_cast(pr, c.at(o.dv_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
-    CAPDEC_TRY(G(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_ib, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_ib, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
     CAPDEC_TRY(transpose_cast(pr, c.at(o.dq_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
-    CAPDEC_TRY(G(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_hb, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_hb, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
   } else {
     // LSTM: weight_hh.grad [4D][D] = dpre^T . H_prev ; weight_ih.grad [4D][X] = dpre^T . [Xe | z]
-    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tC), p.ldR, g.w_ha, D, 0, nullptr, nullptr, 0, NQ, D, Ri));
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tC), p.ldR, g.w_ha, D, 0, nullptr, nullptr, 0, NQ, D, Ri));
     CAPDEC_TRY(transpose_cast(pr, c.at(o.Xe), 1, c.at(o.tB), 1, 1, Ri, M, 0, p.ldM, p.ldR, 0, 1, st));
-    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia, X, 0, nullptr, nullptr, 0, NQ, M, Ri));
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia, X, 0, nullptr, nullptr, 0, NQ, M, Ri));
     if (p.att) {
       CAPDEC_TRY(transpose_cast(pr, c.at(o.z), 1, c.at(o.tB), 1, 1, Ri, E, 0, E, p.ldR, 0, 1, st));
-      CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia + M, X, 0, nullptr, nullptr, 0, NQ, E, Ri));
+      CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia + M, X, 0, nullptr, nullptr, 0, NQ, E, Ri));
     }
-    CAPDEC_TRY(G(c, c.at(o.dpre), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
+    CAPDEC_TRY(G_(c, c.at(o.dpre), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
   }
   if (g.emb) {
     CAPDEC_CUDA_OK(cudaMemsetAsync(g.emb, 0, (size_t)V * M * 4, st));
@@ -588,8 +588,8 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   if (p.att) {
     // f_beta / decoder_att: [dbeta_pre | datt2]^T . H_prev
     CAPDEC_TRY(transpose_cast(pr, c.at(o.dba), 1, c.at(o.tA), 1, 1, Ri, E + A, 0, p.ldEA, p.ldR, 0, 1, st));
-    CAPDEC_TRY(G(c, c.at(o.tA), p.ldR, c.at(o.tC), p.ldR, g.f_beta_w, D, 0, nullptr, nullptr, 0, E, D, Ri));
-    CAPDEC_TRY(G(c, c.ft(o.tA, (int64_t)E * p.ldR), p.ldR, c.at(o.tC), p.ldR, g.dec_att_w, D, 0, nullptr,
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tC), p.ldR, g.f_beta_w, D, 0, nullptr, nullptr, 0, E, D, Ri));
+    CAPDEC_TRY(G_(c, c.ft(o.tA, (int64_t)E * p.ldR), p.ldR, c.at(o.tC), p.ldR, g.dec_att_w, D, 0, nullptr,
                  nullptr, 0, A, D, Ri));
     CAPDEC_TRY(colsum(pr, c.at(o.dba), 1, p.ldEA, Ri, E, g.f_beta_b, 0, st));
     CAPDEC_TRY(colsum(pr, c.ft(o.dba, E), 1, p.ldEA, Ri, A, g.dec_att_b, 0, st));
@@ -601,16 +601,207 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     CAPDEC_TRY(colsum(pr, c.at(o.dAtt1), 0, A, BP, A, g.enc_att_b, 0, st));
     CAPDEC_TRY(transpose_cast(pr, c.at(o.dAtt1), 0, c.at(o.tA), 1, 1, BP, A, 0, A, p.ldBP, 0, 1, st));
     CAPDEC_TRY(transpose_cast(pr, c.at(o.enc_s), 1, c.at(o.tB), 1, 1, BP, E, 0, E, p.ldBP, 0, 1, st));
-    CAPDEC_TRY(G(c, c.at(o.tA), p.ldBP, c.at(o.tB), p.ldBP, g.enc_att_w, E, 0, nullptr, nullptr, 0, A, E, BP));
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldBP, c.at(o.tB), p.ldBP, g.enc_att_w, E, 0, nullptr, nullptr, 0, A, E, BP));
   }
   // init_h / init_c: dh0 = dh_rec, dc0 = dc after the last reverse step
   CAPDEC_TRY(transpose_cast(pr, c.at(o.mean), 0, c.at(o.tB), 1, 1, B, E, 0, E, p.ldB, 0, 1, st));
   CAPDEC_TRY(transpose_cast(pr, c.at(o.dh_rec), 0, c.at(o.tA), 1, 1, B, D, 0, D, p.ldB, 0, 1, st));
-  CAPDEC_TRY(G(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.init_h_w, E, 0, nullptr, nullptr, 0, D, E, B));
+  CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.init_h_w, E, 0, nullptr, nullptr, 0, D, E, B));
   CAPDEC_TRY(colsum(pr, c.at(o.dh_rec), 0, D, B, D, g.init_h_b, 0, st));
   CAPDEC_TRY(transpose_cast(pr, c.at(o.dc), 0, c.at(o.tA), 1, 1, B, D, 0, D, p.ldB, 0, 1, st));
-  CAPDEC_TRY(G(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.init_c_w, E, 0, nullptr, nullptr, 0, D, E, B));
+  CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.init_c_w, E, 0, nullptr, nullptr, 0, D, E, B));
   CAPDEC_TRY(colsum(pr, c.at(o.dc), 0, D, B, D, g.init_c_b, 0, st));
+  return CAPDEC_OK;
+}
+
+
+// =====================================================================================
+// Batched beam search (reference `sample`: attention_scn.py:160-296, pure_scn.py:142-249,
+// pure_attention.py:153-281).  G independent searches of k beams advance together as
+// R = G*k rows; image g owns rows g*k .. g*k+k-1 and all of them read the SAME feature map
+// (the reference merely `expand`s it, :189), so the attention kernel runs with
+// rows_per_map = k.  Every step is the training step's kernel sequence in eval mode followed
+// by the vocabulary GEMM, the fused log-softmax + top-k selection (beam.cu) and the re-ordering
+// of the recurrent state; the host is never consulted inside the loop.
+// =====================================================================================
+namespace {
+
+struct BeamPlan {
+  Plan w;                 // weight offsets only (built for B = 1, T = 1)
+  int R;
+  struct Off {
+    size_t enc_f, att1, mean, meanF, meanX, tagsG, tagsX, v, q, H, C, Hn, Cn, Xe, U, g1, z, m, pre,
+        logits, alpha_hist, prev_word, scoreA, scoreB, src_row, live, krem, has_done, best_score,
+        best_t, best_parent, bp_parent, bp_word, total;
+  } o;
+};
+
+int make_beam_plan(const CapdecDims& d_in, int G, int k, int n_steps, bool want_alpha, BeamPlan* bp) {
+  CAPDEC_REQUIRE(G > 0 && k >= 1 && k <= 8 && n_steps >= 1 && n_steps <= 62, CAPDEC_ERR_BAD_SHAPE,
+                 "beam search: bad G=%d k=%d steps=%d", G, k, n_steps);
+  CapdecDims d = d_in;
+  d.B = 1; d.T = 1; d.L = 2;
+  CAPDEC_TRY(make_plan(d, false, &bp->w));
+  const Plan& p = bp->w;
+  const int64_t R = (int64_t)G * k;
+  bp->R = (int)R;
+  const size_t f = p.fsz;
+  const int64_t P = d.P, E = d.E, A = d.A, D = d.D, F = d.F, V = d.V, NQ = p.NQ, NG1 = p.NG1;
+  size_t cur = p.o.enc_s;            // first byte after the packed weights
+  auto take = [&](size_t bytes) { size_t at = cur; cur += (size_t)round_up((int64_t)bytes, 256); return at; };
+  BeamPlan::Off& o = bp->o;
+  memset(&o, 0, sizeof o);
+  o.enc_f = take((size_t)G * P * E * f);
+  if (p.att) o.att1 = take((size_t)G * P * A * f);
+  o.mean = take((size_t)G * E * 4);
+  o.meanF = take((size_t)G * p.ldE * f);
+  o.meanX = take((size_t)R * p.ldE * f);
+  if (p.scn) {
+    o.tagsG = take((size_t)G * p.ldS * f);
+    o.tagsX = take((size_t)R * p.ldS * f);
+    o.v = take((size_t)R * NQ * 4);
+    o.q = take((size_t)R * NQ * 4);
+  }
+  o.H = take((size_t)R * p.ldD * f);
+  o.C = take((size_t)R * D * 4);
+  o.Hn = take((size_t)R * p.ldD * f);
+  o.Cn = take((size_t)R * D * 4);
+  o.Xe = take((size_t)R * p.ldM * f);
+  o.U = take((size_t)R * NQ * 4);
+  o.g1 = take((size_t)R * NG1 * 4);
+  if (p.att) o.z = take((size_t)R * E * f);
+  if (p.scn) {
+    o.m = take((size_t)4 * R * 2 * F * f);
+    o.pre = take((size_t)R * 4 * D * 4);
+  }
+  o.logits = take((size_t)R * V * 4);
+  if (p.att) o.alpha_hist = take((size_t)(want_alpha ? n_steps : 1) * R * P * 4);
+  o.prev_word = take((size_t)R * 4);
+  o.scoreA = take((size_t)R * 4);
+  o.scoreB = take((size_t)R * 4);
+  o.src_row = take((size_t)R * 4);
+  o.live = take((size_t)G * 4);
+  o.krem = take((size_t)G * 4);
+  o.has_done = take((size_t)G * 4);
+  o.best_score = take((size_t)G * 4);
+  o.best_t = take((size_t)G * 4);
+  o.best_parent = take((size_t)G * 4);
+  o.bp_parent = take((size_t)n_steps * R * 4);
+  o.bp_word = take((size_t)n_steps * R * 4);
+  o.total = cur;
+  return CAPDEC_OK;
+}
+
+}  // namespace
+
+size_t beam_workspace_bytes(const CapdecDims& d, int G, int k, int n_steps) {
+  BeamPlan bp;
+  // sized for the alpha history; a search without it needs less but never more
+  if (make_beam_plan(d, G, k, n_steps, true, &bp) != CAPDEC_OK) return 0;
+  return bp.o.total;
+}
+
+int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, const float* tags, int G,
+                int k, int n_steps, int32_t start_id, int32_t end_id, int32_t* out_seq,
+                int32_t* out_len, float* out_score, int32_t* out_completed, float* out_alpha,
+                int32_t* trace_parent, int32_t* trace_word, float* trace_score, void* workspace,
+                size_t ws_bytes, cudaStream_t st) {
+  BeamPlan bp;
+  const bool want_alpha = out_alpha != nullptr && d.kind != CAPDEC_PURE_SCN;
+  CAPDEC_TRY(make_beam_plan(d, G, k, n_steps, want_alpha, &bp));
+  CAPDEC_REQUIRE(ws_bytes >= bp.o.total, CAPDEC_ERR_WORKSPACE, "beam workspace %zu < %zu", ws_bytes,
+                 bp.o.total);
+  CAPDEC_REQUIRE(((uintptr_t)workspace % 256) == 0, CAPDEC_ERR_BAD_ARG, "workspace must be 256-B aligned");
+  CAPDEC_REQUIRE(start_id >= 0 && start_id < d.V && end_id >= 0 && end_id < d.V, CAPDEC_ERR_BAD_ARG,
+                 "start/end token outside the vocabulary");
+  Ctx c;
+  c.p = bp.w;
+  c.ws = (uint8_t*)workspace;
+  c.st = st;
+  c.prec = d.precision;
+  const Plan& p = c.p;
+  const BeamPlan::Off& o = bp.o;
+  const int pr = c.prec;
+  const int R = bp.R, P = d.P, E = d.E, A = d.A, M = d.M, D = d.D, F = d.F, S = d.S, V = d.V, NQ = p.NQ,
+            NG1 = p.NG1;
+  CAPDEC_REQUIRE(!p.scn || tags, CAPDEC_ERR_BAD_ARG, "beam search: tags is NULL");
+
+  CAPDEC_TRY(pack_weights(c, w));
+  // ---- per-image prologue (attention_scn.py:176-214) ----
+  CAPDEC_TRY(gather_features(pr, enc, (int64_t)P * E, E, 1, nullptr, c.at(o.enc_f), c.at<float>(o.mean),
+                             c.at(o.meanF), p.ldE, G, P, E, st));
+  if (p.att)
+    CAPDEC_TRY(G_(c, c.at(o.enc_f), E, c.at(p.o.Wp_e), p.ldE, c.at(o.att1), A, 1, w.enc_att_b, nullptr, 0,
+                  G * P, A, E));
+  CAPDEC_TRY(expand_rows(pr, c.at(o.meanF), p.ldE, c.at(o.meanX), p.ldE, G, k, E, st));
+  CAPDEC_TRY(G_(c, c.at(o.meanX), p.ldE, c.ft(p.o.Wp_init, 0), p.ldE, c.at(o.H), p.ldD, 1, w.init_h_b,
+                nullptr, 0, R, D, E));
+  CAPDEC_TRY(G_(c, c.at(o.meanX), p.ldE, c.ft(p.o.Wp_init, (int64_t)D * p.ldE), p.ldE, c.at(o.C), D, 0,
+                w.init_c_b, nullptr, 0, R, D, E));
+  if (p.scn) {
+    CAPDEC_TRY(copy_cast(pr, tags, 0, S, c.at(o.tagsG), 1, p.ldS, G, S, st));
+    CAPDEC_TRY(expand_rows(pr, c.at(o.tagsG), p.ldS, c.at(o.tagsX), p.ldS, G, k, S, st));
+    CAPDEC_TRY(G_(c, c.at(o.tagsX), p.ldS, c.at(p.o.Wp_ibT), p.ldS, c.at(o.v), NQ, 0, nullptr, nullptr, 0,
+                  R, NQ, S));
+    CAPDEC_TRY(G_(c, c.at(o.tagsX), p.ldS, c.at(p.o.Wp_hbT), p.ldS, c.at(o.q), NQ, 0, nullptr, nullptr, 0,
+                  R, NQ, S));
+  }
+  int32_t* prev_word = c.at<int32_t>(o.prev_word);
+  int32_t* src_row = c.at<int32_t>(o.src_row);
+  int32_t* live = c.at<int32_t>(o.live);
+  int32_t* krem = c.at<int32_t>(o.krem);
+  int32_t* has_done = c.at<int32_t>(o.has_done);
+  float* best_score = c.at<float>(o.best_score);
+  int32_t* best_t = c.at<int32_t>(o.best_t);
+  int32_t* best_parent = c.at<int32_t>(o.best_parent);
+  int32_t* bpp = c.at<int32_t>(o.bp_parent);
+  int32_t* bpw = c.at<int32_t>(o.bp_word);
+  float* score_in = c.at<float>(o.scoreA);
+  float* score_out = c.at<float>(o.scoreB);
+  CAPDEC_TRY(beam_init(prev_word, score_in, live, krem, has_done, best_score, best_t, best_parent, G, k,
+                       start_id, st));
+  CAPDEC_CUDA_OK(cudaMemsetAsync(score_out, 0, (size_t)R * 4, st));
+  CAPDEC_CUDA_OK(cudaMemsetAsync(bpp, 0, (size_t)n_steps * R * 4, st));
+  CAPDEC_CUDA_OK(cudaMemsetAsync(bpw, 0, (size_t)n_steps * R * 4, st));
+
+  // ---- the search loop (attention_scn.py:216-290) ----
+  for (int t = 0; t < n_steps; ++t) {
+    float* g1 = c.at<float>(o.g1);
+    float* U = c.at<float>(o.U);
+    CAPDEC_TRY(beam_embed(pr, w.emb, prev_word, c.at(o.Xe), p.ldM, R, M, V, st));
+    CAPDEC_TRY(G_(c, c.at(o.Xe), p.ldM, c.at(p.o.Wp_xq), p.ldX, U, NQ, 0, nullptr, nullptr, 0, R, NQ, M));
+    CAPDEC_TRY(G_(c, c.at(o.H), p.ldD, c.at(p.o.Wp_cat1), p.ldD, g1, NG1, 0, c.at<float>(p.o.b_cat1),
+                  nullptr, 0, R, NG1, D));
+    const float* pcol = g1 + (p.att ? A + E : 0);
+    if (p.att) {
+      float* alpha_t = c.at<float>(o.alpha_hist) + (want_alpha ? (int64_t)t * R * P : 0);
+      CAPDEC_TRY(attention_fwd(pr, c.at(o.att1), c.at(o.enc_f), g1, NG1, A, w.full_att_w, w.full_att_b,
+                               alpha_t, P, c.at(o.z), E, nullptr, R, k, P, E, A, st));
+      CAPDEC_TRY(G_(c, c.at(o.z), E, c.ft(p.o.Wp_xq, M), p.ldX, U, NQ, 0, nullptr, U, NQ, R, NQ, E));
+    }
+    if (p.scn) {
+      CAPDEC_TRY(scn_form_m(pr, U, NQ, pcol, NG1, c.at<float>(o.v), c.at<float>(o.q), c.at(o.m), R, R, F, st));
+      CAPDEC_TRY(G_(c, c.at(o.m), 2 * F, c.at(p.o.Wp_c), p.ld2F, c.at(o.pre), 4 * D, 0, nullptr, nullptr, 0,
+                    R, D, 2 * F, R, 4, (int64_t)R * 2 * F, (int64_t)D * p.ld2F, D));
+      CAPDEC_TRY(cell_fwd(pr, c.at<float>(o.pre), 4 * D, nullptr, 0, w.b_ih, w.b_hh, 0, c.at<float>(o.C),
+                          c.at<float>(o.Cn), nullptr, c.at(o.Hn), p.ldD, nullptr, 0.f, nullptr, 0, 1, R, D, st));
+    } else {
+      CAPDEC_TRY(cell_fwd(pr, U, NQ, pcol, NG1, w.b_ih, w.b_hh, 1, c.at<float>(o.C), c.at<float>(o.Cn),
+                          nullptr, c.at(o.Hn), p.ldD, nullptr, 0.f, nullptr, 0, 1, R, D, st));
+    }
+    // scores = log_softmax(fc(h)) (:235-236; eval mode: dropout is the identity)
+    CAPDEC_TRY(G_(c, c.at(o.Hn), p.ldD, c.at(p.o.Wp_fc), p.ldD, c.at(o.logits), V, 0, w.fc_b, nullptr, 0,
+                  R, V, D));
+    CAPDEC_TRY(beam_select(c.at<float>(o.logits), V, G, k, t, end_id, score_in, score_out, prev_word,
+                           src_row, live, krem, has_done, best_score, best_t, best_parent, bpp, bpw,
+                           trace_parent, trace_word, trace_score, n_steps, st));
+    CAPDEC_TRY(beam_gather_state(pr, c.at(o.Hn), c.at<float>(o.Cn), c.at(o.H), c.at<float>(o.C), src_row,
+                                 live, R, k, D, p.ldD, st));
+    float* tmp = score_in; score_in = score_out; score_out = tmp;
+  }
+  CAPDEC_TRY(beam_finalize(G, k, n_steps, P, start_id, end_id, score_in, live, has_done, best_score, best_t,
+                           best_parent, bpp, bpw, want_alpha ? c.at<float>(o.alpha_hist) : nullptr, out_seq,
+                           out_len, out_score, out_completed, out_alpha, st));
   return CAPDEC_OK;
 }
 

@@ -61,6 +61,30 @@ int concat_bias(float* dst, const float* a, int na, const float* b, int nb, int 
 int zero_rows_beyond_len(float* x, const int32_t* len_d, int B, int T, int64_t row_elems,
                          cudaStream_t st);
 
+// dst[(g*k + j)*ldd + c] = src[g*lds + c]   (feature type both sides; beam rows share their image's row)
+int expand_rows(int precision, const void* src, int64_t lds, void* dst, int64_t ldd, int G, int k, int C,
+                cudaStream_t st);
+
+// ---- beam.cu ----
+int beam_init(int32_t* prev_word, float* score, int32_t* live, int32_t* krem, int32_t* has_done,
+              float* best_score, int32_t* best_t, int32_t* best_parent, int G, int k, int32_t start_id,
+              cudaStream_t st);
+int beam_embed(int precision, const float* emb, const int32_t* prev_word, void* Xe, int64_t ldx, int rows,
+               int M, int V, cudaStream_t st);
+int beam_gather_state(int precision, const void* h_new, const float* c_new, void* h_state, float* c_state,
+                      const int32_t* src_row, const int32_t* live, int rows, int k, int D, int64_t ldh,
+                      cudaStream_t st);
+int beam_select(const float* logits, int V, int G, int k, int t, int32_t end_id, const float* score_in,
+                float* score_out, int32_t* prev_word, int32_t* src_row, int32_t* live, int32_t* krem,
+                int32_t* has_done, float* best_score, int32_t* best_t, int32_t* best_parent,
+                int32_t* bp_parent, int32_t* bp_word, int32_t* tr_parent, int32_t* tr_word,
+                float* tr_score, int n_steps, cudaStream_t st);
+int beam_finalize(int G, int k, int n_steps, int P, int32_t start_id, int32_t end_id, const float* score,
+                  const int32_t* live, const int32_t* has_done, const float* best_score,
+                  const int32_t* best_t, const int32_t* best_parent, const int32_t* bp_parent,
+                  const int32_t* bp_word, const float* alpha_hist, int32_t* out_seq, int32_t* out_len,
+                  float* out_score, int32_t* out_completed, float* out_alpha, cudaStream_t st);
+
 // ---- loss.cu ----
 int loss_fwd(const CapdecDims& d, const float* pred, const float* alphas, const int64_t* caps,
              const int32_t* len_d, int n_tokens, float alpha_c, float* loss_out, float* lse_out,

@@ -120,18 +120,70 @@ __global__ void embedding_gather_kernel(const float* __restrict__ emb,
   for (int i = threadIdx.x; i < M; i += blockDim.x) dst[i] = from_f<FT>(src[i]);
 }
 
+// Deterministic scatter: the block of row r = (t,b) is the LEADER of its token if no earlier valid row
+// carries the same token; the leader sums every row of that token in row order and stores the result
+// (no atomics -> bit-reproducible gradients, which the CUDA-graph replay test relies on).
 __global__ void embedding_scatter_add_kernel(const float* __restrict__ dXe, int64_t ldx,
                                              const int64_t* __restrict__ caps, int L,
                                              const int32_t* __restrict__ len_d, float* dEmb, int B,
                                              int T, int M, int V) {
+  extern __shared__ int s_rows[];              // rows that carry this block's token (ascending)
+  __shared__ int s_n, s_dup;
   const int r = blockIdx.x;
   const int t = r / B, b = r - t * B;
   if (t >= len_d[b]) return;
-  int64_t w = caps[(int64_t)b * L + t];
+  const int64_t w = caps[(int64_t)b * L + t];
   if (w < 0 || w >= V) return;
-  const float* src = dXe + (int64_t)r * ldx;
+  if (threadIdx.x == 0) { s_n = 0; s_dup = 0; }
+  __syncthreads();
+  for (int r2 = threadIdx.x; r2 < r; r2 += blockDim.x) {
+    const int t2 = r2 / B, b2 = r2 - t2 * B;
+    if (t2 < len_d[b2] && caps[(int64_t)b2 * L + t2] == w) s_dup = 1;
+  }
+  __syncthreads();
+  if (s_dup) return;
+  // leader: collect the later rows with the same token, in ascending order (chunked ballot-free scan)
+  const int R = B * T;
+  for (int base = r; base < R; base += blockDim.x) {
+    const int r2 = base + threadIdx.x;
+    bool hit = false;
+    if (r2 < R) {
+      const int t2 = r2 / B, b2 = r2 - t2 * B;
+      hit = t2 < len_d[b2] && caps[(int64_t)b2 * L + t2] == w;
+    }
+    // ordered compaction inside the chunk: thread i appends after all hits of threads < i
+    __shared__ int s_flag[128];
+    s_flag[threadIdx.x] = hit ? 1 : 0;
+    __syncthreads();
+    if (hit) {
+      int pos = s_n;
+      for (int i = 0; i < (int)threadIdx.x; ++i) pos += s_flag[i];
+      s_rows[pos] = r2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int c = 0;
+      for (int i = 0; i < (int)blockDim.x; ++i) c += s_flag[i];
+      s_n += c;
+    }
+    __syncthreads();
+  }
+  const int n = s_n;
   float* dst = dEmb + w * M;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) atomicAdd(dst + i, src[i]);
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j) acc += dXe[(int64_t)s_rows[j] * ldx + i];
+    dst[i] = acc;
+  }
+}
+
+template <typename FT>
+__global__ void expand_rows_kernel(const FT* __restrict__ src, int64_t lds, FT* __restrict__ dst,
+                                   int64_t ldd, int k, int C) {
+  const int r = blockIdx.x;
+  const FT* s = src + (int64_t)(r / k) * lds;
+  FT* d = dst + (int64_t)r * ldd;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) d[i] = s[i];
 }
 
 template <typename FT>
@@ -371,7 +423,27 @@ int embedding_scatter_add(const float* dXe, int64_t ldx, const int64_t* caps, in
                           const int32_t* len_d, float* dEmb, int B, int T, int M, int V,
                           cudaStream_t st) {
   if (B * T <= 0) return CAPDEC_OK;
-  embedding_scatter_add_kernel<<<B * T, 128, 0, st>>>(dXe, ldx, caps, L, len_d, dEmb, B, T, M, V);
+  CAPDEC_REQUIRE((size_t)B * T * sizeof(int) <= 160 * 1024, CAPDEC_ERR_BAD_SHAPE,
+                 "embedding scatter: B*T=%d rows exceed the shared row list", B * T);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CAPDEC_CUDA_OK(cudaFuncSetAttribute(embedding_scatter_add_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  embedding_scatter_add_kernel<<<B * T, 128, (size_t)B * T * sizeof(int), st>>>(dXe, ldx, caps, L, len_d,
+                                                                             dEmb, B, T, M, V);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int expand_rows(int precision, const void* src, int64_t lds, void* dst, int64_t ldd, int G, int k, int C,
+                cudaStream_t st) {
+  if (G * k <= 0) return CAPDEC_OK;
+  if (precision == CAPDEC_BF16)
+    expand_rows_kernel<bf16><<<G * k, 128, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, k, C);
+  else
+    expand_rows_kernel<float><<<G * k, 128, 0, st>>>((const float*)src, lds, (float*)dst, ldd, k, C);
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }

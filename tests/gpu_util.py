@@ -51,6 +51,13 @@ def rel_err(got, ref):
     return (got - ref).abs().max().item() / denom
 
 
+def rel_err_fro(got, ref):
+    """Frobenius-norm relative error: robust to single-element jumps (relu-kink flips)."""
+    ref = ref.detach().double().cpu()
+    got = got.detach().double().cpu()
+    return (got - ref).norm().item() / max(ref.norm().item(), 1e-30)
+
+
 def oracle_run(kind, sd, enc, tags, caps, caplens, sort_ind=None, dtype=torch.float64, alpha_c=1.0):
     """Forward + loss + backward through the oracle (CPU, fp64 by default)."""
     p = {k: v.detach().cpu().to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
