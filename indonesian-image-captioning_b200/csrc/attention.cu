@@ -57,7 +57,9 @@ attn_fwd_kernel(FwdArgs a) {
   float* al = sc + Ppad;           // [Ppad] alpha
   float* red = al + Ppad;          // [NTHREADS * VEC] cross-group reduction
 
+  pdl_launch_dependents();
   if (CL > 1) cluster.barrier_arrive();     // "everyone has started" barrier, waited on before the push
+  pdl_wait();                               // g1 / features come from the previous kernels of the stream
 
   const FT* att1 = (const FT*)a.att1 + (int64_t)map * P * A;
   const FT* enc = (const FT*)a.enc + (int64_t)map * P * E;
@@ -254,7 +256,9 @@ attn_bwd_kernel(BwdArgs a) {
   float* redA = de + Ppad;                    // [NWARPS][2][Apad]
   float* partA = redA + NWARPS * 2 * Apad;    // [CL_MAX][2][Apad]  (used on rank 0)
 
+  pdl_launch_dependents();
   if (CL > 1) cluster.barrier_arrive();
+  pdl_wait();
 
   const FT* att1 = (const FT*)a.att1 + (int64_t)row * P * A;
   const FT* enc = (const FT*)a.enc + (int64_t)row * P * E;
@@ -452,22 +456,9 @@ size_t bwd_smem(int P, int A) {
   return (size_t)(CL_MAX * Ppad + 2 * Ppad + NWARPS * 2 * Apad + CL_MAX * 2 * Apad) * sizeof(float);
 }
 
-template <typename KernelT, typename ArgsT>
-int launch_cluster(KernelT kernel, const ArgsT& args, int rows, int CL, size_t smem, cudaStream_t st) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(rows * CL, 1, 1);
-  cfg.blockDim = dim3(NTHREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CAPDEC_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, args));
+template <typename ArgsT>
+int launch_cluster(void (*kernel)(ArgsT), const ArgsT& args, int rows, int CL, size_t smem, cudaStream_t st) {
+  CAPDEC_CUDA_OK(launch_pdl(kernel, dim3(rows * CL, 1, 1), dim3(NTHREADS, 1, 1), smem, st, CL, args));
   count_launch();
   return CAPDEC_OK;
 }

@@ -1,5 +1,6 @@
 // capi.cu -- the extern "C" surface of libcapdec.so (see include/capdec.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -21,6 +22,14 @@ const char* get_error() { return g_err; }
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* s = getenv("CAPDEC_PDL");
+    return !(s && s[0] == '0');
+  }();
+  return on;
+}
 
 static std::once_flag g_init_once;
 static int g_init_rc = CAPDEC_OK;

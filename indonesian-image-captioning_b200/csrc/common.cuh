@@ -54,6 +54,39 @@ void count_launch();          // process-wide kernel-launch counter (capdec_laun
     }                                                                               \
   } while (0)
 
+bool pdl_enabled();           // CAPDEC_PDL=0 switches programmatic dependent launch off
+
+// Launch `kernel` on `st` with the PDL attribute (and an optional cluster x-dimension).  Every
+// kernel launched through here MUST call pdl_wait() (or pdl_prologue()) before its first global
+// memory access.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t st, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
@@ -123,6 +156,19 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while the
+// previous kernel of the stream is still draining.  pdl_wait() blocks until that kernel has
+// completed and its writes are visible; nothing produced by it may be touched before.
+// pdl_launch_dependents() lets the NEXT kernel begin its own launch early.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // counter-based dropout keep decision: splitmix64-style hash of (seed, index)
@@ -138,6 +184,45 @@ __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, floa
 // ---------------------------------------------------------------------------
 // GEMM engine interface (both engines): out[r, n] = sum_k X[r,k] * W[n,k]
 // ---------------------------------------------------------------------------
+// Fused epilogues of the tcgen05 engine (gemm_tc.cu).  Every mode first forms
+// val = acc (+ bias[n]) (+ addm[r, n]) and then:
+enum GemmEpi {
+  EPI_PLAIN = 0,   // out[r, n] = val
+  EPI_G1 = 1,      // out[r, n] = val (fp32); columns n >= col0 are the SCN recurrent factor p = h W_ha:
+                   //   m[(g*mB + r)*2F + F + f] = ft(val * q[r, n-col0]),  g = (n-col0)/F, f = (n-col0)%F
+  EPI_P3 = 2,      // out[r, n] = val (fp32, u = x W_ia);  m[(g*mB + r)*2F + f] = ft(val * v[r, n])
+  EPI_CELL = 3,    // 4 accumulators (grid batch = gate i,f,o,c of one d tile): LSTM pointwise ->
+                   //   c_new, gates, h (+ dropout copy)                      (scn_cell.py:146-152)
+  EPI_WR = 4,      // backward: acc = [w | r] = dpre_g [W_ic_g | W_hc_g]; grid batch = gate g.
+                   //   n <  F: du[r, gF+n] = ft(w v), dv_acc[r, gF+n] += w u
+                   //   n >= F: dp[r, gF+f] = ft(r q), dq_acc[r, gF+f] += r p
+  EPI_DHCELL = 5   // backward: acc = recurrent gradient dh of step t; fused LSTM pointwise backward
+                   //   (cell_bwd) -> dpre_t (ft), dc updated in place; rows >= rows take acc = 0
+};
+
+struct EpiArgs {
+  // G1 / P3 / WR
+  const float* fa = nullptr;        // G1: q   P3: v   WR: v
+  const float* fb = nullptr;        //                  WR: q
+  const float* fc = nullptr; int64_t ldc = 0;   //      WR: u (ld)
+  const float* fd = nullptr; int64_t ldd = 0;   //      WR: p (ld)
+  void* m = nullptr;                // G1 / P3: m operand of the P4 GEMM (feature type)
+  void* du = nullptr; int64_t lddu = 0;         // WR
+  void* dp = nullptr; int64_t lddp = 0;         // WR
+  float* dv_acc = nullptr; float* dq_acc = nullptr;   // WR  [rows][4F]
+  int mB = 0, F = 0, col0 = 0;
+  int vB = 0;                       // P3: > 0 -> row r uses v[r % vB] (all (t,b) rows in one GEMM)
+  // CELL / DHCELL
+  const float* b1 = nullptr; const float* b2 = nullptr;
+  const float* c_prev = nullptr; float* c_new = nullptr; float* gates = nullptr;
+  void* h_out = nullptr; int64_t ldh = 0; void* hd_out = nullptr;
+  float dropout_p = 0.f; const uint64_t* seed = nullptr; int t = 0, T = 1, D = 0;
+  const float* dh_fc = nullptr; int64_t ld_dhfc = 0; float* dc = nullptr; void* dpre = nullptr;
+  const float* c_new_r = nullptr;   // DHCELL: c_t (read)
+  int rows_epi = 0;                 // DHCELL: rows the fused pointwise covers (>= rows)
+  int lstm_order = 0;
+};
+
 struct GemmArgs {
   const void* X = nullptr;  int64_t ldx = 0;     // activations, rows x K, K contiguous, feature type
   const void* W = nullptr;  int64_t ldw = 0;     // weights,     N x K,    K contiguous, feature type
@@ -147,16 +232,25 @@ struct GemmArgs {
   const float* addm = nullptr; int64_t ldadd = 0;  // fp32 [rows, N] added in the epilogue (may alias out)
   int rows = 0, N = 0, K = 0;
   int rows_alloc = 0;                            // rows physically present in X (>= rows); 0 -> rows
-  int splitk = 0;                                // tcgen05 engine: 0 = off, -1 = auto, n = n slices.  The
-                                                 // output must then be PRE-INITIALISED (zero or the in-place
-                                                 // addend); the SIMT engine ignores this and overwrites.
+  int splitk = 0;                                // tcgen05 engine: 0 = off, -1 = auto, n = n K-slices that
+                                                 // add into the output (EPI_PLAIN) or `abuf` (fused modes)
+                                                 // with fp32 atomics: PRE-INITIALISE it (zeros, or the
+                                                 // in-place addend).  Ignored by the SIMT engine.
   int batch = 1;                                 // grid.z
   int64_t sX = 0, sW = 0, sO = 0, sBias = 0, sAdd = 0;   // element strides per batch index
+  int epi = EPI_PLAIN;                           // tcgen05 engine only
+  // fused modes: fp32 accumulation buffer, element (acc, z, r, n) at abuf[z*a_sz + acc*a_sa + r*a_ld + n]
+  // (default: `out`), and the per-tile ticket counters (>= #tiles ints, zero on entry, left zero)
+  float* abuf = nullptr; int64_t a_ld = 0, a_sz = 0, a_sa = 0;
+  int* counters = nullptr;
+  EpiArgs e;
 };
 
 int gemm_simt(const GemmArgs& a, cudaStream_t st);   // fp32 FFMA engine   (gemm_simt.cu)
 int gemm_tc(const GemmArgs& a, cudaStream_t st);     // tcgen05 + TMA bf16 (gemm_tc.cu)
+constexpr int GEMM_TC_MAX_TILE_COUNTERS = 4096;
 int gemm_tc_init();
+bool gemm_tc_cell_fusable(int rows);   // EPI_CELL keeps 4 accumulators per tile: small row counts only
 
 static inline int gemm(int precision, const GemmArgs& a, cudaStream_t st) {
   return precision == CAPDEC_BF16 ? gemm_tc(a, st) : gemm_simt(a, st);

@@ -15,6 +15,8 @@
 //   CELL i,f,o,g~ -> c_t, h_t (+ dropout copy for fc)
 // The time-invariant products (att1, v, q, U_emb, h0/c0) and the vocabulary projection
 // over all (b,t) rows are batched GEMMs outside the loop.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -26,21 +28,27 @@ namespace {
 
 inline int64_t pad8(int64_t x) { return round_up(x, 8); }
 
+bool fused_epilogue_enabled() {
+  const char* s = getenv("CAPDEC_FUSED_EPILOGUE");      // read per call: tests flip it
+  return s && s[0] == '1';
+}
+
 struct Plan {
   CapdecDims d;
   bool att, scn, bwd;
   int X, NQ, NG1, fsz;             // fsz = sizeof(feature type)
-  int64_t ldE, ldD, ldX, ldS, ld2F, ldV, ldNQ, ldEA, ldM, ldR, ldB, ldBP, ldA;
+  int64_t ldE, ldD, ldX, ldS, ld2F, ldV, ldNQ, ldEA, ldM, ldR, ldB, ldBP, ldA, ldPX;
+  bool fused;                      // bf16 SCN path with the fused GEMM epilogues (gemm_tc.cu)
   // byte offsets into the workspace
   struct Off {
     // packed weights (feature type) + fp32 bias vectors
     size_t Wp_e, Wp_cat1, b_cat1, Wp_xq, Wp_ibT, Wp_hbT, Wp_c, Wp_init, Wp_fc;
-    size_t Wp_fcT, Wp_cT, Wp_hq, Wp_xin, Wp_b6;
+    size_t Wp_fcT, Wp_cT, Wp_hq, Wp_xin, Wp_b6, Wp_hx;
     // forward activations
     size_t enc_s, att1, mean, meanF, tagsF, v, q, Xe, U, g1, awe, z, m, pre, gates, C, H0, Hall,
-        Hd, lenD, seedD, capsD;
+        Hd, lenD, seedD, capsD, counters;
     // backward buffers
-    size_t dlogF, dHfc, dh_rec, dc, dpre, wr, du, dp, dv_acc, dq_acc, dz, dba, dAtt1, dwf, dbf, dXe;
+    size_t dlogF, dHfc, dh_rec, dc, dpre, wr, du, dpx, dv_acc, dq_acc, dz, dba, dAtt1, dwf, dbf, dXe;
     size_t tA, tB, tC;             // transposed-operand scratch
     size_t total;
   } o;
@@ -72,6 +80,10 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
   p->ld2F = pad8(2 * d.F); p->ldV = pad8(d.V); p->ldNQ = pad8(p->NQ); p->ldEA = pad8(d.E + d.A);
   p->ldM = pad8(d.M); p->ldR = pad8((int64_t)d.B * d.T); p->ldB = pad8(d.B);
   p->ldBP = pad8((int64_t)d.B * d.P); p->ldA = pad8(d.A);
+  p->ldPX = pad8(p->NQ + (p->att ? d.E + d.A : 0));
+  // opt-in (CAPDEC_FUSED_EPILOGUE=1): on B200 the ticketed last-CTA epilogues cost as much as the
+  // pointwise kernels they replace, so the default keeps the plain split-K GEMMs
+  p->fused = fused_epilogue_enabled() && d.precision == CAPDEC_BF16 && p->scn && gemm_tc_cell_fusable(d.B);
 
   const size_t f = p->fsz;
   const int64_t B = d.B, T = d.T, P = d.P, E = d.E, A = d.A, M = d.M, D = d.D, F = d.F, S = d.S,
@@ -95,9 +107,10 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
   if (with_bwd) {
     o.Wp_fcT = take(D * p->ldV * f);
     if (p->scn) o.Wp_cT = take(4 * 2 * F * p->ldD * f);
-    o.Wp_hq = take(D * p->ldNQ * f);                // SCN: W_ha [D][4F] ; LSTM: W_hh^T [D][4D]
+    if (!p->scn) o.Wp_hq = take(D * p->ldNQ * f);   // LSTM: W_hh^T [D][4D]
     o.Wp_xin = take(X * p->ldNQ * f);               // SCN: W_ia [X][4F] ; LSTM: W_ih^T [X][4D]
-    if (p->att) o.Wp_b6 = take(D * p->ldEA * f);
+    if (p->att && !p->scn) o.Wp_b6 = take(D * p->ldEA * f);
+    if (p->scn) o.Wp_hx = take(D * p->ldPX * f);     // [W_ha | W_beta^T | W_d^T]
   }
   // ---- forward activations ----
   o.enc_s = take(B * P * E * f);
@@ -117,7 +130,7 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
     o.z = take(R * E * f);
   }
   if (p->scn) {
-    o.m = take(T * 4 * B * 2 * F * f);
+    o.m = take(4 * R * 2 * F * f);                    // [gate][t*B + b][u*v | p*q]
     o.pre = take(R * 4 * D * 4);                     // per step: split-K GEMMs accumulate into zeroed slots
   }
   o.gates = take(R * 4 * D * 4);
@@ -128,6 +141,7 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
   o.lenD = take(B * 4);
   o.seedD = take(8);
   o.capsD = take((size_t)B * d.L * 8);
+  o.counters = take((size_t)GEMM_TC_MAX_TILE_COUNTERS * 4);   // split-K tickets of the fused GEMM epilogues
   if (with_bwd) {
     o.dlogF = take(R * p->ldV * f);
     o.dHfc = take(R * D * 4);
@@ -137,7 +151,7 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
     if (p->scn) {
       o.wr = take(R * 4 * 2 * F * 4);
       o.du = take(R * NQ * f);
-      o.dp = take(R * NQ * f);
+      o.dpx = take(R * p->ldPX * f);                 // per row [dp | dbeta_pre | datt2]
       o.dv_acc = take(B * NQ * 4);
       o.dq_acc = take(B * NQ * 4);
     }
@@ -250,13 +264,20 @@ int pack_weights(const Ctx& c, const CapdecParams& w) {
                                   c.ft(p.o.Wp_cT, ((int64_t)g * 2 * F + F) * p.ldD), 1, 1, D, F, 0, NQ,
                                   p.ldD, 0, 1, st));
       }
-      CAPDEC_TRY(copy_cast(pr, w.w_ha, 0, NQ, c.at(p.o.Wp_hq), 1, p.ldNQ, D, NQ, st));
       CAPDEC_TRY(copy_cast(pr, w.w_ia, 0, NQ, c.at(p.o.Wp_xin), 1, p.ldNQ, X, NQ, st));
     } else {
       CAPDEC_TRY(transpose_cast(pr, w.w_ha, 0, c.at(p.o.Wp_hq), 1, 1, NQ, D, 0, D, p.ldNQ, 0, 1, st));
       CAPDEC_TRY(transpose_cast(pr, w.w_ia, 0, c.at(p.o.Wp_xin), 1, 1, NQ, X, 0, X, p.ldNQ, 0, 1, st));
     }
-    if (p.att) {
+    if (p.scn) {
+      // Wp_hx = [ W_ha | W_beta^T | W_d^T ]   (D x (4F + E + A)): ONE GEMM gives the recurrent dh
+      CAPDEC_TRY(copy_cast(pr, w.w_ha, 0, NQ, c.at(p.o.Wp_hx), 1, p.ldPX, D, NQ, st));
+      if (p.att) {
+        CAPDEC_TRY(transpose_cast(pr, w.f_beta_w, 0, c.ft(p.o.Wp_hx, NQ), 1, 1, E, D, 0, D, p.ldPX, 0, 1, st));
+        CAPDEC_TRY(transpose_cast(pr, w.dec_att_w, 0, c.ft(p.o.Wp_hx, NQ + E), 1, 1, A, D, 0, D, p.ldPX, 0, 1, st));
+      }
+    }
+    if (p.att && !p.scn) {
       // Wp_b6 = [ W_beta^T | W_d^T ]   (D x (E+A))
       CAPDEC_TRY(transpose_cast(pr, w.f_beta_w, 0, c.ft(p.o.Wp_b6, 0), 1, 1, E, D, 0, D, p.ldEA, 0, 1, st));
       CAPDEC_TRY(transpose_cast(pr, w.dec_att_w, 0, c.ft(p.o.Wp_b6, E), 1, 1, A, D, 0, D, p.ldEA, 0, 1, st));
@@ -338,10 +359,8 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
                  NQ, S));
   }
   // embeddings of the teacher tokens and their input-side projection, all (t,b) rows at once
+  const bool fused = p.fused;
   CAPDEC_TRY(embedding_gather(pr, w.emb, capsD, d.L, c.at(o.Xe), p.ldM, B, T, M, V, st));
-  CAPDEC_TRY(G_(c, c.at(o.Xe), p.ldM, c.at(o.Wp_xq), p.ldX, c.at(o.U), NQ, 0, nullptr, nullptr, 0, (int)R,
-               NQ, M));
-  if (alphas) CAPDEC_CUDA_OK(cudaMemsetAsync(alphas, 0, (size_t)R * P * 4, st));
   if (ragged) {
     // rows beyond a caption's length are never written by the step kernels; the batched GEMMs over
     // all (t,b) rows must see finite (zero) operands there
@@ -350,11 +369,27 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.z), 0, (size_t)R * E * p.fsz, st));
     if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.m), 0, (size_t)R * 4 * 2 * F * p.fsz, st));
   }
-  // split-K GEMMs of the tcgen05 engine accumulate with atomics into pre-zeroed outputs
+  if (fused && !p.att) {
+    // pure_scn: the whole input side is non-recurrent -- u = Emb W_ia AND the left half u*v of the
+    // P4 operand for every (t,b) row come out of this one GEMM
+    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.U), 0, (size_t)R * NQ * 4, st));
+    GemmArgs a;
+    a.X = c.at(o.Xe); a.ldx = p.ldM; a.W = c.at(o.Wp_xq); a.ldw = p.ldX; a.out = c.at(o.U); a.ldo = NQ;
+    a.rows = (int)R; a.N = NQ; a.K = M; a.epi = EPI_P3;
+    a.e.fa = c.at<float>(o.v); a.e.m = c.at(o.m); a.e.mB = (int)R; a.e.F = F; a.e.vB = B;
+    CAPDEC_TRY(gemm(pr, a, st));
+  } else {
+    CAPDEC_TRY(G_(c, c.at(o.Xe), p.ldM, c.at(o.Wp_xq), p.ldX, c.at(o.U), NQ, 0, nullptr, nullptr, 0, (int)R,
+                  NQ, M));
+  }
+  if (alphas) CAPDEC_CUDA_OK(cudaMemsetAsync(alphas, 0, (size_t)R * P * 4, st));
+  // split-K GEMMs of the tcgen05 engine accumulate with atomics into pre-zeroed buffers
   const int SK = pr == CAPDEC_BF16 ? -1 : 0;
+  int* counters = c.at<int>(o.counters);
   if (SK) {
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.g1), 0, (size_t)R * NG1 * 4, st));
     if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.pre), 0, (size_t)R * 4 * D * 4, st));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)GEMM_TC_MAX_TILE_COUNTERS * 4, st));
   }
 
   const bool drop = dropout_p > 0.f;
@@ -365,28 +400,57 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     const int64_t ldh = t == 0 ? p.ldD : (int64_t)T * D;
     float* g1 = c.at<float>(o.g1) + (int64_t)t * B * NG1;
     float* U = c.at<float>(o.U) + (int64_t)t * B * NQ;
-    CAPDEC_TRY(G_(c, hprev, ldh, c.at(o.Wp_cat1), p.ldD, g1, NG1, 0, c.at<float>(o.b_cat1), nullptr, 0, n,
-                 NG1, D, B, 1, 0, 0, 0, SK));
+    void* m = p.scn ? c.ft(o.m, (int64_t)t * B * 2 * F) : nullptr;     // gate stride R*2F
     const float* pcol = g1 + (p.att ? A + E : 0);
-    if (p.att) {
-      void* z = c.ft(o.z, (int64_t)t * B * E);
-      float* awe = save_bwd ? c.at<float>(o.awe) + (int64_t)t * B * E : nullptr;
-      CAPDEC_TRY(attention_fwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w, w.full_att_b,
-                               alphas + (int64_t)t * P, (int64_t)T * P, z, E, awe, n, 1, P, E, A, st));
-      // u (in place over U_emb[t]) += z . W_x[:, M:]^T
-      CAPDEC_TRY(G_(c, z, E, c.ft(o.Wp_xq, M), p.ldX, U, NQ, 0, nullptr, U, NQ, n, NQ, E, B, 1, 0, 0, 0, SK));
-    }
     const float* c_prev = c.at<float>(o.C) + (int64_t)t * B * D;
     float* c_new = c.at<float>(o.C) + (int64_t)(t + 1) * B * D;
     float* gates = c.at<float>(o.gates) + (int64_t)t * B * 4 * D;
     void* hout = c.ft(o.Hall, (int64_t)t * D);
     void* hdout = drop ? c.ft(o.Hd, (int64_t)t * D) : nullptr;
-    if (p.scn) {
-      void* m = c.ft(o.m, (int64_t)t * 4 * B * 2 * F);
-      CAPDEC_TRY(scn_form_m(pr, U, NQ, pcol, NG1, c.at<float>(o.v), c.at<float>(o.q), m, n, B, F, st));
+    {
+      // G1: [att2 | beta_pre | p] = h_{t-1} [W_d ; W_beta ; W_ha^T]^T (+ fused p*q -> right half of m)
+      GemmArgs a;
+      a.X = hprev; a.ldx = ldh; a.W = c.at(o.Wp_cat1); a.ldw = p.ldD; a.out = g1; a.ldo = NG1;
+      a.bias = c.at<float>(o.b_cat1); a.rows = n; a.N = NG1; a.K = D; a.rows_alloc = B; a.splitk = SK;
+      if (fused) {
+        a.epi = EPI_G1;
+        a.e.fa = c.at<float>(o.q); a.e.m = m; a.e.mB = (int)R; a.e.F = F; a.e.col0 = p.att ? A + E : 0;
+        a.counters = counters;
+      }
+      CAPDEC_TRY(gemm(pr, a, st));
+    }
+    if (p.att) {
+      void* z = c.ft(o.z, (int64_t)t * B * E);
+      float* awe = save_bwd ? c.at<float>(o.awe) + (int64_t)t * B * E : nullptr;
+      CAPDEC_TRY(attention_fwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w, w.full_att_b,
+                               alphas + (int64_t)t * P, (int64_t)T * P, z, E, awe, n, 1, P, E, A, st));
+      // u (in place over U_emb[t]) += z . W_x[:, M:]^T   (+ fused u*v -> left half of m)
+      GemmArgs a;
+      a.X = z; a.ldx = E; a.W = c.ft(o.Wp_xq, M); a.ldw = p.ldX; a.out = U; a.ldo = NQ; a.addm = U;
+      a.ldadd = NQ; a.rows = n; a.N = NQ; a.K = E; a.rows_alloc = B; a.splitk = SK;
+      if (fused) {
+        a.epi = EPI_P3;
+        a.e.fa = c.at<float>(o.v); a.e.m = m; a.e.mB = (int)R; a.e.F = F; a.e.vB = 0;
+        a.counters = counters;
+      }
+      CAPDEC_TRY(gemm(pr, a, st));
+    }
+    if (fused) {
+      // P4 + LSTM pointwise: pre_g = m_g [W_ic_g | W_hc_g]^T for the 4 gates of one d tile in one CTA
+      GemmArgs a;
+      a.X = m; a.ldx = 2 * F; a.sX = R * 2 * F; a.W = c.at(o.Wp_c); a.ldw = p.ld2F;
+      a.sW = (int64_t)D * p.ld2F; a.batch = 4; a.rows = n; a.N = D; a.K = 2 * F; a.rows_alloc = B;
+      a.splitk = SK; a.epi = EPI_CELL; a.counters = counters;
+      a.abuf = c.at<float>(o.pre) + (int64_t)t * B * 4 * D; a.a_ld = 4 * D; a.a_sa = D;
+      a.e.b1 = w.b_ih; a.e.b2 = w.b_hh; a.e.c_prev = c_prev; a.e.c_new = c_new; a.e.gates = gates;
+      a.e.h_out = hout; a.e.ldh = (int64_t)T * D; a.e.hd_out = hdout; a.e.dropout_p = dropout_p;
+      a.e.seed = c.at<uint64_t>(o.seedD); a.e.t = t; a.e.T = T; a.e.D = D; a.e.lstm_order = 0;
+      CAPDEC_TRY(gemm(pr, a, st));
+    } else if (p.scn) {
+      CAPDEC_TRY(scn_form_m(pr, U, NQ, pcol, NG1, c.at<float>(o.v), c.at<float>(o.q), m, n, (int)R, F, st));
       float* pre = c.at<float>(o.pre) + (int64_t)t * B * 4 * D;
       CAPDEC_TRY(G_(c, m, 2 * F, c.at(o.Wp_c), p.ld2F, pre, 4 * D, 0, nullptr, nullptr, 0, n, D, 2 * F, B, 4,
-                   (int64_t)B * 2 * F, (int64_t)D * p.ld2F, D, SK));
+                    R * 2 * F, (int64_t)D * p.ld2F, D, SK));
       CAPDEC_TRY(cell_fwd(pr, pre, 4 * D, nullptr, 0, w.b_ih, w.b_hh, 0, c_prev, c_new,
                           gates, hout, (int64_t)T * D, hdout, dropout_p, c.at<uint64_t>(o.seedD), t, T, n, D, st));
     } else {
@@ -448,10 +512,19 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   CAPDEC_TRY(colsum(pr, dlog, 1, lddl, (int)R, V, g.fc_b, 0, st));
 
   const int SK = pr == CAPDEC_BF16 ? -1 : 0;
+  const bool fused = p.fused;
+  // where the loop leaves dp (gradient wrt p = h W_ha) and [dbeta_pre | datt2]
+  // SCN: one row of dpx = [dp | dbeta_pre | datt2], so ONE GEMM with [W_ha | W_beta^T | W_d^T] gives dh
+  const void* dp_all = p.scn ? c.at(o.dpx) : nullptr;
+  const int64_t lddp = p.ldPX;
+  const void* dba_all = p.scn ? c.ft(o.dpx, NQ) : c.at(o.dba);
+  const int64_t lddba = p.scn ? p.ldPX : p.ldEA;
+  int* counters = c.at<int>(o.counters);
   CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dh_rec), 0, (size_t)(T + 1) * B * D * 4, st));
   if (SK) {
     if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.wr), 0, (size_t)R * 4 * 2 * F * 4, st));
     if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dz), 0, (size_t)R * E * 4, st));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)GEMM_TC_MAX_TILE_COUNTERS * 4, st));
   }
   CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dc), 0, (size_t)B * D * 4, st));
   if (p.scn) {
@@ -463,52 +536,119 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dpre), 0, (size_t)R * 4 * D * p.fsz, st));
     if (p.scn) {
       CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.du), 0, (size_t)R * NQ * p.fsz, st));
-      CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dp), 0, (size_t)R * NQ * p.fsz, st));
+      CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dpx), 0, (size_t)R * p.ldPX * p.fsz, st));
     }
     if (p.att) {
-      CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dba), 0, (size_t)R * p.ldEA * p.fsz, st));
+      if (!p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dba), 0, (size_t)R * p.ldEA * p.fsz, st));
       CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dwf), 0, (size_t)R * A * 4, st));
       CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dbf), 0, (size_t)R * 4, st));
     }
   }
 
   // ---------------- reverse-time recurrence ----------------
+  auto cell_bwd_step = [&](int t, const float* dh_in) {
+    return cell_bwd(pr, c.at<float>(o.dHfc) + (int64_t)t * D, (int64_t)T * D, dh_in, c.at<float>(o.dc),
+                    c.at<float>(o.gates) + (int64_t)t * B * 4 * D, c.at<float>(o.C) + (int64_t)t * B * D,
+                    c.at<float>(o.C) + (int64_t)(t + 1) * B * D, p.scn ? 0 : 1, dropout_p,
+                    c.at<uint64_t>(o.seedD), t, T, c.ft(o.dpre, (int64_t)t * B * 4 * D), nullptr, bt[t], D, st);
+  };
+  if (fused)    // the last step's pointwise backward; every earlier one rides on the dh GEMM below
+    CAPDEC_TRY(cell_bwd_step(T - 1, c.at<float>(o.dh_rec) + (int64_t)T * B * D));
   for (int t = T - 1; t >= 0; --t) {
     const int n = bt[t];
     float* g1 = c.at<float>(o.g1) + (int64_t)t * B * NG1;
     const float* pcol = g1 + (p.att ? A + E : 0);
     const float* U = c.at<float>(o.U) + (int64_t)t * B * NQ;
-    const float* c_prev = c.at<float>(o.C) + (int64_t)t * B * D;
-    const float* c_new = c.at<float>(o.C) + (int64_t)(t + 1) * B * D;
-    const float* gates = c.at<float>(o.gates) + (int64_t)t * B * 4 * D;
     void* dpre = c.ft(o.dpre, (int64_t)t * B * 4 * D);
+    float* dz = p.att ? c.at<float>(o.dz) + (int64_t)t * B * E : nullptr;
+    if (fused) {
+      void* du_t = c.ft(o.du, (int64_t)t * B * NQ);
+      void* dpx_t = c.ft(o.dpx, (int64_t)t * B * p.ldPX);
+      {
+        // [w_g | r_g] = dpre_g [W_ic_g | W_hc_g] with the factor products fused in the epilogue:
+        // du = w*v, dp = r*q, dv_acc += w*u, dq_acc += r*p
+        GemmArgs a;
+        a.X = dpre; a.ldx = 4 * D; a.sX = D; a.W = c.at(o.Wp_cT); a.ldw = p.ldD;
+        a.sW = (int64_t)2 * F * p.ldD; a.batch = 4; a.rows = n; a.N = 2 * F; a.K = D; a.rows_alloc = B;
+        a.splitk = SK; a.epi = EPI_WR; a.counters = counters;
+        a.abuf = c.at<float>(o.wr) + (int64_t)t * 4 * B * 2 * F; a.a_ld = 2 * F; a.a_sz = (int64_t)B * 2 * F;
+        a.e.fa = c.at<float>(o.v); a.e.fb = c.at<float>(o.q); a.e.fc = U; a.e.ldc = NQ; a.e.fd = pcol;
+        a.e.ldd = NG1; a.e.du = du_t; a.e.lddu = NQ; a.e.dp = dpx_t; a.e.lddp = p.ldPX;
+        a.e.dv_acc = c.at<float>(o.dv_acc); a.e.dq_acc = c.at<float>(o.dq_acc); a.e.F = F;
+        CAPDEC_TRY(gemm(pr, a, st));
+      }
+      if (p.att) {
+        // dz = du . W_x[M:, :]^T ; attention backward writes [dbeta_pre | datt2] next to dp
+        CAPDEC_TRY(G_(c, du_t, NQ, c.ft(o.Wp_xin, (int64_t)M * p.ldNQ), p.ldNQ, dz, E, 0, nullptr,
+                      nullptr, 0, n, E, NQ, B, 1, 0, 0, 0, SK));
+        CAPDEC_TRY(attention_bwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w,
+                                 alphas + (int64_t)t * P, (int64_t)T * P,
+                                 d_alphas ? d_alphas + (int64_t)t * P : nullptr, (int64_t)T * P,
+                                 dz, E, c.at<float>(o.awe) + (int64_t)t * B * E,
+                                 c.ft(o.dpx, (int64_t)t * B * p.ldPX + NQ), p.ldPX,
+                                 c.at<float>(o.dAtt1), c.at<float>(o.dwf) + (int64_t)t * B * A,
+                                 c.at<float>(o.dbf) + (int64_t)t * B, n, P, E, A, st));
+      }
+      {
+        // dh_{t-1} = [dp | dbeta_pre | datt2] [W_ha | W_beta^T | W_d^T]^T, and (t > 0) the LSTM
+        // pointwise backward of step t-1 in the epilogue
+        GemmArgs a;
+        a.X = dpx_t; a.ldx = p.ldPX; a.W = c.at(o.Wp_hx); a.ldw = p.ldPX; a.rows = n; a.N = D;
+        a.K = NQ + (p.att ? E + A : 0); a.rows_alloc = B; a.splitk = SK;
+        if (t > 0) {
+          const int tp = t - 1;
+          a.epi = EPI_DHCELL; a.counters = counters;
+          a.abuf = c.at<float>(o.dh_rec) + (int64_t)t * B * D; a.a_ld = D;     // zeroed slot of step t
+          a.e.rows_epi = bt[tp];
+          a.e.dh_fc = c.at<float>(o.dHfc) + (int64_t)tp * D; a.e.ld_dhfc = (int64_t)T * D;
+          a.e.gates = c.at<float>(o.gates) + (int64_t)tp * B * 4 * D;
+          a.e.c_prev = c.at<float>(o.C) + (int64_t)tp * B * D;
+          a.e.c_new_r = c.at<float>(o.C) + (int64_t)(tp + 1) * B * D;
+          a.e.dc = c.at<float>(o.dc); a.e.dpre = c.ft(o.dpre, (int64_t)tp * B * 4 * D);
+          a.e.dropout_p = dropout_p; a.e.seed = c.at<uint64_t>(o.seedD); a.e.t = tp; a.e.T = T; a.e.D = D;
+          a.e.lstm_order = 0;
+        } else {
+          a.out = c.at<float>(o.dh_rec); a.ldo = D;       // dh0 -> init_h gradients
+        }
+        CAPDEC_TRY(gemm(pr, a, st));
+      }
+      continue;
+    }
+    // ---- default path: plain (split-K) GEMMs + pointwise kernels, chained with PDL ----
     // dhs[t+1]: recurrent gradient flowing into h_t ; dhs[t]: what this step sends to h_{t-1}
     const float* dh_in = c.at<float>(o.dh_rec) + (int64_t)(t + 1) * B * D;
     float* dh_rec = c.at<float>(o.dh_rec) + (int64_t)t * B * D;
-    float* wr = p.scn ? c.at<float>(o.wr) + (int64_t)t * 4 * B * 2 * F : nullptr;
-    float* dz = p.att ? c.at<float>(o.dz) + (int64_t)t * B * E : nullptr;
-    CAPDEC_TRY(cell_bwd(pr, c.at<float>(o.dHfc) + (int64_t)t * D, (int64_t)T * D, dh_in, c.at<float>(o.dc),
-                        gates, c_prev, c_new, p.scn ? 0 : 1, dropout_p, c.at<uint64_t>(o.seedD), t, T, dpre, nullptr, n, D, st));
-    const void* du;      // gradient wrt u (input-side pre-products) and wrt p (recurrent side)
-    const void* dpp;
+    CAPDEC_TRY(cell_bwd_step(t, dh_in));
     if (p.scn) {
-      // [w_g | r_g] = dpre_g . [W_ic_g | W_hc_g]
+      float* wr = c.at<float>(o.wr) + (int64_t)t * 4 * B * 2 * F;
+      void* du_t = c.ft(o.du, (int64_t)t * B * NQ);
+      void* dpx_t = c.ft(o.dpx, (int64_t)t * B * p.ldPX);
+      // [w_g | r_g] = dpre_g . [W_ic_g | W_hc_g] ; du = w*v, dp = r*q, dv_acc += w*u, dq_acc += r*p
       CAPDEC_TRY(G_(c, dpre, 4 * D, c.at(o.Wp_cT), p.ldD, wr, 2 * F, 0, nullptr, nullptr, 0, n, 2 * F,
                    D, B, 4, D, (int64_t)2 * F * p.ldD, (int64_t)B * 2 * F, SK));
-      void* du_t = c.ft(o.du, (int64_t)t * B * NQ);
-      void* dp_t = c.ft(o.dp, (int64_t)t * B * NQ);
       CAPDEC_TRY(scn_bwd_products(pr, wr, U, NQ, pcol, NG1, c.at<float>(o.v),
-                                  c.at<float>(o.q), du_t, dp_t, c.at<float>(o.dv_acc),
-                                  c.at<float>(o.dq_acc), n, B, F, st));
-      du = du_t; dpp = dp_t;
+                                  c.at<float>(o.q), du_t, dpx_t, c.at<float>(o.dv_acc),
+                                  c.at<float>(o.dq_acc), n, B, F, p.ldPX, st));
+      if (p.att) {
+        // dz = du . W_x[M:, :]^T ; attention backward writes [dbeta_pre | datt2] next to dp
+        CAPDEC_TRY(G_(c, du_t, NQ, c.ft(o.Wp_xin, (int64_t)M * p.ldNQ), p.ldNQ, dz, E, 0, nullptr,
+                      nullptr, 0, n, E, NQ, B, 1, 0, 0, 0, SK));
+        CAPDEC_TRY(attention_bwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w,
+                                 alphas + (int64_t)t * P, (int64_t)T * P,
+                                 d_alphas ? d_alphas + (int64_t)t * P : nullptr, (int64_t)T * P,
+                                 dz, E, c.at<float>(o.awe) + (int64_t)t * B * E,
+                                 c.ft(o.dpx, (int64_t)t * B * p.ldPX + NQ), p.ldPX,
+                                 c.at<float>(o.dAtt1), c.at<float>(o.dwf) + (int64_t)t * B * A,
+                                 c.at<float>(o.dbf) + (int64_t)t * B, n, P, E, A, st));
+      }
+      // dh_{t-1} = [dp | dbeta_pre | datt2] . [W_ha | W_beta^T | W_d^T]^T
+      CAPDEC_TRY(G_(c, dpx_t, p.ldPX, c.at(o.Wp_hx), p.ldPX, dh_rec, D, 0, nullptr, nullptr, 0, n, D,
+                    NQ + (p.att ? E + A : 0), B, 1, 0, 0, 0, SK));
     } else {
-      du = dpre; dpp = dpre;
-    }
-    // dh_{t-1} (recurrent part) = dp . W_hq^T
-    CAPDEC_TRY(G_(c, dpp, NQ, c.at(o.Wp_hq), p.ldNQ, dh_rec, D, 0, nullptr, nullptr, 0, n, D, NQ, B, 1, 0, 0, 0, SK));
-    if (p.att) {
-      // dz = du . W_x[M:, :]^T
-      CAPDEC_TRY(G_(c, du, NQ, c.ft(o.Wp_xin, (int64_t)M * p.ldNQ), p.ldNQ, dz, E, 0, nullptr,
+      // LSTM: dh_{t-1} (recurrent part) = dpre . W_hh
+      CAPDEC_TRY(G_(c, dpre, NQ, c.at(o.Wp_hq), p.ldNQ, dh_rec, D, 0, nullptr, nullptr, 0, n, D, NQ, B, 1, 0, 0, 0, SK));
+      // dz = dpre . W_ih[:, M:]
+      CAPDEC_TRY(G_(c, dpre, NQ, c.ft(o.Wp_xin, (int64_t)M * p.ldNQ), p.ldNQ, dz, E, 0, nullptr,
                    nullptr, 0, n, E, NQ, B, 1, 0, 0, 0, SK));
       void* dba = c.ft(o.dba, (int64_t)t * B * p.ldEA);
       CAPDEC_TRY(attention_bwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w,
@@ -539,16 +679,16 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   if (p.scn) {
     // m^T: per gate [2F][R]
     for (int gg = 0; gg < 4; ++gg)
-      CAPDEC_TRY(transpose_cast(pr, c.ft(o.m, (int64_t)gg * B * 2 * F), 1,
-                                c.ft(o.tB, (int64_t)gg * 2 * F * p.ldR), 1, T, B, 2 * F,
-                                (int64_t)4 * B * 2 * F, 2 * F, p.ldR, B, 1, st));
+      CAPDEC_TRY(transpose_cast(pr, c.ft(o.m, (int64_t)gg * R * 2 * F), 1,
+                                c.ft(o.tB, (int64_t)gg * 2 * F * p.ldR), 1, 1, Ri, 2 * F, 0, 2 * F,
+                                p.ldR, 0, 1, st));
     // weight_ic.grad[:, gF:(g+1)F] = dpre_g^T . (u_g*v_g) ; weight_hc.grad likewise with (p_g*q_g)
     CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ic, NQ, 0, nullptr, nullptr, 0, D, F, Ri, 0, 4,
                  (int64_t)D * p.ldR, (int64_t)2 * F * p.ldR, F));
     CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.ft(o.tB, (int64_t)F * p.ldR), p.ldR, g.w_hc, NQ, 0, nullptr, nullptr,
                  0, D, F, Ri, 0, 4, (int64_t)D * p.ldR, (int64_t)2 * F * p.ldR, F));
     // weight_ha.grad [D][4F] = H_prev^T . dp
-    CAPDEC_TRY(transpose_cast(pr, c.at(o.dp), 1, c.at(o.tB), 1, 1, Ri, NQ, 0, NQ, p.ldR, 0, 1, st));
+    CAPDEC_TRY(transpose_cast(pr, dp_all, 1, c.at(o.tB), 1, 1, Ri, NQ, 0, lddp, p.ldR, 0, 1, st));
     CAPDEC_TRY(G_(c, c.at(o.tC), p.ldR, c.at(o.tB), p.ldR, g.w_ha, NQ, 0, nullptr, nullptr, 0, D, NQ, Ri));
     // weight_ia.grad [X][4F] = [Xe | z]^T . du
     CAPDEC_TRY(transpose_cast(pr, c.at(o.du), 1, c.at(o.tB), 1, 1, Ri, NQ, 0, NQ, p.ldR, 0, 1, st));
@@ -587,12 +727,12 @@ int backward(const CapdecDims& d, const CapdecParams& w,
 
   if (p.att) {
     // f_beta / decoder_att: [dbeta_pre | datt2]^T . H_prev
-    CAPDEC_TRY(transpose_cast(pr, c.at(o.dba), 1, c.at(o.tA), 1, 1, Ri, E + A, 0, p.ldEA, p.ldR, 0, 1, st));
+    CAPDEC_TRY(transpose_cast(pr, dba_all, 1, c.at(o.tA), 1, 1, Ri, E + A, 0, lddba, p.ldR, 0, 1, st));
     CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tC), p.ldR, g.f_beta_w, D, 0, nullptr, nullptr, 0, E, D, Ri));
     CAPDEC_TRY(G_(c, c.ft(o.tA, (int64_t)E * p.ldR), p.ldR, c.at(o.tC), p.ldR, g.dec_att_w, D, 0, nullptr,
                  nullptr, 0, A, D, Ri));
-    CAPDEC_TRY(colsum(pr, c.at(o.dba), 1, p.ldEA, Ri, E, g.f_beta_b, 0, st));
-    CAPDEC_TRY(colsum(pr, c.ft(o.dba, E), 1, p.ldEA, Ri, A, g.dec_att_b, 0, st));
+    CAPDEC_TRY(colsum(pr, dba_all, 1, lddba, Ri, E, g.f_beta_b, 0, st));
+    CAPDEC_TRY(colsum(pr, (const uint8_t*)dba_all + (size_t)E * p.fsz, 1, lddba, Ri, A, g.dec_att_b, 0, st));
     // full_att: per-row partials reduced over all (t,b)
     CAPDEC_TRY(colsum(pr, c.at(o.dwf), 0, A, Ri, A, g.full_att_w, 0, st));
     CAPDEC_TRY(colsum(pr, c.at(o.dbf), 0, 1, Ri, 1, g.full_att_b, 0, st));

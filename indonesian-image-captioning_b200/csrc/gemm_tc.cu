@@ -17,6 +17,8 @@
 // K-major, multi-stage ring with full/empty mbarriers.
 #include <cuda.h>   // CUtensorMap types only; the encode function is fetched at run time
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -111,42 +113,150 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-template <int BNR>
+template <int BNR, int NACC>
 struct Cfg {
-  static constexpr int STAGES = (BNR == 128) ? 4 : 6;
+  static constexpr int STAGES = (BNR == 64 && NACC == 4) ? 3 : 4;
   static constexpr int W_BYTES = BM * BK * 2;
   static constexpr int X_BYTES = BNR * BK * 2;
   static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
+  static constexpr int TMEM_COLS = (NACC * BNR) <= 32 ? 32 : (NACC * BNR) <= 64 ? 64 :
+                                   (NACC * BNR) <= 128 ? 128 : (NACC * BNR) <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BNR < 32 ? 32 : BNR;
 };
 
-template <int BNR>
+struct KArgs {
+  void* out; int64_t ldo; int out_ft;
+  const float* bias; const float* addm; int64_t ldadd;
+  int rows, N, K;
+  int64_t sO, sBias, sAdd;
+  int splits;            // K-slices per output tile (grid.z = batch * splits)
+  // accumulation buffer of the fused epilogues: element (acc, z, r, n) lives at
+  // abuf[z*a_sz + acc*a_sa + r*a_ld + n]; K-slices add into it with fp32 atomics (pre-zeroed or
+  // pre-filled with the addend by the caller) and the LAST CTA of a tile (ticket counter) reads the
+  // complete sums back and applies the fused epilogue
+  float* abuf; int64_t a_ld, a_sz, a_sa;
+  int* counters;         // one ticket counter per output tile, zero on entry, left zero
+  EpiArgs e;
+};
+
+// one output element (r, n) of batch z with its NACC accumulated values.  Read-only operands are
+// fetched with __ldg so that the unrolled caller can issue the loads of several rows together;
+// `extra` is the value the caller pre-loaded for the mode (DHCELL: dc[r, n]).
+template <int NACC, int EPI>
+__device__ __forceinline__ void epilogue_elem(const KArgs& a, int z, int r, int n, const float (&acc)[NACC],
+                                              float extra) {
+  const EpiArgs& e = a.e;
+  float val = acc[0];
+  if (EPI != EPI_CELL && EPI != EPI_DHCELL) {
+    if (a.bias) val += __ldg(a.bias + (int64_t)z * a.sBias + n);
+    if (a.addm) val += __ldg(a.addm + (int64_t)z * a.sAdd + (int64_t)r * a.ldadd + n);
+  }
+  if (EPI == EPI_G1) {
+    ((float*)a.out)[(int64_t)r * a.ldo + n] = val;
+    if (n >= e.col0) {
+      const int nn = n - e.col0;
+      const int g = nn / e.F, f = nn - g * e.F;
+      ((bf16*)e.m)[((int64_t)g * e.mB + r) * 2 * e.F + e.F + f] =
+          __float2bfloat16_rn(val * __ldg(e.fa + (int64_t)r * 4 * e.F + nn));
+    }
+  } else if (EPI == EPI_P3) {
+    ((float*)a.out)[(int64_t)r * a.ldo + n] = val;
+    const int g = n / e.F, f = n - g * e.F;
+    const int rv = e.vB > 0 ? r % e.vB : r;
+    ((bf16*)e.m)[((int64_t)g * e.mB + r) * 2 * e.F + f] =
+        __float2bfloat16_rn(val * __ldg(e.fa + (int64_t)rv * 4 * e.F + n));
+  } else if (EPI == EPI_CELL) {
+    const int D = e.D, d = n;
+    float pre[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float x = acc[g < NACC ? g : 0];
+      if (e.b1) x += __ldg(e.b1 + g * D + d);
+      if (e.b2) x += __ldg(e.b2 + g * D + d);
+      pre[g] = x;
+    }
+    const int so = e.lstm_order ? 3 : 2, sg = e.lstm_order ? 2 : 3;
+    const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), og = sigmoidf_(pre[so]);
+    const float gg = tanhf(pre[sg]);
+    const int64_t i = (int64_t)r * D + d;
+    const float c = fg * __ldg(e.c_prev + i) + ig * gg;
+    const float h = og * tanhf(c);
+    e.c_new[i] = c;
+    if (e.gates) {
+      float* gp = e.gates + (int64_t)r * 4 * D + d;
+      gp[0] = ig; gp[D] = fg; gp[2 * D] = og; gp[3 * D] = gg;
+    }
+    ((bf16*)e.h_out)[(int64_t)r * e.ldh + d] = __float2bfloat16_rn(h);
+    if (e.hd_out) {
+      const float sc = dropout_scale(__ldg(e.seed), ((uint64_t)r * e.T + e.t) * D + d, e.dropout_p);
+      ((bf16*)e.hd_out)[(int64_t)r * e.ldh + d] = __float2bfloat16_rn(h * sc);
+    }
+  } else if (EPI == EPI_WR) {
+    const int F = e.F, g = z;
+    if (n < F) {
+      const int64_t k = (int64_t)r * 4 * F + g * F + n;
+      ((bf16*)e.du)[(int64_t)r * e.lddu + g * F + n] = __float2bfloat16_rn(val * __ldg(e.fa + k));
+      atomicAdd(e.dv_acc + k, val * __ldg(e.fc + (int64_t)r * e.ldc + g * F + n));   // sole writer: RED, no stall
+    } else {
+      const int f = n - F;
+      const int64_t k = (int64_t)r * 4 * F + g * F + f;
+      ((bf16*)e.dp)[(int64_t)r * e.lddp + g * F + f] = __float2bfloat16_rn(val * __ldg(e.fb + k));
+      atomicAdd(e.dq_acc + k, val * __ldg(e.fd + (int64_t)r * e.ldd + g * F + f));
+    }
+  } else if (EPI == EPI_DHCELL) {
+    const int D = e.D, d = n;
+    const int64_t i = (int64_t)r * D + d;
+    float dh = r < a.rows ? val : 0.f;          // rows that ended at this step start from dh = 0
+    {
+      float g = __ldg(e.dh_fc + (int64_t)r * e.ld_dhfc + d);
+      if (e.dropout_p > 0.f) g *= dropout_scale(__ldg(e.seed), ((uint64_t)r * e.T + e.t) * D + d, e.dropout_p);
+      dh += g;
+    }
+    const float* gp = e.gates + (int64_t)r * 4 * D + d;
+    const float ig = __ldg(gp), fg = __ldg(gp + D), og = __ldg(gp + 2 * D), gg = __ldg(gp + 3 * D);
+    const float tc = tanhf(__ldg(e.c_new_r + i));
+    const float dcn = extra + dh * og * (1.f - tc * tc);
+    const float dpo = dh * tc * og * (1.f - og);
+    const float dpi = dcn * gg * ig * (1.f - ig);
+    const float dpf = dcn * __ldg(e.c_prev + i) * fg * (1.f - fg);
+    const float dpg = dcn * ig * (1.f - gg * gg);
+    e.dc[i] = dcn * fg;
+    const int so = e.lstm_order ? 3 : 2, sg = e.lstm_order ? 2 : 3;
+    bf16* dp = (bf16*)e.dpre + (int64_t)r * 4 * D + d;
+    dp[0] = __float2bfloat16_rn(dpi);
+    dp[D] = __float2bfloat16_rn(dpf);
+    dp[(int64_t)so * D] = __float2bfloat16_rn(dpo);
+    dp[(int64_t)sg * D] = __float2bfloat16_rn(dpg);
+  }
+}
+
+template <int BNR, int NACC, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
-               void* out, int64_t ldo, int out_ft, const float* __restrict__ bias,
-               const float* addm, int64_t ldadd, int rows, int N, int K,
-               int64_t sO, int64_t sBias, int64_t sAdd, int splits) {
-  using C = Cfg<BNR>;
+               const __grid_constant__ KArgs a) {
+  using C = Cfg<BNR, NACC>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
-  // bars[0..S) full, [S..2S) empty, [2S] tmem_full ; then tmem base slot
+  // bars[0..S) full, [S..2S) empty, [2S] tmem_full ; then tmem base slot, then the "last CTA" flag
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * C::STAGES + 1);
+  volatile uint32_t* last_flag = tmem_slot + 1;
+
+  pdl_launch_dependents();
+  const int splits = a.splits;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BM;
   const int r0 = blockIdx.y * BNR;
-  // grid.z = batch * splits: split-K slices of one output tile are reduced with fp32 atomics
-  // into an output the caller has pre-initialised (zero, or the in-place addend)
+  // grid.z = batch * splits
   const int z = blockIdx.z / splits;
   const int split = blockIdx.z - z * splits;
-  const int nkb_total = (K + BK - 1) / BK;
+  const int nkb_total = (a.K + BK - 1) / BK;
   const int kb_begin = (int)(((int64_t)nkb_total * split) / splits);
   const int kb_end = (int)(((int64_t)nkb_total * (split + 1)) / splits);
-  const int nkb = kb_end - kb_begin;
+  const int nunits = (kb_end - kb_begin) * NACC;     // pipeline units: (k-block, accumulator)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -169,19 +279,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // everything below may read what the previous kernel of the stream wrote
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------- TMA producer -------------------------
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % C::STAGES;
-        const uint32_t ph = (kb / C::STAGES) & 1;
+      for (int u = 0; u < nunits; ++u) {
+        const int s = u % C::STAGES;
+        const uint32_t ph = (u / C::STAGES) & 1;
+        const int kb = kb_begin + u / NACC;
+        const int zz = NACC > 1 ? (u % NACC) : z;
         mbar_wait(smem_u32(&bars[C::STAGES + s]), ph ^ 1);
         const uint32_t full = smem_u32(&bars[s]);
         mbar_expect_tx(full, C::STAGE_BYTES);
         const uint32_t ws = smem_u32(smem + s * C::STAGE_BYTES);
-        tma_load_3d(ws, &mapW, full, (kb_begin + kb) * BK, n0, z);
-        tma_load_3d(ws + C::W_BYTES, &mapX, full, (kb_begin + kb) * BK, r0, z);
+        tma_load_3d(ws, &mapW, full, kb * BK, n0, zz);
+        tma_load_3d(ws + C::W_BYTES, &mapX, full, kb * BK, r0, zz);
       }
     }
   } else if (warp == 1) {
@@ -190,9 +303,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       // instruction descriptor: D=F32, A=B=BF16, both K-major, N=BNR, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNR >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % C::STAGES;
-        const uint32_t ph = (kb / C::STAGES) & 1;
+      for (int u = 0; u < nunits; ++u) {
+        const int s = u % C::STAGES;
+        const uint32_t ph = (u / C::STAGES) & 1;
+        const int acc = NACC > 1 ? (u % NACC) : 0;
+        const int kb_rel = u / NACC;
         mbar_wait(smem_u32(&bars[s]), ph);
         tc_fence_after();
         const uint32_t ws = smem_u32(smem + s * C::STAGE_BYTES);
@@ -202,41 +317,103 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the
           // (addr >> 4) start-address field
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_bf16(tmem_base + (uint32_t)(acc * BNR), adesc + 2 * k, bdesc + 2 * k, idesc,
+                    (kb_rel | k) != 0);
         }
         umma_commit(smem_u32(&bars[C::STAGES + s]));     // frees the smem stage when MMAs retire
       }
-      umma_commit(smem_u32(&bars[2 * C::STAGES]));       // accumulator complete
+      umma_commit(smem_u32(&bars[2 * C::STAGES]));       // accumulators complete
     }
   } else {
     // ------------------------- epilogue warps 2..5 -------------------------
     mbar_wait(smem_u32(&bars[2 * C::STAGES]), 0);
     tc_fence_after();
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
-    const int n = n0 + q * 32 + lane;       // output feature owned by this thread
-    const bool n_ok = n < N;
-    float bv = 0.f;
-    if (bias != nullptr && n_ok && split == 0) bv = bias[(int64_t)z * sBias + n];
-    float* outf = (float*)out + (int64_t)z * sO;
-    bf16* outh = (bf16*)out + (int64_t)z * sO;
-    const float* add = addm ? addm + (int64_t)z * sAdd : nullptr;
-    // split-K: the addend is applied once (split 0) unless it IS the output (in-place accumulate)
-    if (splits > 1 && (split != 0 || (const void*)add == (const void*)outf)) add = nullptr;
+    const int nl = q * 32 + lane;           // tile-local output feature owned by this thread
+    const int n = n0 + nl;
+    const bool n_ok = n < a.N;
+    if (EPI == EPI_PLAIN) {
+      // plain epilogue: TMEM -> registers -> global; K-slices add with fp32 atomics into an output
+      // the caller pre-initialised (zero, or the in-place addend)
+      float bv = 0.f;
+      if (a.bias != nullptr && n_ok && split == 0) bv = a.bias[(int64_t)z * a.sBias + n];
+      float* outf = (float*)a.out + (int64_t)z * a.sO;
+      bf16* outh = (bf16*)a.out + (int64_t)z * a.sO;
+      const float* add = a.addm ? a.addm + (int64_t)z * a.sAdd : nullptr;
+      if (splits > 1 && (split != 0 || (const void*)add == (const void*)outf)) add = nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BNR; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (n_ok) {
+      for (int c0 = 0; c0 < BNR; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (n_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int r = r0 + c0 + j;
-          if (r < rows) {
-            float val = __uint_as_float(v[j]) + bv;
-            if (add) val += add[(int64_t)r * ldadd + n];
-            if (splits > 1) atomicAdd(&outf[(int64_t)r * ldo + n], val);
-            else if (out_ft) outh[(int64_t)r * ldo + n] = __float2bfloat16_rn(val);
-            else outf[(int64_t)r * ldo + n] = val;
+          for (int j = 0; j < 32; ++j) {
+            const int r = r0 + c0 + j;
+            if (r < a.rows) {
+              float val = __uint_as_float(v[j]) + bv;
+              if (add) val += add[(int64_t)r * a.ldadd + n];
+              if (splits > 1) atomicAdd(&outf[(int64_t)r * a.ldo + n], val);
+              else if (a.out_ft) outh[(int64_t)r * a.ldo + n] = __float2bfloat16_rn(val);
+              else outf[(int64_t)r * a.ldo + n] = val;
+            }
           }
+        }
+      }
+    } else {
+      // fused epilogues, pass 1: this CTA's partial sums are ADDED to the accumulation buffer (the
+      // caller pre-initialised it: zeros, or the in-place addend)
+      float* ab = a.abuf + (int64_t)z * a.a_sz + n;
+#pragma unroll 1
+      for (int acc = 0; acc < NACC; ++acc) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BNR; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BNR + c0), v);
+          if (n_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int r = r0 + c0 + j;
+              if (r < a.rows) {
+                atomicAdd(ab + (int64_t)acc * a.a_sa + (int64_t)r * a.a_ld, __uint_as_float(v[j]));
+              }
+            }
+          }
+        }
+      }
+      bool last = true;
+      if (splits > 1) {
+        // ticket: the CTA that finishes a tile last owns its fused epilogue
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          int* ctr = a.counters + (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * z));
+          const int ticket = atomicAdd(ctr, 1);
+          const bool l = ticket == splits - 1;
+          if (l) *ctr = 0;                       // every K-slice has taken its ticket: rearm
+          *last_flag = l ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        last = *last_flag != 0u;
+        if (last) __threadfence();
+      }
+      if (last && n_ok) {
+        // pass 2: complete sums -> fused epilogue (thread = feature n, loop over the tile's rows)
+        const int rows_lim = (EPI == EPI_DHCELL) ? a.e.rows_epi : a.rows;
+        const int r_end = min(r0 + BNR, rows_lim);
+        constexpr int RB = 8;                    // rows in flight per thread
+        for (int rb = r0; rb < r_end; rb += RB) {
+          float acc[RB][NACC], extra[RB];
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            const int r = min(rb + i, r_end - 1);
+#pragma unroll
+            for (int k = 0; k < NACC; ++k)
+              acc[i][k] = __ldcg(ab + (int64_t)k * a.a_sa + (int64_t)r * a.a_ld);
+            extra[i] = (EPI == EPI_DHCELL) ? __ldcg(a.e.dc + (int64_t)r * a.e.D + n) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < RB; ++i)
+            if (rb + i < r_end) epilogue_elem<NACC, EPI>(a, z, rb + i, n, acc[i], extra[i]);
         }
       }
     }
@@ -312,29 +489,75 @@ int get_map(const void* p, int64_t ld, int rows, int K, int batch, int64_t sb, i
   return CAPDEC_OK;
 }
 
-template <int BNR>
+template <int BNR, int NACC, int EPI>
 int launch(const GemmArgs& a, cudaStream_t st) {
-  using C = Cfg<BNR>;
+  using C = Cfg<BNR, NACC>;
+  auto kernel = gemm_tc_kernel<BNR, NACC, EPI>;
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  });
+  CAPDEC_REQUIRE(attr_rc == cudaSuccess, CAPDEC_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc_kernel) failed: %s",
+                 cudaGetErrorString(attr_rc));
   CUtensorMap mW, mX;
   CAPDEC_TRY(get_map(a.W, a.ldw, a.N, a.K, a.batch, a.sW, BM, &mW));
-  const int xrows = a.rows_alloc > a.rows ? a.rows_alloc : a.rows;
+  const int rows_epi = (EPI == EPI_DHCELL && a.e.rows_epi > a.rows) ? a.e.rows_epi : a.rows;
+  int xrows = a.rows_alloc > a.rows ? a.rows_alloc : a.rows;
+  if (xrows < rows_epi) xrows = rows_epi;
   CAPDEC_TRY(get_map(a.X, a.ldx, xrows, a.K, a.batch, a.sX, BNR, &mX));
-  // split-K only for fp32 outputs that the caller pre-initialised (GemmArgs::splitk)
+  // split-K: grid.z = batch * splits; the K-slices of a tile add into one fp32 buffer
   const int nkb = ceil_div(a.K, BK);
+  const int zb = NACC > 1 ? 1 : a.batch;           // NACC > 1: the batch (gate) index is looped inside
+  const int row_tiles = ceil_div(rows_epi, BNR);
+  const int tiles = ceil_div(a.N, BM) * row_tiles * zb;
   int splits = 1;
-  if (a.splitk != 0 && !a.out_ft) {
-    const int tiles = ceil_div(a.N, BM) * ceil_div(a.rows, BNR) * a.batch;
+  if (a.splitk != 0 && !(EPI == EPI_PLAIN && a.out_ft)) {
     splits = a.splitk > 0 ? a.splitk : (148 + tiles - 1) / tiles;     // auto: about one CTA per SM
     if (splits > nkb / 2) splits = nkb / 2;                            // >= 2 k-blocks per CTA
     if (splits > 16) splits = 16;
     if (splits < 1) splits = 1;
   }
-  dim3 grid(ceil_div(a.N, BM), ceil_div(a.rows, BNR), a.batch * splits);
-  gemm_tc_kernel<BNR><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(
-      mW, mX, a.out, a.ldo, a.out_ft, a.bias, a.addm, a.ldadd, a.rows, a.N, a.K, a.sO, a.sBias,
-      a.sAdd, splits);
-  CAPDEC_LAUNCH_OK();
+  KArgs k;
+  k.out = a.out; k.ldo = a.ldo; k.out_ft = a.out_ft; k.bias = a.bias; k.addm = a.addm; k.ldadd = a.ldadd;
+  k.rows = a.rows; k.N = a.N; k.K = a.K; k.sO = a.sO; k.sBias = a.sBias; k.sAdd = a.sAdd;
+  k.splits = splits; k.e = a.e;
+  k.abuf = a.abuf; k.a_ld = a.a_ld; k.a_sz = a.a_sz; k.a_sa = a.a_sa; k.counters = a.counters;
+  if (EPI != EPI_PLAIN) {
+    if (!k.abuf) { k.abuf = (float*)a.out; k.a_ld = a.ldo; k.a_sz = a.sO; k.a_sa = 0; }
+    CAPDEC_REQUIRE(k.abuf != nullptr && !a.out_ft, CAPDEC_ERR_BAD_ARG,
+                   "gemm_tc: fused epilogues need an fp32 accumulation buffer");
+    CAPDEC_REQUIRE(splits == 1 || (k.counters != nullptr && tiles <= GEMM_TC_MAX_TILE_COUNTERS),
+                   CAPDEC_ERR_BAD_ARG, "gemm_tc: split-K with a fused epilogue needs ticket counters (%d tiles)",
+                   tiles);
+    if ((const void*)k.addm == (const void*)k.abuf) k.addm = nullptr;   // addend already sits in the buffer
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(ceil_div(a.N, BM), row_tiles, zb * splits);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  CAPDEC_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, mW, mX, k));
+  count_launch();
   return CAPDEC_OK;
+}
+
+template <int NACC, int EPI>
+int launch_rows(const GemmArgs& a, cudaStream_t st) {
+  const int rows = (EPI == EPI_DHCELL && a.e.rows_epi > a.rows) ? a.e.rows_epi : a.rows;
+  if (rows <= 32) return launch<32, NACC, EPI>(a, st);
+  if (rows <= 64 || NACC > 1) return launch<64, NACC, EPI>(a, st);
+  return launch<128, NACC, EPI>(a, st);
 }
 
 }  // namespace
@@ -351,31 +574,33 @@ int gemm_tc_init() {
       return;
     }
     g_encode = (EncodeTiledFn)fn;
-    cudaError_t e1 = cudaFuncSetAttribute(gemm_tc_kernel<32>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Cfg<32>::SMEM_BYTES);
-    cudaError_t e2 = cudaFuncSetAttribute(gemm_tc_kernel<64>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Cfg<64>::SMEM_BYTES);
-    cudaError_t e3 = cudaFuncSetAttribute(gemm_tc_kernel<128>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          Cfg<128>::SMEM_BYTES);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm_tc_kernel) failed: %s",
-                cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
-      g_init_rc = CAPDEC_ERR_CUDA;
-    }
   });
   return g_init_rc;
 }
 
+// fused CELL epilogue keeps 4 accumulators of BNR columns each: rows <= 64 per tile row
+bool gemm_tc_cell_fusable(int rows) { return rows <= 64; }
+
 int gemm_tc(const GemmArgs& a, cudaStream_t st) {
-  if (a.rows <= 0 || a.N <= 0) return CAPDEC_OK;
-  CAPDEC_REQUIRE(a.X && a.W && a.out && a.K > 0, CAPDEC_ERR_BAD_ARG, "gemm_tc: null operand");
+  if (a.rows <= 0 && !(a.epi == EPI_DHCELL && a.e.rows_epi > 0)) return CAPDEC_OK;
+  if (a.N <= 0) return CAPDEC_OK;
+  CAPDEC_REQUIRE(a.X && a.W && a.K > 0, CAPDEC_ERR_BAD_ARG, "gemm_tc: null operand");
   CAPDEC_TRY(gemm_tc_init());
-  if (a.rows <= 32) return launch<32>(a, st);
-  if (a.rows <= 64) return launch<64>(a, st);
-  return launch<128>(a, st);
+  switch (a.epi) {
+    case EPI_PLAIN:
+      CAPDEC_REQUIRE(a.out, CAPDEC_ERR_BAD_ARG, "gemm_tc: null output");
+      return launch_rows<1, EPI_PLAIN>(a, st);
+    case EPI_G1: return launch_rows<1, EPI_G1>(a, st);
+    case EPI_P3: return launch_rows<1, EPI_P3>(a, st);
+    case EPI_WR: return launch_rows<1, EPI_WR>(a, st);
+    case EPI_DHCELL: return launch_rows<1, EPI_DHCELL>(a, st);
+    case EPI_CELL:
+      CAPDEC_REQUIRE(a.batch == 4 && a.rows <= 64, CAPDEC_ERR_BAD_SHAPE,
+                     "gemm_tc: fused cell epilogue needs batch == 4 gates and rows <= 64 (rows=%d)", a.rows);
+      return launch_rows<4, EPI_CELL>(a, st);
+  }
+  set_error("gemm_tc: bad epilogue %d", a.epi);
+  return CAPDEC_ERR_BAD_ARG;
 }
 
 }  // namespace capdec

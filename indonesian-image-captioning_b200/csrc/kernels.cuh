@@ -51,10 +51,11 @@ int cell_bwd(int precision, const float* dh_fc, int64_t ld_dhfc, const float* dh
              const float* gates, const float* c_prev, const float* c_new, int lstm_order,
              float dropout_p, const uint64_t* seed, int t, int T, void* dpre, float* dpre_f32, int rows,
              int D, cudaStream_t st);
-// SCN backward pointwise: du = w*v, dp = r*q, dv_acc += w*u, dq_acc += r*p ; wr = [g][b][w(F)|r(F)]
+// SCN backward pointwise: du = w*v, dp = r*q (row pitch lddp), dv_acc += w*u, dq_acc += r*p ;
+// wr = [g][b][w(F)|r(F)]
 int scn_bwd_products(int precision, const float* wr, const float* u, int64_t ldu, const float* p,
                      int64_t ldp, const float* v, const float* q, void* du, void* dp,
-                     float* dv_acc, float* dq_acc, int rows, int B, int F, cudaStream_t st);
+                     float* dv_acc, float* dq_acc, int rows, int B, int F, int64_t lddp, cudaStream_t st);
 // out[i] = a[i] (+ b[i]) ; small helpers
 int concat_bias(float* dst, const float* a, int na, const float* b, int nb, int nzero,
                 cudaStream_t st);

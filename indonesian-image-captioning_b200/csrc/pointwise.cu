@@ -191,6 +191,8 @@ __global__ void scn_form_m_kernel(const float* __restrict__ u, int64_t ldu,
                                   const float* __restrict__ p, int64_t ldp,
                                   const float* __restrict__ v, const float* __restrict__ q,
                                   FT* __restrict__ m, int rows, int B, int F) {
+  // B = rows per gate block of m: m[g][B][2F]
+  pdl_prologue();
   const int64_t total = (int64_t)rows * 4 * F;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -219,6 +221,7 @@ __global__ void cell_fwd_kernel(const float* __restrict__ preA, int64_t ldA,
                                 float* __restrict__ c_new, float* __restrict__ gates,
                                 FT* __restrict__ h_out, int64_t ldh, FT* __restrict__ hd_out,
                                 float dropout_p, const uint64_t* __restrict__ seed_dev, int t, int T, int rows, int D) {
+  pdl_prologue();
   int si, sf, so, sg;
   gate_slots(lstm_order, si, sf, so, sg);
   const int64_t total = (int64_t)rows * D;
@@ -258,6 +261,7 @@ __global__ void cell_bwd_kernel(const float* __restrict__ dh_fc, int64_t ld_dhfc
                                 const float* __restrict__ c_new, int lstm_order, float dropout_p,
                                 const uint64_t* __restrict__ seed_dev, int t, int T, FT* __restrict__ dpre,
                                 float* __restrict__ dpre_f32, int rows, int D) {
+  pdl_prologue();
   int si, sf, so, sg;
   gate_slots(lstm_order, si, sf, so, sg);
   const int64_t total = (int64_t)rows * D;
@@ -299,7 +303,8 @@ __global__ void scn_bwd_products_kernel(const float* __restrict__ wr, const floa
                                         const float* __restrict__ v, const float* __restrict__ q,
                                         FT* __restrict__ du, FT* __restrict__ dp,
                                         float* __restrict__ dv_acc, float* __restrict__ dq_acc,
-                                        int rows, int B, int F) {
+                                        int rows, int B, int F, int64_t lddp) {
+  pdl_prologue();
   const int64_t total = (int64_t)rows * 4 * F;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -310,7 +315,7 @@ __global__ void scn_bwd_products_kernel(const float* __restrict__ wr, const floa
     const float w = src[f], r = src[F + f];
     const int64_t k = (int64_t)b * 4 * F + n;
     du[k] = from_f<FT>(w * v[k]);
-    dp[k] = from_f<FT>(r * q[k]);
+    dp[(int64_t)b * lddp + n] = from_f<FT>(r * q[k]);
     dv_acc[k] += w * u[(int64_t)b * ldu + n];
     dq_acc[k] += r * p[(int64_t)b * ldp + n];
   }
@@ -453,9 +458,9 @@ int scn_form_m(int precision, const float* u, int64_t ldu, const float* p, int64
   if (rows <= 0) return CAPDEC_OK;
   const int g = grid_for((int64_t)rows * 4 * F, 256);
   if (precision == CAPDEC_BF16)
-    scn_form_m_kernel<bf16><<<g, 256, 0, st>>>(u, ldu, p, ldp, v, q, (bf16*)m, rows, B, F);
+    CAPDEC_CUDA_OK(launch_pdl(scn_form_m_kernel<bf16>, dim3(g), dim3(256), 0, st, 1, u, ldu, p, ldp, v, q, (bf16*)m, rows, B, F));
   else
-    scn_form_m_kernel<float><<<g, 256, 0, st>>>(u, ldu, p, ldp, v, q, (float*)m, rows, B, F);
+    CAPDEC_CUDA_OK(launch_pdl(scn_form_m_kernel<float>, dim3(g), dim3(256), 0, st, 1, u, ldu, p, ldp, v, q, (float*)m, rows, B, F));
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }
@@ -467,13 +472,13 @@ int cell_fwd(int precision, const float* preA, int64_t ldA, const float* preB, i
   if (rows <= 0) return CAPDEC_OK;
   const int g = grid_for((int64_t)rows * D, 128);
   if (precision == CAPDEC_BF16)
-    cell_fwd_kernel<bf16><<<g, 128, 0, st>>>(preA, ldA, preB, ldB, b1, b2, lstm_order, c_prev, c_new,
+    CAPDEC_CUDA_OK(launch_pdl(cell_fwd_kernel<bf16>, dim3(g), dim3(128), 0, st, 1, preA, ldA, preB, ldB, b1, b2, lstm_order, c_prev, c_new,
                                              gates, (bf16*)h_out, ldh, (bf16*)hd_out, dropout_p, seed,
-                                             t, T, rows, D);
+                                             t, T, rows, D));
   else
-    cell_fwd_kernel<float><<<g, 128, 0, st>>>(preA, ldA, preB, ldB, b1, b2, lstm_order, c_prev, c_new,
+    CAPDEC_CUDA_OK(launch_pdl(cell_fwd_kernel<float>, dim3(g), dim3(128), 0, st, 1, preA, ldA, preB, ldB, b1, b2, lstm_order, c_prev, c_new,
                                               gates, (float*)h_out, ldh, (float*)hd_out, dropout_p,
-                                              seed, t, T, rows, D);
+                                              seed, t, T, rows, D));
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }
@@ -485,28 +490,28 @@ int cell_bwd(int precision, const float* dh_fc, int64_t ld_dhfc, const float* dh
   if (rows <= 0) return CAPDEC_OK;
   const int g = grid_for((int64_t)rows * D, 128);
   if (precision == CAPDEC_BF16)
-    cell_bwd_kernel<bf16><<<g, 128, 0, st>>>(dh_fc, ld_dhfc, dh_rec, dc, gates, c_prev, c_new,
+    CAPDEC_CUDA_OK(launch_pdl(cell_bwd_kernel<bf16>, dim3(g), dim3(128), 0, st, 1, dh_fc, ld_dhfc, dh_rec, dc, gates, c_prev, c_new,
                                              lstm_order, dropout_p, seed, t, T, (bf16*)dpre, dpre_f32,
-                                             rows, D);
+                                             rows, D));
   else
-    cell_bwd_kernel<float><<<g, 128, 0, st>>>(dh_fc, ld_dhfc, dh_rec, dc, gates, c_prev, c_new,
+    CAPDEC_CUDA_OK(launch_pdl(cell_bwd_kernel<float>, dim3(g), dim3(128), 0, st, 1, dh_fc, ld_dhfc, dh_rec, dc, gates, c_prev, c_new,
                                               lstm_order, dropout_p, seed, t, T, (float*)dpre,
-                                              dpre_f32, rows, D);
+                                              dpre_f32, rows, D));
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }
 
 int scn_bwd_products(int precision, const float* wr, const float* u, int64_t ldu, const float* p,
                      int64_t ldp, const float* v, const float* q, void* du, void* dp,
-                     float* dv_acc, float* dq_acc, int rows, int B, int F, cudaStream_t st) {
+                     float* dv_acc, float* dq_acc, int rows, int B, int F, int64_t lddp, cudaStream_t st) {
   if (rows <= 0) return CAPDEC_OK;
   const int g = grid_for((int64_t)rows * 4 * F, 256);
   if (precision == CAPDEC_BF16)
-    scn_bwd_products_kernel<bf16><<<g, 256, 0, st>>>(wr, u, ldu, p, ldp, v, q, (bf16*)du, (bf16*)dp,
-                                                     dv_acc, dq_acc, rows, B, F);
+    CAPDEC_CUDA_OK(launch_pdl(scn_bwd_products_kernel<bf16>, dim3(g), dim3(256), 0, st, 1, wr, u, ldu, p, ldp, v, q, (bf16*)du, (bf16*)dp,
+                                                     dv_acc, dq_acc, rows, B, F, lddp));
   else
-    scn_bwd_products_kernel<float><<<g, 256, 0, st>>>(wr, u, ldu, p, ldp, v, q, (float*)du,
-                                                      (float*)dp, dv_acc, dq_acc, rows, B, F);
+    CAPDEC_CUDA_OK(launch_pdl(scn_bwd_products_kernel<float>, dim3(g), dim3(256), 0, st, 1, wr, u, ldu, p, ldp, v, q, (float*)du,
+                                                      (float*)dp, dv_acc, dq_acc, rows, B, F, lddp));
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }

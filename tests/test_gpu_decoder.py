@@ -67,9 +67,12 @@ def test_fp32_matches_reference_golden(name, loss_path):
         assert torch.equal(dec.decode_step.bias_ih.grad, dec.decode_step.bias_hh.grad)
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
 @pytest.mark.parametrize("name", ["train_attention_scn_medium", "train_pure_scn_medium",
                                   "train_pure_attention_medium"])
-def test_bf16_within_tolerance(name):
+def test_bf16_within_tolerance(name, fused, monkeypatch):
+    """fused=1 also drives the opt-in fused GEMM epilogues (CAPDEC_FUSED_EPILOGUE, gemm_tc.cu)."""
+    monkeypatch.setenv("CAPDEC_FUSED_EPILOGUE", fused)
     blob = load_golden(name)
     with capdec.precision_scope("bf16"):
         kind, dec, (enc, tags, caps, caplens) = _load(blob)
@@ -132,9 +135,12 @@ def test_fp32_full_width_matches_oracle(kind):
         assert not bad, bad
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_full_size_properties(precision):
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16-fused"])
+def test_full_size_properties(precision, monkeypatch):
     """BASELINE config 3 per-GPU shape (B=32, T=50, V=10k): size-independent properties."""
+    if precision == "bf16-fused":
+        monkeypatch.setenv("CAPDEC_FUSED_EPILOGUE", "1")
+        precision = "bf16"
     dims = dict(A=512, M=512, D=512, F=512, S=1000, V=10000, E=2048)
     B = 32
     lengths = O.tie_free_lengths(B)
