@@ -190,6 +190,10 @@ int capdec_gemm(int precision, const void* X, int64_t ldx, const void* W, int64_
                 int rows, int N, int K, int batch, int64_t sX, int64_t sW, int64_t sO,
                 int splitk, void* stream);
 
+/* Scratch floats capdec_attention_step needs for `rows` rows; capdec_attention_bwd_step needs this
+ * plus rows * ((P + 3) & ~3). */
+size_t capdec_attention_scratch_floats(int precision, int rows, int P, int E);
+
 /* Attention.forward on prepared features: att1 (G,P,A) / enc (G,P,E) in the feature type,
  * g1 (rows, ldg) fp32 with att2 at column 0 and the f_beta pre-activation at column
  * beta_col (beta_col < 0: no gate, z = awe).  Row r uses feature map r / rows_per_map. */
@@ -198,7 +202,7 @@ int capdec_attention_step(int precision, const void* att1, const void* enc,
                           const float* w_f, const float* b_f,
                           float* alpha_out, int64_t alpha_stride,
                           void* z_out, float* awe_out,
-                          int rows, int rows_per_map, int P, int E, int A, void* stream);
+                          int rows, int rows_per_map, int P, int E, int A, float* scratch, void* stream);
 
 /* Backward of capdec_attention_step for `rows` rows with one feature map each (training):
  * inputs dz (rows,E) = d loss / d z, the saved awe (rows,E) and alpha (rows, alpha_stride),
@@ -211,7 +215,7 @@ int capdec_attention_bwd_step(int precision, const void* att1, const void* enc,
                               const float* dalpha_ext, int64_t dalpha_stride,
                               const float* dz, const float* awe,
                               void* dba, int64_t lddba, float* dAtt1, float* dwf_part,
-                              float* dbf_part, int rows, int P, int E, int A, void* stream);
+                              float* dbf_part, int rows, int P, int E, int A, float* scratch, void* stream);
 
 /* SCNCell.forward for `rows` rows on fp32 master weights (packs them internally into
  * `workspace`): h_out/c_out (rows,D).  x (rows,X). */

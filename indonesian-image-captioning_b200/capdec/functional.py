@@ -429,11 +429,13 @@ def attention_step(att1, enc, g1, beta_col, w_f, b_f, rows_per_map=1, precision=
     alpha = torch.empty(rows, P, dtype=torch.float32, device=enc.device)
     z = torch.empty(rows, E, dtype=ft, device=enc.device)
     awe = torch.empty(rows, E, dtype=torch.float32, device=enc.device) if want_awe else None
+    scratch = torch.empty(max(1, lib.capdec_attention_scratch_floats(precision_code(prec), rows, P, E)),
+                          dtype=torch.float32, device=enc.device)
     with torch.cuda.device(enc.device):
         rc = lib.capdec_attention_step(precision_code(prec), _lib.ptr(att1), _lib.ptr(enc), _lib.ptr(g1),
                                        g1.stride(0), beta_col, _lib.ptr(w_f), _lib.ptr(b_f),
                                        _lib.ptr(alpha), P, _lib.ptr(z), _lib.ptr(awe), rows, rows_per_map,
-                                       P, E, A, _stream())
+                                       P, E, A, _lib.ptr(scratch), _stream())
     _lib.check(rc, "capdec_attention_step")
     return z, alpha, awe
 
@@ -455,12 +457,15 @@ def attention_bwd_step(att1, enc, g1, beta_col, w_f, alpha, dz, awe, dalpha_ext=
         dAtt1 = torch.zeros(rows, P, A, dtype=torch.float32, device=dev)
     dwf = torch.empty(rows, A, dtype=torch.float32, device=dev)
     dbf = torch.empty(rows, dtype=torch.float32, device=dev)
+    n_scr = lib.capdec_attention_scratch_floats(precision_code(prec), rows, P, E) + rows * ((P + 3) // 4 * 4)
+    scratch = torch.empty(max(1, n_scr), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = lib.capdec_attention_bwd_step(
             precision_code(prec), _lib.ptr(att1), _lib.ptr(enc), _lib.ptr(g1), g1.stride(0), beta_col,
             _lib.ptr(w_f), _lib.ptr(alpha), alpha.stride(0), _lib.ptr(dalpha_ext),
             dalpha_ext.stride(0) if dalpha_ext is not None else 0, _lib.ptr(dz), _lib.ptr(awe),
-            _lib.ptr(dba), ld, _lib.ptr(dAtt1), _lib.ptr(dwf), _lib.ptr(dbf), rows, P, E, A, _stream())
+            _lib.ptr(dba), ld, _lib.ptr(dAtt1), _lib.ptr(dwf), _lib.ptr(dbf), rows, P, E, A,
+            _lib.ptr(scratch), _stream())
     _lib.check(rc, "capdec_attention_bwd_step")
     return dba[:, :E], dba[:, E:E + A], dAtt1, dwf, dbf
 

@@ -8,93 +8,122 @@
 //   awe   = sum_p alpha_p enc[p,:]
 //   z     = sigmoid(beta_pre) * awe                      beta_pre = W_beta h + b_beta (G1 GEMM)
 //
-// This is the HBM/L2-bandwidth kernel of the decoder: every row streams att1[b] (P*A) and
-// enc[b] (P*E) once per step.  One thread-block CLUSTER handles one row: the CL CTAs of
-// the cluster split the P pixels for the score phase and the E channels for the weighted
-// sum; the 196 scores are exchanged through distributed shared memory (push model, one
-// cluster barrier), so a row's features are read exactly once while B*CL CTAs (>= 2 per SM
-// at B = 32) keep enough 16-byte loads in flight to cover the L2/HBM latency.  All global
-// feature loads are coalesced and L1-bypassing; reductions over the attention dim and the
-// softmax use warp shuffles.
-#include <cooperative_groups.h>
+// This is the bandwidth stage of the decoder: every row streams att1[b] (P*A) and enc[b] (P*E)
+// once per step, and at B = 32 rows it is LATENCY that decides (32 MB per step is 3-5 us of L2
+// bandwidth).  Each direction is therefore two short, wide kernels chained with programmatic
+// dependent launch, every thread issuing all of its 16-byte feature loads before the first use
+// (and before the PDL wait, since the features do not depend on the previous kernel):
+//
+//   forward   attn_scores_kernel   grid (pixel chunks, rows)    e_p for one chunk of pixels
+//             attn_wsum_kernel     grid (channel chunks, rows)  softmax (redundant per CTA, 196
+//                                                               values) + weighted sum + gate
+//   backward  attn_bwd_a_kernel    grid (channel chunks, rows)  gate backward + partial
+//                                                               dalpha_p = enc[p, chunk] . dawe
+//             attn_bwd_b_kernel    grid (rows)                  softmax backward + relu/score
+//                                                               backward -> datt2, dw_f, de
+//   after the loop  attn_datt1_kernel   dAtt1[b,p,a] = w_f[a] sum_t de[t,b,p] 1[att1+att2_t > 0]
+//
+// The (P x A) fp32 gradient of att1 is NOT read-modified-written every step (that alone was
+// 25.7 MB of traffic per step at B = 32): the steps only keep de (P floats per row) and the
+// batched kernel rebuilds the relu masks from att1 and the saved att2_t.  The first version of
+// this file used one thread-block cluster per row with a DSMEM score exchange; cluster launches
+// and the two cluster barriers cost more than the second kernel does.
+// All global feature loads are coalesced 16-byte L1-bypassing loads; reductions over the
+// attention / channel dims use warp shuffles.
 #include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace capdec {
 
 namespace {
 
-constexpr int NTHREADS = 256;
-constexpr int NWARPS = NTHREADS / 32;
-constexpr int CL_MAX = 8;
-constexpr int PXB = 4;        // pixels a warp keeps in flight per iteration
+constexpr int NT = 256;           // threads of the wide kernels
+constexpr int NW = NT / 32;
+constexpr int NTB = 512;          // threads of attn_bwd_b_kernel (one CTA per row)
+constexpr int NWB = NTB / 32;
+constexpr int PXS = 4;            // pixels a warp keeps in flight (score-side kernels)
+constexpr int UNR = 13;           // pixels a thread keeps in flight (channel-side kernels)
 
-struct FwdArgs {
-  const void* att1; const void* enc; const float* g1; int64_t ldg; int beta_col;
-  const float* w_f; const float* b_f; float* alpha_out; int64_t alpha_stride;
-  void* z_out; int64_t ldz; float* awe_out; int rows, rows_per_map, P, E, A;
+__device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
+
+// block-wide max / sum over NTHR threads through `red` (>= NTHR/32 floats)
+template <int NTHR>
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float m = red[0];
+#pragma unroll
+  for (int w = 1; w < NTHR / 32; ++w) m = fmaxf(m, red[w]);
+  return m;
+}
+template <int NTHR>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < NTHR / 32; ++w) s += red[w];
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------
+// forward A: scores of one pixel chunk
+// ---------------------------------------------------------------------------------------
+struct ScoreArgs {
+  const void* att1; const float* g1; int64_t ldg; const float* w_f; const float* b_f;
+  float* scores; int rows_per_map, P, A, Pc;
 };
 
 // NCH = 16-byte chunks per lane along the attention dim: A <= 32 * VEC * NCH
 template <typename FT, int NCH>
-__global__ void __launch_bounds__(NTHREADS)
-attn_fwd_kernel(FwdArgs a) {
+__global__ void __launch_bounds__(NT)
+attn_scores_kernel(ScoreArgs a) {
   constexpr int VEC = FTraits<FT>::VEC;
-  extern __shared__ __align__(16) float smem_f[];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int CL = (int)cluster.num_blocks();
-  const int rank = (int)cluster.block_rank();
-  const int row = blockIdx.x / CL;
-  const int map = row / a.rows_per_map;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int P = a.P, E = a.E, A = a.A;
-  const int Ppad = (P + 3) & ~3;
-  float* sc = smem_f;              // [Ppad] scores (all pixels, after the exchange)
-  float* al = sc + Ppad;           // [Ppad] alpha
-  float* red = al + Ppad;          // [NTHREADS * VEC] cross-group reduction
-
   pdl_launch_dependents();
-  if (CL > 1) cluster.barrier_arrive();     // "everyone has started" barrier, waited on before the push
-  pdl_wait();                               // g1 / features come from the previous kernels of the stream
-
+  const int row = blockIdx.y;
+  const int map = row / a.rows_per_map;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = a.P, A = a.A;
+  const int p_begin = blockIdx.x * a.Pc;
+  const int p_end = min(P, p_begin + a.Pc);
   const FT* att1 = (const FT*)a.att1 + (int64_t)map * P * A;
-  const FT* enc = (const FT*)a.enc + (int64_t)map * P * E;
+  // feature loads do not depend on the previous kernel: issue them before the PDL wait
+  uint4 v[PXS][NCH];
+  const int p0 = p_begin + warp;
+#pragma unroll
+  for (int i = 0; i < PXS; ++i) {
+    const int pi = p0 + i * NW;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int a0 = (c * 32 + lane) * VEC;
+      v[i][c] = make_uint4(0, 0, 0, 0);
+      if (a0 < A && pi < p_end) v[i][c] = ld_stream16(att1 + (int64_t)pi * A + a0);
+    }
+  }
+  pdl_wait();                               // g1 comes from the previous kernel of the stream
   const float* g1 = a.g1 + (int64_t)row * a.ldg;
-
-  // ---------------- phase 1: scores for this CTA's pixel slice ----------------
-  const int Pc = (P + CL - 1) / CL;
-  const int p_begin = rank * Pc;
-  const int p_end = min(P, p_begin + Pc);
   float att2[NCH][VEC], wf[NCH][VEC];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int a0 = (c * 32 + lane) * VEC;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      att2[c][v] = (a0 + v < A) ? g1[a0 + v] : 0.f;
-      wf[c][v] = (a0 + v < A) ? a.w_f[a0 + v] : 0.f;
+    for (int k = 0; k < VEC; ++k) {
+      att2[c][k] = (a0 + k < A) ? g1[a0 + k] : 0.f;
+      wf[c][k] = (a0 + k < A) ? a.w_f[a0 + k] : 0.f;
     }
   }
   const float bf = a.b_f[0];
-  for (int p = p_begin + warp; p < p_end; p += PXB * NWARPS) {
-    uint4 v[PXB][NCH];
+  float* sc = a.scores + (int64_t)row * pad4(P);
+  for (int p = p0;; p += PXS * NW) {
 #pragma unroll
-    for (int i = 0; i < PXB; ++i) {
-      const int pi = p + i * NWARPS;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int a0 = (c * 32 + lane) * VEC;
-        v[i][c] = make_uint4(0, 0, 0, 0);
-        if (a0 < A && pi < p_end) v[i][c] = ld_stream16(att1 + (int64_t)pi * A + a0);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < PXB; ++i) {
-      const int pi = p + i * NWARPS;
+    for (int i = 0; i < PXS; ++i) {
+      const int pi = p + i * NW;
       float s = 0.f;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -106,459 +135,533 @@ attn_fwd_kernel(FwdArgs a) {
       s = warp_sum(s);
       if (lane == 0 && pi < p_end) sc[pi] = s + bf;
     }
-  }
-  __syncthreads();
-  if (CL > 1) {
-    cluster.barrier_wait();                 // all CTAs of the cluster are running: DSMEM is valid
-    const int n_own = p_end - p_begin;
-    for (int i = tid; i < n_own * (CL - 1); i += NTHREADS) {
-      const int peer = (rank + 1 + i / n_own) % CL;
-      const int p = p_begin + i % n_own;
-      cluster.map_shared_rank(sc, peer)[p] = sc[p];
-    }
-    cluster.sync();                         // release/acquire: every CTA now holds all P scores
-  }
-
-  // ---------------- phase 2: softmax over the P pixels (warp 0) ----------------
-  if (warp == 0) {
-    float m = -INFINITY;
-    for (int p = lane; p < P; p += 32) m = fmaxf(m, sc[p]);
-    m = warp_max(m);
-    float s = 0.f;
-    for (int p = lane; p < P; p += 32) {
-      const float e = expf(sc[p] - m);
-      al[p] = e;
-      s += e;
-    }
-    s = warp_sum(s);
-    const float inv = 1.0f / s;
-    for (int p = lane; p < P; p += 32) {
-      const float v = al[p] * inv;
-      al[p] = v;
-      if (rank == 0 && a.alpha_out) a.alpha_out[(int64_t)row * a.alpha_stride + p] = v;
-    }
-  }
-  __syncthreads();
-
-  // ---------------- phase 3: awe over this CTA's channel slice ----------------
-  const int Ec = E / CL;
-  const int e_begin = rank * Ec;
-  const int ncol = Ec / VEC;
-  const int ncolPass = min(ncol, NTHREADS);
-  const int groups = NTHREADS / ncolPass;
-  const int grp = tid / ncolPass;
-  const int cip = tid % ncolPass;
-  constexpr int UNR = 8;
-  for (int cb = 0; cb < ncol; cb += ncolPass) {
-    const int col = cb + cip;
-    const bool active = grp < groups && col < ncol;
-    float acc[VEC];
+    if (p + PXS * NW >= p_end) break;
+    // more pixels than one pass covers (very large batches only): reload
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-    if (active) {
-      const FT* src = enc + e_begin + col * VEC;
-      int p = grp;
-      for (; p + (UNR - 1) * groups < P; p += UNR * groups) {
-        uint4 q[UNR];
+    for (int i = 0; i < PXS; ++i) {
+      const int pi = p + PXS * NW + i * NW;
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) q[u] = ld_stream16(src + (int64_t)(p + u * groups) * E);
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const float w = al[p + u * groups];
-          float f[VEC];
-          unpack16(q[u], f, FT());
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[v] = fmaf(w, f[v], acc[v]);
-        }
-      }
-      for (; p < P; p += groups) {
-        uint4 q0 = ld_stream16(src + (int64_t)p * E);
-        const float w0 = al[p];
-        float f[VEC];
-        unpack16(q0, f, FT());
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(w0, f[v], acc[v]);
-      }
-    }
-    if (groups > 1) {
-      __syncthreads();
-      if (active && grp > 0) {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) red[((grp - 1) * ncolPass + cip) * VEC + v] = acc[v];
-      }
-      __syncthreads();
-      if (active && grp == 0) {
-        for (int g = 1; g < groups; ++g)
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[v] += red[((g - 1) * ncolPass + cip) * VEC + v];
-      }
-    }
-    if (active && grp == 0) {
-      const int e0 = e_begin + col * VEC;
-      float zv[VEC];
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        float gate = 1.0f;
-        if (a.beta_col >= 0) gate = sigmoidf_(g1[a.beta_col + e0 + v]);
-        zv[v] = gate * acc[v];
-      }
-      if (a.awe_out) {
-        float* dst = a.awe_out + (int64_t)row * E + e0;
-#pragma unroll
-        for (int v = 0; v < VEC; v += 4)
-          *reinterpret_cast<float4*>(dst + v) = make_float4(acc[v], acc[v + 1], acc[v + 2], acc[v + 3]);
-      }
-      if (a.z_out) {
-        FT* dst = (FT*)a.z_out + (int64_t)row * a.ldz + e0;
-        *reinterpret_cast<uint4*>(dst) = pack16(zv, FT());
+      for (int c = 0; c < NCH; ++c) {
+        const int a0 = (c * 32 + lane) * VEC;
+        v[i][c] = make_uint4(0, 0, 0, 0);
+        if (a0 < A && pi < p_end) v[i][c] = ld_stream16(att1 + (int64_t)pi * A + a0);
       }
     }
   }
 }
 
-// ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------
+// forward B: softmax + weighted sum over one channel chunk + gate
+// ---------------------------------------------------------------------------------------
+struct WsumArgs {
+  const void* enc; const float* g1; int64_t ldg; int beta_col;
+  const float* scores; float* alpha_out; int64_t alpha_stride;
+  void* z_out; int64_t ldz; float* awe_out;
+  int rows_per_map, P, E, ncol;       // ncol = 16-byte columns per CTA
+};
+
+template <typename FT>
+__global__ void __launch_bounds__(NT)
+attn_wsum_kernel(WsumArgs a) {
+  constexpr int VEC = FTraits<FT>::VEC;
+  extern __shared__ __align__(16) float smem_f[];
+  pdl_launch_dependents();
+  const int row = blockIdx.y;
+  const int map = row / a.rows_per_map;
+  const int tid = threadIdx.x;
+  const int P = a.P, E = a.E, ncol = a.ncol;
+  const int Ppad = pad4(P);
+  float* al = smem_f;                 // [Ppad] alpha
+  float* red = al + Ppad;             // [NT * VEC] cross-group reduction (+ block reductions)
+  const int groups = NT / ncol;       // pixel groups; threads >= groups*ncol idle
+  const int grp = tid / ncol, col = tid - grp * ncol;
+  const bool active = grp < groups;
+  const int e0 = (blockIdx.x * ncol + col) * VEC;
+  const FT* src = (const FT*)a.enc + (int64_t)map * P * E + e0;
+  // first wave of feature loads before the PDL wait (they do not depend on the scores)
+  uint4 q[UNR];
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    const int p = grp + u * groups;
+    q[u] = make_uint4(0, 0, 0, 0);
+    if (active && p < P) q[u] = ld_stream16(src + (int64_t)p * E);
+  }
+  pdl_wait();
+  // ---- softmax over the P scores (every CTA of the row does it; 196 values) ----
+  const float* sc = a.scores + (int64_t)row * Ppad;
+  float m = -INFINITY;
+  for (int p = tid; p < P; p += NT) { const float s = sc[p]; al[p] = s; m = fmaxf(m, s); }
+  m = block_max<NT>(m, red);
+  float sum = 0.f;
+  for (int p = tid; p < P; p += NT) { const float e = expf(al[p] - m); al[p] = e; sum += e; }
+  sum = block_sum<NT>(sum, red);
+  const float inv = 1.0f / sum;
+  for (int p = tid; p < P; p += NT) {
+    const float v = al[p] * inv;
+    al[p] = v;
+    if (blockIdx.x == 0 && a.alpha_out) a.alpha_out[(int64_t)row * a.alpha_stride + p] = v;
+  }
+  __syncthreads();
+  // ---- weighted sum ----
+  float acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  for (int pb = 0; pb < P; pb += UNR * groups) {
+    if (pb > 0) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int p = pb + grp + u * groups;
+        q[u] = make_uint4(0, 0, 0, 0);
+        if (active && p < P) q[u] = ld_stream16(src + (int64_t)p * E);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int p = pb + grp + u * groups;
+      const float w = (active && p < P) ? al[p] : 0.f;
+      float f[VEC];
+      unpack16(q[u], f, FT());
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w, f[k], acc[k]);
+    }
+  }
+  if (groups > 1) {
+    __syncthreads();
+    if (active && grp > 0) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) red[((grp - 1) * ncol + col) * VEC + k] = acc[k];
+    }
+    __syncthreads();
+    if (grp == 0) {
+      for (int g = 1; g < groups; ++g)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] += red[((g - 1) * ncol + col) * VEC + k];
+    }
+  }
+  if (grp == 0) {
+    const float* g1 = a.g1 + (int64_t)row * a.ldg;
+    float zv[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float gate = 1.0f;
+      if (a.beta_col >= 0) gate = sigmoidf_(g1[a.beta_col + e0 + k]);
+      zv[k] = gate * acc[k];
+    }
+    if (a.awe_out) {
+      float* dst = a.awe_out + (int64_t)row * E + e0;
+#pragma unroll
+      for (int k = 0; k < VEC; k += 4)
+        *reinterpret_cast<float4*>(dst + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+    }
+    if (a.z_out) {
+      FT* dst = (FT*)a.z_out + (int64_t)row * a.ldz + e0;
+      *reinterpret_cast<uint4*>(dst) = pack16(zv, FT());
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // backward (attention part)
 //   dgate = dz*awe ; dawe = dz*gate ; dbeta_pre = dgate*gate*(1-gate)
 //   dalpha_p = enc[p,:].dawe + dalpha_ext_p
 //   de_p = alpha_p (dalpha_p - sum_q alpha_q dalpha_q)
 //   drelu[p,a] = de_p w_f[a] 1[att1[p,a]+att2[a] > 0]
-//   datt2[a] = sum_p drelu[p,a] ; dAtt1[p,a] += drelu[p,a] (accumulated over time)
+//   datt2[a] = sum_p drelu[p,a] ; dAtt1[p,a] += drelu[p,a] (after the loop, attn_datt1_kernel)
 //   dw_f[a] += sum_p de_p relu(.)[p,a] ; db_f += sum_p de_p
-// ---------------------------------------------------------------------------
-struct BwdArgs {
-  const void* att1; const void* enc; const float* g1; int64_t ldg; int beta_col;
-  const float* w_f; const float* alpha; int64_t alpha_stride;
-  const float* dalpha_ext; int64_t dalpha_stride;
+// ---------------------------------------------------------------------------------------
+struct BwdAArgs {
+  const void* enc; const float* g1; int64_t ldg; int beta_col;
   const float* dz; int64_t lddz; const float* awe;
   void* dba; int64_t lddba;           // feature type: [dbeta_pre (E) | datt2 (A)]
-  float* dAtt1;                       // [rows][P][A] fp32, accumulated
-  float* dwf_part; float* dbf_part;   // [rows][A], [rows]
-  int rows, P, E, A;
+  float* part;                        // [rows][EC][Ppad] partial dalpha
+  int P, E, ncol, cpl;                // cpl = lanes per pixel group (power of two, >= ncol, <= 32)
 };
 
-// NCE = 16-byte chunks per lane along the CTA's channel slice: E/CL <= 32 * VEC * NCE
-template <typename FT, int NCH, int NCE>
-__global__ void __launch_bounds__(NTHREADS)
-attn_bwd_kernel(BwdArgs a) {
+template <typename FT>
+__global__ void __launch_bounds__(NT)
+attn_bwd_a_kernel(BwdAArgs a) {
   constexpr int VEC = FTraits<FT>::VEC;
-  extern __shared__ __align__(16) float smem_f[];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int CL = (int)cluster.num_blocks();
-  const int rank = (int)cluster.block_rank();
-  const int row = blockIdx.x / CL;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int P = a.P, E = a.E, A = a.A;
-  const int Ppad = (P + 3) & ~3;
-  const int Apad = (A + 3) & ~3;
-  float* part = smem_f;                       // [CL_MAX][Ppad] partial dalpha from each CTA
-  float* al = part + CL_MAX * Ppad;           // [Ppad] alpha
-  float* de = al + Ppad;                      // [Ppad]
-  float* redA = de + Ppad;                    // [NWARPS][2][Apad]
-  float* partA = redA + NWARPS * 2 * Apad;    // [CL_MAX][2][Apad]  (used on rank 0)
-
   pdl_launch_dependents();
-  if (CL > 1) cluster.barrier_arrive();
-  pdl_wait();
-
-  const FT* att1 = (const FT*)a.att1 + (int64_t)row * P * A;
-  const FT* enc = (const FT*)a.enc + (int64_t)row * P * E;
-  const float* g1 = a.g1 + (int64_t)row * a.ldg;
-  const float* dz = a.dz + (int64_t)row * a.lddz;
-  const float* awe = a.awe + (int64_t)row * E;
-  FT* dba = (FT*)a.dba + (int64_t)row * a.lddba;
-
-  // ---- phase A: gate backward on this CTA's channel slice; keep dawe in registers ----
-  const int Ec = E / CL;
-  const int e_begin = rank * Ec;
-  const int ncol = Ec / VEC;                  // host guarantees ncol <= 32*NCE
-  float dawe[NCE][VEC];
+  const int row = blockIdx.y, chunk = blockIdx.x, EC = gridDim.x;
+  const int tid = threadIdx.x;
+  const int P = a.P, E = a.E, ncol = a.ncol, cpl = a.cpl;
+  const int Ppad = pad4(P);
+  const int npg = NT / cpl;           // pixel groups per CTA
+  const int pg = tid / cpl, col = tid - pg * cpl;
+  const bool col_ok = col < ncol;
+  const int e0 = (chunk * ncol + col) * VEC;
+  const FT* src = (const FT*)a.enc + (int64_t)row * P * E + e0;
+  uint4 q[UNR];
 #pragma unroll
-  for (int c = 0; c < NCE; ++c) {
-    const int col = c * 32 + lane;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) dawe[c][v] = 0.f;
-    if (col < ncol) {
-      const int e0 = e_begin + col * VEC;
-      float db[VEC];
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const float gate = sigmoidf_(g1[a.beta_col + e0 + v]);
-        const float d = dz[e0 + v];
-        dawe[c][v] = d * gate;
-        db[v] = d * awe[e0 + v] * gate * (1.0f - gate);
-      }
-      if (warp == 0) *reinterpret_cast<uint4*>(dba + e0) = pack16(db, FT());
-    }
+  for (int u = 0; u < UNR; ++u) {
+    const int p = pg + u * npg;
+    q[u] = make_uint4(0, 0, 0, 0);
+    if (col_ok && p < P) q[u] = ld_stream16(src + (int64_t)p * E);
   }
-  for (int p = tid; p < P; p += NTHREADS) al[p] = a.alpha[(int64_t)row * a.alpha_stride + p];
-
-  // ---- phase B: partial dalpha_p = enc[p, slice] . dawe[slice]  (warp per pixel) ----
-  float* my_part = part + rank * Ppad;
-  for (int p = warp; p < P; p += PXB * NWARPS) {
-    uint4 v[PXB][NCE];
+  pdl_wait();                         // dz comes from the previous kernel
+  // ---- gate backward on this thread's 16-byte column ----
+  float dawe[VEC];
 #pragma unroll
-    for (int i = 0; i < PXB; ++i) {
-      const int pi = p + i * NWARPS;
+  for (int k = 0; k < VEC; ++k) dawe[k] = 0.f;
+  if (col_ok) {
+    const float* g1 = a.g1 + (int64_t)row * a.ldg + a.beta_col + e0;
+    const float* dz = a.dz + (int64_t)row * a.lddz + e0;
+    const float* awe = a.awe + (int64_t)row * E + e0;
+    float db[VEC];
 #pragma unroll
-      for (int c = 0; c < NCE; ++c) {
-        const int col = c * 32 + lane;
-        v[i][c] = make_uint4(0, 0, 0, 0);
-        if (col < ncol && pi < P) v[i][c] = ld_stream16(enc + (int64_t)pi * E + e_begin + col * VEC);
+    for (int k = 0; k < VEC; ++k) {
+      const float gate = sigmoidf_(g1[k]);
+      const float d = dz[k];
+      dawe[k] = d * gate;
+      db[k] = d * awe[k] * gate * (1.0f - gate);
+    }
+    if (pg == 0) *reinterpret_cast<uint4*>((FT*)a.dba + (int64_t)row * a.lddba + e0) = pack16(db, FT());
+  }
+  // ---- partial dalpha_p over this channel chunk ----
+  float* part = a.part + ((int64_t)row * EC + chunk) * Ppad;
+  for (int pb = 0; pb < P; pb += UNR * npg) {
+    if (pb > 0) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int p = pb + pg + u * npg;
+        q[u] = make_uint4(0, 0, 0, 0);
+        if (col_ok && p < P) q[u] = ld_stream16(src + (int64_t)p * E);
       }
     }
 #pragma unroll
-    for (int i = 0; i < PXB; ++i) {
-      const int pi = p + i * NWARPS;
+    for (int u = 0; u < UNR; ++u) {
+      const int p = pb + pg + u * npg;
+      float f[VEC];
+      unpack16(q[u], f, FT());
       float s = 0.f;
 #pragma unroll
-      for (int c = 0; c < NCE; ++c) {
-        float f[VEC];
-        unpack16(v[i][c], f, FT());
+      for (int k = 0; k < VEC; ++k) s = fmaf(f[k], dawe[k], s);
+      for (int o = cpl >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (col == 0 && p < P) part[p] = s;
+    }
+  }
+}
+
+struct BwdBArgs {
+  const void* att1; const float* g1; int64_t ldg; const float* w_f;
+  const float* alpha; int64_t alpha_stride; const float* dalpha_ext; int64_t dalpha_stride;
+  const float* part; int EC;
+  void* dba; int64_t lddba; int dba_col;       // datt2 -> dba[row][dba_col + a]
+  float* de_out;                               // [rows][Ppad]
+  float* dwf_part; float* dbf_part;            // [rows][A], [rows]
+  int P, A;
+};
+
+template <typename FT, int NCH>
+__global__ void __launch_bounds__(NTB, 1)
+attn_bwd_b_kernel(BwdBArgs a) {
+  constexpr int VEC = FTraits<FT>::VEC;
+  extern __shared__ __align__(16) float smem_f[];
+  pdl_launch_dependents();
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P = a.P, A = a.A;
+  const int Ppad = pad4(P), Apad = pad4(A);
+  float* al = smem_f;                 // [Ppad] alpha
+  float* de = al + Ppad;              // [Ppad]
+  float* red = de + Ppad;             // [32]
+  float* redA = red + 32;             // [NWB][2][Apad]
+  const FT* att1 = (const FT*)a.att1 + (int64_t)row * P * A;
+  // first wave of att1 loads before the PDL wait
+  uint4 v[PXS][NCH];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) s = fmaf(f[k], dawe[c][k], s);
-      }
-      s = warp_sum(s);
-      if (lane == 0 && pi < P) my_part[pi] = s;
+  for (int i = 0; i < PXS; ++i) {
+    const int pi = warp + i * NWB;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int a0 = (c * 32 + lane) * VEC;
+      v[i][c] = make_uint4(0, 0, 0, 0);
+      if (a0 < A && pi < P) v[i][c] = ld_stream16(att1 + (int64_t)pi * A + a0);
     }
   }
+  pdl_wait();
+  // ---- dalpha = sum of the channel-chunk partials (+ external), softmax backward ----
+  float dot = 0.f;
+  for (int p = tid; p < P; p += NTB) {
+    float d = 0.f;
+    for (int c = 0; c < a.EC; ++c) d += a.part[((int64_t)row * a.EC + c) * Ppad + p];
+    if (a.dalpha_ext) d += a.dalpha_ext[(int64_t)row * a.dalpha_stride + p];
+    const float al_p = a.alpha[(int64_t)row * a.alpha_stride + p];
+    al[p] = al_p;
+    de[p] = d;
+    dot = fmaf(al_p, d, dot);
+  }
+  dot = block_sum<NTB>(dot, red);
+  float sde = 0.f;
+  for (int p = tid; p < P; p += NTB) {
+    const float x = al[p] * (de[p] - dot);
+    de[p] = x;
+    sde += x;
+    if (a.de_out) a.de_out[(int64_t)row * Ppad + p] = x;
+  }
+  sde = block_sum<NTB>(sde, red);
+  if (tid == 0) a.dbf_part[row] = sde;
   __syncthreads();
-  if (CL > 1) {
-    cluster.barrier_wait();
-    for (int i = tid; i < P * (CL - 1); i += NTHREADS) {
-      const int peer = (rank + 1 + i / P) % CL;
-      const int p = i % P;
-      cluster.map_shared_rank(part, peer)[rank * Ppad + p] = my_part[p];
-    }
-    cluster.sync();
-  }
-
-  // ---- phase C: softmax backward (warp 0), de_p for all pixels ----
-  if (warp == 0) {
-    float dot = 0.f;
-    for (int p = lane; p < P; p += 32) {
-      float d = 0.f;
-      for (int r = 0; r < CL; ++r) d += part[r * Ppad + p];
-      if (a.dalpha_ext) d += a.dalpha_ext[(int64_t)row * a.dalpha_stride + p];
-      de[p] = d;
-      dot = fmaf(al[p], d, dot);
-    }
-    dot = warp_sum(dot);
-    float sde = 0.f;
-    for (int p = lane; p < P; p += 32) {
-      const float v = al[p] * (de[p] - dot);
-      de[p] = v;
-      sde += v;
-    }
-    sde = warp_sum(sde);
-    if (lane == 0 && rank == 0) a.dbf_part[row] = sde;
-  }
-  __syncthreads();
-
-  // ---- phase D: relu/score backward on this CTA's pixel slice ----
-  const int Pc = (P + CL - 1) / CL;
-  const int p_begin = rank * Pc;
-  const int p_end = min(P, p_begin + Pc);
+  // ---- relu / score backward: warp per pixel, lane holds NCH*VEC attention features ----
+  const float* g1 = a.g1 + (int64_t)row * a.ldg;
   float att2[NCH][VEC], wf[NCH][VEC], dacc[NCH][VEC], wacc[NCH][VEC];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int a0 = (c * 32 + lane) * VEC;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      att2[c][v] = (a0 + v < A) ? g1[a0 + v] : 0.f;
-      wf[c][v] = (a0 + v < A) ? a.w_f[a0 + v] : 0.f;
-      dacc[c][v] = 0.f;
-      wacc[c][v] = 0.f;
+    for (int k = 0; k < VEC; ++k) {
+      att2[c][k] = (a0 + k < A) ? g1[a0 + k] : 0.f;
+      wf[c][k] = (a0 + k < A) ? a.w_f[a0 + k] : 0.f;
+      dacc[c][k] = 0.f;
+      wacc[c][k] = 0.f;
     }
   }
-  float* dA = a.dAtt1 + (int64_t)row * P * A;
-  for (int p = p_begin + warp; p < p_end; p += 2 * NWARPS) {
-    const int p2 = p + NWARPS;
-    const bool has2 = p2 < p_end;
-    uint4 q1[NCH], q2[NCH];
+  for (int p = warp; p < P; p += PXS * NWB) {
+    if (p != warp) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int a0 = (c * 32 + lane) * VEC;
-      q1[c] = make_uint4(0, 0, 0, 0);
-      q2[c] = make_uint4(0, 0, 0, 0);
-      if (a0 < A) {
-        q1[c] = ld_stream16(att1 + (int64_t)p * A + a0);
-        if (has2) q2[c] = ld_stream16(att1 + (int64_t)p2 * A + a0);
+      for (int i = 0; i < PXS; ++i) {
+        const int pi = p + i * NWB;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int a0 = (c * 32 + lane) * VEC;
+          v[i][c] = make_uint4(0, 0, 0, 0);
+          if (a0 < A && pi < P) v[i][c] = ld_stream16(att1 + (int64_t)pi * A + a0);
+        }
       }
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      if (i == 1 && !has2) break;
-      const int pi = i == 0 ? p : p2;
-      const float dep = de[pi];
+    for (int i = 0; i < PXS; ++i) {
+      const int pi = p + i * NWB;
+      const float dep = pi < P ? de[pi] : 0.f;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        const int a0 = (c * 32 + lane) * VEC;
-        if (a0 < A) {
-          float f[VEC], dr[VEC];
-          unpack16(i == 0 ? q1[c] : q2[c], f, FT());
+        float f[VEC];
+        unpack16(v[i][c], f, FT());
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) {
-            const float pre = f[v] + att2[c][v];
-            const float on = pre > 0.f ? 1.f : 0.f;
-            dr[v] = dep * wf[c][v] * on;
-            dacc[c][v] += dr[v];
-            wacc[c][v] = fmaf(dep, pre * on, wacc[c][v]);
-          }
-          float* d = dA + (int64_t)pi * A + a0;
-#pragma unroll
-          for (int v = 0; v < VEC; v += 4) {
-            float4 o = *reinterpret_cast<float4*>(d + v);
-            o.x += dr[v]; o.y += dr[v + 1]; o.z += dr[v + 2]; o.w += dr[v + 3];
-            *reinterpret_cast<float4*>(d + v) = o;
-          }
+        for (int k = 0; k < VEC; ++k) {
+          const float pre = f[k] + att2[c][k];
+          const float on = pre > 0.f ? 1.f : 0.f;
+          dacc[c][k] = fmaf(dep * wf[c][k], on, dacc[c][k]);
+          wacc[c][k] = fmaf(dep, pre * on, wacc[c][k]);
         }
       }
     }
   }
-  // cross-warp reduction of datt2 / dw_f partials
+  // cross-warp reduction of datt2 / dw_f
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int a0 = (c * 32 + lane) * VEC;
     if (a0 < A) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        redA[(warp * 2 + 0) * Apad + a0 + v] = dacc[c][v];
-        redA[(warp * 2 + 1) * Apad + a0 + v] = wacc[c][v];
+      for (int k = 0; k < VEC; ++k) {
+        redA[(warp * 2 + 0) * Apad + a0 + k] = dacc[c][k];
+        redA[(warp * 2 + 1) * Apad + a0 + k] = wacc[c][k];
       }
     }
   }
   __syncthreads();
-  float* dstA = (CL > 1) ? cluster.map_shared_rank(partA, 0) : partA;
-  for (int i = tid; i < 2 * A; i += NTHREADS) {
-    const int which = i / A, aa = i % A;
+  FT* dba = (FT*)a.dba + (int64_t)row * a.lddba + a.dba_col;
+  for (int i = tid; i < 2 * A; i += NTB) {
+    const int which = i / A, aa = i - which * A;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < NWARPS; ++w) s += redA[(w * 2 + which) * Apad + aa];
-    dstA[(rank * 2 + which) * Apad + aa] = s;
+    for (int w = 0; w < NWB; ++w) s += redA[(w * 2 + which) * Apad + aa];
+    if (which == 0) dba[aa] = from_f<FT>(s);
+    else a.dwf_part[(int64_t)row * A + aa] = s;
   }
-  if (CL > 1) cluster.sync(); else __syncthreads();
-  if (rank == 0) {
-    for (int aa = tid; aa < A; aa += NTHREADS) {
-      float s0 = 0.f, s1 = 0.f;
-      for (int r = 0; r < CL; ++r) {
-        s0 += partA[(r * 2 + 0) * Apad + aa];
-        s1 += partA[(r * 2 + 1) * Apad + aa];
+}
+
+// ---------------------------------------------------------------------------------------
+// after the loop: dAtt1[b,p,a] (+)= w_f[a] * sum_t de[t,b,p] * 1[att1[b,p,a] + att2[t,b,a] > 0]
+// grid (pixel tiles, B); thread = attention feature(s); PT pixels per CTA in registers
+// ---------------------------------------------------------------------------------------
+constexpr int PT = 14;
+struct Datt1Args {
+  const void* att1; const float* g1; int64_t ldg; int64_t g1_step;      // att2[t][b] = g1 + t*g1_step + b*ldg
+  const float* de; int64_t de_step;                                     // de[t][b][Ppad]
+  const float* w_f; float* dAtt1; int accumulate; int T, P, A;
+};
+
+template <typename FT, int NA>
+__global__ void __launch_bounds__(NT)
+attn_datt1_kernel(Datt1Args a) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int b = blockIdx.y, p0 = blockIdx.x * PT;
+  const int tid = threadIdx.x;
+  const int T = a.T, P = a.P, A = a.A, Ppad = pad4(P);
+  float* sde = smem_f;                // [T][PT]
+  for (int i = tid; i < T * PT; i += NT) {
+    const int t = i / PT, j = i - t * PT;
+    sde[i] = (p0 + j < P) ? a.de[(int64_t)t * a.de_step + (int64_t)b * Ppad + p0 + j] : 0.f;
+  }
+  const FT* att1 = (const FT*)a.att1 + ((int64_t)b * P + p0) * A;
+  float x[NA][PT], acc[NA][PT];
+#pragma unroll
+  for (int c = 0; c < NA; ++c) {
+    const int aa = tid + c * NT;
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      x[c][j] = (aa < A && p0 + j < P) ? to_f(att1[(int64_t)j * A + aa]) : 0.f;
+      acc[c][j] = 0.f;
+    }
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    const float* att2 = a.g1 + (int64_t)t * a.g1_step + (int64_t)b * a.ldg;
+#pragma unroll
+    for (int c = 0; c < NA; ++c) {
+      const int aa = tid + c * NT;
+      const float a2 = aa < A ? att2[aa] : 0.f;
+#pragma unroll
+      for (int j = 0; j < PT; ++j)
+        acc[c][j] = fmaf(sde[t * PT + j], (x[c][j] + a2 > 0.f) ? 1.f : 0.f, acc[c][j]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NA; ++c) {
+    const int aa = tid + c * NT;
+    if (aa < A) {
+      const float wf = a.w_f[aa];
+#pragma unroll
+      for (int j = 0; j < PT; ++j) {
+        if (p0 + j < P) {
+          float* dst = a.dAtt1 + ((int64_t)b * P + p0 + j) * A + aa;
+          const float val = wf * acc[c][j];
+          *dst = a.accumulate ? *dst + val : val;
+        }
       }
-      dba[E + aa] = from_f<FT>(s0);
-      a.dwf_part[(int64_t)row * A + aa] = s1;
     }
   }
 }
 
-size_t fwd_smem(int P) { return (size_t)(2 * ((P + 3) & ~3) + NTHREADS * 8) * sizeof(float); }
-size_t bwd_smem(int P, int A) {
-  const int Ppad = (P + 3) & ~3, Apad = (A + 3) & ~3;
-  return (size_t)(CL_MAX * Ppad + 2 * Ppad + NWARPS * 2 * Apad + CL_MAX * 2 * Apad) * sizeof(float);
+// ------------------------------- host side -------------------------------
+// channel chunking shared by forward B and backward A: ncol 16-byte columns per CTA, <= 32
+struct Chunking { int EC, ncol, cpl; };
+Chunking pick_chunks(int E, int vec, int rows) {
+  const int cols = E / vec;
+  int EC = ceil_div(cols, 32);
+  while (cols % EC != 0) ++EC;
+  // small batches: more, narrower CTAs so that every thread's loads fit one wave
+  while ((int64_t)rows * EC < 2 * 148 && (cols / EC) % 2 == 0 && cols / EC > 8) EC *= 2;
+  Chunking c;
+  c.EC = EC;
+  c.ncol = cols / EC;
+  c.cpl = 1;
+  while (c.cpl < c.ncol) c.cpl *= 2;
+  return c;
 }
 
 template <typename ArgsT>
-int launch_cluster(void (*kernel)(ArgsT), const ArgsT& args, int rows, int CL, size_t smem, cudaStream_t st) {
-  CAPDEC_CUDA_OK(launch_pdl(kernel, dim3(rows * CL, 1, 1), dim3(NTHREADS, 1, 1), smem, st, CL, args));
+int launch_attn(void (*kernel)(ArgsT), dim3 grid, int threads, size_t smem, cudaStream_t st,
+                const ArgsT& args) {
+  CAPDEC_CUDA_OK(launch_pdl(kernel, grid, dim3(threads, 1, 1), smem, st, 1, args));
   count_launch();
-  return CAPDEC_OK;
-}
-
-int env_cluster() {
-  static int v = [] {
-    const char* s = getenv("CAPDEC_ATTN_CLUSTER");
-    return s ? atoi(s) : 0;
-  }();
-  return v;
-}
-
-// cluster size: >= 2 CTAs per SM over the 148 SMs when the batch is small, bounded by the
-// divisibility of the channel slice; CAPDEC_ATTN_CLUSTER overrides (tuning sweeps)
-int pick_cluster(int rows, int E, int vec, int min_cl) {
-  int cl = min_cl;
-  const int want = env_cluster();
-  if (want > 0) {
-    while (cl < want && cl < CL_MAX && (E % (2 * cl * vec)) == 0) cl *= 2;
-    return cl;
-  }
-  while (cl < CL_MAX && rows * cl < 2 * 148 - 40 && (E % (2 * cl * vec)) == 0) cl *= 2;
-  return cl;
-}
-
-template <typename FT, int NCH>
-int launch_bwd(const BwdArgs& a, int CL, int nce, size_t smem, cudaStream_t st) {
-  if (nce <= 1) return launch_cluster(attn_bwd_kernel<FT, NCH, 1>, a, a.rows, CL, smem, st);
-  if (nce <= 2) return launch_cluster(attn_bwd_kernel<FT, NCH, 2>, a, a.rows, CL, smem, st);
-  return launch_cluster(attn_bwd_kernel<FT, NCH, 4>, a, a.rows, CL, smem, st);
-}
-
-template <typename FT, int NCH>
-int set_bwd_attr() {
-  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<FT, NCH, 1>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<FT, NCH, 2>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_kernel<FT, NCH, 4>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   return CAPDEC_OK;
 }
 
 }  // namespace
 
 int attention_init() {
-  CAPDEC_TRY((set_bwd_attr<float, 2>()));
-  CAPDEC_TRY((set_bwd_attr<float, 4>()));
-  CAPDEC_TRY((set_bwd_attr<bf16, 2>()));
-  CAPDEC_TRY((set_bwd_attr<bf16, 4>()));
+  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_b_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_b_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_b_kernel<bf16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CAPDEC_CUDA_OK(cudaFuncSetAttribute(attn_bwd_b_kernel<bf16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   return CAPDEC_OK;
+}
+
+size_t attention_scratch_floats(int precision, int rows, int P, int E) {
+  if (rows <= 0 || P <= 0 || E <= 0) return 0;
+  const int vec = precision == CAPDEC_BF16 ? 8 : 4;
+  if (E % vec != 0) return 0;
+  const int Ppad = (P + 3) & ~3;
+  // forward: scores [rows][Ppad]; backward: partial dalpha [rows][EC][Ppad] (EC is largest at rows = 1)
+  const Chunking c = pick_chunks(E, vec, 1);
+  return (size_t)rows * (size_t)c.EC * Ppad;
 }
 
 int attention_fwd(int precision, const void* att1, const void* enc, const float* g1, int64_t ldg,
                   int beta_col, const float* w_f, const float* b_f, float* alpha_out,
                   int64_t alpha_stride, void* z_out, int64_t ldz, float* awe_out, int rows,
-                  int rows_per_map, int P, int E, int A, cudaStream_t st) {
+                  int rows_per_map, int P, int E, int A, float* scratch, cudaStream_t st) {
   if (rows <= 0) return CAPDEC_OK;
   const int vec = precision == CAPDEC_BF16 ? 8 : 4;
   CAPDEC_REQUIRE(E % vec == 0 && A % vec == 0 && A <= 32 * vec * 4, CAPDEC_ERR_BAD_SHAPE,
                  "attention: need E,A multiples of %d and A <= %d (E=%d A=%d)", vec, 32 * vec * 4, E, A);
-  FwdArgs a{att1, enc, g1, ldg, beta_col, w_f, b_f, alpha_out, alpha_stride, z_out, ldz, awe_out,
-            rows, rows_per_map, P, E, A};
-  const int CL = pick_cluster(rows, E, vec, 1);
+  CAPDEC_REQUIRE(scratch != nullptr, CAPDEC_ERR_BAD_ARG, "attention: scratch is NULL");
+  // ---- A: scores ----
+  int PC = ceil_div(P, PXS * NW);                                   // one pass of PXS*NW pixels per CTA ...
+  while ((int64_t)rows * PC > 8 * 148 && PC > 1) PC = (PC + 1) / 2;     // ... unless the grid gets too large
+  ScoreArgs sa{att1, g1, ldg, w_f, b_f, scratch, rows_per_map, P, A, ceil_div(P, PC)};
+  PC = ceil_div(P, sa.Pc);
   const bool small = A <= 32 * vec * 2;
+  dim3 gs(PC, rows, 1);
   if (precision == CAPDEC_BF16) {
-    if (small) return launch_cluster(attn_fwd_kernel<bf16, 2>, a, rows, CL, fwd_smem(P), st);
-    return launch_cluster(attn_fwd_kernel<bf16, 4>, a, rows, CL, fwd_smem(P), st);
+    if (small) CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 2>, gs, NT, 0, st, sa));
+    else CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 4>, gs, NT, 0, st, sa));
+  } else {
+    if (small) CAPDEC_TRY(launch_attn(attn_scores_kernel<float, 2>, gs, NT, 0, st, sa));
+    else CAPDEC_TRY(launch_attn(attn_scores_kernel<float, 4>, gs, NT, 0, st, sa));
   }
-  if (small) return launch_cluster(attn_fwd_kernel<float, 2>, a, rows, CL, fwd_smem(P), st);
-  return launch_cluster(attn_fwd_kernel<float, 4>, a, rows, CL, fwd_smem(P), st);
+  // ---- B: softmax + weighted sum + gate ----
+  const Chunking ch = pick_chunks(E, vec, rows);
+  WsumArgs wa{enc, g1, ldg, beta_col, scratch, alpha_out, alpha_stride, z_out, ldz, awe_out,
+              rows_per_map, P, E, ch.ncol};
+  const size_t smem = (size_t)(((P + 3) & ~3) + NT * 8) * sizeof(float);
+  dim3 gw(ch.EC, rows, 1);
+  if (precision == CAPDEC_BF16) return launch_attn(attn_wsum_kernel<bf16>, gw, NT, smem, st, wa);
+  return launch_attn(attn_wsum_kernel<float>, gw, NT, smem, st, wa);
 }
 
 int attention_bwd(int precision, const void* att1, const void* enc, const float* g1, int64_t ldg,
                   int beta_col, const float* w_f, const float* alpha, int64_t alpha_stride,
                   const float* dalpha_ext, int64_t dalpha_stride, const float* dz, int64_t lddz,
-                  const float* awe, void* dba, int64_t lddba, float* dAtt1, float* dwf_part,
-                  float* dbf_part, int rows, int P, int E, int A, cudaStream_t st) {
+                  const float* awe, void* dba, int64_t lddba, float* de_out, float* dwf_part,
+                  float* dbf_part, int rows, int P, int E, int A, float* scratch, cudaStream_t st) {
   if (rows <= 0) return CAPDEC_OK;
   const int vec = precision == CAPDEC_BF16 ? 8 : 4;
   CAPDEC_REQUIRE(E % vec == 0 && A % vec == 0 && A <= 32 * vec * 4 && beta_col >= 0,
                  CAPDEC_ERR_BAD_SHAPE, "attention bwd: unsupported dims E=%d A=%d", E, A);
-  // the E slice of one CTA must fit the per-lane register cache: E/CL/vec <= 32*4
-  int min_cl = 1;
-  while (min_cl < CL_MAX && (E / min_cl) > 32 * 4 * vec) min_cl *= 2;
-  CAPDEC_REQUIRE((E / min_cl) <= 32 * 4 * vec && E % (min_cl * vec) == 0, CAPDEC_ERR_BAD_SHAPE,
-                 "attention bwd: E=%d too large / not divisible", E);
-  BwdArgs a{att1, enc, g1, ldg, beta_col, w_f, alpha, alpha_stride, dalpha_ext, dalpha_stride,
-            dz, lddz, awe, dba, lddba, dAtt1, dwf_part, dbf_part, rows, P, E, A};
-  const int CL = pick_cluster(rows, E, vec, min_cl);
-  const int nce = ceil_div(E / CL / vec, 32);
-  const size_t smem = bwd_smem(P, A);
+  CAPDEC_REQUIRE(scratch != nullptr, CAPDEC_ERR_BAD_ARG, "attention bwd: scratch is NULL");
+  const Chunking ch = pick_chunks(E, vec, rows);
+  BwdAArgs aa{enc, g1, ldg, beta_col, dz, lddz, awe, dba, lddba, scratch, P, E, ch.ncol, ch.cpl};
+  dim3 ga(ch.EC, rows, 1);
+  if (precision == CAPDEC_BF16) CAPDEC_TRY(launch_attn(attn_bwd_a_kernel<bf16>, ga, NT, 0, st, aa));
+  else CAPDEC_TRY(launch_attn(attn_bwd_a_kernel<float>, ga, NT, 0, st, aa));
+  BwdBArgs ba{att1, g1, ldg, w_f, alpha, alpha_stride, dalpha_ext, dalpha_stride, scratch, ch.EC,
+              dba, lddba, E, de_out, dwf_part, dbf_part, P, A};
+  const int Ppad = (P + 3) & ~3, Apad = (A + 3) & ~3;
+  const size_t smem = (size_t)(2 * Ppad + 32 + NWB * 2 * Apad) * sizeof(float);
   CAPDEC_REQUIRE(smem <= 160 * 1024, CAPDEC_ERR_BAD_SHAPE, "attention bwd: smem %zu too large", smem);
   const bool small = A <= 32 * vec * 2;
+  dim3 gb(rows, 1, 1);
   if (precision == CAPDEC_BF16) {
-    if (small) return launch_bwd<bf16, 2>(a, CL, nce, smem, st);
-    return launch_bwd<bf16, 4>(a, CL, nce, smem, st);
+    if (small) return launch_attn(attn_bwd_b_kernel<bf16, 2>, gb, NTB, smem, st, ba);
+    return launch_attn(attn_bwd_b_kernel<bf16, 4>, gb, NTB, smem, st, ba);
   }
-  if (small) return launch_bwd<float, 2>(a, CL, nce, smem, st);
-  return launch_bwd<float, 4>(a, CL, nce, smem, st);
+  if (small) return launch_attn(attn_bwd_b_kernel<float, 2>, gb, NTB, smem, st, ba);
+  return launch_attn(attn_bwd_b_kernel<float, 4>, gb, NTB, smem, st, ba);
+}
+
+int attention_datt1(int precision, const void* att1, const float* g1, int64_t ldg, int64_t g1_step,
+                    const float* de, int64_t de_step, const float* w_f, float* dAtt1, int accumulate,
+                    int B, int T, int P, int A, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return CAPDEC_OK;
+  CAPDEC_REQUIRE(A <= 4 * NT, CAPDEC_ERR_BAD_SHAPE, "attention dAtt1: A=%d too large", A);
+  Datt1Args a{att1, g1, ldg, g1_step, de, de_step, w_f, dAtt1, accumulate, T, P, A};
+  const size_t smem = (size_t)T * PT * sizeof(float);
+  dim3 grid(ceil_div(P, PT), B, 1);
+  const int na = ceil_div(A, NT);
+  if (precision == CAPDEC_BF16) {
+    if (na <= 1) attn_datt1_kernel<bf16, 1><<<grid, NT, smem, st>>>(a);
+    else if (na <= 2) attn_datt1_kernel<bf16, 2><<<grid, NT, smem, st>>>(a);
+    else attn_datt1_kernel<bf16, 4><<<grid, NT, smem, st>>>(a);
+  } else {
+    if (na <= 1) attn_datt1_kernel<float, 1><<<grid, NT, smem, st>>>(a);
+    else if (na <= 2) attn_datt1_kernel<float, 2><<<grid, NT, smem, st>>>(a);
+    else attn_datt1_kernel<float, 4><<<grid, NT, smem, st>>>(a);
+  }
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
 }
 
 }  // namespace capdec

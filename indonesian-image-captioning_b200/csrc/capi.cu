@@ -157,15 +157,19 @@ int capdec_gemm(int precision, const void* X, int64_t ldx, const void* W, int64_
   return gemm(precision, a, (cudaStream_t)stream);
 }
 
+size_t capdec_attention_scratch_floats(int precision, int rows, int P, int E) {
+  return attention_scratch_floats(precision, rows, P, E);
+}
+
 int capdec_attention_step(int precision, const void* att1, const void* enc, const float* g1,
                           int64_t ldg, int beta_col, const float* w_f, const float* b_f,
                           float* alpha_out, int64_t alpha_stride, void* z_out, float* awe_out, int rows,
-                          int rows_per_map, int P, int E, int A, void* stream) {
-  CAPDEC_REQUIRE(att1 && enc && g1 && w_f && b_f && rows_per_map >= 1, CAPDEC_ERR_BAD_ARG,
+                          int rows_per_map, int P, int E, int A, float* scratch, void* stream) {
+  CAPDEC_REQUIRE(att1 && enc && g1 && w_f && b_f && scratch && rows_per_map >= 1, CAPDEC_ERR_BAD_ARG,
                  "capdec_attention_step: bad argument");
   CAPDEC_TRY(capdec_init());
   return attention_fwd(precision, att1, enc, g1, ldg, beta_col, w_f, b_f, alpha_out, alpha_stride, z_out,
-                       E, awe_out, rows, rows_per_map, P, E, A, (cudaStream_t)stream);
+                       E, awe_out, rows, rows_per_map, P, E, A, scratch, (cudaStream_t)stream);
 }
 
 int capdec_attention_bwd_step(int precision, const void* att1, const void* enc, const float* g1,
@@ -173,13 +177,18 @@ int capdec_attention_bwd_step(int precision, const void* att1, const void* enc, 
                               int64_t alpha_stride, const float* dalpha_ext, int64_t dalpha_stride,
                               const float* dz, const float* awe, void* dba, int64_t lddba, float* dAtt1,
                               float* dwf_part, float* dbf_part, int rows, int P, int E, int A,
-                              void* stream) {
-  CAPDEC_REQUIRE(att1 && enc && g1 && w_f && alpha && dz && awe && dba && dAtt1 && dwf_part && dbf_part,
+                              float* scratch, void* stream) {
+  CAPDEC_REQUIRE(att1 && enc && g1 && w_f && alpha && dz && awe && dba && dAtt1 && dwf_part && dbf_part &&
+                     scratch,
                  CAPDEC_ERR_BAD_ARG, "capdec_attention_bwd_step: null argument");
   CAPDEC_TRY(capdec_init());
-  return attention_bwd(precision, att1, enc, g1, ldg, beta_col, w_f, alpha, alpha_stride, dalpha_ext,
-                       dalpha_stride, dz, E, awe, dba, lddba, dAtt1, dwf_part, dbf_part, rows, P, E, A,
-                       (cudaStream_t)stream);
+  // scratch = [partial dalpha | de (rows x pad4(P))]
+  float* de = scratch + attention_scratch_floats(precision, rows, P, E);
+  CAPDEC_TRY(attention_bwd(precision, att1, enc, g1, ldg, beta_col, w_f, alpha, alpha_stride, dalpha_ext,
+                           dalpha_stride, dz, E, awe, dba, lddba, de, dwf_part, dbf_part, rows, P, E, A,
+                           scratch, (cudaStream_t)stream));
+  return attention_datt1(precision, att1, g1, ldg, 0, de, 0, w_f, dAtt1, 1, rows, 1, P, A,
+                         (cudaStream_t)stream);
 }
 
 // ---- SCNCell.forward on fp32 master weights (unit entry; models/scn_cell.py:52-154) ----

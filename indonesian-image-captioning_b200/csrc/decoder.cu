@@ -46,9 +46,9 @@ struct Plan {
     size_t Wp_fcT, Wp_cT, Wp_hq, Wp_xin, Wp_b6, Wp_hx;
     // forward activations
     size_t enc_s, att1, mean, meanF, tagsF, v, q, Xe, U, g1, awe, z, m, pre, gates, C, H0, Hall,
-        Hd, lenD, seedD, capsD, counters;
+        Hd, lenD, seedD, capsD, counters, att_scr;
     // backward buffers
-    size_t dlogF, dHfc, dh_rec, dc, dpre, wr, du, dpx, dv_acc, dq_acc, dz, dba, dAtt1, dwf, dbf, dXe;
+    size_t dlogF, dHfc, dh_rec, dc, dpre, wr, du, dpx, de, dv_acc, dq_acc, dz, dba, dAtt1, dwf, dbf, dXe;
     size_t tA, tB, tC;             // transposed-operand scratch
     size_t total;
   } o;
@@ -141,6 +141,7 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
   o.lenD = take(B * 4);
   o.seedD = take(8);
   o.capsD = take((size_t)B * d.L * 8);
+  if (p->att) o.att_scr = take(attention_scratch_floats(d.precision, (int)B, (int)P, (int)E) * 4);
   o.counters = take((size_t)GEMM_TC_MAX_TILE_COUNTERS * 4);   // split-K tickets of the fused GEMM epilogues
   if (with_bwd) {
     o.dlogF = take(R * p->ldV * f);
@@ -159,6 +160,7 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
       o.dz = take(R * E * 4);
       o.dba = take(R * p->ldEA * f);
       o.dAtt1 = take(B * P * A * 4);
+      o.de = take(R * ((P + 3) / 4 * 4) * 4);          // softmax-input gradients of every step
       o.dwf = take(R * A * 4);
       o.dbf = take(R * 4);
     }
@@ -423,7 +425,8 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
       void* z = c.ft(o.z, (int64_t)t * B * E);
       float* awe = save_bwd ? c.at<float>(o.awe) + (int64_t)t * B * E : nullptr;
       CAPDEC_TRY(attention_fwd(pr, c.at(o.att1), c.at(o.enc_s), g1, NG1, A, w.full_att_w, w.full_att_b,
-                               alphas + (int64_t)t * P, (int64_t)T * P, z, E, awe, n, 1, P, E, A, st));
+                               alphas + (int64_t)t * P, (int64_t)T * P, z, E, awe, n, 1, P, E, A,
+                               c.at<float>(o.att_scr), st));
       // u (in place over U_emb[t]) += z . W_x[:, M:]^T   (+ fused u*v -> left half of m)
       GemmArgs a;
       a.X = z; a.ldx = E; a.W = c.ft(o.Wp_xq, M); a.ldw = p.ldX; a.out = U; a.ldo = NQ; a.addm = U;
@@ -531,7 +534,8 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dv_acc), 0, (size_t)B * NQ * 4, st));
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dq_acc), 0, (size_t)B * NQ * 4, st));
   }
-  if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dAtt1), 0, (size_t)B * P * A * 4, st));
+  const int Ppad = (P + 3) / 4 * 4;
+  if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.de), 0, (size_t)R * Ppad * 4, st));
   if (ragged) {
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dpre), 0, (size_t)R * 4 * D * p.fsz, st));
     if (p.scn) {
@@ -561,6 +565,7 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     const float* U = c.at<float>(o.U) + (int64_t)t * B * NQ;
     void* dpre = c.ft(o.dpre, (int64_t)t * B * 4 * D);
     float* dz = p.att ? c.at<float>(o.dz) + (int64_t)t * B * E : nullptr;
+    float* de_t = p.att ? c.at<float>(o.de) + (int64_t)t * B * Ppad : nullptr;
     if (fused) {
       void* du_t = c.ft(o.du, (int64_t)t * B * NQ);
       void* dpx_t = c.ft(o.dpx, (int64_t)t * B * p.ldPX);
@@ -586,8 +591,8 @@ int backward(const CapdecDims& d, const CapdecParams& w,
                                  d_alphas ? d_alphas + (int64_t)t * P : nullptr, (int64_t)T * P,
                                  dz, E, c.at<float>(o.awe) + (int64_t)t * B * E,
                                  c.ft(o.dpx, (int64_t)t * B * p.ldPX + NQ), p.ldPX,
-                                 c.at<float>(o.dAtt1), c.at<float>(o.dwf) + (int64_t)t * B * A,
-                                 c.at<float>(o.dbf) + (int64_t)t * B, n, P, E, A, st));
+                                 de_t, c.at<float>(o.dwf) + (int64_t)t * B * A,
+                                 c.at<float>(o.dbf) + (int64_t)t * B, n, P, E, A, c.at<float>(o.att_scr), st));
       }
       {
         // dh_{t-1} = [dp | dbeta_pre | datt2] [W_ha | W_beta^T | W_d^T]^T, and (t > 0) the LSTM
@@ -638,8 +643,8 @@ int backward(const CapdecDims& d, const CapdecParams& w,
                                  d_alphas ? d_alphas + (int64_t)t * P : nullptr, (int64_t)T * P,
                                  dz, E, c.at<float>(o.awe) + (int64_t)t * B * E,
                                  c.ft(o.dpx, (int64_t)t * B * p.ldPX + NQ), p.ldPX,
-                                 c.at<float>(o.dAtt1), c.at<float>(o.dwf) + (int64_t)t * B * A,
-                                 c.at<float>(o.dbf) + (int64_t)t * B, n, P, E, A, st));
+                                 de_t, c.at<float>(o.dwf) + (int64_t)t * B * A,
+                                 c.at<float>(o.dbf) + (int64_t)t * B, n, P, E, A, c.at<float>(o.att_scr), st));
       }
       // dh_{t-1} = [dp | dbeta_pre | datt2] . [W_ha | W_beta^T | W_d^T]^T
       CAPDEC_TRY(G_(c, dpx_t, p.ldPX, c.at(o.Wp_hx), p.ldPX, dh_rec, D, 0, nullptr, nullptr, 0, n, D,
@@ -655,8 +660,8 @@ int backward(const CapdecDims& d, const CapdecParams& w,
                                alphas + (int64_t)t * P, (int64_t)T * P,
                                d_alphas ? d_alphas + (int64_t)t * P : nullptr, (int64_t)T * P,
                                dz, E, c.at<float>(o.awe) + (int64_t)t * B * E, dba, p.ldEA,
-                               c.at<float>(o.dAtt1), c.at<float>(o.dwf) + (int64_t)t * B * A,
-                               c.at<float>(o.dbf) + (int64_t)t * B, n, P, E, A, st));
+                               de_t, c.at<float>(o.dwf) + (int64_t)t * B * A,
+                               c.at<float>(o.dbf) + (int64_t)t * B, n, P, E, A, c.at<float>(o.att_scr), st));
       // dh_{t-1} += [dbeta_pre | datt2] . [W_beta^T | W_d^T]^T
       CAPDEC_TRY(G_(c, dba, p.ldEA, c.at(o.Wp_b6), p.ldEA, dh_rec, D, 0, nullptr, dh_rec, D, n, D, E + A, B, 1,
                    0, 0, 0, SK));
@@ -736,6 +741,9 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     // full_att: per-row partials reduced over all (t,b)
     CAPDEC_TRY(colsum(pr, c.at(o.dwf), 0, A, Ri, A, g.full_att_w, 0, st));
     CAPDEC_TRY(colsum(pr, c.at(o.dbf), 0, 1, Ri, 1, g.full_att_b, 0, st));
+    // dAtt1[b,p,:] = w_f * sum_t de[t,b,p] 1[att1[b,p,:] + att2_t[b,:] > 0]  (masks rebuilt, not stored)
+    CAPDEC_TRY(attention_datt1(pr, c.at(o.att1), c.at<float>(o.g1), NG1, (int64_t)B * NG1, c.at<float>(o.de),
+                               (int64_t)B * Ppad, w.full_att_w, c.at<float>(o.dAtt1), 0, B, T, P, A, st));
     // encoder_att: dAtt1^T . enc  (K = B*P pixel rows)
     const int BP = B * P;
     CAPDEC_TRY(colsum(pr, c.at(o.dAtt1), 0, A, BP, A, g.enc_att_b, 0, st));
@@ -771,7 +779,7 @@ struct BeamPlan {
   int R;
   struct Off {
     size_t enc_f, att1, mean, meanF, meanX, tagsG, tagsX, v, q, H, C, Hn, Cn, Xe, U, g1, z, m, pre,
-        logits, alpha_hist, prev_word, scoreA, scoreB, src_row, live, krem, has_done, best_score,
+        logits, alpha_hist, att_scr, prev_word, scoreA, scoreB, src_row, live, krem, has_done, best_score,
         best_t, best_parent, bp_parent, bp_word, total;
   } o;
 };
@@ -815,6 +823,7 @@ int make_beam_plan(const CapdecDims& d_in, int G, int k, int n_steps, bool want_
     o.pre = take((size_t)R * 4 * D * 4);
   }
   o.logits = take((size_t)R * V * 4);
+  if (p.att) o.att_scr = take(attention_scratch_floats(d.precision, (int)R, (int)P, (int)E) * 4);
   if (p.att) o.alpha_hist = take((size_t)(want_alpha ? n_steps : 1) * R * P * 4);
   o.prev_word = take((size_t)R * 4);
   o.scoreA = take((size_t)R * 4);
@@ -916,7 +925,7 @@ int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, co
     if (p.att) {
       float* alpha_t = c.at<float>(o.alpha_hist) + (want_alpha ? (int64_t)t * R * P : 0);
       CAPDEC_TRY(attention_fwd(pr, c.at(o.att1), c.at(o.enc_f), g1, NG1, A, w.full_att_w, w.full_att_b,
-                               alpha_t, P, c.at(o.z), E, nullptr, R, k, P, E, A, st));
+                               alpha_t, P, c.at(o.z), E, nullptr, R, k, P, E, A, c.at<float>(o.att_scr), st));
       CAPDEC_TRY(G_(c, c.at(o.z), E, c.ft(p.o.Wp_xq, M), p.ldX, U, NQ, 0, nullptr, U, NQ, R, NQ, E));
     }
     if (p.scn) {

@@ -6,15 +6,23 @@ namespace capdec {
 
 // ---- attention.cu ----
 int attention_init();
+// scratch floats both directions need for `rows` rows (forward: scores; backward: partial dalpha)
+size_t attention_scratch_floats(int precision, int rows, int P, int E);
 int attention_fwd(int precision, const void* att1, const void* enc, const float* g1, int64_t ldg,
                   int beta_col, const float* w_f, const float* b_f, float* alpha_out,
                   int64_t alpha_stride, void* z_out, int64_t ldz, float* awe_out, int rows,
-                  int rows_per_map, int P, int E, int A, cudaStream_t st);
+                  int rows_per_map, int P, int E, int A, float* scratch, cudaStream_t st);
+// de_out (rows, pad4(P)) receives the softmax-input gradient of every pixel (consumed by attention_datt1)
 int attention_bwd(int precision, const void* att1, const void* enc, const float* g1, int64_t ldg,
                   int beta_col, const float* w_f, const float* alpha, int64_t alpha_stride,
                   const float* dalpha_ext, int64_t dalpha_stride, const float* dz, int64_t lddz,
-                  const float* awe, void* dba, int64_t lddba, float* dAtt1, float* dwf_part,
-                  float* dbf_part, int rows, int P, int E, int A, cudaStream_t st);
+                  const float* awe, void* dba, int64_t lddba, float* de_out, float* dwf_part,
+                  float* dbf_part, int rows, int P, int E, int A, float* scratch, cudaStream_t st);
+// dAtt1[b,p,a] (+)= w_f[a] sum_t de[t,b,p] 1[att1[b,p,a] + att2[t,b,a] > 0] ; att2[t][b] = g1 + t*g1_step + b*ldg,
+// de[t][b] = de + t*de_step + b*pad4(P)
+int attention_datt1(int precision, const void* att1, const float* g1, int64_t ldg, int64_t g1_step,
+                    const float* de, int64_t de_step, const float* w_f, float* dAtt1, int accumulate,
+                    int B, int T, int P, int A, cudaStream_t st);
 
 // ---- pointwise.cu ----
 // dst[c*ldd + i*d_i + j*d_j] = src[i*s_i + j*s_j + c]   for i<ni, j<nj, c<C   (transpose + cast)
