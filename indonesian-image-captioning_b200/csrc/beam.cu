@@ -76,7 +76,8 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
   return a;
 }
 
-// one CTA per image
+// one CTA per image; KL = length of the per-thread candidate lists (>= beam size)
+template <int KL>
 __global__ void __launch_bounds__(NT)
 beam_select_kernel(const float* __restrict__ logits, int V, int k, int t, int32_t end_id,
                    const float* __restrict__ score_in, float* __restrict__ score_out,
@@ -132,18 +133,32 @@ beam_select_kernel(const float* __restrict__ logits, int V, int k, int t, int32_
     __syncthreads();
   }
 
-  // top-kr of score_j + log_softmax(row j)[v] over the ns*V candidates, descending
-  const int total = ns * V;
-  for (int r = 0; r < kr; ++r) {
-    ArgMax best{-INFINITY, 0x7fffffff};
-    for (int i = tid; i < total; i += NT) {
-      bool taken = false;
-      for (int q = 0; q < r; ++q) taken |= (s_sel[q] == i);
-      if (taken) continue;
-      const int j = i / V, v = i - j * V;
-      const float val = s_score[j] + ((base[(int64_t)j * V + v] - s_max[j]) - s_logsum[j]);
-      best = better(best, ArgMax{val, i});
+  // top-kr of score_j + log_softmax(row j)[v] over the ns*V candidates, descending (value, then
+  // smaller flat index: a strict total order, so the result does not depend on the schedule).
+  // ONE pass over the logits: every thread keeps the kr best of its own candidates in registers
+  // (sorted), then kr block-wide arg-max rounds pop the winners off the thread-local lists.
+  // (the lists hold KL >= kr entries: a superset of what is needed, with static register indexing)
+  ArgMax mine[KL];
+#pragma unroll
+  for (int q = 0; q < KL; ++q) mine[q] = ArgMax{-INFINITY, 0x7fffffff};
+  for (int j = 0; j < ns; ++j) {
+    const float* x = base + (int64_t)j * V;
+    const float sj = s_score[j], mj = s_max[j], lj = s_logsum[j];
+    for (int v = tid; v < V; v += NT) {
+      const ArgMax cand{sj + ((x[v] - mj) - lj), j * V + v};
+      const ArgMax last = mine[KL - 1];
+      if (cand.v > last.v || (cand.v == last.v && cand.idx < last.idx)) {
+        mine[KL - 1] = cand;
+#pragma unroll
+        for (int q = KL - 1; q > 0; --q) {
+          const ArgMax lo = mine[q], hi = mine[q - 1];
+          if (lo.v > hi.v || (lo.v == hi.v && lo.idx < hi.idx)) { mine[q] = hi; mine[q - 1] = lo; }
+        }
+      }
     }
+  }
+  for (int r = 0; r < kr; ++r) {
+    ArgMax best = mine[0];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       ArgMax other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.idx, o)};
@@ -151,11 +166,17 @@ beam_select_kernel(const float* __restrict__ logits, int V, int k, int t, int32_
     }
     if (lane == 0) { red_v[warp] = best.v; red_i[warp] = best.idx; }
     __syncthreads();
+    ArgMax b{red_v[0], red_i[0]};
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) b = better(b, ArgMax{red_v[w], red_i[w]});
     if (tid == 0) {
-      ArgMax b{red_v[0], red_i[0]};
-      for (int w = 1; w < NT / 32; ++w) b = better(b, ArgMax{red_v[w], red_i[w]});
       s_sel[r] = b.idx;
       s_selv[r] = b.v;
+    }
+    if (mine[0].idx == b.idx) {      // the owner pops its head (flat indices are unique)
+#pragma unroll
+      for (int q = 0; q + 1 < KL; ++q) mine[q] = mine[q + 1];
+      mine[KL - 1] = ArgMax{-INFINITY, 0x7fffffff};
     }
     __syncthreads();
   }
@@ -303,9 +324,14 @@ int beam_select(const float* logits, int V, int G, int k, int t, int32_t end_id,
                 int32_t* bp_parent, int32_t* bp_word, int32_t* tr_parent, int32_t* tr_word,
                 float* tr_score, int n_steps, cudaStream_t st) {
   CAPDEC_REQUIRE(k >= 1 && k <= KMAX, CAPDEC_ERR_BAD_SHAPE, "beam size must be 1..%d (got %d)", KMAX, k);
-  beam_select_kernel<<<G, NT, 0, st>>>(logits, V, k, t, end_id, score_in, score_out, prev_word, src_row,
-                                       live, krem, has_done, best_score, best_t, best_parent, bp_parent,
-                                       bp_word, tr_parent, tr_word, tr_score, n_steps, G);
+  if (k <= 4)
+    beam_select_kernel<4><<<G, NT, 0, st>>>(logits, V, k, t, end_id, score_in, score_out, prev_word, src_row,
+                                            live, krem, has_done, best_score, best_t, best_parent, bp_parent,
+                                            bp_word, tr_parent, tr_word, tr_score, n_steps, G);
+  else
+    beam_select_kernel<KMAX><<<G, NT, 0, st>>>(logits, V, k, t, end_id, score_in, score_out, prev_word, src_row,
+                                               live, krem, has_done, best_score, best_t, best_parent, bp_parent,
+                                               bp_word, tr_parent, tr_word, tr_score, n_steps, G);
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }

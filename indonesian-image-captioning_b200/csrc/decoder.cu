@@ -46,7 +46,7 @@ struct Plan {
     size_t Wp_fcT, Wp_cT, Wp_hq, Wp_xin, Wp_b6, Wp_hx;
     // forward activations
     size_t enc_s, att1, mean, meanF, tagsF, v, q, Xe, U, g1, awe, z, m, pre, gates, C, H0, Hall,
-        Hd, lenD, seedD, capsD, counters, att_scr;
+        Hd, lenD, seedD, capsD, counters, att_scr, bar, Ht, zk, enc_cm;
     // backward buffers
     size_t dlogF, dHfc, dh_rec, dc, dpre, wr, du, dpx, de, dv_acc, dq_acc, dz, dba, dAtt1, dwf, dbf, dXe;
     size_t tA, tB, tC;             // transposed-operand scratch
@@ -143,6 +143,14 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
   o.capsD = take((size_t)B * d.L * 8);
   if (p->att) o.att_scr = take(attention_scratch_floats(d.precision, (int)B, (int)P, (int)E) * 4);
   o.counters = take((size_t)GEMM_TC_MAX_TILE_COUNTERS * 4);   // split-K tickets of the fused GEMM epilogues
+  o.bar = take(256);                                          // grid-barrier counter of the persistent kernels
+  if (d.precision == CAPDEC_BF16 && p->scn) {                 // operand copies of the persistent kernel (recur.cu)
+    o.Ht = take(R * D * f);
+    if (p->att) {
+      o.zk = take(R * E * f);
+      o.enc_cm = take(B * P * E * f);
+    }
+  }
   if (with_bwd) {
     o.dlogF = take(R * p->ldV * f);
     o.dHfc = take(R * D * 4);
@@ -385,18 +393,43 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
                   NQ, M));
   }
   if (alphas) CAPDEC_CUDA_OK(cudaMemsetAsync(alphas, 0, (size_t)R * P * 4, st));
+  const bool drop = dropout_p > 0.f;
+  // ---------------- the recurrence as ONE persistent cooperative kernel (recur.cu) ----------------
+  bool persistent = false;
+  RecurFwdArgs ra;
+  if (pr == CAPDEC_BF16 && p.scn && !fused && (!p.att || alphas)) {
+    ra.att = p.att ? 1 : 0;
+    ra.B = B; ra.T = T; ra.P = P; ra.E = E; ra.A = A; ra.M = M; ra.D = D; ra.F = F;
+    ra.len = c.at<int32_t>(o.lenD);
+    ra.Wcat1 = c.at(o.Wp_cat1); ra.ldD = p.ldD;
+    ra.Wxz = c.ft(o.Wp_xq, M); ra.ldX = p.ldX;
+    ra.Wc = c.at(o.Wp_c); ra.ld2F = p.ld2F;
+    ra.b_cat1 = c.at<float>(o.b_cat1); ra.b_ih = w.b_ih; ra.b_hh = w.b_hh;
+    if (p.att) {
+      ra.att1 = c.at(o.att1); ra.enc = c.at(o.enc_s); ra.w_f = w.full_att_w; ra.b_f = w.full_att_b;
+      ra.alphas = alphas; ra.awe = save_bwd ? c.at<float>(o.awe) : nullptr; ra.z = c.at(o.z);
+      ra.scores = c.at<float>(o.att_scr);
+    }
+    ra.v = c.at<float>(o.v); ra.q = c.at<float>(o.q);
+    ra.Ht = c.at(o.Ht); ra.zk = p.att ? c.at(o.zk) : nullptr; ra.enc_cm = p.att ? c.at(o.enc_cm) : nullptr;
+    ra.H0 = c.at(o.H0); ra.ldH0 = p.ldD; ra.Hall = c.at(o.Hall); ra.Hd = drop ? c.at(o.Hd) : nullptr;
+    ra.C = c.at<float>(o.C); ra.U = c.at<float>(o.U); ra.g1 = c.at<float>(o.g1); ra.m = c.at(o.m);
+    ra.pre = c.at<float>(o.pre); ra.gates = c.at<float>(o.gates); ra.bar = c.at<unsigned>(o.bar);
+    ra.dropout_p = dropout_p; ra.seed = c.at<uint64_t>(o.seedD);
+    persistent = recur_fwd_supported(ra);
+  }
+  if (persistent) CAPDEC_TRY(recur_fwd(ra, st));
   // split-K GEMMs of the tcgen05 engine accumulate with atomics into pre-zeroed buffers
   const int SK = pr == CAPDEC_BF16 ? -1 : 0;
   int* counters = c.at<int>(o.counters);
-  if (SK) {
+  if (SK && !persistent) {
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.g1), 0, (size_t)R * NG1 * 4, st));
     if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.pre), 0, (size_t)R * 4 * D * 4, st));
     CAPDEC_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)GEMM_TC_MAX_TILE_COUNTERS * 4, st));
   }
 
-  const bool drop = dropout_p > 0.f;
-  // ---------------- the recurrence ----------------
-  for (int t = 0; t < T; ++t) {
+  // ---------------- the recurrence, one kernel chain per step ----------------
+  for (int t = 0; t < (persistent ? 0 : T); ++t) {
     const int n = bt[t];
     const void* hprev = t == 0 ? c.at(o.H0) : c.ft(o.Hall, (int64_t)(t - 1) * D);
     const int64_t ldh = t == 0 ? p.ldD : (int64_t)T * D;

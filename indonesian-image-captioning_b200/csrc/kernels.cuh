@@ -74,6 +74,30 @@ int zero_rows_beyond_len(float* x, const int32_t* len_d, int B, int T, int64_t r
 int expand_rows(int precision, const void* src, int64_t lds, void* dst, int64_t ldd, int G, int k, int C,
                 cudaStream_t st);
 
+// ---- recur.cu: persistent (one cooperative launch for all T steps) SCN decoder recurrence, bf16 ----
+struct RecurFwdArgs {
+  int att = 0;                       // 1: attention_scn, 0: pure_scn
+  int B = 0, T = 0, P = 0, E = 0, A = 0, M = 0, D = 0, F = 0;
+  const int32_t* len = nullptr;      // device [B]
+  const void* Wcat1 = nullptr; int64_t ldD = 0;
+  const void* Wxz = nullptr; int64_t ldX = 0;      // W_ia[M:, :]^T, i.e. Wp_xq + M
+  const void* Wc = nullptr; int64_t ld2F = 0;
+  const float* b_cat1 = nullptr; const float* b_ih = nullptr; const float* b_hh = nullptr;
+  const void* att1 = nullptr; const void* enc = nullptr; const float* w_f = nullptr; const float* b_f = nullptr;
+  const float* v = nullptr; const float* q = nullptr;
+  const void* H0 = nullptr; int64_t ldH0 = 0;
+  void* Hall = nullptr; void* Hd = nullptr;
+  void* Ht = nullptr;                // [T][B][D] time-major copy of h (G1 operand of the next step)
+  void* zk = nullptr;                // [T][E/512][B][512] chunk-major copy of z (P3 operand)
+  void* enc_cm = nullptr;            // [B][E/512][P][512] chunk-major copy of enc (built by recur_fwd)
+  float* C = nullptr; float* U = nullptr; float* g1 = nullptr; float* alphas = nullptr; float* awe = nullptr;
+  void* z = nullptr; void* m = nullptr; float* pre = nullptr; float* gates = nullptr; float* scores = nullptr;
+  unsigned* bar = nullptr;           // 4-byte grid-barrier counter (zeroed by recur_fwd)
+  float dropout_p = 0.f; const uint64_t* seed = nullptr;
+};
+bool recur_fwd_supported(const RecurFwdArgs& a);     // shape / device / CAPDEC_PERSISTENT check
+int recur_fwd(const RecurFwdArgs& a, cudaStream_t st);
+
 // ---- beam.cu ----
 int beam_init(int32_t* prev_word, float* score, int32_t* live, int32_t* krem, int32_t* has_done,
               float* best_score, int32_t* best_t, int32_t* best_parent, int G, int k, int32_t start_id,

@@ -1,0 +1,718 @@
+// recur.cu -- the persistent decoder kernel: the whole teacher-forced time loop of the
+// SCN-LSTM / attention decoders in ONE cooperative launch (bf16 feature mode).
+//
+// Reference math: models/decoders/attention_scn.py:139-156 (the `for t` loop),
+// models/scn_cell.py:52-154, models/attention.py:26-44; restated in SURVEY.md App. A.1.
+//
+// Why: at 32 captions per GPU a decode step is ~18 MFLOP per row and 1 MB of features per
+// row -- every stage finishes in 1-3 us, so a chain of 7 dependent kernel launches per step
+// (>= 3 us each even with programmatic dependent launch inside a CUDA graph) is pure latency.
+// Here one CTA per SM stays resident for all T steps:
+//   * the recurrent and factor weights (W_d | W_beta | W_ha, W_ia[M:], W_ic | W_hc; 17.3 MB in
+//     bf16 at the 512-dim config) are sliced BY OUTPUT FEATURE over the CTAs and loaded into shared
+//     memory ONCE; each CTA owns 16-32 output features of every GEMM with the full K, so no
+//     split-K, no atomics, no zero-filled accumulators, bit-reproducible sums;
+//   * a GEMM phase = every warp takes 1/8 of K, loads the 32 x K/8 activation slice straight
+//     from L2 into mma fragments (16-byte loads, K permuted identically for both operands),
+//     mma.sync m16n8k16 bf16 -> fp32, 8-way reduction through shared memory, fused epilogue
+//     (bias, factor products u*v / p*q written as the next GEMM's operand);
+//   * attention = the same two stages as attention.cu (scores per pixel, softmax + weighted
+//     sum + gate per 512-channel chunk), features streamed from L2 with 16-byte loads;
+//   * phases are separated by a grid barrier (one release-add + acquire-spin per CTA, ~1 us)
+//     instead of a kernel boundary.  6 barriers per step for attention_scn.
+// tcgen05 is not used here on purpose: its 128-lane M granularity would force 8-way split-K
+// with atomics (and a seventh phase to consume the sums) for GEMMs whose whole tensor work is
+// 0.3 us per step; the batched GEMMs outside the loop (vocabulary, att1, embedding side,
+// weight gradients) stay on the tcgen05 engine (gemm_tc.cu).
+#include <stdlib.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace capdec {
+
+namespace {
+
+constexpr int RT = 512;             // threads per CTA
+constexpr int RW = RT / 32;         // 16 warps: warp w of a GEMM phase = (m-tile w & 1, K slice w >> 1)
+constexpr int KSL = RW / 2;         // K slices of a GEMM phase
+constexpr int KC = 512;             // K elements per staged activation chunk (1 KB per row)
+constexpr int WPAD = 64;            // bytes of padding per resident weight row (bank spread)
+constexpr int STAGE = 32 * KC * 2;  // one staging buffer: 32 rows of KC bf16 = 32 KB; two of them
+constexpr int REDLD = 16 + 8;       // floats per row of the cross-warp reduction scratch (2 n-tiles)
+constexpr int CHUNK = KC;           // channels per weighted-sum work item (1 KB per pixel)
+constexpr int NCOL = CHUNK / 8;     // 16-byte columns per chunk
+constexpr int GROUPS = RT / NCOL;   // pixel groups of the weighted sum (8)
+constexpr int WPXS = STAGE / (CHUNK * 2);   // pixels per weighted-sum stage (32)
+constexpr int SCI = 2 * STAGE / 1024;       // score items (<= 1 KB each) the two stages hold (64)
+
+__host__ __device__ __forceinline__ int pad4i(int x) { return (x + 3) & ~3; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA bulk copy global -> shared memory (one contiguous run), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// global data written by other CTAs with ordinary stores is about to be read through the async proxy
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                         uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// MUFU-based transcendentals (abs. error ~1e-6; the results are rounded to bf16 operands anyway)
+__device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) { return 2.0f * fsigmoid(2.0f * x) - 1.0f; }
+
+// grid-wide barrier of a cooperative launch: monotonically increasing arrival counter.  Split in
+// arrive / wait so that loads which do not depend on the other CTAs are issued in between.
+__device__ __forceinline__ void grid_arrive(unsigned* ctr) {
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+}
+__device__ __forceinline__ void grid_wait(unsigned* ctr, unsigned& target) {
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+    fence_proxy_async();
+  }
+  __syncthreads();
+}
+
+struct FwdP {
+  int B, T, P, E, A, M, D, F, NQ, NG1;
+  int64_t R;                     // B*T
+  const int32_t* len;            // [B] decode lengths, sorted descending
+  // packed bf16 weights, K contiguous
+  const bf16* Wcat1; int64_t ldD;   // [NG1][ldD]   [W_d ; W_beta ; W_ha^T]
+  const bf16* Wxz; int64_t ldX;     // [NQ][ldX]    W_ia[M:, :]^T (already offset by M)
+  const bf16* Wc; int64_t ld2F;     // [4][D][ld2F] [W_ic_g | W_hc_g]
+  const float* b_cat1; const float* b_ih; const float* b_hh;
+  const bf16* att1;                 // [B][P][A]
+  const bf16* enc_cm;               // [B][E/512][P][512]   chunk-major copy of the features
+  const float* w_f; const float* b_f;
+  const float* v; const float* q;   // [B][NQ]
+  const bf16* H0;                   // [B][D]
+  bf16* Hall; bf16* Hd;             // (B, T, D)
+  bf16* Ht;                         // [T][B][D]   time-major copy of h_t: the next step's G1 operand
+  float* C;                         // [T+1][B][D]
+  float* U;                         // [T][B][NQ]   in: Emb W_ia[:M] ; out: u
+  float* g1;                        // [T][B][NG1]  att2 | beta_pre | p
+  float* alphas;                    // (B, T, P)
+  float* awe;                       // [T][B][E] or null
+  bf16* z;                          // [T][B][E]
+  bf16* zk;                         // [T][E/512][B][512]   chunk-major copy of z: the P3 operand
+  bf16* m;                          // [4][R][2F]
+  float* pre;                       // [T][B][4D]
+  float* gates;                     // [T][B][4D]
+  float* scores;                    // [B][pad4(P)]
+  unsigned* bar;
+  float dropout_p; const uint64_t* seed;
+  long long* prof;                  // debug (CAPDEC_RECUR_PROF=1): [T][16] clock64 stamps of CTA 0
+  int mask;                         // debug: bit i set -> phase i runs (G1, scores, wsum, P3, P4, cell)
+};
+
+// Shared-memory pipeline state: two 32 KB staging buffers (adjacent), each with a "full" mbarrier;
+// use[s] counts completed fills of stage s (parity of the next wait).
+struct Pipe {
+  uint8_t* stg;        // generic pointer to stage 0; stage 1 = stg + STAGE
+  uint32_t stg_a;      // shared-memory address of stage 0
+  uint32_t full[2];    // mbarrier addresses
+  uint32_t use[2];
+};
+
+// thread 0 copies `bytes` contiguous bytes into stage s
+__device__ __forceinline__ void stage_fill(const Pipe& pp, int s, const void* src, uint32_t bytes) {
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(pp.full[s], bytes);
+    bulk_g2s(pp.stg_a + s * STAGE, src, bytes, pp.full[s]);
+  }
+}
+
+// One GEMM job of this CTA: NH * 16 output features with the full K:
+//   out[h] = sum_k A[row, k] * W[h*16 + j, k]       (row = tid / 16, j = tid % 16)
+// A arrives in `nfill` fills of n rows x KF (= 64 * BPW) bf16, each fill ONE contiguous TMA bulk copy
+// (the producers write chunk-major copies for exactly this reason), double buffered;
+// W: shared memory, rows of `wstride` bytes, resident for the whole kernel.
+// Warp (mt, ks) multiplies rows [16 mt, 16 mt + 16) with BPW 32-wide k blocks of every fill; each lane
+// fetches 16 bytes (8 consecutive k) per row and block with ONE LDS.128 and feeds them to two
+// m16n8k16 mma -- the same k permutation is used for the weight fragments, so no ldmatrix /
+// transposition is needed.  The 8 K-slice partials meet in shared memory.
+template <int NH, int BPW>
+__device__ __forceinline__ void gemm_job(Pipe& pp, const bf16* __restrict__ src, int64_t fill_stride, int n,
+                                         const uint8_t* Ws, int wstride, int nfill, float* red,
+                                         float (&out)[NH]) {
+  constexpr int KF = 64 * BPW * 4;           // K elements per fill: 8 slices x BPW blocks x 32
+  constexpr int SPF = KF * 2 * 32 / STAGE;   // stages one fill occupies (1 or 2)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int mt = warp & 1, ks = warp >> 1;
+  const uint32_t fill_bytes = (uint32_t)n * KF * 2;
+  stage_fill(pp, 0, src, fill_bytes);
+  if (SPF == 1 && nfill > 1) stage_fill(pp, 1, src + fill_stride, fill_bytes);
+  float acc[2 * NH][4];
+#pragma unroll
+  for (int nt = 0; nt < 2 * NH; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+  const uint8_t* a_base = pp.stg + (size_t)(mt * 16 + g) * (KF * 2) + ks * (BPW * 64) + 16 * c;
+  const uint8_t* w_base = Ws + (size_t)g * wstride + ks * (BPW * 64) + 16 * c;
+#pragma unroll 1
+  for (int kf = 0; kf < nfill; ++kf) {
+    const int s = SPF == 1 ? (kf & 1) : 0;
+    mbar_wait(pp.full[s], pp.use[s] & 1);
+    pp.use[s]++;
+    const uint8_t* ap = a_base + s * STAGE;
+    const uint8_t* wp = w_base + (size_t)kf * KF * 2;
+#pragma unroll
+    for (int j = 0; j < BPW; ++j) {
+      const uint4 alo = *reinterpret_cast<const uint4*>(ap + j * 64);
+      const uint4 ahi = *reinterpret_cast<const uint4*>(ap + 8 * (KF * 2) + j * 64);
+#pragma unroll
+      for (int nt = 0; nt < 2 * NH; ++nt) {
+        const uint4 b = *reinterpret_cast<const uint4*>(wp + (size_t)nt * 8 * wstride + j * 64);
+        mma_bf16(acc[nt], alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
+        mma_bf16(acc[nt], alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
+      }
+    }
+    if (kf + 2 < nfill) {
+      __syncthreads();                       // every warp is done with stage s
+      stage_fill(pp, s, src + (int64_t)(kf + 2) * fill_stride, fill_bytes);
+    }
+  }
+  const int row = threadIdx.x >> 4, j = threadIdx.x & 15;
+  float* mine = red + (ks * 32 + mt * 16 + g) * REDLD + 2 * c;
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    if (h > 0) __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      *reinterpret_cast<float2*>(mine + q * 8) = make_float2(acc[2 * h + q][0], acc[2 * h + q][1]);
+      *reinterpret_cast<float2*>(mine + 8 * REDLD + q * 8) = make_float2(acc[2 * h + q][2], acc[2 * h + q][3]);
+    }
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < KSL; ++w) sum += red[(w * 32 + row) * REDLD + j];
+    out[h] = sum;
+  }
+  __syncthreads();                           // staging buffers and `red` are free again
+}
+
+// copy `nrows` weight rows (K bf16 each, global pitch ldw elements) into shared memory rows of
+// K*2 + WPAD bytes; rows at or beyond `valid` are zero-filled
+__device__ __noinline__ void load_weight_rows(uint8_t* Ws, const bf16* Wg, int64_t ldw, int K, int nrows,
+                                              int valid) {
+  const int vec_per_row = K / 8;
+  const int wstride = K * 2 + WPAD;
+  for (int i = threadIdx.x; i < nrows * vec_per_row; i += RT) {
+    const int r = i / vec_per_row, cidx = i - r * vec_per_row;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (r < valid) val = __ldg(reinterpret_cast<const uint4*>(Wg + (int64_t)r * ldw) + cidx);
+    *reinterpret_cast<uint4*>(Ws + (size_t)r * wstride + (size_t)cidx * 16) = val;
+  }
+}
+
+template <bool ATT, int NT1>
+__global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant__ FwdP p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int NT3 = 2, NT4 = 2;
+  const int D = p.D, E = p.E, F = p.F, B = p.B, T = p.T, P = p.P, NQ = p.NQ, NG1 = p.NG1, A = p.A;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // shared memory carve-up: stages | W1 | W3 | W4 | red | al | lens | mbarriers
+  const int w1s = D * 2 + WPAD, w3s = E * 2 + WPAD, w4s = 2 * F * 2 + WPAD;
+  uint8_t* stg = smem;
+  uint8_t* W1s = stg + 2 * STAGE;
+  uint8_t* W3s = W1s + (size_t)NT1 * 8 * w1s;
+  uint8_t* W4s = W3s + (ATT ? (size_t)NT3 * 8 * w3s : 0);
+  float* red = reinterpret_cast<float*>(W4s + (size_t)NT4 * 8 * w4s);
+  float* al = red + KSL * 32 * REDLD;
+  int* lens = reinterpret_cast<int*>(al + pad4i(P > 0 ? P : 4));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lens + ((B + 3) & ~3) + 2);
+  bars = reinterpret_cast<uint64_t*>(((uintptr_t)bars + 7) & ~(uintptr_t)7);
+  Pipe pp;
+  pp.stg = stg; pp.stg_a = smem_u32(stg);
+  pp.full[0] = smem_u32(&bars[0]); pp.full[1] = smem_u32(&bars[1]);
+  pp.use[0] = pp.use[1] = 0;
+  if (tid == 0) {
+    mbar_init(pp.full[0], 1);
+    mbar_init(pp.full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  // ---- which output features this CTA owns ----
+  const int f1 = blockIdx.x * NT1 * 8;                 // first G1 feature
+  const int f3 = blockIdx.x * NT3 * 8;                 // first P3 feature (u)
+  const int tpg = D / 8;
+  const int t4 = blockIdx.x * NT4;                     // first P4 tile; tiles never straddle a gate
+  const int gate4 = t4 / tpg, d4 = (t4 - gate4 * tpg) * 8;
+  const bool has1 = f1 < NG1, has3 = ATT && f3 < NQ, has4 = t4 < 4 * tpg;
+  // ---- one-time: weight slices -> shared memory ----
+  if (has1) load_weight_rows(W1s, p.Wcat1 + (int64_t)f1 * p.ldD, p.ldD, D, NT1 * 8, NG1 - f1);
+  if (has3) load_weight_rows(W3s, p.Wxz + (int64_t)f3 * p.ldX, p.ldX, E, NT3 * 8, NQ - f3);
+  if (has4) load_weight_rows(W4s, p.Wc + ((int64_t)gate4 * D + d4) * p.ld2F, p.ld2F, 2 * F, NT4 * 8, D - d4);
+  for (int i = tid; i < B; i += RT) lens[i] = p.len[i];
+  __syncthreads();
+
+  const int erow = tid >> 4, ej = tid & 15;            // epilogue mapping of gemm_job
+  const int col0 = ATT ? A + E : 0;
+  const int Ppad = pad4i(P);
+  const int chunks = ATT ? E / CHUNK : 1;
+  const int grp = tid / NCOL, col = tid - grp * NCOL;  // weighted-sum mapping
+  const float drop_p = p.dropout_p;
+  const uint64_t seed = drop_p > 0.f ? __ldg(p.seed) : 0ull;
+  const int a_lane = lane * 8;                         // scores: this lane's 8 attention channels (x2)
+
+  unsigned target = 0;
+  int stamp = 0;
+#define RECUR_STAMP()                                                                      \
+  do {                                                                                     \
+    if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[t * 16 + (stamp++ & 15)] = clock64(); \
+  } while (0)
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    stamp = 0;
+    RECUR_STAMP();
+    const int n = __popc(__ballot_sync(0xffffffffu, lane < B && lens[lane] > t));   // B <= 32, lengths sorted
+    const int64_t tb = (int64_t)t * B;
+    // ================= G1: [att2 | beta_pre | p] = h_{t-1} W_cat1^T + b, and p*q -> m =================
+    if (has1 && (p.mask & 1)) {
+      const bf16* hprev = t == 0 ? p.H0 : p.Ht + (tb - B) * D;
+      float out[NT1 / 2];
+      gemm_job<NT1 / 2, 2>(pp, hprev, 0, n, W1s, w1s, 1, red, out);
+      if (erow < n) {
+        float* g1 = p.g1 + (tb + erow) * NG1;
+#pragma unroll
+        for (int i = 0; i < NT1 / 2; ++i) {
+          const int nf = f1 + i * 16 + ej;
+          if (nf < NG1) {
+            const float val = out[i] + __ldg(p.b_cat1 + nf);
+            g1[nf] = val;
+            if (nf >= col0) {
+              const int nn = nf - col0;
+              const int gg = nn / F, f = nn - gg * F;
+              p.m[((int64_t)gg * p.R + tb + erow) * 2 * F + F + f] =
+                  __float2bfloat16_rn(val * __ldg(p.q + (int64_t)erow * NQ + nn));
+            }
+          }
+        }
+      }
+    }
+    if (!ATT) {
+      // pure_scn: the input half u*v of the P4 operand (u = Emb W_ia is not recurrent)
+      const int total = n * NQ;
+#pragma unroll 1
+      for (int i = blockIdx.x * RT + tid; i < total; i += gridDim.x * RT) {
+        const int b = i / NQ, nf = i - b * NQ;
+        const int gg = nf / F, f = nf - gg * F;
+        const float u = __ldg(p.U + (tb + b) * NQ + nf);
+        p.m[((int64_t)gg * p.R + tb + b) * 2 * F + f] = __float2bfloat16_rn(u * __ldg(p.v + (int64_t)b * NQ + nf));
+      }
+    }
+    RECUR_STAMP();
+    if (ATT) {
+      // ================= scores e[b, px] = w_f . relu(att1[b, px, :] + att2[b, :]) + b_f =================
+      // this CTA's contiguous share of the (b, px) items = consecutive att1 rows: ONE bulk copy, issued
+      // while the grid barrier is crossed -- att1 does not depend on this step
+      const int items = n * P;
+      const int per = (items + gridDim.x - 1) / gridDim.x;
+      const int i0 = blockIdx.x * per, i1 = min(items, i0 + per);
+      grid_arrive(p.bar);
+#pragma unroll 1
+      for (int base = i0; base < i1 || base == i0; base += SCI) {
+        const int cnt = (p.mask & 2) ? max(0, min(SCI, i1 - base)) : 0;
+        if (cnt > 0) stage_fill(pp, 0, p.att1 + (int64_t)base * A, (uint32_t)cnt * A * 2);
+        if (base == i0) {
+          grid_wait(p.bar, target);
+          RECUR_STAMP();
+        }
+        if (cnt > 0) {
+          mbar_wait(pp.full[0], pp.use[0] & 1);
+          pp.use[0]++;
+          const float bfv = __ldg(p.b_f);
+#pragma unroll 1
+          for (int i = warp; i < cnt; i += RW) {
+            const int it = base + i;
+            const int b = it / P, px = it - b * P;
+            const float* g1 = p.g1 + (tb + b) * NG1;
+            float s = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int a = cc * 256 + a_lane;
+              if (a < A) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(stg + (size_t)(i * A + a) * 2);
+                float f[8];
+                unpack16(raw, f, bf16());
+                const float4 x0 = __ldcg(reinterpret_cast<const float4*>(g1 + a));
+                const float4 x1 = __ldcg(reinterpret_cast<const float4*>(g1 + a + 4));
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_f + a));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_f + a + 4));
+                s = fmaf(w0.x, fmaxf(f[0] + x0.x, 0.f), s); s = fmaf(w0.y, fmaxf(f[1] + x0.y, 0.f), s);
+                s = fmaf(w0.z, fmaxf(f[2] + x0.z, 0.f), s); s = fmaf(w0.w, fmaxf(f[3] + x0.w, 0.f), s);
+                s = fmaf(w1.x, fmaxf(f[4] + x1.x, 0.f), s); s = fmaf(w1.y, fmaxf(f[5] + x1.y, 0.f), s);
+                s = fmaf(w1.z, fmaxf(f[6] + x1.z, 0.f), s); s = fmaf(w1.w, fmaxf(f[7] + x1.w, 0.f), s);
+              }
+            }
+            s = warp_sum(s);
+            if (lane == 0) p.scores[(int64_t)b * Ppad + px] = s + bfv;
+          }
+          if (base + SCI < i1) __syncthreads();
+        }
+      }
+      RECUR_STAMP();
+      // ================= softmax + weighted sum over a 512-channel chunk + gate -> z =================
+      // item = (row, chunk); its pixels stream through the two stages, 32 pixels (32 KB, one bulk copy
+      // from the chunk-major feature copy) per fill; the first two fills are in flight during the barrier
+      grid_arrive(p.bar);
+      {
+        const int items_w = (p.mask & 4) ? n * chunks : 0;
+        const int nfill = (P + WPXS - 1) / WPXS;
+        bool first = true;
+#pragma unroll 1
+        for (int item = blockIdx.x; item < items_w || first; item += gridDim.x) {
+          const bool live = item < items_w;
+          const int row = live ? item / chunks : 0, chunk = live ? item - row * chunks : 0;
+          const bf16* src = p.enc_cm + ((int64_t)row * chunks + chunk) * P * CHUNK;
+          if (live) {
+            stage_fill(pp, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
+            if (nfill > 1) stage_fill(pp, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
+          }
+          if (first) {
+            grid_wait(p.bar, target);
+            RECUR_STAMP();
+            first = false;
+          }
+          if (!live) break;
+          // softmax (every CTA of the row recomputes it: P <= RT values, one per thread)
+          float sv = -INFINITY;
+          if (tid < P) sv = __ldcg(p.scores + (int64_t)row * Ppad + tid);
+          float mx = warp_max(sv);
+          if (lane == 0) red[warp] = mx;
+          __syncthreads();
+          mx = red[0];
+#pragma unroll
+          for (int w = 1; w < RW; ++w) mx = fmaxf(mx, red[w]);
+          const float ex = tid < P ? __expf(sv - mx) : 0.f;
+          float sum = warp_sum(ex);
+          if (lane == 0) red[RW + warp] = sum;
+          __syncthreads();
+          sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < RW; ++w) sum += red[RW + w];
+          const float alpha = __fdividef(ex, sum);
+          if (tid < P) {
+            al[tid] = alpha;
+            if (chunk == 0) p.alphas[((int64_t)row * T + t) * P + tid] = alpha;
+          }
+          __syncthreads();
+          float acc[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 1
+          for (int fi = 0; fi < nfill; ++fi) {
+            const int s = fi & 1;
+            const int px0 = fi * WPXS, cnt = min(WPXS, P - px0);
+            mbar_wait(pp.full[s], pp.use[s] & 1);
+            pp.use[s]++;
+            const uint8_t* base = stg + s * STAGE + col * 16;
+#pragma unroll
+            for (int u = 0; u < WPXS / GROUPS; ++u) {
+              const int pl = grp + u * GROUPS;
+              if (pl < cnt) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(base + (size_t)pl * CHUNK * 2);
+                const float w = al[px0 + pl];
+                float f[8];
+                unpack16(raw, f, bf16());
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, f[k], acc[k]);
+              }
+            }
+            if (fi + 2 < nfill) {
+              __syncthreads();
+              const int pxn = (fi + 2) * WPXS;
+              stage_fill(pp, s, src + (int64_t)pxn * CHUNK, (uint32_t)min(WPXS, P - pxn) * CHUNK * 2);
+            }
+          }
+          // cross-group reduction through shared memory (red: >= 2 RW + (GROUPS-1) * NCOL * 8 floats)
+          if (grp > 0) {
+            float4* dst = reinterpret_cast<float4*>(red + 2 * RW + ((grp - 1) * NCOL + col) * 8);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+          }
+          __syncthreads();
+          if (grp == 0) {
+#pragma unroll 1
+            for (int gq = 1; gq < GROUPS; ++gq) {
+              const float4* sp = reinterpret_cast<const float4*>(red + 2 * RW + ((gq - 1) * NCOL + col) * 8);
+              const float4 s0 = sp[0], s1 = sp[1];
+              acc[0] += s0.x; acc[1] += s0.y; acc[2] += s0.z; acc[3] += s0.w;
+              acc[4] += s1.x; acc[5] += s1.y; acc[6] += s1.z; acc[7] += s1.w;
+            }
+            const int e0 = chunk * CHUNK + col * 8;
+            const float* g1 = p.g1 + (tb + row) * NG1 + A + e0;
+            const float4 b0 = __ldcg(reinterpret_cast<const float4*>(g1));
+            const float4 b1 = __ldcg(reinterpret_cast<const float4*>(g1 + 4));
+            const float bp[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float zv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) zv[k] = fsigmoid(bp[k]) * acc[k];
+            if (p.awe) {
+              float* dst = p.awe + (tb + row) * E + e0;
+              *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+            const uint4 zp = pack16(zv, bf16());
+            *reinterpret_cast<uint4*>(p.z + (tb + row) * E + e0) = zp;
+            *reinterpret_cast<uint4*>(p.zk + (((int64_t)t * chunks + chunk) * B + row) * CHUNK + col * 8) = zp;
+          }
+          __syncthreads();
+        }
+      }
+      RECUR_STAMP();
+      grid_arrive(p.bar);
+      grid_wait(p.bar, target);
+      RECUR_STAMP();
+      // ================= P3: u = Emb W_ia[:M] + z W_ia[M:], and u*v -> m =================
+      if (has3 && (p.mask & 8)) {
+        float out[1];
+        gemm_job<1, 2>(pp, p.zk + (int64_t)t * chunks * B * CHUNK, (int64_t)B * CHUNK, n, W3s, w3s, E / KC, red, out);
+        const int nf = f3 + ej;
+        if (erow < n && nf < NQ) {
+          float* U = p.U + (tb + erow) * NQ;
+          const float val = out[0] + U[nf];
+          U[nf] = val;
+          const int gg = nf / F, f = nf - gg * F;
+          p.m[((int64_t)gg * p.R + tb + erow) * 2 * F + f] =
+              __float2bfloat16_rn(val * __ldg(p.v + (int64_t)erow * NQ + nf));
+        }
+      }
+      RECUR_STAMP();
+    }
+    grid_arrive(p.bar);
+    grid_wait(p.bar, target);
+    RECUR_STAMP();
+    // ================= P4: pre_g = m_g [W_ic_g | W_hc_g]^T  (the n x 2F operand is one bulk copy) =========
+    if (has4 && (p.mask & 16)) {
+      float out[1];
+      gemm_job<1, 4>(pp, p.m + ((int64_t)gate4 * p.R + tb) * 2 * F, 0, n, W4s, w4s, 1, red, out);
+      const int d = d4 + ej;
+      if (erow < n && d < D) p.pre[(tb + erow) * 4 * D + (int64_t)gate4 * D + d] = out[0];
+    }
+    RECUR_STAMP();
+    grid_arrive(p.bar);
+    grid_wait(p.bar, target);
+    RECUR_STAMP();
+    // ================= LSTM pointwise (scn_cell.py:146-152), gate order i,f,o,c =================
+    {
+      const int total = (p.mask & 32) ? n * D : 0;
+      const float* c_prev = p.C + tb * D;
+      float* c_new = p.C + (tb + B) * D;
+#pragma unroll 1
+      for (int i = blockIdx.x * RT + tid; i < total; i += gridDim.x * RT) {
+        const int b = i / D, d = i - b * D;
+        const float* pre = p.pre + (tb + b) * 4 * D + d;
+        float x[4];
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq)
+          x[gq] = __ldcg(pre + gq * D) + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
+        const float ig = fsigmoid(x[0]), fg = fsigmoid(x[1]), og = fsigmoid(x[2]);
+        const float gg = ftanh(x[3]);
+        const float c = fg * __ldcg(c_prev + i) + ig * gg;
+        const float h = og * ftanh(c);
+        c_new[i] = c;
+        float* gp = p.gates + (tb + b) * 4 * D + d;
+        gp[0] = ig; gp[D] = fg; gp[2 * D] = og; gp[3 * D] = gg;
+        const int64_t ho = ((int64_t)b * T + t) * D + d;
+        const bf16 hb = __float2bfloat16_rn(h);
+        p.Hall[ho] = hb;
+        p.Ht[tb * D + i] = hb;
+        if (drop_p > 0.f)
+          p.Hd[ho] = __float2bfloat16_rn(h * dropout_scale(seed, ((uint64_t)b * T + t) * D + d, drop_p));
+      }
+    }
+    RECUR_STAMP();
+    grid_arrive(p.bar);
+    grid_wait(p.bar, target);
+    RECUR_STAMP();
+  }
+#undef RECUR_STAMP
+}
+
+// enc_cm[b][c][p][j] = enc[b][p][c*512 + j]: every (pixel, 512-channel chunk) run of 1 KB becomes
+// contiguous with its neighbours in p, so a weighted-sum stage is ONE bulk copy
+__global__ void chunk_major_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int P, int E) {
+  const int vpr = E / 8, vpc = CHUNK / 8, chunks = E / CHUNK;
+  const int64_t total = (int64_t)B * P * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bp = i / vpr;
+    const int e8 = (int)(i - bp * vpr);
+    const int b = (int)(bp / P), px = (int)(bp - (int64_t)b * P);
+    const int c = e8 / vpc, j = e8 - c * vpc;
+    dst[(((int64_t)b * chunks + c) * P + px) * vpc + j] = src[i];
+  }
+}
+
+struct DevInfo { int sms = 0; int smem_optin = 0; bool coop = false; };
+DevInfo g_dev[64];
+std::once_flag g_dev_once[64];
+
+const DevInfo* dev_info() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::call_once(g_dev_once[dev], [dev] {
+    DevInfo& d = g_dev[dev];
+    int v = 0;
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
+    d.coop = v != 0;
+  });
+  return &g_dev[dev];
+}
+
+size_t fwd_smem_bytes(const RecurFwdArgs& a, int nt1, int nt3, int nt4) {
+  size_t s = 2 * (size_t)STAGE;
+  s += (size_t)nt1 * 8 * (a.D * 2 + WPAD);
+  if (a.att) s += (size_t)nt3 * 8 * (a.E * 2 + WPAD);
+  s += (size_t)nt4 * 8 * (2 * a.F * 2 + WPAD);
+  s += (size_t)KSL * 32 * REDLD * 4;
+  s += (size_t)pad4i(a.P > 0 ? a.P : 4) * 4;
+  s += (size_t)(((a.B + 3) & ~3) + 2) * 4;
+  return s + 8 + 2 * 8 + 128;
+}
+
+int pick_nt(int tiles, int ctas) {
+  if (tiles <= 2 * ctas) return 2;
+  if (tiles <= 4 * ctas) return 4;
+  return 0;
+}
+
+bool persistent_enabled() {
+  const char* s = getenv("CAPDEC_PERSISTENT");      // read per call: tests flip it
+  return !(s && s[0] == '0');
+}
+
+// decide the tiling; returns false when the shape is outside what the persistent kernel covers
+bool plan_fwd(const RecurFwdArgs& a, const DevInfo* di, int* nt1, int* nt3, int* nt4, size_t* smem) {
+  if (!di || !di->coop || di->sms < 8) return false;
+  if (a.B < 1 || a.B > 32 || a.T < 1) return false;
+  if (a.D != KC || 2 * a.F != 2 * KC) return false;     // G1 operand = one 512-wide fill, P4 operand = one 1024-wide fill
+  if (a.att && (a.E % KC || a.E % CHUNK || a.A % 8 || a.A > 512 || a.P < 1 || a.P > RT)) return false;
+  const int NQ = 4 * a.F, NG1 = (a.att ? a.A + a.E : 0) + NQ;
+  *nt1 = pick_nt(NG1 / 8, di->sms);
+  *nt3 = a.att ? pick_nt(NQ / 8, di->sms) : 2;
+  *nt4 = pick_nt(4 * (a.D / 8), di->sms);
+  if (!*nt1 || *nt3 != 2 || *nt4 != 2) return false;
+  if ((a.D / 8) % *nt4) return false;               // a CTA's P4 tiles stay inside one gate
+  *smem = fwd_smem_bytes(a, *nt1, *nt3, *nt4);
+  return *smem <= (size_t)di->smem_optin;
+}
+
+}  // namespace
+
+bool recur_fwd_supported(const RecurFwdArgs& a) {
+  if (!persistent_enabled()) return false;
+  int n1, n3, n4;
+  size_t smem;
+  return plan_fwd(a, dev_info(), &n1, &n3, &n4, &smem);
+}
+
+int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
+  const DevInfo* di = dev_info();
+  int nt1, nt3, nt4;
+  size_t smem;
+  CAPDEC_REQUIRE(plan_fwd(a, di, &nt1, &nt3, &nt4, &smem), CAPDEC_ERR_BAD_SHAPE,
+                 "recur_fwd: shape not covered by the persistent kernel");
+  FwdP p;
+  memset(&p, 0, sizeof p);
+  p.B = a.B; p.T = a.T; p.P = a.P; p.E = a.E; p.A = a.A; p.M = a.M; p.D = a.D; p.F = a.F;
+  p.NQ = 4 * a.F; p.NG1 = (a.att ? a.A + a.E : 0) + p.NQ; p.R = (int64_t)a.B * a.T;
+  p.len = a.len; p.Wcat1 = (const bf16*)a.Wcat1; p.ldD = a.ldD; p.Wxz = (const bf16*)a.Wxz; p.ldX = a.ldX;
+  p.Wc = (const bf16*)a.Wc; p.ld2F = a.ld2F; p.b_cat1 = a.b_cat1; p.b_ih = a.b_ih; p.b_hh = a.b_hh;
+  p.att1 = (const bf16*)a.att1; p.enc_cm = (const bf16*)a.enc_cm; p.w_f = a.w_f; p.b_f = a.b_f; p.v = a.v; p.q = a.q;
+  p.H0 = (const bf16*)a.H0; p.Ht = (bf16*)a.Ht; p.zk = (bf16*)a.zk; p.Hall = (bf16*)a.Hall; p.Hd = (bf16*)a.Hd; p.C = a.C; p.U = a.U;
+  p.g1 = a.g1; p.alphas = a.alphas; p.awe = a.awe; p.z = (bf16*)a.z; p.m = (bf16*)a.m; p.pre = a.pre;
+  p.gates = a.gates; p.scores = a.scores; p.bar = a.bar; p.dropout_p = a.dropout_p; p.seed = a.seed;
+
+  auto kernel = a.att ? (nt1 == 4 ? recur_fwd_kernel<true, 4> : recur_fwd_kernel<true, 2>)
+                      : (nt1 == 4 ? recur_fwd_kernel<false, 4> : recur_fwd_kernel<false, 2>);
+  CAPDEC_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CAPDEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RT, smem));
+  CAPDEC_REQUIRE(per_sm >= 1, CAPDEC_ERR_CUDA, "recur_fwd: kernel does not fit one CTA per SM (smem %zu)", smem);
+  CAPDEC_REQUIRE(a.ldH0 == a.D, CAPDEC_ERR_BAD_SHAPE, "recur_fwd: H0 must be dense");
+  if (a.att) {
+    chunk_major_kernel<<<di->sms * 8, 256, 0, st>>>((const uint4*)a.enc, (uint4*)a.enc_cm, a.B, a.P, a.E);
+    CAPDEC_LAUNCH_OK();
+  }
+  CAPDEC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 4, st));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(di->sms, 1, 1);
+  cfg.blockDim = dim3(RT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  p.mask = 63;
+  if (const char* mk = getenv("CAPDEC_RECUR_MASK")) p.mask = atoi(mk);
+  const char* prof_env = getenv("CAPDEC_RECUR_PROF");
+  const bool prof = prof_env && prof_env[0] == '1';
+  if (prof) {
+    CAPDEC_CUDA_OK(cudaMalloc(&p.prof, (size_t)(a.T * 16 + 64) * sizeof(long long)));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(p.prof, 0, (size_t)(a.T * 16 + 64) * sizeof(long long), st));
+  }
+  CAPDEC_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
+  count_launch();
+  if (prof) {
+    // debug only: synchronises.  Prints per-phase cycles of CTA 0 (work, barrier wait) for a few steps.
+    std::vector<long long> h((size_t)a.T * 16 + 64);
+    CAPDEC_CUDA_OK(cudaStreamSynchronize(st));
+    CAPDEC_CUDA_OK(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.prof);
+    for (int t = 0; t < a.T; t += (a.T > 8 ? a.T / 4 : 1)) {
+      fprintf(stderr, "recur_fwd prof t=%d:", t);
+      for (int k = 1; k < 16 && h[t * 16 + k]; ++k) fprintf(stderr, " %lld", h[t * 16 + k] - h[t * 16 + k - 1]);
+      fprintf(stderr, "\n");
+    }
+  }
+  return CAPDEC_OK;
+}
+
+}  // namespace capdec

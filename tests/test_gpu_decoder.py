@@ -254,19 +254,25 @@ def test_graph_replay_matches_eager(kind):
         assert torch.equal(s_graph, s_eager) and l_graph == l_eager
 
 
-def test_bf16_full_width_matches_oracle():
-    """bf16 fast path at the reference dims against the fp64 oracle."""
+@pytest.mark.parametrize("persistent", ["1", "0"])
+@pytest.mark.parametrize("kind", [O.ATTENTION_SCN, O.PURE_SCN, O.PURE_ATTENTION])
+def test_bf16_full_width_matches_oracle(kind, persistent, monkeypatch):
+    """bf16 fast path at the reference dims against the fp64 oracle; persistent=1 runs the SCN
+    recurrences as one cooperative kernel each way (recur.cu), 0 the per-step kernel chains."""
+    monkeypatch.setenv("CAPDEC_PERSISTENT", persistent)
     dims = dict(A=512, M=512, D=512, F=512, S=1000, V=10000, E=2048)
     lengths = [9, 5, 12, 3]
     enc, tags, caps, caplens = O.synthetic_batch(4, dims["V"], seed=3, lengths=lengths)
     with capdec.precision_scope("bf16"):
         torch.manual_seed(0)
-        dec = build_decoder(O.ATTENTION_SCN, dims).eval()
+        dec = build_decoder(kind, dims).eval()
         sd = {k: v.detach().cpu() for k, v in dec.state_dict().items()}
-        scores, caps_sorted, dl, alphas, sort_ind = dec(enc.cuda(), tags.cuda(), caps.cuda(), caplens.cuda())
-        ref = oracle_run(O.ATTENTION_SCN, sd, enc, tags, caps, caplens, sort_ind=sort_ind)
+        scores, caps_sorted, dl, alphas, sort_ind = call_forward(dec, kind, enc.cuda(), tags.cuda(), caps.cuda(),
+                                                                 caplens.cuda())
+        ref = oracle_run(kind, sd, enc, tags, caps, caplens, sort_ind=sort_ind)
         assert rel_err(scores, ref["scores"]) < BF16_TOL
-        assert rel_err(alphas, ref["alphas"]) < BF16_TOL
+        if alphas is not None:
+            assert rel_err(alphas, ref["alphas"]) < BF16_TOL
         loss, _ = dec.loss(scores, caps_sorted, dl, alphas)
         assert abs(loss.item() - ref["loss"].item()) < BF16_TOL * abs(ref["loss"].item())
         loss.backward()
@@ -281,3 +287,45 @@ def test_bf16_full_width_matches_oracle():
             if e > 0.08:
                 bad.append((n, e))
         assert not bad, bad
+
+
+@pytest.mark.parametrize("train_mode", [False, True])
+@pytest.mark.parametrize("kind", [O.ATTENTION_SCN, O.PURE_SCN])
+def test_persistent_recurrence_matches_step_kernels(kind, train_mode, monkeypatch):
+    """Config-3 per-GPU shape (B=32, ragged lengths): the persistent cooperative kernels (recur.cu) and
+    the per-step kernel chains are two schedules of the same bf16 arithmetic -- outputs, saved state and
+    gradients agree to summation-order noise, the dropout masks are the same counter-based stream, and
+    the persistent forward is bit-reproducible (no atomics)."""
+    dims = dict(A=512, M=512, D=512, F=512, S=1000, V=10000, E=2048)
+    B = 32
+    lengths = O.tie_free_lengths(B)
+    enc, tags, caps, caplens = O.synthetic_batch(B, dims["V"], seed=7, lengths=lengths)
+    args = [t.cuda() for t in (enc, tags, caps, caplens)]
+    res = {}
+    with capdec.precision_scope("bf16"):
+        torch.manual_seed(0)
+        dec = build_decoder(kind, dims)
+        dec.train(train_mode)
+        for mode in ("1", "0", "1"):
+            monkeypatch.setenv("CAPDEC_PERSISTENT", mode)
+            torch.manual_seed(11)
+            dec.zero_grad(set_to_none=True)
+            scores, caps_sorted, dl, alphas, sort_ind = call_forward(dec, kind, *args)
+            loss, _ = dec.loss(scores, caps_sorted, dl, alphas)
+            loss.backward()
+            cur = (scores.clone(), None if alphas is None else alphas.clone(), loss.item(),
+                   {n: p.grad.clone() for n, p in dec.named_parameters()})
+            if mode == "1" and "1" in res:
+                assert torch.equal(cur[0], res["1"][0])          # deterministic forward
+            res[mode] = cur
+    a, b = res["1"], res["0"]
+    assert torch.isfinite(a[0]).all()
+    assert rel_err(a[0], b[0]) < 5e-3
+    if a[1] is not None:
+        assert rel_err(a[1], b[1]) < 5e-3
+    assert abs(a[2] - b[2]) < 1e-3 * abs(b[2])
+    for n in a[3]:
+        if n == "attention.full_att.bias":      # mathematically zero (softmax shift invariance): rounding noise
+            continue
+        e = rel_err_fro(a[3][n], b[3][n])
+        assert e < 3e-2, (n, e)

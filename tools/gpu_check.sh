@@ -14,7 +14,7 @@ if [ "${2:-}" != "quick" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
       --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu.log 2>&1
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'attn_fwd|attn_bwd|gemm_tc_kernel' -s 600 -c 12 \
+  ncu --set full --clock-control none --import-source on -k regex:'attn_scores|attn_wsum|attn_bwd|gemm_tc_kernel' -s 700 -c 16 \
       -f -o $OUT/${TAG}_prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu2.log 2>&1
 fi
 tail -5 $OUT/${TAG}_tests.log; cat $OUT/${TAG}_smoke.log | tail -3; cat $OUT/${TAG}_bench_train.json $OUT/${TAG}_bench_decode.json; tail -3 $OUT/${TAG}_bench_decode.err
