@@ -81,13 +81,16 @@ struct ScoreArgs {
 };
 
 // NCH = 16-byte chunks per lane along the attention dim: A <= 32 * VEC * NCH
-template <typename FT, int NCH>
+// RPM = rows of one feature map handled by the SAME CTA (beam search: the k beams of an image share
+//       att1, attention_scn.py:189 `expand`): the map is read once for all of them.  RPM == 1: one row
+//       per CTA, map = row / rows_per_map.
+template <typename FT, int NCH, int RPM>
 __global__ void __launch_bounds__(NT)
 attn_scores_kernel(ScoreArgs a) {
   constexpr int VEC = FTraits<FT>::VEC;
   pdl_launch_dependents();
-  const int row = blockIdx.y;
-  const int map = row / a.rows_per_map;
+  const int row0 = RPM == 1 ? blockIdx.y : blockIdx.y * RPM;
+  const int map = RPM == 1 ? row0 / a.rows_per_map : blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = a.P, A = a.A;
   const int p_begin = blockIdx.x * a.Pc;
@@ -107,33 +110,41 @@ attn_scores_kernel(ScoreArgs a) {
     }
   }
   pdl_wait();                               // g1 comes from the previous kernel of the stream
-  const float* g1 = a.g1 + (int64_t)row * a.ldg;
-  float att2[NCH][VEC], wf[NCH][VEC];
+  float att2[RPM][NCH][VEC], wf[NCH][VEC];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int a0 = (c * 32 + lane) * VEC;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      att2[c][k] = (a0 + k < A) ? g1[a0 + k] : 0.f;
       wf[c][k] = (a0 + k < A) ? a.w_f[a0 + k] : 0.f;
+#pragma unroll
+      for (int j = 0; j < RPM; ++j)
+        att2[j][c][k] = (a0 + k < A) ? a.g1[(int64_t)(row0 + j) * a.ldg + a0 + k] : 0.f;
     }
   }
   const float bf = a.b_f[0];
-  float* sc = a.scores + (int64_t)row * pad4(P);
+  const int Ppad = pad4(P);
   for (int p = p0;; p += PXS * NW) {
 #pragma unroll
     for (int i = 0; i < PXS; ++i) {
       const int pi = p + i * NW;
-      float s = 0.f;
+      float s[RPM];
+#pragma unroll
+      for (int j = 0; j < RPM; ++j) s[j] = 0.f;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         float f[VEC];
         unpack16(v[i][c], f, FT());
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) s = fmaf(wf[c][k], fmaxf(f[k] + att2[c][k], 0.f), s);
+        for (int k = 0; k < VEC; ++k)
+#pragma unroll
+          for (int j = 0; j < RPM; ++j) s[j] = fmaf(wf[c][k], fmaxf(f[k] + att2[j][c][k], 0.f), s[j]);
       }
-      s = warp_sum(s);
-      if (lane == 0 && pi < p_end) sc[pi] = s + bf;
+#pragma unroll
+      for (int j = 0; j < RPM; ++j) {
+        const float t = warp_sum(s[j]);
+        if (lane == 0 && pi < p_end) a.scores[(int64_t)(row0 + j) * Ppad + pi] = t + bf;
+      }
     }
     if (p + PXS * NW >= p_end) break;
     // more pixels than one pass covers (very large batches only): reload
@@ -160,19 +171,19 @@ struct WsumArgs {
   int rows_per_map, P, E, ncol;       // ncol = 16-byte columns per CTA
 };
 
-template <typename FT>
+template <typename FT, int RPM>
 __global__ void __launch_bounds__(NT)
 attn_wsum_kernel(WsumArgs a) {
   constexpr int VEC = FTraits<FT>::VEC;
   extern __shared__ __align__(16) float smem_f[];
   pdl_launch_dependents();
-  const int row = blockIdx.y;
-  const int map = row / a.rows_per_map;
+  const int row0 = RPM == 1 ? blockIdx.y : blockIdx.y * RPM;
+  const int map = RPM == 1 ? row0 / a.rows_per_map : blockIdx.y;
   const int tid = threadIdx.x;
   const int P = a.P, E = a.E, ncol = a.ncol;
   const int Ppad = pad4(P);
-  float* al = smem_f;                 // [Ppad] alpha
-  float* red = al + Ppad;             // [NT * VEC] cross-group reduction (+ block reductions)
+  float* al = smem_f;                 // [RPM][Ppad] alpha
+  float* red = al + RPM * Ppad;       // [NT * VEC] cross-group reduction (+ block reductions)
   const int groups = NT / ncol;       // pixel groups; threads >= groups*ncol idle
   const int grp = tid / ncol, col = tid - grp * ncol;
   const bool active = grp < groups;
@@ -187,25 +198,31 @@ attn_wsum_kernel(WsumArgs a) {
     if (active && p < P) q[u] = ld_stream16(src + (int64_t)p * E);
   }
   pdl_wait();
-  // ---- softmax over the P scores (every CTA of the row does it; 196 values) ----
-  const float* sc = a.scores + (int64_t)row * Ppad;
-  float m = -INFINITY;
-  for (int p = tid; p < P; p += NT) { const float s = sc[p]; al[p] = s; m = fmaxf(m, s); }
-  m = block_max<NT>(m, red);
-  float sum = 0.f;
-  for (int p = tid; p < P; p += NT) { const float e = expf(al[p] - m); al[p] = e; sum += e; }
-  sum = block_sum<NT>(sum, red);
-  const float inv = 1.0f / sum;
-  for (int p = tid; p < P; p += NT) {
-    const float v = al[p] * inv;
-    al[p] = v;
-    if (blockIdx.x == 0 && a.alpha_out) a.alpha_out[(int64_t)row * a.alpha_stride + p] = v;
+  // ---- softmax over the P scores of every row of this CTA (196 values each) ----
+#pragma unroll 1
+  for (int j = 0; j < RPM; ++j) {
+    const float* sc = a.scores + (int64_t)(row0 + j) * Ppad;
+    float* alj = al + j * Ppad;
+    float m = -INFINITY;
+    for (int p = tid; p < P; p += NT) { const float s = sc[p]; alj[p] = s; m = fmaxf(m, s); }
+    m = block_max<NT>(m, red);
+    float sum = 0.f;
+    for (int p = tid; p < P; p += NT) { const float e = expf(alj[p] - m); alj[p] = e; sum += e; }
+    sum = block_sum<NT>(sum, red);
+    const float inv = 1.0f / sum;
+    for (int p = tid; p < P; p += NT) {
+      const float v = alj[p] * inv;
+      alj[p] = v;
+      if (blockIdx.x == 0 && a.alpha_out) a.alpha_out[(int64_t)(row0 + j) * a.alpha_stride + p] = v;
+    }
   }
   __syncthreads();
-  // ---- weighted sum ----
-  float acc[VEC];
+  // ---- weighted sums: every feature vector is used for all RPM rows ----
+  float acc[RPM][VEC];
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  for (int j = 0; j < RPM; ++j)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[j][k] = 0.f;
   for (int pb = 0; pb < P; pb += UNR * groups) {
     if (pb > 0) {
 #pragma unroll
@@ -218,44 +235,58 @@ attn_wsum_kernel(WsumArgs a) {
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int p = pb + grp + u * groups;
-      const float w = (active && p < P) ? al[p] : 0.f;
       float f[VEC];
       unpack16(q[u], f, FT());
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w, f[k], acc[k]);
+      for (int j = 0; j < RPM; ++j) {
+        const float w = (active && p < P) ? al[j * Ppad + p] : 0.f;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[j][k] = fmaf(w, f[k], acc[j][k]);
+      }
     }
   }
-  if (groups > 1) {
-    __syncthreads();
-    if (active && grp > 0) {
+#pragma unroll 1
+  for (int j = 0; j < RPM; ++j) {
+    float accj[VEC];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) red[((grp - 1) * ncol + col) * VEC + k] = acc[k];
+    for (int jj = 0; jj < RPM; ++jj)
+      if (jj == j) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) accj[k] = acc[jj][k];
+      }
+    if (groups > 1) {
+      __syncthreads();
+      if (active && grp > 0) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) red[((grp - 1) * ncol + col) * VEC + k] = accj[k];
+      }
+      __syncthreads();
+      if (grp == 0) {
+        for (int g = 1; g < groups; ++g)
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) accj[k] += red[((g - 1) * ncol + col) * VEC + k];
+      }
     }
-    __syncthreads();
     if (grp == 0) {
-      for (int g = 1; g < groups; ++g)
+      const int row = row0 + j;
+      const float* g1 = a.g1 + (int64_t)row * a.ldg;
+      float zv[VEC];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[k] += red[((g - 1) * ncol + col) * VEC + k];
-    }
-  }
-  if (grp == 0) {
-    const float* g1 = a.g1 + (int64_t)row * a.ldg;
-    float zv[VEC];
+      for (int k = 0; k < VEC; ++k) {
+        float gate = 1.0f;
+        if (a.beta_col >= 0) gate = sigmoidf_(g1[a.beta_col + e0 + k]);
+        zv[k] = gate * accj[k];
+      }
+      if (a.awe_out) {
+        float* dst = a.awe_out + (int64_t)row * E + e0;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      float gate = 1.0f;
-      if (a.beta_col >= 0) gate = sigmoidf_(g1[a.beta_col + e0 + k]);
-      zv[k] = gate * acc[k];
-    }
-    if (a.awe_out) {
-      float* dst = a.awe_out + (int64_t)row * E + e0;
-#pragma unroll
-      for (int k = 0; k < VEC; k += 4)
-        *reinterpret_cast<float4*>(dst + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
-    }
-    if (a.z_out) {
-      FT* dst = (FT*)a.z_out + (int64_t)row * a.ldz + e0;
-      *reinterpret_cast<uint4*>(dst) = pack16(zv, FT());
+        for (int k = 0; k < VEC; k += 4)
+          *reinterpret_cast<float4*>(dst + k) = make_float4(accj[k], accj[k + 1], accj[k + 2], accj[k + 3]);
+      }
+      if (a.z_out) {
+        FT* dst = (FT*)a.z_out + (int64_t)row * a.ldz + e0;
+        *reinterpret_cast<uint4*>(dst) = pack16(zv, FT());
+      }
     }
   }
 }
@@ -588,28 +619,42 @@ int attention_fwd(int precision, const void* att1, const void* enc, const float*
   CAPDEC_REQUIRE(E % vec == 0 && A % vec == 0 && A <= 32 * vec * 4, CAPDEC_ERR_BAD_SHAPE,
                  "attention: need E,A multiples of %d and A <= %d (E=%d A=%d)", vec, 32 * vec * 4, E, A);
   CAPDEC_REQUIRE(scratch != nullptr, CAPDEC_ERR_BAD_ARG, "attention: scratch is NULL");
+  // rows of one feature map (beam search) are handled by one CTA when the beam width has an instance
+  const int rpm = (precision == CAPDEC_BF16 && A <= 32 * vec * 2 && rows_per_map >= 2 && rows_per_map <= 5 &&
+                   rows % rows_per_map == 0) ? rows_per_map : 1;
+  const int gy = rows / rpm;
   // ---- A: scores ----
   int PC = ceil_div(P, PXS * NW);                                   // one pass of PXS*NW pixels per CTA ...
-  while ((int64_t)rows * PC > 8 * 148 && PC > 1) PC = (PC + 1) / 2;     // ... unless the grid gets too large
+  while ((int64_t)gy * PC > 64 * 148 && PC > 1) PC = (PC + 1) / 2;      // ... unless the grid gets too large
   ScoreArgs sa{att1, g1, ldg, w_f, b_f, scratch, rows_per_map, P, A, ceil_div(P, PC)};
   PC = ceil_div(P, sa.Pc);
   const bool small = A <= 32 * vec * 2;
-  dim3 gs(PC, rows, 1);
+  dim3 gs(PC, gy, 1);
   if (precision == CAPDEC_BF16) {
-    if (small) CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 2>, gs, NT, 0, st, sa));
-    else CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 4>, gs, NT, 0, st, sa));
+    if (rpm == 2) CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 2, 2>, gs, NT, 0, st, sa));
+    else if (rpm == 3) CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 2, 3>, gs, NT, 0, st, sa));
+    else if (rpm == 4) CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 2, 4>, gs, NT, 0, st, sa));
+    else if (rpm == 5) CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 2, 5>, gs, NT, 0, st, sa));
+    else if (small) CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 2, 1>, gs, NT, 0, st, sa));
+    else CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 4, 1>, gs, NT, 0, st, sa));
   } else {
-    if (small) CAPDEC_TRY(launch_attn(attn_scores_kernel<float, 2>, gs, NT, 0, st, sa));
-    else CAPDEC_TRY(launch_attn(attn_scores_kernel<float, 4>, gs, NT, 0, st, sa));
+    if (small) CAPDEC_TRY(launch_attn(attn_scores_kernel<float, 2, 1>, gs, NT, 0, st, sa));
+    else CAPDEC_TRY(launch_attn(attn_scores_kernel<float, 4, 1>, gs, NT, 0, st, sa));
   }
   // ---- B: softmax + weighted sum + gate ----
-  const Chunking ch = pick_chunks(E, vec, rows);
+  const Chunking ch = pick_chunks(E, vec, gy);
   WsumArgs wa{enc, g1, ldg, beta_col, scratch, alpha_out, alpha_stride, z_out, ldz, awe_out,
               rows_per_map, P, E, ch.ncol};
-  const size_t smem = (size_t)(((P + 3) & ~3) + NT * 8) * sizeof(float);
-  dim3 gw(ch.EC, rows, 1);
-  if (precision == CAPDEC_BF16) return launch_attn(attn_wsum_kernel<bf16>, gw, NT, smem, st, wa);
-  return launch_attn(attn_wsum_kernel<float>, gw, NT, smem, st, wa);
+  const size_t smem = (size_t)(rpm * ((P + 3) & ~3) + NT * 8) * sizeof(float);
+  dim3 gw(ch.EC, gy, 1);
+  if (precision == CAPDEC_BF16) {
+    if (rpm == 2) return launch_attn(attn_wsum_kernel<bf16, 2>, gw, NT, smem, st, wa);
+    if (rpm == 3) return launch_attn(attn_wsum_kernel<bf16, 3>, gw, NT, smem, st, wa);
+    if (rpm == 4) return launch_attn(attn_wsum_kernel<bf16, 4>, gw, NT, smem, st, wa);
+    if (rpm == 5) return launch_attn(attn_wsum_kernel<bf16, 5>, gw, NT, smem, st, wa);
+    return launch_attn(attn_wsum_kernel<bf16, 1>, gw, NT, smem, st, wa);
+  }
+  return launch_attn(attn_wsum_kernel<float, 1>, gw, NT, smem, st, wa);
 }
 
 int attention_bwd(int precision, const void* att1, const void* enc, const float* g1, int64_t ldg,

@@ -115,7 +115,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 
 template <int BNR, int NACC>
 struct Cfg {
-  static constexpr int STAGES = (BNR == 64 && NACC == 4) ? 3 : 4;
+  // 3 stages for the 128-row tile: 96 KB per CTA, so TWO CTAs share an SM and one tile's prologue /
+  // epilogue overlaps the other's main loop (with 4 stages = 128 KB only one CTA fits)
+  static constexpr int STAGES = ((BNR == 64 && NACC == 4) || BNR == 128) ? 3 : 4;
   static constexpr int W_BYTES = BM * BK * 2;
   static constexpr int X_BYTES = BNR * BK * 2;
   static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
