@@ -376,7 +376,15 @@ def run_b200(args):
 
     roof = cpu_b = None
     if rank == 0:
-        roof = measure_roofline(dev, kind, dims, per_gpu_b if mode == "train" else 3 * 64, peaks, args.precision)
+        roof = None
+        if mode == "train" and kind != "pure_attention" and args.precision == "bf16":
+            roof = measure_recurrence_roofline(lib, dec, kind, dims, per_gpu_b, resident, peaks)
+        pair = measure_roofline(dev, kind, dims, per_gpu_b if mode == "train" else 3 * 64, peaks, args.precision)
+        if roof is None:
+            roof = pair
+        elif pair is not None:
+            roof["attention_step_kernels"] = {k: pair[k] for k in ("kernel", "achieved", "frac", "us_per_launch",
+                                                                   "algorithmic_bytes_per_launch", "traffic", "note")}
         if not args.no_cpu_baseline:
             if mode == "train":
                 cpu_b = cpu_train_sample(kind, dims, 4, 3, 1)
@@ -399,10 +407,65 @@ def run_b200(args):
     return 0
 
 
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum), or None when there is no capture of it."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def measure_recurrence_roofline(lib, dec, kind, dims, rows, inputs, peaks):
+    """Dominant kernel of the training step: recur_fwd_kernel (csrc/recur.cu), ONE cooperative launch that
+    runs all T decode steps.  Algorithmic bytes per launch = T * rows * P * (A + E) * 2 (every
+    caption-step streams its att1 and enc rows, 1.004 MB in bf16); for pure_scn (no feature stream) the
+    recurrent weights touched per step instead.  Duration: CUDA events recorded by the library on the
+    launching stream around the kernel (capdec_recur_timing), eager launches, mean of 5 after 2 warm-ups."""
+    import capdec
+    was = capdec.graphs_enabled() if hasattr(capdec, "graphs_enabled") else True
+    capdec.set_graphs(False)
+    lib.capdec_recur_timing(1)
+    enc, tags, caps, caplens = inputs
+    ms = []
+    try:
+        for it in range(7):
+            dec(enc, tags, caps, caplens)          # grad mode: the kernel also saves awe for the backward
+            t = float(lib.capdec_recur_last_ms())
+            if it >= 2 and t > 0:
+                ms.append(t)
+    finally:
+        lib.capdec_recur_timing(0)
+        capdec.set_graphs(was)
+    if not ms:
+        return None
+    t_ms = sum(ms) / len(ms)
+    P, E, A, D, F, T = 196, dims["E"], dims["A"], dims["D"], dims["F"], CAP_LEN - 1
+    if kind == "attention_scn":
+        bytes_alg = T * rows * P * (A + E) * 2
+        what = "T*rows*P*(A+E)*2 B of attention features"
+    else:
+        bytes_alg = T * (4 * F * D + 4 * D * 2 * F) * 2
+        what = "T * (W_ha + [W_ic|W_hc]) bf16 recurrent weights (resident in shared memory, so the HBM figure is an upper bound of need)"
+    achieved = bytes_alg / (t_ms * 1e-3) / 1e9
+    return {"kernel": "recur_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic("recur_fwd_kernel"),
+            "us_per_launch": 1e3 * t_ms, "rows": rows, "steps_per_launch": T,
+            "algorithmic_bytes_per_launch": bytes_alg, "peak_source": peaks["source"],
+            "note": "one cooperative launch = all %d decode steps; algorithmic bytes = %s; at %d rows the kernel "
+                    "is bound by its %d grid barriers and dependent L2 round trips per step, not by HBM (the "
+                    "features stay L2-resident across steps) -- see DESIGN.md" % (T, what, rows,
+                                                                                 6 if kind == "attention_scn" else 3)}
+
+
 def measure_roofline(dev, kind, dims, rows, peaks, precision):
-    """Dominant per-step kernel: the attention step (csrc/attention.cu attn_fwd_kernel).  Algorithmic
-    bytes per launch = rows * P * (A + E) * sizeof(feature) (1.004 MB per caption-step in
-    bf16), divided by its average duration measured with CUDA events on the launching stream."""
+    """The attention step as two stand-alone kernels (csrc/attention.cu attn_scores_kernel + attn_wsum_kernel),
+    the per-step path of pure_attention, fp32 mode, beam search and of shapes the persistent kernel does not
+    cover.  Algorithmic bytes per launch pair = rows * P * (A + E) * sizeof(feature) (1.004 MB
+    per caption-step in bf16), divided by its average duration measured with CUDA events on the launching
+    stream."""
     if kind == "pure_scn":
         return None
     from capdec import functional as CF
@@ -436,11 +499,13 @@ def measure_roofline(dev, kind, dims, rows, peaks, precision):
     us = 1e3 * s.elapsed_time(e) / n
     bytes_alg = rows * P * (A + E) * (2 if precision == "bf16" else 4)
     achieved = bytes_alg / (us * 1e-6) / 1e9
-    return {"kernel": "attn_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "us_per_launch": us, "rows": rows,
+    return {"kernel": "attn_scores_kernel+attn_wsum_kernel", "bound": "hbm", "achieved": achieved,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic("attn_scores_kernel+attn_wsum_kernel"),
+            "us_per_launch": us, "rows": rows,
             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": peaks["source"],
             "note": "features of one step (%.1f MB) are L2-resident across back-to-back launches, as in the "
-                    "decode loop; %d launches replayed from a CUDA graph, CUDA-event timed" % (bytes_alg / 1e6, n)}
+                    "decode loop; %d launch pairs replayed from a CUDA graph, CUDA-event timed" % (bytes_alg / 1e6, n)}
 
 
 def main():

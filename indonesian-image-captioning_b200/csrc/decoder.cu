@@ -49,6 +49,7 @@ struct Plan {
         Hd, lenD, seedD, capsD, counters, att_scr, bar, Ht, zk, enc_cm;
     // backward buffers
     size_t dlogF, dHfc, dh_rec, dc, dpre, wr, du, dpx, de, dv_acc, dq_acc, dz, dba, dAtt1, dwf, dbf, dXe;
+    size_t dpre_gm, duk, dpxk, att1_cm;     // chunk-major operand copies of the persistent backward (recur.cu)
     size_t tA, tB, tC;             // transposed-operand scratch
     size_t total;
   } o;
@@ -173,6 +174,12 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
       o.dbf = take(R * 4);
     }
     o.dXe = take(R * M * 4);
+    if (d.precision == CAPDEC_BF16 && p->scn) {
+      o.dpre_gm = take(R * 4 * D * f);
+      o.duk = take(R * NQ * f);
+      o.dpxk = take(R * p->ldPX * f);
+      if (p->att) o.att1_cm = take(B * P * A * f);
+    }
     // transposed operands for the weight-gradient GEMMs (K = rows).  tA/tB are sized for
     // the largest pair used together, tC for the shared H_prev^T.
     int64_t widest = V;
@@ -582,7 +589,38 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     }
   }
 
-  // ---------------- reverse-time recurrence ----------------
+  // ---------------- reverse-time recurrence as ONE persistent cooperative kernel (recur.cu) ----------------
+  bool persistent = false;
+  if (pr == CAPDEC_BF16 && p.scn && !fused) {
+    RecurBwdArgs rb;
+    rb.att = p.att ? 1 : 0;
+    rb.B = B; rb.T = T; rb.P = P; rb.E = E; rb.A = A; rb.M = M; rb.D = D; rb.F = F; rb.ldPX = p.ldPX;
+    rb.len = c.at<int32_t>(o.lenD);
+    rb.WcT = c.at(o.Wp_cT); rb.ldD = p.ldD;
+    rb.Wxin = c.ft(o.Wp_xin, (int64_t)M * p.ldNQ); rb.ldNQ = p.ldNQ;
+    rb.Whx = c.at(o.Wp_hx); rb.ldhx = p.ldPX;
+    rb.dHfc = c.at<float>(o.dHfc); rb.gates = c.at<float>(o.gates); rb.C = c.at<float>(o.C);
+    rb.dc = c.at<float>(o.dc); rb.dh_rec = c.at<float>(o.dh_rec);
+    rb.dpre = c.at(o.dpre); rb.dpre_gm = c.at(o.dpre_gm);
+    rb.U = c.at<float>(o.U); rb.g1 = c.at<float>(o.g1); rb.v = c.at<float>(o.v); rb.q = c.at<float>(o.q);
+    rb.du = c.at(o.du); rb.duk = c.at(o.duk); rb.dpx = c.at(o.dpx); rb.dpxk = c.at(o.dpxk);
+    rb.dv_acc = c.at<float>(o.dv_acc); rb.dq_acc = c.at<float>(o.dq_acc);
+    if (p.att) {
+      rb.dz = c.at<float>(o.dz); rb.awe = c.at<float>(o.awe); rb.alphas = alphas; rb.d_alphas = d_alphas;
+      rb.enc_cm = c.at(o.enc_cm); rb.att1 = c.at(o.att1); rb.att1_cm = c.at(o.att1_cm); rb.w_f = w.full_att_w;
+      RecurFwdArgs fa;        // did the forward (same dims, same switches) build the chunk-major feature copy?
+      fa.att = 1; fa.B = B; fa.T = T; fa.P = P; fa.E = E; fa.A = A; fa.M = M; fa.D = D; fa.F = F;
+      rb.enc = c.at(o.enc_s); rb.build_enc_cm = recur_fwd_supported(fa) ? 0 : 1;
+      rb.part = c.at<float>(o.att_scr); rb.de = c.at<float>(o.de); rb.dwf = c.at<float>(o.dwf);
+      rb.dbf = c.at<float>(o.dbf);
+    }
+    rb.bar = c.at<unsigned>(o.bar); rb.dropout_p = dropout_p; rb.seed = c.at<uint64_t>(o.seedD);
+    if ((!p.att || alphas) && recur_bwd_supported(rb)) {
+      persistent = true;
+      CAPDEC_TRY(recur_bwd(rb, st));
+    }
+  }
+  // ---------------- reverse-time recurrence, one kernel chain per step ----------------
   auto cell_bwd_step = [&](int t, const float* dh_in) {
     return cell_bwd(pr, c.at<float>(o.dHfc) + (int64_t)t * D, (int64_t)T * D, dh_in, c.at<float>(o.dc),
                     c.at<float>(o.gates) + (int64_t)t * B * 4 * D, c.at<float>(o.C) + (int64_t)t * B * D,
@@ -591,7 +629,7 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   };
   if (fused)    // the last step's pointwise backward; every earlier one rides on the dh GEMM below
     CAPDEC_TRY(cell_bwd_step(T - 1, c.at<float>(o.dh_rec) + (int64_t)T * B * D));
-  for (int t = T - 1; t >= 0; --t) {
+  for (int t = persistent ? -1 : T - 1; t >= 0; --t) {
     const int n = bt[t];
     float* g1 = c.at<float>(o.g1) + (int64_t)t * B * NG1;
     const float* pcol = g1 + (p.att ? A + E : 0);

@@ -97,6 +97,31 @@ struct RecurFwdArgs {
 };
 bool recur_fwd_supported(const RecurFwdArgs& a);     // shape / device / CAPDEC_PERSISTENT check
 int recur_fwd(const RecurFwdArgs& a, cudaStream_t st);
+struct RecurBwdArgs {
+  int att = 0;
+  int B = 0, T = 0, P = 0, E = 0, A = 0, M = 0, D = 0, F = 0;
+  int64_t ldPX = 0;
+  const int32_t* len = nullptr;
+  const void* WcT = nullptr; int64_t ldD = 0;       // Wp_cT
+  const void* Wxin = nullptr; int64_t ldNQ = 0;     // Wp_xin + M rows
+  const void* Whx = nullptr; int64_t ldhx = 0;      // Wp_hx
+  const float* dHfc = nullptr; const float* gates = nullptr; const float* C = nullptr;
+  float* dc = nullptr; float* dh_rec = nullptr;
+  void* dpre = nullptr; void* dpre_gm = nullptr;
+  const float* U = nullptr; const float* g1 = nullptr; const float* v = nullptr; const float* q = nullptr;
+  void* du = nullptr; void* duk = nullptr; void* dpx = nullptr; void* dpxk = nullptr;
+  float* dv_acc = nullptr; float* dq_acc = nullptr; float* dz = nullptr;
+  const float* awe = nullptr; const float* alphas = nullptr; const float* d_alphas = nullptr;
+  const void* enc_cm = nullptr; const void* att1 = nullptr; const float* w_f = nullptr;
+  void* att1_cm = nullptr;           // [B][A/128][P][128] quarter-major copy of att1 (built by recur_bwd)
+  const void* enc = nullptr; int build_enc_cm = 0;   // build enc_cm from enc first (forward ran per-step kernels)
+  float* part = nullptr; float* de = nullptr; float* dwf = nullptr; float* dbf = nullptr;
+  unsigned* bar = nullptr; float dropout_p = 0.f; const uint64_t* seed = nullptr;
+};
+bool recur_bwd_supported(const RecurBwdArgs& a);
+int recur_bwd(const RecurBwdArgs& a, cudaStream_t st);
+void recur_timing(int enable);
+float recur_last_ms();
 
 // ---- beam.cu ----
 int beam_init(int32_t* prev_word, float* score, int32_t* live, int32_t* krem, int32_t* has_done,

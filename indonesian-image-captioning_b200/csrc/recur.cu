@@ -571,10 +571,409 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
 #undef RECUR_STAMP
 }
 
-// enc_cm[b][c][p][j] = enc[b][p][c*512 + j]: every (pixel, 512-channel chunk) run of 1 KB becomes
-// contiguous with its neighbours in p, so a weighted-sum stage is ONE bulk copy
-__global__ void chunk_major_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int P, int E) {
-  const int vpr = E / 8, vpc = CHUNK / 8, chunks = E / CHUNK;
+// =====================================================================================
+// Reverse-time recurrence as one cooperative launch: the mirror image of
+// recur_fwd_kernel.  Per step, six phases separated by grid barriers:
+//   C   LSTM pointwise backward (dh from the fc gradient + the recurrent gradient) -> dpre_t
+//   W   [w_g | r_g] = dpre_g [W_ic_g | W_hc_g]  and the factor products du = w*v, dp = r*q,
+//       dv_acc += w*u, dq_acc += r*p fused in the epilogue (full K per CTA: no atomics)
+//   Z   dz = du W_ia[M:]^T
+//   A   gate backward + partial dalpha_p = enc[p, chunk] . dawe   (streams enc, like the forward sum)
+//   B   softmax backward, relu / score backward -> datt2, dw_f, de   (streams att1; one CTA per row)
+//   H   dh_{t-1} = [dp | dbeta_pre | datt2] [W_ha | W_beta^T | W_d^T]^T   (K = 4608 split in 512-wide
+//       jobs over the CTAs; the partial sums meet in fp32 atomics on a zeroed slot, as before)
+// Operands that cross CTAs are written twice: in the layout the batched weight-gradient GEMMs read
+// after the loop, and chunk-major ([K/512][B][512]) so that every staging fill is one bulk copy.
+// =====================================================================================
+struct BwdP {
+  int B, T, P, E, A, M, D, F, NQ, NG1;
+  int64_t R, ldPX;
+  const int32_t* len;
+  const bf16* WcT; int64_t ldD;       // [4][2F][ldD]   [W_ic_g^T ; W_hc_g^T]
+  const bf16* Wxin; int64_t ldNQ;     // [E][ldNQ]      W_ia[M:, :] (already offset by M rows)
+  const bf16* Whx; int64_t ldhx;      // [D][ldhx]      [W_ha | W_beta^T | W_d^T]
+  const float* dHfc;                  // (B, T, D) fp32: d loss / d h_t through the vocabulary projection
+  const float* gates; const float* C;
+  float* dc;                          // [B][D]
+  float* dh_rec;                      // [T+1][B][D], zero on entry
+  bf16* dpre;                         // [T][B][4D]
+  bf16* dpre_gm;                      // [T][4][B][D]
+  const float* U; const float* g1; const float* v; const float* q;
+  bf16* du;                           // [T][B][NQ]
+  bf16* duk;                          // [T][NQ/512][B][512]
+  bf16* dpx;                          // [T][B][ldPX]   dp | dbeta_pre | datt2
+  bf16* dpxk;                         // [T][KH/512][B][512]
+  float* dv_acc; float* dq_acc;       // [B][NQ]
+  float* dz;                          // [T][B][E]
+  const float* awe; const float* alphas; const float* d_alphas;
+  const bf16* enc_cm; const float* w_f;
+  const bf16* att1_cm;                // [B][A/128][P][128]   quarter-major copy of att1
+  float* part;                        // [B][E/512][pad4(P)]
+  float* de; float* dwf; float* dbf;  // [T][B][pad4(P)], [T][B][A], [T][B]
+  unsigned* bar;
+  float dropout_p; const uint64_t* seed;
+  long long* prof;                    // debug (CAPDEC_RECUR_PROF=1): [T][16] clock64 stamps of CTA 0
+};
+
+template <bool ATT>
+__global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant__ BwdP p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int D = p.D, E = p.E, F = p.F, B = p.B, T = p.T, P = p.P, NQ = p.NQ, NG1 = p.NG1, A = p.A;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wWs = D * 2 + WPAD, wZs = NQ * 2 + WPAD, wHs = KC * 2 + WPAD;
+  uint8_t* stg = smem;
+  uint8_t* WWs = stg + 2 * STAGE;                         // 32 rows, K = D
+  uint8_t* WZs = WWs + (size_t)32 * wWs;                  // 16 rows, K = NQ   (ATT only)
+  uint8_t* WHs = WZs + (ATT ? (size_t)16 * wZs : 0);      // 2 x 16 rows, K = 512
+  float* red = reinterpret_cast<float*>(WHs + (size_t)32 * wHs);
+  float* al = red + KSL * 32 * REDLD;                     // [pad4(P)]
+  float* des = al + pad4i(P > 0 ? P : 4);                 // [pad4(P)]
+  int* lens = reinterpret_cast<int*>(des + pad4i(P > 0 ? P : 4));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lens + ((B + 3) & ~3) + 2);
+  bars = reinterpret_cast<uint64_t*>(((uintptr_t)bars + 7) & ~(uintptr_t)7);
+  Pipe pp;
+  pp.stg = stg; pp.stg_a = smem_u32(stg);
+  pp.full[0] = smem_u32(&bars[0]); pp.full[1] = smem_u32(&bars[1]);
+  pp.use[0] = pp.use[1] = 0;
+  if (tid == 0) {
+    mbar_init(pp.full[0], 1);
+    mbar_init(pp.full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // ---- roles ----
+  const int c = blockIdx.x;
+  const int spg = 2 * F / 32;                             // 32-feature slices per gate of the W job
+  const bool hasW = c < 4 * spg;
+  const int gateW = c / spg, fW0 = (c - gateW * spg) * 32;
+  const bool hasZ = ATT && c * 16 < E;
+  const int eZ0 = c * 16;
+  const int col0 = ATT ? A + E : 0;
+  const int KH = NQ + (ATT ? E + A : 0);
+  const int nkc = KH / KC, nkq = NQ / KC;
+  const int jobsH = (D / 16) * nkc;
+  if (hasW) load_weight_rows(WWs, p.WcT + ((int64_t)gateW * 2 * F + fW0) * p.ldD, p.ldD, D, 32, 2 * F - fW0);
+  if (hasZ) load_weight_rows(WZs, p.Wxin + (int64_t)eZ0 * p.ldNQ, p.ldNQ, NQ, 16, E - eZ0);
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i) {
+    const int j = c + i * gridDim.x;
+    if (j < jobsH) {
+      const int ds = j / nkc, kc = j - ds * nkc;
+      load_weight_rows(WHs + (size_t)i * 16 * wHs, p.Whx + (int64_t)ds * 16 * p.ldhx + (int64_t)kc * KC, p.ldhx, KC, 16,
+                       D - ds * 16);
+    }
+  }
+  for (int i = tid; i < B; i += RT) lens[i] = p.len[i];
+  __syncthreads();
+
+  const int erow = tid >> 4, ej = tid & 15;
+  const int Ppad = pad4i(P);
+  const int chunks = ATT ? E / CHUNK : 1;
+  const int grp = tid / NCOL, col = tid - grp * NCOL;
+  const float drop_p = p.dropout_p;
+  const uint64_t seed = drop_p > 0.f ? __ldg(p.seed) : 0ull;
+  const int nfillP = (P + WPXS - 1) / WPXS;
+  unsigned target = 0;
+  int stamp = 0;
+#define BSTAMP() do { if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[t * 16 + (stamp++ & 15)] = clock64(); } while (0)
+
+#pragma unroll 1
+  for (int t = T - 1; t >= 0; --t) {
+    stamp = 0;
+    BSTAMP();
+    const int n = __popc(__ballot_sync(0xffffffffu, lane < B && lens[lane] > t));
+    const int64_t tb = (int64_t)t * B;
+    // ================= C: LSTM pointwise backward =================
+    {
+      const int total = n * D;
+      const float* dh_in = p.dh_rec + (tb + B) * D;
+      const float* c_prev = p.C + tb * D;
+      const float* c_new = p.C + (tb + B) * D;
+#pragma unroll 1
+      for (int i = blockIdx.x * RT + tid; i < total; i += gridDim.x * RT) {
+        const int b = i / D, d = i - b * D;
+        float dh = __ldcg(dh_in + i);
+        {
+          float g = __ldg(p.dHfc + ((int64_t)b * T + t) * D + d);
+          if (drop_p > 0.f) g *= dropout_scale(seed, ((uint64_t)b * T + t) * D + d, drop_p);
+          dh += g;
+        }
+        const float* gp = p.gates + (tb + b) * 4 * D + d;
+        const float ig = __ldg(gp), fg = __ldg(gp + D), og = __ldg(gp + 2 * D), gg = __ldg(gp + 3 * D);
+        const float tc = ftanh(__ldg(c_new + i));
+        const float dcn = p.dc[i] + dh * og * (1.f - tc * tc);
+        const float dpv[4] = {dcn * gg * ig * (1.f - ig), dcn * __ldg(c_prev + i) * fg * (1.f - fg),
+                              dh * tc * og * (1.f - og), dcn * ig * (1.f - gg * gg)};       // i, f, o, c
+        p.dc[i] = dcn * fg;
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          const bf16 x = __float2bfloat16_rn(dpv[gq]);
+          p.dpre[(tb + b) * 4 * D + gq * D + d] = x;
+          p.dpre_gm[(((int64_t)t * 4 + gq) * B + b) * D + d] = x;
+        }
+      }
+    }
+    BSTAMP();
+    grid_arrive(p.bar);
+    grid_wait(p.bar, target);
+    BSTAMP();
+    // ================= W: [w | r] = dpre_g [W_ic_g | W_hc_g] and the factor products =================
+    if (hasW) {
+      float out[2];
+      gemm_job<2, 2>(pp, p.dpre_gm + ((int64_t)t * 4 + gateW) * B * D, 0, n, WWs, wWs, 1, red, out);
+      if (erow < n) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int nf = fW0 + i * 16 + ej;
+          if (nf < 2 * F) {
+            const bool is_w = nf < F;
+            const int n4 = gateW * F + (is_w ? nf : nf - F);
+            const int64_t k = (int64_t)erow * NQ + n4;
+            const float val = out[i];
+            if (is_w) {
+              const bf16 x = __float2bfloat16_rn(val * __ldg(p.v + k));
+              p.du[(tb + erow) * NQ + n4] = x;
+              p.duk[(((int64_t)t * nkq + n4 / KC) * B + erow) * KC + (n4 % KC)] = x;
+              p.dv_acc[k] += val * __ldg(p.U + (tb + erow) * NQ + n4);
+            } else {
+              const bf16 x = __float2bfloat16_rn(val * __ldg(p.q + k));
+              p.dpx[(tb + erow) * p.ldPX + n4] = x;
+              p.dpxk[(((int64_t)t * nkc + n4 / KC) * B + erow) * KC + (n4 % KC)] = x;
+              p.dq_acc[k] += val * __ldg(p.g1 + (tb + erow) * NG1 + col0 + n4);
+            }
+          }
+        }
+      }
+    }
+    BSTAMP();
+    if (ATT) {
+      grid_arrive(p.bar);
+      grid_wait(p.bar, target);
+      BSTAMP();
+      // ================= Z: dz = du W_ia[M:]^T =================
+      if (hasZ) {
+        float out[1];
+        gemm_job<1, 2>(pp, p.duk + (int64_t)t * nkq * B * KC, (int64_t)B * KC, n, WZs, wZs, nkq, red, out);
+        const int e = eZ0 + ej;
+        if (erow < n && e < E) p.dz[(tb + erow) * E + e] = out[0];
+      }
+      BSTAMP();
+      // ================= A: gate backward + partial dalpha over one 512-channel chunk =================
+      grid_arrive(p.bar);
+      {
+        const int items = n * chunks;
+        bool first = true;
+#pragma unroll 1
+        for (int item = blockIdx.x; item < items || first; item += gridDim.x) {
+          const bool live = item < items;
+          const int row = live ? item / chunks : 0, chunk = live ? item - row * chunks : 0;
+          const bf16* src = p.enc_cm + ((int64_t)row * chunks + chunk) * P * CHUNK;
+          if (live) {
+            stage_fill(pp, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
+            if (nfillP > 1) stage_fill(pp, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
+          }
+          if (first) {
+            grid_wait(p.bar, target);
+            BSTAMP();
+            first = false;
+          }
+          if (!live) break;
+          const int e0 = chunk * CHUNK + col * 8;
+          float dawe[8];
+          {
+            const float* dzp = p.dz + (tb + row) * E + e0;
+            const float* bpp = p.g1 + (tb + row) * NG1 + A + e0;
+            const float* awp = p.awe + (tb + row) * E + e0;
+            const float4 z0 = __ldcg(reinterpret_cast<const float4*>(dzp)), z1 = __ldcg(reinterpret_cast<const float4*>(dzp + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bpp)), b1 = __ldg(reinterpret_cast<const float4*>(bpp + 4));
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(awp)), a1 = __ldg(reinterpret_cast<const float4*>(awp + 4));
+            const float dzv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+            const float bp[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const float aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float db[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float gate = fsigmoid(bp[k]);
+              dawe[k] = dzv[k] * gate;
+              db[k] = dzv[k] * aw[k] * gate * (1.0f - gate);
+            }
+            if (grp == 0) {
+              const uint4 pk = pack16(db, bf16());
+              *reinterpret_cast<uint4*>(p.dpx + (tb + row) * p.ldPX + NQ + e0) = pk;
+              *reinterpret_cast<uint4*>(p.dpxk + (((int64_t)t * nkc + nkq + chunk) * B + row) * KC + col * 8) = pk;
+            }
+          }
+          if (tid < Ppad) al[tid] = 0.f;
+          __syncthreads();
+#pragma unroll 1
+          for (int fi = 0; fi < nfillP; ++fi) {
+            const int s = fi & 1;
+            const int px0 = fi * WPXS, cnt = min(WPXS, P - px0);
+            mbar_wait(pp.full[s], pp.use[s] & 1);
+            pp.use[s]++;
+            const uint8_t* base = stg + s * STAGE + col * 16;
+#pragma unroll
+            for (int u = 0; u < WPXS / GROUPS; ++u) {
+              const int pl = grp + u * GROUPS;          // warp-uniform
+              if (pl < cnt) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(base + (size_t)pl * CHUNK * 2);
+                float f[8];
+                unpack16(raw, f, bf16());
+                float sdot = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sdot = fmaf(f[k], dawe[k], sdot);
+                sdot = warp_sum(sdot);
+                if (lane == 0) atomicAdd(&al[px0 + pl], sdot);     // the two warps of a pixel group
+              }
+            }
+            if (fi + 2 < nfillP) {
+              __syncthreads();
+              const int pxn = (fi + 2) * WPXS;
+              stage_fill(pp, s, src + (int64_t)pxn * CHUNK, (uint32_t)min(WPXS, P - pxn) * CHUNK * 2);
+            }
+          }
+          __syncthreads();
+          if (tid < P) p.part[((int64_t)row * chunks + chunk) * Ppad + tid] = al[tid];
+          __syncthreads();
+        }
+      }
+      BSTAMP();
+      // ================= B: softmax backward + relu / score backward =================
+      // item = (row, quarter of the attention channels): the quarter-major copy att1_cm makes the
+      // item's P x 128 slab contiguous (two bulk copies), datt2 / dw_f of different quarters are
+      // disjoint, and every CTA redoes the row's tiny softmax backward
+      grid_arrive(p.bar);
+      {
+        constexpr int QW = 128;                                  // channels per item
+        constexpr int BPX = STAGE / (QW * 2);                    // pixels per fill (128)
+        const int quarters = A / QW;
+        const int items = n * quarters;
+        const bool live = (int)blockIdx.x < items;
+        const int row = blockIdx.x / quarters, qa = blockIdx.x - row * quarters;
+        const bf16* src = p.att1_cm + ((int64_t)row * quarters + qa) * P * QW;
+        const int nfillB = (P + BPX - 1) / BPX;
+        if (live) {
+          stage_fill(pp, 0, src, (uint32_t)min(BPX, P) * QW * 2);
+          if (nfillB > 1) stage_fill(pp, 1, src + (int64_t)BPX * QW, (uint32_t)min(BPX, P - BPX) * QW * 2);
+        }
+        grid_wait(p.bar, target);
+        BSTAMP();
+        if (live) {
+          // dalpha = sum of the channel-chunk partials (+ external); de = alpha (dalpha - alpha . dalpha)
+          float d = 0.f, alp = 0.f;
+          if (tid < P) {
+            for (int cc = 0; cc < chunks; ++cc) d += __ldcg(p.part + ((int64_t)row * chunks + cc) * Ppad + tid);
+            if (p.d_alphas) d += __ldg(p.d_alphas + ((int64_t)row * T + t) * P + tid);
+            alp = __ldg(p.alphas + ((int64_t)row * T + t) * P + tid);
+          }
+          float dot = warp_sum(alp * d);
+          if (lane == 0) red[warp] = dot;
+          __syncthreads();
+          dot = 0.f;
+#pragma unroll
+          for (int w = 0; w < RW; ++w) dot += red[w];
+          const float x = alp * (d - dot);
+          if (tid < P) {
+            des[tid] = x;
+            if (qa == 0) p.de[(tb + row) * Ppad + tid] = x;
+          }
+          float sde = warp_sum(tid < P ? x : 0.f);
+          if (lane == 0) red[RW + warp] = sde;
+          __syncthreads();
+          if (tid == 0 && qa == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < RW; ++w) tot += red[RW + w];
+            p.dbf[tb + row] = tot;
+          }
+          // warp per pixel, lane holds 4 attention features
+          const int a0 = qa * QW + lane * 4;
+          float att2[4], wf[4], dacc[4], wacc[4];
+          {
+            const float4 x2 = __ldg(reinterpret_cast<const float4*>(p.g1 + (tb + row) * NG1 + a0));
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w_f + a0));
+            att2[0] = x2.x; att2[1] = x2.y; att2[2] = x2.z; att2[3] = x2.w;
+            wf[0] = w4.x; wf[1] = w4.y; wf[2] = w4.z; wf[3] = w4.w;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { dacc[k] = 0.f; wacc[k] = 0.f; }
+#pragma unroll 1
+          for (int fi = 0; fi < nfillB; ++fi) {
+            const int s = fi & 1;
+            const int px0 = fi * BPX, cnt = min(BPX, P - px0);
+            mbar_wait(pp.full[s], pp.use[s] & 1);
+            pp.use[s]++;
+            const uint8_t* base = stg + s * STAGE + lane * 8;
+#pragma unroll 4
+            for (int pl = warp; pl < cnt; pl += RW) {
+              const float dep = des[px0 + pl];
+              const uint2 raw = *reinterpret_cast<const uint2*>(base + (size_t)pl * QW * 2);
+              const float f[4] = {__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                                  __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u)};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float pre = f[k] + att2[k];
+                const float on = pre > 0.f ? 1.f : 0.f;
+                dacc[k] = fmaf(dep * wf[k], on, dacc[k]);
+                wacc[k] = fmaf(dep, pre * on, wacc[k]);
+              }
+            }
+            if (fi + 2 < nfillB) {
+              __syncthreads();
+              const int pxn = (fi + 2) * BPX;
+              stage_fill(pp, s, src + (int64_t)pxn * QW, (uint32_t)min(BPX, P - pxn) * QW * 2);
+            }
+          }
+          __syncthreads();                                       // the staging buffers become the reduction scratch
+          float* slab = reinterpret_cast<float*>(stg);           // [RW][2][QW]
+          *reinterpret_cast<float4*>(slab + (warp * 2 + 0) * QW + lane * 4) = make_float4(dacc[0], dacc[1], dacc[2], dacc[3]);
+          *reinterpret_cast<float4*>(slab + (warp * 2 + 1) * QW + lane * 4) = make_float4(wacc[0], wacc[1], wacc[2], wacc[3]);
+          __syncthreads();
+          if (tid < 2 * QW) {
+            const int which = tid / QW, aa = tid - which * QW;
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < RW; ++w) sum += slab[(w * 2 + which) * QW + aa];
+            const int a = qa * QW + aa;
+            if (which == 0) {
+              const bf16 xb = __float2bfloat16_rn(sum);
+              p.dpx[(tb + row) * p.ldPX + NQ + E + a] = xb;
+              p.dpxk[(((int64_t)t * nkc + nkq + chunks) * B + row) * KC + a] = xb;
+            } else {
+              p.dwf[(tb + row) * A + a] = sum;
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+    BSTAMP();
+    grid_arrive(p.bar);
+    grid_wait(p.bar, target);
+    BSTAMP();
+    // ================= H: dh_{t-1} += [dp | dbeta_pre | datt2] chunk . W_hx chunk^T =================
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+      const int j = c + i * gridDim.x;
+      if (j < jobsH) {
+        const int ds = j / nkc, kc = j - ds * nkc;
+        float out[1];
+        gemm_job<1, 2>(pp, p.dpxk + ((int64_t)t * nkc + kc) * B * KC, 0, n, WHs + (size_t)i * 16 * wHs, wHs, 1, red, out);
+        const int d = ds * 16 + ej;
+        if (erow < n && d < D) atomicAdd(p.dh_rec + (tb + erow) * D + d, out[0]);
+      }
+    }
+    BSTAMP();
+    grid_arrive(p.bar);
+    grid_wait(p.bar, target);
+    BSTAMP();
+  }
+#undef BSTAMP
+}
+
+// dst[b][c][p][j] = src[b][p][c*cw + j]: every (pixel, cw-channel chunk) run becomes contiguous with its
+// neighbours in p, so that a staging fill of the persistent kernels is ONE bulk copy
+__global__ void chunk_major_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int P, int E, int cw) {
+  const int vpr = E / 8, vpc = cw / 8, chunks = E / cw;
   const int64_t total = (int64_t)B * P * vpr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t bp = i / vpr;
@@ -619,6 +1018,10 @@ int pick_nt(int tiles, int ctas) {
   if (tiles <= 4 * ctas) return 4;
   return 0;
 }
+
+bool g_timing = false;
+cudaEvent_t g_ev[2] = {nullptr, nullptr};
+bool g_timed = false;
 
 bool persistent_enabled() {
   const char* s = getenv("CAPDEC_PERSISTENT");      // read per call: tests flip it
@@ -675,7 +1078,7 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   CAPDEC_REQUIRE(per_sm >= 1, CAPDEC_ERR_CUDA, "recur_fwd: kernel does not fit one CTA per SM (smem %zu)", smem);
   CAPDEC_REQUIRE(a.ldH0 == a.D, CAPDEC_ERR_BAD_SHAPE, "recur_fwd: H0 must be dense");
   if (a.att) {
-    chunk_major_kernel<<<di->sms * 8, 256, 0, st>>>((const uint4*)a.enc, (uint4*)a.enc_cm, a.B, a.P, a.E);
+    chunk_major_kernel<<<di->sms * 8, 256, 0, st>>>((const uint4*)a.enc, (uint4*)a.enc_cm, a.B, a.P, a.E, CHUNK);
     CAPDEC_LAUNCH_OK();
   }
   CAPDEC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 4, st));
@@ -698,8 +1101,19 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
     CAPDEC_CUDA_OK(cudaMalloc(&p.prof, (size_t)(a.T * 16 + 64) * sizeof(long long)));
     CAPDEC_CUDA_OK(cudaMemsetAsync(p.prof, 0, (size_t)(a.T * 16 + 64) * sizeof(long long), st));
   }
+  if (g_timing) {
+    if (!g_ev[0]) {
+      CAPDEC_CUDA_OK(cudaEventCreate(&g_ev[0]));
+      CAPDEC_CUDA_OK(cudaEventCreate(&g_ev[1]));
+    }
+    CAPDEC_CUDA_OK(cudaEventRecord(g_ev[0], st));
+  }
   CAPDEC_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
   count_launch();
+  if (g_timing) {
+    CAPDEC_CUDA_OK(cudaEventRecord(g_ev[1], st));
+    g_timed = true;
+  }
   if (prof) {
     // debug only: synchronises.  Prints per-phase cycles of CTA 0 (work, barrier wait) for a few steps.
     std::vector<long long> h((size_t)a.T * 16 + 64);
@@ -713,6 +1127,112 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
     }
   }
   return CAPDEC_OK;
+}
+
+namespace {
+size_t bwd_smem_bytes(const RecurBwdArgs& a) {
+  size_t s = 2 * (size_t)STAGE;
+  s += (size_t)32 * (a.D * 2 + WPAD);
+  if (a.att) s += (size_t)16 * (4 * a.F * 2 + WPAD);
+  s += (size_t)32 * (KC * 2 + WPAD);
+  s += (size_t)KSL * 32 * REDLD * 4;
+  s += (size_t)2 * pad4i(a.P > 0 ? a.P : 4) * 4;
+  s += (size_t)(((a.B + 3) & ~3) + 2) * 4;
+  return s + 8 + 2 * 8 + 128;
+}
+
+bool plan_bwd(const RecurBwdArgs& a, const DevInfo* di, size_t* smem) {
+  if (!di || !di->coop || di->sms < 8) return false;
+  if (a.B < 1 || a.B > 32 || a.T < 1) return false;
+  if (a.D != KC || a.F % 16 || (4 * a.F) % KC) return false;
+  if (a.att && (a.E % KC || a.A != KC || a.P < 1 || a.P > RT)) return false;
+  const int NQ = 4 * a.F, KH = NQ + (a.att ? a.E + a.A : 0);
+  if (4 * (2 * a.F / 32) > di->sms) return false;               // W job: one 32-feature slice per CTA
+  if (a.att && a.E / 16 > di->sms) return false;                // Z job: 16 features per CTA
+  if ((a.D / 16) * (KH / KC) > 2 * di->sms) return false;       // H jobs: at most two per CTA
+  // red also holds the [2][A] accumulators of phase B
+  if (a.att && 4 * a.A / 128 * a.B > 4 * di->sms) return false;  // B items: one (row, quarter) per CTA
+  if (a.att && a.B * (a.A / 128) > di->sms) return false;
+  *smem = bwd_smem_bytes(a);
+  return *smem <= (size_t)di->smem_optin;
+}
+}  // namespace
+
+bool recur_bwd_supported(const RecurBwdArgs& a) {
+  if (!persistent_enabled()) return false;
+  size_t smem;
+  return plan_bwd(a, dev_info(), &smem);
+}
+
+int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
+  const DevInfo* di = dev_info();
+  size_t smem;
+  CAPDEC_REQUIRE(plan_bwd(a, di, &smem), CAPDEC_ERR_BAD_SHAPE, "recur_bwd: shape not covered by the persistent kernel");
+  BwdP p;
+  memset(&p, 0, sizeof p);
+  p.B = a.B; p.T = a.T; p.P = a.P; p.E = a.E; p.A = a.A; p.M = a.M; p.D = a.D; p.F = a.F;
+  p.NQ = 4 * a.F; p.NG1 = (a.att ? a.A + a.E : 0) + p.NQ; p.R = (int64_t)a.B * a.T; p.ldPX = a.ldPX;
+  p.len = a.len; p.WcT = (const bf16*)a.WcT; p.ldD = a.ldD; p.Wxin = (const bf16*)a.Wxin; p.ldNQ = a.ldNQ;
+  p.Whx = (const bf16*)a.Whx; p.ldhx = a.ldhx; p.dHfc = a.dHfc; p.gates = a.gates; p.C = a.C; p.dc = a.dc;
+  p.dh_rec = a.dh_rec; p.dpre = (bf16*)a.dpre; p.dpre_gm = (bf16*)a.dpre_gm; p.U = a.U; p.g1 = a.g1; p.v = a.v;
+  p.q = a.q; p.du = (bf16*)a.du; p.duk = (bf16*)a.duk; p.dpx = (bf16*)a.dpx; p.dpxk = (bf16*)a.dpxk;
+  p.dv_acc = a.dv_acc; p.dq_acc = a.dq_acc; p.dz = a.dz; p.awe = a.awe; p.alphas = a.alphas; p.d_alphas = a.d_alphas;
+  p.enc_cm = (const bf16*)a.enc_cm; p.att1_cm = (const bf16*)a.att1_cm; p.w_f = a.w_f; p.part = a.part; p.de = a.de;
+  p.dwf = a.dwf; p.dbf = a.dbf; p.bar = a.bar; p.dropout_p = a.dropout_p; p.seed = a.seed;
+  auto kernel = a.att ? recur_bwd_kernel<true> : recur_bwd_kernel<false>;
+  CAPDEC_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CAPDEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RT, smem));
+  CAPDEC_REQUIRE(per_sm >= 1, CAPDEC_ERR_CUDA, "recur_bwd: kernel does not fit one CTA per SM (smem %zu)", smem);
+  if (a.att && a.build_enc_cm) {      // the forward ran the per-step path: the chunk-major feature copy is missing
+    chunk_major_kernel<<<di->sms * 8, 256, 0, st>>>((const uint4*)a.enc, (uint4*)a.enc_cm, a.B, a.P, a.E, CHUNK);
+    CAPDEC_LAUNCH_OK();
+  }
+  if (a.att) {
+    chunk_major_kernel<<<di->sms * 4, 256, 0, st>>>((const uint4*)a.att1, (uint4*)a.att1_cm, a.B, a.P, a.A, 128);
+    CAPDEC_LAUNCH_OK();
+  }
+  CAPDEC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 4, st));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(di->sms, 1, 1);
+  cfg.blockDim = dim3(RT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const char* prof_env = getenv("CAPDEC_RECUR_PROF");
+  const bool prof = prof_env && prof_env[0] == '1';
+  if (prof) {
+    CAPDEC_CUDA_OK(cudaMalloc(&p.prof, (size_t)a.T * 16 * sizeof(long long)));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(p.prof, 0, (size_t)a.T * 16 * sizeof(long long), st));
+  }
+  CAPDEC_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
+  count_launch();
+  if (prof) {
+    std::vector<long long> h((size_t)a.T * 16);
+    CAPDEC_CUDA_OK(cudaStreamSynchronize(st));
+    CAPDEC_CUDA_OK(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.prof);
+    for (int t = 0; t < a.T; t += (a.T > 8 ? a.T / 4 : 1)) {
+      fprintf(stderr, "recur_bwd prof t=%d:", t);
+      for (int k = 1; k < 16 && h[t * 16 + k]; ++k) fprintf(stderr, " %lld", h[t * 16 + k] - h[t * 16 + k - 1]);
+      fprintf(stderr, "\n");
+    }
+  }
+  return CAPDEC_OK;
+}
+
+void recur_timing(int enable) { g_timing = enable != 0; if (!enable) g_timed = false; }
+float recur_last_ms() {
+  if (!g_timed) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(g_ev[1]) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, g_ev[0], g_ev[1]) != cudaSuccess) return -1.f;
+  return ms;
 }
 
 }  // namespace capdec

@@ -5,16 +5,16 @@ set -u
 TAG=${1:-r1}
 OUT=gpurun_out
 mkdir -p $OUT
-python -m pytest tests -m gpu -q 2>&1 | grep -v "^E  *+\|tensor(\[" | tail -25 > $OUT/${TAG}_tests.log
-python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1
-python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench_train.json 2> $OUT/${TAG}_bench_train.err
-python bench.py --workload attention_scn_decode --steps 3 --warmup 3 > $OUT/${TAG}_bench_decode.json 2> $OUT/${TAG}_bench_decode.err
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -v "^E  *+\|tensor(\[" | tail -25 > $OUT/${TAG}_tests.log
+timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1
+timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench_train.json 2> $OUT/${TAG}_bench_train.err
+timeout 600 python bench.py --workload attention_scn_decode --steps 3 --warmup 3 > $OUT/${TAG}_bench_decode.json 2> $OUT/${TAG}_bench_decode.err
 if [ "${2:-}" != "quick" ]; then
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_plain.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
+  timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_plain.log 2>&1 &&
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
       --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu.log 2>&1
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'attn_scores|attn_wsum|attn_bwd|gemm_tc_kernel' -s 700 -c 16 \
+  timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_plain2.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'recur_fwd_kernel|attn_bwd_a|attn_bwd_b|attn_scores|attn_wsum' -s 6 -c 10 \
       -f -o $OUT/${TAG}_prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu2.log 2>&1
 fi
 tail -5 $OUT/${TAG}_tests.log; cat $OUT/${TAG}_smoke.log | tail -3; cat $OUT/${TAG}_bench_train.json $OUT/${TAG}_bench_decode.json; tail -3 $OUT/${TAG}_bench_decode.err
