@@ -198,6 +198,14 @@ int capdec_gemm(int precision, const void* X, int64_t ldx, const void* W, int64_
                 int rows, int N, int K, int batch, int64_t sX, int64_t sW, int64_t sO,
                 int splitk, void* stream);
 
+/* Weight-gradient product on TRANSPOSED bf16 operands (tcgen05 engine, MN-major UMMA descriptors):
+ *   out[r, n] (fp32, ldo) = sum_k XT[k, r] * WT[k, n]      XT [K][rows] pitch ldx, WT [K][N] pitch ldw.
+ * This is dW = dY^T X of an nn.Linear whose inputs X and output gradients dY are stored row = sample
+ * (what torch autograd computes for the reference's `@` / nn.Linear weights) without a transposition
+ * pass.  batch > 1: element strides sX / sW / sO between the batch members. */
+int capdec_gemm_tn(const void* XT, int64_t ldx, const void* WT, int64_t ldw, float* out, int64_t ldo,
+                   int rows, int N, int K, int batch, int64_t sX, int64_t sW, int64_t sO, void* stream);
+
 /* Scratch floats capdec_attention_step needs for `rows` rows; capdec_attention_bwd_step needs this
  * plus rows * ((P + 3) & ~3). */
 size_t capdec_attention_scratch_floats(int precision, int rows, int P, int E);

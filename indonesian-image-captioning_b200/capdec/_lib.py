@@ -52,6 +52,7 @@ SIGNATURES = {
                                 C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "capdec_gemm": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i64,
                          _i64, _i64, _i, _vp]),
+    "capdec_gemm_tn": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i64, _i64, _i64, _vp]),
     "capdec_attention_scratch_floats": (_sz, [_i, _i, _i, _i]),
     "capdec_attention_step": (_i, [_i, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i,
                                    _i, _i, _i, _vp, _vp]),

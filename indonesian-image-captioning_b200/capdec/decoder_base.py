@@ -56,14 +56,17 @@ class CaptionDecoderBase(nn.Module):
             enc = enc.float()
         lens, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True)   # same op as :117-118
         caps_sorted = encoded_captions[sort_ind].contiguous()
-        decode_lengths = (lens - 1).tolist()                       # host sync, as upstream (:131)
+        # everything that does not need the lengths on the host comes BEFORE the sync below: after it the
+        # GPU is idle until the first launch
         tags = None
         if self.kind != "pure_attention":
             tags = semantic_input.detach().float().contiguous()    # NOT permuted (App. C-1)
         p = self.dropout.p if self.training else 0.0
         seed = int(torch.empty((), dtype=torch.int64).random_().item()) if p > 0 else 0
-        out, meta = CF.decoder_forward(self.kind, self._param_list(), enc.detach(), tags, caps_sorted,
-                                       sort_ind, decode_lengths, dims_kw=self._dims_kw(), dropout_p=p,
+        params, dims_kw, enc_d = self._param_list(), self._dims_kw(), enc.detach()
+        decode_lengths = (lens - 1).tolist()                       # host sync, as upstream (:131)
+        out, meta = CF.decoder_forward(self.kind, params, enc_d, tags, caps_sorted,
+                                       sort_ind, decode_lengths, dims_kw=dims_kw, dropout_p=p,
                                        seed=seed)
         if self.kind == "pure_scn":
             predictions, alphas = out, None

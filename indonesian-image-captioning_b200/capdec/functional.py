@@ -107,6 +107,11 @@ class _Plan:
         self.predictions = torch.empty(B, T, V, dtype=torch.float32, device=dev)
         self.alphas = None if kind == "pure_scn" else torch.empty(B, T, P, dtype=torch.float32, device=dev)
         self.len_h = (C.c_int32 * B)(*decode_lengths)
+        self.len_list = [int(x) for x in decode_lengths]
+        # device copy of the lengths for the fused loss: pinned + non_blocking, so that nothing on the
+        # host waits for the stream (a pageable torch.tensor(..., device=) copy would block until the
+        # forward graph has drained and expose the whole host cost of loss + backward)
+        self.len_d = torch.tensor(self.len_list, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
         self.params = params
         self.pstruct = _params_struct(kind, params)
         self.flat_grads = None
@@ -377,7 +382,11 @@ def caption_loss(scores, caps_sorted, decode_lengths, alphas=None, alpha_c=1.0, 
     else:
         dims = make_dims("attention_scn" if alphas is not None else "pure_scn",
                          precision or get_precision(), B, T, P, 8, 8, 8, 8, 8, 8, V, caps_sorted.shape[1])
-    len_d = torch.tensor(list(decode_lengths), dtype=torch.int32, device=scores.device)
+    plan = meta.get("plan") if meta is not None else None
+    if plan is not None and plan.len_list == [int(x) for x in decode_lengths]:
+        len_d = plan.len_d                      # staged by the forward: no blocking host-to-device copy here
+    else:
+        len_d = torch.tensor(list(decode_lengths), dtype=torch.int32, device=scores.device)
     n_tokens = int(sum(decode_lengths)) if n_tokens is None else int(n_tokens)
     return FusedLossFn.apply(scores, alphas, caps_sorted, len_d, n_tokens, float(alpha_c), dims, meta)
 
@@ -413,6 +422,25 @@ def gemm(X, W, bias=None, addm=None, out_ft=False, precision=None, splitk=0, out
                              _lib.ptr(addm), addm.stride(-2) if addm is not None else 0, rows, N, K,
                              batch, sX, sW, sO, splitk, _stream())
     _lib.check(rc, "capdec_gemm")
+    return out
+
+
+def gemm_tn(XT, WT, out=None):
+    """out[r,n] = sum_k XT[k,r] WT[k,n] on transposed bf16 operands (weight-gradient products): the tcgen05
+    engine with MN-major operand descriptors, no transposition pass.  XT (K,rows) / WT (K,N), last dim
+    contiguous, 16-byte pitch."""
+    lib = _lib.load()
+    _require_cuda(XT, WT)
+    assert XT.dtype == torch.bfloat16 and WT.dtype == torch.bfloat16 and XT.stride(-1) == 1 and WT.stride(-1) == 1
+    K, rows = XT.shape
+    N = WT.shape[1]
+    assert WT.shape[0] == K
+    if out is None:
+        out = torch.empty(rows, N, dtype=torch.float32, device=XT.device)
+    with torch.cuda.device(XT.device):
+        rc = lib.capdec_gemm_tn(_lib.ptr(XT), XT.stride(0), _lib.ptr(WT), WT.stride(0), _lib.ptr(out), out.stride(0),
+                                rows, N, K, 1, 0, 0, 0, _stream())
+    _lib.check(rc, "capdec_gemm_tn")
     return out
 
 

@@ -160,6 +160,17 @@ int capdec_gemm(int precision, const void* X, int64_t ldx, const void* W, int64_
   return gemm(precision, a, (cudaStream_t)stream);
 }
 
+int capdec_gemm_tn(const void* XT, int64_t ldx, const void* WT, int64_t ldw, float* out, int64_t ldo,
+                   int rows, int N, int K, int batch, int64_t sX, int64_t sW, int64_t sO, void* stream) {
+  CAPDEC_REQUIRE(XT && WT && out && rows > 0 && N > 0 && K > 0, CAPDEC_ERR_BAD_ARG, "capdec_gemm_tn: bad argument");
+  CAPDEC_TRY(capdec_init());
+  GemmArgs a;
+  a.tn = 3;
+  a.X = XT; a.ldx = ldx; a.W = WT; a.ldw = ldw; a.out = out; a.ldo = ldo; a.rows = rows; a.N = N; a.K = K;
+  a.batch = batch < 1 ? 1 : batch; a.sX = sX; a.sW = sW; a.sO = sO;
+  return gemm(CAPDEC_BF16, a, (cudaStream_t)stream);
+}
+
 size_t capdec_attention_scratch_floats(int precision, int rows, int P, int E) {
   return attention_scratch_floats(precision, rows, P, E);
 }

@@ -238,6 +238,9 @@ struct GemmArgs {
                                                  // in-place addend).  Ignored by the SIMT engine.
   int batch = 1;                                 // grid.z
   int64_t sX = 0, sW = 0, sO = 0, sBias = 0, sAdd = 0;   // element strides per batch index
+  int tn = 0;                                    // bit 0: W is given transposed, W^T [K][N] (pitch ldw); bit 1: X is,
+                                                 // X^T [K][rows] (pitch ldx).  3: out[r, n] = sum_k XT[k, r] WT[k, n]
+                                                 // (weight-gradient products; tcgen05 engine, EPI_PLAIN only)
   int epi = EPI_PLAIN;                           // tcgen05 engine only
   // fused modes: fp32 accumulation buffer, element (acc, z, r, n) at abuf[z*a_sz + acc*a_sa + r*a_ld + n]
   // (default: `out`), and the per-tile ticket counters (>= #tiles ints, zero on entry, left zero)

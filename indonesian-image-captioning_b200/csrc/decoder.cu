@@ -201,6 +201,7 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
     grow(tB, (size_t)E * p->ldB * f);
     if (p->att) {
       grow(tA, (size_t)A * p->ldBP * f);
+      grow(tA, (size_t)B * P * p->ldA * f);          // bf16 copy of dAtt1 [B*P][A] (transposed-operand GEMM)
       grow(tB, (size_t)E * p->ldBP * f);
     }
     o.tA = take(tA);
@@ -229,6 +230,16 @@ int G_(const Ctx& c, const void* X, int64_t ldx, const void* W, int64_t ldw, voi
   a.bias = bias; a.addm = addm; a.ldadd = ldadd; a.rows = rows; a.N = N; a.K = K;
   a.rows_alloc = rows_alloc; a.batch = batch; a.sX = sX; a.sW = sW; a.sO = sO; a.splitk = splitk;
   return gemm(c.prec, a, c.st);
+}
+
+// tcgen05 engine with transposed operand(s) (bf16 only): tn bit 0 = W is W^T [K][N], bit 1 = X is X^T [K][rows]
+int GT_(const Ctx& c, int tn, const void* X, int64_t ldx, const void* W, int64_t ldw, float* out, int64_t ldo,
+        int rows, int N, int K, int batch = 1, int64_t sX = 0, int64_t sW = 0, int64_t sO = 0) {
+  GemmArgs a;
+  a.tn = tn;
+  a.X = X; a.ldx = ldx; a.W = W; a.ldw = ldw; a.out = out; a.ldo = ldo; a.rows = rows; a.N = N; a.K = K;
+  a.batch = batch; a.sX = sX; a.sW = sW; a.sO = sO;
+  return gemm(CAPDEC_BF16, a, c.st);
 }
 
 // fp32 master weights -> packed feature-type operands ([N_out][K] , K contiguous)
@@ -548,10 +559,16 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   // dH_fc[(b,t), :] = dlogits . W_fc
   CAPDEC_TRY(G_(c, dlog, lddl, c.at(o.Wp_fcT), p.ldV, c.at(o.dHfc), D, 0, nullptr, nullptr, 0, (int)R, D, V));
   // fc.weight.grad = dlogits^T . dropout(H) ; fc.bias.grad = colsum(dlogits)     (rows in (b,t) order)
-  CAPDEC_TRY(transpose_cast(pr, dlog, 1, c.at(o.tA), 1, 1, (int)R, V, 0, lddl, p.ldR, 0, 1, st));
-  CAPDEC_TRY(transpose_cast(pr, drop ? c.at(o.Hd) : c.at(o.Hall), 1, c.at(o.tB), 1, 1, (int)R, D, 0, D,
-                            p.ldR, 0, 1, st));
-  CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.fc_w, D, 0, nullptr, nullptr, 0, V, D, (int)R));
+  // bf16: the operands stay as they are ([sample][feature]) -- transposed-operand GEMM, no transposition pass
+  const bool tn = pr == CAPDEC_BF16;
+  if (tn) {
+    CAPDEC_TRY(GT_(c, 3, dlog, lddl, drop ? c.at(o.Hd) : c.at(o.Hall), D, g.fc_w, D, V, D, (int)R));
+  } else {
+    CAPDEC_TRY(transpose_cast(pr, dlog, 1, c.at(o.tA), 1, 1, (int)R, V, 0, lddl, p.ldR, 0, 1, st));
+    CAPDEC_TRY(transpose_cast(pr, drop ? c.at(o.Hd) : c.at(o.Hall), 1, c.at(o.tB), 1, 1, (int)R, D, 0, D,
+                              p.ldR, 0, 1, st));
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.fc_w, D, 0, nullptr, nullptr, 0, V, D, (int)R));
+  }
   CAPDEC_TRY(colsum(pr, dlog, 1, lddl, (int)R, V, g.fc_b, 0, st));
 
   const int SK = pr == CAPDEC_BF16 ? -1 : 0;
@@ -750,6 +767,33 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   // bias_ih.grad == bias_hh.grad = colsum(dpre)
   CAPDEC_TRY(colsum(pr, c.at(o.dpre), 1, 4 * D, Ri, 4 * D, g.b_ih, 0, st));
   CAPDEC_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * D * 4, cudaMemcpyDeviceToDevice, st));
+  if (tn) {
+    if (p.scn) {
+      // weight_ic.grad[:, gF:(g+1)F] = dpre_g^T . (u_g*v_g) ; weight_hc.grad likewise with (p_g*q_g)
+      CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), 4 * D, c.at(o.m), 2 * F, g.w_ic, NQ, D, F, Ri, 4, D, R * 2 * F, F));
+      CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), 4 * D, c.ft(o.m, F), 2 * F, g.w_hc, NQ, D, F, Ri, 4, D, R * 2 * F, F));
+      // weight_ha.grad [D][4F] = H_prev^T . dp
+      CAPDEC_TRY(GT_(c, 1, c.at(o.tC), p.ldR, dp_all, lddp, g.w_ha, NQ, D, NQ, Ri));
+      // weight_ia.grad [X][4F] = [Xe | z]^T . du
+      CAPDEC_TRY(GT_(c, 3, c.at(o.Xe), p.ldM, c.at(o.du), NQ, g.w_ia, NQ, M, NQ, Ri));
+      if (p.att)
+        CAPDEC_TRY(GT_(c, 3, c.at(o.z), E, c.at(o.du), NQ, g.w_ia + (int64_t)M * NQ, NQ, E, NQ, Ri));
+      // embedding.weight.grad: dXe = du . W_ia[:M]^T, scattered to the consumed token rows
+      CAPDEC_TRY(G_(c, c.at(o.du), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
+      // weight_ib.grad [S][4F] = s^T . sum_t dv ; weight_hb.grad = s^T . sum_t dq   (B rows: tiny)
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.tagsF), 1, c.at(o.tA), 1, 1, B, S, 0, p.ldS, p.ldB, 0, 1, st));
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.dv_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
+      CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_ib, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.dq_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
+      CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_hb, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
+    } else {
+      // LSTM: weight_hh.grad [4D][D] = dpre^T . H_prev ; weight_ih.grad [4D][X] = dpre^T . [Xe | z]
+      CAPDEC_TRY(GT_(c, 2, c.at(o.dpre), NQ, c.at(o.tC), p.ldR, g.w_ha, D, NQ, D, Ri));
+      CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), NQ, c.at(o.Xe), p.ldM, g.w_ia, X, NQ, M, Ri));
+      if (p.att) CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), NQ, c.at(o.z), E, g.w_ia + M, X, NQ, E, Ri));
+      CAPDEC_TRY(G_(c, c.at(o.dpre), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
+    }
+  } else {
   // dpre^T [4D][R]
   CAPDEC_TRY(transpose_cast(pr, c.at(o.dpre), 1, c.at(o.tA), 1, 1, Ri, 4 * D, 0, 4 * D, p.ldR, 0, 1, st));
   if (p.scn) {
@@ -795,6 +839,7 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     }
     CAPDEC_TRY(G_(c, c.at(o.dpre), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
   }
+  }
   if (g.emb) {
     CAPDEC_CUDA_OK(cudaMemsetAsync(g.emb, 0, (size_t)V * M * 4, st));
     CAPDEC_TRY(embedding_scatter_add(c.at<float>(o.dXe), M, c.at<int64_t>(o.capsD), d.L, c.at<int32_t>(o.lenD), g.emb, B, T,
@@ -803,10 +848,15 @@ int backward(const CapdecDims& d, const CapdecParams& w,
 
   if (p.att) {
     // f_beta / decoder_att: [dbeta_pre | datt2]^T . H_prev
-    CAPDEC_TRY(transpose_cast(pr, dba_all, 1, c.at(o.tA), 1, 1, Ri, E + A, 0, lddba, p.ldR, 0, 1, st));
-    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tC), p.ldR, g.f_beta_w, D, 0, nullptr, nullptr, 0, E, D, Ri));
-    CAPDEC_TRY(G_(c, c.ft(o.tA, (int64_t)E * p.ldR), p.ldR, c.at(o.tC), p.ldR, g.dec_att_w, D, 0, nullptr,
-                 nullptr, 0, A, D, Ri));
+    if (tn) {
+      CAPDEC_TRY(GT_(c, 2, dba_all, lddba, c.at(o.tC), p.ldR, g.f_beta_w, D, E, D, Ri));
+      CAPDEC_TRY(GT_(c, 2, (const uint8_t*)dba_all + (size_t)E * p.fsz, lddba, c.at(o.tC), p.ldR, g.dec_att_w, D, A, D, Ri));
+    } else {
+      CAPDEC_TRY(transpose_cast(pr, dba_all, 1, c.at(o.tA), 1, 1, Ri, E + A, 0, lddba, p.ldR, 0, 1, st));
+      CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tC), p.ldR, g.f_beta_w, D, 0, nullptr, nullptr, 0, E, D, Ri));
+      CAPDEC_TRY(G_(c, c.ft(o.tA, (int64_t)E * p.ldR), p.ldR, c.at(o.tC), p.ldR, g.dec_att_w, D, 0, nullptr,
+                   nullptr, 0, A, D, Ri));
+    }
     CAPDEC_TRY(colsum(pr, dba_all, 1, lddba, Ri, E, g.f_beta_b, 0, st));
     CAPDEC_TRY(colsum(pr, (const uint8_t*)dba_all + (size_t)E * p.fsz, 1, lddba, Ri, A, g.dec_att_b, 0, st));
     // full_att: per-row partials reduced over all (t,b)
@@ -818,9 +868,14 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     // encoder_att: dAtt1^T . enc  (K = B*P pixel rows)
     const int BP = B * P;
     CAPDEC_TRY(colsum(pr, c.at(o.dAtt1), 0, A, BP, A, g.enc_att_b, 0, st));
-    CAPDEC_TRY(transpose_cast(pr, c.at(o.dAtt1), 0, c.at(o.tA), 1, 1, BP, A, 0, A, p.ldBP, 0, 1, st));
-    CAPDEC_TRY(transpose_cast(pr, c.at(o.enc_s), 1, c.at(o.tB), 1, 1, BP, E, 0, E, p.ldBP, 0, 1, st));
-    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldBP, c.at(o.tB), p.ldBP, g.enc_att_w, E, 0, nullptr, nullptr, 0, A, E, BP));
+    if (tn) {
+      CAPDEC_TRY(copy_cast(pr, c.at(o.dAtt1), 0, A, c.at(o.tA), 1, p.ldA, BP, A, st));      // fp32 -> bf16, same layout
+      CAPDEC_TRY(GT_(c, 3, c.at(o.tA), p.ldA, c.at(o.enc_s), E, g.enc_att_w, E, A, E, BP));
+    } else {
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.dAtt1), 0, c.at(o.tA), 1, 1, BP, A, 0, A, p.ldBP, 0, 1, st));
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.enc_s), 1, c.at(o.tB), 1, 1, BP, E, 0, E, p.ldBP, 0, 1, st));
+      CAPDEC_TRY(G_(c, c.at(o.tA), p.ldBP, c.at(o.tB), p.ldBP, g.enc_att_w, E, 0, nullptr, nullptr, 0, A, E, BP));
+    }
   }
   // init_h / init_c: dh0 = dh_rec, dc0 = dc after the last reverse step
   CAPDEC_TRY(transpose_cast(pr, c.at(o.mean), 0, c.at(o.tB), 1, 1, B, E, 0, E, p.ldB, 0, 1, st));

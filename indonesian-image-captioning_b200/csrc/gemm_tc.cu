@@ -113,6 +113,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
+// MN-major, 128B-swizzled operand tile (the contraction index k is the SLOW dimension in memory):
+// 64 MN-elements (128 B) contiguous, 8 k-rows per swizzle atom (1024 B), k-groups SBO = 1024 B apart,
+// 64-wide MN blocks LBO = 8192 B apart (one TMA box {64 mn, 64 k} each).  Canonical layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (CUTLASS make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(8192 >> 4) << 16;                 // LBO: next 64-wide MN block
+  d |= (uint64_t)(1024 >> 4) << 32;                 // SBO: next group of 8 k-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+
 template <int BNR, int NACC>
 struct Cfg {
   // 3 stages for the 128-row tile: 96 KB per CTA, so TWO CTAs share an SM and one tile's prologue /
@@ -232,7 +246,10 @@ __device__ __forceinline__ void epilogue_elem(const KArgs& a, int z, int r, int 
   }
 }
 
-template <int BNR, int NACC, int EPI>
+// TN: bit 0 = the W operand is given TRANSPOSED (W^T [K][N]), bit 1 = the X operand is (X^T [K][rows]) --
+// the layout of a weight-gradient product dW = dY^T X, whose contraction runs over the sample rows:
+// MN-major UMMA operands, no explicit transposition pass.
+template <int BNR, int NACC, int EPI, int TN = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
                const __grid_constant__ KArgs a) {
@@ -295,8 +312,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         const uint32_t full = smem_u32(&bars[s]);
         mbar_expect_tx(full, C::STAGE_BYTES);
         const uint32_t ws = smem_u32(smem + s * C::STAGE_BYTES);
-        tma_load_3d(ws, &mapW, full, kb * BK, n0, zz);
-        tma_load_3d(ws + C::W_BYTES, &mapX, full, kb * BK, r0, zz);
+        if (TN & 1) {
+#pragma unroll
+          for (int h = 0; h < BM / 64; ++h) tma_load_3d(ws + h * 8192, &mapW, full, n0 + h * 64, kb * BK, zz);
+        } else {
+          tma_load_3d(ws, &mapW, full, kb * BK, n0, zz);
+        }
+        if (TN & 2) {
+#pragma unroll
+          for (int h = 0; h < BNR / 64; ++h) tma_load_3d(ws + C::W_BYTES + h * 8192, &mapX, full, r0 + h * 64, kb * BK, zz);
+        } else {
+          tma_load_3d(ws + C::W_BYTES, &mapX, full, kb * BK, r0, zz);
+        }
       }
     }
   } else if (warp == 1) {
@@ -304,7 +331,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       // ------------------------- MMA issuer -------------------------
       // instruction descriptor: D=F32, A=B=BF16, both K-major, N=BNR, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNR >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BM >> 4) << 24) | ((TN & 1) ? (1u << 15) : 0u) |          // a major = MN
+                             ((TN & 2) ? (1u << 16) : 0u);                                        // b major = MN
       for (int u = 0; u < nunits; ++u) {
         const int s = u % C::STAGES;
         const uint32_t ph = (u / C::STAGES) & 1;
@@ -313,13 +341,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         mbar_wait(smem_u32(&bars[s]), ph);
         tc_fence_after();
         const uint32_t ws = smem_u32(smem + s * C::STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc(ws);
-        const uint64_t bdesc = make_smem_desc(ws + C::W_BYTES);
+        const uint64_t adesc = (TN & 1) ? make_smem_desc_mn(ws) : make_smem_desc(ws);
+        const uint64_t bdesc = (TN & 2) ? make_smem_desc_mn(ws + C::W_BYTES) : make_smem_desc(ws + C::W_BYTES);
+        // K-major: 16 elements = 32 bytes along K inside the swizzle atom (+2 in the (addr >> 4) field);
+        // MN-major: 16 k-rows = two 1024-byte atoms (+128)
+        constexpr int ASTEP = (TN & 1) ? 128 : 2, BSTEP = (TN & 2) ? 128 : 2;
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the
-          // (addr >> 4) start-address field
-          umma_bf16(tmem_base + (uint32_t)(acc * BNR), adesc + 2 * k, bdesc + 2 * k, idesc,
+          umma_bf16(tmem_base + (uint32_t)(acc * BNR), adesc + ASTEP * k, bdesc + BSTEP * k, idesc,
                     (kb_rel | k) != 0);
         }
         umma_commit(smem_u32(&bars[C::STAGES + s]));     // frees the smem stage when MMAs retire
@@ -441,7 +470,7 @@ std::once_flag g_once;
 int g_init_rc = CAPDEC_OK;
 
 struct MapKey {
-  const void* p; int64_t ld, sb; int rows, K, batch, box;
+  const void* p; int64_t ld, sb; int rows, K, batch, box;     // box < 0: transposed operand [K][rows]
   bool operator==(const MapKey& o) const {
     return p == o.p && ld == o.ld && sb == o.sb && rows == o.rows && K == o.K && batch == o.batch &&
            box == o.box;
@@ -471,9 +500,13 @@ int get_map(const void* p, int64_t ld, int rows, int K, int batch, int64_t sb, i
                  CAPDEC_ERR_BAD_SHAPE,
                  "gemm_tc: operand needs 16-byte aligned base/pitch (ptr=%p ld=%lld sb=%lld)", p,
                  (long long)ld, (long long)sb);
-  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
-  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch == 1 ? (int64_t)rows * ld : sb) * 2};
-  cuuint32_t box3[3] = {(cuuint32_t)BK, (cuuint32_t)box, 1};
+  // box > 0: operand [rows][K], K contiguous, tile {64 k, box rows}.  box < 0: transposed operand
+  // [K][rows], rows contiguous, tile {64 rows, 64 k}
+  const bool tn = box < 0;
+  cuuint64_t gdim[3] = {(cuuint64_t)(tn ? rows : K), (cuuint64_t)(tn ? K : rows), (cuuint64_t)batch};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2,
+                        (cuuint64_t)(batch == 1 ? (int64_t)(tn ? K : rows) * ld : sb) * 2};
+  cuuint32_t box3[3] = {(cuuint32_t)BK, (cuuint32_t)(tn ? 64 : box), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
   CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p), gdim, gstr,
@@ -491,10 +524,10 @@ int get_map(const void* p, int64_t ld, int rows, int K, int batch, int64_t sb, i
   return CAPDEC_OK;
 }
 
-template <int BNR, int NACC, int EPI>
+template <int BNR, int NACC, int EPI, int TN = 0>
 int launch(const GemmArgs& a, cudaStream_t st) {
   using C = Cfg<BNR, NACC>;
-  auto kernel = gemm_tc_kernel<BNR, NACC, EPI>;
+  auto kernel = gemm_tc_kernel<BNR, NACC, EPI, TN>;
   static std::once_flag once;
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(once, [&] {
@@ -503,11 +536,11 @@ int launch(const GemmArgs& a, cudaStream_t st) {
   CAPDEC_REQUIRE(attr_rc == cudaSuccess, CAPDEC_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc_kernel) failed: %s",
                  cudaGetErrorString(attr_rc));
   CUtensorMap mW, mX;
-  CAPDEC_TRY(get_map(a.W, a.ldw, a.N, a.K, a.batch, a.sW, BM, &mW));
+  CAPDEC_TRY(get_map(a.W, a.ldw, a.N, a.K, a.batch, a.sW, (TN & 1) ? -1 : BM, &mW));
   const int rows_epi = (EPI == EPI_DHCELL && a.e.rows_epi > a.rows) ? a.e.rows_epi : a.rows;
   int xrows = a.rows_alloc > a.rows ? a.rows_alloc : a.rows;
   if (xrows < rows_epi) xrows = rows_epi;
-  CAPDEC_TRY(get_map(a.X, a.ldx, xrows, a.K, a.batch, a.sX, BNR, &mX));
+  CAPDEC_TRY(get_map(a.X, a.ldx, xrows, a.K, a.batch, a.sX, (TN & 2) ? -1 : BNR, &mX));
   // split-K: grid.z = batch * splits; the K-slices of a tile add into one fp32 buffer
   const int nkb = ceil_div(a.K, BK);
   const int zb = NACC > 1 ? 1 : a.batch;           // NACC > 1: the batch (gate) index is looped inside
@@ -591,6 +624,15 @@ int gemm_tc(const GemmArgs& a, cudaStream_t st) {
   switch (a.epi) {
     case EPI_PLAIN:
       CAPDEC_REQUIRE(a.out, CAPDEC_ERR_BAD_ARG, "gemm_tc: null output");
+      if (a.tn) {
+        // transposed operand(s): 64- or 128-wide row tiles (one or two 64-column TMA boxes)
+        const bool small = a.rows <= 64;
+        switch (a.tn & 3) {
+          case 1: return small ? launch<64, 1, EPI_PLAIN, 1>(a, st) : launch<128, 1, EPI_PLAIN, 1>(a, st);
+          case 2: return small ? launch<64, 1, EPI_PLAIN, 2>(a, st) : launch<128, 1, EPI_PLAIN, 2>(a, st);
+          default: return small ? launch<64, 1, EPI_PLAIN, 3>(a, st) : launch<128, 1, EPI_PLAIN, 3>(a, st);
+        }
+      }
       return launch_rows<1, EPI_PLAIN>(a, st);
     case EPI_G1: return launch_rows<1, EPI_G1>(a, st);
     case EPI_P3: return launch_rows<1, EPI_P3>(a, st);

@@ -55,20 +55,30 @@ __global__ void copy_cast_kernel(const TS* __restrict__ src, int64_t lds, TD* __
   }
 }
 
-template <typename T>
+// block (32, RY): thread (x, y) sums rows y, y + RY, ... of column n; four rows in flight per thread.
+// The partial sums meet in a FIXED order (deterministic: the fp32 parity mode is bit-reproducible).
+template <typename T, int RY>
 __global__ void colsum_kernel(const T* __restrict__ X, int64_t ld, int R, int N, float* out,
                               int accumulate) {
-  __shared__ float red[8][33];
+  __shared__ float red[RY][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.f;
-  if (n < N)
-    for (int r = threadIdx.y; r < R; r += 8) s += ldf(X + (int64_t)r * ld + n);
-  red[threadIdx.y][threadIdx.x] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (n < N) {
+    int r = threadIdx.y;
+    for (; r + 3 * RY < R; r += 4 * RY) {
+      s0 += ldf(X + (int64_t)r * ld + n);
+      s1 += ldf(X + (int64_t)(r + RY) * ld + n);
+      s2 += ldf(X + (int64_t)(r + 2 * RY) * ld + n);
+      s3 += ldf(X + (int64_t)(r + 3 * RY) * ld + n);
+    }
+    for (; r < R; r += RY) s0 += ldf(X + (int64_t)r * ld + n);
+  }
+  red[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    for (int k = 0; k < RY; ++k) t += red[k][threadIdx.x];
     out[n] = accumulate ? out[n] + t : t;
   }
 }
@@ -390,11 +400,16 @@ int copy_cast(int precision, const void* src, int src_ft, int64_t lds, void* dst
 int colsum(int precision, const void* X, int x_ft, int64_t ld, int R, int N, float* out,
            int accumulate, cudaStream_t st) {
   if (N <= 0) return CAPDEC_OK;
-  dim3 grid(ceil_div(N, 32)), block(32, 8);
-  if (x_ft && precision == CAPDEC_BF16)
-    colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)X, ld, R, N, out, accumulate);
-  else
-    colsum_kernel<float><<<grid, block, 0, st>>>((const float*)X, ld, R, N, out, accumulate);
+  // few column blocks (N <= ~5000): 32 row lanes per block, otherwise the grid already fills the chip
+  const bool tall = ceil_div(N, 32) < 296 && R >= 256;
+  dim3 grid(ceil_div(N, 32)), block(32, tall ? 32 : 8);
+  if (x_ft && precision == CAPDEC_BF16) {
+    if (tall) colsum_kernel<bf16, 32><<<grid, block, 0, st>>>((const bf16*)X, ld, R, N, out, accumulate);
+    else colsum_kernel<bf16, 8><<<grid, block, 0, st>>>((const bf16*)X, ld, R, N, out, accumulate);
+  } else {
+    if (tall) colsum_kernel<float, 32><<<grid, block, 0, st>>>((const float*)X, ld, R, N, out, accumulate);
+    else colsum_kernel<float, 8><<<grid, block, 0, st>>>((const float*)X, ld, R, N, out, accumulate);
+  }
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }

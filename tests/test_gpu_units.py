@@ -193,3 +193,18 @@ def test_attention_bwd_step_matches_autograd(precision, tol, rows, P, E, A):
     assert rel_err(dAtt1, a1.grad) < tol
     assert rel_err(dwf.sum(0), wf.grad) < tol
     assert abs(dbf.sum().item() - bf.grad.item()) < 1e-4
+
+
+@pytest.mark.parametrize("rows,N,K", [(512, 512, 1600), (10000, 512, 1600), (64, 200, 96), (2560, 2048, 1600),
+                                      (100, 56, 37 * 8)])
+def test_gemm_tn_matches_torch(rows, N, K):
+    """Transposed-operand (MN-major tcgen05) weight-gradient product against fp32 torch on the same bf16 values."""
+    from capdec import functional as CF
+    g = torch.Generator(device="cuda").manual_seed(rows + N + K)
+    ldx, ldw = (rows + 7) // 8 * 8, (N + 7) // 8 * 8
+    XT = torch.randn(K, ldx, device="cuda", generator=g).to(torch.bfloat16)[:, :rows]
+    WT = torch.randn(K, ldw, device="cuda", generator=g).to(torch.bfloat16)[:, :N]
+    out = CF.gemm_tn(XT, WT)
+    ref = XT.float().t() @ WT.float()
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err
