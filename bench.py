@@ -11,8 +11,9 @@ A "step" is one pass of the hot path over one batch of synthetic input:
     (T = 50 decode steps), vocab 10k, dims 512, 14x14x2048 features, 1000 tags.
   * decode workload (config 4): beam=3 search, <= 51 steps, images sharded over the ranks.
 `value` times the step with its inputs already resident in HBM; `e2e` times the same step through
-the public module API starting from pinned HOST buffers (H2D copies of features / tags / captions
-inside the timed region, loss read back to the host every step).
+the public module API starting from pinned HOST buffers: every timed step issues one batch of H2D
+copies (features / tags / captions) on a copy stream -- double buffered, so the copy of the next
+batch overlaps the current step's compute -- and reads the loss back to the host.
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -286,9 +287,29 @@ def run_b200(args):
         def step_resident():
             step(resident)
 
+        # e2e input pipeline: every step copies ONE batch host -> device from pinned memory on a copy stream
+        # (double buffered: the copy of the next batch overlaps this step's compute, the way a DataLoader
+        # with pin_memory + non_blocking feeds the reference's training loop) and reads the loss back
+        copy_stream = torch.cuda.Stream(device=dev)
+        pending = []
+
+        def issue_copy():
+            with torch.cuda.stream(copy_stream):
+                bufs = [t.to(dev, non_blocking=True) for t in pinned]
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            pending.append((bufs, ev))
+
         def step_e2e():
-            inputs = [t.to(dev, non_blocking=True) for t in pinned]
-            loss = step(inputs)
+            if not pending:
+                issue_copy()
+            bufs, ev = pending.pop(0)
+            issue_copy()                                   # next step's inputs start moving now
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            for b in bufs:
+                b.record_stream(cur)
+            loss = step(bufs)
             return loss.item()        # D2H read of the step's result
 
         for _ in range(warmup):
@@ -341,8 +362,26 @@ def run_b200(args):
         def step_resident():
             decode(enc_d, tags_d)
 
+        copy_stream = torch.cuda.Stream(device=dev)
+        pending = []
+
+        def issue_copy():
+            with torch.cuda.stream(copy_stream):
+                bufs = [enc_h.to(dev, non_blocking=True), tags_h.to(dev, non_blocking=True)]
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            pending.append((bufs, ev))
+
         def step_e2e():
-            r = decode(enc_h.to(dev, non_blocking=True), tags_h.to(dev, non_blocking=True))
+            if not pending:
+                issue_copy()
+            bufs, ev = pending.pop(0)
+            issue_copy()                                   # the next shard of images starts moving now
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            for b in bufs:
+                b.record_stream(cur)
+            r = decode(bufs[0], bufs[1])
             return r["seq"].cpu(), r["len"].cpu()
 
         for _ in range(warmup):
@@ -419,45 +458,62 @@ def load_traffic(kernel):
 
 
 def measure_recurrence_roofline(lib, dec, kind, dims, rows, inputs, peaks):
-    """Dominant kernel of the training step: recur_fwd_kernel (csrc/recur.cu), ONE cooperative launch that
-    runs all T decode steps.  Algorithmic bytes per launch = T * rows * P * (A + E) * 2 (every
-    caption-step streams its att1 and enc rows, 1.004 MB in bf16); for pure_scn (no feature stream) the
-    recurrent weights touched per step instead.  Duration: CUDA events recorded by the library on the
-    launching stream around the kernel (capdec_recur_timing), eager launches, mean of 5 after 2 warm-ups."""
+    """Dominant kernels of the training step: recur_bwd_kernel and recur_fwd_kernel (csrc/recur.cu), ONE
+    cooperative launch each for all T decode steps.  Algorithmic bytes per launch = T * rows * P * (A + E) * 2
+    in both directions (every caption-step streams its att1 and enc rows, 1.004 MB in bf16; the
+    backward re-reads both and keeps no per-step dAtt1 read-modify-write); for pure_scn (no feature stream)
+    the recurrent weights touched per step instead.  Duration: CUDA events recorded by the library on the
+    launching stream around each kernel (capdec_recur_timing), eager launches of the full step, mean of 5
+    after 2 warm-ups.  The roofline entry is the slower of the two; the other one rides along."""
     import capdec
-    was = capdec.graphs_enabled() if hasattr(capdec, "graphs_enabled") else True
+    was = capdec.graphs_enabled()
     capdec.set_graphs(False)
     lib.capdec_recur_timing(1)
     enc, tags, caps, caplens = inputs
-    ms = []
+    ms = {0: [], 1: []}
     try:
         for it in range(7):
-            dec(enc, tags, caps, caplens)          # grad mode: the kernel also saves awe for the backward
-            t = float(lib.capdec_recur_last_ms())
-            if it >= 2 and t > 0:
-                ms.append(t)
+            out = dec(enc, tags, caps, caplens)      # grad mode: the kernel also saves awe for the backward
+            alphas = None if kind == "pure_scn" else out[3]
+            loss, _ = dec.loss(out[0], out[1], out[2], alphas)
+            for p in dec.parameters():
+                p.grad = None
+            loss.backward()
+            for which in (0, 1):
+                t = float(lib.capdec_recur_last_ms(which))
+                if it >= 2 and t > 0:
+                    ms[which].append(t)
     finally:
         lib.capdec_recur_timing(0)
         capdec.set_graphs(was)
-    if not ms:
+    if not ms[0] or not ms[1]:
         return None
-    t_ms = sum(ms) / len(ms)
     P, E, A, D, F, T = 196, dims["E"], dims["A"], dims["D"], dims["F"], CAP_LEN - 1
     if kind == "attention_scn":
         bytes_alg = T * rows * P * (A + E) * 2
         what = "T*rows*P*(A+E)*2 B of attention features"
     else:
         bytes_alg = T * (4 * F * D + 4 * D * 2 * F) * 2
-        what = "T * (W_ha + [W_ic|W_hc]) bf16 recurrent weights (resident in shared memory, so the HBM figure is an upper bound of need)"
-    achieved = bytes_alg / (t_ms * 1e-3) / 1e9
-    return {"kernel": "recur_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic("recur_fwd_kernel"),
-            "us_per_launch": 1e3 * t_ms, "rows": rows, "steps_per_launch": T,
-            "algorithmic_bytes_per_launch": bytes_alg, "peak_source": peaks["source"],
-            "note": "one cooperative launch = all %d decode steps; algorithmic bytes = %s; at %d rows the kernel "
-                    "is bound by its %d grid barriers and dependent L2 round trips per step, not by HBM (the "
-                    "features stay L2-resident across steps) -- see DESIGN.md" % (T, what, rows,
-                                                                                 6 if kind == "attention_scn" else 3)}
+        what = ("T * (W_ha + [W_ic|W_hc]) bf16 recurrent weights (resident in shared memory, so the HBM "
+                "figure is an upper bound of need)")
+
+    def entry(which, name):
+        t_ms = sum(ms[which]) / len(ms[which])
+        achieved = bytes_alg / (t_ms * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(name), "us_per_launch": 1e3 * t_ms,
+                "rows": rows, "steps_per_launch": T, "algorithmic_bytes_per_launch": bytes_alg,
+                "peak_source": peaks["source"]}
+
+    fwd, bwd = entry(0, "recur_fwd_kernel"), entry(1, "recur_bwd_kernel")
+    main, other = (bwd, fwd) if bwd["us_per_launch"] >= fwd["us_per_launch"] else (fwd, bwd)
+    nbar = 6 if kind == "attention_scn" else 3
+    main["note"] = ("one cooperative launch = all %d decode steps; algorithmic bytes = %s; at %d rows the kernel is "
+                    "bound by its %d grid barriers (~1.5 us each) and dependent L2 round trips per step, not by HBM: "
+                    "the features stay L2-resident across steps, so the measured DRAM traffic is far BELOW the "
+                    "algorithmic stream -- see DESIGN.md" % (T, what, rows, nbar))
+    main["other_direction"] = other
+    return main
 
 
 def measure_roofline(dev, kind, dims, rows, peaks, precision):

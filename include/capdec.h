@@ -177,13 +177,14 @@ int capdec_beam_search(const CapdecDims* dims, const CapdecParams* params,
                        float* trace_score,
                        void* workspace, size_t workspace_bytes, void* stream);
 
-/* Measurement aid for bench.py: with timing enabled, the persistent recurrence kernel of the next
- * capdec_forward_train calls (csrc/recur.cu: the whole `for t` loop of attention_scn.py:139-156 in
- * one cooperative launch) is bracketed by CUDA events on the launching stream.
- * capdec_recur_last_ms() waits for the second event and returns the kernel's device time in
+/* Measurement aid for bench.py: with timing enabled, the persistent recurrence kernels of the next
+ * capdec_forward_train / capdec_backward calls (csrc/recur.cu: the whole `for t` loop of
+ * attention_scn.py:139-156, resp. its reverse-time gradient, in one cooperative launch each) are
+ * bracketed by CUDA events on the launching stream.  capdec_recur_last_ms(which) (0 = forward
+ * kernel, 1 = backward kernel) waits for the second event and returns the kernel's device time in
  * milliseconds (< 0: nothing was timed).  Do not enable it while the stream is being captured. */
 void capdec_recur_timing(int enable);
-float capdec_recur_last_ms(void);
+float capdec_recur_last_ms(int which);
 
 /* ---- unit entry points (single kernels, used by the parity tests) ---- */
 

@@ -38,7 +38,7 @@ SIGNATURES = {
     "capdec_init": (_i, []),
     "capdec_launch_count": (C.c_ulonglong, []),
     "capdec_recur_timing": (None, [_i]),
-    "capdec_recur_last_ms": (_f, []),
+    "capdec_recur_last_ms": (_f, [_i]),
     "capdec_workspace_bytes": (_sz, [C.POINTER(Dims), _i]),
     "capdec_forward_train": (_i, [C.POINTER(Dims), C.POINTER(Params), _vp, _i64, _i64, _i64, _vp, _vp,
                                   _vp, _vp, _f, _u64, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -17,8 +17,16 @@ class CaptionDecoderBase(nn.Module):
 
     # ------------------------------------------------------------------ helpers
     def _param_list(self):
-        sd = dict(self.named_parameters())
-        return [sd[n] for n in CF.param_names(self.kind)]
+        # (owning module, attribute) pairs are resolved once; the Parameter objects are looked up on every
+        # call, so re-assigned parameters (load_pretrained_embeddings) are picked up
+        slots = self.__dict__.get("_capdec_param_slots")
+        if slots is None:
+            slots = []
+            for n in CF.param_names(self.kind):
+                mod_path, _, attr = n.rpartition(".")
+                slots.append((self.get_submodule(mod_path) if mod_path else self, attr))
+            self.__dict__["_capdec_param_slots"] = slots
+        return [m._parameters[a] for m, a in slots]
 
     def _dims_kw(self):
         return {"A": getattr(self, "attention_dim", 0), "M": self.embed_dim, "D": self.decoder_dim,

@@ -65,7 +65,7 @@ const char* capdec_last_error(void) { return get_error(); }
 unsigned long long capdec_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void capdec_recur_timing(int enable) { recur_timing(enable); }
-float capdec_recur_last_ms(void) { return recur_last_ms(); }
+float capdec_recur_last_ms(int which) { return recur_last_ms(which); }
 
 int capdec_init(void) {
   std::call_once(g_init_once, [] { g_init_rc = do_init(); });

@@ -121,7 +121,7 @@ struct RecurBwdArgs {
 bool recur_bwd_supported(const RecurBwdArgs& a);
 int recur_bwd(const RecurBwdArgs& a, cudaStream_t st);
 void recur_timing(int enable);
-float recur_last_ms();
+float recur_last_ms(int which);
 
 // ---- beam.cu ----
 int beam_init(int32_t* prev_word, float* score, int32_t* live, int32_t* krem, int32_t* has_done,

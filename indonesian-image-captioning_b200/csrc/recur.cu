@@ -183,11 +183,15 @@ __device__ __forceinline__ void gemm_job(Pipe& pp, const bf16* __restrict__ src,
   const uint32_t fill_bytes = (uint32_t)n * KF * 2;
   stage_fill(pp, 0, src, fill_bytes);
   if (SPF == 1 && nfill > 1) stage_fill(pp, 1, src + fill_stride, fill_bytes);
-  float acc[2 * NH][4];
+  // one accumulator per (n-tile, k block): legacy mma.sync has a long issue-to-result latency on sm_100, so
+  // the only dependent pair inside a fill is the two k16 halves of one block
+  float accb[2 * NH][BPW][4];
 #pragma unroll
   for (int nt = 0; nt < 2 * NH; ++nt)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    for (int j = 0; j < BPW; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) accb[nt][j][i] = 0.f;
   const uint8_t* a_base = pp.stg + (size_t)(mt * 16 + g) * (KF * 2) + ks * (BPW * 64) + 16 * c;
   const uint8_t* w_base = Ws + (size_t)g * wstride + ks * (BPW * 64) + 16 * c;
 #pragma unroll 1
@@ -204,8 +208,8 @@ __device__ __forceinline__ void gemm_job(Pipe& pp, const bf16* __restrict__ src,
 #pragma unroll
       for (int nt = 0; nt < 2 * NH; ++nt) {
         const uint4 b = *reinterpret_cast<const uint4*>(wp + (size_t)nt * 8 * wstride + j * 64);
-        mma_bf16(acc[nt], alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
-        mma_bf16(acc[nt], alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
+        mma_bf16(accb[nt][j], alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
+        mma_bf16(accb[nt][j], alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
       }
     }
     if (kf + 2 < nfill) {
@@ -213,6 +217,16 @@ __device__ __forceinline__ void gemm_job(Pipe& pp, const bf16* __restrict__ src,
       stage_fill(pp, s, src + (int64_t)(kf + 2) * fill_stride, fill_bytes);
     }
   }
+  float acc[2 * NH][4];
+#pragma unroll
+  for (int nt = 0; nt < 2 * NH; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float sum = accb[nt][0][i];
+#pragma unroll
+      for (int jb = 1; jb < BPW; ++jb) sum += accb[nt][jb][i];
+      acc[nt][i] = sum;
+    }
   const int row = threadIdx.x >> 4, j = threadIdx.x & 15;
   float* mine = red + (ks * 32 + mt * 16 + g) * REDLD + 2 * c;
 #pragma unroll
@@ -311,6 +325,13 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
     // ================= G1: [att2 | beta_pre | p] = h_{t-1} W_cat1^T + b, and p*q -> m =================
     if (has1 && (p.mask & 1)) {
       const bf16* hprev = t == 0 ? p.H0 : p.Ht + (tb - B) * D;
+      float bias1[NT1 / 2], q1[NT1 / 2];
+#pragma unroll
+      for (int i = 0; i < NT1 / 2; ++i) {              // epilogue operands first: hidden behind the GEMM
+        const int nf = f1 + i * 16 + ej;
+        bias1[i] = nf < NG1 ? __ldg(p.b_cat1 + nf) : 0.f;
+        q1[i] = (erow < n && nf >= col0 && nf < NG1) ? __ldg(p.q + (int64_t)erow * NQ + (nf - col0)) : 0.f;
+      }
       float out[NT1 / 2];
       gemm_job<NT1 / 2, 2>(pp, hprev, 0, n, W1s, w1s, 1, red, out);
       if (erow < n) {
@@ -319,13 +340,12 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
         for (int i = 0; i < NT1 / 2; ++i) {
           const int nf = f1 + i * 16 + ej;
           if (nf < NG1) {
-            const float val = out[i] + __ldg(p.b_cat1 + nf);
+            const float val = out[i] + bias1[i];
             g1[nf] = val;
             if (nf >= col0) {
               const int nn = nf - col0;
               const int gg = nn / F, f = nn - gg * F;
-              p.m[((int64_t)gg * p.R + tb + erow) * 2 * F + F + f] =
-                  __float2bfloat16_rn(val * __ldg(p.q + (int64_t)erow * NQ + nn));
+              p.m[((int64_t)gg * p.R + tb + erow) * 2 * F + F + f] = __float2bfloat16_rn(val * q1[i]);
             }
           }
         }
@@ -507,16 +527,19 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
       RECUR_STAMP();
       // ================= P3: u = Emb W_ia[:M] + z W_ia[M:], and u*v -> m =================
       if (has3 && (p.mask & 8)) {
+        // the epilogue's operands are requested before the GEMM: their L2 round trip hides behind it
+        const int nf = f3 + ej;
+        const bool ok3 = erow < n && nf < NQ;
+        float* U = p.U + (tb + erow) * NQ;
+        const float u_emb = ok3 ? __ldg(U + nf) : 0.f;           // written by the batched GEMM before this kernel
+        const float v3 = ok3 ? __ldg(p.v + (int64_t)erow * NQ + nf) : 0.f;
         float out[1];
         gemm_job<1, 2>(pp, p.zk + (int64_t)t * chunks * B * CHUNK, (int64_t)B * CHUNK, n, W3s, w3s, E / KC, red, out);
-        const int nf = f3 + ej;
-        if (erow < n && nf < NQ) {
-          float* U = p.U + (tb + erow) * NQ;
-          const float val = out[0] + U[nf];
+        if (ok3) {
+          const float val = out[0] + u_emb;
           U[nf] = val;
           const int gg = nf / F, f = nf - gg * F;
-          p.m[((int64_t)gg * p.R + tb + erow) * 2 * F + f] =
-              __float2bfloat16_rn(val * __ldg(p.v + (int64_t)erow * NQ + nf));
+          p.m[((int64_t)gg * p.R + tb + erow) * 2 * F + f] = __float2bfloat16_rn(val * v3);
         }
       }
       RECUR_STAMP();
@@ -718,6 +741,21 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
     BSTAMP();
     // ================= W: [w | r] = dpre_g [W_ic_g | W_hc_g] and the factor products =================
     if (hasW) {
+      // epilogue operands (factor, forward activation, running sum) are requested before the GEMM
+      float fac[2], act[2], run[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int nf = fW0 + i * 16 + ej;
+        fac[i] = act[i] = run[i] = 0.f;
+        if (erow < n && nf < 2 * F) {
+          const bool is_w = nf < F;
+          const int n4 = gateW * F + (is_w ? nf : nf - F);
+          const int64_t k = (int64_t)erow * NQ + n4;
+          fac[i] = __ldg((is_w ? p.v : p.q) + k);
+          act[i] = is_w ? __ldg(p.U + (tb + erow) * NQ + n4) : __ldg(p.g1 + (tb + erow) * NG1 + col0 + n4);
+          run[i] = (is_w ? p.dv_acc : p.dq_acc)[k];              // only this thread ever touches element k
+        }
+      }
       float out[2];
       gemm_job<2, 2>(pp, p.dpre_gm + ((int64_t)t * 4 + gateW) * B * D, 0, n, WWs, wWs, 1, red, out);
       if (erow < n) {
@@ -729,16 +767,15 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             const int n4 = gateW * F + (is_w ? nf : nf - F);
             const int64_t k = (int64_t)erow * NQ + n4;
             const float val = out[i];
+            const bf16 x = __float2bfloat16_rn(val * fac[i]);
             if (is_w) {
-              const bf16 x = __float2bfloat16_rn(val * __ldg(p.v + k));
               p.du[(tb + erow) * NQ + n4] = x;
               p.duk[(((int64_t)t * nkq + n4 / KC) * B + erow) * KC + (n4 % KC)] = x;
-              p.dv_acc[k] += val * __ldg(p.U + (tb + erow) * NQ + n4);
+              p.dv_acc[k] = run[i] + val * act[i];
             } else {
-              const bf16 x = __float2bfloat16_rn(val * __ldg(p.q + k));
               p.dpx[(tb + erow) * p.ldPX + n4] = x;
               p.dpxk[(((int64_t)t * nkc + n4 / KC) * B + erow) * KC + (n4 % KC)] = x;
-              p.dq_acc[k] += val * __ldg(p.g1 + (tb + erow) * NG1 + col0 + n4);
+              p.dq_acc[k] = run[i] + val * act[i];
             }
           }
         }
@@ -1020,8 +1057,8 @@ int pick_nt(int tiles, int ctas) {
 }
 
 bool g_timing = false;
-cudaEvent_t g_ev[2] = {nullptr, nullptr};
-bool g_timed = false;
+cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};     // [0,1] forward kernel, [2,3] backward kernel
+bool g_timed[2] = {false, false};
 
 bool persistent_enabled() {
   const char* s = getenv("CAPDEC_PERSISTENT");      // read per call: tests flip it
@@ -1102,17 +1139,15 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
     CAPDEC_CUDA_OK(cudaMemsetAsync(p.prof, 0, (size_t)(a.T * 16 + 64) * sizeof(long long), st));
   }
   if (g_timing) {
-    if (!g_ev[0]) {
-      CAPDEC_CUDA_OK(cudaEventCreate(&g_ev[0]));
-      CAPDEC_CUDA_OK(cudaEventCreate(&g_ev[1]));
-    }
+    for (int i = 0; i < 4; ++i)
+      if (!g_ev[i]) CAPDEC_CUDA_OK(cudaEventCreate(&g_ev[i]));
     CAPDEC_CUDA_OK(cudaEventRecord(g_ev[0], st));
   }
   CAPDEC_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
   count_launch();
   if (g_timing) {
     CAPDEC_CUDA_OK(cudaEventRecord(g_ev[1], st));
-    g_timed = true;
+    g_timed[0] = true;
   }
   if (prof) {
     // debug only: synchronises.  Prints per-phase cycles of CTA 0 (work, barrier wait) for a few steps.
@@ -1210,8 +1245,17 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
     CAPDEC_CUDA_OK(cudaMalloc(&p.prof, (size_t)a.T * 16 * sizeof(long long)));
     CAPDEC_CUDA_OK(cudaMemsetAsync(p.prof, 0, (size_t)a.T * 16 * sizeof(long long), st));
   }
+  if (g_timing) {
+    for (int i = 0; i < 4; ++i)
+      if (!g_ev[i]) CAPDEC_CUDA_OK(cudaEventCreate(&g_ev[i]));
+    CAPDEC_CUDA_OK(cudaEventRecord(g_ev[2], st));
+  }
   CAPDEC_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
   count_launch();
+  if (g_timing) {
+    CAPDEC_CUDA_OK(cudaEventRecord(g_ev[3], st));
+    g_timed[1] = true;
+  }
   if (prof) {
     std::vector<long long> h((size_t)a.T * 16);
     CAPDEC_CUDA_OK(cudaStreamSynchronize(st));
@@ -1226,12 +1270,15 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
   return CAPDEC_OK;
 }
 
-void recur_timing(int enable) { g_timing = enable != 0; if (!enable) g_timed = false; }
-float recur_last_ms() {
-  if (!g_timed) return -1.f;
+void recur_timing(int enable) {
+  g_timing = enable != 0;
+  if (!enable) g_timed[0] = g_timed[1] = false;
+}
+float recur_last_ms(int which) {
+  if (which < 0 || which > 1 || !g_timed[which]) return -1.f;
   float ms = -1.f;
-  if (cudaEventSynchronize(g_ev[1]) != cudaSuccess) return -1.f;
-  if (cudaEventElapsedTime(&ms, g_ev[0], g_ev[1]) != cudaSuccess) return -1.f;
+  if (cudaEventSynchronize(g_ev[2 * which + 1]) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, g_ev[2 * which], g_ev[2 * which + 1]) != cudaSuccess) return -1.f;
   return ms;
 }
 

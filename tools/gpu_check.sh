@@ -14,7 +14,7 @@ if [ "${2:-}" != "quick" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
       --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu.log 2>&1
   timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_plain2.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'recur_fwd_kernel|attn_bwd_a|attn_bwd_b|attn_scores|attn_wsum' -s 6 -c 10 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'recur_fwd_kernel|recur_bwd_kernel' -s 4 -c 4 \
       -f -o $OUT/${TAG}_prof python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu2.log 2>&1
 fi
 tail -5 $OUT/${TAG}_tests.log; cat $OUT/${TAG}_smoke.log | tail -3; cat $OUT/${TAG}_bench_train.json $OUT/${TAG}_bench_decode.json; tail -3 $OUT/${TAG}_bench_decode.err
