@@ -250,10 +250,15 @@ int pack_weights(const Ctx& c, const CapdecParams& w) {
   cudaStream_t st = c.st;
   const int D = d.D, E = d.E, A = d.A, M = d.M, F = d.F, S = d.S, V = d.V, X = p.X, NQ = p.NQ;
   int row = 0;     // row cursor inside Wp_cat1
+  PackTable tbl;
+  bool ok = true;
+  // dst[r][c] = src[r][c] (CC) / dst[c][r] = src[r][c] (TT), fp32 master -> feature type, all in one launch
+  auto CC = [&](const float* src, int64_t lds, void* dst, int64_t ldd, int R_, int C_) { ok = ok && tbl.add(src, lds, dst, ldd, R_, C_, 0); };
+  auto TT = [&](const float* src, int64_t lds, void* dst, int64_t ldd, int R_, int C_) { ok = ok && tbl.add(src, lds, dst, ldd, R_, C_, 1); };
   if (p.att) {
-    CAPDEC_TRY(copy_cast(pr, w.enc_att_w, 0, E, c.at(p.o.Wp_e), 1, p.ldE, A, E, st));
-    CAPDEC_TRY(copy_cast(pr, w.dec_att_w, 0, D, c.ft(p.o.Wp_cat1, 0), 1, p.ldD, A, D, st));
-    CAPDEC_TRY(copy_cast(pr, w.f_beta_w, 0, D, c.ft(p.o.Wp_cat1, (int64_t)A * p.ldD), 1, p.ldD, E, D, st));
+    CC(w.enc_att_w, E, c.at(p.o.Wp_e), p.ldE, A, E);
+    CC(w.dec_att_w, D, c.ft(p.o.Wp_cat1, 0), p.ldD, A, D);
+    CC(w.f_beta_w, D, c.ft(p.o.Wp_cat1, (int64_t)A * p.ldD), p.ldD, E, D);
     row = A + E;
     CAPDEC_TRY(concat_bias(c.at<float>(p.o.b_cat1), w.dec_att_b, A, w.f_beta_b, E, NQ, st));
   } else {
@@ -261,56 +266,52 @@ int pack_weights(const Ctx& c, const CapdecParams& w) {
   }
   if (p.scn) {
     // W_ha (D,4F) -> rows [row, row+4F) of cat1 as W_ha^T
-    CAPDEC_TRY(transpose_cast(pr, w.w_ha, 0, c.ft(p.o.Wp_cat1, (int64_t)row * p.ldD), 1, 1, D, NQ, 0, NQ,
-                              p.ldD, 0, 1, st));
-    CAPDEC_TRY(transpose_cast(pr, w.w_ia, 0, c.at(p.o.Wp_xq), 1, 1, X, NQ, 0, NQ, p.ldX, 0, 1, st));
-    CAPDEC_TRY(transpose_cast(pr, w.w_ib, 0, c.at(p.o.Wp_ibT), 1, 1, S, NQ, 0, NQ, p.ldS, 0, 1, st));
-    CAPDEC_TRY(transpose_cast(pr, w.w_hb, 0, c.at(p.o.Wp_hbT), 1, 1, S, NQ, 0, NQ, p.ldS, 0, 1, st));
+    TT(w.w_ha, NQ, c.ft(p.o.Wp_cat1, (int64_t)row * p.ldD), p.ldD, D, NQ);
+    TT(w.w_ia, NQ, c.at(p.o.Wp_xq), p.ldX, X, NQ);
+    TT(w.w_ib, NQ, c.at(p.o.Wp_ibT), p.ldS, S, NQ);
+    TT(w.w_hb, NQ, c.at(p.o.Wp_hbT), p.ldS, S, NQ);
     for (int g = 0; g < 4; ++g) {
       // Wp_c[g] = [ W_ic[:, gF:(g+1)F] | W_hc[:, gF:(g+1)F] ]   (D x 2F)
-      CAPDEC_TRY(copy_cast(pr, w.w_ic + g * F, 0, NQ, c.ft(p.o.Wp_c, (int64_t)g * D * p.ld2F), 1,
-                           p.ld2F, D, F, st));
-      CAPDEC_TRY(copy_cast(pr, w.w_hc + g * F, 0, NQ, c.ft(p.o.Wp_c, (int64_t)g * D * p.ld2F + F), 1,
-                           p.ld2F, D, F, st));
+      CC(w.w_ic + g * F, NQ, c.ft(p.o.Wp_c, (int64_t)g * D * p.ld2F), p.ld2F, D, F);
+      CC(w.w_hc + g * F, NQ, c.ft(p.o.Wp_c, (int64_t)g * D * p.ld2F + F), p.ld2F, D, F);
     }
   } else {
     // LSTM: weight_hh (4D,D) and weight_ih (4D,X) are already [N_out][K]
-    CAPDEC_TRY(copy_cast(pr, w.w_ha, 0, D, c.ft(p.o.Wp_cat1, (int64_t)row * p.ldD), 1, p.ldD, NQ, D, st));
-    CAPDEC_TRY(copy_cast(pr, w.w_ia, 0, X, c.at(p.o.Wp_xq), 1, p.ldX, NQ, X, st));
+    CC(w.w_ha, D, c.ft(p.o.Wp_cat1, (int64_t)row * p.ldD), p.ldD, NQ, D);
+    CC(w.w_ia, X, c.at(p.o.Wp_xq), p.ldX, NQ, X);
   }
-  CAPDEC_TRY(copy_cast(pr, w.init_h_w, 0, E, c.ft(p.o.Wp_init, 0), 1, p.ldE, D, E, st));
-  CAPDEC_TRY(copy_cast(pr, w.init_c_w, 0, E, c.ft(p.o.Wp_init, (int64_t)D * p.ldE), 1, p.ldE, D, E, st));
-  CAPDEC_TRY(copy_cast(pr, w.fc_w, 0, D, c.at(p.o.Wp_fc), 1, p.ldD, V, D, st));
+  CC(w.init_h_w, E, c.ft(p.o.Wp_init, 0), p.ldE, D, E);
+  CC(w.init_c_w, E, c.ft(p.o.Wp_init, (int64_t)D * p.ldE), p.ldE, D, E);
+  CC(w.fc_w, D, c.at(p.o.Wp_fc), p.ldD, V, D);
   if (p.bwd) {
-    CAPDEC_TRY(transpose_cast(pr, w.fc_w, 0, c.at(p.o.Wp_fcT), 1, 1, V, D, 0, D, p.ldV, 0, 1, st));
+    TT(w.fc_w, D, c.at(p.o.Wp_fcT), p.ldV, V, D);
     if (p.scn) {
       for (int g = 0; g < 4; ++g) {
         // Wp_cT[g] = [ W_ic_g^T ; W_hc_g^T ]  (2F x D)
-        CAPDEC_TRY(transpose_cast(pr, w.w_ic + g * F, 0, c.ft(p.o.Wp_cT, (int64_t)g * 2 * F * p.ldD), 1,
-                                  1, D, F, 0, NQ, p.ldD, 0, 1, st));
-        CAPDEC_TRY(transpose_cast(pr, w.w_hc + g * F, 0,
-                                  c.ft(p.o.Wp_cT, ((int64_t)g * 2 * F + F) * p.ldD), 1, 1, D, F, 0, NQ,
-                                  p.ldD, 0, 1, st));
+        TT(w.w_ic + g * F, NQ, c.ft(p.o.Wp_cT, (int64_t)g * 2 * F * p.ldD), p.ldD, D, F);
+        TT(w.w_hc + g * F, NQ, c.ft(p.o.Wp_cT, ((int64_t)g * 2 * F + F) * p.ldD), p.ldD, D, F);
       }
-      CAPDEC_TRY(copy_cast(pr, w.w_ia, 0, NQ, c.at(p.o.Wp_xin), 1, p.ldNQ, X, NQ, st));
+      CC(w.w_ia, NQ, c.at(p.o.Wp_xin), p.ldNQ, X, NQ);
     } else {
-      CAPDEC_TRY(transpose_cast(pr, w.w_ha, 0, c.at(p.o.Wp_hq), 1, 1, NQ, D, 0, D, p.ldNQ, 0, 1, st));
-      CAPDEC_TRY(transpose_cast(pr, w.w_ia, 0, c.at(p.o.Wp_xin), 1, 1, NQ, X, 0, X, p.ldNQ, 0, 1, st));
+      TT(w.w_ha, D, c.at(p.o.Wp_hq), p.ldNQ, NQ, D);
+      TT(w.w_ia, X, c.at(p.o.Wp_xin), p.ldNQ, NQ, X);
     }
     if (p.scn) {
       // Wp_hx = [ W_ha | W_beta^T | W_d^T ]   (D x (4F + E + A)): ONE GEMM gives the recurrent dh
-      CAPDEC_TRY(copy_cast(pr, w.w_ha, 0, NQ, c.at(p.o.Wp_hx), 1, p.ldPX, D, NQ, st));
+      CC(w.w_ha, NQ, c.at(p.o.Wp_hx), p.ldPX, D, NQ);
       if (p.att) {
-        CAPDEC_TRY(transpose_cast(pr, w.f_beta_w, 0, c.ft(p.o.Wp_hx, NQ), 1, 1, E, D, 0, D, p.ldPX, 0, 1, st));
-        CAPDEC_TRY(transpose_cast(pr, w.dec_att_w, 0, c.ft(p.o.Wp_hx, NQ + E), 1, 1, A, D, 0, D, p.ldPX, 0, 1, st));
+        TT(w.f_beta_w, D, c.ft(p.o.Wp_hx, NQ), p.ldPX, E, D);
+        TT(w.dec_att_w, D, c.ft(p.o.Wp_hx, NQ + E), p.ldPX, A, D);
       }
     }
     if (p.att && !p.scn) {
       // Wp_b6 = [ W_beta^T | W_d^T ]   (D x (E+A))
-      CAPDEC_TRY(transpose_cast(pr, w.f_beta_w, 0, c.ft(p.o.Wp_b6, 0), 1, 1, E, D, 0, D, p.ldEA, 0, 1, st));
-      CAPDEC_TRY(transpose_cast(pr, w.dec_att_w, 0, c.ft(p.o.Wp_b6, E), 1, 1, A, D, 0, D, p.ldEA, 0, 1, st));
+      TT(w.f_beta_w, D, c.ft(p.o.Wp_b6, 0), p.ldEA, E, D);
+      TT(w.dec_att_w, D, c.ft(p.o.Wp_b6, E), p.ldEA, A, D);
     }
   }
+  CAPDEC_REQUIRE(ok, CAPDEC_ERR_BAD_ARG, "pack_weights: segment table overflow");
+  CAPDEC_TRY(pack_multi(pr, tbl, st));
   return CAPDEC_OK;
 }
 

@@ -33,6 +33,19 @@ int transpose_cast(int precision, const void* src, int src_ft, void* dst, int ds
 // dst[r*ldd + c] = src[r*lds + c]  (cast), r<R, c<C
 int copy_cast(int precision, const void* src, int src_ft, int64_t lds, void* dst, int dst_ft,
               int64_t ldd, int R, int C, cudaStream_t st);
+// One launch for many fp32 -> feature-type matrix copies / transposes (the per-call weight packing):
+//   transpose == 0: dst[r*ldd + c] = src[r*lds + c]     transpose == 1: dst[c*ldd + r] = src[r*lds + c]
+struct PackSeg { const float* src; void* dst; int R, C; int64_t lds, ldd; int transpose; int tile0; };
+struct PackTable {
+  PackSeg seg[40];
+  int n = 0;
+  bool add(const float* src, int64_t lds, void* dst, int64_t ldd, int R, int C, int transpose) {
+    if (n >= 40 || R <= 0 || C <= 0) return R <= 0 || C <= 0;
+    seg[n++] = PackSeg{src, dst, R, C, lds, ldd, transpose, 0};
+    return true;
+  }
+};
+int pack_multi(int precision, PackTable& t, cudaStream_t st);
 // out[n] (=|+=) sum_r X[r*ld + n]
 int colsum(int precision, const void* X, int x_ft, int64_t ld, int R, int N, float* out,
            int accumulate, cudaStream_t st);

@@ -55,6 +55,37 @@ __global__ void copy_cast_kernel(const TS* __restrict__ src, int64_t lds, TD* __
   }
 }
 
+// All weight packing of one call in ONE launch: a table of (fp32 source matrix -> feature-type copy or
+// transpose) segments, 32 x 32 source tiles, one tile per CTA.
+template <typename TD>
+__global__ void pack_multi_kernel(const __grid_constant__ PackTable t) {
+  __shared__ float tile[32][33];
+  int si = 0;
+  while (si + 1 < t.n && (int)blockIdx.x >= t.seg[si + 1].tile0) ++si;
+  const PackSeg& g = t.seg[si];
+  const int local = blockIdx.x - g.tile0;
+  const int tiles_c = (g.C + 31) / 32;
+  const int r0 = (local / tiles_c) * 32, c0 = (local % tiles_c) * 32;
+  const float* src = g.src;
+  TD* dst = (TD*)g.dst;
+  if (!g.transpose) {
+    for (int k = threadIdx.y; k < 32; k += 8) {
+      const int r = r0 + k, c = c0 + threadIdx.x;
+      if (r < g.R && c < g.C) dst[(int64_t)r * g.ldd + c] = from_f<TD>(src[(int64_t)r * g.lds + c]);
+    }
+    return;
+  }
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + threadIdx.x;
+    tile[k][threadIdx.x] = (r < g.R && c < g.C) ? src[(int64_t)r * g.lds + c] : 0.f;
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int c = c0 + k, r = r0 + threadIdx.x;
+    if (r < g.R && c < g.C) dst[(int64_t)c * g.ldd + r] = from_f<TD>(tile[threadIdx.x][k]);
+  }
+}
+
 // block (32, RY): thread (x, y) sums rows y, y + RY, ... of column n; four rows in flight per thread.
 // The partial sums meet in a FIXED order (deterministic: the fp32 parity mode is bit-reproducible).
 template <typename T, int RY>
@@ -382,6 +413,21 @@ int transpose_cast(int precision, const void* src, int src_ft, void* dst, int ds
   DISPATCH_2FT(precision, src_ft, dst_ft, CALL);
 #undef CALL
   CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
+int pack_multi(int precision, PackTable& t, cudaStream_t st) {
+  if (t.n <= 0) return CAPDEC_OK;
+  int tiles = 0;
+  for (int i = 0; i < t.n; ++i) {
+    t.seg[i].tile0 = tiles;
+    tiles += ceil_div(t.seg[i].R, 32) * ceil_div(t.seg[i].C, 32);
+  }
+  if (tiles <= 0) return CAPDEC_OK;
+  if (precision == CAPDEC_BF16) pack_multi_kernel<bf16><<<tiles, dim3(32, 8), 0, st>>>(t);
+  else pack_multi_kernel<float><<<tiles, dim3(32, 8), 0, st>>>(t);
+  CAPDEC_LAUNCH_OK();
+  t.n = 0;
   return CAPDEC_OK;
 }
 
