@@ -145,7 +145,7 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
   if (p->att) o.att_scr = take(attention_scratch_floats(d.precision, (int)B, (int)P, (int)E) * 4);
   o.counters = take((size_t)GEMM_TC_MAX_TILE_COUNTERS * 4);   // split-K tickets of the fused GEMM epilogues
   o.bar = take(256);                                          // grid-barrier counter of the persistent kernels
-  if (d.precision == CAPDEC_BF16 && p->scn) {                 // operand copies of the persistent kernel (recur.cu)
+  if (d.precision == CAPDEC_BF16 && (p->scn || p->att)) {     // operand copies of the persistent kernel (recur.cu)
     o.Ht = take(R * D * f);
     if (p->att) {
       o.zk = take(R * E * f);
@@ -174,9 +174,9 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
       o.dbf = take(R * 4);
     }
     o.dXe = take(R * M * 4);
-    if (d.precision == CAPDEC_BF16 && p->scn) {
+    if (d.precision == CAPDEC_BF16 && (p->scn || p->att)) {
       o.dpre_gm = take(R * 4 * D * f);
-      o.duk = take(R * NQ * f);
+      if (p->scn) o.duk = take(R * NQ * f);
       o.dpxk = take(R * p->ldPX * f);
       if (p->att) o.att1_cm = take(B * P * A * f);
     }
@@ -416,24 +416,25 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
   // ---------------- the recurrence as ONE persistent cooperative kernel (recur.cu) ----------------
   bool persistent = false;
   RecurFwdArgs ra;
-  if (pr == CAPDEC_BF16 && p.scn && !fused && (!p.att || alphas)) {
+  if (pr == CAPDEC_BF16 && (p.scn || p.att) && !fused && (!p.att || alphas)) {
     ra.att = p.att ? 1 : 0;
+    ra.lstm = p.scn ? 0 : 1;
     ra.B = B; ra.T = T; ra.P = P; ra.E = E; ra.A = A; ra.M = M; ra.D = D; ra.F = F;
     ra.len = c.at<int32_t>(o.lenD);
     ra.Wcat1 = c.at(o.Wp_cat1); ra.ldD = p.ldD;
     ra.Wxz = c.ft(o.Wp_xq, M); ra.ldX = p.ldX;
-    ra.Wc = c.at(o.Wp_c); ra.ld2F = p.ld2F;
+    ra.Wc = p.scn ? c.at(o.Wp_c) : nullptr; ra.ld2F = p.ld2F;
     ra.b_cat1 = c.at<float>(o.b_cat1); ra.b_ih = w.b_ih; ra.b_hh = w.b_hh;
     if (p.att) {
       ra.att1 = c.at(o.att1); ra.enc = c.at(o.enc_s); ra.w_f = w.full_att_w; ra.b_f = w.full_att_b;
       ra.alphas = alphas; ra.awe = save_bwd ? c.at<float>(o.awe) : nullptr; ra.z = c.at(o.z);
       ra.scores = c.at<float>(o.att_scr);
     }
-    ra.v = c.at<float>(o.v); ra.q = c.at<float>(o.q);
+    ra.v = p.scn ? c.at<float>(o.v) : nullptr; ra.q = p.scn ? c.at<float>(o.q) : nullptr;
     ra.Ht = c.at(o.Ht); ra.zk = p.att ? c.at(o.zk) : nullptr; ra.enc_cm = p.att ? c.at(o.enc_cm) : nullptr;
     ra.H0 = c.at(o.H0); ra.ldH0 = p.ldD; ra.Hall = c.at(o.Hall); ra.Hd = drop ? c.at(o.Hd) : nullptr;
-    ra.C = c.at<float>(o.C); ra.U = c.at<float>(o.U); ra.g1 = c.at<float>(o.g1); ra.m = c.at(o.m);
-    ra.pre = c.at<float>(o.pre); ra.gates = c.at<float>(o.gates); ra.bar = c.at<unsigned>(o.bar);
+    ra.C = c.at<float>(o.C); ra.U = c.at<float>(o.U); ra.g1 = c.at<float>(o.g1); ra.m = p.scn ? c.at(o.m) : nullptr;
+    ra.pre = p.scn ? c.at<float>(o.pre) : nullptr; ra.gates = c.at<float>(o.gates); ra.bar = c.at<unsigned>(o.bar);
     ra.dropout_p = dropout_p; ra.seed = c.at<uint64_t>(o.seedD);
     persistent = recur_fwd_supported(ra);
   }
@@ -609,25 +610,37 @@ int backward(const CapdecDims& d, const CapdecParams& w,
 
   // ---------------- reverse-time recurrence as ONE persistent cooperative kernel (recur.cu) ----------------
   bool persistent = false;
-  if (pr == CAPDEC_BF16 && p.scn && !fused) {
+  if (pr == CAPDEC_BF16 && (p.scn || p.att) && !fused) {
     RecurBwdArgs rb;
     rb.att = p.att ? 1 : 0;
+    rb.lstm = p.scn ? 0 : 1;
     rb.B = B; rb.T = T; rb.P = P; rb.E = E; rb.A = A; rb.M = M; rb.D = D; rb.F = F; rb.ldPX = p.ldPX;
     rb.len = c.at<int32_t>(o.lenD);
-    rb.WcT = c.at(o.Wp_cT); rb.ldD = p.ldD;
+    rb.WcT = p.scn ? c.at(o.Wp_cT) : nullptr; rb.ldD = p.ldD;
     rb.Wxin = c.ft(o.Wp_xin, (int64_t)M * p.ldNQ); rb.ldNQ = p.ldNQ;
-    rb.Whx = c.at(o.Wp_hx); rb.ldhx = p.ldPX;
+    if (p.scn) {
+      rb.Whx = c.at(o.Wp_hx); rb.ldhx = p.ldPX;
+      rb.dbx = c.at(o.dpx); rb.ldbx = p.ldPX; rb.dbx_off = NQ;
+    } else {
+      rb.Whx = c.at(o.Wp_hq); rb.ldhx = p.ldNQ;          // W_hh^T [D][4D]
+      rb.Whx2 = c.at(o.Wp_b6); rb.ldhx2 = p.ldEA;        // [W_beta^T | W_d^T] [D][E+A]
+      rb.dbx = c.at(o.dba); rb.ldbx = p.ldEA; rb.dbx_off = 0;
+    }
     rb.dHfc = c.at<float>(o.dHfc); rb.gates = c.at<float>(o.gates); rb.C = c.at<float>(o.C);
     rb.dc = c.at<float>(o.dc); rb.dh_rec = c.at<float>(o.dh_rec);
     rb.dpre = c.at(o.dpre); rb.dpre_gm = c.at(o.dpre_gm);
-    rb.U = c.at<float>(o.U); rb.g1 = c.at<float>(o.g1); rb.v = c.at<float>(o.v); rb.q = c.at<float>(o.q);
-    rb.du = c.at(o.du); rb.duk = c.at(o.duk); rb.dpx = c.at(o.dpx); rb.dpxk = c.at(o.dpxk);
-    rb.dv_acc = c.at<float>(o.dv_acc); rb.dq_acc = c.at<float>(o.dq_acc);
+    rb.U = c.at<float>(o.U); rb.g1 = c.at<float>(o.g1);
+    if (p.scn) {
+      rb.v = c.at<float>(o.v); rb.q = c.at<float>(o.q);
+      rb.du = c.at(o.du); rb.duk = c.at(o.duk); rb.dpx = c.at(o.dpx);
+      rb.dv_acc = c.at<float>(o.dv_acc); rb.dq_acc = c.at<float>(o.dq_acc);
+    }
+    rb.dpxk = c.at(o.dpxk);
     if (p.att) {
       rb.dz = c.at<float>(o.dz); rb.awe = c.at<float>(o.awe); rb.alphas = alphas; rb.d_alphas = d_alphas;
       rb.enc_cm = c.at(o.enc_cm); rb.att1 = c.at(o.att1); rb.att1_cm = c.at(o.att1_cm); rb.w_f = w.full_att_w;
       RecurFwdArgs fa;        // did the forward (same dims, same switches) build the chunk-major feature copy?
-      fa.att = 1; fa.B = B; fa.T = T; fa.P = P; fa.E = E; fa.A = A; fa.M = M; fa.D = D; fa.F = F;
+      fa.att = 1; fa.lstm = p.scn ? 0 : 1; fa.B = B; fa.T = T; fa.P = P; fa.E = E; fa.A = A; fa.M = M; fa.D = D; fa.F = F;
       rb.enc = c.at(o.enc_s); rb.build_enc_cm = recur_fwd_supported(fa) ? 0 : 1;
       rb.part = c.at<float>(o.att_scr); rb.de = c.at<float>(o.de); rb.dwf = c.at<float>(o.dwf);
       rb.dbf = c.at<float>(o.dbf);

@@ -89,7 +89,8 @@ int expand_rows(int precision, const void* src, int64_t lds, void* dst, int64_t 
 
 // ---- recur.cu: persistent (one cooperative launch for all T steps) SCN decoder recurrence, bf16 ----
 struct RecurFwdArgs {
-  int att = 0;                       // 1: attention_scn, 0: pure_scn
+  int att = 0;                       // 1: attention_scn / pure_attention, 0: pure_scn
+  int lstm = 0;                      // 1: pure_attention (nn.LSTMCell, F unused)
   int B = 0, T = 0, P = 0, E = 0, A = 0, M = 0, D = 0, F = 0;
   const int32_t* len = nullptr;      // device [B]
   const void* Wcat1 = nullptr; int64_t ldD = 0;
@@ -111,13 +112,15 @@ struct RecurFwdArgs {
 bool recur_fwd_supported(const RecurFwdArgs& a);     // shape / device / CAPDEC_PERSISTENT check
 int recur_fwd(const RecurFwdArgs& a, cudaStream_t st);
 struct RecurBwdArgs {
-  int att = 0;
+  int att = 0, lstm = 0;
   int B = 0, T = 0, P = 0, E = 0, A = 0, M = 0, D = 0, F = 0;
   int64_t ldPX = 0;
   const int32_t* len = nullptr;
   const void* WcT = nullptr; int64_t ldD = 0;       // Wp_cT
   const void* Wxin = nullptr; int64_t ldNQ = 0;     // Wp_xin + M rows
-  const void* Whx = nullptr; int64_t ldhx = 0;      // Wp_hx
+  const void* Whx = nullptr; int64_t ldhx = 0;      // Wp_hx (LSTM: Wp_hq)
+  const void* Whx2 = nullptr; int64_t ldhx2 = 0;    // LSTM: Wp_b6
+  void* dbx = nullptr; int64_t ldbx = 0; int dbx_off = 0;   // destination of [dbeta_pre | datt2]
   const float* dHfc = nullptr; const float* gates = nullptr; const float* C = nullptr;
   float* dc = nullptr; float* dh_rec = nullptr;
   void* dpre = nullptr; void* dpre_gm = nullptr;

@@ -260,7 +260,10 @@ __device__ __noinline__ void load_weight_rows(uint8_t* Ws, const bf16* Wg, int64
   }
 }
 
-template <bool ATT, int NT1>
+// LSTM = true: the pure_attention decoder (nn.LSTMCell on [emb ; z], pure_attention.py:143-146, gate order
+// i,f,g,o): the G1 job yields [att2 | beta_pre | h W_hh^T], P3 adds z W_ih[:, M:]^T to the batched embedding
+// part, and the cell phase follows directly (no factor products, no P4).
+template <bool ATT, int NT1, bool LSTM = false>
 __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant__ FwdP p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NT3 = 2, NT4 = 2;
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
   uint8_t* W1s = stg + 2 * STAGE;
   uint8_t* W3s = W1s + (size_t)NT1 * 8 * w1s;
   uint8_t* W4s = W3s + (ATT ? (size_t)NT3 * 8 * w3s : 0);
-  float* red = reinterpret_cast<float*>(W4s + (size_t)NT4 * 8 * w4s);
+  float* red = reinterpret_cast<float*>(W4s + (LSTM ? 0 : (size_t)NT4 * 8 * w4s));
   float* al = red + KSL * 32 * REDLD;
   int* lens = reinterpret_cast<int*>(al + pad4i(P > 0 ? P : 4));
   uint64_t* bars = reinterpret_cast<uint64_t*>(lens + ((B + 3) & ~3) + 2);
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
   const int tpg = D / 8;
   const int t4 = blockIdx.x * NT4;                     // first P4 tile; tiles never straddle a gate
   const int gate4 = t4 / tpg, d4 = (t4 - gate4 * tpg) * 8;
-  const bool has1 = f1 < NG1, has3 = ATT && f3 < NQ, has4 = t4 < 4 * tpg;
+  const bool has1 = f1 < NG1, has3 = ATT && f3 < NQ, has4 = !LSTM && t4 < 4 * tpg;
   // ---- one-time: weight slices -> shared memory ----
   if (has1) load_weight_rows(W1s, p.Wcat1 + (int64_t)f1 * p.ldD, p.ldD, D, NT1 * 8, NG1 - f1);
   if (has3) load_weight_rows(W3s, p.Wxz + (int64_t)f3 * p.ldX, p.ldX, E, NT3 * 8, NQ - f3);
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
       for (int i = 0; i < NT1 / 2; ++i) {              // epilogue operands first: hidden behind the GEMM
         const int nf = f1 + i * 16 + ej;
         bias1[i] = nf < NG1 ? __ldg(p.b_cat1 + nf) : 0.f;
-        q1[i] = (erow < n && nf >= col0 && nf < NG1) ? __ldg(p.q + (int64_t)erow * NQ + (nf - col0)) : 0.f;
+        q1[i] = (!LSTM && erow < n && nf >= col0 && nf < NG1) ? __ldg(p.q + (int64_t)erow * NQ + (nf - col0)) : 0.f;
       }
       float out[NT1 / 2];
       gemm_job<NT1 / 2, 2>(pp, hprev, 0, n, W1s, w1s, 1, red, out);
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
           if (nf < NG1) {
             const float val = out[i] + bias1[i];
             g1[nf] = val;
-            if (nf >= col0) {
+            if (!LSTM && nf >= col0) {
               const int nn = nf - col0;
               const int gg = nn / F, f = nn - gg * F;
               p.m[((int64_t)gg * p.R + tb + erow) * 2 * F + F + f] = __float2bfloat16_rn(val * q1[i]);
@@ -532,14 +535,16 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
         const bool ok3 = erow < n && nf < NQ;
         float* U = p.U + (tb + erow) * NQ;
         const float u_emb = ok3 ? __ldg(U + nf) : 0.f;           // written by the batched GEMM before this kernel
-        const float v3 = ok3 ? __ldg(p.v + (int64_t)erow * NQ + nf) : 0.f;
+        const float v3 = (!LSTM && ok3) ? __ldg(p.v + (int64_t)erow * NQ + nf) : 0.f;
         float out[1];
         gemm_job<1, 2>(pp, p.zk + (int64_t)t * chunks * B * CHUNK, (int64_t)B * CHUNK, n, W3s, w3s, E / KC, red, out);
         if (ok3) {
           const float val = out[0] + u_emb;
           U[nf] = val;
-          const int gg = nf / F, f = nf - gg * F;
-          p.m[((int64_t)gg * p.R + tb + erow) * 2 * F + f] = __float2bfloat16_rn(val * v3);
+          if (!LSTM) {
+            const int gg = nf / F, f = nf - gg * F;
+            p.m[((int64_t)gg * p.R + tb + erow) * 2 * F + f] = __float2bfloat16_rn(val * v3);
+          }
         }
       }
       RECUR_STAMP();
@@ -547,17 +552,19 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
     grid_arrive(p.bar);
     grid_wait(p.bar, target);
     RECUR_STAMP();
-    // ================= P4: pre_g = m_g [W_ic_g | W_hc_g]^T  (the n x 2F operand is one bulk copy) =========
-    if (has4 && (p.mask & 16)) {
-      float out[1];
-      gemm_job<1, 4>(pp, p.m + ((int64_t)gate4 * p.R + tb) * 2 * F, 0, n, W4s, w4s, 1, red, out);
-      const int d = d4 + ej;
-      if (erow < n && d < D) p.pre[(tb + erow) * 4 * D + (int64_t)gate4 * D + d] = out[0];
+    if (!LSTM) {
+      // ================= P4: pre_g = m_g [W_ic_g | W_hc_g]^T  (the n x 2F operand is one bulk copy) =========
+      if (has4 && (p.mask & 16)) {
+        float out[1];
+        gemm_job<1, 4>(pp, p.m + ((int64_t)gate4 * p.R + tb) * 2 * F, 0, n, W4s, w4s, 1, red, out);
+        const int d = d4 + ej;
+        if (erow < n && d < D) p.pre[(tb + erow) * 4 * D + (int64_t)gate4 * D + d] = out[0];
+      }
+      RECUR_STAMP();
+      grid_arrive(p.bar);
+      grid_wait(p.bar, target);
+      RECUR_STAMP();
     }
-    RECUR_STAMP();
-    grid_arrive(p.bar);
-    grid_wait(p.bar, target);
-    RECUR_STAMP();
     // ================= LSTM pointwise (scn_cell.py:146-152), gate order i,f,o,c =================
     {
       const int total = (p.mask & 32) ? n * D : 0;
@@ -566,11 +573,21 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
 #pragma unroll 1
       for (int i = blockIdx.x * RT + tid; i < total; i += gridDim.x * RT) {
         const int b = i / D, d = i - b * D;
-        const float* pre = p.pre + (tb + b) * 4 * D + d;
         float x[4];
+        if (LSTM) {
+          // pre = (Emb W_ih[:M] + z W_ih[M:]) + h W_hh + b_ih + b_hh, torch gate order i,f,g,o
+          const float* ua = p.U + (tb + b) * NQ + d;
+          const float* hb = p.g1 + (tb + b) * NG1 + col0 + d;
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq)
-          x[gq] = __ldcg(pre + gq * D) + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
+          for (int gq = 0; gq < 4; ++gq)
+            x[gq] = __ldcg(ua + gq * D) + __ldcg(hb + gq * D) + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
+          const float t2 = x[2]; x[2] = x[3]; x[3] = t2;        // -> i, f, o, g
+        } else {
+          const float* pre = p.pre + (tb + b) * 4 * D + d;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq)
+            x[gq] = __ldcg(pre + gq * D) + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
+        }
         const float ig = fsigmoid(x[0]), fg = fsigmoid(x[1]), og = fsigmoid(x[2]);
         const float gg = ftanh(x[3]);
         const float c = fg * __ldcg(c_prev + i) + ig * gg;
@@ -614,7 +631,9 @@ struct BwdP {
   const int32_t* len;
   const bf16* WcT; int64_t ldD;       // [4][2F][ldD]   [W_ic_g^T ; W_hc_g^T]
   const bf16* Wxin; int64_t ldNQ;     // [E][ldNQ]      W_ia[M:, :] (already offset by M rows)
-  const bf16* Whx; int64_t ldhx;      // [D][ldhx]      [W_ha | W_beta^T | W_d^T]
+  const bf16* Whx; int64_t ldhx;      // [D][ldhx]      [W_ha | W_beta^T | W_d^T]   (LSTM: W_hh^T [D][4D])
+  const bf16* Whx2; int64_t ldhx2;    // LSTM only: [W_beta^T | W_d^T]  [D][E+A]
+  bf16* dbx; int64_t ldbx; int dbx_off;   // where [dbeta_pre | datt2] of a row go: dpx + 4F (SCN) or dba (LSTM)
   const float* dHfc;                  // (B, T, D) fp32: d loss / d h_t through the vocabulary projection
   const float* gates; const float* C;
   float* dc;                          // [B][D]
@@ -638,7 +657,10 @@ struct BwdP {
   long long* prof;                    // debug (CAPDEC_RECUR_PROF=1): [T][16] clock64 stamps of CTA 0
 };
 
-template <bool ATT>
+// LSTM = true (pure_attention): no factor products (phase W is skipped), dz = dpre W_ih[:, M:], the recurrent
+// gradient contracts [dpre | dbeta_pre | datt2] with [W_hh | W_beta^T | W_d^T] held in two weight matrices, and
+// the attention gradients go to the [dbeta_pre | datt2] buffer of that decoder.
+template <bool ATT, bool LSTM = false>
 __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant__ BwdP p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int D = p.D, E = p.E, F = p.F, B = p.B, T = p.T, P = p.P, NQ = p.NQ, NG1 = p.NG1, A = p.A;
@@ -666,7 +688,7 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
   // ---- roles ----
   const int c = blockIdx.x;
   const int spg = 2 * F / 32;                             // 32-feature slices per gate of the W job
-  const bool hasW = c < 4 * spg;
+  const bool hasW = !LSTM && c < 4 * spg;
   const int gateW = c / spg, fW0 = (c - gateW * spg) * 32;
   const bool hasZ = ATT && c * 16 < E;
   const int eZ0 = c * 16;
@@ -681,8 +703,12 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
     const int j = c + i * gridDim.x;
     if (j < jobsH) {
       const int ds = j / nkc, kc = j - ds * nkc;
-      load_weight_rows(WHs + (size_t)i * 16 * wHs, p.Whx + (int64_t)ds * 16 * p.ldhx + (int64_t)kc * KC, p.ldhx, KC, 16,
-                       D - ds * 16);
+      if (LSTM && kc >= nkq)
+        load_weight_rows(WHs + (size_t)i * 16 * wHs, p.Whx2 + (int64_t)ds * 16 * p.ldhx2 + (int64_t)(kc - nkq) * KC,
+                         p.ldhx2, KC, 16, D - ds * 16);
+      else
+        load_weight_rows(WHs + (size_t)i * 16 * wHs, p.Whx + (int64_t)ds * 16 * p.ldhx + (int64_t)kc * KC, p.ldhx, KC, 16,
+                         D - ds * 16);
     }
   }
   for (int i = tid; i < B; i += RT) lens[i] = p.len[i];
@@ -724,8 +750,10 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
         const float ig = __ldg(gp), fg = __ldg(gp + D), og = __ldg(gp + 2 * D), gg = __ldg(gp + 3 * D);
         const float tc = ftanh(__ldg(c_new + i));
         const float dcn = p.dc[i] + dh * og * (1.f - tc * tc);
+        const float dpo = dh * tc * og * (1.f - og), dpg = dcn * ig * (1.f - gg * gg);
+        // pre-activation slots: i, f, o, c (SCN cell) or i, f, g, o (nn.LSTMCell)
         const float dpv[4] = {dcn * gg * ig * (1.f - ig), dcn * __ldg(c_prev + i) * fg * (1.f - fg),
-                              dh * tc * og * (1.f - og), dcn * ig * (1.f - gg * gg)};       // i, f, o, c
+                              LSTM ? dpg : dpo, LSTM ? dpo : dpg};
         p.dc[i] = dcn * fg;
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
@@ -783,13 +811,16 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
     }
     BSTAMP();
     if (ATT) {
-      grid_arrive(p.bar);
-      grid_wait(p.bar, target);
+      if (!LSTM) {
+        grid_arrive(p.bar);
+        grid_wait(p.bar, target);
+      }
       BSTAMP();
-      // ================= Z: dz = du W_ia[M:]^T =================
+      // ================= Z: dz = du W_ia[M:]^T   (LSTM: dpre W_ih[:, M:]) =================
       if (hasZ) {
         float out[1];
-        gemm_job<1, 2>(pp, p.duk + (int64_t)t * nkq * B * KC, (int64_t)B * KC, n, WZs, wZs, nkq, red, out);
+        gemm_job<1, 2>(pp, LSTM ? p.dpre_gm + (int64_t)t * 4 * B * D : p.duk + (int64_t)t * nkq * B * KC,
+                       (int64_t)B * KC, n, WZs, wZs, nkq, red, out);
         const int e = eZ0 + ej;
         if (erow < n && e < E) p.dz[(tb + erow) * E + e] = out[0];
       }
@@ -835,7 +866,7 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             }
             if (grp == 0) {
               const uint4 pk = pack16(db, bf16());
-              *reinterpret_cast<uint4*>(p.dpx + (tb + row) * p.ldPX + NQ + e0) = pk;
+              *reinterpret_cast<uint4*>(p.dbx + (tb + row) * p.ldbx + p.dbx_off + e0) = pk;
               *reinterpret_cast<uint4*>(p.dpxk + (((int64_t)t * nkc + nkq + chunk) * B + row) * KC + col * 8) = pk;
             }
           }
@@ -973,7 +1004,7 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             const int a = qa * QW + aa;
             if (which == 0) {
               const bf16 xb = __float2bfloat16_rn(sum);
-              p.dpx[(tb + row) * p.ldPX + NQ + E + a] = xb;
+              p.dbx[(tb + row) * p.ldbx + p.dbx_off + E + a] = xb;
               p.dpxk[(((int64_t)t * nkc + nkq + chunks) * B + row) * KC + a] = xb;
             } else {
               p.dwf[(tb + row) * A + a] = sum;
@@ -994,7 +1025,9 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
       if (j < jobsH) {
         const int ds = j / nkc, kc = j - ds * nkc;
         float out[1];
-        gemm_job<1, 2>(pp, p.dpxk + ((int64_t)t * nkc + kc) * B * KC, 0, n, WHs + (size_t)i * 16 * wHs, wHs, 1, red, out);
+        const bf16* srcH = (LSTM && kc < nkq) ? p.dpre_gm + ((int64_t)t * 4 + kc) * B * D
+                                              : p.dpxk + ((int64_t)t * nkc + kc) * B * KC;
+        gemm_job<1, 2>(pp, srcH, 0, n, WHs + (size_t)i * 16 * wHs, wHs, 1, red, out);
         const int d = ds * 16 + ej;
         if (erow < n && d < D) atomicAdd(p.dh_rec + (tb + erow) * D + d, out[0]);
       }
@@ -1069,15 +1102,16 @@ bool persistent_enabled() {
 bool plan_fwd(const RecurFwdArgs& a, const DevInfo* di, int* nt1, int* nt3, int* nt4, size_t* smem) {
   if (!di || !di->coop || di->sms < 8) return false;
   if (a.B < 1 || a.B > 32 || a.T < 1) return false;
-  if (a.D != KC || 2 * a.F != 2 * KC) return false;     // G1 operand = one 512-wide fill, P4 operand = one 1024-wide fill
+  if (a.D != KC || (!a.lstm && 2 * a.F != 2 * KC)) return false;   // G1 operand = one 512-wide fill, P4 operand = one 1024-wide fill
+  if (a.lstm && !a.att) return false;
   if (a.att && (a.E % KC || a.E % CHUNK || a.A % 8 || a.A > 512 || a.P < 1 || a.P > RT)) return false;
-  const int NQ = 4 * a.F, NG1 = (a.att ? a.A + a.E : 0) + NQ;
+  const int NQ = a.lstm ? 4 * a.D : 4 * a.F, NG1 = (a.att ? a.A + a.E : 0) + NQ;
   *nt1 = pick_nt(NG1 / 8, di->sms);
   *nt3 = a.att ? pick_nt(NQ / 8, di->sms) : 2;
   *nt4 = pick_nt(4 * (a.D / 8), di->sms);
   if (!*nt1 || *nt3 != 2 || *nt4 != 2) return false;
   if ((a.D / 8) % *nt4) return false;               // a CTA's P4 tiles stay inside one gate
-  *smem = fwd_smem_bytes(a, *nt1, *nt3, *nt4);
+  *smem = fwd_smem_bytes(a, *nt1, *nt3, a.lstm ? 0 : *nt4);
   return *smem <= (size_t)di->smem_optin;
 }
 
@@ -1099,7 +1133,7 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   FwdP p;
   memset(&p, 0, sizeof p);
   p.B = a.B; p.T = a.T; p.P = a.P; p.E = a.E; p.A = a.A; p.M = a.M; p.D = a.D; p.F = a.F;
-  p.NQ = 4 * a.F; p.NG1 = (a.att ? a.A + a.E : 0) + p.NQ; p.R = (int64_t)a.B * a.T;
+  p.NQ = a.lstm ? 4 * a.D : 4 * a.F; p.NG1 = (a.att ? a.A + a.E : 0) + p.NQ; p.R = (int64_t)a.B * a.T;
   p.len = a.len; p.Wcat1 = (const bf16*)a.Wcat1; p.ldD = a.ldD; p.Wxz = (const bf16*)a.Wxz; p.ldX = a.ldX;
   p.Wc = (const bf16*)a.Wc; p.ld2F = a.ld2F; p.b_cat1 = a.b_cat1; p.b_ih = a.b_ih; p.b_hh = a.b_hh;
   p.att1 = (const bf16*)a.att1; p.enc_cm = (const bf16*)a.enc_cm; p.w_f = a.w_f; p.b_f = a.b_f; p.v = a.v; p.q = a.q;
@@ -1107,8 +1141,9 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   p.g1 = a.g1; p.alphas = a.alphas; p.awe = a.awe; p.z = (bf16*)a.z; p.m = (bf16*)a.m; p.pre = a.pre;
   p.gates = a.gates; p.scores = a.scores; p.bar = a.bar; p.dropout_p = a.dropout_p; p.seed = a.seed;
 
-  auto kernel = a.att ? (nt1 == 4 ? recur_fwd_kernel<true, 4> : recur_fwd_kernel<true, 2>)
-                      : (nt1 == 4 ? recur_fwd_kernel<false, 4> : recur_fwd_kernel<false, 2>);
+  auto kernel = a.lstm ? (nt1 == 4 ? recur_fwd_kernel<true, 4, true> : recur_fwd_kernel<true, 2, true>)
+                : a.att ? (nt1 == 4 ? recur_fwd_kernel<true, 4> : recur_fwd_kernel<true, 2>)
+                        : (nt1 == 4 ? recur_fwd_kernel<false, 4> : recur_fwd_kernel<false, 2>);
   CAPDEC_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CAPDEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RT, smem));
@@ -1168,7 +1203,7 @@ namespace {
 size_t bwd_smem_bytes(const RecurBwdArgs& a) {
   size_t s = 2 * (size_t)STAGE;
   s += (size_t)32 * (a.D * 2 + WPAD);
-  if (a.att) s += (size_t)16 * (4 * a.F * 2 + WPAD);
+  if (a.att) s += (size_t)16 * ((a.lstm ? 4 * a.D : 4 * a.F) * 2 + WPAD);
   s += (size_t)32 * (KC * 2 + WPAD);
   s += (size_t)KSL * 32 * REDLD * 4;
   s += (size_t)2 * pad4i(a.P > 0 ? a.P : 4) * 4;
@@ -1179,10 +1214,11 @@ size_t bwd_smem_bytes(const RecurBwdArgs& a) {
 bool plan_bwd(const RecurBwdArgs& a, const DevInfo* di, size_t* smem) {
   if (!di || !di->coop || di->sms < 8) return false;
   if (a.B < 1 || a.B > 32 || a.T < 1) return false;
-  if (a.D != KC || a.F % 16 || (4 * a.F) % KC) return false;
+  if (a.lstm && !a.att) return false;
+  if (a.D != KC || (!a.lstm && (a.F % 16 || (4 * a.F) % KC))) return false;
   if (a.att && (a.E % KC || a.A != KC || a.P < 1 || a.P > RT)) return false;
-  const int NQ = 4 * a.F, KH = NQ + (a.att ? a.E + a.A : 0);
-  if (4 * (2 * a.F / 32) > di->sms) return false;               // W job: one 32-feature slice per CTA
+  const int NQ = a.lstm ? 4 * a.D : 4 * a.F, KH = NQ + (a.att ? a.E + a.A : 0);
+  if (!a.lstm && 4 * (2 * a.F / 32) > di->sms) return false;    // W job: one 32-feature slice per CTA
   if (a.att && a.E / 16 > di->sms) return false;                // Z job: 16 features per CTA
   if ((a.D / 16) * (KH / KC) > 2 * di->sms) return false;       // H jobs: at most two per CTA
   // red also holds the [2][A] accumulators of phase B
@@ -1206,7 +1242,8 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
   BwdP p;
   memset(&p, 0, sizeof p);
   p.B = a.B; p.T = a.T; p.P = a.P; p.E = a.E; p.A = a.A; p.M = a.M; p.D = a.D; p.F = a.F;
-  p.NQ = 4 * a.F; p.NG1 = (a.att ? a.A + a.E : 0) + p.NQ; p.R = (int64_t)a.B * a.T; p.ldPX = a.ldPX;
+  p.NQ = a.lstm ? 4 * a.D : 4 * a.F; p.NG1 = (a.att ? a.A + a.E : 0) + p.NQ; p.R = (int64_t)a.B * a.T; p.ldPX = a.ldPX;
+  p.Whx2 = (const bf16*)a.Whx2; p.ldhx2 = a.ldhx2; p.dbx = (bf16*)a.dbx; p.ldbx = a.ldbx; p.dbx_off = a.dbx_off;
   p.len = a.len; p.WcT = (const bf16*)a.WcT; p.ldD = a.ldD; p.Wxin = (const bf16*)a.Wxin; p.ldNQ = a.ldNQ;
   p.Whx = (const bf16*)a.Whx; p.ldhx = a.ldhx; p.dHfc = a.dHfc; p.gates = a.gates; p.C = a.C; p.dc = a.dc;
   p.dh_rec = a.dh_rec; p.dpre = (bf16*)a.dpre; p.dpre_gm = (bf16*)a.dpre_gm; p.U = a.U; p.g1 = a.g1; p.v = a.v;
@@ -1214,7 +1251,7 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
   p.dv_acc = a.dv_acc; p.dq_acc = a.dq_acc; p.dz = a.dz; p.awe = a.awe; p.alphas = a.alphas; p.d_alphas = a.d_alphas;
   p.enc_cm = (const bf16*)a.enc_cm; p.att1_cm = (const bf16*)a.att1_cm; p.w_f = a.w_f; p.part = a.part; p.de = a.de;
   p.dwf = a.dwf; p.dbf = a.dbf; p.bar = a.bar; p.dropout_p = a.dropout_p; p.seed = a.seed;
-  auto kernel = a.att ? recur_bwd_kernel<true> : recur_bwd_kernel<false>;
+  auto kernel = a.lstm ? recur_bwd_kernel<true, true> : a.att ? recur_bwd_kernel<true> : recur_bwd_kernel<false>;
   CAPDEC_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CAPDEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RT, smem));

@@ -290,7 +290,7 @@ def test_bf16_full_width_matches_oracle(kind, persistent, monkeypatch):
 
 
 @pytest.mark.parametrize("train_mode", [False, True])
-@pytest.mark.parametrize("kind", [O.ATTENTION_SCN, O.PURE_SCN])
+@pytest.mark.parametrize("kind", [O.ATTENTION_SCN, O.PURE_SCN, O.PURE_ATTENTION])
 def test_persistent_recurrence_matches_step_kernels(kind, train_mode, monkeypatch):
     """Config-3 per-GPU shape (B=32, ragged lengths): the persistent cooperative kernels (recur.cu) and
     the per-step kernel chains are two schedules of the same bf16 arithmetic -- outputs, saved state and
