@@ -32,6 +32,8 @@
 // attention / channel dims use warp shuffles.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -289,6 +291,151 @@ attn_wsum_kernel(WsumArgs a) {
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// forward B, streaming variant for large batches (beam search: 1 875 rows, 0.5 GB of features per step,
+// HBM-bound): the chunk-major feature copy enc_cm [map][E/512][P][512] makes the P x 512 slab of a
+// (map, chunk) item contiguous, so the pixels stream through a 3-stage shared-memory ring with ONE
+// cp.async.bulk (32 pixels = 32 KB) per stage -- the bytes in flight no longer depend on registers,
+// and two CTAs per SM overlap each other's softmax / epilogue.  RPM rows (beams) share the item.
+// ---------------------------------------------------------------------------------------
+constexpr int WS_STAGES = 3;
+constexpr int WS_PX = 32;                       // pixels per stage
+constexpr int WS_CH = 512;                      // channels per item
+constexpr int WS_STAGE_BYTES = WS_PX * WS_CH * 2;
+
+template <int RPM>
+__global__ void __launch_bounds__(NT)
+attn_wsum_stream_kernel(WsumArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* stg = smem_raw;
+  float* al = reinterpret_cast<float*>(stg + WS_STAGES * WS_STAGE_BYTES);     // [RPM][Ppad]
+  const int P = a.P, E = a.E;
+  const int Ppad = pad4(P);
+  float* red = al + RPM * Ppad;                                               // [3 * 64 * 8] + block reductions
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 3 * 64 * 8 + 32);
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = blockIdx.x, map = blockIdx.y;
+  const int row0 = map * RPM;
+  const int chunks = E / WS_CH;
+  const bf16* src = (const bf16*)a.enc + ((int64_t)map * chunks + chunk) * P * WS_CH;
+  const int nfill = (P + WS_PX - 1) / WS_PX;
+  uint32_t full[WS_STAGES];
+#pragma unroll
+  for (int s = 0; s < WS_STAGES; ++s) full[s] = smem_u32(&bars[s]);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < WS_STAGES; ++s) mbar_init(full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto fill = [&](int fi) {
+    if (tid == 0) {
+      const int s = fi % WS_STAGES;
+      const uint32_t bytes = (uint32_t)min(WS_PX, P - fi * WS_PX) * WS_CH * 2;
+      mbar_expect_tx(full[s], bytes);
+      bulk_g2s(smem_u32(stg) + s * WS_STAGE_BYTES, src + (int64_t)fi * WS_PX * WS_CH, bytes, full[s]);
+    }
+  };
+  // the features do not depend on the previous kernel: the ring is filled before the PDL wait
+#pragma unroll
+  for (int fi = 0; fi < WS_STAGES; ++fi)
+    if (fi < nfill) fill(fi);
+  pdl_wait();
+  // ---- softmax over the P scores of every row of this CTA ----
+#pragma unroll 1
+  for (int j = 0; j < RPM; ++j) {
+    const float* sc = a.scores + (int64_t)(row0 + j) * Ppad;
+    float* alj = al + j * Ppad;
+    float m = -INFINITY;
+    for (int p = tid; p < P; p += NT) { const float s = sc[p]; alj[p] = s; m = fmaxf(m, s); }
+    m = block_max<NT>(m, red);
+    float sum = 0.f;
+    for (int p = tid; p < P; p += NT) { const float e = expf(alj[p] - m); alj[p] = e; sum += e; }
+    sum = block_sum<NT>(sum, red);
+    const float inv = 1.0f / sum;
+    for (int p = tid; p < P; p += NT) {
+      const float v = alj[p] * inv;
+      alj[p] = v;
+      if (chunk == 0 && a.alpha_out) a.alpha_out[(int64_t)(row0 + j) * a.alpha_stride + p] = v;
+    }
+  }
+  __syncthreads();
+  // ---- weighted sums: thread = (pixel group of 4, 16-byte column of 64) ----
+  const int grp = tid >> 6, col = tid & 63;
+  float acc[RPM][8];
+#pragma unroll
+  for (int j = 0; j < RPM; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+#pragma unroll 1
+  for (int fi = 0; fi < nfill; ++fi) {
+    const int s = fi % WS_STAGES;
+    const int px0 = fi * WS_PX, cnt = min(WS_PX, P - px0);
+    mbar_wait(full[s], (fi / WS_STAGES) & 1);
+    const uint8_t* base = stg + s * WS_STAGE_BYTES + col * 16;
+#pragma unroll
+    for (int u = 0; u < WS_PX / 4; ++u) {
+      const int pl = grp + u * 4;
+      if (pl < cnt) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(base + (size_t)pl * WS_CH * 2);
+        float f[8];
+        unpack16(raw, f, bf16());
+#pragma unroll
+        for (int j = 0; j < RPM; ++j) {
+          const float w = al[j * Ppad + px0 + pl];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(w, f[k], acc[j][k]);
+        }
+      }
+    }
+    if (fi + WS_STAGES < nfill) {
+      __syncthreads();                  // every warp is done with stage s
+      fill(fi + WS_STAGES);
+    }
+  }
+  // ---- cross-group reduction, gate, outputs ----
+#pragma unroll 1
+  for (int j = 0; j < RPM; ++j) {
+    float accj[8];
+#pragma unroll
+    for (int jj = 0; jj < RPM; ++jj)
+      if (jj == j) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) accj[k] = acc[jj][k];
+      }
+    __syncthreads();
+    if (grp > 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[((grp - 1) * 64 + col) * 8 + k] = accj[k];
+    }
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+      for (int g = 1; g < 4; ++g)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) accj[k] += red[((g - 1) * 64 + col) * 8 + k];
+      const int row = row0 + j;
+      const int e0 = chunk * WS_CH + col * 8;
+      const float* g1 = a.g1 + (int64_t)row * a.ldg;
+      float zv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float gate = 1.0f;
+        if (a.beta_col >= 0) gate = sigmoidf_(g1[a.beta_col + e0 + k]);
+        zv[k] = gate * accj[k];
+      }
+      if (a.awe_out) {
+        float* dst = a.awe_out + (int64_t)row * E + e0;
+        *reinterpret_cast<float4*>(dst) = make_float4(accj[0], accj[1], accj[2], accj[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(accj[4], accj[5], accj[6], accj[7]);
+      }
+      if (a.z_out) *reinterpret_cast<uint4*>((bf16*)a.z_out + (int64_t)row * a.ldz + e0) = pack16(zv, bf16());
+    }
+  }
+  (void)lane; (void)warp;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -610,10 +757,24 @@ size_t attention_scratch_floats(int precision, int rows, int P, int E) {
   return (size_t)rows * (size_t)c.EC * Ppad;
 }
 
+namespace {
+template <int RPM>
+int launch_wsum_stream(const WsumArgs& wa, int maps, cudaStream_t st) {
+  auto kernel = attn_wsum_stream_kernel<RPM>;
+  const size_t smem = (size_t)WS_STAGES * WS_STAGE_BYTES + (size_t)(RPM * ((wa.P + 3) & ~3) + 3 * 64 * 8 + 32) * 4 +
+                      WS_STAGES * 8 + 16;
+  static std::once_flag once;
+  static cudaError_t rc = cudaSuccess;
+  std::call_once(once, [&] { rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); });
+  CAPDEC_REQUIRE(rc == cudaSuccess && smem <= 112 * 1024, CAPDEC_ERR_CUDA, "attn_wsum_stream: smem %zu", smem);
+  return launch_attn(kernel, dim3(wa.E / WS_CH, maps, 1), NT, smem, st, wa);
+}
+}  // namespace
+
 int attention_fwd(int precision, const void* att1, const void* enc, const float* g1, int64_t ldg,
                   int beta_col, const float* w_f, const float* b_f, float* alpha_out,
                   int64_t alpha_stride, void* z_out, int64_t ldz, float* awe_out, int rows,
-                  int rows_per_map, int P, int E, int A, float* scratch, cudaStream_t st) {
+                  int rows_per_map, int P, int E, int A, float* scratch, cudaStream_t st, const void* enc_cm) {
   if (rows <= 0) return CAPDEC_OK;
   const int vec = precision == CAPDEC_BF16 ? 8 : 4;
   CAPDEC_REQUIRE(E % vec == 0 && A % vec == 0 && A <= 32 * vec * 4, CAPDEC_ERR_BAD_SHAPE,
@@ -642,6 +803,20 @@ int attention_fwd(int precision, const void* att1, const void* enc, const float*
     else CAPDEC_TRY(launch_attn(attn_scores_kernel<float, 4, 1>, gs, NT, 0, st, sa));
   }
   // ---- B: softmax + weighted sum + gate ----
+  const char* force = getenv("CAPDEC_WSUM_STREAM");          // tests: 1 forces the streaming kernel at any size
+  const bool stream_ok = enc_cm != nullptr && precision == CAPDEC_BF16 && E % WS_CH == 0 && rpm == rows_per_map;
+  if (stream_ok && (gy >= 148 || (force && force[0] == '1')) && !(force && force[0] == '0')) {
+    // large batches: shared-memory ring fed by bulk copies from the chunk-major feature copy
+    WsumArgs ws{enc_cm, g1, ldg, beta_col, scratch, alpha_out, alpha_stride, z_out, ldz, awe_out,
+                rows_per_map, P, E, 0};
+    switch (rpm) {
+      case 1: return launch_wsum_stream<1>(ws, gy, st);
+      case 2: return launch_wsum_stream<2>(ws, gy, st);
+      case 3: return launch_wsum_stream<3>(ws, gy, st);
+      case 4: return launch_wsum_stream<4>(ws, gy, st);
+      case 5: return launch_wsum_stream<5>(ws, gy, st);
+    }
+  }
   const Chunking ch = pick_chunks(E, vec, gy);
   WsumArgs wa{enc, g1, ldg, beta_col, scratch, alpha_out, alpha_stride, z_out, ldz, awe_out,
               rows_per_map, P, E, ch.ncol};

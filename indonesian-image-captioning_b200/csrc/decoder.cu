@@ -918,7 +918,7 @@ struct BeamPlan {
   Plan w;                 // weight offsets only (built for B = 1, T = 1)
   int R;
   struct Off {
-    size_t enc_f, att1, mean, meanF, meanX, tagsG, tagsX, v, q, H, C, Hn, Cn, Xe, U, g1, z, m, pre,
+    size_t enc_f, enc_cm, att1, mean, meanF, meanX, tagsG, tagsX, v, q, H, C, Hn, Cn, Xe, U, g1, z, m, pre,
         logits, alpha_hist, att_scr, prev_word, scoreA, scoreB, src_row, live, krem, has_done, best_score,
         best_t, best_parent, bp_parent, bp_word, total;
   } o;
@@ -940,6 +940,7 @@ int make_beam_plan(const CapdecDims& d_in, int G, int k, int n_steps, bool want_
   BeamPlan::Off& o = bp->o;
   memset(&o, 0, sizeof o);
   o.enc_f = take((size_t)G * P * E * f);
+  if (p.att && d.precision == CAPDEC_BF16 && E % 512 == 0) o.enc_cm = take((size_t)G * P * E * f);   // streaming weighted sum
   if (p.att) o.att1 = take((size_t)G * P * A * f);
   o.mean = take((size_t)G * E * 4);
   o.meanF = take((size_t)G * p.ldE * f);
@@ -1022,6 +1023,8 @@ int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, co
   if (p.att)
     CAPDEC_TRY(G_(c, c.at(o.enc_f), E, c.at(p.o.Wp_e), p.ldE, c.at(o.att1), A, 1, w.enc_att_b, nullptr, 0,
                   G * P, A, E));
+  const bool have_cm = p.att && pr == CAPDEC_BF16 && E % 512 == 0;
+  if (have_cm) CAPDEC_TRY(chunk_major_copy(c.at(o.enc_f), c.at(o.enc_cm), G, P, E, 512, st));
   CAPDEC_TRY(expand_rows(pr, c.at(o.meanF), p.ldE, c.at(o.meanX), p.ldE, G, k, E, st));
   CAPDEC_TRY(G_(c, c.at(o.meanX), p.ldE, c.ft(p.o.Wp_init, 0), p.ldE, c.at(o.H), p.ldD, 1, w.init_h_b,
                 nullptr, 0, R, D, E));
@@ -1065,7 +1068,8 @@ int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, co
     if (p.att) {
       float* alpha_t = c.at<float>(o.alpha_hist) + (want_alpha ? (int64_t)t * R * P : 0);
       CAPDEC_TRY(attention_fwd(pr, c.at(o.att1), c.at(o.enc_f), g1, NG1, A, w.full_att_w, w.full_att_b,
-                               alpha_t, P, c.at(o.z), E, nullptr, R, k, P, E, A, c.at<float>(o.att_scr), st));
+                               alpha_t, P, c.at(o.z), E, nullptr, R, k, P, E, A, c.at<float>(o.att_scr), st,
+                               have_cm ? c.at(o.enc_cm) : nullptr));
       CAPDEC_TRY(G_(c, c.at(o.z), E, c.ft(p.o.Wp_xq, M), p.ldX, U, NQ, 0, nullptr, U, NQ, R, NQ, E));
     }
     if (p.scn) {

@@ -11,7 +11,10 @@ size_t attention_scratch_floats(int precision, int rows, int P, int E);
 int attention_fwd(int precision, const void* att1, const void* enc, const float* g1, int64_t ldg,
                   int beta_col, const float* w_f, const float* b_f, float* alpha_out,
                   int64_t alpha_stride, void* z_out, int64_t ldz, float* awe_out, int rows,
-                  int rows_per_map, int P, int E, int A, float* scratch, cudaStream_t st);
+                  int rows_per_map, int P, int E, int A, float* scratch, cudaStream_t st,
+                  const void* enc_cm = nullptr);      // optional chunk-major feature copy [map][E/512][P][512]
+// dst[b][c][p][j] = src[b][p][c*cw + j]   (bf16; chunk-major copies for one-bulk-copy staging fills)
+int chunk_major_copy(const void* src, void* dst, int B, int P, int E, int cw, cudaStream_t st);
 // de_out (rows, pad4(P)) receives the softmax-input gradient of every pixel (consumed by attention_datt1)
 int attention_bwd(int precision, const void* att1, const void* enc, const float* g1, int64_t ldg,
                   int beta_col, const float* w_f, const float* alpha, int64_t alpha_stride,

@@ -51,36 +51,6 @@ constexpr int SCI = 2 * STAGE / 1024;       // score items (<= 1 KB each) the tw
 
 __host__ __device__ __forceinline__ int pad4i(int x) { return (x + 3) & ~3; }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// TMA bulk copy global -> shared memory (one contiguous run), completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-// global data written by other CTAs with ordinary stores is about to be read through the async proxy
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
 __device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2,
                                          uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -1116,6 +1086,13 @@ bool plan_fwd(const RecurFwdArgs& a, const DevInfo* di, int* nt1, int* nt3, int*
 }
 
 }  // namespace
+
+int chunk_major_copy(const void* src, void* dst, int B, int P, int E, int cw, cudaStream_t st) {
+  CAPDEC_REQUIRE(E % cw == 0 && cw % 8 == 0, CAPDEC_ERR_BAD_SHAPE, "chunk_major_copy: E=%d cw=%d", E, cw);
+  chunk_major_kernel<<<148 * 8, 256, 0, st>>>((const uint4*)src, (uint4*)dst, B, P, E, cw);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
 
 bool recur_fwd_supported(const RecurFwdArgs& a) {
   if (!persistent_enabled()) return false;

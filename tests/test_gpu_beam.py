@@ -134,3 +134,28 @@ def test_beam_bf16_runs_and_full_width_properties():
             assert torch.equal(r2["seq"][0], r2["seq"][1])
             if prec == "fp32":
                 assert torch.equal(r2["seq"][0], res["seq"][0])
+
+
+@pytest.mark.parametrize("k", [1, 3, 5])
+def test_beam_streaming_weighted_sum_matches_register_kernel(k, monkeypatch):
+    """bf16 beam search at the reference dims: the shared-memory-ring weighted sum (chunk-major feature copy,
+    one bulk copy per stage; the large-batch path) and the register-streaming kernel are two schedules of the
+    same sums -- identical tokens, alphas and scores to rounding."""
+    dims = dict(A=512, M=512, D=512, F=512, S=1000, V=10000, E=2048)
+    G = 7
+    g = torch.Generator().manual_seed(11)
+    enc = torch.randn(G, 14, 14, dims["E"], generator=g).relu_().cuda()
+    tags = torch.rand(G, dims["S"], generator=g).cuda()
+    out = {}
+    with capdec.precision_scope("bf16"):
+        torch.manual_seed(0)
+        dec = build_decoder(O.ATTENTION_SCN, dims).eval()
+        for mode in ("1", "0"):
+            monkeypatch.setenv("CAPDEC_WSUM_STREAM", mode)
+            with torch.no_grad():
+                out[mode] = dec.sample_batch(k, dims["V"] - 2, dims["V"] - 1, enc, tags, max_steps=12, want_trace=True)
+    a, b = out["1"], out["0"]
+    assert torch.equal(a["seq"], b["seq"])
+    assert (a["alpha"] - b["alpha"]).abs().max().item() < 1e-5
+    assert (a["score"] - b["score"]).abs().max().item() < 1e-3
+    assert ((a["alpha"][:, 1:].sum(-1) - 1).abs() < 1e-3).all()
