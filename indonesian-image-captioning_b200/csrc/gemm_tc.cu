@@ -102,6 +102,53 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
   return d;
 }
 
+// Epilogue stores of one 32-row chunk held in registers (thread = output feature n, v[j] = row r0 + j):
+// the row pointer advances by the pitch, nothing is recomputed per element (the first version spent ~40
+// instructions per element on 64-bit index arithmetic and parameter reloads: 10 us per 128 x 128 tile).
+template <bool OUT_FT>
+__device__ __forceinline__ void store_chunk(void* out, int64_t ldo, int r0, int rows, float bv, const float* add,
+                                            int64_t ldadd, const uint32_t (&v)[32]) {
+  const int nr = min(32, rows - r0);
+  if (nr <= 0) return;
+  if (OUT_FT) {
+    bf16* po = (bf16*)out + (int64_t)r0 * ldo;
+    if (add == nullptr && nr == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { *po = __float2bfloat16_rn(__uint_as_float(v[j]) + bv); po += ldo; }
+    } else {
+      const float* pa = add ? add + (int64_t)r0 * ldadd : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < nr) {
+          float val = __uint_as_float(v[j]) + bv;
+          if (pa) val += *pa;
+          *po = __float2bfloat16_rn(val);
+        }
+        po += ldo;
+        if (pa) pa += ldadd;
+      }
+    }
+  } else {
+    float* po = (float*)out + (int64_t)r0 * ldo;
+    if (add == nullptr && nr == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { *po = __uint_as_float(v[j]) + bv; po += ldo; }
+    } else {
+      const float* pa = add ? add + (int64_t)r0 * ldadd : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < nr) {
+          float val = __uint_as_float(v[j]) + bv;
+          if (pa) val += *pa;
+          *po = val;
+        }
+        po += ldo;
+        if (pa) pa += ldadd;
+      }
+    }
+  }
+}
+
 template <int BNR, int NACC>
 struct Cfg {
   // 3 stages for the 128-row tile: 96 KB per CTA, so TWO CTAs share an SM and one tile's prologue /
@@ -352,16 +399,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         if (n_ok) {
+          if (splits > 1) {
+            float* po = outf + (int64_t)(r0 + c0) * a.ldo + n;
+            const float* pa = add ? add + (int64_t)(r0 + c0) * a.ldadd + n : nullptr;
+            const int nr = min(32, a.rows - (r0 + c0));
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int r = r0 + c0 + j;
-            if (r < a.rows) {
-              float val = __uint_as_float(v[j]) + bv;
-              if (add) val += add[(int64_t)r * a.ldadd + n];
-              if (splits > 1) atomicAdd(&outf[(int64_t)r * a.ldo + n], val);
-              else if (a.out_ft) outh[(int64_t)r * a.ldo + n] = __float2bfloat16_rn(val);
-              else outf[(int64_t)r * a.ldo + n] = val;
+            for (int j = 0; j < 32; ++j) {
+              if (j < nr) atomicAdd(po, __uint_as_float(v[j]) + bv + (pa ? *pa : 0.f));
+              po += a.ldo;
+              if (pa) pa += a.ldadd;
             }
+          } else if (a.out_ft) {
+            store_chunk<true>(outh + n, a.ldo, r0 + c0, a.rows, bv, add ? add + n : nullptr, a.ldadd, v);
+          } else {
+            store_chunk<false>(outf + n, a.ldo, r0 + c0, a.rows, bv, add ? add + n : nullptr, a.ldadd, v);
           }
         }
       }
@@ -432,6 +483,156 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Persistent variant for the large plain GEMMs (vocabulary projection, att1, weight gradients, the
+// beam-search GEMMs): one CTA per SM walks over its 128 x 128 output tiles; the TMA ring (6 stages)
+// keeps running across tile boundaries and the accumulator is DOUBLE BUFFERED in TMEM (2 x 128
+// columns), so the epilogue of tile i (TMEM -> registers -> global) overlaps the main loop of tile
+// i + 1 and the per-tile prologue (barrier init, TMEM allocation, first-load latency) is paid once.
+// ---------------------------------------------------------------------------------------
+constexpr int PS_STAGES = 6;
+constexpr int PS_BNR = 128;
+constexpr int PS_STAGE_BYTES = (BM + PS_BNR) * BK * 2;
+constexpr int PS_SMEM_BYTES = PS_STAGES * PS_STAGE_BYTES + 1024 + 256;
+
+template <int TN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
+                       const __grid_constant__ KArgs a, int tiles_n, int tiles_r, int num_tiles) {
+  constexpr int W_BYTES = BM * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + PS_STAGES * PS_STAGE_BYTES);
+  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * PS_STAGES + 4);
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    for (int s = 0; s < PS_STAGES; ++s) {
+      mbar_init(smem_u32(&bars[s]), 1);
+      mbar_init(smem_u32(&bars[PS_STAGES + s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bars[2 * PS_STAGES + b]), 1);          // tmem_full: one tcgen05.commit
+      mbar_init(smem_u32(&bars[2 * PS_STAGES + 2 + b]), 4);      // tmem_empty: the four epilogue warps
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const int nkb = (a.K + BK - 1) / BK;
+  const int tiles_nr = tiles_n * tiles_r;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------- TMA producer -------------------------
+      uint32_t u = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int z = t / tiles_nr, rem = t - z * tiles_nr;
+        const int rt = rem / tiles_n, nt = rem - rt * tiles_n;
+        const int n0 = nt * BM, r0 = rt * PS_BNR;
+        for (int kb = 0; kb < nkb; ++kb, ++u) {
+          const int s = u % PS_STAGES;
+          const uint32_t ph = (u / PS_STAGES) & 1;
+          mbar_wait(smem_u32(&bars[PS_STAGES + s]), ph ^ 1);
+          const uint32_t full = smem_u32(&bars[s]);
+          mbar_expect_tx(full, PS_STAGE_BYTES);
+          const uint32_t ws = smem_u32(smem + s * PS_STAGE_BYTES);
+          if (TN & 1) {
+#pragma unroll
+            for (int h = 0; h < BM / 64; ++h) tma_load_3d(ws + h * 8192, &mapW, full, n0 + h * 64, kb * BK, z);
+          } else {
+            tma_load_3d(ws, &mapW, full, kb * BK, n0, z);
+          }
+          if (TN & 2) {
+#pragma unroll
+            for (int h = 0; h < PS_BNR / 64; ++h) tma_load_3d(ws + W_BYTES + h * 8192, &mapX, full, r0 + h * 64, kb * BK, z);
+          } else {
+            tma_load_3d(ws + W_BYTES, &mapX, full, kb * BK, r0, z);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------- MMA issuer -------------------------
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PS_BNR >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24) | ((TN & 1) ? (1u << 15) : 0u) |
+                             ((TN & 2) ? (1u << 16) : 0u);
+      constexpr int ASTEP = (TN & 1) ? 128 : 2, BSTEP = (TN & 2) ? 128 : 2;
+      uint32_t u = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+        const int buf = i & 1;
+        mbar_wait(smem_u32(&bars[2 * PS_STAGES + 2 + buf]), (uint32_t)((i >> 1) & 1) ^ 1u);   // epilogue drained it
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb, ++u) {
+          const int s = u % PS_STAGES;
+          const uint32_t ph = (u / PS_STAGES) & 1;
+          mbar_wait(smem_u32(&bars[s]), ph);
+          tc_fence_after();
+          const uint32_t ws = smem_u32(smem + s * PS_STAGE_BYTES);
+          const uint64_t adesc = (TN & 1) ? make_smem_desc_mn(ws) : make_smem_desc(ws);
+          const uint64_t bdesc = (TN & 2) ? make_smem_desc_mn(ws + W_BYTES) : make_smem_desc(ws + W_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(tmem_base + (uint32_t)(buf * PS_BNR), adesc + ASTEP * k, bdesc + BSTEP * k, idesc, (kb | k) != 0);
+          umma_commit(smem_u32(&bars[PS_STAGES + s]));
+        }
+        umma_commit(smem_u32(&bars[2 * PS_STAGES + buf]));
+      }
+    }
+  } else {
+    // ------------------------- epilogue warps 2..5 -------------------------
+    const int q = warp & 3;
+    int i = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+      const int buf = i & 1;
+      const int z = t / tiles_nr, rem = t - z * tiles_nr;
+      const int rt = rem / tiles_n, nt = rem - rt * tiles_n;
+      const int n = nt * BM + q * 32 + lane, r0 = rt * PS_BNR;
+      const bool n_ok = n < a.N;
+      float bv = 0.f;
+      if (a.bias != nullptr && n_ok) bv = a.bias[(int64_t)z * a.sBias + n];
+      float* outf = (float*)a.out + (int64_t)z * a.sO;
+      bf16* outh = (bf16*)a.out + (int64_t)z * a.sO;
+      const float* add = a.addm ? a.addm + (int64_t)z * a.sAdd : nullptr;
+      mbar_wait(smem_u32(&bars[2 * PS_STAGES + buf]), (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < PS_BNR; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * PS_BNR + c0), v);
+        if (n_ok) {
+          if (a.out_ft) store_chunk<true>(outh + n, a.ldo, r0 + c0, a.rows, bv, add ? add + n : nullptr, a.ldadd, v);
+          else store_chunk<false>(outf + n, a.ldo, r0 + c0, a.rows, bv, add ? add + n : nullptr, a.ldadd, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[2 * PS_STAGES + 2 + buf])) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
 }
 
@@ -562,6 +763,59 @@ int launch(const GemmArgs& a, cudaStream_t st) {
   return CAPDEC_OK;
 }
 
+int g_sm_count = 0;
+
+template <int TN>
+int launch_persist(const GemmArgs& a, cudaStream_t st) {
+  auto kernel = gemm_tc_persist_kernel<TN>;
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM_BYTES);
+  });
+  CAPDEC_REQUIRE(attr_rc == cudaSuccess, CAPDEC_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc_persist_kernel) failed: %s",
+                 cudaGetErrorString(attr_rc));
+  if (g_sm_count == 0) {
+    int dev = 0;
+    CAPDEC_CUDA_OK(cudaGetDevice(&dev));
+    CAPDEC_CUDA_OK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  CUtensorMap mW, mX;
+  CAPDEC_TRY(get_map(a.W, a.ldw, a.N, a.K, a.batch, a.sW, (TN & 1) ? -1 : BM, &mW));
+  const int xrows = a.rows_alloc > a.rows ? a.rows_alloc : a.rows;
+  CAPDEC_TRY(get_map(a.X, a.ldx, xrows, a.K, a.batch, a.sX, (TN & 2) ? -1 : PS_BNR, &mX));
+  const int tiles_n = ceil_div(a.N, BM), tiles_r = ceil_div(a.rows, PS_BNR);
+  const int num_tiles = tiles_n * tiles_r * a.batch;
+  KArgs k;
+  k.out = a.out; k.ldo = a.ldo; k.out_ft = a.out_ft; k.bias = a.bias; k.addm = a.addm; k.ldadd = a.ldadd;
+  k.rows = a.rows; k.N = a.N; k.K = a.K; k.sO = a.sO; k.sBias = a.sBias; k.sAdd = a.sAdd;
+  k.splits = 1; k.e = a.e;
+  k.abuf = nullptr; k.a_ld = 0; k.a_sz = 0; k.a_sa = 0; k.counters = nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(num_tiles < g_sm_count ? num_tiles : g_sm_count, 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = PS_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  CAPDEC_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, mW, mX, k, tiles_n, tiles_r, num_tiles));
+  count_launch();
+  return CAPDEC_OK;
+}
+
+bool persist_enabled() {
+  const char* s = getenv("CAPDEC_GEMM_PERSIST");        // read per call: tests flip it
+  return !(s && s[0] == '0');
+}
+
 template <int NACC, int EPI>
 int launch_rows(const GemmArgs& a, cudaStream_t st) {
   const int rows = (EPI == EPI_DHCELL && a.e.rows_epi > a.rows) ? a.e.rows_epi : a.rows;
@@ -599,6 +853,18 @@ int gemm_tc(const GemmArgs& a, cudaStream_t st) {
   switch (a.epi) {
     case EPI_PLAIN:
       CAPDEC_REQUIRE(a.out, CAPDEC_ERR_BAD_ARG, "gemm_tc: null output");
+      // more than one wave of 128 x 128 tiles and no split-K: the persistent multi-tile kernel
+      // (measured: it wins for many short-K tiles -- vocabulary projection 22.7 vs 27.1 us -- and loses to
+      // two co-resident single-tile CTAs per SM when K is long or the tiles are few)
+      if (persist_enabled() && (a.splitk == 0 || a.out_ft) && a.rows > 128 && a.K <= 1024 &&
+          (int64_t)ceil_div(a.N, BM) * ceil_div(a.rows, PS_BNR) * a.batch > 4 * 148) {
+        switch (a.tn & 3) {
+          case 0: return launch_persist<0>(a, st);
+          case 1: return launch_persist<1>(a, st);
+          case 2: return launch_persist<2>(a, st);
+          default: return launch_persist<3>(a, st);
+        }
+      }
       if (a.tn) {
         // transposed operand(s): 64- or 128-wide row tiles (one or two 64-column TMA boxes)
         const bool small = a.rows <= 64;
