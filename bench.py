@@ -446,9 +446,12 @@ def run_b200(args):
     return 0
 
 
-def load_traffic(kernel):
+def load_traffic(kernel, rows=32):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/traffic.json:
-    dram__bytes_read.sum + dram__bytes_write.sum), or None when there is no capture of it."""
+    dram__bytes_read.sum + dram__bytes_write.sum), or None when there is no capture of it.  The captures were
+    taken at the config-3 shape (32 rows per GPU): other shapes get None."""
+    if rows != 32:
+        return None
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as fh:
@@ -501,7 +504,7 @@ def measure_recurrence_roofline(lib, dec, kind, dims, rows, inputs, peaks):
         t_ms = sum(ms[which]) / len(ms[which])
         achieved = bytes_alg / (t_ms * 1e-3) / 1e9
         return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(name), "us_per_launch": 1e3 * t_ms,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(name, rows), "us_per_launch": 1e3 * t_ms,
                 "rows": rows, "steps_per_launch": T, "algorithmic_bytes_per_launch": bytes_alg,
                 "peak_source": peaks["source"]}
 
@@ -557,7 +560,7 @@ def measure_roofline(dev, kind, dims, rows, peaks, precision):
     achieved = bytes_alg / (us * 1e-6) / 1e9
     return {"kernel": "attn_scores_kernel+attn_wsum_kernel", "bound": "hbm", "achieved": achieved,
             "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic("attn_scores_kernel+attn_wsum_kernel"),
+            "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic("attn_scores_kernel+attn_wsum_kernel", rows),
             "us_per_launch": us, "rows": rows,
             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": peaks["source"],
             "note": "features of one step (%.1f MB) are L2-resident across back-to-back launches, as in the "
