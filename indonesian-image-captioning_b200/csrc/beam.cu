@@ -76,8 +76,25 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
   return a;
 }
 
-// one CTA per image; KL = length of the per-thread candidate lists (>= beam size)
+// sorted insertion of `cand` into a descending list of KL entries (value, then smaller index)
 template <int KL>
+__device__ __forceinline__ void list_insert(ArgMax (&l)[KL], ArgMax cand) {
+  const ArgMax last = l[KL - 1];
+  if (cand.v > last.v || (cand.v == last.v && cand.idx < last.idx)) {
+    l[KL - 1] = cand;
+#pragma unroll
+    for (int q = KL - 1; q > 0; --q) {
+      const ArgMax lo = l[q], hi = l[q - 1];
+      if (lo.v > hi.v || (lo.v == hi.v && lo.idx < hi.idx)) { l[q] = hi; l[q - 1] = lo; }
+    }
+  }
+}
+
+// one CTA per image; KL = length of the per-thread candidate lists (>= beam size).
+// FAST (bf16 mode): ONE pass per row -- online log-sum-exp and the row's KL largest raw logits per thread
+// (within a row, ordering by logit = ordering by log-probability); the exact mode keeps the three-pass
+// arithmetic that the fp32 token-parity tests pin.
+template <int KL, bool FAST>
 __global__ void __launch_bounds__(NT)
 beam_select_kernel(const float* __restrict__ logits, int V, int k, int t, int32_t end_id,
                    const float* __restrict__ score_in, float* __restrict__ score_out,
@@ -107,6 +124,51 @@ beam_select_kernel(const float* __restrict__ logits, int V, int k, int t, int32_
   const int ns = (t == 0) ? 1 : s;             // first step: all k rows are identical, use row 0 (:242-244)
   const float* base = logits + (int64_t)g * k * V;
 
+  ArgMax mine[KL];
+#pragma unroll
+  for (int q = 0; q < KL; ++q) mine[q] = ArgMax{-INFINITY, 0x7fffffff};
+  if (FAST) {
+    for (int j = 0; j < ns; ++j) {
+      const float* x = base + (int64_t)j * V;
+      ArgMax rowl[KL];
+#pragma unroll
+      for (int q = 0; q < KL; ++q) rowl[q] = ArgMax{-INFINITY, 0x7fffffff};
+      float m = -INFINITY, sum = 0.f;
+      const int V4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? (V >> 2) : 0;      // 16-byte loads when aligned
+      for (int i4 = tid; i4 < V4; i4 += NT) {
+        const float4 q4 = *reinterpret_cast<const float4*>(x + 4 * i4);
+        const float xs[4] = {q4.x, q4.y, q4.z, q4.w};
+        const float mn = fmaxf(fmaxf(fmaxf(xs[0], xs[1]), fmaxf(xs[2], xs[3])), m);
+        sum = sum * __expf(m - mn) + (__expf(xs[0] - mn) + __expf(xs[1] - mn)) + (__expf(xs[2] - mn) + __expf(xs[3] - mn));
+        m = mn;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) list_insert<KL>(rowl, ArgMax{xs[e], 4 * i4 + e});
+      }
+      for (int i = 4 * V4 + tid; i < V; i += NT) {
+        const float xv = x[i];
+        const float mn = fmaxf(m, xv);
+        sum = sum * __expf(m - mn) + __expf(xv - mn);
+        m = mn;
+        list_insert<KL>(rowl, ArgMax{xv, i});
+      }
+      float mb = warp_max(m);
+      if (lane == 0) red_v[warp] = mb;
+      __syncthreads();
+      mb = red_v[0];
+      for (int w = 1; w < NT / 32; ++w) mb = fmaxf(mb, red_v[w]);
+      __syncthreads();
+      float sb = warp_sum(sum * __expf(m - mb));          // threads without elements: 0 * exp(-inf) = 0
+      if (lane == 0) red_v[warp] = sb;
+      __syncthreads();
+      sb = 0.f;
+      for (int w = 0; w < NT / 32; ++w) sb += red_v[w];
+      __syncthreads();
+      const float lj = logf(sb), sj = score_in[g * k + j];
+#pragma unroll
+      for (int q = 0; q < KL; ++q)
+        if (rowl[q].idx != 0x7fffffff) list_insert<KL>(mine, ArgMax{sj + ((rowl[q].v - mb) - lj), j * V + rowl[q].idx});
+    }
+  } else {
   // log-sum-exp of each considered row
   for (int j = 0; j < ns; ++j) {
     const float* x = base + (int64_t)j * V;
@@ -138,24 +200,11 @@ beam_select_kernel(const float* __restrict__ logits, int V, int k, int t, int32_
   // ONE pass over the logits: every thread keeps the kr best of its own candidates in registers
   // (sorted), then kr block-wide arg-max rounds pop the winners off the thread-local lists.
   // (the lists hold KL >= kr entries: a superset of what is needed, with static register indexing)
-  ArgMax mine[KL];
-#pragma unroll
-  for (int q = 0; q < KL; ++q) mine[q] = ArgMax{-INFINITY, 0x7fffffff};
   for (int j = 0; j < ns; ++j) {
     const float* x = base + (int64_t)j * V;
     const float sj = s_score[j], mj = s_max[j], lj = s_logsum[j];
-    for (int v = tid; v < V; v += NT) {
-      const ArgMax cand{sj + ((x[v] - mj) - lj), j * V + v};
-      const ArgMax last = mine[KL - 1];
-      if (cand.v > last.v || (cand.v == last.v && cand.idx < last.idx)) {
-        mine[KL - 1] = cand;
-#pragma unroll
-        for (int q = KL - 1; q > 0; --q) {
-          const ArgMax lo = mine[q], hi = mine[q - 1];
-          if (lo.v > hi.v || (lo.v == hi.v && lo.idx < hi.idx)) { mine[q] = hi; mine[q - 1] = lo; }
-        }
-      }
-    }
+    for (int v = tid; v < V; v += NT) list_insert<KL>(mine, ArgMax{sj + ((x[v] - mj) - lj), j * V + v});
+  }
   }
   for (int r = 0; r < kr; ++r) {
     ArgMax best = mine[0];
@@ -322,16 +371,16 @@ int beam_select(const float* logits, int V, int G, int k, int t, int32_t end_id,
                 float* score_out, int32_t* prev_word, int32_t* src_row, int32_t* live, int32_t* krem,
                 int32_t* has_done, float* best_score, int32_t* best_t, int32_t* best_parent,
                 int32_t* bp_parent, int32_t* bp_word, int32_t* tr_parent, int32_t* tr_word,
-                float* tr_score, int n_steps, cudaStream_t st) {
+                float* tr_score, int n_steps, cudaStream_t st, int fast) {
   CAPDEC_REQUIRE(k >= 1 && k <= KMAX, CAPDEC_ERR_BAD_SHAPE, "beam size must be 1..%d (got %d)", KMAX, k);
-  if (k <= 4)
-    beam_select_kernel<4><<<G, NT, 0, st>>>(logits, V, k, t, end_id, score_in, score_out, prev_word, src_row,
-                                            live, krem, has_done, best_score, best_t, best_parent, bp_parent,
-                                            bp_word, tr_parent, tr_word, tr_score, n_steps, G);
-  else
-    beam_select_kernel<KMAX><<<G, NT, 0, st>>>(logits, V, k, t, end_id, score_in, score_out, prev_word, src_row,
-                                               live, krem, has_done, best_score, best_t, best_parent, bp_parent,
-                                               bp_word, tr_parent, tr_word, tr_score, n_steps, G);
+#define BS_LAUNCH(KL_, FAST_)                                                                              \
+  beam_select_kernel<KL_, FAST_><<<G, NT, 0, st>>>(logits, V, k, t, end_id, score_in, score_out, prev_word,   \
+                                                   src_row, live, krem, has_done, best_score, best_t,         \
+                                                   best_parent, bp_parent, bp_word, tr_parent, tr_word,       \
+                                                   tr_score, n_steps, G)
+  if (k <= 4) { if (fast) BS_LAUNCH(4, true); else BS_LAUNCH(4, false); }
+  else { if (fast) BS_LAUNCH(KMAX, true); else BS_LAUNCH(KMAX, false); }
+#undef BS_LAUNCH
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }

@@ -1056,6 +1056,9 @@ int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, co
   CAPDEC_CUDA_OK(cudaMemsetAsync(bpp, 0, (size_t)n_steps * R * 4, st));
   CAPDEC_CUDA_OK(cudaMemsetAsync(bpw, 0, (size_t)n_steps * R * 4, st));
 
+  // bf16 mode: single-pass selection (CAPDEC_BEAM_EXACT=1 keeps the three-pass arithmetic of the parity mode)
+  const char* exact_env = getenv("CAPDEC_BEAM_EXACT");
+  const bool fast_select = pr == CAPDEC_BF16 && !(exact_env && exact_env[0] == '1');
   // ---- the search loop (attention_scn.py:216-290) ----
   for (int t = 0; t < n_steps; ++t) {
     float* g1 = c.at<float>(o.g1);
@@ -1087,7 +1090,7 @@ int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, co
                   R, V, D));
     CAPDEC_TRY(beam_select(c.at<float>(o.logits), V, G, k, t, end_id, score_in, score_out, prev_word,
                            src_row, live, krem, has_done, best_score, best_t, best_parent, bpp, bpw,
-                           trace_parent, trace_word, trace_score, n_steps, st));
+                           trace_parent, trace_word, trace_score, n_steps, st, fast_select ? 1 : 0));
     CAPDEC_TRY(beam_gather_state(pr, c.at(o.Hn), c.at<float>(o.Cn), c.at(o.H), c.at<float>(o.C), src_row,
                                  live, R, k, D, p.ldD, st));
     float* tmp = score_in; score_in = score_out; score_out = tmp;

@@ -155,7 +155,7 @@ int beam_select(const float* logits, int V, int G, int k, int t, int32_t end_id,
                 float* score_out, int32_t* prev_word, int32_t* src_row, int32_t* live, int32_t* krem,
                 int32_t* has_done, float* best_score, int32_t* best_t, int32_t* best_parent,
                 int32_t* bp_parent, int32_t* bp_word, int32_t* tr_parent, int32_t* tr_word,
-                float* tr_score, int n_steps, cudaStream_t st);
+                float* tr_score, int n_steps, cudaStream_t st, int fast = 0);   // fast: single-pass (bf16 mode)
 int beam_finalize(int G, int k, int n_steps, int P, int32_t start_id, int32_t end_id, const float* score,
                   const int32_t* live, const int32_t* has_done, const float* best_score,
                   const int32_t* best_t, const int32_t* best_parent, const int32_t* bp_parent,

@@ -159,3 +159,28 @@ def test_beam_streaming_weighted_sum_matches_register_kernel(k, monkeypatch):
     assert (a["alpha"] - b["alpha"]).abs().max().item() < 1e-5
     assert (a["score"] - b["score"]).abs().max().item() < 1e-3
     assert ((a["alpha"][:, 1:].sum(-1) - 1).abs() < 1e-3).all()
+
+
+@pytest.mark.parametrize("k", [1, 3, 5])
+def test_beam_single_pass_selection_matches_exact_selection(k, monkeypatch):
+    """bf16 mode selects with ONE pass per row (online log-sum-exp, per-row raw-logit top-k); the parity mode's
+    three-pass arithmetic on the same logits must give the same picks and scores to rounding."""
+    dims = dict(A=512, M=512, D=512, F=512, S=1000, V=10000, E=2048)
+    G = 6
+    g = torch.Generator().manual_seed(5)
+    enc = torch.randn(G, 14, 14, dims["E"], generator=g).relu_().cuda()
+    tags = torch.rand(G, dims["S"], generator=g).cuda()
+    out = {}
+    with capdec.precision_scope("bf16"):
+        torch.manual_seed(0)
+        dec = build_decoder(O.ATTENTION_SCN, dims).eval()
+        with torch.no_grad():
+            dec.fc.weight.mul_(30.0)          # peaked distributions: distinct candidates, well-separated scores
+        for mode in ("0", "1"):
+            monkeypatch.setenv("CAPDEC_BEAM_EXACT", mode)
+            with torch.no_grad():
+                out[mode] = dec.sample_batch(k, dims["V"] - 2, dims["V"] - 1, enc, tags, max_steps=10, want_trace=True)
+    a, b = out["0"], out["1"]
+    assert torch.equal(a["trace"][0], b["trace"][0]) and torch.equal(a["trace"][1], b["trace"][1])
+    assert torch.equal(a["seq"], b["seq"])
+    assert (a["trace"][2] - b["trace"][2]).abs().max().item() < 1e-3
