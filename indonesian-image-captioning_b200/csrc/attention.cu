@@ -294,6 +294,76 @@ attn_wsum_kernel(WsumArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// forward A, streaming variant for large batches (beam search): one CTA = (feature map, quarter of the
+// pixels); its att1 rows are consecutive in memory, so ONE cp.async.bulk (<= 49 KB) stages them while
+// the att2 vectors of the RPM rows (beams) are fetched; every staged pixel is used for all RPM rows.
+// ---------------------------------------------------------------------------------------
+constexpr int SS_QUARTERS = 4;
+
+template <int RPM>
+__global__ void __launch_bounds__(NT)
+attn_scores_stream_kernel(ScoreArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int P = a.P, A = a.A;                                   // A == 512
+  const int map = blockIdx.y, row0 = map * RPM;
+  const int pq = (P + SS_QUARTERS - 1) / SS_QUARTERS;
+  const int p_begin = blockIdx.x * pq, p_end = min(P, p_begin + pq);
+  const int cnt = p_end - p_begin;
+  if (cnt <= 0) return;
+  const uint32_t full = smem_u32(&bar);
+  if (tid == 0) {
+    mbar_init(full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(full, (uint32_t)cnt * A * 2);
+    bulk_g2s(smem_u32(smem_raw), (const bf16*)a.att1 + ((int64_t)map * P + p_begin) * A, (uint32_t)cnt * A * 2, full);
+  }
+  pdl_wait();                               // g1 comes from the previous kernel of the stream
+  float att2[RPM][2][8], wf[2][8];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int a0 = (c * 32 + lane) * 8;
+    const float4 w0 = *reinterpret_cast<const float4*>(a.w_f + a0), w1 = *reinterpret_cast<const float4*>(a.w_f + a0 + 4);
+    wf[c][0] = w0.x; wf[c][1] = w0.y; wf[c][2] = w0.z; wf[c][3] = w0.w;
+    wf[c][4] = w1.x; wf[c][5] = w1.y; wf[c][6] = w1.z; wf[c][7] = w1.w;
+#pragma unroll
+    for (int j = 0; j < RPM; ++j) {
+      const float* g = a.g1 + (int64_t)(row0 + j) * a.ldg + a0;
+      const float4 x0 = *reinterpret_cast<const float4*>(g), x1 = *reinterpret_cast<const float4*>(g + 4);
+      att2[j][c][0] = x0.x; att2[j][c][1] = x0.y; att2[j][c][2] = x0.z; att2[j][c][3] = x0.w;
+      att2[j][c][4] = x1.x; att2[j][c][5] = x1.y; att2[j][c][6] = x1.z; att2[j][c][7] = x1.w;
+    }
+  }
+  const float bf = a.b_f[0];
+  const int Ppad = pad4(P);
+  __syncthreads();                          // barrier initialised before anyone waits on it
+  mbar_wait(full, 0);
+#pragma unroll 1
+  for (int pl = warp; pl < cnt; pl += NW) {
+    float s[RPM];
+#pragma unroll
+    for (int j = 0; j < RPM; ++j) s[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(smem_raw + ((size_t)pl * A + (c * 32 + lane) * 8) * 2);
+      float f[8];
+      unpack16(raw, f, bf16());
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int j = 0; j < RPM; ++j) s[j] = fmaf(wf[c][k], fmaxf(f[k] + att2[j][c][k], 0.f), s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < RPM; ++j) {
+      const float tsum = warp_sum(s[j]);
+      if (lane == 0) a.scores[(int64_t)(row0 + j) * Ppad + p_begin + pl] = tsum + bf;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // forward B, streaming variant for large batches (beam search: 1 875 rows, 0.5 GB of features per step,
 // HBM-bound): the chunk-major feature copy enc_cm [map][E/512][P][512] makes the P x 512 slab of a
 // (map, chunk) item contiguous, so the pixels stream through a 3-stage shared-memory ring with ONE
@@ -784,14 +854,43 @@ int attention_fwd(int precision, const void* att1, const void* enc, const float*
   const int rpm = (precision == CAPDEC_BF16 && A <= 32 * vec * 2 && rows_per_map >= 2 && rows_per_map <= 5 &&
                    rows % rows_per_map == 0) ? rows_per_map : 1;
   const int gy = rows / rpm;
+  const char* force = getenv("CAPDEC_WSUM_STREAM");          // tests: 1 forces the streaming kernels at any size
+  const bool want_stream = precision == CAPDEC_BF16 && rpm == rows_per_map && !(force && force[0] == '0') &&
+                           (gy >= 148 || (force && force[0] == '1'));
   // ---- A: scores ----
+  bool scores_done = false;
+  if (want_stream && A == 512 && ((uintptr_t)g1 % 16) == 0 && (ldg % 4) == 0) {
+    ScoreArgs sa{att1, g1, ldg, w_f, b_f, scratch, rows_per_map, P, A, 0};
+    const size_t smem = (size_t)ceil_div(P, SS_QUARTERS) * A * 2;
+    dim3 gs(SS_QUARTERS, gy, 1);
+#define SS_LAUNCH(R_)                                                                                         \
+    do {                                                                                                       \
+      static std::once_flag once;                                                                              \
+      static cudaError_t rc = cudaSuccess;                                                                     \
+      std::call_once(once, [&] {                                                                               \
+        rc = cudaFuncSetAttribute(attn_scores_stream_kernel<R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+      });                                                                                                      \
+      CAPDEC_REQUIRE(rc == cudaSuccess && smem <= 100 * 1024, CAPDEC_ERR_CUDA, "attn_scores_stream: smem %zu", smem); \
+      CAPDEC_TRY(launch_attn(attn_scores_stream_kernel<R_>, gs, NT, smem, st, sa));                            \
+    } while (0)
+    switch (rpm) {
+      case 1: SS_LAUNCH(1); break;
+      case 2: SS_LAUNCH(2); break;
+      case 3: SS_LAUNCH(3); break;
+      case 4: SS_LAUNCH(4); break;
+      default: SS_LAUNCH(5); break;
+    }
+#undef SS_LAUNCH
+    scores_done = true;
+  }
   int PC = ceil_div(P, PXS * NW);                                   // one pass of PXS*NW pixels per CTA ...
   while ((int64_t)gy * PC > 64 * 148 && PC > 1) PC = (PC + 1) / 2;      // ... unless the grid gets too large
   ScoreArgs sa{att1, g1, ldg, w_f, b_f, scratch, rows_per_map, P, A, ceil_div(P, PC)};
   PC = ceil_div(P, sa.Pc);
   const bool small = A <= 32 * vec * 2;
   dim3 gs(PC, gy, 1);
-  if (precision == CAPDEC_BF16) {
+  if (scores_done) {
+  } else if (precision == CAPDEC_BF16) {
     if (rpm == 2) CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 2, 2>, gs, NT, 0, st, sa));
     else if (rpm == 3) CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 2, 3>, gs, NT, 0, st, sa));
     else if (rpm == 4) CAPDEC_TRY(launch_attn(attn_scores_kernel<bf16, 2, 4>, gs, NT, 0, st, sa));
@@ -803,9 +902,7 @@ int attention_fwd(int precision, const void* att1, const void* enc, const float*
     else CAPDEC_TRY(launch_attn(attn_scores_kernel<float, 4, 1>, gs, NT, 0, st, sa));
   }
   // ---- B: softmax + weighted sum + gate ----
-  const char* force = getenv("CAPDEC_WSUM_STREAM");          // tests: 1 forces the streaming kernel at any size
-  const bool stream_ok = enc_cm != nullptr && precision == CAPDEC_BF16 && E % WS_CH == 0 && rpm == rows_per_map;
-  if (stream_ok && (gy >= 148 || (force && force[0] == '1')) && !(force && force[0] == '0')) {
+  if (want_stream && enc_cm != nullptr && E % WS_CH == 0) {
     // large batches: shared-memory ring fed by bulk copies from the chunk-major feature copy
     WsumArgs ws{enc_cm, g1, ldg, beta_col, scratch, alpha_out, alpha_stride, z_out, ldz, awe_out,
                 rows_per_map, P, E, 0};
