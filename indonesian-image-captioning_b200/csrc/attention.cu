@@ -414,19 +414,18 @@ attn_wsum_stream_kernel(WsumArgs a) {
   for (int fi = 0; fi < WS_STAGES; ++fi)
     if (fi < nfill) fill(fi);
   pdl_wait();
-  // ---- softmax over the P scores of every row of this CTA ----
-#pragma unroll 1
-  for (int j = 0; j < RPM; ++j) {
+  // ---- softmax over the P scores of every row of this CTA: one WARP per row (shuffle reductions only) ----
+  for (int j = warp; j < RPM; j += NW) {
     const float* sc = a.scores + (int64_t)(row0 + j) * Ppad;
     float* alj = al + j * Ppad;
     float m = -INFINITY;
-    for (int p = tid; p < P; p += NT) { const float s = sc[p]; alj[p] = s; m = fmaxf(m, s); }
-    m = block_max<NT>(m, red);
+    for (int p = lane; p < P; p += 32) { const float sv = sc[p]; alj[p] = sv; m = fmaxf(m, sv); }
+    m = warp_max(m);
     float sum = 0.f;
-    for (int p = tid; p < P; p += NT) { const float e = expf(alj[p] - m); alj[p] = e; sum += e; }
-    sum = block_sum<NT>(sum, red);
+    for (int p = lane; p < P; p += 32) { const float e = expf(alj[p] - m); alj[p] = e; sum += e; }
+    sum = warp_sum(sum);
     const float inv = 1.0f / sum;
-    for (int p = tid; p < P; p += NT) {
+    for (int p = lane; p < P; p += 32) {
       const float v = alj[p] * inv;
       alj[p] = v;
       if (chunk == 0 && a.alpha_out) a.alpha_out[(int64_t)(row0 + j) * a.alpha_stride + p] = v;
