@@ -175,10 +175,10 @@ def run_reference(args):
         # bounded sample so that K+W steps finish within minutes: 4 captions/step of the same shape
         steps_b = min(steps, 6)
         cb = cpu_train_sample(kind, dims, 4, steps_b, min(warmup, 1))
-        metric = "captions/sec (train fwd+loss+bwd)"
+        metric = "captions/sec (train fwd+loss+bwd, %s)" % kind          # the B200 arm's metric string
     else:
         cb = cpu_decode_sample(kind, dims, min(8, max(2, steps)), 3)
-        metric = "captions/sec (beam=3 decode)"
+        metric = "captions/sec (beam=3 decode, %s)" % kind
     line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "captions/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
