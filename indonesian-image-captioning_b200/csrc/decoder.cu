@@ -559,7 +559,11 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     dlog = c.at(o.dlogF); lddl = p.ldV;
   }
   // dH_fc[(b,t), :] = dlogits . W_fc
-  CAPDEC_TRY(G_(c, dlog, lddl, c.at(o.Wp_fcT), p.ldV, c.at(o.dHfc), D, 0, nullptr, nullptr, 0, (int)R, D, V));
+  // K = V is long and the output small (R x D): split K four ways in bf16 mode (fp32 atomics into a zeroed buffer)
+  const int sk_fc = pr == CAPDEC_BF16 ? 4 : 0;
+  if (sk_fc) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dHfc), 0, (size_t)R * D * 4, st));
+  CAPDEC_TRY(G_(c, dlog, lddl, c.at(o.Wp_fcT), p.ldV, c.at(o.dHfc), D, 0, nullptr, nullptr, 0, (int)R, D, V, 0, 1, 0, 0,
+                0, sk_fc));
   // fc.weight.grad = dlogits^T . dropout(H) ; fc.bias.grad = colsum(dlogits)     (rows in (b,t) order)
   // bf16: the operands stay as they are ([sample][feature]) -- transposed-operand GEMM, no transposition pass
   const bool tn = pr == CAPDEC_BF16;

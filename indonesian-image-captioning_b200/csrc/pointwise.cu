@@ -128,14 +128,16 @@ __global__ void gather_features_kernel(const float* __restrict__ enc, int64_t sb
   FT* dst = enc_s + (int64_t)b * P * E + e;
   float s = 0.f;
   int p = 0;
-  for (; p + 3 < P; p += 4) {
-    const float v0 = src[(int64_t)p * sp], v1 = src[(int64_t)(p + 1) * sp];
-    const float v2 = src[(int64_t)(p + 2) * sp], v3 = src[(int64_t)(p + 3) * sp];
-    dst[(int64_t)p * E] = from_f<FT>(v0);
-    dst[(int64_t)(p + 1) * E] = from_f<FT>(v1);
-    dst[(int64_t)(p + 2) * E] = from_f<FT>(v2);
-    dst[(int64_t)(p + 3) * E] = from_f<FT>(v3);
-    s += v0; s += v1; s += v2; s += v3;
+  constexpr int U = 14;                         // pixels in flight per thread (196 = 14 * 14)
+  for (; p + U <= P; p += U) {
+    float v[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) v[i] = src[(int64_t)(p + i) * sp];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      dst[(int64_t)(p + i) * E] = from_f<FT>(v[i]);
+      s += v[i];
+    }
   }
   for (; p < P; ++p) {
     const float v0 = src[(int64_t)p * sp];

@@ -809,21 +809,26 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             stage_fill(pp, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
             if (nfillP > 1) stage_fill(pp, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
           }
+          // the saved forward activations (gate pre-activation, awe) do not depend on this step's barrier:
+          // requested before it is crossed
+          const int e0 = chunk * CHUNK + col * 8;
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0, a0 = b0, a1 = b0;
+          if (live) {
+            const float* bpp = p.g1 + (tb + row) * NG1 + A + e0;
+            const float* awp = p.awe + (tb + row) * E + e0;
+            b0 = __ldg(reinterpret_cast<const float4*>(bpp)); b1 = __ldg(reinterpret_cast<const float4*>(bpp + 4));
+            a0 = __ldg(reinterpret_cast<const float4*>(awp)); a1 = __ldg(reinterpret_cast<const float4*>(awp + 4));
+          }
           if (first) {
             grid_wait(p.bar, target);
             BSTAMP();
             first = false;
           }
           if (!live) break;
-          const int e0 = chunk * CHUNK + col * 8;
           float dawe[8];
           {
             const float* dzp = p.dz + (tb + row) * E + e0;
-            const float* bpp = p.g1 + (tb + row) * NG1 + A + e0;
-            const float* awp = p.awe + (tb + row) * E + e0;
             const float4 z0 = __ldcg(reinterpret_cast<const float4*>(dzp)), z1 = __ldcg(reinterpret_cast<const float4*>(dzp + 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bpp)), b1 = __ldg(reinterpret_cast<const float4*>(bpp + 4));
-            const float4 a0 = __ldg(reinterpret_cast<const float4*>(awp)), a1 = __ldg(reinterpret_cast<const float4*>(awp + 4));
             const float dzv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
             const float bp[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             const float aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
