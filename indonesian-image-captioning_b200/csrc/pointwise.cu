@@ -56,33 +56,54 @@ __global__ void copy_cast_kernel(const TS* __restrict__ src, int64_t lds, TD* __
 }
 
 // All weight packing of one call in ONE launch: a table of (fp32 source matrix -> feature-type copy or
-// transpose) segments, 32 x 32 source tiles, one tile per CTA.
+// transpose) segments, 64 x 64 source tiles, one tile per CTA.
 template <typename TD>
 __global__ void pack_multi_kernel(const __grid_constant__ PackTable t) {
-  __shared__ float tile[32][33];
+  constexpr int TS = 64;                      // source tile edge: 64 x 64 elements per CTA, 16 per thread
+  __shared__ float tile[TS][TS + 1];
   int si = 0;
   while (si + 1 < t.n && (int)blockIdx.x >= t.seg[si + 1].tile0) ++si;
   const PackSeg& g = t.seg[si];
   const int local = blockIdx.x - g.tile0;
-  const int tiles_c = (g.C + 31) / 32;
-  const int r0 = (local / tiles_c) * 32, c0 = (local % tiles_c) * 32;
+  const int tiles_c = (g.C + TS - 1) / TS;
+  const int r0 = (local / tiles_c) * TS, c0 = (local % tiles_c) * TS;
   const float* src = g.src;
   TD* dst = (TD*)g.dst;
+  float v[TS / 8][2];
+#pragma unroll
+  for (int i = 0; i < TS / 8; ++i) {
+    const int r = r0 + threadIdx.y + 8 * i;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + threadIdx.x + 32 * h;
+      v[i][h] = (r < g.R && c < g.C) ? src[(int64_t)r * g.lds + c] : 0.f;
+    }
+  }
   if (!g.transpose) {
-    for (int k = threadIdx.y; k < 32; k += 8) {
-      const int r = r0 + k, c = c0 + threadIdx.x;
-      if (r < g.R && c < g.C) dst[(int64_t)r * g.ldd + c] = from_f<TD>(src[(int64_t)r * g.lds + c]);
+#pragma unroll
+    for (int i = 0; i < TS / 8; ++i) {
+      const int r = r0 + threadIdx.y + 8 * i;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = c0 + threadIdx.x + 32 * h;
+        if (r < g.R && c < g.C) dst[(int64_t)r * g.ldd + c] = from_f<TD>(v[i][h]);
+      }
     }
     return;
   }
-  for (int k = threadIdx.y; k < 32; k += 8) {
-    const int r = r0 + k, c = c0 + threadIdx.x;
-    tile[k][threadIdx.x] = (r < g.R && c < g.C) ? src[(int64_t)r * g.lds + c] : 0.f;
-  }
+#pragma unroll
+  for (int i = 0; i < TS / 8; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) tile[threadIdx.y + 8 * i][threadIdx.x + 32 * h] = v[i][h];
   __syncthreads();
-  for (int k = threadIdx.y; k < 32; k += 8) {
-    const int c = c0 + k, r = r0 + threadIdx.x;
-    if (r < g.R && c < g.C) dst[(int64_t)c * g.ldd + r] = from_f<TD>(tile[threadIdx.x][k]);
+#pragma unroll
+  for (int i = 0; i < TS / 8; ++i) {
+    const int c = c0 + threadIdx.y + 8 * i;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = r0 + threadIdx.x + 32 * h;
+      if (r < g.R && c < g.C) dst[(int64_t)c * g.ldd + r] = from_f<TD>(tile[threadIdx.x + 32 * h][threadIdx.y + 8 * i]);
+    }
   }
 }
 
@@ -423,7 +444,7 @@ int pack_multi(int precision, PackTable& t, cudaStream_t st) {
   int tiles = 0;
   for (int i = 0; i < t.n; ++i) {
     t.seg[i].tile0 = tiles;
-    tiles += ceil_div(t.seg[i].R, 32) * ceil_div(t.seg[i].C, 32);
+    tiles += ceil_div(t.seg[i].R, 64) * ceil_div(t.seg[i].C, 64);
   }
   if (tiles <= 0) return CAPDEC_OK;
   if (precision == CAPDEC_BF16) pack_multi_kernel<bf16><<<tiles, dim3(32, 8), 0, st>>>(t);

@@ -403,6 +403,14 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
             stage_fill(pp, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
             if (nfill > 1) stage_fill(pp, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
           }
+          // the gate pre-activation comes from this step's G1 phase (two barriers ago): requested now, used in
+          // the epilogue
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (live && grp == 0) {
+            const float* g1 = p.g1 + (tb + row) * NG1 + A + chunk * CHUNK + col * 8;
+            b0 = __ldcg(reinterpret_cast<const float4*>(g1));
+            b1 = __ldcg(reinterpret_cast<const float4*>(g1 + 4));
+          }
           if (first) {
             grid_wait(p.bar, target);
             RECUR_STAMP();
@@ -475,9 +483,6 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
               acc[4] += s1.x; acc[5] += s1.y; acc[6] += s1.z; acc[7] += s1.w;
             }
             const int e0 = chunk * CHUNK + col * 8;
-            const float* g1 = p.g1 + (tb + row) * NG1 + A + e0;
-            const float4 b0 = __ldcg(reinterpret_cast<const float4*>(g1));
-            const float4 b1 = __ldcg(reinterpret_cast<const float4*>(g1 + 4));
             const float bp[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float zv[8];
 #pragma unroll
