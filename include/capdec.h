@@ -115,7 +115,12 @@ size_t capdec_workspace_bytes(const CapdecDims* dims, int with_backward);
  *                  and stage them in the workspace.  2 = COMPUTE PHASE only: touches nothing but
  *                  params, workspace, predictions and alphas, so with fixed pointers it can be
  *                  captured ONCE into a CUDA graph (cudaStreamBeginCapture on `stream`) and
- *                  replayed every iteration after a fresh phase-1 call. */
+ *                  replayed every iteration after a fresh phase-1 call.  The compute phase can be cut
+ *                  in two: 4 = its PROLOGUE alone (weight packing, time-invariant products, embedding
+ *                  projection: everything before the recurrence), 2|8 = the rest (recurrence +
+ *                  vocabulary projection) after a prologue that has already been launched -- the host
+ *                  can queue 1|4 BEFORE it learns the decode lengths of a repeated shape and keep
+ *                  the GPU busy while it waits for them (capdec/functional.py `speculate`). */
 int capdec_forward_train(const CapdecDims* dims, const CapdecParams* params,
                          const float* enc, int64_t enc_sb, int64_t enc_sp, int64_t enc_se,
                          const int64_t* sort_ind, const float* tags,

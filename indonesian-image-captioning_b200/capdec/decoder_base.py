@@ -63,6 +63,14 @@ class CaptionDecoderBase(nn.Module):
         if enc.dtype != torch.float32:
             enc = enc.float()
         lens, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True)   # same op as :117-118
+        # the lengths travel to the host through a pinned buffer + event instead of a blocking .tolist(): the
+        # launches queued below run while the host waits for them
+        lens_host = torch.empty(lens.shape, dtype=lens.dtype, pin_memory=True) if lens.is_cuda else None
+        lens_ev = None
+        if lens_host is not None:
+            lens_host.copy_(lens, non_blocking=True)
+            lens_ev = torch.cuda.Event()
+            lens_ev.record()
         caps_sorted = encoded_captions[sort_ind].contiguous()
         # everything that does not need the lengths on the host comes BEFORE the sync below: after it the
         # GPU is idle until the first launch
@@ -72,10 +80,16 @@ class CaptionDecoderBase(nn.Module):
         p = self.dropout.p if self.training else 0.0
         seed = int(torch.empty((), dtype=torch.int64).random_().item()) if p > 0 else 0
         params, dims_kw, enc_d = self._param_list(), self._dims_kw(), enc.detach()
-        decode_lengths = (lens - 1).tolist()                       # host sync, as upstream (:131)
+        spec = CF.speculate(self.kind, params, enc_d, tags, caps_sorted, sort_ind, dims_kw=dims_kw, dropout_p=p,
+                            seed=seed) if lens_ev is not None else None
+        if lens_ev is not None:                                    # host sync, as upstream (:131)
+            lens_ev.synchronize()
+            decode_lengths = (lens_host - 1).tolist()
+        else:
+            decode_lengths = (lens - 1).tolist()
         out, meta = CF.decoder_forward(self.kind, params, enc_d, tags, caps_sorted,
                                        sort_ind, decode_lengths, dims_kw=dims_kw, dropout_p=p,
-                                       seed=seed)
+                                       seed=seed, spec=spec)
         if self.kind == "pure_scn":
             predictions, alphas = out, None
         else:

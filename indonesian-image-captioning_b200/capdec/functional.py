@@ -57,6 +57,7 @@ def set_graphs(flag):
     _graphs_enabled = bool(flag)
     if not flag:
         _plans.clear()
+        _last_plan.clear()
 
 
 def graphs_enabled():
@@ -184,6 +185,54 @@ def _get_plan(kind, dims, decode_lengths, need_bwd, params, dev, dropout_on):
     return plan
 
 
+_last_plan = {}      # base signature (everything but the decode lengths) -> most recent plan
+
+
+def _base_key(kind, dims, need_bwd, dropout_on, dev, params):
+    return (kind, dims.precision, dims.B, dims.P, dims.E, dims.A, dims.M, dims.D, dims.F, dims.S, dims.V, dims.L,
+            need_bwd, dropout_on, dev.index, tuple(p.data_ptr() for p in params))
+
+
+def speculate(kind, module_params, enc, tags, caps_sorted, sort_ind, *, dims_kw, dropout_p=0.0, seed=0,
+              precision=None):
+    """Graph mode only.  The reference API hands the decode lengths back as a python list, so every forward
+    has a host sync; the host work between that sync and the first launch would leave the GPU idle.  If the
+    previous forward with the same signature (shapes, parameters) is still planned, its INPUT phase and the
+    PROLOGUE of its compute phase (nothing in them depends on the lengths' values beyond what that plan
+    already fixes) are queued here, BEFORE the caller waits for the lengths.  decoder_forward() then checks
+    the real lengths against the plan: equal -> only the rest of the compute phase is launched; different ->
+    the normal path runs and this launch was wasted work in another plan's workspace."""
+    if not _graphs_enabled:
+        return None
+    lib = _lib.load()
+    B, P, E = enc.shape
+    prec = precision or get_precision()
+    params = [p.detach() for p in module_params]
+    need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in module_params)
+    probe = make_dims(kind, prec, B, 1, P, E, dims_kw.get("A", 0), dims_kw["M"], dims_kw["D"],
+                      dims_kw.get("F", 0), dims_kw.get("S", 0), dims_kw["V"], caps_sorted.shape[1])
+    plan = _last_plan.get(_base_key(kind, probe, need_bwd, dropout_p > 0, enc.device, params))
+    if plan is None or not any(v is plan for v in _plans.values()):
+        return None
+    if not (enc.is_cuda and enc.dtype == torch.float32):
+        return None
+    sb, sp, se = enc.stride()
+    dims = plan.dims
+
+    def call(phases):
+        rc = lib.capdec_forward_train(
+            C.byref(dims), C.byref(plan.pstruct), _lib.ptr(enc), sb, sp, se, _lib.ptr(sort_ind),
+            _lib.ptr(tags), _lib.ptr(caps_sorted), plan.len_h, float(dropout_p), int(seed) & ((1 << 63) - 1),
+            1 if need_bwd else 0, phases, _lib.ptr(plan.predictions), _lib.ptr(plan.alphas),
+            _lib.ptr(plan.ws), plan.ws_bytes, _stream())
+        _lib.check(rc, "capdec_forward_train")
+
+    with torch.cuda.device(enc.device):
+        call(1)
+        plan.run("pre", lambda: call(4))
+    return plan
+
+
 class DecoderTrainFn(torch.autograd.Function):
     """predictions, alphas = decoder(enc, tags, caps_sorted, sort_ind; params) -- one C call each way
     (or one graph replay each way)."""
@@ -217,11 +266,17 @@ class DecoderTrainFn(torch.autograd.Function):
             _lib.check(rc, "capdec_forward_train")
 
         with torch.cuda.device(dev):
-            if use_graph:
+            if use_graph and meta.get("spec") is plan:
+                # inputs + prologue were queued before the host waited for the lengths (speculate())
+                plan.run("rest", lambda: call(2 | 8))
+            elif use_graph:
                 call(1)                                   # input phase: reads the caller's tensors
                 plan.run("fwd", lambda: call(2))
             else:
                 call(3)
+        if use_graph:
+            _last_plan[_base_key(kind, dims, need_bwd, meta["dropout_p"] > 0, dev, params)] = plan
+        meta.pop("spec", None)
         ctx.meta = meta
         ctx.plan = plan
         ctx.use_graph = use_graph
@@ -289,7 +344,7 @@ class DecoderTrainFn(torch.autograd.Function):
 
 
 def decoder_forward(kind, module_params, enc, tags, caps_sorted, sort_ind, decode_lengths, *,
-                    dims_kw, dropout_p=0.0, seed=0, precision=None):
+                    dims_kw, dropout_p=0.0, seed=0, precision=None, spec=None):
     """Run the teacher-forced decoder.  `module_params`: tensors in PARAM_MAP[kind] order."""
     B, P, E = enc.shape
     T = max(decode_lengths)
@@ -299,7 +354,7 @@ def decoder_forward(kind, module_params, enc, tags, caps_sorted, sort_ind, decod
     need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in module_params)
     meta = {"kind": kind, "dims": dims, "decode_lengths": [int(x) for x in decode_lengths],
             "dropout_p": float(dropout_p), "seed": int(seed) & ((1 << 63) - 1), "need_bwd": need_bwd,
-            "param_refs": list(module_params)}
+            "param_refs": list(module_params), "spec": spec}
     out = DecoderTrainFn.apply(meta, enc, tags, caps_sorted, sort_ind, *module_params)
     return out, meta
 

@@ -367,53 +367,16 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     if (p.scn)   // tags are NOT permuted (App. C-1): row i of the sorted batch uses tags[i]
       CAPDEC_TRY(copy_cast(pr, tags, 0, S, c.at(o.tagsF), 1, p.ldS, B, S, st));
   }
-  if (!(phases & 2)) return CAPDEC_OK;
+  // compute phases: PROLOGUE = everything before the recurrence (weight packing, time-invariant products,
+  // embedding projection, buffer zeroing), REST = recurrence + vocabulary projection.  bit 1 (2) asks for
+  // both unless bit 3 (8) says the prologue has already been launched; bit 2 (4) asks for the prologue alone
+  const bool do_pro = (phases & 4) || ((phases & 2) && !(phases & 8));
+  const bool do_rest = (phases & 2) != 0;
+  if (!do_pro && !do_rest) return CAPDEC_OK;
   const int64_t* capsD = c.at<int64_t>(o.capsD);
-
-  CAPDEC_TRY(pack_weights(c, w));
-
-  // ---------------- prologue: time-invariant products ----------------
-  if (p.att)   // att1 = enc . W_e^T + b_e      (attention.py:35, hoisted)
-    CAPDEC_TRY(G_(c, c.at(o.enc_s), E, c.at(o.Wp_e), p.ldE, c.at(o.att1), A, 1, w.enc_att_b, nullptr, 0,
-                 B * P, A, E));
-  // h0 -> H0 (feature type), c0 -> C[0] (fp32)   (attention_scn.py:90-92)
-  CAPDEC_TRY(G_(c, c.at(o.meanF), p.ldE, c.ft(o.Wp_init, 0), p.ldE, c.at(o.H0), p.ldD, 1, w.init_h_b,
-               nullptr, 0, B, D, E));
-  CAPDEC_TRY(G_(c, c.at(o.meanF), p.ldE, c.ft(o.Wp_init, (int64_t)D * p.ldE), p.ldE, c.at(o.C), D, 0,
-               w.init_c_b, nullptr, 0, B, D, E));
-  if (p.scn) {   // v = s W_ib, q = s W_hb   (scn_cell.py:78-81, 134-143)
-    CAPDEC_TRY(G_(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_ibT), p.ldS, c.at(o.v), NQ, 0, nullptr, nullptr, 0, B,
-                 NQ, S));
-    CAPDEC_TRY(G_(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_hbT), p.ldS, c.at(o.q), NQ, 0, nullptr, nullptr, 0, B,
-                 NQ, S));
-  }
-  // embeddings of the teacher tokens and their input-side projection, all (t,b) rows at once
   const bool fused = p.fused;
-  CAPDEC_TRY(embedding_gather(pr, w.emb, capsD, d.L, c.at(o.Xe), p.ldM, B, T, M, V, st));
-  if (ragged) {
-    // rows beyond a caption's length are never written by the step kernels; the batched GEMMs over
-    // all (t,b) rows must see finite (zero) operands there
-    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.Hall), 0, (size_t)R * D * p.fsz, st));
-    if (dropout_p > 0.f) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.Hd), 0, (size_t)R * D * p.fsz, st));
-    if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.z), 0, (size_t)R * E * p.fsz, st));
-    if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.m), 0, (size_t)R * 4 * 2 * F * p.fsz, st));
-  }
-  if (fused && !p.att) {
-    // pure_scn: the whole input side is non-recurrent -- u = Emb W_ia AND the left half u*v of the
-    // P4 operand for every (t,b) row come out of this one GEMM
-    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.U), 0, (size_t)R * NQ * 4, st));
-    GemmArgs a;
-    a.X = c.at(o.Xe); a.ldx = p.ldM; a.W = c.at(o.Wp_xq); a.ldw = p.ldX; a.out = c.at(o.U); a.ldo = NQ;
-    a.rows = (int)R; a.N = NQ; a.K = M; a.epi = EPI_P3;
-    a.e.fa = c.at<float>(o.v); a.e.m = c.at(o.m); a.e.mB = (int)R; a.e.F = F; a.e.vB = B;
-    CAPDEC_TRY(gemm(pr, a, st));
-  } else {
-    CAPDEC_TRY(G_(c, c.at(o.Xe), p.ldM, c.at(o.Wp_xq), p.ldX, c.at(o.U), NQ, 0, nullptr, nullptr, 0, (int)R,
-                  NQ, M));
-  }
-  if (alphas) CAPDEC_CUDA_OK(cudaMemsetAsync(alphas, 0, (size_t)R * P * 4, st));
   const bool drop = dropout_p > 0.f;
-  // ---------------- the recurrence as ONE persistent cooperative kernel (recur.cu) ----------------
+  // the recurrence as ONE persistent cooperative kernel (recur.cu) when the shape is covered
   bool persistent = false;
   RecurFwdArgs ra;
   if (pr == CAPDEC_BF16 && (p.scn || p.att) && !fused && (!p.att || alphas)) {
@@ -438,15 +401,62 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     ra.dropout_p = dropout_p; ra.seed = c.at<uint64_t>(o.seedD);
     persistent = recur_fwd_supported(ra);
   }
-  if (persistent) CAPDEC_TRY(recur_fwd(ra, st));
-  // split-K GEMMs of the tcgen05 engine accumulate with atomics into pre-zeroed buffers
   const int SK = pr == CAPDEC_BF16 ? -1 : 0;
   int* counters = c.at<int>(o.counters);
-  if (SK && !persistent) {
+
+  if (do_pro) {
+  CAPDEC_TRY(pack_weights(c, w));
+
+  // ---------------- prologue: time-invariant products ----------------
+  if (p.att)   // att1 = enc . W_e^T + b_e      (attention.py:35, hoisted)
+    CAPDEC_TRY(G_(c, c.at(o.enc_s), E, c.at(o.Wp_e), p.ldE, c.at(o.att1), A, 1, w.enc_att_b, nullptr, 0,
+                 B * P, A, E));
+  // h0 -> H0 (feature type), c0 -> C[0] (fp32)   (attention_scn.py:90-92)
+  CAPDEC_TRY(G_(c, c.at(o.meanF), p.ldE, c.ft(o.Wp_init, 0), p.ldE, c.at(o.H0), p.ldD, 1, w.init_h_b,
+               nullptr, 0, B, D, E));
+  CAPDEC_TRY(G_(c, c.at(o.meanF), p.ldE, c.ft(o.Wp_init, (int64_t)D * p.ldE), p.ldE, c.at(o.C), D, 0,
+               w.init_c_b, nullptr, 0, B, D, E));
+  if (p.scn) {   // v = s W_ib, q = s W_hb   (scn_cell.py:78-81, 134-143)
+    CAPDEC_TRY(G_(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_ibT), p.ldS, c.at(o.v), NQ, 0, nullptr, nullptr, 0, B,
+                 NQ, S));
+    CAPDEC_TRY(G_(c, c.at(o.tagsF), p.ldS, c.at(o.Wp_hbT), p.ldS, c.at(o.q), NQ, 0, nullptr, nullptr, 0, B,
+                 NQ, S));
+  }
+  // embeddings of the teacher tokens and their input-side projection, all (t,b) rows at once
+  CAPDEC_TRY(embedding_gather(pr, w.emb, capsD, d.L, c.at(o.Xe), p.ldM, B, T, M, V, st));
+  if (ragged) {
+    // rows beyond a caption's length are never written by the step kernels; the batched GEMMs over
+    // all (t,b) rows must see finite (zero) operands there
+    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.Hall), 0, (size_t)R * D * p.fsz, st));
+    if (dropout_p > 0.f) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.Hd), 0, (size_t)R * D * p.fsz, st));
+    if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.z), 0, (size_t)R * E * p.fsz, st));
+    if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.m), 0, (size_t)R * 4 * 2 * F * p.fsz, st));
+  }
+  if (fused && !p.att) {
+    // pure_scn: the whole input side is non-recurrent -- u = Emb W_ia AND the left half u*v of the
+    // P4 operand for every (t,b) row come out of this one GEMM
+    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.U), 0, (size_t)R * NQ * 4, st));
+    GemmArgs a;
+    a.X = c.at(o.Xe); a.ldx = p.ldM; a.W = c.at(o.Wp_xq); a.ldw = p.ldX; a.out = c.at(o.U); a.ldo = NQ;
+    a.rows = (int)R; a.N = NQ; a.K = M; a.epi = EPI_P3;
+    a.e.fa = c.at<float>(o.v); a.e.m = c.at(o.m); a.e.mB = (int)R; a.e.F = F; a.e.vB = B;
+    CAPDEC_TRY(gemm(pr, a, st));
+  } else {
+    CAPDEC_TRY(G_(c, c.at(o.Xe), p.ldM, c.at(o.Wp_xq), p.ldX, c.at(o.U), NQ, 0, nullptr, nullptr, 0, (int)R,
+                  NQ, M));
+  }
+  if (alphas) CAPDEC_CUDA_OK(cudaMemsetAsync(alphas, 0, (size_t)R * P * 4, st));
+  if (persistent) {
+    CAPDEC_TRY(recur_fwd_prepare(ra, st));          // chunk-major feature copy
+  } else if (SK) {
+    // split-K GEMMs of the tcgen05 engine accumulate with atomics into pre-zeroed buffers
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.g1), 0, (size_t)R * NG1 * 4, st));
     if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.pre), 0, (size_t)R * 4 * D * 4, st));
     CAPDEC_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)GEMM_TC_MAX_TILE_COUNTERS * 4, st));
   }
+  }   // do_pro
+  if (!do_rest) return CAPDEC_OK;
+  if (persistent) CAPDEC_TRY(recur_fwd(ra, st));
 
   // ---------------- the recurrence, one kernel chain per step ----------------
   for (int t = 0; t < (persistent ? 0 : T); ++t) {

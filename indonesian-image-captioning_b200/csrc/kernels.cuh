@@ -113,6 +113,7 @@ struct RecurFwdArgs {
   float dropout_p = 0.f; const uint64_t* seed = nullptr;
 };
 bool recur_fwd_supported(const RecurFwdArgs& a);     // shape / device / CAPDEC_PERSISTENT check
+int recur_fwd_prepare(const RecurFwdArgs& a, cudaStream_t st);   // chunk-major feature copy (once per batch)
 int recur_fwd(const RecurFwdArgs& a, cudaStream_t st);
 struct RecurBwdArgs {
   int att = 0, lstm = 0;

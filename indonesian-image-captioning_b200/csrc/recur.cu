@@ -1111,6 +1111,12 @@ bool recur_fwd_supported(const RecurFwdArgs& a) {
   return plan_fwd(a, dev_info(), &n1, &n3, &n4, &smem);
 }
 
+// once per batch, before recur_fwd: the chunk-major copy of the features ([B][E/512][P][512])
+int recur_fwd_prepare(const RecurFwdArgs& a, cudaStream_t st) {
+  if (!a.att) return CAPDEC_OK;
+  return chunk_major_copy(a.enc, a.enc_cm, a.B, a.P, a.E, CHUNK, st);
+}
+
 int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   const DevInfo* di = dev_info();
   int nt1, nt3, nt4;
@@ -1136,10 +1142,6 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   CAPDEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RT, smem));
   CAPDEC_REQUIRE(per_sm >= 1, CAPDEC_ERR_CUDA, "recur_fwd: kernel does not fit one CTA per SM (smem %zu)", smem);
   CAPDEC_REQUIRE(a.ldH0 == a.D, CAPDEC_ERR_BAD_SHAPE, "recur_fwd: H0 must be dense");
-  if (a.att) {
-    chunk_major_kernel<<<di->sms * 8, 256, 0, st>>>((const uint4*)a.enc, (uint4*)a.enc_cm, a.B, a.P, a.E, CHUNK);
-    CAPDEC_LAUNCH_OK();
-  }
   CAPDEC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 4, st));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
