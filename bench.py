@@ -332,6 +332,8 @@ def run_b200(args):
         h2d = sum(t.numel() * t.element_size() for t in pinned)
         result.update(total_ms=total_ms, e2e_ms=e2e_ms, launches=launches, clocks=clocks, h2d=h2d, d2h=4,
                       units_per_step=per_gpu_b)
+        if rank == 0:
+            result["optimizer_step"] = measure_optimizer(dec, peaks)
         metric = "captions/sec (train fwd+loss+bwd, %s)" % kind
     else:
         dec.eval()
@@ -442,6 +444,8 @@ def run_b200(args):
                         "d2h_bytes_per_step": result["d2h"], "ms_per_step": e2e_ms / steps},
                 "gpu_launches": int(result["launches"]), "clocks": result["clocks"], "roofline": roof,
                 "cpu_baseline": cpu_b, "peaks": peaks}
+        if result.get("optimizer_step"):
+            line["optimizer_step"] = result["optimizer_step"]       # reported separately
         print(json.dumps(line))
     return 0
 
@@ -517,6 +521,47 @@ def measure_recurrence_roofline(lib, dec, kind, dims, rows, inputs, peaks):
                     "algorithmic stream -- see DESIGN.md" % (T, what, rows, nbar))
     main["other_direction"] = other
     return main
+
+
+def measure_optimizer(dec, peaks):
+    """The reference's per-iteration optimizer work (trains/attention_scn.py:244-252: clip_gradient + Adam.step)
+    on the decoder parameters, outside the headline metric: the fused kernel of capdec.optim.ClipAdam next to
+    the stock torch ops.  CUDA-event timed, mean of 10 after 3 warm-ups."""
+    from capdec.optim import ClipAdam
+    params = [p for p in dec.parameters() if p.requires_grad and p.grad is not None]
+    if not params:
+        return None
+    n = sum(p.numel() for p in params)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / 10
+
+    saved = [p.detach().clone() for p in params]
+    fused = ClipAdam(params, lr=4e-4, grad_clip=5.0)
+    t_fused = timed(fused.step)
+    stock = torch.optim.Adam(params, lr=4e-4)
+
+    def stock_step():
+        for p in params:
+            p.grad.data.clamp_(-5.0, 5.0)
+        stock.step()
+    t_stock = timed(stock_step)
+    with torch.no_grad():
+        for p, q in zip(params, saved):
+            p.copy_(q)
+    nbytes = n * 4 * 8                 # read p, g, m, v ; write p, m, v, g
+    return {"parameters": n, "fused_clip_adam_ms": t_fused, "torch_clamp_plus_adam_ms": t_stock,
+            "fused_gbs": nbytes / (t_fused * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (t_fused * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "algorithmic_bytes": nbytes}
 
 
 def measure_roofline(dev, kind, dims, rows, peaks, precision):

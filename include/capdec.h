@@ -182,6 +182,22 @@ int capdec_beam_search(const CapdecDims* dims, const CapdecParams* params,
                        float* trace_score,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Fused gradient clip + Adam step over up to any number of fp32 tensors (reference:
+ * utils/optimizer.py:1-11 `clip_gradient` = in-place clamp of every .grad to [-grad_clip, grad_clip], then
+ * torch.optim.Adam.step(), trains/attention_scn.py:244-252).  One launch per CAPDEC_ADAM_MAX_SEGS tensors.
+ *   segs          HOST array of n_segs entries: device pointers p (parameter), g (gradient), m (exp_avg),
+ *                 v (exp_avg_sq), n elements each
+ *   step          1-based step count (bias corrections 1 - beta^step, as torch)
+ *   grad_clip     <= 0: no clamp
+ *   write_clipped != 0: the clamped gradient is written back to g, as the reference leaves it */
+#define CAPDEC_ADAM_MAX_SEGS 48
+typedef struct CapdecAdamSeg {
+  float* p; float* g; float* m; float* v;
+  int64_t n;
+} CapdecAdamSeg;
+int capdec_clip_adam_step(const CapdecAdamSeg* segs, int n_segs, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, double grad_clip, int step, int write_clipped, void* stream);
+
 /* Measurement aid for bench.py: with timing enabled, the persistent recurrence kernels of the next
  * capdec_forward_train / capdec_backward calls (csrc/recur.cu: the whole `for t` loop of
  * attention_scn.py:139-156, resp. its reverse-time gradient, in one cooperative launch each) are

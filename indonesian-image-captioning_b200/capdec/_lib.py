@@ -26,6 +26,10 @@ PARAM_FIELDS = ("enc_att_w", "enc_att_b", "dec_att_w", "dec_att_b", "full_att_w"
                 "fc_w", "fc_b")
 
 
+class AdamSeg(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64)]
+
+
 class Params(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
 
@@ -37,6 +41,7 @@ SIGNATURES = {
     "capdec_last_error": (C.c_char_p, []),
     "capdec_init": (_i, []),
     "capdec_launch_count": (C.c_ulonglong, []),
+    "capdec_clip_adam_step": (_i, [C.POINTER(AdamSeg), _i] + [C.c_double] * 6 + [_i, _i, _vp]),
     "capdec_recur_timing": (None, [_i]),
     "capdec_recur_last_ms": (_f, [_i]),
     "capdec_workspace_bytes": (_sz, [C.POINTER(Dims), _i]),

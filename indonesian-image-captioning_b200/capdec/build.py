@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_ROOT, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(PKG_ROOT, "libcapdec.so")
 SOURCES = ["capi.cu", "decoder.cu", "attention.cu", "pointwise.cu", "loss.cu", "gemm_simt.cu",
-           "gemm_tc.cu", "beam.cu", "recur.cu"]
+           "gemm_tc.cu", "beam.cu", "recur.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

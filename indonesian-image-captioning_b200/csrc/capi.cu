@@ -64,6 +64,13 @@ const char* capdec_last_error(void) { return get_error(); }
 
 unsigned long long capdec_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int capdec_clip_adam_step(const CapdecAdamSeg* segs, int n_segs, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, double grad_clip, int step, int write_clipped, void* stream) {
+  CAPDEC_TRY(capdec_init());
+  return clip_adam_step(segs, n_segs, lr, beta1, beta2, eps, weight_decay, grad_clip, step, write_clipped,
+                        (cudaStream_t)stream);
+}
+
 void capdec_recur_timing(int enable) { recur_timing(enable); }
 float capdec_recur_last_ms(int which) { return recur_last_ms(which); }
 

@@ -98,3 +98,25 @@ def test_same_seed_same_init_as_reference(kind, cls, tmp_path):
     assert list(mine) == list(ref)
     for k in ref:
         assert torch.equal(mine[k], ref[k]), k
+
+
+def test_clip_adam_is_an_optimizer_and_has_no_cpu_path():
+    """ClipAdam keeps torch.optim.Adam's param_groups / state layout (reference: trains/attention_scn.py:91-92,
+    utils/optimizer.py adjust_learning_rate) and refuses CPU tensors."""
+    import torch
+    from capdec.optim import ClipAdam
+    from capdec._lib import CapdecError
+    p = torch.nn.Parameter(torch.zeros(4, 3))
+    opt = ClipAdam([p], lr=4e-4, grad_clip=5.0)
+    assert isinstance(opt, torch.optim.Optimizer)
+    assert opt.param_groups[0]["lr"] == 4e-4 and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    for group in opt.param_groups:
+        group["lr"] *= 0.8
+    assert abs(opt.state_dict()["param_groups"][0]["lr"] - 3.2e-4) < 1e-12
+    opt.step()                      # no gradients: nothing to do, no library call
+    p.grad = torch.ones_like(p)
+    try:
+        opt.step()
+        assert False, "CPU tensors must be refused"
+    except CapdecError:
+        pass
