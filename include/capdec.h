@@ -182,6 +182,19 @@ int capdec_beam_search(const CapdecDims* dims, const CapdecParams* params,
                        float* trace_score,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Top-k accuracy count (reference utils/metric.py:25-39 `accuracy(scores, targets, k)` as
+ * called on the packed scores in trains/attention_scn.py:255, 338).  hits_out[0] = number of rows whose target
+ * is among the k largest logits (ties: the smaller index ranks first).  Two forms:
+ *   packed:   scores (rows, V) with pitch ld, targets (rows) int64; caps_sorted = decode_len_d = NULL
+ *   unpacked: scores = the (B,T,V) predictions of capdec_forward_train (ld = V, rows = B*T), targets = NULL,
+ *             caps_sorted (B,L) and decode_len_d (B): row (b,t) counts iff t < decode_len[b], target
+ *             caps_sorted[b, t+1] -- no pack_padded_sequence copy of the logits is needed.
+ * The count stays on the device: the caller decides when to read it (the reference's .item() every iteration
+ * is a host sync). */
+int capdec_topk_hits(const float* scores, int64_t ld, const int64_t* targets, const int64_t* caps_sorted,
+                     const int32_t* decode_len_d, int rows, int T, int L, int V, int k, int32_t* hits_out,
+                     void* stream);
+
 /* Fused gradient clip + Adam step over up to any number of fp32 tensors (reference:
  * utils/optimizer.py:1-11 `clip_gradient` = in-place clamp of every .grad to [-grad_clip, grad_clip], then
  * torch.optim.Adam.step(), trains/attention_scn.py:244-252).  One launch per CAPDEC_ADAM_MAX_SEGS tensors.

@@ -41,6 +41,7 @@ SIGNATURES = {
     "capdec_last_error": (C.c_char_p, []),
     "capdec_init": (_i, []),
     "capdec_launch_count": (C.c_ulonglong, []),
+    "capdec_topk_hits": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "capdec_clip_adam_step": (_i, [C.POINTER(AdamSeg), _i] + [C.c_double] * 6 + [_i, _i, _vp]),
     "capdec_recur_timing": (None, [_i]),
     "capdec_recur_last_ms": (_f, [_i]),

@@ -64,6 +64,13 @@ const char* capdec_last_error(void) { return get_error(); }
 
 unsigned long long capdec_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int capdec_topk_hits(const float* scores, int64_t ld, const int64_t* targets, const int64_t* caps_sorted,
+                     const int32_t* decode_len_d, int rows, int T, int L, int V, int k, int32_t* hits_out,
+                     void* stream) {
+  CAPDEC_TRY(capdec_init());
+  return topk_hits(scores, ld, targets, caps_sorted, decode_len_d, rows, T, L, V, k, hits_out, (cudaStream_t)stream);
+}
+
 int capdec_clip_adam_step(const CapdecAdamSeg* segs, int n_segs, double lr, double beta1, double beta2, double eps,
                           double weight_decay, double grad_clip, int step, int write_clipped, void* stream) {
   CAPDEC_TRY(capdec_init());

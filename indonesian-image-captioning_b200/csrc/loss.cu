@@ -62,6 +62,37 @@ ce_fwd_kernel(const float* __restrict__ pred, const int64_t* __restrict__ caps,
   }
 }
 
+// Top-k accuracy count (utils/metric.py:25-39 `accuracy`: scores.topk(k) contains the target).  One CTA per
+// row: the target is a hit iff fewer than k logits rank before it (larger value; equal value and smaller
+// index -- the order of a descending stable sort).  Two row sources: the (B,T,V) predictions with the
+// captions / lengths of the training step (caps != NULL; rows beyond a caption's length do not count), or
+// packed (N,V) scores with (N) targets, as the reference's loss glue builds them.
+__global__ void __launch_bounds__(NT)
+topk_hits_kernel(const float* __restrict__ scores, int64_t ld, const int64_t* __restrict__ targets,
+                 const int64_t* __restrict__ caps, const int32_t* __restrict__ len_d, int T, int L, int V, int k,
+                 int* __restrict__ hits) {
+  __shared__ float sh[NT / 32];
+  const int r = blockIdx.x;
+  int64_t tgt;
+  if (caps) {
+    const int b = r / T, t = r - b * T;
+    if (t >= len_d[b]) return;
+    tgt = caps[(int64_t)b * L + t + 1];
+  } else {
+    tgt = targets[r];
+  }
+  if (tgt < 0 || tgt >= V) return;              // out-of-range label: never in the top k
+  const float* x = scores + (int64_t)r * ld;
+  const float xt = x[tgt];
+  int before = 0;
+  for (int i = threadIdx.x; i < V; i += NT) {
+    const float v = x[i];
+    before += (v > xt || (v == xt && i < (int)tgt)) ? 1 : 0;
+  }
+  const float tot = block_sum((float)before, sh);     // exact: counts stay far below 2^24
+  if (threadIdx.x == 0 && tot < (float)k) atomicAdd(hits, 1);
+}
+
 // one CTA per caption b: sum_p (1 - sum_t alpha[b,t,p])^2
 __global__ void __launch_bounds__(NT)
 alpha_reg_fwd_kernel(const float* __restrict__ alphas, int T, int P, float* __restrict__ regpart) {
@@ -190,6 +221,17 @@ int loss_bwd(const CapdecDims& d, const float* pred, const float* alphas, const 
                                              d_alphas);
     CAPDEC_LAUNCH_OK();
   }
+  return CAPDEC_OK;
+}
+
+int topk_hits(const float* scores, int64_t ld, const int64_t* targets, const int64_t* caps, const int32_t* len_d,
+              int rows, int T, int L, int V, int k, int* hits, cudaStream_t st) {
+  CAPDEC_REQUIRE(scores && hits && (targets || (caps && len_d)) && rows >= 0 && V > 0 && k >= 1, CAPDEC_ERR_BAD_ARG,
+                 "topk_hits: bad argument");
+  CAPDEC_CUDA_OK(cudaMemsetAsync(hits, 0, sizeof(int), st));
+  if (rows == 0) return CAPDEC_OK;
+  topk_hits_kernel<<<rows, NT, 0, st>>>(scores, ld, targets, caps, len_d, T > 0 ? T : 1, L, V, k, hits);
+  CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }
 
