@@ -106,10 +106,10 @@ struct RecurFwdArgs {
   void* Hall = nullptr; void* Hd = nullptr;
   void* Ht = nullptr;                // [T][B][D] time-major copy of h (G1 operand of the next step)
   void* zk = nullptr;                // [T][E/512][B][512] chunk-major copy of z (P3 operand)
-  void* enc_cm = nullptr;            // [B][E/512][P][512] chunk-major copy of enc (built by recur_fwd)
+  void* enc_cm = nullptr;            // [B][E/256][P][256] chunk-major copy of enc (built by recur_fwd)
   float* C = nullptr; float* U = nullptr; float* g1 = nullptr; float* alphas = nullptr; float* awe = nullptr;
   void* z = nullptr; void* m = nullptr; float* pre = nullptr; float* gates = nullptr; float* scores = nullptr;
-  unsigned* bar = nullptr;           // 4-byte grid-barrier counter (zeroed by recur_fwd)
+  unsigned* bar = nullptr;           // 256 bytes: two grid-barrier counters 128 bytes apart (zeroed by recur_fwd)
   float dropout_p = 0.f; const uint64_t* seed = nullptr;
 };
 bool recur_fwd_supported(const RecurFwdArgs& a);     // shape / device / CAPDEC_PERSISTENT check
@@ -133,7 +133,7 @@ struct RecurBwdArgs {
   float* dv_acc = nullptr; float* dq_acc = nullptr; float* dz = nullptr;
   const float* awe = nullptr; const float* alphas = nullptr; const float* d_alphas = nullptr;
   const void* enc_cm = nullptr; const void* att1 = nullptr; const float* w_f = nullptr;
-  void* att1_cm = nullptr;           // [B][A/128][P][128] quarter-major copy of att1 (built by recur_bwd)
+  void* att1_cm = nullptr;           // [B][A/64][P][64] eighth-major copy of att1 (built by recur_bwd)
   const void* enc = nullptr; int build_enc_cm = 0;   // build enc_cm from enc first (forward ran per-step kernels)
   float* part = nullptr; float* de = nullptr; float* dwf = nullptr; float* dbf = nullptr;
   unsigned* bar = nullptr; float dropout_p = 0.f; const uint64_t* seed = nullptr;

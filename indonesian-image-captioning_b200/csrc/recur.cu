@@ -12,14 +12,20 @@
 //     bf16 at the 512-dim config) are sliced BY OUTPUT FEATURE over the CTAs and loaded into shared
 //     memory ONCE; each CTA owns 16-32 output features of every GEMM with the full K, so no
 //     split-K, no atomics, no zero-filled accumulators, bit-reproducible sums;
-//   * a GEMM phase = every warp takes 1/8 of K, loads the 32 x K/8 activation slice straight
-//     from L2 into mma fragments (16-byte loads, K permuted identically for both operands),
+//   * TWO ROW GROUPS PER CTA: batch rows are independent through the whole recurrence, so the 512
+//     threads of a CTA are two groups of 256 (group g owns rows [16 g, 16 g + 16) = one m16 tile)
+//     that run the time loop INDEPENDENTLY of each other -- own staging buffers, own mbarriers, own
+//     named barrier (bar.sync 1 + g), own grid-barrier counter -- and share only the resident weight
+//     slices.  A grid barrier costs ~1.3 us of pure latency (release-add, L2 round trips, poll);
+//     while one group waits in it the other group's phase keeps the SM busy;
+//   * a GEMM phase of a group = warp w takes 1/8 of K, reads the 16 x K/8 activation slice from the
+//     group's staging buffer (ONE TMA bulk copy per fill from a chunk-major operand copy) with
+//     16-byte loads straight into mma fragments (K permuted identically for both operands),
 //     mma.sync m16n8k16 bf16 -> fp32, 8-way reduction through shared memory, fused epilogue
 //     (bias, factor products u*v / p*q written as the next GEMM's operand);
-//   * attention = the same two stages as attention.cu (scores per pixel, softmax + weighted
-//     sum + gate per 512-channel chunk), features streamed from L2 with 16-byte loads;
-//   * phases are separated by a grid barrier (one release-add + acquire-spin per CTA, ~1 us)
-//     instead of a kernel boundary.  6 barriers per step for attention_scn.
+//   * attention = scores per (row, pixel) item, softmax + weighted sum + gate per (row, 256-channel
+//     chunk) item, features streamed through the staging buffers (one bulk copy per 32 pixels);
+//   * phases are separated by the group's grid barrier instead of a kernel boundary.
 // tcgen05 is not used here on purpose: its 128-lane M granularity would force 8-way split-K
 // with atomics (and a seventh phase to consume the sums) for GEMMs whose whole tensor work is
 // 0.3 us per step; the batched GEMMs outside the loop (vocabulary, att1, embedding side,
@@ -36,18 +42,26 @@ namespace capdec {
 
 namespace {
 
-constexpr int RT = 512;             // threads per CTA
-constexpr int RW = RT / 32;         // 16 warps: warp w of a GEMM phase = (m-tile w & 1, K slice w >> 1)
-constexpr int KSL = RW / 2;         // K slices of a GEMM phase
+constexpr int RT = 512;             // threads per CTA = two row groups
+constexpr int GT = 256;             // threads per row group
+constexpr int GW = GT / 32;         // 8 warps per group: warp w of a GEMM phase = K slice w
+constexpr int GR = 16;              // rows per group = one m16 tile
+constexpr int KSL = GW;             // K slices of a GEMM phase
 constexpr int KC = 512;             // K elements per staged activation chunk (1 KB per row)
 constexpr int WPAD = 64;            // bytes of padding per resident weight row (bank spread)
-constexpr int STAGE = 32 * KC * 2;  // one staging buffer: 32 rows of KC bf16 = 32 KB; two of them
+constexpr int STAGE = GR * KC * 2;  // one staging buffer: 16 rows of KC bf16 = 16 KB; two per group
 constexpr int REDLD = 16 + 8;       // floats per row of the cross-warp reduction scratch (2 n-tiles)
-constexpr int CHUNK = KC;           // channels per weighted-sum work item (1 KB per pixel)
-constexpr int NCOL = CHUNK / 8;     // 16-byte columns per chunk
-constexpr int GROUPS = RT / NCOL;   // pixel groups of the weighted sum (8)
+constexpr int REDF = KSL * GR * REDLD;      // floats of one group's reduction scratch (12 KB)
+constexpr int CHUNK = 256;          // channels per weighted-sum work item (512 B per pixel)
+constexpr int NCOL = CHUNK / 8;     // 16-byte columns per chunk = one warp
+constexpr int GROUPS = GT / NCOL;   // pixel groups of the weighted sum (8 = the warps of the row group)
 constexpr int WPXS = STAGE / (CHUNK * 2);   // pixels per weighted-sum stage (32)
-constexpr int SCI = 2 * STAGE / 1024;       // score items (<= 1 KB each) the two stages hold (64)
+constexpr int SCI = 2 * STAGE / 1024;       // score items (<= 1 KB each) the two stages hold (32)
+constexpr int QW = 64;              // attention channels per item of backward phase B
+constexpr int BPX = STAGE / (QW * 2);       // pixels per fill of phase B (128)
+static_assert(NCOL == 32, "weighted-sum mapping: one warp per pixel group");
+static_assert(REDF >= 2 * GW + (GROUPS - 1) * NCOL * 8, "reduction scratch too small for the weighted sum");
+static_assert(2 * STAGE >= 2 * GW * 2 * QW * 4, "staging buffers too small for the phase-B slab");
 
 __host__ __device__ __forceinline__ int pad4i(int x) { return (x + 3) & ~3; }
 
@@ -64,22 +78,185 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float ftanh(float x) { return 2.0f * fsigmoid(2.0f * x) - 1.0f; }
 
-// grid-wide barrier of a cooperative launch: monotonically increasing arrival counter.  Split in
-// arrive / wait so that loads which do not depend on the other CTAs are issued in between.
-__device__ __forceinline__ void grid_arrive(unsigned* ctr) {
-  __syncthreads();
-  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+// Shared-memory pipeline state of one row group: two 16 KB staging buffers (adjacent), each with a
+// "full" mbarrier.
+struct Pipe {
+  uint8_t* stg;        // generic pointer to stage 0; stage 1 = stg + STAGE
+  uint32_t stg_a;      // shared-memory address of stage 0
+  uint32_t full0;      // mbarrier address of stage 0; stage 1's is 8 bytes further
+  uint32_t phase;      // bit s = parity of the next wait on stage s
+};
+// no dynamically indexed members: the whole group state stays in registers
+__device__ __forceinline__ uint32_t pipe_full(const Pipe& pp, int s) { return pp.full0 + 8u * (uint32_t)s; }
+__device__ __forceinline__ void pipe_wait(Pipe& pp, int s) {
+  mbar_wait(pipe_full(pp, s), (pp.phase >> s) & 1u);
+  pp.phase ^= 1u << s;
 }
-__device__ __forceinline__ void grid_wait(unsigned* ctr, unsigned& target) {
-  target += gridDim.x;
-  if (threadIdx.x == 0) {
+
+// Everything one row group owns.
+struct Grp {
+  int g;               // 0 / 1
+  int tid, warp;       // thread / warp index inside the group
+  int row0;            // first batch row of the group (16 g)
+  int vcta;            // CTA index used to deal out (row, ...) work items: reversed for group 1, so that the two
+                       // groups' items of a partially filled wave land on different SMs
+  Pipe pp;
+  float* red;          // [REDF]
+  float* al;           // [pad4(P)]
+  unsigned* bar;       // the group's grid-barrier counter
+  unsigned target;
+};
+
+// barrier over the 256 threads of a row group
+__device__ __forceinline__ void gsync(const Grp& G) {
+  asm volatile("bar.sync %0, %1;" ::"r"(G.g + 1), "n"(GT) : "memory");
+}
+
+// grid-wide barrier of one row group (cooperative launch: all CTAs are resident): monotonically increasing
+// arrival counter.  Split in arrive / wait so that loads which do not depend on the other CTAs are issued in
+// between.
+__device__ __forceinline__ void grid_arrive(const Grp& G) {
+  gsync(G);
+  if (G.tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(G.bar), "r"(1u) : "memory");
+}
+__device__ __forceinline__ void grid_wait(Grp& G) {
+  G.target += gridDim.x;
+  if (G.tid == 0) {
     unsigned v;
     do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while (v < target);
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(G.bar) : "memory");
+    } while (v < G.target);
     fence_proxy_async();
   }
-  __syncthreads();
+  gsync(G);
+}
+
+// the group's leader copies `bytes` contiguous bytes into stage s
+__device__ __forceinline__ void stage_fill(const Grp& G, int s, const void* src, uint32_t bytes) {
+  if (G.tid == 0) {
+    mbar_expect_tx(pipe_full(G.pp, s), bytes);
+    bulk_g2s(G.pp.stg_a + s * STAGE, src, bytes, pipe_full(G.pp, s));
+  }
+}
+
+// One GEMM job of a row group: NH * 16 output features with the full K:
+//   out[h] = sum_k A[row, k] * W[h*16 + j, k]       (row = G.tid / 16, j = G.tid % 16)
+// A arrives in `nfill` fills of n rows x KF (= 64 * BPW * 4) bf16, each fill ONE contiguous TMA bulk copy
+// (the producers write chunk-major copies for exactly this reason), double buffered;
+// W: shared memory, rows of `wstride` bytes, resident for the whole kernel (shared by both groups).
+// Warp ks multiplies the 16 rows with BPW 32-wide k blocks of every fill; each lane fetches 16 bytes
+// (8 consecutive k) per row and block with ONE LDS.128 and feeds them to two m16n8k16 mma -- the same
+// k permutation is used for the weight fragments, so no ldmatrix / transposition is needed.  The 8
+// K-slice partials meet in shared memory.
+template <int NH, int BPW>
+__device__ __forceinline__ void gemm_job(Grp& G, const bf16* __restrict__ src, int64_t fill_stride, int n,
+                                         const uint8_t* Ws, int wstride, int nfill, float (&out)[NH]) {
+  constexpr int KF = 64 * BPW * 4;           // K elements per fill: 8 slices x BPW blocks x 32
+  constexpr int SPF = KF * 2 * GR / STAGE;   // stages one fill occupies (1 or 2)
+  Pipe& pp = G.pp;
+  const int lane = G.tid & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int ks = G.warp;
+  const uint32_t fill_bytes = (uint32_t)n * KF * 2;
+  stage_fill(G, 0, src, fill_bytes);
+  if (SPF == 1 && nfill > 1) stage_fill(G, 1, src + fill_stride, fill_bytes);
+  // one accumulator per (n-tile, k block): legacy mma.sync has a long issue-to-result latency on sm_100, so
+  // the only dependent pair inside a fill is the two k16 halves of one block
+  float accb[2 * NH][BPW][4];
+#pragma unroll
+  for (int nt = 0; nt < 2 * NH; ++nt)
+#pragma unroll
+    for (int j = 0; j < BPW; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) accb[nt][j][i] = 0.f;
+  const uint8_t* a_base = pp.stg + (size_t)g * (KF * 2) + ks * (BPW * 64) + 16 * c;
+  const uint8_t* w_base = Ws + (size_t)g * wstride + ks * (BPW * 64) + 16 * c;
+#pragma unroll 1
+  for (int kf = 0; kf < nfill; ++kf) {
+    const int s = SPF == 1 ? (kf & 1) : 0;
+    pipe_wait(pp, s);
+    const uint8_t* ap = a_base + s * STAGE;
+    const uint8_t* wp = w_base + (size_t)kf * KF * 2;
+#pragma unroll
+    for (int j = 0; j < BPW; ++j) {
+      const uint4 alo = *reinterpret_cast<const uint4*>(ap + j * 64);
+      const uint4 ahi = *reinterpret_cast<const uint4*>(ap + 8 * (KF * 2) + j * 64);
+#pragma unroll
+      for (int nt = 0; nt < 2 * NH; ++nt) {
+        const uint4 b = *reinterpret_cast<const uint4*>(wp + (size_t)nt * 8 * wstride + j * 64);
+        mma_bf16(accb[nt][j], alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
+        mma_bf16(accb[nt][j], alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
+      }
+    }
+    if (kf + 2 < nfill) {
+      gsync(G);                              // every warp of the group is done with stage s
+      stage_fill(G, s, src + (int64_t)(kf + 2) * fill_stride, fill_bytes);
+    }
+  }
+  float acc[2 * NH][4];
+#pragma unroll
+  for (int nt = 0; nt < 2 * NH; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float sum = accb[nt][0][i];
+#pragma unroll
+      for (int jb = 1; jb < BPW; ++jb) sum += accb[nt][jb][i];
+      acc[nt][i] = sum;
+    }
+  const int row = G.tid >> 4, j = G.tid & 15;
+  float* mine = G.red + (ks * GR + g) * REDLD + 2 * c;
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    if (h > 0) gsync(G);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      *reinterpret_cast<float2*>(mine + q * 8) = make_float2(acc[2 * h + q][0], acc[2 * h + q][1]);
+      *reinterpret_cast<float2*>(mine + 8 * REDLD + q * 8) = make_float2(acc[2 * h + q][2], acc[2 * h + q][3]);
+    }
+    gsync(G);
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < KSL; ++w) sum += G.red[(w * GR + row) * REDLD + j];
+    out[h] = sum;
+  }
+  gsync(G);                                  // staging buffers and `red` are free again
+}
+
+// copy `nrows` weight rows (K bf16 each, global pitch ldw elements) into shared memory rows of
+// K*2 + WPAD bytes; rows at or beyond `valid` are zero-filled.  Whole CTA.
+__device__ __noinline__ void load_weight_rows(uint8_t* Ws, const bf16* Wg, int64_t ldw, int K, int nrows,
+                                              int valid) {
+  const int vec_per_row = K / 8;
+  const int wstride = K * 2 + WPAD;
+  for (int i = threadIdx.x; i < nrows * vec_per_row; i += RT) {
+    const int r = i / vec_per_row, cidx = i - r * vec_per_row;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (r < valid) val = __ldg(reinterpret_cast<const uint4*>(Wg + (int64_t)r * ldw) + cidx);
+    *reinterpret_cast<uint4*>(Ws + (size_t)r * wstride + (size_t)cidx * 16) = val;
+  }
+}
+
+// set up the row group of the calling thread; `stg`: 4 staging buffers, `red`: 2 x REDF floats, `al`: 2 x alw
+// floats, `bars`: 4 mbarriers (initialised by thread 0 of the CTA before the first __syncthreads)
+__device__ __forceinline__ void grp_init(Grp& G, uint8_t* stg, float* red, float* al, int alw, uint64_t* bars,
+                                         unsigned* gbar) {
+  G.g = threadIdx.x / GT;
+  G.tid = threadIdx.x - G.g * GT;
+  G.warp = G.tid >> 5;
+  G.row0 = G.g * GR;
+  G.vcta = G.g ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  G.pp.stg = stg + (size_t)G.g * 2 * STAGE;
+  G.pp.stg_a = smem_u32(G.pp.stg);
+  G.pp.full0 = smem_u32(&bars[2 * G.g]);
+  G.pp.phase = 0;
+  G.red = red + (size_t)G.g * REDF;
+  G.al = al + (size_t)G.g * alw;
+  G.bar = gbar + G.g * 32;                   // counters 128 bytes apart
+  G.target = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 }
 
 struct FwdP {
@@ -92,7 +269,7 @@ struct FwdP {
   const bf16* Wc; int64_t ld2F;     // [4][D][ld2F] [W_ic_g | W_hc_g]
   const float* b_cat1; const float* b_ih; const float* b_hh;
   const bf16* att1;                 // [B][P][A]
-  const bf16* enc_cm;               // [B][E/512][P][512]   chunk-major copy of the features
+  const bf16* enc_cm;               // [B][E/256][P][256]   chunk-major copy of the features
   const float* w_f; const float* b_f;
   const float* v; const float* q;   // [B][NQ]
   const bf16* H0;                   // [B][D]
@@ -109,126 +286,11 @@ struct FwdP {
   float* pre;                       // [T][B][4D]
   float* gates;                     // [T][B][4D]
   float* scores;                    // [B][pad4(P)]
-  unsigned* bar;
+  unsigned* bar;                    // two counters, 128 bytes apart
   float dropout_p; const uint64_t* seed;
-  long long* prof;                  // debug (CAPDEC_RECUR_PROF=1): [T][16] clock64 stamps of CTA 0
+  long long* prof;                  // debug (CAPDEC_RECUR_PROF=1): [T][16] clock64 stamps of CTA 0, group 0
   int mask;                         // debug: bit i set -> phase i runs (G1, scores, wsum, P3, P4, cell)
 };
-
-// Shared-memory pipeline state: two 32 KB staging buffers (adjacent), each with a "full" mbarrier;
-// use[s] counts completed fills of stage s (parity of the next wait).
-struct Pipe {
-  uint8_t* stg;        // generic pointer to stage 0; stage 1 = stg + STAGE
-  uint32_t stg_a;      // shared-memory address of stage 0
-  uint32_t full[2];    // mbarrier addresses
-  uint32_t use[2];
-};
-
-// thread 0 copies `bytes` contiguous bytes into stage s
-__device__ __forceinline__ void stage_fill(const Pipe& pp, int s, const void* src, uint32_t bytes) {
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(pp.full[s], bytes);
-    bulk_g2s(pp.stg_a + s * STAGE, src, bytes, pp.full[s]);
-  }
-}
-
-// One GEMM job of this CTA: NH * 16 output features with the full K:
-//   out[h] = sum_k A[row, k] * W[h*16 + j, k]       (row = tid / 16, j = tid % 16)
-// A arrives in `nfill` fills of n rows x KF (= 64 * BPW) bf16, each fill ONE contiguous TMA bulk copy
-// (the producers write chunk-major copies for exactly this reason), double buffered;
-// W: shared memory, rows of `wstride` bytes, resident for the whole kernel.
-// Warp (mt, ks) multiplies rows [16 mt, 16 mt + 16) with BPW 32-wide k blocks of every fill; each lane
-// fetches 16 bytes (8 consecutive k) per row and block with ONE LDS.128 and feeds them to two
-// m16n8k16 mma -- the same k permutation is used for the weight fragments, so no ldmatrix /
-// transposition is needed.  The 8 K-slice partials meet in shared memory.
-template <int NH, int BPW>
-__device__ __forceinline__ void gemm_job(Pipe& pp, const bf16* __restrict__ src, int64_t fill_stride, int n,
-                                         const uint8_t* Ws, int wstride, int nfill, float* red,
-                                         float (&out)[NH]) {
-  constexpr int KF = 64 * BPW * 4;           // K elements per fill: 8 slices x BPW blocks x 32
-  constexpr int SPF = KF * 2 * 32 / STAGE;   // stages one fill occupies (1 or 2)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, c = lane & 3;
-  const int mt = warp & 1, ks = warp >> 1;
-  const uint32_t fill_bytes = (uint32_t)n * KF * 2;
-  stage_fill(pp, 0, src, fill_bytes);
-  if (SPF == 1 && nfill > 1) stage_fill(pp, 1, src + fill_stride, fill_bytes);
-  // one accumulator per (n-tile, k block): legacy mma.sync has a long issue-to-result latency on sm_100, so
-  // the only dependent pair inside a fill is the two k16 halves of one block
-  float accb[2 * NH][BPW][4];
-#pragma unroll
-  for (int nt = 0; nt < 2 * NH; ++nt)
-#pragma unroll
-    for (int j = 0; j < BPW; ++j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) accb[nt][j][i] = 0.f;
-  const uint8_t* a_base = pp.stg + (size_t)(mt * 16 + g) * (KF * 2) + ks * (BPW * 64) + 16 * c;
-  const uint8_t* w_base = Ws + (size_t)g * wstride + ks * (BPW * 64) + 16 * c;
-#pragma unroll 1
-  for (int kf = 0; kf < nfill; ++kf) {
-    const int s = SPF == 1 ? (kf & 1) : 0;
-    mbar_wait(pp.full[s], pp.use[s] & 1);
-    pp.use[s]++;
-    const uint8_t* ap = a_base + s * STAGE;
-    const uint8_t* wp = w_base + (size_t)kf * KF * 2;
-#pragma unroll
-    for (int j = 0; j < BPW; ++j) {
-      const uint4 alo = *reinterpret_cast<const uint4*>(ap + j * 64);
-      const uint4 ahi = *reinterpret_cast<const uint4*>(ap + 8 * (KF * 2) + j * 64);
-#pragma unroll
-      for (int nt = 0; nt < 2 * NH; ++nt) {
-        const uint4 b = *reinterpret_cast<const uint4*>(wp + (size_t)nt * 8 * wstride + j * 64);
-        mma_bf16(accb[nt][j], alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
-        mma_bf16(accb[nt][j], alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
-      }
-    }
-    if (kf + 2 < nfill) {
-      __syncthreads();                       // every warp is done with stage s
-      stage_fill(pp, s, src + (int64_t)(kf + 2) * fill_stride, fill_bytes);
-    }
-  }
-  float acc[2 * NH][4];
-#pragma unroll
-  for (int nt = 0; nt < 2 * NH; ++nt)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float sum = accb[nt][0][i];
-#pragma unroll
-      for (int jb = 1; jb < BPW; ++jb) sum += accb[nt][jb][i];
-      acc[nt][i] = sum;
-    }
-  const int row = threadIdx.x >> 4, j = threadIdx.x & 15;
-  float* mine = red + (ks * 32 + mt * 16 + g) * REDLD + 2 * c;
-#pragma unroll
-  for (int h = 0; h < NH; ++h) {
-    if (h > 0) __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      *reinterpret_cast<float2*>(mine + q * 8) = make_float2(acc[2 * h + q][0], acc[2 * h + q][1]);
-      *reinterpret_cast<float2*>(mine + 8 * REDLD + q * 8) = make_float2(acc[2 * h + q][2], acc[2 * h + q][3]);
-    }
-    __syncthreads();
-    float sum = 0.f;
-#pragma unroll
-    for (int w = 0; w < KSL; ++w) sum += red[(w * 32 + row) * REDLD + j];
-    out[h] = sum;
-  }
-  __syncthreads();                           // staging buffers and `red` are free again
-}
-
-// copy `nrows` weight rows (K bf16 each, global pitch ldw elements) into shared memory rows of
-// K*2 + WPAD bytes; rows at or beyond `valid` are zero-filled
-__device__ __noinline__ void load_weight_rows(uint8_t* Ws, const bf16* Wg, int64_t ldw, int K, int nrows,
-                                              int valid) {
-  const int vec_per_row = K / 8;
-  const int wstride = K * 2 + WPAD;
-  for (int i = threadIdx.x; i < nrows * vec_per_row; i += RT) {
-    const int r = i / vec_per_row, cidx = i - r * vec_per_row;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (r < valid) val = __ldg(reinterpret_cast<const uint4*>(Wg + (int64_t)r * ldw) + cidx);
-    *reinterpret_cast<uint4*>(Ws + (size_t)r * wstride + (size_t)cidx * 16) = val;
-  }
-}
 
 // LSTM = true: the pure_attention decoder (nn.LSTMCell on [emb ; z], pure_attention.py:143-146, gate order
 // i,f,g,o): the G1 job yields [att2 | beta_pre | h W_hh^T], P3 adds z W_ih[:, M:]^T to the batched embedding
@@ -238,29 +300,24 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NT3 = 2, NT4 = 2;
   const int D = p.D, E = p.E, F = p.F, B = p.B, T = p.T, P = p.P, NQ = p.NQ, NG1 = p.NG1, A = p.A;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // shared memory carve-up: stages | W1 | W3 | W4 | red | al | lens | mbarriers
+  const int lane = threadIdx.x & 31;
+  // shared memory carve-up: 4 stages | W1 | W3 | W4 | red[2] | al[2] | lens | mbarriers[4]
   const int w1s = D * 2 + WPAD, w3s = E * 2 + WPAD, w4s = 2 * F * 2 + WPAD;
-  uint8_t* stg = smem;
-  uint8_t* W1s = stg + 2 * STAGE;
+  const int alw = pad4i(P > 0 ? P : 4);
+  uint8_t* W1s = smem + 4 * STAGE;
   uint8_t* W3s = W1s + (size_t)NT1 * 8 * w1s;
   uint8_t* W4s = W3s + (ATT ? (size_t)NT3 * 8 * w3s : 0);
   float* red = reinterpret_cast<float*>(W4s + (LSTM ? 0 : (size_t)NT4 * 8 * w4s));
-  float* al = red + KSL * 32 * REDLD;
-  int* lens = reinterpret_cast<int*>(al + pad4i(P > 0 ? P : 4));
+  float* al = red + 2 * REDF;
+  int* lens = reinterpret_cast<int*>(al + 2 * alw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(lens + ((B + 3) & ~3) + 2);
   bars = reinterpret_cast<uint64_t*>(((uintptr_t)bars + 7) & ~(uintptr_t)7);
-  Pipe pp;
-  pp.stg = stg; pp.stg_a = smem_u32(stg);
-  pp.full[0] = smem_u32(&bars[0]); pp.full[1] = smem_u32(&bars[1]);
-  pp.use[0] = pp.use[1] = 0;
-  if (tid == 0) {
-    mbar_init(pp.full[0], 1);
-    mbar_init(pp.full[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  Grp G;
+  grp_init(G, smem, red, al, alw, bars, p.bar);
+  uint8_t* const stg = G.pp.stg;
+  const int tid = G.tid, warp = G.warp, row0 = G.row0;
 
-  // ---- which output features this CTA owns ----
+  // ---- which output features this CTA owns (both groups: same weights, different rows) ----
   const int f1 = blockIdx.x * NT1 * 8;                 // first G1 feature
   const int f3 = blockIdx.x * NT3 * 8;                 // first P3 feature (u)
   const int tpg = D / 8;
@@ -271,43 +328,47 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
   if (has1) load_weight_rows(W1s, p.Wcat1 + (int64_t)f1 * p.ldD, p.ldD, D, NT1 * 8, NG1 - f1);
   if (has3) load_weight_rows(W3s, p.Wxz + (int64_t)f3 * p.ldX, p.ldX, E, NT3 * 8, NQ - f3);
   if (has4) load_weight_rows(W4s, p.Wc + ((int64_t)gate4 * D + d4) * p.ld2F, p.ld2F, 2 * F, NT4 * 8, D - d4);
-  for (int i = tid; i < B; i += RT) lens[i] = p.len[i];
+  for (int i = threadIdx.x; i < B; i += RT) lens[i] = p.len[i];
   __syncthreads();
+  if (row0 >= B) return;                               // this group has no rows at all (B <= 16)
 
-  const int erow = tid >> 4, ej = tid & 15;            // epilogue mapping of gemm_job
+  const int lrow = tid >> 4, ej = tid & 15;            // epilogue mapping of gemm_job (row inside the group)
+  const int erow = row0 + lrow;                        // batch row
   const int col0 = ATT ? A + E : 0;
   const int Ppad = pad4i(P);
   const int chunks = ATT ? E / CHUNK : 1;
-  const int grp = tid / NCOL, col = tid - grp * NCOL;  // weighted-sum mapping
+  const int grp = warp, col = lane;                    // weighted-sum mapping: warp = pixel group, lane = 16-byte column
   const float drop_p = p.dropout_p;
   const uint64_t seed = drop_p > 0.f ? __ldg(p.seed) : 0ull;
   const int a_lane = lane * 8;                         // scores: this lane's 8 attention channels (x2)
+  const int nctas = gridDim.x;
 
-  unsigned target = 0;
   int stamp = 0;
-#define RECUR_STAMP()                                                                      \
-  do {                                                                                     \
-    if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[t * 16 + (stamp++ & 15)] = clock64(); \
+#define RECUR_STAMP()                                                                                  \
+  do {                                                                                                 \
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[t * 16 + (stamp++ & 15)] = clock64();    \
   } while (0)
 #pragma unroll 1
   for (int t = 0; t < T; ++t) {
     stamp = 0;
     RECUR_STAMP();
-    const int n = __popc(__ballot_sync(0xffffffffu, lane < B && lens[lane] > t));   // B <= 32, lengths sorted
+    // live rows of this group (lengths sorted descending): once it has none it never has any again
+    const int n = __popc(__ballot_sync(0xffffffffu, lane < GR && row0 + lane < B && lens[min(row0 + lane, B - 1)] > t));
+    if (n == 0) break;
     const int64_t tb = (int64_t)t * B;
     // ================= G1: [att2 | beta_pre | p] = h_{t-1} W_cat1^T + b, and p*q -> m =================
     if (has1 && (p.mask & 1)) {
-      const bf16* hprev = t == 0 ? p.H0 : p.Ht + (tb - B) * D;
+      const bf16* hprev = (t == 0 ? p.H0 : p.Ht + (tb - B) * D) + (int64_t)row0 * D;
       float bias1[NT1 / 2], q1[NT1 / 2];
 #pragma unroll
       for (int i = 0; i < NT1 / 2; ++i) {              // epilogue operands first: hidden behind the GEMM
         const int nf = f1 + i * 16 + ej;
         bias1[i] = nf < NG1 ? __ldg(p.b_cat1 + nf) : 0.f;
-        q1[i] = (!LSTM && erow < n && nf >= col0 && nf < NG1) ? __ldg(p.q + (int64_t)erow * NQ + (nf - col0)) : 0.f;
+        q1[i] = (!LSTM && lrow < n && nf >= col0 && nf < NG1) ? __ldg(p.q + (int64_t)erow * NQ + (nf - col0)) : 0.f;
       }
       float out[NT1 / 2];
-      gemm_job<NT1 / 2, 2>(pp, hprev, 0, n, W1s, w1s, 1, red, out);
-      if (erow < n) {
+      gemm_job<NT1 / 2, 2>(G, hprev, 0, n, W1s, w1s, 1, out);
+      if (lrow < n) {
         float* g1 = p.g1 + (tb + erow) * NG1;
 #pragma unroll
         for (int i = 0; i < NT1 / 2; ++i) {
@@ -328,8 +389,9 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
       // pure_scn: the input half u*v of the P4 operand (u = Emb W_ia is not recurrent)
       const int total = n * NQ;
 #pragma unroll 1
-      for (int i = blockIdx.x * RT + tid; i < total; i += gridDim.x * RT) {
-        const int b = i / NQ, nf = i - b * NQ;
+      for (int i = G.vcta * GT + tid; i < total; i += nctas * GT) {
+        const int bl = i / NQ, nf = i - bl * NQ;
+        const int b = row0 + bl;
         const int gg = nf / F, f = nf - gg * F;
         const float u = __ldg(p.U + (tb + b) * NQ + nf);
         p.m[((int64_t)gg * p.R + tb + b) * 2 * F + f] = __float2bfloat16_rn(u * __ldg(p.v + (int64_t)b * NQ + nf));
@@ -338,28 +400,28 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
     RECUR_STAMP();
     if (ATT) {
       // ================= scores e[b, px] = w_f . relu(att1[b, px, :] + att2[b, :]) + b_f =================
-      // this CTA's contiguous share of the (b, px) items = consecutive att1 rows: ONE bulk copy, issued
+      // this group's share of the (b, px) items of its rows = consecutive att1 rows: ONE bulk copy, issued
       // while the grid barrier is crossed -- att1 does not depend on this step
       const int items = n * P;
-      const int per = (items + gridDim.x - 1) / gridDim.x;
-      const int i0 = blockIdx.x * per, i1 = min(items, i0 + per);
-      grid_arrive(p.bar);
+      const int per = (items + nctas - 1) / nctas;
+      const int i0 = G.vcta * per, i1 = min(items, i0 + per);
+      grid_arrive(G);
 #pragma unroll 1
       for (int base = i0; base < i1 || base == i0; base += SCI) {
         const int cnt = (p.mask & 2) ? max(0, min(SCI, i1 - base)) : 0;
-        if (cnt > 0) stage_fill(pp, 0, p.att1 + (int64_t)base * A, (uint32_t)cnt * A * 2);
+        if (cnt > 0) stage_fill(G, 0, p.att1 + ((int64_t)row0 * P + base) * A, (uint32_t)cnt * A * 2);
         if (base == i0) {
-          grid_wait(p.bar, target);
+          grid_wait(G);
           RECUR_STAMP();
         }
         if (cnt > 0) {
-          mbar_wait(pp.full[0], pp.use[0] & 1);
-          pp.use[0]++;
+          pipe_wait(G.pp, 0);
           const float bfv = __ldg(p.b_f);
 #pragma unroll 1
-          for (int i = warp; i < cnt; i += RW) {
+          for (int i = warp; i < cnt; i += GW) {
             const int it = base + i;
-            const int b = it / P, px = it - b * P;
+            const int bl = it / P, px = it - bl * P;
+            const int b = row0 + bl;
             const float* g1 = p.g1 + (tb + b) * NG1;
             float s = 0.f;
 #pragma unroll
@@ -382,26 +444,27 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
             s = warp_sum(s);
             if (lane == 0) p.scores[(int64_t)b * Ppad + px] = s + bfv;
           }
-          if (base + SCI < i1) __syncthreads();
+          if (base + SCI < i1) gsync(G);
         }
       }
       RECUR_STAMP();
-      // ================= softmax + weighted sum over a 512-channel chunk + gate -> z =================
-      // item = (row, chunk); its pixels stream through the two stages, 32 pixels (32 KB, one bulk copy
+      // ================= softmax + weighted sum over a 256-channel chunk + gate -> z =================
+      // item = (row, chunk); its pixels stream through the two stages, 32 pixels (16 KB, one bulk copy
       // from the chunk-major feature copy) per fill; the first two fills are in flight during the barrier
-      grid_arrive(p.bar);
+      grid_arrive(G);
       {
         const int items_w = (p.mask & 4) ? n * chunks : 0;
         const int nfill = (P + WPXS - 1) / WPXS;
         bool first = true;
 #pragma unroll 1
-        for (int item = blockIdx.x; item < items_w || first; item += gridDim.x) {
+        for (int item = G.vcta; item < items_w || first; item += nctas) {
           const bool live = item < items_w;
-          const int row = live ? item / chunks : 0, chunk = live ? item - row * chunks : 0;
+          const int rl = live ? item / chunks : 0, chunk = live ? item - rl * chunks : 0;
+          const int row = row0 + rl;
           const bf16* src = p.enc_cm + ((int64_t)row * chunks + chunk) * P * CHUNK;
           if (live) {
-            stage_fill(pp, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
-            if (nfill > 1) stage_fill(pp, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
+            stage_fill(G, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
+            if (nfill > 1) stage_fill(G, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
           }
           // the gate pre-activation comes from this step's G1 phase (two barriers ago): requested now, used in
           // the epilogue
@@ -412,33 +475,33 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
             b1 = __ldcg(reinterpret_cast<const float4*>(g1 + 4));
           }
           if (first) {
-            grid_wait(p.bar, target);
+            grid_wait(G);
             RECUR_STAMP();
             first = false;
           }
           if (!live) break;
-          // softmax (every CTA of the row recomputes it: P <= RT values, one per thread)
+          // softmax (every group working on the row recomputes it: P <= GT values, one per thread)
           float sv = -INFINITY;
           if (tid < P) sv = __ldcg(p.scores + (int64_t)row * Ppad + tid);
           float mx = warp_max(sv);
-          if (lane == 0) red[warp] = mx;
-          __syncthreads();
-          mx = red[0];
+          if (lane == 0) G.red[warp] = mx;
+          gsync(G);
+          mx = G.red[0];
 #pragma unroll
-          for (int w = 1; w < RW; ++w) mx = fmaxf(mx, red[w]);
+          for (int w = 1; w < GW; ++w) mx = fmaxf(mx, G.red[w]);
           const float ex = tid < P ? __expf(sv - mx) : 0.f;
           float sum = warp_sum(ex);
-          if (lane == 0) red[RW + warp] = sum;
-          __syncthreads();
+          if (lane == 0) G.red[GW + warp] = sum;
+          gsync(G);
           sum = 0.f;
 #pragma unroll
-          for (int w = 0; w < RW; ++w) sum += red[RW + w];
+          for (int w = 0; w < GW; ++w) sum += G.red[GW + w];
           const float alpha = __fdividef(ex, sum);
           if (tid < P) {
-            al[tid] = alpha;
+            G.al[tid] = alpha;
             if (chunk == 0) p.alphas[((int64_t)row * T + t) * P + tid] = alpha;
           }
-          __syncthreads();
+          gsync(G);
           float acc[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -446,15 +509,14 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
           for (int fi = 0; fi < nfill; ++fi) {
             const int s = fi & 1;
             const int px0 = fi * WPXS, cnt = min(WPXS, P - px0);
-            mbar_wait(pp.full[s], pp.use[s] & 1);
-            pp.use[s]++;
+            pipe_wait(G.pp, s);
             const uint8_t* base = stg + s * STAGE + col * 16;
 #pragma unroll
             for (int u = 0; u < WPXS / GROUPS; ++u) {
               const int pl = grp + u * GROUPS;
               if (pl < cnt) {
                 const uint4 raw = *reinterpret_cast<const uint4*>(base + (size_t)pl * CHUNK * 2);
-                const float w = al[px0 + pl];
+                const float w = G.al[px0 + pl];
                 float f[8];
                 unpack16(raw, f, bf16());
 #pragma unroll
@@ -462,22 +524,22 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
               }
             }
             if (fi + 2 < nfill) {
-              __syncthreads();
+              gsync(G);
               const int pxn = (fi + 2) * WPXS;
-              stage_fill(pp, s, src + (int64_t)pxn * CHUNK, (uint32_t)min(WPXS, P - pxn) * CHUNK * 2);
+              stage_fill(G, s, src + (int64_t)pxn * CHUNK, (uint32_t)min(WPXS, P - pxn) * CHUNK * 2);
             }
           }
-          // cross-group reduction through shared memory (red: >= 2 RW + (GROUPS-1) * NCOL * 8 floats)
+          // cross-group reduction through shared memory (red: >= 2 GW + (GROUPS-1) * NCOL * 8 floats)
           if (grp > 0) {
-            float4* dst = reinterpret_cast<float4*>(red + 2 * RW + ((grp - 1) * NCOL + col) * 8);
+            float4* dst = reinterpret_cast<float4*>(G.red + 2 * GW + ((grp - 1) * NCOL + col) * 8);
             dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
             dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
           }
-          __syncthreads();
+          gsync(G);
           if (grp == 0) {
 #pragma unroll 1
             for (int gq = 1; gq < GROUPS; ++gq) {
-              const float4* sp = reinterpret_cast<const float4*>(red + 2 * RW + ((gq - 1) * NCOL + col) * 8);
+              const float4* sp = reinterpret_cast<const float4*>(G.red + 2 * GW + ((gq - 1) * NCOL + col) * 8);
               const float4 s0 = sp[0], s1 = sp[1];
               acc[0] += s0.x; acc[1] += s0.y; acc[2] += s0.z; acc[3] += s0.w;
               acc[4] += s1.x; acc[5] += s1.y; acc[6] += s1.z; acc[7] += s1.w;
@@ -494,25 +556,25 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
             }
             const uint4 zp = pack16(zv, bf16());
             *reinterpret_cast<uint4*>(p.z + (tb + row) * E + e0) = zp;
-            *reinterpret_cast<uint4*>(p.zk + (((int64_t)t * chunks + chunk) * B + row) * CHUNK + col * 8) = zp;
+            *reinterpret_cast<uint4*>(p.zk + (((int64_t)t * (E / KC) + e0 / KC) * B + row) * KC + (e0 % KC)) = zp;
           }
-          __syncthreads();
+          gsync(G);
         }
       }
       RECUR_STAMP();
-      grid_arrive(p.bar);
-      grid_wait(p.bar, target);
+      grid_arrive(G);
+      grid_wait(G);
       RECUR_STAMP();
       // ================= P3: u = Emb W_ia[:M] + z W_ia[M:], and u*v -> m =================
       if (has3 && (p.mask & 8)) {
         // the epilogue's operands are requested before the GEMM: their L2 round trip hides behind it
         const int nf = f3 + ej;
-        const bool ok3 = erow < n && nf < NQ;
+        const bool ok3 = lrow < n && nf < NQ;
         float* U = p.U + (tb + erow) * NQ;
         const float u_emb = ok3 ? __ldg(U + nf) : 0.f;           // written by the batched GEMM before this kernel
         const float v3 = (!LSTM && ok3) ? __ldg(p.v + (int64_t)erow * NQ + nf) : 0.f;
         float out[1];
-        gemm_job<1, 2>(pp, p.zk + (int64_t)t * chunks * B * CHUNK, (int64_t)B * CHUNK, n, W3s, w3s, E / KC, red, out);
+        gemm_job<1, 2>(G, p.zk + ((int64_t)t * (E / KC) * B + row0) * KC, (int64_t)B * KC, n, W3s, w3s, E / KC, out);
         if (ok3) {
           const float val = out[0] + u_emb;
           U[nf] = val;
@@ -524,30 +586,31 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
       }
       RECUR_STAMP();
     }
-    grid_arrive(p.bar);
-    grid_wait(p.bar, target);
+    grid_arrive(G);
+    grid_wait(G);
     RECUR_STAMP();
     if (!LSTM) {
       // ================= P4: pre_g = m_g [W_ic_g | W_hc_g]^T  (the n x 2F operand is one bulk copy) =========
       if (has4 && (p.mask & 16)) {
         float out[1];
-        gemm_job<1, 4>(pp, p.m + ((int64_t)gate4 * p.R + tb) * 2 * F, 0, n, W4s, w4s, 1, red, out);
+        gemm_job<1, 4>(G, p.m + ((int64_t)gate4 * p.R + tb + row0) * 2 * F, 0, n, W4s, w4s, 1, out);
         const int d = d4 + ej;
-        if (erow < n && d < D) p.pre[(tb + erow) * 4 * D + (int64_t)gate4 * D + d] = out[0];
+        if (lrow < n && d < D) p.pre[(tb + erow) * 4 * D + (int64_t)gate4 * D + d] = out[0];
       }
       RECUR_STAMP();
-      grid_arrive(p.bar);
-      grid_wait(p.bar, target);
+      grid_arrive(G);
+      grid_wait(G);
       RECUR_STAMP();
     }
     // ================= LSTM pointwise (scn_cell.py:146-152), gate order i,f,o,c =================
     {
       const int total = (p.mask & 32) ? n * D : 0;
-      const float* c_prev = p.C + tb * D;
-      float* c_new = p.C + (tb + B) * D;
+      const float* c_prev = p.C + (tb + row0) * D;
+      float* c_new = p.C + (tb + B + row0) * D;
 #pragma unroll 1
-      for (int i = blockIdx.x * RT + tid; i < total; i += gridDim.x * RT) {
-        const int b = i / D, d = i - b * D;
+      for (int i = G.vcta * GT + tid; i < total; i += nctas * GT) {
+        const int bl = i / D, d = i - bl * D;
+        const int b = row0 + bl;
         float x[4];
         if (LSTM) {
           // pre = (Emb W_ih[:M] + z W_ih[M:]) + h W_hh + b_ih + b_hh, torch gate order i,f,g,o
@@ -573,14 +636,14 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
         const int64_t ho = ((int64_t)b * T + t) * D + d;
         const bf16 hb = __float2bfloat16_rn(h);
         p.Hall[ho] = hb;
-        p.Ht[tb * D + i] = hb;
+        p.Ht[(tb + row0) * D + i] = hb;
         if (drop_p > 0.f)
           p.Hd[ho] = __float2bfloat16_rn(h * dropout_scale(seed, ((uint64_t)b * T + t) * D + d, drop_p));
       }
     }
     RECUR_STAMP();
-    grid_arrive(p.bar);
-    grid_wait(p.bar, target);
+    grid_arrive(G);
+    grid_wait(G);
     RECUR_STAMP();
   }
 #undef RECUR_STAMP
@@ -588,15 +651,18 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
 
 // =====================================================================================
 // Reverse-time recurrence as one cooperative launch: the mirror image of
-// recur_fwd_kernel.  Per step, six phases separated by grid barriers:
+// recur_fwd_kernel, with the same two independent row groups per CTA.  Per step, six phases
+// separated by the group's grid barrier:
 //   C   LSTM pointwise backward (dh from the fc gradient + the recurrent gradient) -> dpre_t
 //   W   [w_g | r_g] = dpre_g [W_ic_g | W_hc_g]  and the factor products du = w*v, dp = r*q,
 //       dv_acc += w*u, dq_acc += r*p fused in the epilogue (full K per CTA: no atomics)
 //   Z   dz = du W_ia[M:]^T
-//   A   gate backward + partial dalpha_p = enc[p, chunk] . dawe   (streams enc, like the forward sum)
-//   B   softmax backward, relu / score backward -> datt2, dw_f, de   (streams att1; one CTA per row)
+//   A   gate backward + partial dalpha_p = enc[p, chunk] . dawe   (streams enc, like the forward sum;
+//       item = (row, 256-channel chunk): one warp owns a pixel's whole 512-byte run)
+//   B   softmax backward, relu / score backward -> datt2, dw_f, de   (streams att1;
+//       item = (row, 64 attention channels))
 //   H   dh_{t-1} = [dp | dbeta_pre | datt2] [W_ha | W_beta^T | W_d^T]^T   (K = 4608 split in 512-wide
-//       jobs over the CTAs; the partial sums meet in fp32 atomics on a zeroed slot, as before)
+//       jobs over the CTAs; the partial sums meet in fp32 atomics on a zeroed slot)
 // Operands that cross CTAs are written twice: in the layout the batched weight-gradient GEMMs read
 // after the loop, and chunk-major ([K/512][B][512]) so that every staging fill is one bulk copy.
 // =====================================================================================
@@ -623,13 +689,13 @@ struct BwdP {
   float* dv_acc; float* dq_acc;       // [B][NQ]
   float* dz;                          // [T][B][E]
   const float* awe; const float* alphas; const float* d_alphas;
-  const bf16* enc_cm; const float* w_f;
-  const bf16* att1_cm;                // [B][A/128][P][128]   quarter-major copy of att1
-  float* part;                        // [B][E/512][pad4(P)]
+  const bf16* enc_cm; const float* w_f;   // enc_cm [B][E/256][P][256]
+  const bf16* att1_cm;                // [B][A/64][P][64]   eighth-major copy of att1
+  float* part;                        // [B][E/256][pad4(P)]
   float* de; float* dwf; float* dbf;  // [T][B][pad4(P)], [T][B][A], [T][B]
   unsigned* bar;
   float dropout_p; const uint64_t* seed;
-  long long* prof;                    // debug (CAPDEC_RECUR_PROF=1): [T][16] clock64 stamps of CTA 0
+  long long* prof;                    // debug (CAPDEC_RECUR_PROF=1): [T][16] clock64 stamps of CTA 0, group 0
 };
 
 // LSTM = true (pure_attention): no factor products (phase W is skipped), dz = dpre W_ih[:, M:], the recurrent
@@ -639,29 +705,26 @@ template <bool ATT, bool LSTM = false>
 __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant__ BwdP p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int D = p.D, E = p.E, F = p.F, B = p.B, T = p.T, P = p.P, NQ = p.NQ, NG1 = p.NG1, A = p.A;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lane = threadIdx.x & 31;
   const int wWs = D * 2 + WPAD, wZs = NQ * 2 + WPAD, wHs = KC * 2 + WPAD;
-  uint8_t* stg = smem;
-  uint8_t* WWs = stg + 2 * STAGE;                         // 32 rows, K = D
+  const int alw = pad4i(P > 0 ? P : 4);
+  // shared memory carve-up: 4 stages | WW | WZ | WH | red[2] | des[2] | lens | mbarriers[4]
+  uint8_t* WWs = smem + 4 * STAGE;                        // 32 rows, K = D
   uint8_t* WZs = WWs + (size_t)32 * wWs;                  // 16 rows, K = NQ   (ATT only)
   uint8_t* WHs = WZs + (ATT ? (size_t)16 * wZs : 0);      // 2 x 16 rows, K = 512
   float* red = reinterpret_cast<float*>(WHs + (size_t)32 * wHs);
-  float* al = red + KSL * 32 * REDLD;                     // [pad4(P)]
-  float* des = al + pad4i(P > 0 ? P : 4);                 // [pad4(P)]
-  int* lens = reinterpret_cast<int*>(des + pad4i(P > 0 ? P : 4));
+  float* desb = red + 2 * REDF;                           // [2][pad4(P)]
+  int* lens = reinterpret_cast<int*>(desb + 2 * alw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(lens + ((B + 3) & ~3) + 2);
   bars = reinterpret_cast<uint64_t*>(((uintptr_t)bars + 7) & ~(uintptr_t)7);
-  Pipe pp;
-  pp.stg = stg; pp.stg_a = smem_u32(stg);
-  pp.full[0] = smem_u32(&bars[0]); pp.full[1] = smem_u32(&bars[1]);
-  pp.use[0] = pp.use[1] = 0;
-  if (tid == 0) {
-    mbar_init(pp.full[0], 1);
-    mbar_init(pp.full[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // ---- roles ----
+  Grp G;
+  grp_init(G, smem, red, desb, alw, bars, p.bar);
+  uint8_t* const stg = G.pp.stg;
+  float* const des = G.al;
+  const int tid = G.tid, warp = G.warp, row0 = G.row0;
+  // ---- roles (both groups: same weights, different rows) ----
   const int c = blockIdx.x;
+  const int nctas = gridDim.x;
   const int spg = 2 * F / 32;                             // 32-feature slices per gate of the W job
   const bool hasW = !LSTM && c < 4 * spg;
   const int gateW = c / spg, fW0 = (c - gateW * spg) * 32;
@@ -675,7 +738,7 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
   if (hasZ) load_weight_rows(WZs, p.Wxin + (int64_t)eZ0 * p.ldNQ, p.ldNQ, NQ, 16, E - eZ0);
 #pragma unroll 1
   for (int i = 0; i < 2; ++i) {
-    const int j = c + i * gridDim.x;
+    const int j = c + i * nctas;
     if (j < jobsH) {
       const int ds = j / nkc, kc = j - ds * nkc;
       if (LSTM && kc >= nkq)
@@ -686,35 +749,40 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
                          D - ds * 16);
     }
   }
-  for (int i = tid; i < B; i += RT) lens[i] = p.len[i];
+  for (int i = threadIdx.x; i < B; i += RT) lens[i] = p.len[i];
   __syncthreads();
+  if (row0 >= B) return;                                  // this group has no rows at all (B <= 16)
 
-  const int erow = tid >> 4, ej = tid & 15;
+  const int lrow = tid >> 4, ej = tid & 15;
+  const int erow = row0 + lrow;
   const int Ppad = pad4i(P);
   const int chunks = ATT ? E / CHUNK : 1;
-  const int grp = tid / NCOL, col = tid - grp * NCOL;
+  const int grp = warp, col = lane;                       // phase A mapping: warp = pixel group, lane = 16-byte column
   const float drop_p = p.dropout_p;
   const uint64_t seed = drop_p > 0.f ? __ldg(p.seed) : 0ull;
   const int nfillP = (P + WPXS - 1) / WPXS;
-  unsigned target = 0;
   int stamp = 0;
-#define BSTAMP() do { if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[t * 16 + (stamp++ & 15)] = clock64(); } while (0)
+#define BSTAMP() do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[t * 16 + (stamp++ & 15)] = clock64(); } while (0)
 
 #pragma unroll 1
   for (int t = T - 1; t >= 0; --t) {
     stamp = 0;
     BSTAMP();
-    const int n = __popc(__ballot_sync(0xffffffffu, lane < B && lens[lane] > t));
+    // live rows of this group; none yet (all its captions are shorter than t) -> nothing to do at this step
+    const int n = __popc(__ballot_sync(0xffffffffu, lane < GR && row0 + lane < B && lens[min(row0 + lane, B - 1)] > t));
+    if (n == 0) continue;
     const int64_t tb = (int64_t)t * B;
     // ================= C: LSTM pointwise backward =================
     {
       const int total = n * D;
-      const float* dh_in = p.dh_rec + (tb + B) * D;
-      const float* c_prev = p.C + tb * D;
-      const float* c_new = p.C + (tb + B) * D;
+      const float* dh_in = p.dh_rec + (tb + B + row0) * D;
+      const float* c_prev = p.C + (tb + row0) * D;
+      const float* c_new = p.C + (tb + B + row0) * D;
+      float* dcp = p.dc + (int64_t)row0 * D;
 #pragma unroll 1
-      for (int i = blockIdx.x * RT + tid; i < total; i += gridDim.x * RT) {
-        const int b = i / D, d = i - b * D;
+      for (int i = G.vcta * GT + tid; i < total; i += nctas * GT) {
+        const int bl = i / D, d = i - bl * D;
+        const int b = row0 + bl;
         float dh = __ldcg(dh_in + i);
         {
           float g = __ldg(p.dHfc + ((int64_t)b * T + t) * D + d);
@@ -724,12 +792,12 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
         const float* gp = p.gates + (tb + b) * 4 * D + d;
         const float ig = __ldg(gp), fg = __ldg(gp + D), og = __ldg(gp + 2 * D), gg = __ldg(gp + 3 * D);
         const float tc = ftanh(__ldg(c_new + i));
-        const float dcn = p.dc[i] + dh * og * (1.f - tc * tc);
+        const float dcn = dcp[i] + dh * og * (1.f - tc * tc);
         const float dpo = dh * tc * og * (1.f - og), dpg = dcn * ig * (1.f - gg * gg);
         // pre-activation slots: i, f, o, c (SCN cell) or i, f, g, o (nn.LSTMCell)
         const float dpv[4] = {dcn * gg * ig * (1.f - ig), dcn * __ldg(c_prev + i) * fg * (1.f - fg),
                               LSTM ? dpg : dpo, LSTM ? dpo : dpg};
-        p.dc[i] = dcn * fg;
+        dcp[i] = dcn * fg;
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) {
           const bf16 x = __float2bfloat16_rn(dpv[gq]);
@@ -739,8 +807,8 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
       }
     }
     BSTAMP();
-    grid_arrive(p.bar);
-    grid_wait(p.bar, target);
+    grid_arrive(G);
+    grid_wait(G);
     BSTAMP();
     // ================= W: [w | r] = dpre_g [W_ic_g | W_hc_g] and the factor products =================
     if (hasW) {
@@ -750,7 +818,7 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
       for (int i = 0; i < 2; ++i) {
         const int nf = fW0 + i * 16 + ej;
         fac[i] = act[i] = run[i] = 0.f;
-        if (erow < n && nf < 2 * F) {
+        if (lrow < n && nf < 2 * F) {
           const bool is_w = nf < F;
           const int n4 = gateW * F + (is_w ? nf : nf - F);
           const int64_t k = (int64_t)erow * NQ + n4;
@@ -760,8 +828,8 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
         }
       }
       float out[2];
-      gemm_job<2, 2>(pp, p.dpre_gm + ((int64_t)t * 4 + gateW) * B * D, 0, n, WWs, wWs, 1, red, out);
-      if (erow < n) {
+      gemm_job<2, 2>(G, p.dpre_gm + (((int64_t)t * 4 + gateW) * B + row0) * D, 0, n, WWs, wWs, 1, out);
+      if (lrow < n) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int nf = fW0 + i * 16 + ej;
@@ -787,32 +855,33 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
     BSTAMP();
     if (ATT) {
       if (!LSTM) {
-        grid_arrive(p.bar);
-        grid_wait(p.bar, target);
+        grid_arrive(G);
+        grid_wait(G);
       }
       BSTAMP();
       // ================= Z: dz = du W_ia[M:]^T   (LSTM: dpre W_ih[:, M:]) =================
       if (hasZ) {
         float out[1];
-        gemm_job<1, 2>(pp, LSTM ? p.dpre_gm + (int64_t)t * 4 * B * D : p.duk + (int64_t)t * nkq * B * KC,
-                       (int64_t)B * KC, n, WZs, wZs, nkq, red, out);
+        gemm_job<1, 2>(G, (LSTM ? p.dpre_gm + (int64_t)t * 4 * B * D : p.duk + (int64_t)t * nkq * B * KC) + (int64_t)row0 * KC,
+                       (int64_t)B * KC, n, WZs, wZs, nkq, out);
         const int e = eZ0 + ej;
-        if (erow < n && e < E) p.dz[(tb + erow) * E + e] = out[0];
+        if (lrow < n && e < E) p.dz[(tb + erow) * E + e] = out[0];
       }
       BSTAMP();
-      // ================= A: gate backward + partial dalpha over one 512-channel chunk =================
-      grid_arrive(p.bar);
+      // ================= A: gate backward + partial dalpha over one 256-channel chunk =================
+      grid_arrive(G);
       {
         const int items = n * chunks;
         bool first = true;
 #pragma unroll 1
-        for (int item = blockIdx.x; item < items || first; item += gridDim.x) {
+        for (int item = G.vcta; item < items || first; item += nctas) {
           const bool live = item < items;
-          const int row = live ? item / chunks : 0, chunk = live ? item - row * chunks : 0;
+          const int rl = live ? item / chunks : 0, chunk = live ? item - rl * chunks : 0;
+          const int row = row0 + rl;
           const bf16* src = p.enc_cm + ((int64_t)row * chunks + chunk) * P * CHUNK;
           if (live) {
-            stage_fill(pp, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
-            if (nfillP > 1) stage_fill(pp, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
+            stage_fill(G, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
+            if (nfillP > 1) stage_fill(G, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
           }
           // the saved forward activations (gate pre-activation, awe) do not depend on this step's barrier:
           // requested before it is crossed
@@ -825,7 +894,7 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             a0 = __ldg(reinterpret_cast<const float4*>(awp)); a1 = __ldg(reinterpret_cast<const float4*>(awp + 4));
           }
           if (first) {
-            grid_wait(p.bar, target);
+            grid_wait(G);
             BSTAMP();
             first = false;
           }
@@ -847,21 +916,19 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             if (grp == 0) {
               const uint4 pk = pack16(db, bf16());
               *reinterpret_cast<uint4*>(p.dbx + (tb + row) * p.ldbx + p.dbx_off + e0) = pk;
-              *reinterpret_cast<uint4*>(p.dpxk + (((int64_t)t * nkc + nkq + chunk) * B + row) * KC + col * 8) = pk;
+              *reinterpret_cast<uint4*>(p.dpxk + (((int64_t)t * nkc + nkq + e0 / KC) * B + row) * KC + (e0 % KC)) = pk;
             }
           }
-          if (tid < Ppad) al[tid] = 0.f;
-          __syncthreads();
+          float* part = p.part + ((int64_t)row * chunks + chunk) * Ppad;
 #pragma unroll 1
           for (int fi = 0; fi < nfillP; ++fi) {
             const int s = fi & 1;
             const int px0 = fi * WPXS, cnt = min(WPXS, P - px0);
-            mbar_wait(pp.full[s], pp.use[s] & 1);
-            pp.use[s]++;
+            pipe_wait(G.pp, s);
             const uint8_t* base = stg + s * STAGE + col * 16;
 #pragma unroll
             for (int u = 0; u < WPXS / GROUPS; ++u) {
-              const int pl = grp + u * GROUPS;          // warp-uniform
+              const int pl = grp + u * GROUPS;          // warp-uniform: the warp owns the pixel's 256 channels
               if (pl < cnt) {
                 const uint4 raw = *reinterpret_cast<const uint4*>(base + (size_t)pl * CHUNK * 2);
                 float f[8];
@@ -870,40 +937,37 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
 #pragma unroll
                 for (int k = 0; k < 8; ++k) sdot = fmaf(f[k], dawe[k], sdot);
                 sdot = warp_sum(sdot);
-                if (lane == 0) atomicAdd(&al[px0 + pl], sdot);     // the two warps of a pixel group
+                if (lane == 0) part[px0 + pl] = sdot;
               }
             }
             if (fi + 2 < nfillP) {
-              __syncthreads();
+              gsync(G);
               const int pxn = (fi + 2) * WPXS;
-              stage_fill(pp, s, src + (int64_t)pxn * CHUNK, (uint32_t)min(WPXS, P - pxn) * CHUNK * 2);
+              stage_fill(G, s, src + (int64_t)pxn * CHUNK, (uint32_t)min(WPXS, P - pxn) * CHUNK * 2);
             }
           }
-          __syncthreads();
-          if (tid < P) p.part[((int64_t)row * chunks + chunk) * Ppad + tid] = al[tid];
-          __syncthreads();
+          gsync(G);
         }
       }
       BSTAMP();
       // ================= B: softmax backward + relu / score backward =================
-      // item = (row, quarter of the attention channels): the quarter-major copy att1_cm makes the
-      // item's P x 128 slab contiguous (two bulk copies), datt2 / dw_f of different quarters are
-      // disjoint, and every CTA redoes the row's tiny softmax backward
-      grid_arrive(p.bar);
+      // item = (row, 64 attention channels): the eighth-major copy att1_cm makes the item's P x 64 slab
+      // contiguous (two bulk copies), datt2 / dw_f of different items are disjoint, and every item redoes the
+      // row's tiny softmax backward
+      grid_arrive(G);
       {
-        constexpr int QW = 128;                                  // channels per item
-        constexpr int BPX = STAGE / (QW * 2);                    // pixels per fill (128)
-        const int quarters = A / QW;
-        const int items = n * quarters;
-        const bool live = (int)blockIdx.x < items;
-        const int row = blockIdx.x / quarters, qa = blockIdx.x - row * quarters;
-        const bf16* src = p.att1_cm + ((int64_t)row * quarters + qa) * P * QW;
+        const int eighths = A / QW;
+        const int items = n * eighths;
+        const bool live = G.vcta < items;
+        const int rl = G.vcta / eighths, qa = G.vcta - rl * eighths;
+        const int row = row0 + rl;
+        const bf16* src = p.att1_cm + ((int64_t)row * eighths + qa) * P * QW;
         const int nfillB = (P + BPX - 1) / BPX;
         if (live) {
-          stage_fill(pp, 0, src, (uint32_t)min(BPX, P) * QW * 2);
-          if (nfillB > 1) stage_fill(pp, 1, src + (int64_t)BPX * QW, (uint32_t)min(BPX, P - BPX) * QW * 2);
+          stage_fill(G, 0, src, (uint32_t)min(BPX, P) * QW * 2);
+          if (nfillB > 1) stage_fill(G, 1, src + (int64_t)BPX * QW, (uint32_t)min(BPX, P - BPX) * QW * 2);
         }
-        grid_wait(p.bar, target);
+        grid_wait(G);
         BSTAMP();
         if (live) {
           // dalpha = sum of the channel-chunk partials (+ external); de = alpha (dalpha - alpha . dalpha)
@@ -914,27 +978,28 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             alp = __ldg(p.alphas + ((int64_t)row * T + t) * P + tid);
           }
           float dot = warp_sum(alp * d);
-          if (lane == 0) red[warp] = dot;
-          __syncthreads();
+          if (lane == 0) G.red[warp] = dot;
+          gsync(G);
           dot = 0.f;
 #pragma unroll
-          for (int w = 0; w < RW; ++w) dot += red[w];
+          for (int w = 0; w < GW; ++w) dot += G.red[w];
           const float x = alp * (d - dot);
           if (tid < P) {
             des[tid] = x;
             if (qa == 0) p.de[(tb + row) * Ppad + tid] = x;
           }
           float sde = warp_sum(tid < P ? x : 0.f);
-          if (lane == 0) red[RW + warp] = sde;
-          __syncthreads();
+          if (lane == 0) G.red[GW + warp] = sde;
+          gsync(G);
           if (tid == 0 && qa == 0) {
             float tot = 0.f;
 #pragma unroll
-            for (int w = 0; w < RW; ++w) tot += red[RW + w];
+            for (int w = 0; w < GW; ++w) tot += G.red[GW + w];
             p.dbf[tb + row] = tot;
           }
-          // warp per pixel, lane holds 4 attention features
-          const int a0 = qa * QW + lane * 4;
+          // half-warp per pixel, lane holds 4 attention features
+          const int hl = lane & 15, hp = lane >> 4;
+          const int a0 = qa * QW + hl * 4;
           float att2[4], wf[4], dacc[4], wacc[4];
           {
             const float4 x2 = __ldg(reinterpret_cast<const float4*>(p.g1 + (tb + row) * NG1 + a0));
@@ -948,11 +1013,10 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
           for (int fi = 0; fi < nfillB; ++fi) {
             const int s = fi & 1;
             const int px0 = fi * BPX, cnt = min(BPX, P - px0);
-            mbar_wait(pp.full[s], pp.use[s] & 1);
-            pp.use[s]++;
-            const uint8_t* base = stg + s * STAGE + lane * 8;
+            pipe_wait(G.pp, s);
+            const uint8_t* base = stg + s * STAGE + hl * 8;
 #pragma unroll 4
-            for (int pl = warp; pl < cnt; pl += RW) {
+            for (int pl = 2 * warp + hp; pl < cnt; pl += 2 * GW) {
               const float dep = des[px0 + pl];
               const uint2 raw = *reinterpret_cast<const uint2*>(base + (size_t)pl * QW * 2);
               const float f[4] = {__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
@@ -966,55 +1030,57 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
               }
             }
             if (fi + 2 < nfillB) {
-              __syncthreads();
+              gsync(G);
               const int pxn = (fi + 2) * BPX;
-              stage_fill(pp, s, src + (int64_t)pxn * QW, (uint32_t)min(BPX, P - pxn) * QW * 2);
+              stage_fill(G, s, src + (int64_t)pxn * QW, (uint32_t)min(BPX, P - pxn) * QW * 2);
             }
           }
-          __syncthreads();                                       // the staging buffers become the reduction scratch
-          float* slab = reinterpret_cast<float*>(stg);           // [RW][2][QW]
-          *reinterpret_cast<float4*>(slab + (warp * 2 + 0) * QW + lane * 4) = make_float4(dacc[0], dacc[1], dacc[2], dacc[3]);
-          *reinterpret_cast<float4*>(slab + (warp * 2 + 1) * QW + lane * 4) = make_float4(wacc[0], wacc[1], wacc[2], wacc[3]);
-          __syncthreads();
+          gsync(G);                                              // the staging buffers become the reduction scratch
+          float* slab = reinterpret_cast<float*>(stg);           // [2 GW half-warps][2][QW]
+          const int hw = 2 * warp + hp;
+          *reinterpret_cast<float4*>(slab + (hw * 2 + 0) * QW + hl * 4) = make_float4(dacc[0], dacc[1], dacc[2], dacc[3]);
+          *reinterpret_cast<float4*>(slab + (hw * 2 + 1) * QW + hl * 4) = make_float4(wacc[0], wacc[1], wacc[2], wacc[3]);
+          gsync(G);
           if (tid < 2 * QW) {
             const int which = tid / QW, aa = tid - which * QW;
             float sum = 0.f;
 #pragma unroll
-            for (int w = 0; w < RW; ++w) sum += slab[(w * 2 + which) * QW + aa];
+            for (int w = 0; w < 2 * GW; ++w) sum += slab[(w * 2 + which) * QW + aa];
             const int a = qa * QW + aa;
             if (which == 0) {
               const bf16 xb = __float2bfloat16_rn(sum);
               p.dbx[(tb + row) * p.ldbx + p.dbx_off + E + a] = xb;
-              p.dpxk[(((int64_t)t * nkc + nkq + chunks) * B + row) * KC + a] = xb;
+              p.dpxk[(((int64_t)t * nkc + nkq + E / KC) * B + row) * KC + a] = xb;
             } else {
               p.dwf[(tb + row) * A + a] = sum;
             }
           }
-          __syncthreads();
+          gsync(G);
+          if (tid == 0) fence_proxy_async();                     // the slab (generic writes) is overwritten by bulk copies next
         }
       }
     }
     BSTAMP();
-    grid_arrive(p.bar);
-    grid_wait(p.bar, target);
+    grid_arrive(G);
+    grid_wait(G);
     BSTAMP();
     // ================= H: dh_{t-1} += [dp | dbeta_pre | datt2] chunk . W_hx chunk^T =================
 #pragma unroll 1
     for (int i = 0; i < 2; ++i) {
-      const int j = c + i * gridDim.x;
+      const int j = c + i * nctas;
       if (j < jobsH) {
         const int ds = j / nkc, kc = j - ds * nkc;
         float out[1];
-        const bf16* srcH = (LSTM && kc < nkq) ? p.dpre_gm + ((int64_t)t * 4 + kc) * B * D
-                                              : p.dpxk + ((int64_t)t * nkc + kc) * B * KC;
-        gemm_job<1, 2>(pp, srcH, 0, n, WHs + (size_t)i * 16 * wHs, wHs, 1, red, out);
+        const bf16* srcH = ((LSTM && kc < nkq) ? p.dpre_gm + ((int64_t)t * 4 + kc) * B * D
+                                               : p.dpxk + ((int64_t)t * nkc + kc) * B * KC) + (int64_t)row0 * KC;
+        gemm_job<1, 2>(G, srcH, 0, n, WHs + (size_t)i * 16 * wHs, wHs, 1, out);
         const int d = ds * 16 + ej;
-        if (erow < n && d < D) atomicAdd(p.dh_rec + (tb + erow) * D + d, out[0]);
+        if (lrow < n && d < D) atomicAdd(p.dh_rec + (tb + erow) * D + d, out[0]);
       }
     }
     BSTAMP();
-    grid_arrive(p.bar);
-    grid_wait(p.bar, target);
+    grid_arrive(G);
+    grid_wait(G);
     BSTAMP();
   }
 #undef BSTAMP
@@ -1053,14 +1119,14 @@ const DevInfo* dev_info() {
 }
 
 size_t fwd_smem_bytes(const RecurFwdArgs& a, int nt1, int nt3, int nt4) {
-  size_t s = 2 * (size_t)STAGE;
+  size_t s = 4 * (size_t)STAGE;
   s += (size_t)nt1 * 8 * (a.D * 2 + WPAD);
   if (a.att) s += (size_t)nt3 * 8 * (a.E * 2 + WPAD);
   s += (size_t)nt4 * 8 * (2 * a.F * 2 + WPAD);
-  s += (size_t)KSL * 32 * REDLD * 4;
-  s += (size_t)pad4i(a.P > 0 ? a.P : 4) * 4;
+  s += (size_t)2 * REDF * 4;
+  s += (size_t)2 * pad4i(a.P > 0 ? a.P : 4) * 4;
   s += (size_t)(((a.B + 3) & ~3) + 2) * 4;
-  return s + 8 + 2 * 8 + 128;
+  return s + 8 + 4 * 8 + 128;
 }
 
 int pick_nt(int tiles, int ctas) {
@@ -1084,7 +1150,7 @@ bool plan_fwd(const RecurFwdArgs& a, const DevInfo* di, int* nt1, int* nt3, int*
   if (a.B < 1 || a.B > 32 || a.T < 1) return false;
   if (a.D != KC || (!a.lstm && 2 * a.F != 2 * KC)) return false;   // G1 operand = one 512-wide fill, P4 operand = one 1024-wide fill
   if (a.lstm && !a.att) return false;
-  if (a.att && (a.E % KC || a.E % CHUNK || a.A % 8 || a.A > 512 || a.P < 1 || a.P > RT)) return false;
+  if (a.att && (a.E % KC || a.E % CHUNK || a.A % 8 || a.A > 512 || a.P < 1 || a.P > GT)) return false;
   const int NQ = a.lstm ? 4 * a.D : 4 * a.F, NG1 = (a.att ? a.A + a.E : 0) + NQ;
   *nt1 = pick_nt(NG1 / 8, di->sms);
   *nt3 = a.att ? pick_nt(NQ / 8, di->sms) : 2;
@@ -1111,7 +1177,7 @@ bool recur_fwd_supported(const RecurFwdArgs& a) {
   return plan_fwd(a, dev_info(), &n1, &n3, &n4, &smem);
 }
 
-// once per batch, before recur_fwd: the chunk-major copy of the features ([B][E/512][P][512])
+// once per batch, before recur_fwd: the chunk-major copy of the features ([B][E/256][P][256])
 int recur_fwd_prepare(const RecurFwdArgs& a, cudaStream_t st) {
   if (!a.att) return CAPDEC_OK;
   return chunk_major_copy(a.enc, a.enc_cm, a.B, a.P, a.E, CHUNK, st);
@@ -1142,7 +1208,7 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   CAPDEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RT, smem));
   CAPDEC_REQUIRE(per_sm >= 1, CAPDEC_ERR_CUDA, "recur_fwd: kernel does not fit one CTA per SM (smem %zu)", smem);
   CAPDEC_REQUIRE(a.ldH0 == a.D, CAPDEC_ERR_BAD_SHAPE, "recur_fwd: H0 must be dense");
-  CAPDEC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 4, st));
+  CAPDEC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, st));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(di->sms, 1, 1);
@@ -1190,14 +1256,14 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
 
 namespace {
 size_t bwd_smem_bytes(const RecurBwdArgs& a) {
-  size_t s = 2 * (size_t)STAGE;
+  size_t s = 4 * (size_t)STAGE;
   s += (size_t)32 * (a.D * 2 + WPAD);
   if (a.att) s += (size_t)16 * ((a.lstm ? 4 * a.D : 4 * a.F) * 2 + WPAD);
   s += (size_t)32 * (KC * 2 + WPAD);
-  s += (size_t)KSL * 32 * REDLD * 4;
+  s += (size_t)2 * REDF * 4;
   s += (size_t)2 * pad4i(a.P > 0 ? a.P : 4) * 4;
   s += (size_t)(((a.B + 3) & ~3) + 2) * 4;
-  return s + 8 + 2 * 8 + 128;
+  return s + 8 + 4 * 8 + 128;
 }
 
 bool plan_bwd(const RecurBwdArgs& a, const DevInfo* di, size_t* smem) {
@@ -1205,14 +1271,12 @@ bool plan_bwd(const RecurBwdArgs& a, const DevInfo* di, size_t* smem) {
   if (a.B < 1 || a.B > 32 || a.T < 1) return false;
   if (a.lstm && !a.att) return false;
   if (a.D != KC || (!a.lstm && (a.F % 16 || (4 * a.F) % KC))) return false;
-  if (a.att && (a.E % KC || a.A != KC || a.P < 1 || a.P > RT)) return false;
+  if (a.att && (a.E % KC || a.E % CHUNK || a.A != KC || a.A % QW || a.P < 1 || a.P > GT)) return false;
   const int NQ = a.lstm ? 4 * a.D : 4 * a.F, KH = NQ + (a.att ? a.E + a.A : 0);
   if (!a.lstm && 4 * (2 * a.F / 32) > di->sms) return false;    // W job: one 32-feature slice per CTA
   if (a.att && a.E / 16 > di->sms) return false;                // Z job: 16 features per CTA
   if ((a.D / 16) * (KH / KC) > 2 * di->sms) return false;       // H jobs: at most two per CTA
-  // red also holds the [2][A] accumulators of phase B
-  if (a.att && 4 * a.A / 128 * a.B > 4 * di->sms) return false;  // B items: one (row, quarter) per CTA
-  if (a.att && a.B * (a.A / 128) > di->sms) return false;
+  if (a.att && GR * (a.A / QW) > di->sms) return false;         // B items: one (row, 64 channels) per CTA and row group
   *smem = bwd_smem_bytes(a);
   return *smem <= (size_t)di->smem_optin;
 }
@@ -1250,10 +1314,10 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
     CAPDEC_LAUNCH_OK();
   }
   if (a.att) {
-    chunk_major_kernel<<<di->sms * 4, 256, 0, st>>>((const uint4*)a.att1, (uint4*)a.att1_cm, a.B, a.P, a.A, 128);
+    chunk_major_kernel<<<di->sms * 4, 256, 0, st>>>((const uint4*)a.att1, (uint4*)a.att1_cm, a.B, a.P, a.A, QW);
     CAPDEC_LAUNCH_OK();
   }
-  CAPDEC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 4, st));
+  CAPDEC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, st));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(di->sms, 1, 1);
