@@ -19,6 +19,7 @@ SOURCES = ["capi.cu", "decoder.cu", "attention.cu", "pointwise.cu", "loss.cu", "
            "gemm_tc.cu", "beam.cu", "recur.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+NVCC_FLAGS += os.environ.get("CAPDEC_NVCC_FLAGS", "").split()      # e.g. -DCAPDEC_RECUR_FINE (debug stamps)
 
 
 def _nvcc():

@@ -62,8 +62,27 @@ constexpr int BPX = STAGE / (QW * 2);       // pixels per fill of phase B (128)
 static_assert(NCOL == 32, "weighted-sum mapping: one warp per pixel group");
 static_assert(REDF >= 2 * GW + (GROUPS - 1) * NCOL * 8, "reduction scratch too small for the weighted sum");
 static_assert(2 * STAGE >= 2 * GW * 2 * QW * 4, "staging buffers too small for the phase-B slab");
+static_assert(REDF >= CHUNK / 2 + 4 * GT, "reduction scratch too small for phase A (dawe + 4 x pad4(P) partials, P <= GT)");
+static_assert(WPXS == 32 && GW == 8 && CHUNK == 256, "phase A: 2 pixel tiles x 4 channel quarters per fill");
 
 __host__ __device__ __forceinline__ int pad4i(int x) { return (x + 3) & ~3; }
+
+// Debug build only (-DCAPDEC_RECUR_FINE): tagged clock stamps of thread 0 of CTA 0 (row group 0) inside the phases,
+// printed by the launchers when CAPDEC_RECUR_PROF=1.
+#ifdef CAPDEC_RECUR_FINE
+constexpr int FINE_N = 1 << 16;
+__device__ unsigned long long d_fine[FINE_N];
+__device__ unsigned d_fine_idx;
+#define FSTAMP(tag)                                                                                   \
+  do {                                                                                                \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && G.fidx < FINE_N)                                       \
+      d_fine[G.fidx++] = ((unsigned long long)(tag) << 48) | ((unsigned long long)clock64() & 0xffffffffffffull); \
+  } while (0)
+#define FSTAMP_FLUSH() do { if (blockIdx.x == 0 && threadIdx.x == 0) d_fine_idx = G.fidx; } while (0)
+#else
+#define FSTAMP(tag) do { } while (0)
+#define FSTAMP_FLUSH() do { } while (0)
+#endif
 
 __device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2,
                                          uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -105,6 +124,9 @@ struct Grp {
   float* al;           // [pad4(P)]
   unsigned* bar;       // the group's grid-barrier counter
   unsigned target;
+#ifdef CAPDEC_RECUR_FINE
+  unsigned fidx;
+#endif
 };
 
 // barrier over the 256 threads of a row group
@@ -148,9 +170,10 @@ __device__ __forceinline__ void stage_fill(const Grp& G, int s, const void* src,
 // (8 consecutive k) per row and block with ONE LDS.128 and feeds them to two m16n8k16 mma -- the same
 // k permutation is used for the weight fragments, so no ldmatrix / transposition is needed.  The 8
 // K-slice partials meet in shared memory.
-template <int NH, int BPW>
+// PRE = true: the caller already issued the (single) fill into stage s0.
+template <int NH, int BPW, bool PRE = false>
 __device__ __forceinline__ void gemm_job(Grp& G, const bf16* __restrict__ src, int64_t fill_stride, int n,
-                                         const uint8_t* Ws, int wstride, int nfill, float (&out)[NH]) {
+                                         const uint8_t* Ws, int wstride, int nfill, float (&out)[NH], int s0 = 0) {
   constexpr int KF = 64 * BPW * 4;           // K elements per fill: 8 slices x BPW blocks x 32
   constexpr int SPF = KF * 2 * GR / STAGE;   // stages one fill occupies (1 or 2)
   Pipe& pp = G.pp;
@@ -158,8 +181,12 @@ __device__ __forceinline__ void gemm_job(Grp& G, const bf16* __restrict__ src, i
   const int g = lane >> 2, c = lane & 3;
   const int ks = G.warp;
   const uint32_t fill_bytes = (uint32_t)n * KF * 2;
-  stage_fill(G, 0, src, fill_bytes);
-  if (SPF == 1 && nfill > 1) stage_fill(G, 1, src + fill_stride, fill_bytes);
+  FSTAMP(100);
+  if (!PRE) {
+    stage_fill(G, 0, src, fill_bytes);
+    if (SPF == 1 && nfill > 1) stage_fill(G, 1, src + fill_stride, fill_bytes);
+  }
+  FSTAMP(101);
   // one accumulator per (n-tile, k block): legacy mma.sync has a long issue-to-result latency on sm_100, so
   // the only dependent pair inside a fill is the two k16 halves of one block
   float accb[2 * NH][BPW][4];
@@ -173,8 +200,9 @@ __device__ __forceinline__ void gemm_job(Grp& G, const bf16* __restrict__ src, i
   const uint8_t* w_base = Ws + (size_t)g * wstride + ks * (BPW * 64) + 16 * c;
 #pragma unroll 1
   for (int kf = 0; kf < nfill; ++kf) {
-    const int s = SPF == 1 ? (kf & 1) : 0;
+    const int s = PRE ? s0 : SPF == 1 ? (kf & 1) : 0;
     pipe_wait(pp, s);
+    FSTAMP(102);
     const uint8_t* ap = a_base + s * STAGE;
     const uint8_t* wp = w_base + (size_t)kf * KF * 2;
 #pragma unroll
@@ -193,6 +221,7 @@ __device__ __forceinline__ void gemm_job(Grp& G, const bf16* __restrict__ src, i
       stage_fill(G, s, src + (int64_t)(kf + 2) * fill_stride, fill_bytes);
     }
   }
+  FSTAMP(103);
   float acc[2 * NH][4];
 #pragma unroll
   for (int nt = 0; nt < 2 * NH; ++nt)
@@ -220,6 +249,7 @@ __device__ __forceinline__ void gemm_job(Grp& G, const bf16* __restrict__ src, i
     out[h] = sum;
   }
   gsync(G);                                  // staging buffers and `red` are free again
+  FSTAMP(104);
 }
 
 // copy `nrows` weight rows (K bf16 each, global pitch ldw elements) into shared memory rows of
@@ -253,6 +283,9 @@ __device__ __forceinline__ void grp_init(Grp& G, uint8_t* stg, float* red, float
   G.al = al + (size_t)G.g * alw;
   G.bar = gbar + G.g * 32;                   // counters 128 bytes apart
   G.target = 0;
+#ifdef CAPDEC_RECUR_FINE
+  G.fidx = 0;
+#endif
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -346,7 +379,9 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
   int stamp = 0;
 #define RECUR_STAMP()                                                                                  \
   do {                                                                                                 \
-    if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[t * 16 + (stamp++ & 15)] = clock64();    \
+    if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[t * 16 + (stamp & 15)] = clock64();      \
+    FSTAMP(stamp);                                                                                     \
+    ++stamp;                                                                                           \
   } while (0)
 #pragma unroll 1
   for (int t = 0; t < T; ++t) {
@@ -406,23 +441,58 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
       const int per = (items + nctas - 1) / nctas;
       const int i0 = G.vcta * per, i1 = min(items, i0 + per);
       grid_arrive(G);
+      // step-independent operands (score weights) are requested before the barrier is crossed
+      float wf[2][8];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int a = cc * 256 + a_lane;
+        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+        if (a < A) {
+          w0 = __ldg(reinterpret_cast<const float4*>(p.w_f + a));
+          w1 = __ldg(reinterpret_cast<const float4*>(p.w_f + a + 4));
+        }
+        wf[cc][0] = w0.x; wf[cc][1] = w0.y; wf[cc][2] = w0.z; wf[cc][3] = w0.w;
+        wf[cc][4] = w1.x; wf[cc][5] = w1.y; wf[cc][6] = w1.z; wf[cc][7] = w1.w;
+      }
+      const float bfv = __ldg(p.b_f);
+      const int sci = min(SCI, P);                     // items per fill: never more than one row's worth
 #pragma unroll 1
-      for (int base = i0; base < i1 || base == i0; base += SCI) {
-        const int cnt = (p.mask & 2) ? max(0, min(SCI, i1 - base)) : 0;
+      for (int base = i0; base < i1 || base == i0; base += sci) {
+        const int cnt = (p.mask & 2) ? max(0, min(sci, i1 - base)) : 0;
         if (cnt > 0) stage_fill(G, 0, p.att1 + ((int64_t)row0 * P + base) * A, (uint32_t)cnt * A * 2);
         if (base == i0) {
           grid_wait(G);
           RECUR_STAMP();
         }
         if (cnt > 0) {
+          // a fill's items lie in at most two consecutive rows (sci <= P): both att2 rows are requested at once,
+          // ONE L2 round trip per fill instead of one per item
+          const int bl0 = base / P;
+          const int px_split = (bl0 + 1) * P - base;     // items at or beyond this index belong to row bl0 + 1
+          float x2[2][2][8];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const bool need = r == 0 || px_split < cnt;
+            const float* g1 = p.g1 + (tb + row0 + bl0 + r) * NG1;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int a = cc * 256 + a_lane;
+              float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+              if (need && a < A) {
+                x0 = __ldcg(reinterpret_cast<const float4*>(g1 + a));
+                x1 = __ldcg(reinterpret_cast<const float4*>(g1 + a + 4));
+              }
+              x2[r][cc][0] = x0.x; x2[r][cc][1] = x0.y; x2[r][cc][2] = x0.z; x2[r][cc][3] = x0.w;
+              x2[r][cc][4] = x1.x; x2[r][cc][5] = x1.y; x2[r][cc][6] = x1.z; x2[r][cc][7] = x1.w;
+            }
+          }
           pipe_wait(G.pp, 0);
-          const float bfv = __ldg(p.b_f);
+          FSTAMP(120);
 #pragma unroll 1
           for (int i = warp; i < cnt; i += GW) {
-            const int it = base + i;
-            const int bl = it / P, px = it - bl * P;
-            const int b = row0 + bl;
-            const float* g1 = p.g1 + (tb + b) * NG1;
+            const bool second = i >= px_split;
+            const int bl = bl0 + (second ? 1 : 0);
+            const int px = base + i - bl * P;
             float s = 0.f;
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -431,20 +501,15 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
                 const uint4 raw = *reinterpret_cast<const uint4*>(stg + (size_t)(i * A + a) * 2);
                 float f[8];
                 unpack16(raw, f, bf16());
-                const float4 x0 = __ldcg(reinterpret_cast<const float4*>(g1 + a));
-                const float4 x1 = __ldcg(reinterpret_cast<const float4*>(g1 + a + 4));
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_f + a));
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_f + a + 4));
-                s = fmaf(w0.x, fmaxf(f[0] + x0.x, 0.f), s); s = fmaf(w0.y, fmaxf(f[1] + x0.y, 0.f), s);
-                s = fmaf(w0.z, fmaxf(f[2] + x0.z, 0.f), s); s = fmaf(w0.w, fmaxf(f[3] + x0.w, 0.f), s);
-                s = fmaf(w1.x, fmaxf(f[4] + x1.x, 0.f), s); s = fmaf(w1.y, fmaxf(f[5] + x1.y, 0.f), s);
-                s = fmaf(w1.z, fmaxf(f[6] + x1.z, 0.f), s); s = fmaf(w1.w, fmaxf(f[7] + x1.w, 0.f), s);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  s = fmaf(wf[cc][k], fmaxf(f[k] + (second ? x2[1][cc][k] : x2[0][cc][k]), 0.f), s);
               }
             }
             s = warp_sum(s);
-            if (lane == 0) p.scores[(int64_t)b * Ppad + px] = s + bfv;
+            if (lane == 0) p.scores[(int64_t)(row0 + bl) * Ppad + px] = s + bfv;
           }
-          if (base + SCI < i1) gsync(G);
+          if (base + sci < i1) gsync(G);
         }
       }
       RECUR_STAMP();
@@ -502,6 +567,7 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
             if (chunk == 0) p.alphas[((int64_t)row * T + t) * P + tid] = alpha;
           }
           gsync(G);
+          FSTAMP(110);
           float acc[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -510,6 +576,7 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
             const int s = fi & 1;
             const int px0 = fi * WPXS, cnt = min(WPXS, P - px0);
             pipe_wait(G.pp, s);
+            FSTAMP(111);
             const uint8_t* base = stg + s * STAGE + col * 16;
 #pragma unroll
             for (int u = 0; u < WPXS / GROUPS; ++u) {
@@ -529,6 +596,7 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
               stage_fill(G, s, src + (int64_t)pxn * CHUNK, (uint32_t)min(WPXS, P - pxn) * CHUNK * 2);
             }
           }
+          FSTAMP(112);
           // cross-group reduction through shared memory (red: >= 2 GW + (GROUPS-1) * NCOL * 8 floats)
           if (grp > 0) {
             float4* dst = reinterpret_cast<float4*>(G.red + 2 * GW + ((grp - 1) * NCOL + col) * 8);
@@ -646,6 +714,7 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
     grid_wait(G);
     RECUR_STAMP();
   }
+  FSTAMP_FLUSH();
 #undef RECUR_STAMP
 }
 
@@ -761,8 +830,10 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
   const float drop_p = p.dropout_p;
   const uint64_t seed = drop_p > 0.f ? __ldg(p.seed) : 0ull;
   const int nfillP = (P + WPXS - 1) / WPXS;
+  bf16* const dwv = reinterpret_cast<bf16*>(G.red);        // phase A: dawe of the item, bf16 [CHUNK]
+  float* const psum = G.red + CHUNK / 2;                   // phase A: [4 K quarters][pad4(P)] partial dalpha
   int stamp = 0;
-#define BSTAMP() do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[t * 16 + (stamp++ & 15)] = clock64(); } while (0)
+#define BSTAMP() do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[t * 16 + (stamp & 15)] = clock64(); FSTAMP(stamp); ++stamp; } while (0)
 
 #pragma unroll 1
   for (int t = T - 1; t >= 0; --t) {
@@ -917,27 +988,44 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
               const uint4 pk = pack16(db, bf16());
               *reinterpret_cast<uint4*>(p.dbx + (tb + row) * p.ldbx + p.dbx_off + e0) = pk;
               *reinterpret_cast<uint4*>(p.dpxk + (((int64_t)t * nkc + nkq + e0 / KC) * B + row) * KC + (e0 % KC)) = pk;
+              // dawe as the (single useful) column of the mma B operand
+              *reinterpret_cast<uint4*>(dwv + col * 8) = pack16(dawe, bf16());
             }
           }
-          float* part = p.part + ((int64_t)row * chunks + chunk) * Ppad;
+          gsync(G);
+          FSTAMP(130);
+          // dalpha[px] = enc[px, chunk] . dawe on the tensor pipe: per fill, warp (pt, kq) multiplies the 16-pixel
+          // tile pt with 64 channels (two 32-wide k blocks, same 16-byte-per-lane k permutation as gemm_job); only
+          // column 0 of the n8 tile carries dawe.  ~10 instructions per warp and fill instead of ~120 scalar ones
+          // (the scalar version was issue bound: 1 400 cycles per fill).
+          const int pt = warp & 1, kq = warp >> 1;
+          const int mg = lane >> 2, mc = lane & 3;
+          uint4 bfrag[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            bfrag[j] = mg == 0 ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(dwv) + kq * 128 + j * 64 + 16 * mc)
+                               : make_uint4(0, 0, 0, 0);
 #pragma unroll 1
           for (int fi = 0; fi < nfillP; ++fi) {
             const int s = fi & 1;
             const int px0 = fi * WPXS, cnt = min(WPXS, P - px0);
             pipe_wait(G.pp, s);
-            const uint8_t* base = stg + s * STAGE + col * 16;
+            FSTAMP(131);
+            if (pt * 16 < cnt) {                         // warp-uniform
+              const uint8_t* ap = stg + s * STAGE + (size_t)(pt * 16 + mg) * (CHUNK * 2) + kq * 128 + 16 * mc;
+              float acc[2][4];
 #pragma unroll
-            for (int u = 0; u < WPXS / GROUPS; ++u) {
-              const int pl = grp + u * GROUPS;          // warp-uniform: the warp owns the pixel's 256 channels
-              if (pl < cnt) {
-                const uint4 raw = *reinterpret_cast<const uint4*>(base + (size_t)pl * CHUNK * 2);
-                float f[8];
-                unpack16(raw, f, bf16());
-                float sdot = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) sdot = fmaf(f[k], dawe[k], sdot);
-                sdot = warp_sum(sdot);
-                if (lane == 0) part[px0 + pl] = sdot;
+              for (int j = 0; j < 2; ++j) {
+                acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+                const uint4 alo = *reinterpret_cast<const uint4*>(ap + j * 64);
+                const uint4 ahi = *reinterpret_cast<const uint4*>(ap + 8 * (CHUNK * 2) + j * 64);
+                mma_bf16(acc[j], alo.x, ahi.x, alo.y, ahi.y, bfrag[j].x, bfrag[j].y);
+                mma_bf16(acc[j], alo.z, ahi.z, alo.w, ahi.w, bfrag[j].z, bfrag[j].w);
+              }
+              if (mc == 0) {                             // column 0 of the n8 tile
+                const int pa = px0 + pt * 16 + mg;
+                if (pa < P) psum[kq * Ppad + pa] = acc[0][0] + acc[1][0];
+                if (pa + 8 < P) psum[kq * Ppad + pa + 8] = acc[0][2] + acc[1][2];
               }
             }
             if (fi + 2 < nfillP) {
@@ -946,6 +1034,10 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
               stage_fill(G, s, src + (int64_t)pxn * CHUNK, (uint32_t)min(WPXS, P - pxn) * CHUNK * 2);
             }
           }
+          gsync(G);
+          if (tid < P)
+            p.part[((int64_t)row * chunks + chunk) * Ppad + tid] =
+                (psum[tid] + psum[Ppad + tid]) + (psum[2 * Ppad + tid] + psum[3 * Ppad + tid]);
           gsync(G);
         }
       }
@@ -967,15 +1059,34 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
           stage_fill(G, 0, src, (uint32_t)min(BPX, P) * QW * 2);
           if (nfillB > 1) stage_fill(G, 1, src + (int64_t)BPX * QW, (uint32_t)min(BPX, P - BPX) * QW * 2);
         }
+        // saved forward activations / loss gradients do not depend on this step's barrier: requested before it is crossed
+        const int hl = lane & 15, hp = lane >> 4;      // half-warp per pixel, lane holds 4 attention features
+        const int a0 = qa * QW + hl * 4;
+        float d = 0.f, alp = 0.f;
+        float4 x2 = make_float4(0.f, 0.f, 0.f, 0.f), w4 = x2;
+        if (live) {
+          if (tid < P) {
+            if (p.d_alphas) d = __ldg(p.d_alphas + ((int64_t)row * T + t) * P + tid);
+            alp = __ldg(p.alphas + ((int64_t)row * T + t) * P + tid);
+          }
+          x2 = __ldg(reinterpret_cast<const float4*>(p.g1 + (tb + row) * NG1 + a0));
+          w4 = __ldg(reinterpret_cast<const float4*>(p.w_f + a0));
+        }
         grid_wait(G);
         BSTAMP();
         if (live) {
           // dalpha = sum of the channel-chunk partials (+ external); de = alpha (dalpha - alpha . dalpha)
-          float d = 0.f, alp = 0.f;
           if (tid < P) {
-            for (int cc = 0; cc < chunks; ++cc) d += __ldcg(p.part + ((int64_t)row * chunks + cc) * Ppad + tid);
-            if (p.d_alphas) d += __ldg(p.d_alphas + ((int64_t)row * T + t) * P + tid);
-            alp = __ldg(p.alphas + ((int64_t)row * T + t) * P + tid);
+            // independent loads: all in flight together (a running sum would serialise 8 L2 round trips)
+            const float* pp0 = p.part + (int64_t)row * chunks * Ppad + tid;
+            int cc = 0;
+            for (; cc + 8 <= chunks; cc += 8) {
+              float v[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = __ldcg(pp0 + (int64_t)(cc + k) * Ppad);
+              d += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+            }
+            for (; cc < chunks; ++cc) d += __ldcg(pp0 + (int64_t)cc * Ppad);
           }
           float dot = warp_sum(alp * d);
           if (lane == 0) G.red[warp] = dot;
@@ -997,13 +1108,9 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             for (int w = 0; w < GW; ++w) tot += G.red[GW + w];
             p.dbf[tb + row] = tot;
           }
-          // half-warp per pixel, lane holds 4 attention features
-          const int hl = lane & 15, hp = lane >> 4;
-          const int a0 = qa * QW + hl * 4;
+          FSTAMP(140);
           float att2[4], wf[4], dacc[4], wacc[4];
           {
-            const float4 x2 = __ldg(reinterpret_cast<const float4*>(p.g1 + (tb + row) * NG1 + a0));
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w_f + a0));
             att2[0] = x2.x; att2[1] = x2.y; att2[2] = x2.z; att2[3] = x2.w;
             wf[0] = w4.x; wf[1] = w4.y; wf[2] = w4.z; wf[3] = w4.w;
           }
@@ -1014,6 +1121,7 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             const int s = fi & 1;
             const int px0 = fi * BPX, cnt = min(BPX, P - px0);
             pipe_wait(G.pp, s);
+            FSTAMP(141);
             const uint8_t* base = stg + s * STAGE + hl * 8;
 #pragma unroll 4
             for (int pl = 2 * warp + hp; pl < cnt; pl += 2 * GW) {
@@ -1035,6 +1143,7 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
               stage_fill(G, s, src + (int64_t)pxn * QW, (uint32_t)min(BPX, P - pxn) * QW * 2);
             }
           }
+          FSTAMP(142);
           gsync(G);                                              // the staging buffers become the reduction scratch
           float* slab = reinterpret_cast<float*>(stg);           // [2 GW half-warps][2][QW]
           const int hw = 2 * warp + hp;
@@ -1065,17 +1174,29 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
     grid_wait(G);
     BSTAMP();
     // ================= H: dh_{t-1} += [dp | dbeta_pre | datt2] chunk . W_hx chunk^T =================
-#pragma unroll 1
-    for (int i = 0; i < 2; ++i) {
-      const int j = c + i * nctas;
-      if (j < jobsH) {
+    // the CTA's (at most two) jobs use one staging buffer each: both operand copies are in flight at once
+    {
+      const bf16* srcH[2];
+      bool hasH[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int j = c + i * nctas;
+        hasH[i] = j < jobsH;
         const int ds = j / nkc, kc = j - ds * nkc;
-        float out[1];
-        const bf16* srcH = ((LSTM && kc < nkq) ? p.dpre_gm + ((int64_t)t * 4 + kc) * B * D
-                                               : p.dpxk + ((int64_t)t * nkc + kc) * B * KC) + (int64_t)row0 * KC;
-        gemm_job<1, 2>(G, srcH, 0, n, WHs + (size_t)i * 16 * wHs, wHs, 1, out);
-        const int d = ds * 16 + ej;
-        if (lrow < n && d < D) atomicAdd(p.dh_rec + (tb + erow) * D + d, out[0]);
+        srcH[i] = ((LSTM && kc < nkq) ? p.dpre_gm + ((int64_t)t * 4 + kc) * B * D
+                                      : p.dpxk + ((int64_t)t * nkc + kc) * B * KC) + (int64_t)row0 * KC;
+        if (hasH[i]) stage_fill(G, i, srcH[i], (uint32_t)n * KC * 2);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (hasH[i]) {
+          const int j = c + i * nctas;
+          const int ds = j / nkc;
+          float out[1];
+          gemm_job<1, 2, true>(G, srcH[i], 0, n, WHs + (size_t)i * 16 * wHs, wHs, 1, out, i);
+          const int d = ds * 16 + ej;
+          if (lrow < n && d < D) atomicAdd(p.dh_rec + (tb + erow) * D + d, out[0]);
+        }
       }
     }
     BSTAMP();
@@ -1083,6 +1204,7 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
     grid_wait(G);
     BSTAMP();
   }
+  FSTAMP_FLUSH();
 #undef BSTAMP
 }
 
@@ -1099,6 +1221,35 @@ __global__ void chunk_major_kernel(const uint4* __restrict__ src, uint4* __restr
     dst[(((int64_t)b * chunks + c) * P + px) * vpc + j] = src[i];
   }
 }
+
+#ifdef CAPDEC_RECUR_FINE
+void fine_reset() {
+  unsigned z = 0;
+  cudaMemcpyToSymbol(d_fine_idx, &z, sizeof z);
+}
+void fine_dump(const char* name) {
+  unsigned n = 0;
+  cudaMemcpyFromSymbol(&n, d_fine_idx, sizeof n);
+  if (n > FINE_N) n = FINE_N;
+  std::vector<unsigned long long> h(n);
+  if (n) cudaMemcpyFromSymbol(h.data(), d_fine, n * sizeof(unsigned long long));
+  // print the stamps of one step in the middle: a step starts at tag 0
+  std::vector<unsigned> starts;
+  for (unsigned i = 0; i < n; ++i)
+    if ((h[i] >> 48) == 0) starts.push_back(i);
+  if (starts.size() < 4) return;
+  for (size_t which : {starts.size() / 2, starts.size() / 2 + 1}) {
+    const unsigned b = starts[which], e = which + 1 < starts.size() ? starts[which + 1] : n;
+    fprintf(stderr, "%s fine step #%zu:", name, which);
+    for (unsigned i = b + 1; i <= e && i < n; ++i)
+      fprintf(stderr, " %u:%lld", (unsigned)(h[i] >> 48), (long long)((h[i] & 0xffffffffffffull) - (h[i - 1] & 0xffffffffffffull)));
+    fprintf(stderr, "\n");
+  }
+}
+#else
+void fine_reset() {}
+void fine_dump(const char*) {}
+#endif
 
 struct DevInfo { int sms = 0; int smem_optin = 0; bool coop = false; };
 DevInfo g_dev[64];
@@ -1225,6 +1376,7 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   const char* prof_env = getenv("CAPDEC_RECUR_PROF");
   const bool prof = prof_env && prof_env[0] == '1';
   if (prof) {
+    fine_reset();
     CAPDEC_CUDA_OK(cudaMalloc(&p.prof, (size_t)(a.T * 16 + 64) * sizeof(long long)));
     CAPDEC_CUDA_OK(cudaMemsetAsync(p.prof, 0, (size_t)(a.T * 16 + 64) * sizeof(long long), st));
   }
@@ -1250,6 +1402,7 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
       for (int k = 1; k < 16 && h[t * 16 + k]; ++k) fprintf(stderr, " %lld", h[t * 16 + k] - h[t * 16 + k - 1]);
       fprintf(stderr, "\n");
     }
+    fine_dump("recur_fwd");
   }
   return CAPDEC_OK;
 }
@@ -1332,6 +1485,7 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
   const char* prof_env = getenv("CAPDEC_RECUR_PROF");
   const bool prof = prof_env && prof_env[0] == '1';
   if (prof) {
+    fine_reset();
     CAPDEC_CUDA_OK(cudaMalloc(&p.prof, (size_t)a.T * 16 * sizeof(long long)));
     CAPDEC_CUDA_OK(cudaMemsetAsync(p.prof, 0, (size_t)a.T * 16 * sizeof(long long), st));
   }
@@ -1356,6 +1510,7 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
       for (int k = 1; k < 16 && h[t * 16 + k]; ++k) fprintf(stderr, " %lld", h[t * 16 + k] - h[t * 16 + k - 1]);
       fprintf(stderr, "\n");
     }
+    fine_dump("recur_bwd");
   }
   return CAPDEC_OK;
 }
