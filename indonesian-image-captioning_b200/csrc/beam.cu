@@ -94,9 +94,13 @@ __device__ __forceinline__ void list_insert(ArgMax (&l)[KL], ArgMax cand) {
 // FAST (bf16 mode): ONE pass per row -- online log-sum-exp and the row's KL largest raw logits per thread
 // (within a row, ordering by logit = ordering by log-probability); the exact mode keeps the three-pass
 // arithmetic that the fp32 token-parity tests pin.
-template <int KL, bool FAST>
+// FAST = 2: `logits` is the partial buffer written by the fused vocabulary kernel (gemm_tc_vocab_topk):
+// [row][slots][2 + 2 KL] = {max, sum exp, KL largest logits, their indices} per run of vocabulary tiles one CTA of
+// that kernel walked; the row's log-sum-exp and candidates are merged from its valid slots (the schedule is
+// recomputed from the plan), the (rows x V) logits are never materialised.
+template <int KL, int FAST>
 __global__ void __launch_bounds__(NT)
-beam_select_kernel(const float* __restrict__ logits, int V, int k, int t, int32_t end_id,
+beam_select_kernel(const float* __restrict__ logits, int V, VocabTopkPlan vp, int k, int t, int32_t end_id,
                    const float* __restrict__ score_in, float* __restrict__ score_out,
                    int32_t* __restrict__ prev_word, int32_t* __restrict__ src_row,
                    int32_t* __restrict__ live, int32_t* __restrict__ krem,
@@ -134,7 +138,29 @@ beam_select_kernel(const float* __restrict__ logits, int V, int k, int t, int32_
 #pragma unroll
       for (int q = 0; q < KL; ++q) rowl[q] = ArgMax{-INFINITY, 0x7fffffff};
       float m = -INFINITY, sum = 0.f;
-      const int V4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? (V >> 2) : 0;      // 16-byte loads when aligned
+      if (FAST == 2) {
+        constexpr int PW = 2 + 2 * KL;
+        const int row = g * k + j, rtile = row / 128;
+        const int run_lo = (int)(((int64_t)rtile * vp.tiles_r * vp.grid) / vp.num_tiles);
+        const int run_hi = (int)((((int64_t)(rtile + 1) * vp.tiles_r - 1) * vp.grid) / vp.num_tiles);
+        const int nslot = run_hi - run_lo + 1;
+        const float* pr = logits + ((int64_t)row * vp.slots) * PW;
+        for (int tt = tid; tt < nslot; tt += NT) {
+          const float* q = pr + (int64_t)tt * PW;
+          const float mt = q[0], st = q[1];
+          const float mn = fmaxf(m, mt);
+          if (mn > -INFINITY) {
+            sum = sum * __expf(m - mn) + st * __expf(mt - mn);
+            m = mn;
+          }
+#pragma unroll
+          for (int e = 0; e < KL; ++e) {
+            const int idx = __float_as_int(q[2 + KL + e]);
+            if (idx != 0x7fffffff) list_insert<KL>(rowl, ArgMax{q[2 + e], idx});
+          }
+        }
+      }
+      const int V4 = (FAST == 2) ? 0 : ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? (V >> 2) : 0;   // 16-byte loads when aligned
       for (int i4 = tid; i4 < V4; i4 += NT) {
         const float4 q4 = *reinterpret_cast<const float4*>(x + 4 * i4);
         const float xs[4] = {q4.x, q4.y, q4.z, q4.w};
@@ -144,7 +170,7 @@ beam_select_kernel(const float* __restrict__ logits, int V, int k, int t, int32_
 #pragma unroll
         for (int e = 0; e < 4; ++e) list_insert<KL>(rowl, ArgMax{xs[e], 4 * i4 + e});
       }
-      for (int i = 4 * V4 + tid; i < V; i += NT) {
+      for (int i = 4 * V4 + tid; i < (FAST == 2 ? 0 : V); i += NT) {
         const float xv = x[i];
         const float mn = fmaxf(m, xv);
         sum = sum * __expf(m - mn) + __expf(xv - mn);
@@ -157,7 +183,7 @@ beam_select_kernel(const float* __restrict__ logits, int V, int k, int t, int32_
       mb = red_v[0];
       for (int w = 1; w < NT / 32; ++w) mb = fmaxf(mb, red_v[w]);
       __syncthreads();
-      float sb = warp_sum(sum * __expf(m - mb));          // threads without elements: 0 * exp(-inf) = 0
+      float sb = warp_sum(m > -INFINITY ? sum * __expf(m - mb) : 0.f);   // threads without elements contribute 0
       if (lane == 0) red_v[warp] = sb;
       __syncthreads();
       sb = 0.f;
@@ -371,15 +397,18 @@ int beam_select(const float* logits, int V, int G, int k, int t, int32_t end_id,
                 float* score_out, int32_t* prev_word, int32_t* src_row, int32_t* live, int32_t* krem,
                 int32_t* has_done, float* best_score, int32_t* best_t, int32_t* best_parent,
                 int32_t* bp_parent, int32_t* bp_word, int32_t* tr_parent, int32_t* tr_word,
-                float* tr_score, int n_steps, cudaStream_t st, int fast) {
+                float* tr_score, int n_steps, cudaStream_t st, int fast, const VocabTopkPlan* part) {
   CAPDEC_REQUIRE(k >= 1 && k <= KMAX, CAPDEC_ERR_BAD_SHAPE, "beam size must be 1..%d (got %d)", KMAX, k);
+  VocabTopkPlan vp{0, 0, 0, 0};
+  if (part) vp = *part;
 #define BS_LAUNCH(KL_, FAST_)                                                                              \
-  beam_select_kernel<KL_, FAST_><<<G, NT, 0, st>>>(logits, V, k, t, end_id, score_in, score_out, prev_word,   \
+  beam_select_kernel<KL_, FAST_><<<G, NT, 0, st>>>(logits, V, vp, k, t, end_id, score_in, score_out, prev_word,   \
                                                    src_row, live, krem, has_done, best_score, best_t,         \
                                                    best_parent, bp_parent, bp_word, tr_parent, tr_word,       \
                                                    tr_score, n_steps, G)
-  if (k <= 4) { if (fast) BS_LAUNCH(4, true); else BS_LAUNCH(4, false); }
-  else { if (fast) BS_LAUNCH(KMAX, true); else BS_LAUNCH(KMAX, false); }
+  if (part) { if (k <= 4) BS_LAUNCH(4, 2); else BS_LAUNCH(KMAX, 2); }
+  else if (k <= 4) { if (fast) BS_LAUNCH(4, 1); else BS_LAUNCH(4, 0); }
+  else { if (fast) BS_LAUNCH(KMAX, 1); else BS_LAUNCH(KMAX, 0); }
 #undef BS_LAUNCH
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;

@@ -233,6 +233,10 @@ enum GemmEpi {
                    //   (cell_bwd) -> dpre_t (ft), dc updated in place; rows >= rows take acc = 0
 };
 
+// schedule of the fused vocabulary kernel (gemm_tc.cu), recomputed by the selection kernel (beam.cu)
+struct VocabTopkPlan { int tiles_r, num_tiles, grid, slots; };
+VocabTopkPlan vocab_topk_plan(int rows, int V);
+
 struct EpiArgs {
   // G1 / P3 / WR
   const float* fa = nullptr;        // G1: q   P3: v   WR: v
@@ -254,6 +258,7 @@ struct EpiArgs {
   const float* c_new_r = nullptr;   // DHCELL: c_t (read)
   int rows_epi = 0;                 // DHCELL: rows the fused pointwise covers (>= rows)
   int lstm_order = 0;
+  int topk_slots = 0;               // fused vocabulary kernel: partial slots per batch row
 };
 
 struct GemmArgs {

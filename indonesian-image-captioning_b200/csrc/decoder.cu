@@ -932,8 +932,8 @@ struct BeamPlan {
   Plan w;                 // weight offsets only (built for B = 1, T = 1)
   int R;
   struct Off {
-    size_t enc_f, enc_cm, att1, mean, meanF, meanX, tagsG, tagsX, v, q, H, C, Hn, Cn, Xe, U, g1, z, m, pre,
-        logits, alpha_hist, att_scr, prev_word, scoreA, scoreB, src_row, live, krem, has_done, best_score,
+    size_t enc_f, enc_cm, att1, mean, meanF, meanX, tagsG, tagsX, v, q, H, C, Hn, Cn, Xe, xz, U, g1, z, m, pre,
+        logits, vpart, alpha_hist, att_scr, prev_word, scoreA, scoreB, src_row, live, krem, has_done, best_score,
         best_t, best_parent, bp_parent, bp_word, total;
   } o;
 };
@@ -973,11 +973,13 @@ int make_beam_plan(const CapdecDims& d_in, int G, int k, int n_steps, bool want_
   o.U = take((size_t)R * NQ * 4);
   o.g1 = take((size_t)R * NG1 * 4);
   if (p.att) o.z = take((size_t)R * E * f);
+  if (p.att) o.xz = take((size_t)R * (d.M + E) * f);     // [emb_t | z] rows: ONE K = M+E input-side GEMM per step
   if (p.scn) {
     o.m = take((size_t)4 * R * 2 * F * f);
     o.pre = take((size_t)R * 4 * D * 4);
   }
   o.logits = take((size_t)R * V * 4);
+  if (d.precision == CAPDEC_BF16) o.vpart = take(vocab_topk_part_floats((int)R, (int)V, k <= 4 ? 4 : 8) * 4);
   if (p.att) o.att_scr = take(attention_scratch_floats(d.precision, (int)R, (int)P, (int)E) * 4);
   if (p.att) o.alpha_hist = take((size_t)(want_alpha ? n_steps : 1) * R * P * 4);
   o.prev_word = take((size_t)R * 4);
@@ -1073,21 +1075,39 @@ int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, co
   // bf16 mode: single-pass selection (CAPDEC_BEAM_EXACT=1 keeps the three-pass arithmetic of the parity mode)
   const char* exact_env = getenv("CAPDEC_BEAM_EXACT");
   const bool fast_select = pr == CAPDEC_BF16 && !(exact_env && exact_env[0] == '1');
+  // ... and the vocabulary projection, the log-softmax statistics and the per-tile top-k candidates are ONE kernel
+  // (gemm_tc_vocab_topk): the (rows x V) logits are never written (CAPDEC_BEAM_FUSED=0: separate GEMM + selection)
+  const char* fused_env = getenv("CAPDEC_BEAM_FUSED");
+  const bool fused_vocab = fast_select && !(fused_env && fused_env[0] == '0');
+  const int kl = k <= 4 ? 4 : 8;
+  const VocabTopkPlan vplan = vocab_topk_plan(R, V);
   // ---- the search loop (attention_scn.py:216-290) ----
+  // attention decoders: the embedding and the gated context are written side by side ([emb_t | z], the cell's
+  // input as the reference concatenates it, attention_scn.py:232), so the input-side product is ONE GEMM over
+  // K = M + E instead of a K = M GEMM plus a read-modify-write K = E GEMM over the fp32 U
+  const bool cat_xz = p.att && (M * (int)p.fsz) % 16 == 0;
+  const int64_t ldXZ = (int64_t)M + E;
   for (int t = 0; t < n_steps; ++t) {
     float* g1 = c.at<float>(o.g1);
     float* U = c.at<float>(o.U);
-    CAPDEC_TRY(beam_embed(pr, w.emb, prev_word, c.at(o.Xe), p.ldM, R, M, V, st));
-    CAPDEC_TRY(G_(c, c.at(o.Xe), p.ldM, c.at(p.o.Wp_xq), p.ldX, U, NQ, 0, nullptr, nullptr, 0, R, NQ, M));
+    if (cat_xz) {
+      CAPDEC_TRY(beam_embed(pr, w.emb, prev_word, c.at(o.xz), ldXZ, R, M, V, st));
+    } else {
+      CAPDEC_TRY(beam_embed(pr, w.emb, prev_word, c.at(o.Xe), p.ldM, R, M, V, st));
+      CAPDEC_TRY(G_(c, c.at(o.Xe), p.ldM, c.at(p.o.Wp_xq), p.ldX, U, NQ, 0, nullptr, nullptr, 0, R, NQ, M));
+    }
     CAPDEC_TRY(G_(c, c.at(o.H), p.ldD, c.at(p.o.Wp_cat1), p.ldD, g1, NG1, 0, c.at<float>(p.o.b_cat1),
                   nullptr, 0, R, NG1, D));
     const float* pcol = g1 + (p.att ? A + E : 0);
     if (p.att) {
       float* alpha_t = c.at<float>(o.alpha_hist) + (want_alpha ? (int64_t)t * R * P : 0);
       CAPDEC_TRY(attention_fwd(pr, c.at(o.att1), c.at(o.enc_f), g1, NG1, A, w.full_att_w, w.full_att_b,
-                               alpha_t, P, c.at(o.z), E, nullptr, R, k, P, E, A, c.at<float>(o.att_scr), st,
-                               have_cm ? c.at(o.enc_cm) : nullptr));
-      CAPDEC_TRY(G_(c, c.at(o.z), E, c.ft(p.o.Wp_xq, M), p.ldX, U, NQ, 0, nullptr, U, NQ, R, NQ, E));
+                               alpha_t, P, cat_xz ? c.ft(o.xz, M) : c.at(o.z), cat_xz ? ldXZ : (int64_t)E, nullptr, R,
+                               k, P, E, A, c.at<float>(o.att_scr), st, have_cm ? c.at(o.enc_cm) : nullptr));
+      if (cat_xz)
+        CAPDEC_TRY(G_(c, c.at(o.xz), ldXZ, c.at(p.o.Wp_xq), p.ldX, U, NQ, 0, nullptr, nullptr, 0, R, NQ, M + E));
+      else
+        CAPDEC_TRY(G_(c, c.at(o.z), E, c.ft(p.o.Wp_xq, M), p.ldX, U, NQ, 0, nullptr, U, NQ, R, NQ, E));
     }
     if (p.scn) {
       CAPDEC_TRY(scn_form_m(pr, U, NQ, pcol, NG1, c.at<float>(o.v), c.at<float>(o.q), c.at(o.m), R, R, F, st));
@@ -1100,11 +1120,19 @@ int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, co
                           nullptr, c.at(o.Hn), p.ldD, nullptr, 0.f, nullptr, 0, 1, R, D, st));
     }
     // scores = log_softmax(fc(h)) (:235-236; eval mode: dropout is the identity)
-    CAPDEC_TRY(G_(c, c.at(o.Hn), p.ldD, c.at(p.o.Wp_fc), p.ldD, c.at(o.logits), V, 0, w.fc_b, nullptr, 0,
-                  R, V, D));
-    CAPDEC_TRY(beam_select(c.at<float>(o.logits), V, G, k, t, end_id, score_in, score_out, prev_word,
-                           src_row, live, krem, has_done, best_score, best_t, best_parent, bpp, bpw,
-                           trace_parent, trace_word, trace_score, n_steps, st, fast_select ? 1 : 0));
+    if (fused_vocab) {
+      CAPDEC_TRY(gemm_tc_vocab_topk(c.at(o.Hn), p.ldD, R, c.at(p.o.Wp_fc), p.ldD, V, D, w.fc_b, c.at<float>(o.vpart),
+                                    kl, st));
+      CAPDEC_TRY(beam_select(c.at<float>(o.vpart), V, G, k, t, end_id, score_in, score_out, prev_word,
+                             src_row, live, krem, has_done, best_score, best_t, best_parent, bpp, bpw,
+                             trace_parent, trace_word, trace_score, n_steps, st, 1, &vplan));
+    } else {
+      CAPDEC_TRY(G_(c, c.at(o.Hn), p.ldD, c.at(p.o.Wp_fc), p.ldD, c.at(o.logits), V, 0, w.fc_b, nullptr, 0,
+                    R, V, D));
+      CAPDEC_TRY(beam_select(c.at<float>(o.logits), V, G, k, t, end_id, score_in, score_out, prev_word,
+                             src_row, live, krem, has_done, best_score, best_t, best_parent, bpp, bpw,
+                             trace_parent, trace_word, trace_score, n_steps, st, fast_select ? 1 : 0));
+    }
     CAPDEC_TRY(beam_gather_state(pr, c.at(o.Hn), c.at<float>(o.Cn), c.at(o.H), c.at<float>(o.C), src_row,
                                  live, R, k, D, p.ldD, st));
     float* tmp = score_in; score_in = score_out; score_out = tmp;

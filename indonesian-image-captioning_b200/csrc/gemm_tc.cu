@@ -493,12 +493,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 // columns), so the epilogue of tile i (TMEM -> registers -> global) overlaps the main loop of tile
 // i + 1 and the per-tile prologue (barrier init, TMEM allocation, first-load latency) is paid once.
 // ---------------------------------------------------------------------------------------
+// KL mode: CTA b owns the CONSECUTIVE tiles [ceil(b T / G), ceil((b+1) T / G)) of the (row tile, vocabulary tile)
+// sequence with the vocabulary tile running fastest, so that the epilogue's running statistics of a batch row stay in
+// registers across the vocabulary tiles of a run; plain mode: round robin.
+__device__ __forceinline__ int ps_run_begin(int b, int num_tiles, int grid) {
+  return (int)(((int64_t)b * num_tiles + grid - 1) / grid);
+}
 constexpr int PS_STAGES = 6;
 constexpr int PS_BNR = 128;
 constexpr int PS_STAGE_BYTES = (BM + PS_BNR) * BK * 2;
 constexpr int PS_SMEM_BYTES = PS_STAGES * PS_STAGE_BYTES + 1024 + 256;
 
-template <int TN>
+//
+// KL > 0: the fused vocabulary projection + log-softmax statistics + top-k candidates of beam search
+// (reference: `scores = F.log_softmax(self.fc(h), dim=1)` + `topk`, attention_scn.py:235-253).  The operand roles
+// are EXCHANGED by the caller: the M side ("W", TMEM lanes) holds the batch rows h, the N side ("X", TMEM columns)
+// the vocabulary rows of fc.weight, so that one epilogue thread owns ONE batch row and walks over the tile's 128
+// vocabulary entries in its registers: running maximum, sum of exponentials and the KL largest logits (value,
+// vocabulary index) need no cross-thread traffic.  Per (batch row, vocabulary tile) it writes 2 + 2 KL floats
+// instead of 128 logits: the (rows x V) fp32 logits tensor never exists; beam_select_kernel<.., 2> merges the tiles.
+template <int TN, int KL = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
                        const __grid_constant__ KArgs a, int tiles_n, int tiles_r, int num_tiles) {
@@ -536,14 +550,17 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
   pdl_wait();
   const int nkb = (a.K + BK - 1) / BK;
   const int tiles_nr = tiles_n * tiles_r;
+  const int t_first = KL > 0 ? ps_run_begin(blockIdx.x, num_tiles, gridDim.x) : (int)blockIdx.x;
+  const int t_end = KL > 0 ? ps_run_begin(blockIdx.x + 1, num_tiles, gridDim.x) : num_tiles;
+  const int t_step = KL > 0 ? 1 : (int)gridDim.x;
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------- TMA producer -------------------------
       uint32_t u = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = t_first; t < t_end; t += t_step) {
         const int z = t / tiles_nr, rem = t - z * tiles_nr;
-        const int rt = rem / tiles_n, nt = rem - rt * tiles_n;
+        const int rt = KL > 0 ? rem % tiles_r : rem / tiles_n, nt = KL > 0 ? rem / tiles_r : rem - rt * tiles_n;
         const int n0 = nt * BM, r0 = rt * PS_BNR;
         for (int kb = 0; kb < nkb; ++kb, ++u) {
           const int s = u % PS_STAGES;
@@ -576,7 +593,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       constexpr int ASTEP = (TN & 1) ? 128 : 2, BSTEP = (TN & 2) ? 128 : 2;
       uint32_t u = 0;
       int i = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+      for (int t = t_first; t < t_end; t += t_step, ++i) {
         const int buf = i & 1;
         mbar_wait(smem_u32(&bars[2 * PS_STAGES + 2 + buf]), (uint32_t)((i >> 1) & 1) ^ 1u);   // epilogue drained it
         tc_fence_after();
@@ -600,26 +617,91 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     // ------------------------- epilogue warps 2..5 -------------------------
     const int q = warp & 3;
     int i = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+    // KL mode: running statistics of this thread's batch row over the vocabulary tiles of the CTA's run
+    constexpr int KQ = KL > 0 ? KL : 1;
+    float m = -INFINITY, ssum = 0.f;
+    float lv[KQ];
+    int li[KQ];
+#pragma unroll
+    for (int e = 0; e < KQ; ++e) { lv[e] = -INFINITY; li[e] = 0x7fffffff; }
+    for (int t = t_first; t < t_end; t += t_step, ++i) {
       const int buf = i & 1;
       const int z = t / tiles_nr, rem = t - z * tiles_nr;
-      const int rt = rem / tiles_n, nt = rem - rt * tiles_n;
+      const int rt = KL > 0 ? rem % tiles_r : rem / tiles_n, nt = KL > 0 ? rem / tiles_r : rem - rt * tiles_n;
       const int n = nt * BM + q * 32 + lane, r0 = rt * PS_BNR;
       const bool n_ok = n < a.N;
       float bv = 0.f;
-      if (a.bias != nullptr && n_ok) bv = a.bias[(int64_t)z * a.sBias + n];
+      if (KL == 0 && a.bias != nullptr && n_ok) bv = a.bias[(int64_t)z * a.sBias + n];
       float* outf = (float*)a.out + (int64_t)z * a.sO;
       bf16* outh = (bf16*)a.out + (int64_t)z * a.sO;
       const float* add = a.addm ? a.addm + (int64_t)z * a.sAdd : nullptr;
       mbar_wait(smem_u32(&bars[2 * PS_STAGES + buf]), (uint32_t)((i >> 1) & 1));
       tc_fence_after();
+      if (KL > 0) {
+        // thread = batch row n, TMEM columns = vocabulary entries r0 .. r0 + 127 of this tile
 #pragma unroll 1
-      for (int c0 = 0; c0 < PS_BNR; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * PS_BNR + c0), v);
-        if (n_ok) {
-          if (a.out_ft) store_chunk<true>(outh + n, a.ldo, r0 + c0, a.rows, bv, add ? add + n : nullptr, a.ldadd, v);
-          else store_chunk<false>(outf + n, a.ldo, r0 + c0, a.rows, bv, add ? add + n : nullptr, a.ldadd, v);
+        for (int c0 = 0; c0 < PS_BNR; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * PS_BNR + c0), v);
+          const int vb = r0 + c0;
+          if (vb < a.rows) {
+            float x[32];
+            if (vb + 32 <= a.rows) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __ldg(a.bias + vb + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = (vb + j < a.rows) ? __uint_as_float(v[j]) + __ldg(a.bias + vb + j) : -INFINITY;
+            }
+            float c4[4] = {x[0], x[1], x[2], x[3]};
+#pragma unroll
+            for (int j = 4; j < 32; ++j) c4[j & 3] = fmaxf(c4[j & 3], x[j]);
+            const float cm = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
+            const float mn = fmaxf(m, cm);
+            float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a4[j & 3] += __expf(x[j] - mn);
+            ssum = ssum * __expf(m - mn) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
+            m = mn;
+            if (cm > lv[KQ - 1]) {               // rare once the run has seen a few hundred entries
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (x[j] > lv[KQ - 1]) {         // ascending vocabulary order: an equal value never displaces an earlier one
+                  lv[KQ - 1] = x[j]; li[KQ - 1] = vb + j;
+#pragma unroll
+                  for (int e = KQ - 1; e > 0; --e) {
+                    if (lv[e] > lv[e - 1]) {
+                      const float tv = lv[e]; lv[e] = lv[e - 1]; lv[e - 1] = tv;
+                      const int ti = li[e]; li[e] = li[e - 1]; li[e - 1] = ti;
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+        // the run leaves this row tile (or ends): flush the row's statistics into slot (run - first run of the row tile)
+        if (t + 1 == t_end || (t + 1) / tiles_r != nt) {
+          if (n_ok) {
+            const int run_lo = (int)(((int64_t)nt * tiles_r * gridDim.x) / num_tiles);
+            float* po = (float*)a.out + ((int64_t)n * a.e.topk_slots + ((int)blockIdx.x - run_lo)) * (2 + 2 * KQ);
+            po[0] = m; po[1] = ssum;
+#pragma unroll
+            for (int e = 0; e < KQ; ++e) { po[2 + e] = lv[e]; po[2 + KQ + e] = __int_as_float(li[e]); }
+          }
+          m = -INFINITY; ssum = 0.f;
+#pragma unroll
+          for (int e = 0; e < KQ; ++e) { lv[e] = -INFINITY; li[e] = 0x7fffffff; }
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < PS_BNR; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * PS_BNR + c0), v);
+          if (n_ok) {
+            if (a.out_ft) store_chunk<true>(outh + n, a.ldo, r0 + c0, a.rows, bv, add ? add + n : nullptr, a.ldadd, v);
+            else store_chunk<false>(outf + n, a.ldo, r0 + c0, a.rows, bv, add ? add + n : nullptr, a.ldadd, v);
+          }
         }
       }
       tc_fence_before();
@@ -765,9 +847,9 @@ int launch(const GemmArgs& a, cudaStream_t st) {
 
 int g_sm_count = 0;
 
-template <int TN>
+template <int TN, int KL = 0>
 int launch_persist(const GemmArgs& a, cudaStream_t st) {
-  auto kernel = gemm_tc_persist_kernel<TN>;
+  auto kernel = gemm_tc_persist_kernel<TN, KL>;
   static std::once_flag once;
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(once, [&] {
@@ -794,6 +876,7 @@ int launch_persist(const GemmArgs& a, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(num_tiles < g_sm_count ? num_tiles : g_sm_count, 1, 1);
+  if (KL > 0) cfg.gridDim = dim3(vocab_topk_plan(a.N, a.rows).grid, 1, 1);   // the schedule beam_select recomputes
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = PS_SMEM_BYTES;
   cfg.stream = st;
@@ -886,6 +969,37 @@ int gemm_tc(const GemmArgs& a, cudaStream_t st) {
   }
   set_error("gemm_tc: bad epilogue %d", a.epi);
   return CAPDEC_ERR_BAD_ARG;
+}
+
+// schedule of the fused vocabulary kernel: grid, tiles and partial slots per batch row (a row tile's vocabulary
+// tiles are spread over at most `slots` consecutive CTA runs)
+VocabTopkPlan vocab_topk_plan(int rows, int V) {
+  VocabTopkPlan p;
+  p.tiles_r = ceil_div(V, PS_BNR);
+  p.num_tiles = ceil_div(rows, BM) * p.tiles_r;
+  p.grid = p.num_tiles < 148 ? p.num_tiles : 148;
+  p.slots = (int)(((int64_t)p.tiles_r * p.grid + p.num_tiles - 1) / p.num_tiles) + 1;
+  return p;
+}
+size_t vocab_topk_part_floats(int rows, int V, int kl) {
+  return (size_t)rows * (size_t)vocab_topk_plan(rows, V).slots * (size_t)(2 + 2 * kl);
+}
+
+// Fused vocabulary projection + log-softmax statistics + top-kl candidates (gemm_tc_persist_kernel<0, KL>):
+// part[row][tile][2 + 2 kl] = {max, sum exp(x - max), kl largest logits, their vocabulary indices} per 128-entry
+// vocabulary tile.  H [rows][K] and Wfc [V][K] are bf16, K contiguous.
+int gemm_tc_vocab_topk(const void* H, int64_t ldh, int rows, const void* Wfc, int64_t ldw, int V, int K,
+                       const float* bias, float* part, int kl, cudaStream_t st) {
+  if (rows <= 0 || V <= 0) return CAPDEC_OK;
+  CAPDEC_REQUIRE(H && Wfc && part && K > 0 && (kl == 4 || kl == 8), CAPDEC_ERR_BAD_ARG, "gemm_tc_vocab_topk: bad argument");
+  CAPDEC_TRY(gemm_tc_init());
+  CAPDEC_REQUIRE(bias != nullptr, CAPDEC_ERR_BAD_ARG, "gemm_tc_vocab_topk: bias is NULL");
+  GemmArgs a;
+  a.W = H; a.ldw = ldh; a.N = rows;          // M side: batch rows
+  a.X = Wfc; a.ldx = ldw; a.rows = V;        // N side: vocabulary entries
+  a.K = K; a.out = part; a.bias = bias;
+  a.e.topk_slots = vocab_topk_plan(rows, V).slots;
+  return kl == 4 ? launch_persist<0, 4>(a, st) : launch_persist<0, 8>(a, st);
 }
 
 }  // namespace capdec

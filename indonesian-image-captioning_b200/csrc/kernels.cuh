@@ -156,7 +156,12 @@ int beam_select(const float* logits, int V, int G, int k, int t, int32_t end_id,
                 float* score_out, int32_t* prev_word, int32_t* src_row, int32_t* live, int32_t* krem,
                 int32_t* has_done, float* best_score, int32_t* best_t, int32_t* best_parent,
                 int32_t* bp_parent, int32_t* bp_word, int32_t* tr_parent, int32_t* tr_word,
-                float* tr_score, int n_steps, cudaStream_t st, int fast = 0);   // fast: single-pass (bf16 mode)
+                float* tr_score, int n_steps, cudaStream_t st, int fast = 0,     // fast: single-pass (bf16 mode)
+                const VocabTopkPlan* part = nullptr);   // non-null: `logits` is the partial buffer of gemm_tc_vocab_topk
+// fused vocabulary projection + log-softmax statistics + top-kl candidates per 128-entry vocabulary tile (gemm_tc.cu)
+size_t vocab_topk_part_floats(int rows, int V, int kl);
+int gemm_tc_vocab_topk(const void* H, int64_t ldh, int rows, const void* Wfc, int64_t ldw, int V, int K,
+                       const float* bias, float* part, int kl, cudaStream_t st);
 int beam_finalize(int G, int k, int n_steps, int P, int32_t start_id, int32_t end_id, const float* score,
                   const int32_t* live, const int32_t* has_done, const float* best_score,
                   const int32_t* best_t, const int32_t* best_parent, const int32_t* bp_parent,
