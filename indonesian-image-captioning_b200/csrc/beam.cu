@@ -143,7 +143,7 @@ beam_select_kernel(const float* __restrict__ logits, int V, VocabTopkPlan vp, in
         const int row = g * k + j, rtile = row / 128;
         const int run_lo = (int)(((int64_t)rtile * vp.tiles_r * vp.grid) / vp.num_tiles);
         const int run_hi = (int)((((int64_t)(rtile + 1) * vp.tiles_r - 1) * vp.grid) / vp.num_tiles);
-        const int nslot = run_hi - run_lo + 1;
+        const int nslot = 2 * (run_hi - run_lo + 1);          // two column halves per run
         const float* pr = logits + ((int64_t)row * vp.slots) * PW;
         for (int tt = tid; tt < nslot; tt += NT) {
           const float* q = pr + (int64_t)tt * PW;

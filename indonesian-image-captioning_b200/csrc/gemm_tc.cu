@@ -499,6 +499,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 __device__ __forceinline__ int ps_run_begin(int b, int num_tiles, int grid) {
   return (int)(((int64_t)b * num_tiles + grid - 1) / grid);
 }
+constexpr int PS_THREADS = 320;     // TMA warp, MMA warp, EIGHT epilogue warps: two per TMEM lane quarter, 64 columns each
 constexpr int PS_STAGES = 6;
 constexpr int PS_BNR = 128;
 constexpr int PS_STAGE_BYTES = (BM + PS_BNR) * BK * 2;
@@ -513,7 +514,7 @@ constexpr int PS_SMEM_BYTES = PS_STAGES * PS_STAGE_BYTES + 1024 + 256;
 // vocabulary index) need no cross-thread traffic.  Per (batch row, vocabulary tile) it writes 2 + 2 KL floats
 // instead of 128 logits: the (rows x V) fp32 logits tensor never exists; beam_select_kernel<.., 2> merges the tiles.
 template <int TN, int KL = 0>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(PS_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
                        const __grid_constant__ KArgs a, int tiles_n, int tiles_r, int num_tiles) {
   constexpr int W_BYTES = BM * BK * 2;
@@ -533,7 +534,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bars[2 * PS_STAGES + b]), 1);          // tmem_full: one tcgen05.commit
-      mbar_init(smem_u32(&bars[2 * PS_STAGES + 2 + b]), 4);      // tmem_empty: the four epilogue warps
+      mbar_init(smem_u32(&bars[2 * PS_STAGES + 2 + b]), 8);      // tmem_empty: the eight epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -614,8 +615,12 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       }
     }
   } else {
-    // ------------------------- epilogue warps 2..5 -------------------------
+    // ------------------------- epilogue warps 2..9 -------------------------
+    // warp w may touch TMEM lanes 32 (w & 3) ..; warps w and w + 4 share a lane quarter and take 64 columns each
+    // (one warp per scheduler and quarter left the epilogue latency-exposed: it, not the main loop, set the pace)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int cbeg = half * (PS_BNR / 2), cend = cbeg + PS_BNR / 2;
     int i = 0;
     // KL mode: running statistics of this thread's batch row over the vocabulary tiles of the CTA's run
     constexpr int KQ = KL > 0 ? KL : 1;
@@ -640,7 +645,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
       if (KL > 0) {
         // thread = batch row n, TMEM columns = vocabulary entries r0 .. r0 + 127 of this tile
 #pragma unroll 1
-        for (int c0 = 0; c0 < PS_BNR; c0 += 32) {
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * PS_BNR + c0), v);
           const int vb = r0 + c0;
@@ -663,19 +668,28 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
             for (int j = 0; j < 32; ++j) a4[j & 3] += __expf(x[j] - mn);
             ssum = ssum * __expf(m - mn) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
             m = mn;
-            if (cm > lv[KQ - 1]) {               // rare once the run has seen a few hundred entries
+            // candidates: pop the chunk's maxima while they beat the list tail (usually zero or one round once the
+            // run has seen a few hundred entries); the FIRST maximum wins a tie, and an equal value never displaces
+            // an earlier (smaller-index) entry of the list
+            float top = cm;
+#pragma unroll 1
+            while (top > lv[KQ - 1]) {
+              int jm = 31;
+#pragma unroll
+              for (int j = 30; j >= 0; --j) jm = (x[j] == top) ? j : jm;
+              lv[KQ - 1] = top; li[KQ - 1] = vb + jm;
+#pragma unroll
+              for (int e = KQ - 1; e > 0; --e) {
+                if (lv[e] > lv[e - 1]) {
+                  const float tv = lv[e]; lv[e] = lv[e - 1]; lv[e - 1] = tv;
+                  const int ti = li[e]; li[e] = li[e - 1]; li[e - 1] = ti;
+                }
+              }
+              top = -INFINITY;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                if (x[j] > lv[KQ - 1]) {         // ascending vocabulary order: an equal value never displaces an earlier one
-                  lv[KQ - 1] = x[j]; li[KQ - 1] = vb + j;
-#pragma unroll
-                  for (int e = KQ - 1; e > 0; --e) {
-                    if (lv[e] > lv[e - 1]) {
-                      const float tv = lv[e]; lv[e] = lv[e - 1]; lv[e - 1] = tv;
-                      const int ti = li[e]; li[e] = li[e - 1]; li[e - 1] = ti;
-                    }
-                  }
-                }
+                x[j] = (j == jm) ? -INFINITY : x[j];
+                top = fmaxf(top, x[j]);
               }
             }
           }
@@ -684,7 +698,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
         if (t + 1 == t_end || (t + 1) / tiles_r != nt) {
           if (n_ok) {
             const int run_lo = (int)(((int64_t)nt * tiles_r * gridDim.x) / num_tiles);
-            float* po = (float*)a.out + ((int64_t)n * a.e.topk_slots + ((int)blockIdx.x - run_lo)) * (2 + 2 * KQ);
+            float* po = (float*)a.out + ((int64_t)n * a.e.topk_slots + ((int)blockIdx.x - run_lo) * 2 + half) * (2 + 2 * KQ);
             po[0] = m; po[1] = ssum;
 #pragma unroll
             for (int e = 0; e < KQ; ++e) { po[2 + e] = lv[e]; po[2 + KQ + e] = __int_as_float(li[e]); }
@@ -695,7 +709,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_co
         }
       } else {
 #pragma unroll 1
-        for (int c0 = 0; c0 < PS_BNR; c0 += 32) {
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * PS_BNR + c0), v);
           if (n_ok) {
@@ -877,7 +891,7 @@ int launch_persist(const GemmArgs& a, cudaStream_t st) {
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(num_tiles < g_sm_count ? num_tiles : g_sm_count, 1, 1);
   if (KL > 0) cfg.gridDim = dim3(vocab_topk_plan(a.N, a.rows).grid, 1, 1);   // the schedule beam_select recomputes
-  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.blockDim = dim3(PS_THREADS, 1, 1);
   cfg.dynamicSmemBytes = PS_SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -978,7 +992,7 @@ VocabTopkPlan vocab_topk_plan(int rows, int V) {
   p.tiles_r = ceil_div(V, PS_BNR);
   p.num_tiles = ceil_div(rows, BM) * p.tiles_r;
   p.grid = p.num_tiles < 148 ? p.num_tiles : 148;
-  p.slots = (int)(((int64_t)p.tiles_r * p.grid + p.num_tiles - 1) / p.num_tiles) + 1;
+  p.slots = 2 * ((int)(((int64_t)p.tiles_r * p.grid + p.num_tiles - 1) / p.num_tiles) + 1);   // two column halves per run
   return p;
 }
 size_t vocab_topk_part_floats(int rows, int V, int kl) {
