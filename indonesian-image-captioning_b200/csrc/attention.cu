@@ -377,7 +377,7 @@ constexpr int WS_STAGE_BYTES = WS_PX * WS_CH * 2;
 
 template <int RPM>
 __global__ void __launch_bounds__(NT)
-attn_wsum_stream_kernel(WsumArgs a) {
+attn_wsum_stream_kernel(WsumArgs a, int maps) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* stg = smem_raw;
   float* al = reinterpret_cast<float*>(stg + WS_STAGES * WS_STAGE_BYTES);     // [RPM][Ppad]
@@ -387,11 +387,14 @@ attn_wsum_stream_kernel(WsumArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 3 * 64 * 8 + 32);
   pdl_launch_dependents();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chunk = blockIdx.x, map = blockIdx.y;
-  const int row0 = map * RPM;
   const int chunks = E / WS_CH;
-  const bf16* src = (const bf16*)a.enc + ((int64_t)map * chunks + chunk) * P * WS_CH;
   const int nfill = (P + WS_PX - 1) / WS_PX;
+  // PERSISTENT: this CTA walks over the items b, b + grid, ... (item = (map, chunk), chunks of a map adjacent) and
+  // the ring keeps running ACROSS items: while the softmax prologue / the reduction epilogue of an item execute, the
+  // next item's pixels are already in flight (a one-item CTA left its share of the bandwidth idle for ~25 % of its life)
+  const int items = maps * chunks;
+  const int my_items = ((int)blockIdx.x < items) ? (items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total_fills = my_items * nfill;
   uint32_t full[WS_STAGES];
 #pragma unroll
   for (int s = 0; s < WS_STAGES; ++s) full[s] = smem_u32(&bars[s]);
@@ -401,9 +404,12 @@ attn_wsum_stream_kernel(WsumArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto fill = [&](int fi) {
-    if (tid == 0) {
-      const int s = fi % WS_STAGES;
+  auto fill = [&](int gf) {          // gf = fill index over all of this CTA's items
+    if (tid == 0 && gf < total_fills) {
+      const int k = gf / nfill, fi = gf - k * nfill;
+      const int it = (int)blockIdx.x + k * (int)gridDim.x;
+      const bf16* src = (const bf16*)a.enc + (int64_t)it * P * WS_CH;       // item it = (map, chunk) slab of enc_cm
+      const int s = gf % WS_STAGES;
       const uint32_t bytes = (uint32_t)min(WS_PX, P - fi * WS_PX) * WS_CH * 2;
       mbar_expect_tx(full[s], bytes);
       bulk_g2s(smem_u32(stg) + s * WS_STAGE_BYTES, src + (int64_t)fi * WS_PX * WS_CH, bytes, full[s]);
@@ -411,100 +417,109 @@ attn_wsum_stream_kernel(WsumArgs a) {
   };
   // the features do not depend on the previous kernel: the ring is filled before the PDL wait
 #pragma unroll
-  for (int fi = 0; fi < WS_STAGES; ++fi)
-    if (fi < nfill) fill(fi);
+  for (int gf = 0; gf < WS_STAGES; ++gf) fill(gf);
   pdl_wait();
-  // ---- softmax over the P scores of every row of this CTA: one WARP per row (shuffle reductions only) ----
-  for (int j = warp; j < RPM; j += NW) {
-    const float* sc = a.scores + (int64_t)(row0 + j) * Ppad;
-    float* alj = al + j * Ppad;
-    float m = -INFINITY;
-    for (int p = lane; p < P; p += 32) { const float sv = sc[p]; alj[p] = sv; m = fmaxf(m, sv); }
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int p = lane; p < P; p += 32) { const float e = expf(alj[p] - m); alj[p] = e; sum += e; }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    for (int p = lane; p < P; p += 32) {
-      const float v = alj[p] * inv;
-      alj[p] = v;
-      if (chunk == 0 && a.alpha_out) a.alpha_out[(int64_t)(row0 + j) * a.alpha_stride + p] = v;
-    }
-  }
-  __syncthreads();
-  // ---- weighted sums: thread = (pixel group of 4, 16-byte column of 64) ----
-  const int grp = tid >> 6, col = tid & 63;
-  float acc[RPM][8];
-#pragma unroll
-  for (int j = 0; j < RPM; ++j)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+  const int grp = tid >> 6, col = tid & 63;      // weighted sums: thread = (pixel group of 4, 16-byte column of 64)
+  int gf = 0;                                    // next fill to consume
 #pragma unroll 1
-  for (int fi = 0; fi < nfill; ++fi) {
-    const int s = fi % WS_STAGES;
-    const int px0 = fi * WS_PX, cnt = min(WS_PX, P - px0);
-    mbar_wait(full[s], (fi / WS_STAGES) & 1);
-    const uint8_t* base = stg + s * WS_STAGE_BYTES + col * 16;
+  for (int k = 0; k < my_items; ++k) {
+    const int it = (int)blockIdx.x + k * (int)gridDim.x;
+    const int map = it / chunks, chunk = it - map * chunks;
+    const int row0 = map * RPM;
+    // ---- softmax over the P scores of every row of this item: one WARP per row (shuffle reductions only) ----
+    for (int j = warp; j < RPM; j += NW) {
+      const float* sc = a.scores + (int64_t)(row0 + j) * Ppad;
+      float* alj = al + j * Ppad;
+      float m = -INFINITY;
+      for (int p = lane; p < P; p += 32) { const float sv = sc[p]; alj[p] = sv; m = fmaxf(m, sv); }
+      m = warp_max(m);
+      float sum = 0.f;
+      for (int p = lane; p < P; p += 32) { const float e = expf(alj[p] - m); alj[p] = e; sum += e; }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+      for (int p = lane; p < P; p += 32) {
+        const float v = alj[p] * inv;
+        alj[p] = v;
+        if (chunk == 0 && a.alpha_out) a.alpha_out[(int64_t)(row0 + j) * a.alpha_stride + p] = v;
+      }
+    }
+    __syncthreads();
+    float acc[RPM][8];
 #pragma unroll
-    for (int u = 0; u < WS_PX / 4; ++u) {
-      const int pl = grp + u * 4;
-      if (pl < cnt) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(base + (size_t)pl * WS_CH * 2);
-        float f[8];
-        unpack16(raw, f, bf16());
+    for (int j = 0; j < RPM; ++j)
 #pragma unroll
-        for (int j = 0; j < RPM; ++j) {
-          const float w = al[j * Ppad + px0 + pl];
+      for (int kk = 0; kk < 8; ++kk) acc[j][kk] = 0.f;
+#pragma unroll 1
+    for (int fi = 0; fi < nfill; ++fi, ++gf) {
+      const int s = gf % WS_STAGES;
+      const int px0 = fi * WS_PX, cnt = min(WS_PX, P - px0);
+      mbar_wait(full[s], (gf / WS_STAGES) & 1);
+      const uint8_t* base = stg + s * WS_STAGE_BYTES + col * 16;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(w, f[k], acc[j][k]);
+      for (int u = 0; u < WS_PX / 4; ++u) {
+        const int pl = grp + u * 4;
+        if (pl < cnt) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(base + (size_t)pl * WS_CH * 2);
+          float f[8];
+          unpack16(raw, f, bf16());
+#pragma unroll
+          for (int j = 0; j < RPM; ++j) {
+            const float w = al[j * Ppad + px0 + pl];
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) acc[j][kk] = fmaf(w, f[kk], acc[j][kk]);
+          }
         }
       }
+      if (gf + WS_STAGES < total_fills) {
+        __syncthreads();                  // every warp is done with stage s
+        fill(gf + WS_STAGES);
+      }
     }
-    if (fi + WS_STAGES < nfill) {
-      __syncthreads();                  // every warp is done with stage s
-      fill(fi + WS_STAGES);
-    }
-  }
-  // ---- cross-group reduction, gate, outputs ----
+    // ---- cross-group reduction, gate, outputs ----
+    const int e0 = chunk * WS_CH + col * 8;
 #pragma unroll 1
-  for (int j = 0; j < RPM; ++j) {
-    float accj[8];
+    for (int j = 0; j < RPM; ++j) {
+      float accj[8];
 #pragma unroll
-    for (int jj = 0; jj < RPM; ++jj)
-      if (jj == j) {
+      for (int jj = 0; jj < RPM; ++jj)
+        if (jj == j) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) accj[k] = acc[jj][k];
-      }
-    __syncthreads();
-    if (grp > 0) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) red[((grp - 1) * 64 + col) * 8 + k] = accj[k];
-    }
-    __syncthreads();
-    if (grp == 0) {
-#pragma unroll
-      for (int g = 1; g < 4; ++g)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) accj[k] += red[((g - 1) * 64 + col) * 8 + k];
+          for (int kk = 0; kk < 8; ++kk) accj[kk] = acc[jj][kk];
+        }
       const int row = row0 + j;
-      const int e0 = chunk * WS_CH + col * 8;
-      const float* g1 = a.g1 + (int64_t)row * a.ldg;
-      float zv[8];
+      // gate pre-activations requested before the reduction barriers: their latency hides behind them
+      float gpre[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float gate = 1.0f;
-        if (a.beta_col >= 0) gate = sigmoidf_(g1[a.beta_col + e0 + k]);
-        zv[k] = gate * accj[k];
+      for (int kk = 0; kk < 8; ++kk)
+        gpre[kk] = (grp == 0 && a.beta_col >= 0) ? __ldg(a.g1 + (int64_t)row * a.ldg + a.beta_col + e0 + kk) : 0.f;
+      __syncthreads();
+      if (grp > 0) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) red[((grp - 1) * 64 + col) * 8 + kk] = accj[kk];
       }
-      if (a.awe_out) {
-        float* dst = a.awe_out + (int64_t)row * E + e0;
-        *reinterpret_cast<float4*>(dst) = make_float4(accj[0], accj[1], accj[2], accj[3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(accj[4], accj[5], accj[6], accj[7]);
+      __syncthreads();
+      if (grp == 0) {
+#pragma unroll
+        for (int g = 1; g < 4; ++g)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) accj[kk] += red[((g - 1) * 64 + col) * 8 + kk];
+        float zv[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          float gate = 1.0f;
+          if (a.beta_col >= 0) gate = sigmoidf_(gpre[kk]);
+          zv[kk] = gate * accj[kk];
+        }
+        if (a.awe_out) {
+          float* dst = a.awe_out + (int64_t)row * E + e0;
+          *reinterpret_cast<float4*>(dst) = make_float4(accj[0], accj[1], accj[2], accj[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(accj[4], accj[5], accj[6], accj[7]);
+        }
+        if (a.z_out) *reinterpret_cast<uint4*>((bf16*)a.z_out + (int64_t)row * a.ldz + e0) = pack16(zv, bf16());
       }
-      if (a.z_out) *reinterpret_cast<uint4*>((bf16*)a.z_out + (int64_t)row * a.ldz + e0) = pack16(zv, bf16());
     }
+    __syncthreads();                      // `al` and `red` are rewritten by the next item
   }
-  (void)lane; (void)warp;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -836,7 +851,12 @@ int launch_wsum_stream(const WsumArgs& wa, int maps, cudaStream_t st) {
   static cudaError_t rc = cudaSuccess;
   std::call_once(once, [&] { rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); });
   CAPDEC_REQUIRE(rc == cudaSuccess && smem <= 112 * 1024, CAPDEC_ERR_CUDA, "attn_wsum_stream: smem %zu", smem);
-  return launch_attn(kernel, dim3(wa.E / WS_CH, maps, 1), NT, smem, st, wa);
+  // persistent: two CTAs per SM (smem-limited), each walking over its share of the (map, chunk) items
+  const int items = (wa.E / WS_CH) * maps;
+  const int grid = items < 2 * 148 ? items : 2 * 148;
+  CAPDEC_CUDA_OK(launch_pdl(kernel, dim3(grid, 1, 1), dim3(NT, 1, 1), smem, st, 1, wa, maps));
+  count_launch();
+  return CAPDEC_OK;
 }
 }  // namespace
 
