@@ -375,8 +375,11 @@ constexpr int WS_PX = 32;                       // pixels per stage
 constexpr int WS_CH = 512;                      // channels per item
 constexpr int WS_STAGE_BYTES = WS_PX * WS_CH * 2;
 
+// barrier over the NT consumer threads (the producer warp is not part of it)
+__device__ __forceinline__ void ws_csync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+
 template <int RPM>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT + 32, 2)
 attn_wsum_stream_kernel(WsumArgs a, int maps) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* stg = smem_raw;
@@ -395,29 +398,32 @@ attn_wsum_stream_kernel(WsumArgs a, int maps) {
   const int items = maps * chunks;
   const int my_items = ((int)blockIdx.x < items) ? (items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int total_fills = my_items * nfill;
-  uint32_t full[WS_STAGES];
-#pragma unroll
-  for (int s = 0; s < WS_STAGES; ++s) full[s] = smem_u32(&bars[s]);
+  // full[s]: the stage's bytes have landed (TMA transaction count); empty[s]: all NW consumer warps are done with it.
+  // A dedicated PRODUCER warp refills a stage as soon as it is empty: no CTA-wide barrier in the steady state (with a
+  // __syncthreads per fill the warps spent 4 issue slots of 5 stalled on that barrier, ncu).
+  const uint32_t bar0 = smem_u32(bars);          // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (WS_STAGES + s)
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < WS_STAGES; ++s) mbar_init(full[s], 1);
+    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar0 + 8 * (WS_STAGES + s), NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto fill = [&](int gf) {          // gf = fill index over all of this CTA's items
-    if (tid == 0 && gf < total_fills) {
-      const int k = gf / nfill, fi = gf - k * nfill;
-      const int it = (int)blockIdx.x + k * (int)gridDim.x;
-      const bf16* src = (const bf16*)a.enc + (int64_t)it * P * WS_CH;       // item it = (map, chunk) slab of enc_cm
-      const int s = gf % WS_STAGES;
-      const uint32_t bytes = (uint32_t)min(WS_PX, P - fi * WS_PX) * WS_CH * 2;
-      mbar_expect_tx(full[s], bytes);
-      bulk_g2s(smem_u32(stg) + s * WS_STAGE_BYTES, src + (int64_t)fi * WS_PX * WS_CH, bytes, full[s]);
+  if (warp == NW) {
+    // ---- producer: the features do not depend on the previous kernel, so it starts before the PDL wait ----
+    if (lane == 0) {
+      for (int gf = 0; gf < total_fills; ++gf) {          // gf = fill index over all of this CTA's items
+        const int k = gf / nfill, fi = gf - k * nfill;
+        const int it = (int)blockIdx.x + k * (int)gridDim.x;
+        const bf16* src = (const bf16*)a.enc + (int64_t)it * P * WS_CH;       // item it = (map, chunk) slab of enc_cm
+        const int s = gf % WS_STAGES;
+        mbar_wait(bar0 + 8 * (WS_STAGES + s), ((gf / WS_STAGES) & 1) ^ 1);
+        const uint32_t bytes = (uint32_t)min(WS_PX, P - fi * WS_PX) * WS_CH * 2;
+        mbar_expect_tx(bar0 + 8 * s, bytes);
+        bulk_g2s(smem_u32(stg) + s * WS_STAGE_BYTES, src + (int64_t)fi * WS_PX * WS_CH, bytes, bar0 + 8 * s);
+      }
     }
-  };
-  // the features do not depend on the previous kernel: the ring is filled before the PDL wait
-#pragma unroll
-  for (int gf = 0; gf < WS_STAGES; ++gf) fill(gf);
+    return;
+  }
   pdl_wait();
   const int grp = tid >> 6, col = tid & 63;      // weighted sums: thread = (pixel group of 4, 16-byte column of 64)
   int gf = 0;                                    // next fill to consume
@@ -443,7 +449,7 @@ attn_wsum_stream_kernel(WsumArgs a, int maps) {
         if (chunk == 0 && a.alpha_out) a.alpha_out[(int64_t)(row0 + j) * a.alpha_stride + p] = v;
       }
     }
-    __syncthreads();
+    ws_csync();
     float acc[RPM][8];
 #pragma unroll
     for (int j = 0; j < RPM; ++j)
@@ -453,7 +459,7 @@ attn_wsum_stream_kernel(WsumArgs a, int maps) {
     for (int fi = 0; fi < nfill; ++fi, ++gf) {
       const int s = gf % WS_STAGES;
       const int px0 = fi * WS_PX, cnt = min(WS_PX, P - px0);
-      mbar_wait(full[s], (gf / WS_STAGES) & 1);
+      mbar_wait(bar0 + 8 * s, (gf / WS_STAGES) & 1);
       const uint8_t* base = stg + s * WS_STAGE_BYTES + col * 16;
 #pragma unroll
       for (int u = 0; u < WS_PX / 4; ++u) {
@@ -470,10 +476,9 @@ attn_wsum_stream_kernel(WsumArgs a, int maps) {
           }
         }
       }
-      if (gf + WS_STAGES < total_fills) {
-        __syncthreads();                  // every warp is done with stage s
-        fill(gf + WS_STAGES);
-      }
+      __syncwarp();
+      if (lane == 0)                                      // this warp is done with stage s
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * (WS_STAGES + s)) : "memory");
     }
     // ---- cross-group reduction, gate, outputs ----
     const int e0 = chunk * WS_CH + col * 8;
@@ -492,12 +497,13 @@ attn_wsum_stream_kernel(WsumArgs a, int maps) {
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk)
         gpre[kk] = (grp == 0 && a.beta_col >= 0) ? __ldg(a.g1 + (int64_t)row * a.ldg + a.beta_col + e0 + kk) : 0.f;
-      __syncthreads();
+      ws_csync();
       if (grp > 0) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) red[((grp - 1) * 64 + col) * 8 + kk] = accj[kk];
+        float4* dst = reinterpret_cast<float4*>(red + ((grp - 1) * 64 + col) * 8);
+        dst[0] = make_float4(accj[0], accj[1], accj[2], accj[3]);
+        dst[1] = make_float4(accj[4], accj[5], accj[6], accj[7]);
       }
-      __syncthreads();
+      ws_csync();
       if (grp == 0) {
 #pragma unroll
         for (int g = 1; g < 4; ++g)
@@ -518,7 +524,7 @@ attn_wsum_stream_kernel(WsumArgs a, int maps) {
         if (a.z_out) *reinterpret_cast<uint4*>((bf16*)a.z_out + (int64_t)row * a.ldz + e0) = pack16(zv, bf16());
       }
     }
-    __syncthreads();                      // `al` and `red` are rewritten by the next item
+    ws_csync();                           // `al` and `red` are rewritten by the next item
   }
 }
 
@@ -846,7 +852,7 @@ template <int RPM>
 int launch_wsum_stream(const WsumArgs& wa, int maps, cudaStream_t st) {
   auto kernel = attn_wsum_stream_kernel<RPM>;
   const size_t smem = (size_t)WS_STAGES * WS_STAGE_BYTES + (size_t)(RPM * ((wa.P + 3) & ~3) + 3 * 64 * 8 + 32) * 4 +
-                      WS_STAGES * 8 + 16;
+                      2 * WS_STAGES * 8 + 16;
   static std::once_flag once;
   static cudaError_t rc = cudaSuccess;
   std::call_once(once, [&] { rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); });
@@ -854,7 +860,7 @@ int launch_wsum_stream(const WsumArgs& wa, int maps, cudaStream_t st) {
   // persistent: two CTAs per SM (smem-limited), each walking over its share of the (map, chunk) items
   const int items = (wa.E / WS_CH) * maps;
   const int grid = items < 2 * 148 ? items : 2 * 148;
-  CAPDEC_CUDA_OK(launch_pdl(kernel, dim3(grid, 1, 1), dim3(NT, 1, 1), smem, st, 1, wa, maps));
+  CAPDEC_CUDA_OK(launch_pdl(kernel, dim3(grid, 1, 1), dim3(NT + 32, 1, 1), smem, st, 1, wa, maps));
   count_launch();
   return CAPDEC_OK;
 }

@@ -1,11 +1,8 @@
 #!/bin/bash
+# full ncu capture of the top kernels of the beam-search decode bench (after a plain run exited 0)
 OUT=gpurun_out
-timeout 300 python -m pytest tests/test_gpu_beam.py tests/test_gpu_units.py -m gpu -x -q 2>&1 | tail -3
-python bench.py --workload attention_scn_decode --steps 1 --warmup 3 --no-cpu-baseline > $OUT/dec2_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel|beam_select|attn_wsum|attn_scores' -s 300 -c 16 \
-    -f -o $OUT/dec2_prof python bench.py --workload attention_scn_decode --steps 1 --warmup 3 --no-cpu-baseline > $OUT/dec2_ncu.log 2>&1
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/dec2_plain.log").read().strip().splitlines()[-1])
-print("DECODE", d["value"], d["ms_per_step"])
-PY
+TAG=${1:-dec}
+python bench.py --workload attention_scn_decode --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_plain2.log 2>&1 &&
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'attn_wsum_stream|attn_scores_stream|gemm_tc_persist|beam_select' -s 40 -c 8 \
+    -f -o $OUT/${TAG}_prof python bench.py --workload attention_scn_decode --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu2.log 2>&1
+tail -1 $OUT/${TAG}_plain2.log | cut -c1-200
