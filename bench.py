@@ -515,10 +515,11 @@ def measure_recurrence_roofline(lib, dec, kind, dims, rows, inputs, peaks):
     fwd, bwd = entry(0, "recur_fwd_kernel"), entry(1, "recur_bwd_kernel")
     main, other = (bwd, fwd) if bwd["us_per_launch"] >= fwd["us_per_launch"] else (fwd, bwd)
     nbar = 6 if kind == "attention_scn" else 3
-    main["note"] = ("one cooperative launch = all %d decode steps; algorithmic bytes = %s; at %d rows the kernel is "
-                    "bound by its %d grid barriers (~1.5 us each) and dependent L2 round trips per step, not by HBM: "
-                    "the features stay L2-resident across steps, so the measured DRAM traffic is far BELOW the "
-                    "algorithmic stream -- see DESIGN.md" % (T, what, rows, nbar))
+    main["note"] = ("one cooperative launch = all %d decode steps, two independent 16-row groups per CTA; algorithmic "
+                    "bytes = %s; at %d rows the kernel is bound by its %d grid barriers per step (>= 1.3 us each: "
+                    "tools/barrier_bench.cu) and dependent L2 round trips, not by HBM: the features stay L2-resident "
+                    "across steps, so the measured DRAM traffic is far BELOW the algorithmic stream -- see DESIGN.md"
+                    % (T, what, rows, nbar))
     main["other_direction"] = other
     return main
 

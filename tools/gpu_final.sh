@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-end evidence: tests, smoke, every bench workload, reference arm, ncu launch list + full capture.
-TAG=${1:-r1e}
+TAG=${1:-r1g}
 OUT=gpurun_out
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -v "^E  *+\|tensor(\[" | tail -8 > $OUT/${TAG}_tests.log
