@@ -296,6 +296,15 @@ class DecoderTrainFn(torch.autograd.Function):
         if not plan.need_bwd:
             raise _lib.CapdecError("backward called but forward ran without save_for_backward")
         plan.ensure_grad_buffers()
+        # a .grad left over from an earlier step may ALIAS the static gradient buffer (autograd adopts the
+        # views returned below without copying): this call is about to overwrite that buffer, so such a
+        # gradient is detached into its own storage first (gradient accumulation stays correct)
+        if ctx.param_refs is not None:
+            lo = plan.flat_grads.data_ptr()
+            hi = lo + plan.flat_grads.numel() * 4
+            for p in ctx.param_refs:
+                if p.grad is not None and lo <= p.grad.data_ptr() < hi:
+                    p.grad = p.grad.clone()
         fused = meta.pop("fused_dlogits", None)    # set by FusedLossFn: gradient already in plan.dlog
         if fused:
             slot, d_pred_p, dlog_p = "bwd_fused", None, plan.dlog
@@ -332,10 +341,14 @@ class DecoderTrainFn(torch.autograd.Function):
             else:
                 call()
         meta["flat_grads"] = plan.flat_grads
-        grads = plan.grads
+        # FRESH view objects: autograd's AccumulateGrad adopts an incoming gradient without a copy only when
+        # nobody else holds the tensor object (returning the stored views made it clone all 23 gradients --
+        # 108.7 MB of device copies per step -- and made GradReducer fall back to copy-in / copy-out around
+        # the all-reduce, because .grad no longer lived in the flat buffer)
+        grads = [g.view(g.shape) for g in plan.grads]
         if ctx.use_graph and ctx.param_refs is not None and \
                 any(p.grad is not None for p in ctx.param_refs):
-            # gradient accumulation into an existing .grad that may alias the static buffer
+            # gradient accumulation into an existing .grad: hand out copies, the static buffer is reused
             grads = [g.clone() for g in grads]
         if not ctx.use_graph:
             plan.ws = None          # eager plans are single-use: release the workspace early

@@ -254,6 +254,40 @@ def test_graph_replay_matches_eager(kind):
         assert torch.equal(s_graph, s_eager) and l_graph == l_eager
 
 
+@pytest.mark.parametrize("graphs", [False, True])
+def test_gradients_live_in_the_flat_buffer_and_accumulate(graphs):
+    """`.grad` of every parameter is a view of the ONE flat gradient buffer the backward writes (what
+    capdec.parallel.GradReducer all-reduces in place, no copies), and a second backward WITHOUT zeroing the
+    gradients accumulates correctly although the static buffer is reused (eval mode: deterministic)."""
+    blob = load_golden("train_%s_medium" % O.ATTENTION_SCN)
+    with capdec.precision_scope("fp32"):
+        k, dec, (enc, tags, caps, caplens) = _load(blob)
+        dec.eval()
+
+        def fwd_bwd():
+            out = call_forward(dec, k, enc, tags, caps, caplens)
+            loss, _ = dec.loss(out[0], out[1], out[2], out[3])
+            loss.backward()
+            return out[0]
+
+        capdec.set_graphs(graphs)
+        try:
+            for _ in range(3 if graphs else 1):              # eager, capture, replay
+                dec.zero_grad(set_to_none=True)
+                scores = fwd_bwd()
+            flat = scores._capdec_meta["flat_grads"]
+            lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+            params = [p for p in dec.parameters() if p.requires_grad]
+            assert all(lo <= p.grad.data_ptr() < hi for p in params)
+            assert sum(p.grad.numel() for p in params) == flat.numel()
+            once = [p.grad.clone() for p in params]
+            fwd_bwd()                                        # no zero_grad: accumulate
+            for p, g in zip(params, once):
+                assert torch.allclose(p.grad, 2 * g, rtol=1e-6, atol=1e-12)
+        finally:
+            capdec.set_graphs(False)
+
+
 @pytest.mark.parametrize("persistent", ["1", "0"])
 @pytest.mark.parametrize("kind", [O.ATTENTION_SCN, O.PURE_SCN, O.PURE_ATTENTION])
 def test_bf16_full_width_matches_oracle(kind, persistent, monkeypatch):
