@@ -13,6 +13,7 @@ namespace capdec {
 namespace {
 
 constexpr int NT = 256;
+constexpr int ARS = 4;            // time slices of the alpha-regulariser kernels (ARS * NT threads per CTA)
 
 __device__ __forceinline__ float block_max(float v, float* sh) {
   v = warp_max(v);
@@ -94,20 +95,40 @@ topk_hits_kernel(const float* __restrict__ scores, int64_t ld, const int64_t* __
 }
 
 // one CTA per caption b: sum_p (1 - sum_t alpha[b,t,p])^2
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(ARS * NT)
 alpha_reg_fwd_kernel(const float* __restrict__ alphas, int T, int P, float* __restrict__ regpart) {
-  __shared__ float sh[NT / 32];
+  // one CTA per caption, 4 x NT threads: thread (pixel, time slice) sums every 4th step, so the dependent chain is
+  // T/4 loads long (a single 50-long chain per pixel made this 0.3 MB kernel 13 us)
+  __shared__ float sh[ARS * NT / 32];
+  __shared__ float part[ARS][NT];
   const int b = blockIdx.x;
   const float* a = alphas + (int64_t)b * T * P;
+  const int pl = threadIdx.x % NT, ts = threadIdx.x / NT;
   float acc = 0.f;
-  for (int p = threadIdx.x; p < P; p += NT) {
+  for (int p0 = 0; p0 < P; p0 += NT) {
+    const int p = p0 + pl;
     float s = 0.f;
-    for (int t = 0; t < T; ++t) s += a[(int64_t)t * P + p];
-    const float d = 1.f - s;
-    acc += d * d;
+    if (p < P)
+      for (int t = ts; t < T; t += ARS) s += a[(int64_t)t * P + p];
+    part[ts][pl] = s;
+    __syncthreads();
+    if (ts == 0 && p < P) {
+      float tot = part[0][pl];
+#pragma unroll
+      for (int k = 1; k < ARS; ++k) tot += part[k][pl];
+      const float d = 1.f - tot;
+      acc += d * d;
+    }
+    __syncthreads();
   }
-  acc = block_sum(acc, sh);
-  if (threadIdx.x == 0) regpart[b] = acc;
+  acc = warp_sum(acc);                               // zero in the threads of time slices > 0
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < ARS * NT / 32; ++i) tot += sh[i];
+    regpart[b] = tot;
+  }
 }
 
 __global__ void __launch_bounds__(NT)
@@ -164,20 +185,32 @@ ce_bwd_kernel(const float* __restrict__ pred, const int64_t* __restrict__ caps,
   }
 }
 
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(ARS * NT)
 alpha_reg_bwd_kernel(const float* __restrict__ alphas, const int32_t* __restrict__ len_d, int T,
                      int P, float scale, const float* __restrict__ gscale_dev,
                      float* __restrict__ d_alphas) {
   if (gscale_dev) scale *= gscale_dev[0];
+  __shared__ float part[ARS][NT];
   const int b = blockIdx.x;
   const float* a = alphas + (int64_t)b * T * P;
   float* d = d_alphas + (int64_t)b * T * P;
   const int len = len_d[b];
-  for (int p = threadIdx.x; p < P; p += NT) {
+  const int pl = threadIdx.x % NT, ts = threadIdx.x / NT;      // (pixel, time slice), as in the forward
+  for (int p0 = 0; p0 < P; p0 += NT) {
+    const int p = p0 + pl;
     float s = 0.f;
-    for (int t = 0; t < T; ++t) s += a[(int64_t)t * P + p];
-    const float g = -2.f * (1.f - s) * scale;
-    for (int t = 0; t < T; ++t) d[(int64_t)t * P + p] = t < len ? g : 0.f;
+    if (p < P)
+      for (int t = ts; t < T; t += ARS) s += a[(int64_t)t * P + p];
+    part[ts][pl] = s;
+    __syncthreads();
+    if (p < P) {
+      float tot = part[0][pl];
+#pragma unroll
+      for (int k = 1; k < ARS; ++k) tot += part[k][pl];
+      const float g = -2.f * (1.f - tot) * scale;
+      for (int t = ts; t < T; t += ARS) d[(int64_t)t * P + p] = t < len ? g : 0.f;
+    }
+    __syncthreads();
   }
 }
 
@@ -192,7 +225,7 @@ int loss_fwd(const CapdecDims& d, const float* pred, const float* alphas, const 
   ce_fwd_kernel<<<R, NT, 0, st>>>(pred, caps, len_d, d.T, d.V, d.L, lse_out, nll);
   CAPDEC_LAUNCH_OK();
   if (alphas) {
-    alpha_reg_fwd_kernel<<<d.B, NT, 0, st>>>(alphas, d.T, d.P, regpart);
+    alpha_reg_fwd_kernel<<<d.B, ARS * NT, 0, st>>>(alphas, d.T, d.P, regpart);
     CAPDEC_LAUNCH_OK();
   }
   loss_finalize_kernel<<<1, NT, 0, st>>>(nll, R, regpart, d.B, d.P, n_tokens, alpha_c, loss_out);
@@ -216,7 +249,7 @@ int loss_bwd(const CapdecDims& d, const float* pred, const float* alphas, const 
     CAPDEC_LAUNCH_OK();
   }
   if (alphas && d_alphas) {
-    alpha_reg_bwd_kernel<<<d.B, NT, 0, st>>>(alphas, len_d, d.T, d.P,
+    alpha_reg_bwd_kernel<<<d.B, ARS * NT, 0, st>>>(alphas, len_d, d.T, d.P,
                                              gscale * alpha_c / ((float)d.B * (float)d.P), gscale_dev,
                                              d_alphas);
     CAPDEC_LAUNCH_OK();
