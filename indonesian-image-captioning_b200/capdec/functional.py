@@ -127,12 +127,15 @@ class _Plan:
 
     def ensure_grad_buffers(self):
         if self.flat_grads is None:
-            self.flat_grads = torch.empty(sum(p.numel() for p in self.params), dtype=torch.float32,
+            # every gradient starts on a 256-byte boundary of the ONE flat buffer (vector loads in the fused
+            # optimizer, one in-place all-reduce over the whole buffer; the padding stays zero)
+            pad = lambda n: (n + 63) // 64 * 64
+            self.flat_grads = torch.zeros(sum(pad(p.numel()) for p in self.params), dtype=torch.float32,
                                           device=self.dev)
             self.grads, off = [], 0
             for p in self.params:
                 self.grads.append(self.flat_grads[off:off + p.numel()].view_as(p))
-                off += p.numel()
+                off += pad(p.numel())
             self.gstruct = _params_struct(self.kind, self.grads)
 
     def ensure_dlog(self):

@@ -26,7 +26,7 @@ class GradReducer:
             if g is None or not (lo <= g.data_ptr() < hi) or not g.is_contiguous():
                 return False
             total += g.numel()
-        return total == flat.numel()
+        return 0 < total <= flat.numel()          # the buffer may pad every gradient to an aligned slot
 
     def allreduce(self, meta=None):
         """Sum the gradients over all ranks.  Zero-copy when the backward wrote them into the flat

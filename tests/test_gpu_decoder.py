@@ -279,7 +279,8 @@ def test_gradients_live_in_the_flat_buffer_and_accumulate(graphs):
             lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
             params = [p for p in dec.parameters() if p.requires_grad]
             assert all(lo <= p.grad.data_ptr() < hi for p in params)
-            assert sum(p.grad.numel() for p in params) == flat.numel()
+            assert sum(p.grad.numel() for p in params) <= flat.numel()
+            assert all(p.grad.data_ptr() % 256 == 0 for p in params)      # aligned slots: vector loads in ClipAdam
             once = [p.grad.clone() for p in params]
             fwd_bwd()                                        # no zero_grad: accumulate
             for p, g in zip(params, once):
