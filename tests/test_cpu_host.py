@@ -120,3 +120,18 @@ def test_clip_adam_is_an_optimizer_and_has_no_cpu_path():
         assert False, "CPU tensors must be refused"
     except CapdecError:
         pass
+
+
+def test_evalcap_reference_layout():
+    """capdec.evalcap.transpose_references = the re-shaping of eval_caption.py:135-141 ([image][caption] ->
+    [caption][image]); compute_metrics needs nlg-eval, which this image does not have."""
+    from capdec import evalcap
+    refs = [["a b", "c"], ["d", "e f"], ["g", "h"]]
+    assert evalcap.transpose_references(refs) == [["a b", "d", "g"], ["c", "e f", "h"]]
+    assert evalcap.transpose_references([]) == []
+    try:
+        import nlgeval  # noqa: F401
+    except ImportError:
+        import pytest
+        with pytest.raises(ImportError):
+            evalcap.compute_metrics(refs, ["x", "y", "z"])
