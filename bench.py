@@ -304,12 +304,12 @@ def run_b200(args):
             if not pending:
                 issue_copy()
             bufs, ev = pending.pop(0)
-            issue_copy()                                   # next step's inputs start moving now
             cur = torch.cuda.current_stream()
             cur.wait_event(ev)
             for b in bufs:
                 b.record_stream(cur)
             loss = step(bufs)
+            issue_copy()              # next step's inputs start moving while this step computes (host cost hidden too)
             return loss.item()        # D2H read of the step's result
 
         for _ in range(warmup):
