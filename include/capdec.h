@@ -172,7 +172,11 @@ int capdec_loss_bwd(const CapdecDims* dims, const float* predictions, const floa
  *   out_alpha (G, n_steps+1, P) fp32 or NULL; entry 0 is all ones (attention_scn.py:204)
  *   trace_parent/word (G, n_steps, k) int32 and trace_score fp32, or NULL: the top-k picks of every
  *             step in torch.topk order (-1 / 0 once an image has finished)
- *   dims->B, T, L are ignored. */
+ *   dims->B, T, L are ignored.
+ * CAPDEC_BF16: `scores = F.log_softmax(self.fc(h), dim=1)` + `scores.view(-1).topk(k)` (attention_scn.py:235-253)
+ * run as ONE fused vocabulary kernel (projection + log-softmax statistics + top-k candidates; the (rows x V) logits
+ * are never written) followed by a per-image merge; CAPDEC_FP32 keeps GEMM + the exact three-pass selection that the
+ * token-parity tests pin (environment switches: INTEGRATION.md). */
 size_t capdec_beam_workspace_bytes(const CapdecDims* dims, int G, int k, int n_steps);
 int capdec_beam_search(const CapdecDims* dims, const CapdecParams* params,
                        const float* enc, const float* tags, int G, int k, int n_steps,
