@@ -57,6 +57,10 @@ constexpr int NCOL = CHUNK / 8;     // 16-byte columns per chunk = one warp
 constexpr int GROUPS = GT / NCOL;   // pixel groups of the weighted sum (8 = the warps of the row group)
 constexpr int WPXS = STAGE / (CHUNK * 2);   // pixels per weighted-sum stage (32)
 constexpr int SCI = 2 * STAGE / 1024;       // score items (<= 1 KB each) the two stages hold (32)
+// cycles row group 1 starts after group 0 (attention decoders; CAPDEC_RECUR_SKEW overrides both).  Measured at the
+// config-3 shape: forward 1 249 / 1 205 / 1 225 / 1 234 us and backward 1 315 / 1 306 / 1 280 / 1 279 us per launch
+// for 0 / 8 000 / 16 000 / 24 000 cycles.
+constexpr int RECUR_SKEW_FWD = 8000, RECUR_SKEW_BWD = 20000;
 constexpr int QW = 64;              // attention channels per item of backward phase B
 constexpr int BPX = STAGE / (QW * 2);       // pixels per fill of phase B (128)
 static_assert(NCOL == 32, "weighted-sum mapping: one warp per pixel group");
@@ -292,6 +296,16 @@ __device__ __forceinline__ void grp_init(Grp& G, uint8_t* stg, float* red, float
   }
 }
 
+// The two row groups of a CTA run the same phase sequence; started together they also hit the L2-bound streaming
+// phases (weighted sum, backward phase A) together and share the L2 slice throughput.  Starting group 1 a fraction of a
+// step later keeps them out of phase for the whole launch: one group streams while the other multiplies.
+__device__ __forceinline__ void group_skew(const Grp& G, int cycles) {
+  if (G.g == 1 && cycles > 0) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) __nanosleep(200);
+  }
+}
+
 struct FwdP {
   int B, T, P, E, A, M, D, F, NQ, NG1;
   int64_t R;                     // B*T
@@ -323,6 +337,7 @@ struct FwdP {
   float dropout_p; const uint64_t* seed;
   long long* prof;                  // debug (CAPDEC_RECUR_PROF=1): [T][16] clock64 stamps of CTA 0, group 0
   int mask;                         // debug: bit i set -> phase i runs (G1, scores, wsum, P3, P4, cell)
+  int skew;                         // cycles row group 1 starts after group 0 (see group_skew)
 };
 
 // LSTM = true: the pure_attention decoder (nn.LSTMCell on [emb ; z], pure_attention.py:143-146, gate order
@@ -364,6 +379,7 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
   for (int i = threadIdx.x; i < B; i += RT) lens[i] = p.len[i];
   __syncthreads();
   if (row0 >= B) return;                               // this group has no rows at all (B <= 16)
+  group_skew(G, p.skew);
 
   const int lrow = tid >> 4, ej = tid & 15;            // epilogue mapping of gemm_job (row inside the group)
   const int erow = row0 + lrow;                        // batch row
@@ -765,6 +781,7 @@ struct BwdP {
   unsigned* bar;
   float dropout_p; const uint64_t* seed;
   long long* prof;                    // debug (CAPDEC_RECUR_PROF=1): [T][16] clock64 stamps of CTA 0, group 0
+  int skew;                           // cycles row group 1 starts after group 0 (see group_skew)
 };
 
 // LSTM = true (pure_attention): no factor products (phase W is skipped), dz = dpre W_ih[:, M:], the recurrent
@@ -821,6 +838,7 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
   for (int i = threadIdx.x; i < B; i += RT) lens[i] = p.len[i];
   __syncthreads();
   if (row0 >= B) return;                                  // this group has no rows at all (B <= 16)
+  group_skew(G, p.skew);
 
   const int lrow = tid >> 4, ej = tid & 15;
   const int erow = row0 + lrow;
@@ -1373,6 +1391,8 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   cfg.numAttrs = 1;
   p.mask = 63;
   if (const char* mk = getenv("CAPDEC_RECUR_MASK")) p.mask = atoi(mk);
+  p.skew = a.att ? RECUR_SKEW_FWD : 0;
+  if (const char* sk = getenv("CAPDEC_RECUR_SKEW")) p.skew = atoi(sk);
   const char* prof_env = getenv("CAPDEC_RECUR_PROF");
   const bool prof = prof_env && prof_env[0] == '1';
   if (prof) {
@@ -1457,6 +1477,8 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
   p.dv_acc = a.dv_acc; p.dq_acc = a.dq_acc; p.dz = a.dz; p.awe = a.awe; p.alphas = a.alphas; p.d_alphas = a.d_alphas;
   p.enc_cm = (const bf16*)a.enc_cm; p.att1_cm = (const bf16*)a.att1_cm; p.w_f = a.w_f; p.part = a.part; p.de = a.de;
   p.dwf = a.dwf; p.dbf = a.dbf; p.bar = a.bar; p.dropout_p = a.dropout_p; p.seed = a.seed;
+  p.skew = a.att ? RECUR_SKEW_BWD : 0;
+  if (const char* sk = getenv("CAPDEC_RECUR_SKEW")) p.skew = atoi(sk);
   auto kernel = a.lstm ? recur_bwd_kernel<true, true> : a.att ? recur_bwd_kernel<true> : recur_bwd_kernel<false>;
   CAPDEC_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
