@@ -59,7 +59,8 @@ constexpr int WPXS = STAGE / (CHUNK * 2);   // pixels per weighted-sum stage (32
 constexpr int SCI = 2 * STAGE / 1024;       // score items (<= 1 KB each) the two stages hold (32)
 // cycles row group 1 starts after group 0 (attention decoders; CAPDEC_RECUR_SKEW overrides both).  Measured at the
 // config-3 shape: forward 1 249 / 1 205 / 1 225 / 1 234 us and backward 1 315 / 1 306 / 1 280 / 1 279 us per launch
-// for 0 / 8 000 / 16 000 / 24 000 cycles.
+// for 0 / 8 000 / 16 000 / 24 000 cycles; separately (CAPDEC_RECUR_SKEW_FWD / _BWD): forward 1 240 / 1 202 / 1 202 us
+// for 4 000 / 8 000 / 12 000, backward 1 292 / 1 277 / 1 270 us for 12 000 / 20 000 / 30 000.
 constexpr int RECUR_SKEW_FWD = 8000, RECUR_SKEW_BWD = 20000;
 constexpr int QW = 64;              // attention channels per item of backward phase B
 constexpr int BPX = STAGE / (QW * 2);       // pixels per fill of phase B (128)
@@ -1393,6 +1394,7 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   if (const char* mk = getenv("CAPDEC_RECUR_MASK")) p.mask = atoi(mk);
   p.skew = a.att ? RECUR_SKEW_FWD : 0;
   if (const char* sk = getenv("CAPDEC_RECUR_SKEW")) p.skew = atoi(sk);
+  if (const char* sk = getenv("CAPDEC_RECUR_SKEW_FWD")) p.skew = atoi(sk);
   const char* prof_env = getenv("CAPDEC_RECUR_PROF");
   const bool prof = prof_env && prof_env[0] == '1';
   if (prof) {
@@ -1479,6 +1481,7 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
   p.dwf = a.dwf; p.dbf = a.dbf; p.bar = a.bar; p.dropout_p = a.dropout_p; p.seed = a.seed;
   p.skew = a.att ? RECUR_SKEW_BWD : 0;
   if (const char* sk = getenv("CAPDEC_RECUR_SKEW")) p.skew = atoi(sk);
+  if (const char* sk = getenv("CAPDEC_RECUR_SKEW_BWD")) p.skew = atoi(sk);
   auto kernel = a.lstm ? recur_bwd_kernel<true, true> : a.att ? recur_bwd_kernel<true> : recur_bwd_kernel<false>;
   CAPDEC_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
