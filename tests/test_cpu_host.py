@@ -135,3 +135,48 @@ def test_evalcap_reference_layout():
         import pytest
         with pytest.raises(ImportError):
             evalcap.compute_metrics(refs, ["x", "y", "z"])
+
+
+def test_evalcap_driver_with_a_stub_decoder():
+    """Host logic of capdec.evalcap.generate_captions (string formatting of eval_caption.py:121-129, batching,
+    train/eval mode restore) with a stub in place of the CUDA decoder."""
+    import torch
+    from capdec import evalcap
+
+    word_map = {"<pad>": 0, "a": 1, "b": 2, "c": 3, "<unk>": 4, "<start>": 5, "<end>": 6}
+
+    class Stub(torch.nn.Module):
+        kind = "attention_scn"
+
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self.calls = []
+
+        def sample_batch(self, beam, start, end, enc, tags, max_steps=50, want_alphas=True):
+            assert not self.training and tags is not None and start == 5 and end == 6
+            self.calls.append(enc.size(0))
+            G = enc.size(0)
+            seq = torch.zeros(G, 6, dtype=torch.int32)
+            seq[:, 0] = 5
+            seq[:, 1] = 1 + (enc.view(G, -1)[:, 0].long() % 3).int()
+            seq[:, 2] = 2
+            seq[:, 3] = 6
+            return {"seq": seq, "len": torch.full((G,), 4, dtype=torch.int32),
+                    "completed": torch.tensor([1] * (G - 1) + [0], dtype=torch.int32)}
+
+    dec = Stub().train()
+    enc = torch.arange(5, dtype=torch.float32).view(5, 1, 1, 1)
+    tags = torch.zeros(5, 3)
+    allcaps = torch.tensor([[[5, 1, 2, 6, 0], [5, 3, 6, 0, 0]]] * 5)
+    batches = [(enc[:3], tags[:3], allcaps[:3]), (enc[3:], tags[3:], allcaps[3:])]
+    refs, hyps, done = evalcap.generate_captions(dec, batches, word_map, beam_size=3)
+    assert dec.training and dec.calls == [3, 2]
+    assert hyps == ["a b", "b b", "c b", "a b", "b b"]
+    assert refs == [["a b", "c"]] * 5
+    assert done == [True, True, False, True, False]
+    try:
+        evalcap.generate_captions(dec, [(enc, allcaps)], word_map)      # SCN decoder without tags
+        raise AssertionError("expected ValueError")
+    except ValueError:
+        pass

@@ -64,6 +64,18 @@ def _worker(rank, world, port, ret):
         m.b.grad = flat[4:].view(2, 3)
         out = GradReducer(m, dist).allreduce({"flat_grads": flat})
         ok_zero_copy = out.data_ptr() == flat.data_ptr() and torch.equal(flat, torch.arange(10.) * 3)
+        # padded slots (every gradient starts on an aligned boundary of the flat buffer, as DecoderTrainFn lays them
+        # out): still one in-place all-reduce of the whole buffer
+        padded = torch.zeros(128)
+        m2 = Two()
+        m2.a.grad = padded[0:4]
+        m2.b.grad = padded[64:70].view(2, 3)
+        with torch.no_grad():
+            m2.a.grad.fill_(float(rank + 1))
+            m2.b.grad.fill_(10.0 * (rank + 1))
+        out2 = GradReducer(m2, dist).allreduce({"flat_grads": padded})
+        ok_zero_copy = ok_zero_copy and out2.data_ptr() == padded.data_ptr() and \
+            bool((m2.a.grad == 3).all()) and bool((m2.b.grad == 30).all()) and float(padded[4:64].abs().sum()) == 0.0
         ret[rank] = (err, ok_zero_copy, shard_range(5000, rank, world))
     finally:
         dist.destroy_process_group()
