@@ -248,7 +248,7 @@ int pack_weights(const Ctx& c, const CapdecParams& w) {
   const CapdecDims& d = p.d;
   const int pr = c.prec;
   cudaStream_t st = c.st;
-  const int D = d.D, E = d.E, A = d.A, M = d.M, F = d.F, S = d.S, V = d.V, X = p.X, NQ = p.NQ;
+  const int D = d.D, E = d.E, A = d.A, F = d.F, S = d.S, V = d.V, X = p.X, NQ = p.NQ;
   int row = 0;     // row cursor inside Wp_cat1
   PackTable tbl;
   bool ok = true;
