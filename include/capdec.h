@@ -129,6 +129,14 @@ int capdec_forward_train(const CapdecDims* dims, const CapdecParams* params,
                          float* predictions, float* alphas,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Test / parity hook for the dropout between h_t and fc (reference: `self.fc(self.dropout(h))`,
+ * attention_scn.py:154; nn.Dropout scales the kept elements by 1/(1-p)).  torch's mask RNG cannot be matched,
+ * so the decoder draws its mask from a counter-based hash; this entry writes the keep factors the forward
+ * and backward kernels of a call with the same (dropout_seed, dropout_p) apply: mask_out[i] is 0 or
+ * 1/(1-p) for the flat index i = (b*T + t)*D + d of the sorted batch, n = B*T*D.  Feeding it to an
+ * independent implementation as the dropout mask reproduces the training-mode arithmetic exactly. */
+int capdec_dropout_mask(uint64_t dropout_seed, float dropout_p, int64_t n, float* mask_out, void* stream);
+
 /* Reverse-time backward of capdec_forward_train (same dims / workspace, later on the same
  * stream).  Reads only params, workspace (tags / captions / dropout seed were staged there by the
  * forward), alphas and the d_* inputs -> graph-capturable like the compute phase.

@@ -43,6 +43,7 @@ SIGNATURES = {
     "capdec_launch_count": (C.c_ulonglong, []),
     "capdec_topk_hits": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "capdec_clip_adam_step": (_i, [C.POINTER(AdamSeg), _i] + [C.c_double] * 6 + [_i, _i, _vp]),
+    "capdec_dropout_mask": (_i, [_u64, _f, _i64, _vp, _vp]),
     "capdec_recur_timing": (None, [_i]),
     "capdec_recur_last_ms": (_f, [_i]),
     "capdec_workspace_bytes": (_sz, [C.POINTER(Dims), _i]),

@@ -462,6 +462,21 @@ def caption_loss(scores, caps_sorted, decode_lengths, alphas=None, alpha_c=1.0, 
     return FusedLossFn.apply(scores, alphas, caps_sorted, len_d, n_tokens, float(alpha_c), dims, meta)
 
 
+def dropout_mask(seed, p, B, T, D, device="cuda"):
+    """(B, T, D) keep factors (0 or 1/(1-p)) of the dropout between h_t and fc (attention_scn.py:154) that a
+    forward/backward with this seed applies -- the mask-injection hook of the parity tests: an independent
+    implementation fed with this mask reproduces the training-mode arithmetic."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.CapdecError("capdec ops need a CUDA device; there is no CPU path")
+    out = torch.empty(B, T, D, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.capdec_dropout_mask(int(seed) & ((1 << 63) - 1), float(p), out.numel(), _lib.ptr(out), _stream())
+    _lib.check(rc, "capdec_dropout_mask")
+    return out
+
+
 # ---------------------------------------------------------------------------------
 # unit ops (used by models/scn_cell.py, models/attention.py and the parity tests)
 # ---------------------------------------------------------------------------------

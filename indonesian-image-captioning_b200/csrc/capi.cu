@@ -78,6 +78,11 @@ int capdec_clip_adam_step(const CapdecAdamSeg* segs, int n_segs, double lr, doub
                         (cudaStream_t)stream);
 }
 
+int capdec_dropout_mask(uint64_t dropout_seed, float dropout_p, int64_t n, float* mask_out, void* stream) {
+  CAPDEC_TRY(capdec_init());
+  return dropout_mask(dropout_seed, dropout_p, n, mask_out, (cudaStream_t)stream);
+}
+
 void capdec_recur_timing(int enable) { recur_timing(enable); }
 float capdec_recur_last_ms(int which) { return recur_last_ms(which); }
 

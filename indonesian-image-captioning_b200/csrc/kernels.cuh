@@ -171,6 +171,8 @@ int beam_finalize(int G, int k, int n_steps, int P, int32_t start_id, int32_t en
 int topk_hits(const float* scores, int64_t ld, const int64_t* targets, const int64_t* caps, const int32_t* len_d,
               int rows, int T, int L, int V, int k, int* hits, cudaStream_t st);
 
+int dropout_mask(uint64_t seed, float p, int64_t n, float* out, cudaStream_t st);
+
 // ---- optim.cu ----
 int clip_adam_step(const CapdecAdamSeg* segs, int n_segs, double lr, double beta1, double beta2, double eps,
                    double weight_decay, double grad_clip, int step, int write_clipped, cudaStream_t st);

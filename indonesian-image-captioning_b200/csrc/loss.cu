@@ -268,4 +268,21 @@ int topk_hits(const float* scores, int64_t ld, const int64_t* targets, const int
   return CAPDEC_OK;
 }
 
+
+// the keep factors (0 or 1/(1-p)) the decoder applies to h_t before fc in training mode: the same counter-based
+// hash of (seed, (b*T + t)*D + d) the forward and backward kernels evaluate in place (common.cuh dropout_scale)
+__global__ void dropout_mask_kernel(uint64_t seed, float p, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = dropout_scale(seed, (uint64_t)i, p);
+}
+
+int dropout_mask(uint64_t seed, float p, int64_t n, float* out, cudaStream_t st) {
+  CAPDEC_REQUIRE(out && n >= 0 && p >= 0.f && p < 1.f, CAPDEC_ERR_BAD_ARG, "dropout_mask: bad argument");
+  if (n == 0) return CAPDEC_OK;
+  const int64_t blocks = (n + 255) / 256;
+  dropout_mask_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(seed, p, n, out);
+  CAPDEC_LAUNCH_OK();
+  return CAPDEC_OK;
+}
+
 }  // namespace capdec

@@ -58,12 +58,17 @@ def rel_err_fro(got, ref):
     return (got - ref).norm().item() / max(ref.norm().item(), 1e-30)
 
 
-def oracle_run(kind, sd, enc, tags, caps, caplens, sort_ind=None, dtype=torch.float64, alpha_c=1.0):
-    """Forward + loss + backward through the oracle (CPU, fp64 by default)."""
+def oracle_run(kind, sd, enc, tags, caps, caplens, sort_ind=None, dtype=torch.float64, alpha_c=1.0,
+               dropout_masks=None, hoist=False):
+    """Forward + loss + backward through the oracle (CPU, fp64 by default).  `dropout_masks`: (B,T,D) keep
+    factors in SORTED row order (None = eval mode); `hoist`: att1 computed once (same arithmetic, see
+    tests/test_oracle_golden.py::test_hoisted_att1_is_the_same_arithmetic)."""
     p = {k: v.detach().cpu().to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
     t = None if kind == O.PURE_ATTENTION else tags.cpu().to(dtype)
     out = O.decoder_forward(kind, p, enc.cpu().to(dtype), t, caps.cpu(), caplens.cpu(),
-                            sort_ind=None if sort_ind is None else sort_ind.cpu())
+                            sort_ind=None if sort_ind is None else sort_ind.cpu(),
+                            dropout_masks=None if dropout_masks is None else dropout_masks.cpu().to(dtype),
+                            hoist=hoist)
     if kind == O.PURE_SCN:
         scores, caps_sorted, dl, si = out
         alphas = None

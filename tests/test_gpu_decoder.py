@@ -364,3 +364,68 @@ def test_persistent_recurrence_matches_step_kernels(kind, train_mode, monkeypatc
             continue
         e = rel_err_fro(a[3][n], b[3][n])
         assert e < 3e-2, (n, e)
+
+
+@pytest.mark.parametrize("lengths_kind", ["fixed51", "ragged"])
+@pytest.mark.parametrize("kind", [O.ATTENTION_SCN, O.PURE_SCN, O.PURE_ATTENTION])
+def test_benchmarked_mode_matches_oracle(kind, lengths_kind, monkeypatch):
+    """The exact mode bench.py times -- BASELINE config-3 per-GPU shape (B=32, T=50, V=10k, dims 512), TRAIN mode
+    with dropout p=0.5, bf16 features, persistent recurrence kernels -- against the fp64 oracle, and the same step
+    in fp32 mode.  torch's dropout RNG cannot be matched, so the oracle is fed the decoder's own
+    keep factors (capdec_dropout_mask: the counter-based hash of (seed, b, t, d) that the forward AND the backward
+    kernels evaluate in place) as `dropout_masks` at the reference's dropout site (attention_scn.py:154): a wrong
+    keep scale, a mask that differs between forward and backward, or a mis-indexed mask all show up here.
+    Tolerances: logits / alphas / loss 2e-2 (bf16, BASELINE north_star) and 1e-4 (fp32); gradients of all
+    parameters 8e-2 (bf16) and 2e-4 (fp32) max-norm relative, the two parameters downstream of the relu mask of
+    the attention scores (a mask that flips in the last ulp moves single entries by a whole term) in the
+    Frobenius norm (fp32: 1e-3)."""
+    from capdec import functional as CF
+    monkeypatch.setenv("CAPDEC_PERSISTENT", "1")
+    dims = dict(A=512, M=512, D=512, F=512, S=1000, V=10000, E=2048)
+    B, p_drop = 32, 0.5
+    lengths = [51] * B if lengths_kind == "fixed51" else O.tie_free_lengths(B)
+    enc, tags, caps, caplens = O.synthetic_batch(B, dims["V"], seed=21, lengths=lengths)
+    args = [t.cuda() for t in (enc, tags, caps, caplens)]
+    torch.manual_seed(0)
+    dec = build_decoder(kind, dims).train()
+    assert dec.dropout.p == p_drop
+    sd = {k: v.detach().cpu() for k, v in dec.state_dict().items()}
+    ref = None
+    for prec, tol, gtol, gtol_fro in (("bf16", BF16_TOL, 8e-2, 8e-2), ("fp32", FP32_TOL, 2 * FP32_TOL, 1e-3)):
+        with capdec.precision_scope(prec):
+            torch.manual_seed(123)                       # same dropout seed in both modes
+            dec.zero_grad(set_to_none=True)
+            scores, caps_sorted, dl, alphas, sort_ind = call_forward(dec, kind, *args)
+            T = max(dl)
+            assert T == 50 and dl == sorted([l - 1 for l in lengths], reverse=True)
+            seed = scores._capdec_meta["seed"]
+            mask = CF.dropout_mask(seed, p_drop, B, T, dims["D"])
+            assert set(mask.unique().tolist()) == {0.0, 1.0 / (1.0 - p_drop)}
+            assert abs((mask > 0).float().mean().item() - (1.0 - p_drop)) < 5e-3
+            if ref is None:
+                ref = oracle_run(kind, sd, enc, tags, caps, caplens, sort_ind=sort_ind, dropout_masks=mask,
+                                 hoist=True)
+            assert dl == ref["decode_lengths"]
+            assert rel_err(scores, ref["scores"]) < tol, prec
+            if alphas is not None:
+                assert rel_err(alphas, ref["alphas"]) < tol, prec
+            loss, _ = dec.loss(scores, caps_sorted, dl, alphas)
+            assert abs(loss.item() - ref["loss"].item()) < tol * abs(ref["loss"].item()), prec
+            loss.backward()
+            bad = []
+            for n, p in dec.named_parameters():
+                g = ref["grads"][n]
+                if g.abs().max().item() < 1e-9:          # full_att.bias: mathematically zero
+                    continue
+                if n.startswith("attention.encoder_att") or n.startswith("attention.decoder_att"):
+                    e, lim = rel_err_fro(p.grad, g), gtol_fro
+                else:
+                    e, lim = rel_err(p.grad, g), gtol
+                if e >= lim:
+                    bad.append((prec, n, e, lim))
+            assert not bad, bad
+    # the mask matters: the eval-mode logits are far from the training-mode ones
+    dec.eval()
+    with capdec.precision_scope("bf16"):
+        s_eval = call_forward(dec, kind, *args)[0]
+    assert rel_err(s_eval, ref["scores"]) > 10 * BF16_TOL

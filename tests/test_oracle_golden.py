@@ -96,3 +96,38 @@ def test_beam_search_matches_reference(kind):
                 assert len(got["trace"]) == 51      # App. C-5: up to 51 decode steps
                 assert len(got["seq"]) == 52
     assert n_done > 0 and n_fail > 0
+
+
+@pytest.mark.parametrize("name", ["train_attention_scn_medium", "train_pure_attention_medium", "train_attention_scn_hot"])
+def test_hoisted_att1_is_the_same_arithmetic(name):
+    """decoder_forward(hoist=True) (att1 computed once, batched weighted sum: what the full-size GPU parity
+    tests use so that the checker finishes in seconds) against the as-written structure and the live
+    reference's vectors, with and without an injected dropout mask."""
+    blob = load_golden(name)
+    kind = blob["kind"]
+    tags = None if kind == O.PURE_ATTENTION else blob["tags"].double()
+    B, T = blob["predictions"].shape[:2]
+    D = blob["state_dict"]["init_h.weight"].shape[0]
+    g = torch.Generator().manual_seed(5)
+    mask = (torch.rand(B, T, D, generator=g) >= 0.5).double() * 2.0
+    for masks in (None, mask):
+        res = []
+        for hoist in (False, True):
+            p = {k: v.double().clone().requires_grad_(True) for k, v in blob["state_dict"].items()}
+            out = O.decoder_forward(kind, p, blob["encoder_out"].double(), tags, blob["captions"],
+                                    blob["caption_lengths"], sort_ind=blob["sort_ind"], dropout_masks=masks,
+                                    hoist=hoist)
+            loss = O.caption_loss(out[0], out[1], out[2], out[3])
+            loss.backward()
+            res.append((out[0].detach(), out[3].detach(), loss.item(), {k: v.grad for k, v in p.items()}))
+        a, b = res
+        assert (a[0] - b[0]).abs().max().item() <= 1e-12 * a[0].abs().max().item()
+        assert (a[1] - b[1]).abs().max().item() <= 1e-13
+        assert abs(a[2] - b[2]) <= 1e-12 * abs(a[2])
+        for n in a[3]:
+            if n == "attention.full_att.bias":      # mathematically zero (softmax shift invariance): rounding noise
+                assert a[3][n].abs().max().item() < 1e-15 and b[3][n].abs().max().item() < 1e-15
+                continue
+            assert (a[3][n] - b[3][n]).abs().max().item() <= 1e-11 * max(a[3][n].abs().max().item(), 1e-9), n
+        if masks is None:       # and both agree with what the live reference produced (fp32 goldens)
+            assert (b[0].float() - blob["predictions"]).abs().max().item() <= 2e-5 * blob["predictions"].abs().max().item()
