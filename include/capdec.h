@@ -120,7 +120,14 @@ size_t capdec_workspace_bytes(const CapdecDims* dims, int with_backward);
  *                  projection: everything before the recurrence), 2|8 = the rest (recurrence +
  *                  vocabulary projection) after a prologue that has already been launched -- the host
  *                  can queue 1|4 BEFORE it learns the decode lengths of a repeated shape and keep
- *                  the GPU busy while it waits for them (capdec/functional.py `speculate`). */
+ *                  the GPU busy while it waits for them (capdec/functional.py `speculate`).
+ *                  16 (with 2 and/or 4) = LENGTH-INDEPENDENT compute phases: the launches take the decode lengths
+ *                  only from the device copy the input phase staged (decode_len_h may be NULL), so ONE captured
+ *                  graph serves every batch with the same (B, T) whatever its lengths are.  Needs the persistent
+ *                  recurrence kernels (CAPDEC_BF16 and a shape csrc/recur.cu covers), else CAPDEC_ERR_UNSUPPORTED.
+ *                  In a compute-only call (no bit 1) enc / sort_ind / tags / caps_sorted are not read.
+ *                  32 = re-stage decode_len_h on the device and nothing else (after an input phase that ran
+ *                  before the lengths were known). */
 int capdec_forward_train(const CapdecDims* dims, const CapdecParams* params,
                          const float* enc, int64_t enc_sb, int64_t enc_sp, int64_t enc_se,
                          const int64_t* sort_ind, const float* tags,
@@ -147,12 +154,21 @@ int capdec_dropout_mask(uint64_t dropout_seed, float dropout_p, int64_t n, float
  *   d_alphas       (B,T,P) fp32 gradient of the returned alphas, or NULL
  *   alphas         the (B,T,P) tensor capdec_forward_train wrote
  *   grads          every non-NULL member is OVERWRITTEN with the dense gradient of that
- *                  parameter (reference shapes; bias_ih.grad == bias_hh.grad). */
+ *                  parameter (reference shapes; bias_ih.grad == bias_hh.grad).
+ *   decode_len_h   HOST lengths as given to the forward, or NULL = length-independent launch (the device copy
+ *                  staged by the forward is used; persistent kernels required, see `phases` 16 above)
+ *   phases         0 = everything, else a bit set of the backward's stages IN PRODUCTION ORDER of the gradients,
+ *                  so that a data-parallel caller can all-reduce one bucket of gradients while the next is being
+ *                  computed (capdec/parallel.py):
+ *                    1  fc.weight, fc.bias (and dH_fc)          2  the reverse-time recurrence
+ *                    4  weight_ia / weight_ih, embedding.weight  8  the other cell weights, bias_ih, bias_hh
+ *                    16 attention.*, f_beta.*, init_h.*, init_c.*
+ *                  Stages must run in this order on one stream; each is graph-capturable on its own. */
 int capdec_backward(const CapdecDims* dims, const CapdecParams* params,
                     const int32_t* decode_len_h, float dropout_p,
                     const float* d_predictions, const void* d_logits_ft, const float* d_alphas,
                     const float* alphas, const CapdecParams* grads,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    void* workspace, size_t workspace_bytes, int phases, void* stream);
 
 /* Loss glue: packed cross entropy (mean over N = sum(decode_len)) + alpha_c * mean_{b,p}
  * (1 - sum_t alpha)^2.  loss_out[0] = total, [1] = CE part, [2] = regulariser part.

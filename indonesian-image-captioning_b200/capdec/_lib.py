@@ -50,7 +50,7 @@ SIGNATURES = {
     "capdec_forward_train": (_i, [C.POINTER(Dims), C.POINTER(Params), _vp, _i64, _i64, _i64, _vp, _vp,
                                   _vp, _vp, _f, _u64, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "capdec_backward": (_i, [C.POINTER(Dims), C.POINTER(Params), _vp, _f, _vp, _vp, _vp,
-                             _vp, C.POINTER(Params), _vp, _sz, _vp]),
+                             _vp, C.POINTER(Params), _vp, _sz, _i, _vp]),
     "capdec_loss_fwd": (_i, [C.POINTER(Dims), _vp, _vp, _vp, _vp, C.c_int32, _f, _vp, _vp, _vp]),
     "capdec_loss_bwd": (_i, [C.POINTER(Dims), _vp, _vp, _vp, _vp, C.c_int32, _f, _f, _vp, _vp, _vp, _vp,
                              _vp, _vp]),

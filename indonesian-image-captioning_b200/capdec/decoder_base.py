@@ -8,8 +8,12 @@ per forward and one per backward.
 import torch
 from torch import nn
 
+import os
+
 from . import functional as CF
 from .config import get_precision
+
+_CHECK_IDS = os.environ.get("CAPDEC_CHECK_IDS", "1") != "0"
 
 
 class CaptionDecoderBase(nn.Module):
@@ -59,6 +63,19 @@ class CaptionDecoderBase(nn.Module):
     def _forward_impl(self, encoder_out, semantic_input, encoded_captions, caption_lengths):
         batch_size = encoder_out.size(0)
         encoder_dim = encoder_out.size(-1)
+        if torch.is_grad_enabled() and (encoder_out.requires_grad or
+                                        (semantic_input is not None and semantic_input.requires_grad)):
+            # the reference can fine-tune the encoders through the decoder (fine_tune_encoder=True with an
+            # encoder_optimizer, trains/attention_scn.py:94-109, 141); capdec_backward produces no gradient
+            # with respect to encoder_out / the tags, so that configuration must not train silently
+            raise RuntimeError("capdec decoders do not back-propagate into encoder_out / semantic_input "
+                               "(fine_tune_encoder=True is not supported): detach the encoder outputs")
+        if encoded_captions.dtype != torch.int64 or caption_lengths.dtype != torch.int64:
+            raise RuntimeError("encoded_captions and caption_lengths must be int64 tensors (got %s, %s)"
+                               % (encoded_captions.dtype, caption_lengths.dtype))
+        if self.kind != "pure_attention" and tuple(semantic_input.shape) != (batch_size, self.semantic_dim):
+            raise RuntimeError("semantic_input must have shape (%d, %d), got %s"
+                               % (batch_size, self.semantic_dim, tuple(semantic_input.shape)))
         enc = encoder_out.view(batch_size, -1, encoder_dim)        # strided views are fine (App. C-22)
         if enc.dtype != torch.float32:
             enc = enc.float()
@@ -72,6 +89,11 @@ class CaptionDecoderBase(nn.Module):
             lens_ev = torch.cuda.Event()
             lens_ev.record()
         caps_sorted = encoded_captions[sort_ind].contiguous()
+        if _CHECK_IDS and caps_sorted.is_cuda:
+            # nn.Embedding / CrossEntropyLoss raise on ids outside the vocabulary; the kernels would clamp them.
+            # Asynchronous device-side check (no host sync), CAPDEC_CHECK_IDS=0 removes it.
+            torch._assert_async(((caps_sorted >= 0) & (caps_sorted < self.vocab_size)).all(),
+                                "caption token id outside [0, vocab_size)")
         # everything that does not need the lengths on the host comes BEFORE the sync below: after it the
         # GPU is idle until the first launch
         tags = None

@@ -3,17 +3,22 @@
 All tensors must live on a CUDA device; nothing here computes on the CPU.
 
 Two execution modes for the training step:
-  * eager (default): one C call per forward and per backward; each issues its ~400 kernel
-    launches on the current stream.
-  * graph replay (`capdec.set_graphs(True)` or CAPDEC_GRAPHS=1): per problem signature (dims,
-    decode lengths, parameter pointers) a plan owns static workspace/output/gradient buffers; the
-    compute phase of the forward and the whole backward are captured once into CUDA graphs and
-    replayed, so a step costs a handful of launches on the host.  Outputs are then views of the
-    plan's static buffers and stay valid until the next forward with the same signature.
+  * graph replay (default; `capdec.set_graphs(False)` or CAPDEC_GRAPHS=0 turns it off): per problem FAMILY
+    (dims but T, parameter storage, device) one set of static workspace / output / gradient buffers sized for the
+    longest caption, and per T one plan whose compute phase of the forward and whose backward are captured once
+    into CUDA graphs and replayed, so a step costs a handful of launches on the host.  On the bf16 path with the
+    persistent recurrence kernels the graphs are LENGTH-INDEPENDENT: the kernels read the decode lengths from
+    the device, so ragged batches with the same longest caption replay the same graph (fp32 mode and shapes
+    outside recur.cu key their plans on the exact lengths instead).  Outputs are views of the family's static
+    buffers and stay valid until the next forward of the same family; a forward issued while an earlier one of
+    the family still waits for its backward runs eagerly on buffers of its own.
+  * eager: one C call per forward and per backward on fresh buffers; each issues its launches on the current
+    stream.
 """
 import collections
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -40,9 +45,41 @@ PARAM_MAP = {
     "pure_attention": _ATT + [("embedding.weight", "emb")] + _LSTM + _COMMON_TAIL + _BETA + _FC,
 }
 
-_graphs_enabled = os.environ.get("CAPDEC_GRAPHS", "0") == "1"
-_MAX_PLANS = 4
+# gradient buckets in PRODUCTION ORDER of capdec_backward (its `phases` 1|2, 4, 8, 16): the flat gradient buffer is
+# laid out in this order, so every bucket is one contiguous slice that a data-parallel caller can all-reduce as
+# soon as its stage has been launched (capdec/parallel.py)
+_BUCKET_NAMES = [
+    ("fc.weight", "fc.bias"),
+    ("decode_step.weight_ia", "decode_step.weight_ih", "embedding.weight"),
+    ("decode_step.weight_ic", "decode_step.weight_hc", "decode_step.weight_ha", "decode_step.weight_hh",
+     "decode_step.weight_ib", "decode_step.weight_hb", "decode_step.bias_ih", "decode_step.bias_hh"),
+    ("attention.encoder_att.weight", "attention.encoder_att.bias", "attention.decoder_att.weight",
+     "attention.decoder_att.bias", "attention.full_att.weight", "attention.full_att.bias", "f_beta.weight",
+     "f_beta.bias", "init_h.weight", "init_h.bias", "init_c.weight", "init_c.bias"),
+]
+BUCKET_PHASES = (1 | 2, 4, 8, 16)
+
+
+def grad_buckets(kind):
+    """Per bucket, the indices into PARAM_MAP[kind] of the parameters whose gradients it holds."""
+    names = param_names(kind)
+    out = [[names.index(n) for n in bucket if n in names] for bucket in _BUCKET_NAMES]
+    assert sorted(i for b in out for i in b) == list(range(len(names)))
+    return out
+
+
+_graphs_enabled = os.environ.get("CAPDEC_GRAPHS", "1") != "0"
+_MAX_FAMILIES = 4
 _replayed_launches = 0
+_bucket_hook = None
+
+
+def set_grad_bucket_hook(fn):
+    """fn(bucket_index, n_buckets, flat_slice) is called inside the decoder's backward right after the launches
+    that produce that bucket of the flat gradient buffer have been queued (None removes the hook).  Used by
+    capdec.parallel.GradReducer to overlap the gradient all-reduce with the rest of the backward."""
+    global _bucket_hook
+    _bucket_hook = fn
 
 
 def launch_count():
@@ -56,8 +93,7 @@ def set_graphs(flag):
     global _graphs_enabled
     _graphs_enabled = bool(flag)
     if not flag:
-        _plans.clear()
-        _last_plan.clear()
+        _families.clear()
 
 
 def graphs_enabled():
@@ -94,58 +130,112 @@ def _dims_key(d):
     return tuple(getattr(d, n) for n, _ in _lib.Dims._fields_)
 
 
-class _Plan:
-    """Buffers (and, in graph mode, captured graphs) of one decoder problem signature."""
+def _with_T(d, T):
+    return _lib.Dims(*[T if n == "T" else getattr(d, n) for n, _ in _lib.Dims._fields_])
 
-    def __init__(self, kind, dims, decode_lengths, need_bwd, params, dev):
+
+class _GradStore:
+    """ONE flat fp32 buffer for all gradients of a decoder, in bucket (production) order; every gradient starts
+    on a 256-byte boundary (vector loads in the fused optimizer; the padding stays zero)."""
+
+    def __init__(self, kind, params, dev):
+        pad = lambda n: (n + 63) // 64 * 64
+        self.flat = torch.zeros(sum(pad(p.numel()) for p in params), dtype=torch.float32, device=dev)
+        self.grads = [None] * len(params)
+        self.bucket_slices = []
+        off = 0
+        for bucket in grad_buckets(kind):
+            lo = off
+            for i in bucket:
+                p = params[i]
+                self.grads[i] = self.flat[off:off + p.numel()].view_as(p)
+                off += pad(p.numel())
+            self.bucket_slices.append((lo, off))
+        self.gstruct = _params_struct(kind, self.grads)
+
+
+class _Buffers:
+    """Device buffers of the training step, sized for `T_cap` decode steps."""
+
+    def __init__(self, kind, dims_cap, need_bwd, dev):
         lib = _lib.load()
-        self.kind, self.dims, self.need_bwd, self.dev = kind, dims, need_bwd, dev
-        B, T, P, V = dims.B, dims.T, dims.P, dims.V
-        self.ws_bytes = lib.capdec_workspace_bytes(C.byref(dims), 1 if need_bwd else 0)
+        B, T, P, V = dims_cap.B, dims_cap.T, dims_cap.P, dims_cap.V
+        self.kind, self.dev, self.T_cap, self.need_bwd = kind, dev, T, need_bwd
+        self.ws_bytes = lib.capdec_workspace_bytes(C.byref(dims_cap), 1 if need_bwd else 0)
         if self.ws_bytes == 0:
             _lib.check(-1, "capdec_workspace_bytes")
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
-        self.predictions = torch.empty(B, T, V, dtype=torch.float32, device=dev)
-        self.alphas = None if kind == "pure_scn" else torch.empty(B, T, P, dtype=torch.float32, device=dev)
-        self.len_h = (C.c_int32 * B)(*decode_lengths)
-        self.len_list = [int(x) for x in decode_lengths]
-        # device copy of the lengths for the fused loss: pinned + non_blocking, so that nothing on the
-        # host waits for the stream (a pageable torch.tensor(..., device=) copy would block until the
-        # forward graph has drained and expose the whole host cost of loss + backward)
-        self.len_d = torch.tensor(self.len_list, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+        self.pred = torch.empty(B * T * V, dtype=torch.float32, device=dev)
+        self.alph = None if kind == "pure_scn" else torch.empty(B * T * P, dtype=torch.float32, device=dev)
+        self.dlog = None          # d logits in the GEMM feature type (fused-loss path)
+        self.d_alph = None
+        self.d_pred = None        # static copy of an autograd-provided gradient (generic path)
+        self.len_pin = torch.empty(B, dtype=torch.int32, pin_memory=True)
+        self.len_d = torch.empty(B, dtype=torch.int32, device=dev)
+
+
+class _Plan:
+    """One decoder problem (dims incl. T) on a set of buffers: views of the outputs, the decode lengths as the C
+    ABI wants them and, in graph mode, the captured graphs."""
+
+    def __init__(self, kind, dims, buf, params, gstore, len_free):
+        self.kind, self.dims, self.buf, self.dev = kind, dims, buf, buf.dev
+        self.need_bwd = buf.need_bwd
+        self.len_free = len_free  # graphs do not depend on the decode lengths (only on B and T)
+        B, T, P, V = dims.B, dims.T, dims.P, dims.V
+        self.ws, self.ws_bytes = buf.ws, buf.ws_bytes
+        self.predictions = buf.pred[:B * T * V].view(B, T, V)
+        self.alphas = None if buf.alph is None else buf.alph[:B * T * P].view(B, T, P)
+        self.len_h = (C.c_int32 * B)()
+        self.len_list = None
+        self.len_d = buf.len_d
         self.params = params
         self.pstruct = _params_struct(kind, params)
-        self.flat_grads = None
-        self.grads = None
-        self.gstruct = None
-        self.dlog = None          # d logits in the GEMM feature type (fused-loss path)
-        self.d_alphas = None
-        self.d_pred = None        # static copy of an autograd-provided gradient (generic path)
+        self.gstore = gstore
+        self.dlog = self.d_alphas = None
         self.graphs = {}          # slot -> torch.cuda.CUDAGraph
         self.graph_nodes = {}     # slot -> kernels in the captured graph
         self.calls = {}           # slot -> number of launches so far
 
-    def ensure_grad_buffers(self):
-        if self.flat_grads is None:
-            # every gradient starts on a 256-byte boundary of the ONE flat buffer (vector loads in the fused
-            # optimizer, one in-place all-reduce over the whole buffer; the padding stays zero)
-            pad = lambda n: (n + 63) // 64 * 64
-            self.flat_grads = torch.zeros(sum(pad(p.numel()) for p in self.params), dtype=torch.float32,
-                                          device=self.dev)
-            self.grads, off = [], 0
-            for p in self.params:
-                self.grads.append(self.flat_grads[off:off + p.numel()].view_as(p))
-                off += pad(p.numel())
-            self.gstruct = _params_struct(self.kind, self.grads)
+    def set_lengths(self, decode_lengths):
+        """Host copy for the C ABI + device copy for the fused loss: pinned + non_blocking, so that nothing on the
+        host waits for the stream (a pageable torch.tensor(..., device=) copy would block until the forward has
+        drained and expose the whole host cost of loss + backward)."""
+        self.len_list = [int(x) for x in decode_lengths]
+        self.len_h[:] = self.len_list
+        self.buf.len_pin.copy_(torch.tensor(self.len_list, dtype=torch.int32))
+        self.len_d.copy_(self.buf.len_pin, non_blocking=True)
+
+    # gradient storage is shared by every plan of a family
+    @property
+    def flat_grads(self):
+        return self.gstore.flat
+
+    @property
+    def grads(self):
+        return self.gstore.grads
+
+    @property
+    def gstruct(self):
+        return self.gstore.gstruct
 
     def ensure_dlog(self):
-        if self.dlog is None:
-            d = self.dims
-            ldq = (d.V + 7) // 8 * 8
-            esz = 2 if d.precision == 1 else 4
-            self.dlog = torch.empty(d.B * d.T * ldq * esz, dtype=torch.uint8, device=self.dev)
-        if self.d_alphas is None and self.alphas is not None:
-            self.d_alphas = torch.zeros_like(self.alphas)
+        buf, d = self.buf, self.dims
+        ldq = (d.V + 7) // 8 * 8
+        esz = 2 if d.precision == 1 else 4
+        if buf.dlog is None:
+            buf.dlog = torch.empty(d.B * buf.T_cap * ldq * esz, dtype=torch.uint8, device=self.dev)
+        if buf.d_alph is None and buf.alph is not None:
+            buf.d_alph = torch.zeros_like(buf.alph)
+        self.dlog = buf.dlog
+        self.d_alphas = None if buf.d_alph is None else buf.d_alph[:d.B * d.T * d.P].view(d.B, d.T, d.P)
+
+    def dlog_matrix(self):
+        """The (B*T, V) logits-gradient matrix inside the feature-type buffer."""
+        d = self.dims
+        ldq = (d.V + 7) // 8 * 8
+        ft = torch.bfloat16 if d.precision == 1 else torch.float32
+        return self.dlog.view(ft)[:d.B * d.T * ldq].view(d.B * d.T, ldq)[:, :d.V]
 
     def run(self, slot, launch):
         """Graph mode: call #1 eager (also warms lazy state: tensor maps, function attributes),
@@ -171,68 +261,107 @@ class _Plan:
         self.calls[slot] = n + 1
 
 
-_plans = collections.OrderedDict()
+class _Family:
+    """Everything the graph mode keeps for one decoder problem family = (kind, dims but T, backward wanted, dropout
+    on/off, device, parameter storage, library switches): ONE set of buffers sized for the longest caption
+    (T = L - 1), the flat gradient buffer, and one plan -- i.e. one set of captured graphs -- per T.  The graphs are
+    keyed on (B, T) only: the kernels read the decode lengths from the device, so ragged batches replay them."""
+
+    def __init__(self, kind, dims, need_bwd, params, dev):
+        self.kind, self.need_bwd, self.params, self.dev = kind, need_bwd, params, dev
+        self.buf = _Buffers(kind, _with_T(dims, dims.L - 1), need_bwd, dev)
+        self.gstore = None
+        self.plans = {}           # T (length-independent) or (T, lengths) -> _Plan
+        self.len_free = None      # None = not tried yet
+        self.pending = []         # weak references to outputs whose backward has not run yet
+        self.last_T = self.prev_T = None
+
+    def grad_store(self):
+        if self.gstore is None:
+            self.gstore = _GradStore(self.kind, self.params, self.dev)
+        return self.gstore
+
+    def backward_pending(self):
+        self.pending = [r for r in self.pending if r() is not None]
+        return bool(self.pending)
+
+    def plan(self, dims, decode_lengths):
+        key = dims.T if self.len_free is not False else (dims.T, tuple(decode_lengths))
+        plan = self.plans.get(key)
+        if plan is None:
+            plan = _Plan(self.kind, dims, self.buf, self.params, self.grad_store() if self.need_bwd else None,
+                         self.len_free is not False)
+            self.plans[key] = plan
+            if self.len_free is False and len(self.plans) > 8:      # tuple-keyed plans of a ragged stream
+                self.plans.pop(next(iter(self.plans)))
+        return plan
 
 
-def _get_plan(kind, dims, decode_lengths, need_bwd, params, dev, dropout_on):
-    key = (kind, _dims_key(dims), tuple(decode_lengths), need_bwd, dropout_on, dev.index,
-           tuple(p.data_ptr() for p in params))
-    plan = _plans.get(key)
-    if plan is None:
-        plan = _Plan(kind, dims, decode_lengths, need_bwd, params, dev)
-        _plans[key] = plan
-        while len(_plans) > _MAX_PLANS:
-            _plans.popitem(last=False)
-    else:
-        _plans.move_to_end(key)
-    return plan
+_families = collections.OrderedDict()
 
 
-_last_plan = {}      # base signature (everything but the decode lengths) -> most recent plan
-
-
-def _base_key(kind, dims, need_bwd, dropout_on, dev, params):
+def _family_key(kind, dims, need_bwd, dropout_on, dev, params):
     return (kind, dims.precision, dims.B, dims.P, dims.E, dims.A, dims.M, dims.D, dims.F, dims.S, dims.V, dims.L,
-            need_bwd, dropout_on, dev.index, tuple(p.data_ptr() for p in params))
+            need_bwd, dropout_on, dev.index, tuple(p.data_ptr() for p in params),
+            os.environ.get("CAPDEC_PERSISTENT", ""), os.environ.get("CAPDEC_FUSED_EPILOGUE", ""))
+
+
+def _get_family(kind, dims, need_bwd, dropout_on, dev, params, create=True):
+    key = _family_key(kind, dims, need_bwd, dropout_on, dev, params)
+    fam = _families.get(key)
+    if fam is None:
+        if not create:
+            return None
+        fam = _Family(kind, dims, need_bwd, params, dev)
+        _families[key] = fam
+        while len(_families) > _MAX_FAMILIES:
+            _families.popitem(last=False)
+    else:
+        _families.move_to_end(key)
+    return fam
+
+
+def _fwd_call(plan, enc, tags, caps_sorted, sort_ind, dropout_p, seed, phases):
+    lib = _lib.load()
+    if enc is not None:
+        sb, sp, se = enc.stride()
+    else:
+        sb = sp = se = 0
+    rc = lib.capdec_forward_train(
+        C.byref(plan.dims), C.byref(plan.pstruct), _lib.ptr(enc), sb, sp, se, _lib.ptr(sort_ind),
+        _lib.ptr(tags), _lib.ptr(caps_sorted), plan.len_h, float(dropout_p), int(seed) & ((1 << 63) - 1),
+        1 if plan.need_bwd else 0, phases, _lib.ptr(plan.predictions), _lib.ptr(plan.alphas),
+        _lib.ptr(plan.ws), plan.ws_bytes, _stream())
+    return rc
 
 
 def speculate(kind, module_params, enc, tags, caps_sorted, sort_ind, *, dims_kw, dropout_p=0.0, seed=0,
               precision=None):
     """Graph mode only.  The reference API hands the decode lengths back as a python list, so every forward
-    has a host sync; the host work between that sync and the first launch would leave the GPU idle.  If the
-    previous forward with the same signature (shapes, parameters) is still planned, its INPUT phase and the
-    PROLOGUE of its compute phase (nothing in them depends on the lengths' values beyond what that plan
-    already fixes) are queued here, BEFORE the caller waits for the lengths.  decoder_forward() then checks
-    the real lengths against the plan: equal -> only the rest of the compute phase is launched; different ->
-    the normal path runs and this launch was wasted work in another plan's workspace."""
+    has a host sync; the host work between that sync and the first launch would leave the GPU idle.  When the
+    last two forwards of this family had the same T (fixed-length batches, or a stable longest caption), the
+    INPUT phase and the PROLOGUE of the compute phase for that T are queued here, BEFORE the caller waits for the
+    lengths -- nothing in them depends on the lengths beyond T.  decoder_forward() then checks the real T against
+    the plan: equal -> the lengths are re-staged and only the rest of the compute phase is launched; different ->
+    the normal path runs and this launch was wasted work."""
     if not _graphs_enabled:
         return None
-    lib = _lib.load()
     B, P, E = enc.shape
     prec = precision or get_precision()
     params = [p.detach() for p in module_params]
     need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in module_params)
     probe = make_dims(kind, prec, B, 1, P, E, dims_kw.get("A", 0), dims_kw["M"], dims_kw["D"],
                       dims_kw.get("F", 0), dims_kw.get("S", 0), dims_kw["V"], caps_sorted.shape[1])
-    plan = _last_plan.get(_base_key(kind, probe, need_bwd, dropout_p > 0, enc.device, params))
-    if plan is None or not any(v is plan for v in _plans.values()):
+    fam = _get_family(kind, probe, need_bwd, dropout_p > 0, enc.device, params, create=False)
+    if fam is None or not fam.len_free or fam.last_T is None or fam.last_T != fam.prev_T or fam.backward_pending():
         return None
-    if not (enc.is_cuda and enc.dtype == torch.float32):
+    plan = fam.plans.get(fam.last_T)
+    if plan is None or plan.len_list is None or not (enc.is_cuda and enc.dtype == torch.float32):
         return None
-    sb, sp, se = enc.stride()
-    dims = plan.dims
-
-    def call(phases):
-        rc = lib.capdec_forward_train(
-            C.byref(dims), C.byref(plan.pstruct), _lib.ptr(enc), sb, sp, se, _lib.ptr(sort_ind),
-            _lib.ptr(tags), _lib.ptr(caps_sorted), plan.len_h, float(dropout_p), int(seed) & ((1 << 63) - 1),
-            1 if need_bwd else 0, phases, _lib.ptr(plan.predictions), _lib.ptr(plan.alphas),
-            _lib.ptr(plan.ws), plan.ws_bytes, _stream())
-        _lib.check(rc, "capdec_forward_train")
-
     with torch.cuda.device(enc.device):
-        call(1)
-        plan.run("pre", lambda: call(4))
+        _lib.check(_fwd_call(plan, enc, tags, caps_sorted, sort_ind, dropout_p, seed, 1), "capdec_forward_train")
+        plan.run("pre", lambda: _lib.check(_fwd_call(plan, None, None, None, None, dropout_p, seed, 4 | 16),
+                                           "capdec_forward_train"))
     return plan
 
 
@@ -242,7 +371,6 @@ class DecoderTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, meta, enc, tags, caps_sorted, sort_ind, *params):
-        lib = _lib.load()
         kind = meta["kind"]
         _require_cuda(enc, tags, caps_sorted, sort_ind, *params)
         dims = meta["dims"]
@@ -252,43 +380,77 @@ class DecoderTrainFn(torch.autograd.Function):
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise _lib.CapdecError("decoder parameters must be contiguous float32 master weights")
         need_bwd = meta["need_bwd"]
-        use_graph = _graphs_enabled
-        if use_graph:
-            plan = _get_plan(kind, dims, meta["decode_lengths"], need_bwd, params, dev,
-                             meta["dropout_p"] > 0)
-        else:
-            plan = _Plan(kind, dims, meta["decode_lengths"], need_bwd, params, dev)
-        sb, sp, se = enc.stride()
+        lengths = meta["decode_lengths"]
+        dp, seed = meta["dropout_p"], meta["seed"]
+        fam = None
+        if _graphs_enabled:
+            fam = _get_family(kind, dims, need_bwd, dp > 0, dev, params)
+            if need_bwd and fam.backward_pending():
+                # an earlier forward of this family still waits for its backward (two forwards before a backward,
+                # several losses, checkpointing): its saved activations live in the family's buffers, so this
+                # call runs eagerly on buffers of its own
+                fam = None
+        use_graph = fam is not None
 
-        def call(phases):
-            rc = lib.capdec_forward_train(
-                C.byref(dims), C.byref(plan.pstruct), _lib.ptr(enc), sb, sp, se, _lib.ptr(sort_ind),
-                _lib.ptr(tags), _lib.ptr(caps_sorted), plan.len_h, meta["dropout_p"], meta["seed"],
-                1 if need_bwd else 0, phases, _lib.ptr(plan.predictions), _lib.ptr(plan.alphas),
-                _lib.ptr(plan.ws), plan.ws_bytes, _stream())
-            _lib.check(rc, "capdec_forward_train")
+        def call(plan, phases, inputs=True):
+            if inputs:
+                rc = _fwd_call(plan, enc, tags, caps_sorted, sort_ind, dp, seed, phases)
+            else:
+                rc = _fwd_call(plan, None, None, None, None, dp, seed, phases)
+            return rc
 
         with torch.cuda.device(dev):
-            if use_graph and meta.get("spec") is plan:
-                # inputs + prologue were queued before the host waited for the lengths (speculate())
-                plan.run("rest", lambda: call(2 | 8))
-            elif use_graph:
-                call(1)                                   # input phase: reads the caller's tensors
-                plan.run("fwd", lambda: call(2))
+            if not use_graph:
+                buf = _Buffers(kind, dims, need_bwd, dev)
+                plan = _Plan(kind, dims, buf, params, _GradStore(kind, params, dev) if need_bwd else None, False)
+                plan.set_lengths(lengths)
+                _lib.check(call(plan, 3), "capdec_forward_train")
             else:
-                call(3)
-        if use_graph:
-            _last_plan[_base_key(kind, dims, need_bwd, meta["dropout_p"] > 0, dev, params)] = plan
+                plan = fam.plan(dims, lengths)
+                spec = meta.get("spec")
+                if spec is plan and plan.len_free:
+                    # inputs + prologue were queued before the host waited for the lengths (speculate()): the
+                    # lengths are re-staged (32) and the rest of the compute phase follows
+                    plan.set_lengths(lengths)
+                    _lib.check(call(plan, 32), "capdec_forward_train")
+                    plan.run("rest", lambda: _lib.check(call(plan, 2 | 8 | 16, False), "capdec_forward_train"))
+                else:
+                    plan.set_lengths(lengths)
+                    _lib.check(call(plan, 1), "capdec_forward_train")       # input phase: reads the caller's tensors
+                    if fam.len_free is None:
+                        # first forward of the family: does the shape take the length-independent launch?
+                        rc = call(plan, 2 | 16, False)
+                        if rc == -5:                                        # CAPDEC_ERR_UNSUPPORTED
+                            fam.len_free = False
+                            fam.plans.clear()
+                            plan = fam.plan(dims, lengths)
+                            plan.set_lengths(lengths)
+                            plan.run("fwd", lambda: _lib.check(call(plan, 2, False), "capdec_forward_train"))
+                        else:
+                            _lib.check(rc, "capdec_forward_train")
+                            fam.len_free = True
+                            plan.calls["fwd"] = 1
+                    elif plan.len_free:
+                        plan.run("fwd", lambda: _lib.check(call(plan, 2 | 16, False), "capdec_forward_train"))
+                    else:
+                        plan.run("fwd", lambda: _lib.check(call(plan, 2, False), "capdec_forward_train"))
+                fam.prev_T, fam.last_T = fam.last_T, dims.T
         meta.pop("spec", None)
         ctx.meta = meta
         ctx.plan = plan
+        ctx.family = fam
         ctx.use_graph = use_graph
         ctx.param_refs = meta.pop("param_refs", None)
         meta["plan"] = plan
         predictions = plan.predictions.detach() if use_graph else plan.predictions
-        if plan.alphas is None:
+        alphas = None
+        if plan.alphas is not None:
+            alphas = plan.alphas.detach() if use_graph else plan.alphas
+        if use_graph and need_bwd:
+            ctx.token = _Token()
+            fam.pending.append(weakref.ref(ctx.token))
+        if alphas is None:
             return predictions
-        alphas = plan.alphas.detach() if use_graph else plan.alphas
         return predictions, alphas
 
     @staticmethod
@@ -298,7 +460,6 @@ class DecoderTrainFn(torch.autograd.Function):
         kind, dims, dev = plan.kind, plan.dims, plan.dev
         if not plan.need_bwd:
             raise _lib.CapdecError("backward called but forward ran without save_for_backward")
-        plan.ensure_grad_buffers()
         # a .grad left over from an earlier step may ALIAS the static gradient buffer (autograd adopts the
         # views returned below without copying): this call is about to overwrite that buffer, so such a
         # gradient is detached into its own storage first (gradient accumulation stays correct)
@@ -308,42 +469,64 @@ class DecoderTrainFn(torch.autograd.Function):
             for p in ctx.param_refs:
                 if p.grad is not None and lo <= p.grad.data_ptr() < hi:
                     p.grad = p.grad.clone()
+        buf = plan.buf
         fused = meta.pop("fused_dlogits", None)    # set by FusedLossFn: gradient already in plan.dlog
         if fused:
             slot, d_pred_p, dlog_p = "bwd_fused", None, plan.dlog
             d_alphas_p = plan.d_alphas if kind != "pure_scn" else None
+            # FusedLossFn hands autograd zero-stride zeros; anything else means a SECOND consumer of the scores /
+            # alphas contributed a gradient: it is added to what the fused loss left in the buffers
+            if d_pred is not None and any(d_pred.stride()):
+                plan.dlog_matrix().add_(d_pred.reshape(dims.B * dims.T, dims.V).to(plan.dlog_matrix().dtype))
+            if d_alphas is not None and d_alphas_p is not None and any(d_alphas.stride()):
+                d_alphas_p.add_(d_alphas)
         else:
             slot, dlog_p = "bwd_generic", None
-            if plan.d_pred is None:
-                plan.d_pred = torch.zeros(dims.B, dims.T, dims.V, dtype=torch.float32, device=dev)
+            if buf.d_pred is None:
+                buf.d_pred = torch.zeros(dims.B * buf.T_cap * dims.V, dtype=torch.float32, device=dev)
+            d_pred_p = buf.d_pred[:dims.B * dims.T * dims.V].view(dims.B, dims.T, dims.V)
             if d_pred is None:
-                plan.d_pred.zero_()
+                d_pred_p.zero_()
             else:
-                plan.d_pred.copy_(d_pred)
-            d_pred_p = plan.d_pred
+                d_pred_p.copy_(d_pred)
             d_alphas_p = None
             if kind != "pure_scn":
-                if plan.d_alphas is None:
-                    plan.d_alphas = torch.zeros_like(plan.alphas)
+                if buf.d_alph is None:
+                    buf.d_alph = torch.zeros_like(buf.alph)
+                d_alphas_p = buf.d_alph[:dims.B * dims.T * dims.P].view(dims.B, dims.T, dims.P)
                 if d_alphas is None:
-                    plan.d_alphas.zero_()
+                    d_alphas_p.zero_()
                 else:
-                    plan.d_alphas.copy_(d_alphas)
-                d_alphas_p = plan.d_alphas
+                    d_alphas_p.copy_(d_alphas)
 
-        def call():
+        def call(phases):
             rc = lib.capdec_backward(
-                C.byref(dims), C.byref(plan.pstruct), plan.len_h, meta["dropout_p"], _lib.ptr(d_pred_p),
-                _lib.ptr(dlog_p), _lib.ptr(d_alphas_p), _lib.ptr(plan.alphas), C.byref(plan.gstruct),
-                _lib.ptr(plan.ws), plan.ws_bytes, _stream())
+                C.byref(dims), C.byref(plan.pstruct), None if plan.len_free else plan.len_h, meta["dropout_p"],
+                _lib.ptr(d_pred_p), _lib.ptr(dlog_p), _lib.ptr(d_alphas_p), _lib.ptr(plan.alphas),
+                C.byref(plan.gstruct), _lib.ptr(plan.ws), plan.ws_bytes, phases, _stream())
             _lib.check(rc, "capdec_backward")
 
+        hook = _bucket_hook
         with torch.cuda.device(dev):
-            if ctx.use_graph:
-                plan.run(slot, call)
+            if hook is None:
+                if ctx.use_graph:
+                    plan.run(slot, lambda: call(0))
+                else:
+                    call(0)
             else:
-                call()
+                # stage by stage: the hook starts the all-reduce of a bucket while the next stage is being computed
+                flat = plan.flat_grads
+                nb = len(BUCKET_PHASES)
+                for i, ph in enumerate(BUCKET_PHASES):
+                    if ctx.use_graph:
+                        plan.run("%s_%d" % (slot, ph), lambda ph=ph: call(ph))
+                    else:
+                        call(ph)
+                    lo, hi = plan.gstore.bucket_slices[i]
+                    hook(i, nb, flat[lo:hi])
         meta["flat_grads"] = plan.flat_grads
+        if ctx.family is not None:
+            ctx.token = None                                   # this forward's saved state is no longer needed
         # FRESH view objects: autograd's AccumulateGrad adopts an incoming gradient without a copy only when
         # nobody else holds the tensor object (returning the stored views made it clone all 23 gradients --
         # 108.7 MB of device copies per step -- and made GradReducer fall back to copy-in / copy-out around
@@ -352,11 +535,15 @@ class DecoderTrainFn(torch.autograd.Function):
         if ctx.use_graph and ctx.param_refs is not None and \
                 any(p.grad is not None for p in ctx.param_refs):
             # gradient accumulation into an existing .grad: hand out copies, the static buffer is reused
+            if hook is not None:
+                hook(-1, len(BUCKET_PHASES), plan.flat_grads)   # the reduced values are what must be copied
             grads = [g.clone() for g in grads]
-        if not ctx.use_graph:
-            plan.ws = None          # eager plans are single-use: release the workspace early
-            plan.d_pred = None
         return (None, None, None, None, None) + tuple(grads)
+
+
+class _Token:
+    """Lives as long as the autograd node of a forward whose backward has not run."""
+    __slots__ = ("__weakref__",)
 
 
 def decoder_forward(kind, module_params, enc, tags, caps_sorted, sort_ind, decode_lengths, *,
@@ -415,6 +602,10 @@ class FusedLossFn(torch.autograd.Function):
         g_dev = g_loss.detach().reshape(1).float().contiguous()
         plan = meta.get("plan") if meta is not None else None
         if plan is not None and plan.need_bwd:
+            if meta.get("fused_dlogits"):
+                # the logits gradient of ONE loss lives in the plan's buffer until the decoder's backward consumes it
+                raise _lib.CapdecError("decoder.loss() was applied twice to the outputs of one forward; use the torch "
+                                       "loss glue (pack_padded_sequence + CrossEntropyLoss) for additional losses")
             plan.ensure_dlog()
             d_alphas = plan.d_alphas if ctx.has_alphas else None
             with torch.cuda.device(dev):

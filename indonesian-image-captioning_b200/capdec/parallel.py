@@ -1,7 +1,14 @@
 """Data-parallel training glue: one process per GPU, torch.distributed (NCCL over NVLink on the
-B200 box, gloo in the CPU tests), ONE exchange per iteration -- the sum all-reduce of the decoder
+B200 box, gloo in the CPU tests), ONE exchange step per iteration -- the sum all-reduce of the decoder
 gradients.  The reference has no multi-GPU path; this is the new work BASELINE
 configs 3/5 ask for.
+
+The exchange is BUCKETED AND OVERLAPPED: capdec_backward produces the gradients in four
+stages (fc | reverse loop -> weight_ia + embedding -> other cell weights -> attention / init) into one flat
+buffer laid out in that order; after each stage has been queued, `GradReducer` records an event on the compute
+stream and issues the all-reduce of that bucket on a side stream, so it runs while the next stage's GEMMs are
+still computing.  Only the last (smallest) bucket's all-reduce is exposed.  `allreduce()` after
+`loss.backward()` then merely makes the compute stream wait for the side stream.
 
 Loss scaling contract (see CaptionDecoderBase.loss): every rank divides its cross-entropy sum by
 the GLOBAL token count and its alpha regulariser by world_size, so the SUM of the per-rank
@@ -11,12 +18,50 @@ import torch
 
 
 class GradReducer:
-    def __init__(self, module, dist, async_op=False):
+    def __init__(self, module, dist, overlap=True):
         self.module = module
         self.dist = dist
         self.params = [p for p in module.parameters() if p.requires_grad]
         self._flat = None
+        self._side = None
+        self._reduced = None          # flat buffer whose buckets were all-reduced by the hook in this backward
+        self._n_done = 0
+        self.overlap = bool(overlap)
+        if self.overlap:
+            from . import functional as CF
+            CF.set_grad_bucket_hook(self._on_bucket)
 
+    def close(self):
+        if self.overlap:
+            from . import functional as CF
+            CF.set_grad_bucket_hook(None)
+            self.overlap = False
+
+    # ------------------------------------------------------------------ overlapped path
+    def _on_bucket(self, index, n_buckets, flat_slice):
+        """Called by DecoderTrainFn.backward after the launches that fill bucket `index` have been queued."""
+        if index < 0:                 # "wait for what has been issued" (gradient accumulation needs the sums now)
+            self._join()
+            return
+        if flat_slice.is_cuda:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=flat_slice.device)
+            ev = torch.cuda.Event()
+            ev.record()               # on the compute stream, after this bucket's last kernel
+            self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                self.dist.all_reduce(flat_slice, op=self.dist.ReduceOp.SUM)
+        else:
+            self.dist.all_reduce(flat_slice, op=self.dist.ReduceOp.SUM)
+        self._n_done = index + 1
+        if index == n_buckets - 1:
+            self._reduced = flat_slice.untyped_storage().data_ptr()
+
+    def _join(self):
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+
+    # ------------------------------------------------------------------ after loss.backward()
     @staticmethod
     def _views_of(flat, grads):
         lo = flat.data_ptr()
@@ -29,11 +74,17 @@ class GradReducer:
         return 0 < total <= flat.numel()          # the buffer may pad every gradient to an aligned slot
 
     def allreduce(self, meta=None):
-        """Sum the gradients over all ranks.  Zero-copy when the backward wrote them into the flat
-        buffer of capdec.functional.DecoderTrainFn (meta['flat_grads']); otherwise one coalesced
-        copy in / copy out."""
+        """Sum the gradients over all ranks.  Overlapped mode: the buckets were already all-reduced on the side
+        stream during the backward; the compute stream waits for them.  Otherwise: zero-copy when the backward
+        wrote the gradients into the flat buffer of capdec.functional.DecoderTrainFn (meta['flat_grads']), else
+        one coalesced copy in / copy out."""
         grads = [p.grad for p in self.params]
         flat = meta.get("flat_grads") if isinstance(meta, dict) else None
+        if flat is not None and self._reduced is not None and \
+                self._reduced == flat.untyped_storage().data_ptr():
+            self._reduced = None
+            self._join()
+            return flat
         if flat is not None and self._views_of(flat, grads):
             self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM)
             return flat

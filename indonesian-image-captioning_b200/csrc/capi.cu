@@ -102,10 +102,12 @@ int capdec_forward_train(const CapdecDims* dims, const CapdecParams* params, con
                          float dropout_p, uint64_t dropout_seed, int save_for_backward, int phases,
                          float* predictions, float* alphas, void* workspace, size_t workspace_bytes,
                          void* stream) {
-  CAPDEC_REQUIRE(dims && params && enc && caps_sorted && decode_len_h && predictions && workspace,
-                 CAPDEC_ERR_BAD_ARG, "capdec_forward_train: null argument");
+  CAPDEC_REQUIRE(dims && params && predictions && workspace, CAPDEC_ERR_BAD_ARG, "capdec_forward_train: null argument");
+  CAPDEC_REQUIRE((phases != 0 && !(phases & 1)) || (enc && caps_sorted && decode_len_h), CAPDEC_ERR_BAD_ARG,
+                 "capdec_forward_train: the input phase needs enc, caps_sorted and decode_len_h");
   CAPDEC_REQUIRE(dims->kind == CAPDEC_PURE_SCN || alphas, CAPDEC_ERR_BAD_ARG, "alphas output is NULL");
-  CAPDEC_REQUIRE(dims->kind == CAPDEC_PURE_ATTENTION || tags, CAPDEC_ERR_BAD_ARG, "tags is NULL");
+  CAPDEC_REQUIRE(dims->kind == CAPDEC_PURE_ATTENTION || tags || (phases != 0 && !(phases & 1)), CAPDEC_ERR_BAD_ARG,
+                 "tags is NULL");
   CAPDEC_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, CAPDEC_ERR_BAD_ARG, "dropout_p out of range");
   CAPDEC_TRY(capdec_init());
   return forward_train(*dims, *params, enc, enc_sb, enc_sp, enc_se, sort_ind, tags, caps_sorted,
@@ -118,13 +120,13 @@ int capdec_backward(const CapdecDims* dims, const CapdecParams* params,
                     const int32_t* decode_len_h, float dropout_p,
                     const float* d_predictions, const void* d_logits_ft,
                     const float* d_alphas, const float* alphas, const CapdecParams* grads,
-                    void* workspace, size_t workspace_bytes, void* stream) {
-  CAPDEC_REQUIRE(dims && params && decode_len_h && grads && workspace,
-                 CAPDEC_ERR_BAD_ARG, "capdec_backward: null argument");
+                    void* workspace, size_t workspace_bytes, int phases, void* stream) {
+  CAPDEC_REQUIRE(dims && params && grads && workspace, CAPDEC_ERR_BAD_ARG, "capdec_backward: null argument");
+  CAPDEC_REQUIRE(phases >= 0 && phases <= 31, CAPDEC_ERR_BAD_ARG, "capdec_backward: bad phases");
   CAPDEC_REQUIRE(dims->kind == CAPDEC_PURE_SCN || alphas, CAPDEC_ERR_BAD_ARG, "alphas is NULL");
   CAPDEC_TRY(capdec_init());
   return backward(*dims, *params, decode_len_h, dropout_p,
-                  d_predictions, d_logits_ft, d_alphas, alphas, *grads, workspace, workspace_bytes,
+                  d_predictions, d_logits_ft, d_alphas, alphas, *grads, workspace, workspace_bytes, phases,
                   (cudaStream_t)stream);
 }
 

@@ -336,10 +336,16 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
   CAPDEC_REQUIRE(ws_bytes >= c.p.o.total, CAPDEC_ERR_WORKSPACE, "workspace %zu < %zu", ws_bytes,
                  c.p.o.total);
   CAPDEC_REQUIRE(((uintptr_t)workspace % 256) == 0, CAPDEC_ERR_BAD_ARG, "workspace must be 256-B aligned");
-  CAPDEC_REQUIRE(len_h[0] == d.T, CAPDEC_ERR_BAD_SHAPE, "decode_len[0]=%d != T=%d", len_h[0], d.T);
-  for (int b = 1; b < d.B; ++b)
-    CAPDEC_REQUIRE(len_h[b] <= len_h[b - 1] && len_h[b] >= 1, CAPDEC_ERR_BAD_SHAPE,
-                   "decode lengths must be sorted descending and >= 1");
+  // phases bit 4 (16): LENGTH-INDEPENDENT compute phases -- the launches read the decode lengths only from the
+  // device copy the input phase staged, so one captured graph serves every batch with the same (B, T)
+  const bool len_free = (phases & 16) != 0;
+  CAPDEC_REQUIRE(len_h || (len_free && !(phases & 1)), CAPDEC_ERR_BAD_ARG, "decode_len_h is NULL");
+  if (len_h) {
+    CAPDEC_REQUIRE(len_h[0] == d.T, CAPDEC_ERR_BAD_SHAPE, "decode_len[0]=%d != T=%d", len_h[0], d.T);
+    for (int b = 1; b < d.B; ++b)
+      CAPDEC_REQUIRE(len_h[b] <= len_h[b - 1] && len_h[b] >= 1, CAPDEC_ERR_BAD_SHAPE,
+                     "decode lengths must be sorted descending and >= 1");
+  }
   c.ws = (uint8_t*)workspace;
   c.st = st;
   c.prec = d.precision;
@@ -349,13 +355,17 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
   const int B = d.B, T = d.T, P = d.P, E = d.E, A = d.A, M = d.M, D = d.D, F = d.F, S = d.S, V = d.V,
             NQ = p.NQ, NG1 = p.NG1;
   const int64_t R = (int64_t)B * T;
-  const bool ragged = len_h[B - 1] != T;
+  const bool ragged = len_free || len_h[B - 1] != T;
 
-  std::vector<int> bt(T);
-  for (int t = 0; t < T; ++t) {
+  std::vector<int> bt(T, B);
+  for (int t = 0; t < T && !len_free; ++t) {
     int n = 0;
     while (n < B && len_h[n] > t) ++n;
     bt[t] = n;
+  }
+  if ((phases & 32) && !(phases & 1)) {     // re-stage the decode lengths alone (after a speculative input phase)
+    CAPDEC_REQUIRE(len_h, CAPDEC_ERR_BAD_ARG, "decode_len_h is NULL");
+    CAPDEC_CUDA_OK(cudaMemcpyAsync(c.at(o.lenD), len_h, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   }
   if (phases & 1) {
     CAPDEC_CUDA_OK(cudaMemcpyAsync(c.at(o.lenD), len_h, (size_t)B * 4, cudaMemcpyHostToDevice, st));
@@ -401,6 +411,8 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     ra.dropout_p = dropout_p; ra.seed = c.at<uint64_t>(o.seedD);
     persistent = recur_fwd_supported(ra);
   }
+  CAPDEC_REQUIRE(persistent || !len_free, CAPDEC_ERR_UNSUPPORTED,
+                 "length-independent launch needs the persistent recurrence kernels (bf16, shape covered by recur.cu)");
   const int SK = pr == CAPDEC_BF16 ? -1 : 0;
   int* counters = c.at<int>(o.counters);
 
@@ -535,7 +547,17 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
 int backward(const CapdecDims& d, const CapdecParams& w,
              const int32_t* len_h, float dropout_p, const float* d_pred,
              const void* d_logits_ft, const float* d_alphas, const float* alphas,
-             const CapdecParams& g, void* workspace, size_t ws_bytes, cudaStream_t st) {
+             const CapdecParams& g, void* workspace, size_t ws_bytes, int phases, cudaStream_t st) {
+  // phases (0 = all): the backward in production order of the gradients, so that a data-parallel caller can start
+  // the all-reduce of one bucket of the flat gradient buffer while the next one is still being computed:
+  //   1  fc.weight / fc.bias and dH_fc                 (before the reverse loop)
+  //   2  the reverse-time recurrence
+  //   4  weight_ia (weight_ih) and embedding.weight    (the two largest gradients after fc)
+  //   8  the other cell weights and both cell biases
+  //   16 attention, f_beta, init_h / init_c
+  // Every phase reads only params, workspace, alphas and the d_* inputs -> each is graph-capturable on its own.
+  if (phases == 0) phases = 31;
+  const bool len_free = len_h == nullptr;   // lengths only on the device: persistent recurrence kernels required
   Ctx c;
   CAPDEC_TRY(make_plan(d, true, &c.p));
   CAPDEC_REQUIRE(ws_bytes >= c.p.o.total, CAPDEC_ERR_WORKSPACE, "workspace %zu < %zu", ws_bytes,
@@ -550,10 +572,10 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   const int B = d.B, T = d.T, P = d.P, E = d.E, A = d.A, M = d.M, D = d.D, F = d.F, S = d.S, V = d.V,
             X = p.X, NQ = p.NQ, NG1 = p.NG1;
   const int64_t R = (int64_t)B * T;
-  const bool ragged = len_h[B - 1] != T;
+  const bool ragged = len_free || len_h[B - 1] != T;
   const bool drop = dropout_p > 0.f;
-  std::vector<int> bt(T);
-  for (int t = 0; t < T; ++t) {
+  std::vector<int> bt(T, B);
+  for (int t = 0; t < T && !len_free; ++t) {
     int n = 0;
     while (n < B && len_h[n] > t) ++n;
     bt[t] = n;
@@ -565,9 +587,11 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   if (d_logits_ft) { dlog = d_logits_ft; lddl = p.ldV; }
   else if (pr == CAPDEC_FP32) { dlog = d_pred; lddl = V; }
   else {
-    CAPDEC_TRY(copy_cast(pr, d_pred, 0, V, c.at(o.dlogF), 1, p.ldV, (int)R, V, st));
+    if (phases & 1) CAPDEC_TRY(copy_cast(pr, d_pred, 0, V, c.at(o.dlogF), 1, p.ldV, (int)R, V, st));
     dlog = c.at(o.dlogF); lddl = p.ldV;
   }
+  const bool tn = pr == CAPDEC_BF16;
+  if (phases & 1) {
   // dH_fc[(b,t), :] = dlogits . W_fc
   // K = V is long and the output small (R x D): split K four ways in bf16 mode (fp32 atomics into a zeroed buffer)
   const int sk_fc = pr == CAPDEC_BF16 ? 4 : 0;
@@ -576,7 +600,6 @@ int backward(const CapdecDims& d, const CapdecParams& w,
                 0, sk_fc));
   // fc.weight.grad = dlogits^T . dropout(H) ; fc.bias.grad = colsum(dlogits)     (rows in (b,t) order)
   // bf16: the operands stay as they are ([sample][feature]) -- transposed-operand GEMM, no transposition pass
-  const bool tn = pr == CAPDEC_BF16;
   if (tn) {
     CAPDEC_TRY(GT_(c, 3, dlog, lddl, drop ? c.at(o.Hd) : c.at(o.Hall), D, g.fc_w, D, V, D, (int)R));
   } else {
@@ -586,6 +609,7 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.fc_w, D, 0, nullptr, nullptr, 0, V, D, (int)R));
   }
   CAPDEC_TRY(colsum(pr, dlog, 1, lddl, (int)R, V, g.fc_b, 0, st));
+  }   // phase 1
 
   const int SK = pr == CAPDEC_BF16 ? -1 : 0;
   const bool fused = p.fused;
@@ -596,6 +620,9 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   const void* dba_all = p.scn ? c.ft(o.dpx, NQ) : c.at(o.dba);
   const int64_t lddba = p.scn ? p.ldPX : p.ldEA;
   int* counters = c.at<int>(o.counters);
+  const int Ppad = (P + 3) / 4 * 4;
+  const int Ri = (int)R;
+  if (phases & 2) {
   CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dh_rec), 0, (size_t)(T + 1) * B * D * 4, st));
   if (SK) {
     if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.wr), 0, (size_t)R * 4 * 2 * F * 4, st));
@@ -607,7 +634,6 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dv_acc), 0, (size_t)B * NQ * 4, st));
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dq_acc), 0, (size_t)B * NQ * 4, st));
   }
-  const int Ppad = (P + 3) / 4 * 4;
   if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.de), 0, (size_t)R * Ppad * 4, st));
   if (ragged) {
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dpre), 0, (size_t)R * 4 * D * p.fsz, st));
@@ -665,6 +691,8 @@ int backward(const CapdecDims& d, const CapdecParams& w,
       CAPDEC_TRY(recur_bwd(rb, st));
     }
   }
+  CAPDEC_REQUIRE(persistent || !len_free, CAPDEC_ERR_UNSUPPORTED,
+                 "length-independent launch needs the persistent recurrence kernels (bf16, shape covered by recur.cu)");
   // ---------------- reverse-time recurrence, one kernel chain per step ----------------
   auto cell_bwd_step = [&](int t, const float* dh_in) {
     return cell_bwd(pr, c.at<float>(o.dHfc) + (int64_t)t * D, (int64_t)T * D, dh_in, c.at<float>(o.dc),
@@ -784,96 +812,104 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     }
   }
 
-  // ---------------- weight gradients: batched GEMMs over all (t,b) rows ----------------
-  // X-side operand = (d out-feature)^T [N_out][R], W-side = (input)^T [K_in][R]; K = R rows.
-  const int Ri = (int)R;
-  // H_prev^T [D][R]: column (t,b) = h_{t-1}[b]  (t=0 -> H0, else Hall[b][t-1])
+  // H_prev^T [D][R]: column (t,b) = h_{t-1}[b]  (t=0 -> H0, else Hall[b][t-1]); used by phases 8 and 16
   CAPDEC_TRY(transpose_cast(pr, c.at(o.H0), 1, c.at(o.tC), 1, 1, B, D, 0, p.ldD, p.ldR, 0, 1, st));
   if (T > 1)
     CAPDEC_TRY(transpose_cast(pr, c.at(o.Hall), 1, c.ft(o.tC, B), 1, T - 1, B, D, D, (int64_t)T * D, p.ldR,
                               B, 1, st));
-  // bias_ih.grad == bias_hh.grad = colsum(dpre)
-  CAPDEC_TRY(colsum(pr, c.at(o.dpre), 1, 4 * D, Ri, 4 * D, g.b_ih, 0, st));
-  CAPDEC_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * D * 4, cudaMemcpyDeviceToDevice, st));
-  if (tn) {
-    if (p.scn) {
-      // weight_ic.grad[:, gF:(g+1)F] = dpre_g^T . (u_g*v_g) ; weight_hc.grad likewise with (p_g*q_g)
-      CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), 4 * D, c.at(o.m), 2 * F, g.w_ic, NQ, D, F, Ri, 4, D, R * 2 * F, F));
-      CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), 4 * D, c.ft(o.m, F), 2 * F, g.w_hc, NQ, D, F, Ri, 4, D, R * 2 * F, F));
-      // weight_ha.grad [D][4F] = H_prev^T . dp
-      CAPDEC_TRY(GT_(c, 1, c.at(o.tC), p.ldR, dp_all, lddp, g.w_ha, NQ, D, NQ, Ri));
-      // weight_ia.grad [X][4F] = [Xe | z]^T . du
-      CAPDEC_TRY(GT_(c, 3, c.at(o.Xe), p.ldM, c.at(o.du), NQ, g.w_ia, NQ, M, NQ, Ri));
-      if (p.att)
-        CAPDEC_TRY(GT_(c, 3, c.at(o.z), E, c.at(o.du), NQ, g.w_ia + (int64_t)M * NQ, NQ, E, NQ, Ri));
-      // embedding.weight.grad: dXe = du . W_ia[:M]^T, scattered to the consumed token rows
+  }   // phase 2
+
+  // ---------------- weight gradients: batched GEMMs over all (t,b) rows ----------------
+  // X-side operand = (d out-feature)^T [N_out][R], W-side = (input)^T [K_in][R]; K = R rows.
+  // bf16: the operands stay as they are ([sample][feature]) -- transposed-operand GEMM, no transposition pass
+  if (phases & 4) {
+    // ---- weight_ia.grad [X][4F] = [Xe | z]^T . du  (LSTM: weight_ih.grad [4D][X] = dpre^T . [Xe | z]) and
+    // embedding.weight.grad: dXe = du . W_ia[:M]^T, scattered to the consumed token rows ----
+    if (tn) {
+      if (p.scn) {
+        CAPDEC_TRY(GT_(c, 3, c.at(o.Xe), p.ldM, c.at(o.du), NQ, g.w_ia, NQ, M, NQ, Ri));
+        if (p.att)
+          CAPDEC_TRY(GT_(c, 3, c.at(o.z), E, c.at(o.du), NQ, g.w_ia + (int64_t)M * NQ, NQ, E, NQ, Ri));
+        CAPDEC_TRY(G_(c, c.at(o.du), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
+      } else {
+        CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), NQ, c.at(o.Xe), p.ldM, g.w_ia, X, NQ, M, Ri));
+        if (p.att) CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), NQ, c.at(o.z), E, g.w_ia + M, X, NQ, E, Ri));
+        CAPDEC_TRY(G_(c, c.at(o.dpre), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
+      }
+    } else if (p.scn) {
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.du), 1, c.at(o.tB), 1, 1, Ri, NQ, 0, NQ, p.ldR, 0, 1, st));
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.Xe), 1, c.at(o.tA), 1, 1, Ri, M, 0, p.ldM, p.ldR, 0, 1, st));
+      CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia, NQ, 0, nullptr, nullptr, 0, M, NQ, Ri));
+      if (p.att) {
+        CAPDEC_TRY(transpose_cast(pr, c.at(o.z), 1, c.at(o.tA), 1, 1, Ri, E, 0, E, p.ldR, 0, 1, st));
+        CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia + (int64_t)M * NQ, NQ, 0, nullptr,
+                     nullptr, 0, E, NQ, Ri));
+      }
       CAPDEC_TRY(G_(c, c.at(o.du), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
-      // weight_ib.grad [S][4F] = s^T . sum_t dv ; weight_hb.grad = s^T . sum_t dq   (B rows: tiny)
+    } else {
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.dpre), 1, c.at(o.tA), 1, 1, Ri, 4 * D, 0, 4 * D, p.ldR, 0, 1, st));
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.Xe), 1, c.at(o.tB), 1, 1, Ri, M, 0, p.ldM, p.ldR, 0, 1, st));
+      CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia, X, 0, nullptr, nullptr, 0, NQ, M, Ri));
+      if (p.att) {
+        CAPDEC_TRY(transpose_cast(pr, c.at(o.z), 1, c.at(o.tB), 1, 1, Ri, E, 0, E, p.ldR, 0, 1, st));
+        CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia + M, X, 0, nullptr, nullptr, 0, NQ, E, Ri));
+      }
+      CAPDEC_TRY(G_(c, c.at(o.dpre), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
+    }
+    if (g.emb) {
+      CAPDEC_CUDA_OK(cudaMemsetAsync(g.emb, 0, (size_t)V * M * 4, st));
+      CAPDEC_TRY(embedding_scatter_add(c.at<float>(o.dXe), M, c.at<int64_t>(o.capsD), d.L, c.at<int32_t>(o.lenD), g.emb, B, T,
+                                       M, V, st));
+    }
+  }   // phase 4
+
+  if (phases & 8) {
+    // bias_ih.grad == bias_hh.grad = colsum(dpre)
+    CAPDEC_TRY(colsum(pr, c.at(o.dpre), 1, 4 * D, Ri, 4 * D, g.b_ih, 0, st));
+    CAPDEC_CUDA_OK(cudaMemcpyAsync(g.b_hh, g.b_ih, (size_t)4 * D * 4, cudaMemcpyDeviceToDevice, st));
+    if (tn) {
+      if (p.scn) {
+        // weight_ic.grad[:, gF:(g+1)F] = dpre_g^T . (u_g*v_g) ; weight_hc.grad likewise with (p_g*q_g)
+        CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), 4 * D, c.at(o.m), 2 * F, g.w_ic, NQ, D, F, Ri, 4, D, R * 2 * F, F));
+        CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), 4 * D, c.ft(o.m, F), 2 * F, g.w_hc, NQ, D, F, Ri, 4, D, R * 2 * F, F));
+        // weight_ha.grad [D][4F] = H_prev^T . dp
+        CAPDEC_TRY(GT_(c, 1, c.at(o.tC), p.ldR, dp_all, lddp, g.w_ha, NQ, D, NQ, Ri));
+      } else {
+        // LSTM: weight_hh.grad [4D][D] = dpre^T . H_prev
+        CAPDEC_TRY(GT_(c, 2, c.at(o.dpre), NQ, c.at(o.tC), p.ldR, g.w_ha, D, NQ, D, Ri));
+      }
+    } else {
+      // dpre^T [4D][R]
+      CAPDEC_TRY(transpose_cast(pr, c.at(o.dpre), 1, c.at(o.tA), 1, 1, Ri, 4 * D, 0, 4 * D, p.ldR, 0, 1, st));
+      if (p.scn) {
+        // m^T: per gate [2F][R]
+        for (int gg = 0; gg < 4; ++gg)
+          CAPDEC_TRY(transpose_cast(pr, c.ft(o.m, (int64_t)gg * R * 2 * F), 1,
+                                    c.ft(o.tB, (int64_t)gg * 2 * F * p.ldR), 1, 1, Ri, 2 * F, 0, 2 * F,
+                                    p.ldR, 0, 1, st));
+        CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ic, NQ, 0, nullptr, nullptr, 0, D, F, Ri, 0, 4,
+                     (int64_t)D * p.ldR, (int64_t)2 * F * p.ldR, F));
+        CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.ft(o.tB, (int64_t)F * p.ldR), p.ldR, g.w_hc, NQ, 0, nullptr, nullptr,
+                     0, D, F, Ri, 0, 4, (int64_t)D * p.ldR, (int64_t)2 * F * p.ldR, F));
+        // weight_ha.grad [D][4F] = H_prev^T . dp
+        CAPDEC_TRY(transpose_cast(pr, dp_all, 1, c.at(o.tB), 1, 1, Ri, NQ, 0, lddp, p.ldR, 0, 1, st));
+        CAPDEC_TRY(G_(c, c.at(o.tC), p.ldR, c.at(o.tB), p.ldR, g.w_ha, NQ, 0, nullptr, nullptr, 0, D, NQ, Ri));
+      } else {
+        CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tC), p.ldR, g.w_ha, D, 0, nullptr, nullptr, 0, NQ, D, Ri));
+      }
+    }
+    if (p.scn) {
+      // weight_ib.grad [S][4F] = s^T . sum_t dv ; weight_hb.grad = s^T . sum_t dq   (B rows: tiny; the tag matrix
+      // as the forward saw it: the feature-type copy kept in the workspace)
       CAPDEC_TRY(transpose_cast(pr, c.at(o.tagsF), 1, c.at(o.tA), 1, 1, B, S, 0, p.ldS, p.ldB, 0, 1, st));
       CAPDEC_TRY(transpose_cast(pr, c.at(o.dv_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
       CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_ib, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
       CAPDEC_TRY(transpose_cast(pr, c.at(o.dq_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
       CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_hb, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
-    } else {
-      // LSTM: weight_hh.grad [4D][D] = dpre^T . H_prev ; weight_ih.grad [4D][X] = dpre^T . [Xe | z]
-      CAPDEC_TRY(GT_(c, 2, c.at(o.dpre), NQ, c.at(o.tC), p.ldR, g.w_ha, D, NQ, D, Ri));
-      CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), NQ, c.at(o.Xe), p.ldM, g.w_ia, X, NQ, M, Ri));
-      if (p.att) CAPDEC_TRY(GT_(c, 3, c.at(o.dpre), NQ, c.at(o.z), E, g.w_ia + M, X, NQ, E, Ri));
-      CAPDEC_TRY(G_(c, c.at(o.dpre), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
     }
-  } else {
-  // dpre^T [4D][R]
-  CAPDEC_TRY(transpose_cast(pr, c.at(o.dpre), 1, c.at(o.tA), 1, 1, Ri, 4 * D, 0, 4 * D, p.ldR, 0, 1, st));
-  if (p.scn) {
-    // m^T: per gate [2F][R]
-    for (int gg = 0; gg < 4; ++gg)
-      CAPDEC_TRY(transpose_cast(pr, c.ft(o.m, (int64_t)gg * R * 2 * F), 1,
-                                c.ft(o.tB, (int64_t)gg * 2 * F * p.ldR), 1, 1, Ri, 2 * F, 0, 2 * F,
-                                p.ldR, 0, 1, st));
-    // weight_ic.grad[:, gF:(g+1)F] = dpre_g^T . (u_g*v_g) ; weight_hc.grad likewise with (p_g*q_g)
-    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ic, NQ, 0, nullptr, nullptr, 0, D, F, Ri, 0, 4,
-                 (int64_t)D * p.ldR, (int64_t)2 * F * p.ldR, F));
-    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.ft(o.tB, (int64_t)F * p.ldR), p.ldR, g.w_hc, NQ, 0, nullptr, nullptr,
-                 0, D, F, Ri, 0, 4, (int64_t)D * p.ldR, (int64_t)2 * F * p.ldR, F));
-    // weight_ha.grad [D][4F] = H_prev^T . dp
-    CAPDEC_TRY(transpose_cast(pr, dp_all, 1, c.at(o.tB), 1, 1, Ri, NQ, 0, lddp, p.ldR, 0, 1, st));
-    CAPDEC_TRY(G_(c, c.at(o.tC), p.ldR, c.at(o.tB), p.ldR, g.w_ha, NQ, 0, nullptr, nullptr, 0, D, NQ, Ri));
-    // weight_ia.grad [X][4F] = [Xe | z]^T . du
-    CAPDEC_TRY(transpose_cast(pr, c.at(o.du), 1, c.at(o.tB), 1, 1, Ri, NQ, 0, NQ, p.ldR, 0, 1, st));
-    CAPDEC_TRY(transpose_cast(pr, c.at(o.Xe), 1, c.at(o.tA), 1, 1, Ri, M, 0, p.ldM, p.ldR, 0, 1, st));
-    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia, NQ, 0, nullptr, nullptr, 0, M, NQ, Ri));
-    if (p.att) {
-      CAPDEC_TRY(transpose_cast(pr, c.at(o.z), 1, c.at(o.tA), 1, 1, Ri, E, 0, E, p.ldR, 0, 1, st));
-      CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia + (int64_t)M * NQ, NQ, 0, nullptr,
-                   nullptr, 0, E, NQ, Ri));
-    }
-    // embedding.weight.grad: dXe = du . W_ia[:M]^T, scattered to the consumed token rows
-    CAPDEC_TRY(G_(c, c.at(o.du), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
-    // weight_ib.grad [S][4F] = s^T . sum_t dv ; weight_hb.grad = s^T . sum_t dq
-    // (the tag matrix as the forward saw it: the feature-type copy kept in the workspace)
-    CAPDEC_TRY(transpose_cast(pr, c.at(o.tagsF), 1, c.at(o.tA), 1, 1, B, S, 0, p.ldS, p.ldB, 0, 1, st));
-    CAPDEC_TRY(transpose_cast(pr, c.at(o.dv_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
-    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_ib, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
-    CAPDEC_TRY(transpose_cast(pr, c.at(o.dq_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
-    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_hb, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
-  } else {
-    // LSTM: weight_hh.grad [4D][D] = dpre^T . H_prev ; weight_ih.grad [4D][X] = dpre^T . [Xe | z]
-    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tC), p.ldR, g.w_ha, D, 0, nullptr, nullptr, 0, NQ, D, Ri));
-    CAPDEC_TRY(transpose_cast(pr, c.at(o.Xe), 1, c.at(o.tB), 1, 1, Ri, M, 0, p.ldM, p.ldR, 0, 1, st));
-    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia, X, 0, nullptr, nullptr, 0, NQ, M, Ri));
-    if (p.att) {
-      CAPDEC_TRY(transpose_cast(pr, c.at(o.z), 1, c.at(o.tB), 1, 1, Ri, E, 0, E, p.ldR, 0, 1, st));
-      CAPDEC_TRY(G_(c, c.at(o.tA), p.ldR, c.at(o.tB), p.ldR, g.w_ia + M, X, 0, nullptr, nullptr, 0, NQ, E, Ri));
-    }
-    CAPDEC_TRY(G_(c, c.at(o.dpre), NQ, c.at(o.Wp_xin), p.ldNQ, c.at(o.dXe), M, 0, nullptr, nullptr, 0, Ri, M, NQ));
-  }
-  }
-  if (g.emb) {
-    CAPDEC_CUDA_OK(cudaMemsetAsync(g.emb, 0, (size_t)V * M * 4, st));
-    CAPDEC_TRY(embedding_scatter_add(c.at<float>(o.dXe), M, c.at<int64_t>(o.capsD), d.L, c.at<int32_t>(o.lenD), g.emb, B, T,
-                                     M, V, st));
-  }
+  }   // phase 8
 
+  if (phases & 16) {
   if (p.att) {
     // f_beta / decoder_att: [dbeta_pre | datt2]^T . H_prev
     if (tn) {
@@ -913,6 +949,7 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   CAPDEC_TRY(transpose_cast(pr, c.at(o.dc), 0, c.at(o.tA), 1, 1, B, D, 0, D, p.ldB, 0, 1, st));
   CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.init_c_w, E, 0, nullptr, nullptr, 0, D, E, B));
   CAPDEC_TRY(colsum(pr, c.at(o.dc), 0, D, B, D, g.init_c_b, 0, st));
+  }   // phase 16
   return CAPDEC_OK;
 }
 

@@ -199,5 +199,5 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
 int backward(const CapdecDims& d, const CapdecParams& w,
              const int32_t* len_h, float dropout_p, const float* d_pred,
              const void* d_logits_ft, const float* d_alphas, const float* alphas,
-             const CapdecParams& g, void* workspace, size_t ws_bytes, cudaStream_t st);
+             const CapdecParams& g, void* workspace, size_t ws_bytes, int phases, cudaStream_t st);
 }  // namespace capdec

@@ -76,7 +76,29 @@ def _worker(rank, world, port, ret):
         out2 = GradReducer(m2, dist).allreduce({"flat_grads": padded})
         ok_zero_copy = ok_zero_copy and out2.data_ptr() == padded.data_ptr() and \
             bool((m2.a.grad == 3).all()) and bool((m2.b.grad == 30).all()) and float(padded[4:64].abs().sum()) == 0.0
-        ret[rank] = (err, ok_zero_copy, shard_range(5000, rank, world))
+        # overlapped path: the decoder's backward hands the reducer one bucket of the flat buffer at a time (production
+        # order); allreduce() afterwards must NOT reduce a second time
+        from capdec import functional as CF
+        flatb = torch.zeros(256)
+        m3 = Two()
+        m3.a.grad = flatb[0:4]
+        m3.b.grad = flatb[64:70].view(2, 3)
+        with torch.no_grad():
+            m3.a.grad.fill_(float(rank + 1))
+            m3.b.grad.fill_(10.0 * (rank + 1))
+        red3 = GradReducer(m3, dist, overlap=True)
+        assert CF._bucket_hook is not None
+        CF._bucket_hook(0, 2, flatb[0:64])
+        mid = bool((m3.a.grad == 3).all()) and bool((m3.b.grad == 10.0 * (rank + 1)).all())   # bucket 1 not yet
+        CF._bucket_hook(1, 2, flatb[64:256])
+        out3 = red3.allreduce({"flat_grads": flatb})
+        ok_overlap = mid and out3.data_ptr() == flatb.data_ptr() and bool((m3.a.grad == 3).all()) and \
+            bool((m3.b.grad == 30).all())
+        out4 = red3.allreduce({"flat_grads": flatb})          # a later call without hook activity reduces again
+        ok_overlap = ok_overlap and bool((m3.a.grad == 6).all())
+        red3.close()
+        assert CF._bucket_hook is None
+        ret[rank] = (err, ok_zero_copy and ok_overlap, shard_range(5000, rank, world))
     finally:
         dist.destroy_process_group()
 
@@ -93,3 +115,18 @@ def test_dp_gradients_sum_to_global_gradient():
         assert err < 1e-6
         assert ok
     assert ret[0][2] == (0, 2500) and ret[1][2] == (2500, 5000)
+
+
+def test_gradient_buckets_cover_every_parameter_in_production_order():
+    """The flat gradient buffer is laid out in the order capdec_backward produces the gradients (its `phases`):
+    every parameter of every decoder kind sits in exactly one bucket, fc first."""
+    from capdec import functional as CF
+    for kind in ("attention_scn", "pure_scn", "pure_attention"):
+        names = CF.param_names(kind)
+        buckets = CF.grad_buckets(kind)
+        assert len(buckets) == len(CF.BUCKET_PHASES) == 4
+        flat = [i for b in buckets for i in b]
+        assert sorted(flat) == list(range(len(names)))
+        assert [names[i] for i in buckets[0]] == ["fc.weight", "fc.bias"]
+        assert "embedding.weight" in [names[i] for i in buckets[1]]
+        assert all(names[i].startswith("decode_step.") for i in buckets[2])
