@@ -46,10 +46,11 @@ struct Plan {
     size_t Wp_fcT, Wp_cT, Wp_hq, Wp_xin, Wp_b6, Wp_hx;
     // forward activations
     size_t enc_s, att1, mean, meanF, tagsF, v, q, Xe, U, g1, awe, z, m, pre, gates, C, H0, Hall,
-        Hd, lenD, seedD, capsD, counters, att_scr, bar, Ht, zk, enc_cm;
+        Hd, lenD, seedD, capsD, counters, att_scr, bar, Ht, zk, enc_cm, scores_t;
     // backward buffers
     size_t dlogF, dHfc, dh_rec, dc, dpre, wr, du, dpx, de, dv_acc, dq_acc, dz, dba, dAtt1, dwf, dbf, dXe;
     size_t dpre_gm, duk, dpxk, att1_cm;     // chunk-major operand copies of the persistent backward (recur.cu)
+    size_t dhp, part_t;                     // ... and its per-step exchange buffers
     size_t tA, tB, tC;             // transposed-operand scratch
     size_t total;
   } o;
@@ -130,10 +131,10 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
     o.awe = take(R * E * 4);
     o.z = take(R * E * f);
   }
-  if (p->scn) {
-    o.m = take(4 * R * 2 * F * f);                    // [gate][t*B + b][u*v | p*q]
-    o.pre = take(R * 4 * D * 4);                     // per step: split-K GEMMs accumulate into zeroed slots
-  }
+  if (p->scn) o.m = take(4 * R * 2 * F * f);          // [gate][t*B + b][u*v | p*q]
+  // SCN: gate pre-activations (per step: split-K GEMMs accumulate into zeroed slots); LSTM + persistent kernel: the
+  // input-side product of the step
+  o.pre = take(R * 4 * D * 4);
   o.gates = take(R * 4 * D * 4);
   o.C = take((T + 1) * B * D * 4);
   o.H0 = take(B * p->ldD * f);
@@ -150,6 +151,7 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
     if (p->att) {
       o.zk = take(R * E * f);
       o.enc_cm = take(B * P * E * f);
+      o.scores_t = take(R * ((P + 3) / 4 * 4) * 4);    // per-step attention scores
     }
   }
   if (with_bwd) {
@@ -178,7 +180,11 @@ int make_plan(const CapdecDims& d, bool with_bwd, Plan* p) {
       o.dpre_gm = take(R * 4 * D * f);
       if (p->scn) o.duk = take(R * NQ * f);
       o.dpxk = take(R * p->ldPX * f);
-      if (p->att) o.att1_cm = take(B * P * A * f);
+      o.dhp = take(R * ((p->NQ + (p->att ? E + A : 0)) / 512 + 1) * D * 4);
+      if (p->att) {
+        o.att1_cm = take(B * P * A * f);
+        o.part_t = take(R * ((E + 255) / 256) * ((P + 3) / 4 * 4) * 4);
+      }
     }
     // transposed operands for the weight-gradient GEMMs (K = rows).  tA/tB are sized for
     // the largest pair used together, tC for the shared H_prev^T.
@@ -401,13 +407,14 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     if (p.att) {
       ra.att1 = c.at(o.att1); ra.enc = c.at(o.enc_s); ra.w_f = w.full_att_w; ra.b_f = w.full_att_b;
       ra.alphas = alphas; ra.awe = save_bwd ? c.at<float>(o.awe) : nullptr; ra.z = c.at(o.z);
-      ra.scores = c.at<float>(o.att_scr);
+      ra.scores = c.at<float>(o.scores_t);
     }
+    ra.ragged = ragged ? 1 : 0;
     ra.v = p.scn ? c.at<float>(o.v) : nullptr; ra.q = p.scn ? c.at<float>(o.q) : nullptr;
     ra.Ht = c.at(o.Ht); ra.zk = p.att ? c.at(o.zk) : nullptr; ra.enc_cm = p.att ? c.at(o.enc_cm) : nullptr;
     ra.H0 = c.at(o.H0); ra.ldH0 = p.ldD; ra.Hall = c.at(o.Hall); ra.Hd = drop ? c.at(o.Hd) : nullptr;
     ra.C = c.at<float>(o.C); ra.U = c.at<float>(o.U); ra.g1 = c.at<float>(o.g1); ra.m = p.scn ? c.at(o.m) : nullptr;
-    ra.pre = p.scn ? c.at<float>(o.pre) : nullptr; ra.gates = c.at<float>(o.gates); ra.bar = c.at<unsigned>(o.bar);
+    ra.pre = c.at<float>(o.pre); ra.gates = c.at<float>(o.gates); ra.bar = c.at<unsigned>(o.bar);
     ra.dropout_p = dropout_p; ra.seed = c.at<uint64_t>(o.seedD);
     persistent = recur_fwd_supported(ra);
   }
@@ -442,7 +449,8 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.Hall), 0, (size_t)R * D * p.fsz, st));
     if (dropout_p > 0.f) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.Hd), 0, (size_t)R * D * p.fsz, st));
     if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.z), 0, (size_t)R * E * p.fsz, st));
-    if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.m), 0, (size_t)R * 4 * 2 * F * p.fsz, st));
+    // (the persistent kernel fills m with its exchange pattern and zeroes the dead rows itself)
+    if (p.scn && !persistent) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.m), 0, (size_t)R * 4 * 2 * F * p.fsz, st));
   }
   if (fused && !p.att) {
     // pure_scn: the whole input side is non-recurrent -- u = Emb W_ia AND the left half u*v of the
@@ -667,7 +675,7 @@ int backward(const CapdecDims& d, const CapdecParams& w,
       rb.dbx = c.at(o.dba); rb.ldbx = p.ldEA; rb.dbx_off = 0;
     }
     rb.dHfc = c.at<float>(o.dHfc); rb.gates = c.at<float>(o.gates); rb.C = c.at<float>(o.C);
-    rb.dc = c.at<float>(o.dc); rb.dh_rec = c.at<float>(o.dh_rec);
+    rb.dc = c.at<float>(o.dc); rb.dh_rec = c.at<float>(o.dh_rec); rb.dhp = c.at<float>(o.dhp);
     rb.dpre = c.at(o.dpre); rb.dpre_gm = c.at(o.dpre_gm);
     rb.U = c.at<float>(o.U); rb.g1 = c.at<float>(o.g1);
     if (p.scn) {
@@ -682,7 +690,7 @@ int backward(const CapdecDims& d, const CapdecParams& w,
       RecurFwdArgs fa;        // did the forward (same dims, same switches) build the chunk-major feature copy?
       fa.att = 1; fa.lstm = p.scn ? 0 : 1; fa.B = B; fa.T = T; fa.P = P; fa.E = E; fa.A = A; fa.M = M; fa.D = D; fa.F = F;
       rb.enc = c.at(o.enc_s); rb.build_enc_cm = recur_fwd_supported(fa) ? 0 : 1;
-      rb.part = c.at<float>(o.att_scr); rb.de = c.at<float>(o.de); rb.dwf = c.at<float>(o.dwf);
+      rb.part = c.at<float>(o.part_t); rb.de = c.at<float>(o.de); rb.dwf = c.at<float>(o.dwf);
       rb.dbf = c.at<float>(o.dbf);
     }
     rb.bar = c.at<unsigned>(o.bar); rb.dropout_p = dropout_p; rb.seed = c.at<uint64_t>(o.seedD);

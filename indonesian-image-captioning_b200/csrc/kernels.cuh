@@ -108,8 +108,10 @@ struct RecurFwdArgs {
   void* zk = nullptr;                // [T][E/512][B][512] chunk-major copy of z (P3 operand)
   void* enc_cm = nullptr;            // [B][E/256][P][256] chunk-major copy of enc (built by recur_fwd)
   float* C = nullptr; float* U = nullptr; float* g1 = nullptr; float* alphas = nullptr; float* awe = nullptr;
-  void* z = nullptr; void* m = nullptr; float* pre = nullptr; float* gates = nullptr; float* scores = nullptr;
-  unsigned* bar = nullptr;           // 256 bytes: two grid-barrier counters 128 bytes apart (zeroed by recur_fwd)
+  void* z = nullptr; void* m = nullptr; float* pre = nullptr; float* gates = nullptr;
+  float* scores = nullptr;           // [T][B][pad4(P)] per-step attention scores (exchange buffer)
+  int ragged = 0;                    // some caption is shorter than T (or the lengths are unknown to the host)
+  unsigned* bar = nullptr;           // 256 bytes: abort flag of the dataflow polls (zeroed by recur_fwd)
   float dropout_p = 0.f; const uint64_t* seed = nullptr;
 };
 bool recur_fwd_supported(const RecurFwdArgs& a);     // shape / device / CAPDEC_PERSISTENT check
@@ -126,7 +128,8 @@ struct RecurBwdArgs {
   const void* Whx2 = nullptr; int64_t ldhx2 = 0;    // LSTM: Wp_b6
   void* dbx = nullptr; int64_t ldbx = 0; int dbx_off = 0;   // destination of [dbeta_pre | datt2]
   const float* dHfc = nullptr; const float* gates = nullptr; const float* C = nullptr;
-  float* dc = nullptr; float* dh_rec = nullptr;
+  float* dc = nullptr; float* dh_rec = nullptr;     // [B][D] each: out, gradients of c_0 / h_0
+  float* dhp = nullptr;              // [T][KH/512][B][D] K-chunk partials of the recurrent gradient (exchange buffer)
   void* dpre = nullptr; void* dpre_gm = nullptr;
   const float* U = nullptr; const float* g1 = nullptr; const float* v = nullptr; const float* q = nullptr;
   void* du = nullptr; void* duk = nullptr; void* dpx = nullptr; void* dpxk = nullptr;
@@ -135,7 +138,8 @@ struct RecurBwdArgs {
   const void* enc_cm = nullptr; const void* att1 = nullptr; const float* w_f = nullptr;
   void* att1_cm = nullptr;           // [B][A/64][P][64] eighth-major copy of att1 (built by recur_bwd)
   const void* enc = nullptr; int build_enc_cm = 0;   // build enc_cm from enc first (forward ran per-step kernels)
-  float* part = nullptr; float* de = nullptr; float* dwf = nullptr; float* dbf = nullptr;
+  float* part = nullptr;             // [T][B][E/256][pad4(P)] per-step partial dalpha (exchange buffer)
+  float* de = nullptr; float* dwf = nullptr; float* dbf = nullptr;
   unsigned* bar = nullptr; float dropout_p = 0.f; const uint64_t* seed = nullptr;
 };
 bool recur_bwd_supported(const RecurBwdArgs& a);

@@ -1,8 +1,8 @@
-// recur.cu -- the persistent decoder kernel: the whole teacher-forced time loop of the
-// SCN-LSTM / attention decoders in ONE cooperative launch (bf16 feature mode).
+// recur.cu -- the persistent decoder kernels: the whole teacher-forced time loop of the SCN-LSTM / attention
+// decoders, and its reverse-time gradient, in ONE cooperative launch each (bf16 feature mode).
 //
 // Reference math: models/decoders/attention_scn.py:139-156 (the `for t` loop),
-// models/scn_cell.py:52-154, models/attention.py:26-44; restated in SURVEY.md App. A.1.
+// models/scn_cell.py:52-154, models/attention.py:26-44; restated in SURVEY.md App. A.1 / A.2.
 //
 // Why: at 32 captions per GPU a decode step is ~18 MFLOP per row and 1 MB of features per
 // row -- every stage finishes in 1-3 us, so a chain of 7 dependent kernel launches per step
@@ -15,17 +15,18 @@
 //   * TWO ROW GROUPS PER CTA: batch rows are independent through the whole recurrence, so the 512
 //     threads of a CTA are two groups of 256 (group g owns rows [16 g, 16 g + 16) = one m16 tile)
 //     that run the time loop INDEPENDENTLY of each other -- own staging buffers, own mbarriers, own
-//     named barrier (bar.sync 1 + g), own grid-barrier counter -- and share only the resident weight
-//     slices.  A grid barrier costs ~1.3 us of pure latency (release-add, L2 round trips, poll);
-//     while one group waits in it the other group's phase keeps the SM busy;
-//   * a GEMM phase of a group = warp w takes 1/8 of K, reads the 16 x K/8 activation slice from the
-//     group's staging buffer (ONE TMA bulk copy per fill from a chunk-major operand copy) with
-//     16-byte loads straight into mma fragments (K permuted identically for both operands),
-//     mma.sync m16n8k16 bf16 -> fp32, 8-way reduction through shared memory, fused epilogue
+//     named barrier (bar.sync 1 + g) -- and share only the resident weight slices;
+//   * DATAFLOW, NOT BARRIERS: the phases of a step hand their results to the other CTAs through per-step
+//     buffers pre-filled with a NaN pattern; a consumer polls the data itself and multiplies straight out of
+//     the loaded registers (see "Dataflow exchange" below).  The first version separated the phases by grid
+//     barriers (6 per step, >= 1.3 us each, half of the step) and staged every operand through shared memory;
+//   * a GEMM phase of a group = warp w takes 1/8 of K, reads its 16 x K/8 activation slice from the exchange
+//     buffer with 16-byte relaxed loads straight into mma fragments (K permuted identically for both
+//     operands), mma.sync m16n8k16 bf16 -> fp32, 8-way reduction through shared memory, fused epilogue
 //     (bias, factor products u*v / p*q written as the next GEMM's operand);
 //   * attention = scores per (row, pixel) item, softmax + weighted sum + gate per (row, 256-channel
-//     chunk) item, features streamed through the staging buffers (one bulk copy per 32 pixels);
-//   * phases are separated by the group's grid barrier instead of a kernel boundary.
+//     chunk) item, features streamed through the staging buffers (one TMA bulk copy per 32 pixels, the first
+//     copies in flight while the phase still waits for its inputs).
 // tcgen05 is not used here on purpose: its 128-lane M granularity would force 8-way split-K
 // with atomics (and a seventh phase to consume the sums) for GEMMs whose whole tensor work is
 // 0.3 us per step; the batched GEMMs outside the loop (vocabulary, att1, embedding side,
@@ -127,8 +128,8 @@ struct Grp {
   Pipe pp;
   float* red;          // [REDF]
   float* al;           // [pad4(P)]
-  unsigned* bar;       // the group's grid-barrier counter
-  unsigned target;
+  unsigned* abortp;    // dataflow polls: abort flag (a poll timed out)
+  long long t_end;     // ... and the clock64 value after which a waiting poll raises it
 #ifdef CAPDEC_RECUR_FINE
   unsigned fidx;
 #endif
@@ -139,25 +140,6 @@ __device__ __forceinline__ void gsync(const Grp& G) {
   asm volatile("bar.sync %0, %1;" ::"r"(G.g + 1), "n"(GT) : "memory");
 }
 
-// grid-wide barrier of one row group (cooperative launch: all CTAs are resident): monotonically increasing
-// arrival counter.  Split in arrive / wait so that loads which do not depend on the other CTAs are issued in
-// between.
-__device__ __forceinline__ void grid_arrive(const Grp& G) {
-  gsync(G);
-  if (G.tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(G.bar), "r"(1u) : "memory");
-}
-__device__ __forceinline__ void grid_wait(Grp& G) {
-  G.target += gridDim.x;
-  if (G.tid == 0) {
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(G.bar) : "memory");
-    } while (v < G.target);
-    fence_proxy_async();
-  }
-  gsync(G);
-}
-
 // the group's leader copies `bytes` contiguous bytes into stage s
 __device__ __forceinline__ void stage_fill(const Grp& G, int s, const void* src, uint32_t bytes) {
   if (G.tid == 0) {
@@ -166,34 +148,111 @@ __device__ __forceinline__ void stage_fill(const Grp& G, int s, const void* src,
   }
 }
 
-// One GEMM job of a row group: NH * 16 output features with the full K:
+// =====================================================================================
+// Dataflow exchange between CTAs: NO grid barriers in the forward time loop.
+// Whatever one CTA hands to the others inside the loop (h_t, att2 | beta_pre, the attention scores, z, the factor
+// products m, the gate pre-activations) lives in a PER-STEP buffer that the launcher fills with an all-ones bit
+// pattern (0xFFFF per bf16 / 0xFFFFFFFF per float: a NaN encoding arithmetic never produces -- cvt.rn and the FPU
+// emit the canonical 0x7FFF / 0x7FFFFFFF).  A consumer polls THE DATA ITSELF with relaxed gpu-scope loads until no
+// element shows the pattern and multiplies straight out of the loaded registers: no arrival counter, no release /
+// acquire fence pair, no staging copy -- the hand-off costs one L2 round trip after the producer's store has landed
+// (a grid barrier + bulk copy was >= 3 100 cycles, tools/barrier_bench.cu).  Stores to these buffers are relaxed
+// gpu-scope stores; every element is written once by exactly one thread and never changes afterwards, so a value
+// that is not the pattern is final.  All CTAs are co-resident (cooperative launch) and every phase only waits for
+// data of earlier phases, so the waits cannot form a cycle.  A poll that is still waiting ~2 s after the launch
+// raises the abort flag (first word of `bar`), which makes every other poll give up too: the kernel then ends with
+// garbage instead of hanging the device.
+// =====================================================================================
+constexpr uint32_t SENT = 0xFFFFFFFFu;
+constexpr long long POLL_LIMIT_CYCLES = 4000000000ll;
+
+__device__ __forceinline__ uint4 ldx16(const void* p) {
+  uint4 r;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint32_t ldx4(const void* p) {
+  uint32_t r;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void stx16(void* p, const uint4& v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void stx4(void* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stx4f(float* p, float v) { stx4(p, __float_as_uint(v)); }
+__device__ __forceinline__ void stx2(bf16* p, bf16 v) {
+  asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"(__bfloat16_as_ushort(v)) : "memory");
+}
+// any bf16 lane / any float of the 16 bytes still the fill pattern?
+__device__ __forceinline__ bool sent16(const uint4& v) {
+  return (__vcmpeq2(v.x, SENT) | __vcmpeq2(v.y, SENT) | __vcmpeq2(v.z, SENT) | __vcmpeq2(v.w, SENT)) != 0u;
+}
+__device__ __forceinline__ bool sent32(const uint4& v) { return v.x == SENT || v.y == SENT || v.z == SENT || v.w == SENT; }
+
+// called every 64 spins of a poll loop: true -> give up (somebody timed out, or this poll just did)
+__device__ __noinline__ bool poll_stalled(unsigned* abortp, long long t_end) {
+  if (ldx4(abortp) != 0u) return true;
+  if (clock64() > t_end) {
+    stx4(abortp, 1u);
+    return true;
+  }
+  return false;
+}
+template <bool F32>
+__device__ __forceinline__ uint4 poll16(const Grp& G, const void* p, uint4 v) {
+  unsigned spins = 0;
+  while (F32 ? sent32(v) : sent16(v)) {
+    if ((++spins & 63u) == 0u && poll_stalled(G.abortp, G.t_end)) break;
+    v = ldx16(p);
+  }
+  return v;
+}
+template <bool F32>
+__device__ __forceinline__ uint4 poll16(const Grp& G, const void* p) { return poll16<F32>(G, p, ldx16(p)); }
+__device__ __forceinline__ float poll4f(const Grp& G, const float* p) {
+  uint32_t v = ldx4(p);
+  unsigned spins = 0;
+  while (v == SENT) {
+    if ((++spins & 63u) == 0u && poll_stalled(G.abortp, G.t_end)) break;
+    v = ldx4(p);
+  }
+  return __uint_as_float(v);
+}
+
+// One GEMM job of a row group with the activation operand taken STRAIGHT FROM THE EXCHANGE BUFFER in global memory
+// (see above) into mma fragments: NH * 16 output features with the full K,
 //   out[h] = sum_k A[row, k] * W[h*16 + j, k]       (row = G.tid / 16, j = G.tid % 16)
-// A arrives in `nfill` fills of n rows x KF (= 64 * BPW * 4) bf16, each fill ONE contiguous TMA bulk copy
-// (the producers write chunk-major copies for exactly this reason), double buffered;
-// W: shared memory, rows of `wstride` bytes, resident for the whole kernel (shared by both groups).
-// Warp ks multiplies the 16 rows with BPW 32-wide k blocks of every fill; each lane fetches 16 bytes
-// (8 consecutive k) per row and block with ONE LDS.128 and feeds them to two m16n8k16 mma -- the same
-// k permutation is used for the weight fragments, so no ldmatrix / transposition is needed.  The 8
-// K-slice partials meet in shared memory.
-// PRE = true: the caller already issued the (single) fill into stage s0.
-template <int NH, int BPW, bool PRE = false>
-__device__ __forceinline__ void gemm_job(Grp& G, const bf16* __restrict__ src, int64_t fill_stride, int n,
-                                         const uint8_t* Ws, int wstride, int nfill, float (&out)[NH], int s0 = 0) {
-  constexpr int KF = 64 * BPW * 4;           // K elements per fill: 8 slices x BPW blocks x 32
-  constexpr int SPF = KF * 2 * GR / STAGE;   // stages one fill occupies (1 or 2)
-  Pipe& pp = G.pp;
+// A: NF "fills" of n rows x KF (= 64 * BPW * 4) bf16, fill kf at src + kf * fill_stride, rows KF elements apart
+// (chunk-major [K/512][B][512] copies, or one dense row of 2F).  Warp ks multiplies the 16 rows with BPW 32-wide k
+// blocks of every fill; each lane fetches 16 bytes (8 consecutive k) per row and block -- the same k permutation
+// is used for the weight fragments (shared memory, resident), so no ldmatrix / transposition is needed.  One lane
+// per warp first spins on the warp's first 16 bytes (row 0 is always live), so that a waiting group costs the L2
+// one sector per warp and round trip; then all loads are issued at once and late elements are re-polled one by one.
+template <int NH, int BPW, int NF>
+__device__ __forceinline__ void gemm_job_df(Grp& G, const bf16* __restrict__ src, int64_t fill_stride, int n,
+                                           const uint8_t* Ws, int wstride, float (&out)[NH]) {
+  constexpr int KF = 64 * BPW * 4;
   const int lane = G.tid & 31;
   const int g = lane >> 2, c = lane & 3;
   const int ks = G.warp;
-  const uint32_t fill_bytes = (uint32_t)n * KF * 2;
+  const bool lo = g < n, hi = g + 8 < n;
+  const uint8_t* a_lo = reinterpret_cast<const uint8_t*>(src) + ((size_t)g * KF + ks * (BPW * 32)) * 2 + 16 * c;
+  const uint8_t* a_hi = a_lo + (size_t)8 * KF * 2;
   FSTAMP(100);
-  if (!PRE) {
-    stage_fill(G, 0, src, fill_bytes);
-    if (SPF == 1 && nfill > 1) stage_fill(G, 1, src + fill_stride, fill_bytes);
-  }
+  if (lane == 0) (void)poll16<false>(G, a_lo);
+  __syncwarp();
   FSTAMP(101);
-  // one accumulator per (n-tile, k block): legacy mma.sync has a long issue-to-result latency on sm_100, so
-  // the only dependent pair inside a fill is the two k16 halves of one block
+  uint4 alo[NF][BPW], ahi[NF][BPW];
+#pragma unroll
+  for (int kf = 0; kf < NF; ++kf)
+#pragma unroll
+    for (int j = 0; j < BPW; ++j) {
+      alo[kf][j] = lo ? ldx16(a_lo + (size_t)kf * fill_stride * 2 + j * 64) : make_uint4(0, 0, 0, 0);
+      ahi[kf][j] = hi ? ldx16(a_hi + (size_t)kf * fill_stride * 2 + j * 64) : make_uint4(0, 0, 0, 0);
+    }
   float accb[2 * NH][BPW][4];
 #pragma unroll
   for (int nt = 0; nt < 2 * NH; ++nt)
@@ -201,29 +260,21 @@ __device__ __forceinline__ void gemm_job(Grp& G, const bf16* __restrict__ src, i
     for (int j = 0; j < BPW; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) accb[nt][j][i] = 0.f;
-  const uint8_t* a_base = pp.stg + (size_t)g * (KF * 2) + ks * (BPW * 64) + 16 * c;
   const uint8_t* w_base = Ws + (size_t)g * wstride + ks * (BPW * 64) + 16 * c;
-#pragma unroll 1
-  for (int kf = 0; kf < nfill; ++kf) {
-    const int s = PRE ? s0 : SPF == 1 ? (kf & 1) : 0;
-    pipe_wait(pp, s);
-    FSTAMP(102);
-    const uint8_t* ap = a_base + s * STAGE;
+#pragma unroll
+  for (int kf = 0; kf < NF; ++kf) {
     const uint8_t* wp = w_base + (size_t)kf * KF * 2;
 #pragma unroll
     for (int j = 0; j < BPW; ++j) {
-      const uint4 alo = *reinterpret_cast<const uint4*>(ap + j * 64);
-      const uint4 ahi = *reinterpret_cast<const uint4*>(ap + 8 * (KF * 2) + j * 64);
+      if (lo) alo[kf][j] = poll16<false>(G, a_lo + (size_t)kf * fill_stride * 2 + j * 64, alo[kf][j]);
+      if (hi) ahi[kf][j] = poll16<false>(G, a_hi + (size_t)kf * fill_stride * 2 + j * 64, ahi[kf][j]);
+      const uint4 x = alo[kf][j], y = ahi[kf][j];
 #pragma unroll
       for (int nt = 0; nt < 2 * NH; ++nt) {
         const uint4 b = *reinterpret_cast<const uint4*>(wp + (size_t)nt * 8 * wstride + j * 64);
-        mma_bf16(accb[nt][j], alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
-        mma_bf16(accb[nt][j], alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
+        mma_bf16(accb[nt][j], x.x, y.x, x.y, y.y, b.x, b.y);
+        mma_bf16(accb[nt][j], x.z, y.z, x.w, y.w, b.z, b.w);
       }
-    }
-    if (kf + 2 < nfill) {
-      gsync(G);                              // every warp of the group is done with stage s
-      stage_fill(G, s, src + (int64_t)(kf + 2) * fill_stride, fill_bytes);
     }
   }
   FSTAMP(103);
@@ -253,7 +304,7 @@ __device__ __forceinline__ void gemm_job(Grp& G, const bf16* __restrict__ src, i
     for (int w = 0; w < KSL; ++w) sum += G.red[(w * GR + row) * REDLD + j];
     out[h] = sum;
   }
-  gsync(G);                                  // staging buffers and `red` are free again
+  gsync(G);                                  // `red` is free again
   FSTAMP(104);
 }
 
@@ -286,8 +337,8 @@ __device__ __forceinline__ void grp_init(Grp& G, uint8_t* stg, float* red, float
   G.pp.phase = 0;
   G.red = red + (size_t)G.g * REDF;
   G.al = al + (size_t)G.g * alw;
-  G.bar = gbar + G.g * 32;                   // counters 128 bytes apart
-  G.target = 0;
+  G.abortp = gbar + 16;
+  G.t_end = clock64() + POLL_LIMIT_CYCLES;
 #ifdef CAPDEC_RECUR_FINE
   G.fidx = 0;
 #endif
@@ -331,9 +382,9 @@ struct FwdP {
   bf16* z;                          // [T][B][E]
   bf16* zk;                         // [T][E/512][B][512]   chunk-major copy of z: the P3 operand
   bf16* m;                          // [4][R][2F]
-  float* pre;                       // [T][B][4D]
+  float* pre;                       // [T][B][4D]   (LSTM: z W_ih[:, M:]^T + Emb W_ih[:, :M]^T, [T][B][NQ])
   float* gates;                     // [T][B][4D]
-  float* scores;                    // [B][pad4(P)]
+  float* scores;                    // [T][B][pad4(P)]   per step: an exchange buffer (see "Dataflow exchange")
   unsigned* bar;                    // two counters, 128 bytes apart
   float dropout_p; const uint64_t* seed;
   long long* prof;                  // debug (CAPDEC_RECUR_PROF=1): [T][16] clock64 stamps of CTA 0, group 0
@@ -343,7 +394,15 @@ struct FwdP {
 
 // LSTM = true: the pure_attention decoder (nn.LSTMCell on [emb ; z], pure_attention.py:143-146, gate order
 // i,f,g,o): the G1 job yields [att2 | beta_pre | h W_hh^T], P3 adds z W_ih[:, M:]^T to the batched embedding
-// part, and the cell phase follows directly (no factor products, no P4).
+// part (result in `pre`), and the cell phase follows directly (no factor products, no P4).
+//
+// Phases of one step and what they wait for (dataflow, see "Dataflow exchange" above -- no grid barrier):
+//   G1     h_{t-1} (Ht)                  -> g1 = [att2 | beta_pre | p],  m[:, F:] = p*q
+//   scores att2 rows of g1               -> scores[t]          (att1 slice prefetched by TMA at the top of the step)
+//   wsum   scores[t] row, beta_pre       -> alpha, awe, z, zk  (enc chunk streamed through the staging ring)
+//   P3     zk[t]                         -> u (in place over U_emb), m[:, :F] = u*v      (LSTM: pre)
+//   P4     m[t] (both halves)            -> pre[t]
+//   cell   pre[t] (LSTM: pre + g1)       -> c_t (register + C), gates, h_t -> Hall / Hd / Ht
 template <bool ATT, int NT1, bool LSTM = false>
 __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant__ FwdP p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -392,6 +451,12 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
   const uint64_t seed = drop_p > 0.f ? __ldg(p.seed) : 0ull;
   const int a_lane = lane * 8;                         // scores: this lane's 8 attention channels (x2)
   const int nctas = gridDim.x;
+  const int nfill3 = E / KC;
+  // the cell element (row, d) of this thread is the same at every step (lengths only shrink the live prefix): the
+  // cell state never leaves the thread's register
+  const int ci = G.vcta * GT + tid;                    // i < n * D  <=>  this thread owns element (ci / D, ci % D)
+  const int cbl = ci / D, cd = ci - cbl * D;
+  float c_reg = (cbl < GR && row0 + cbl < B) ? __ldg(p.C + (int64_t)(row0 + cbl) * D + cd) : 0.f;
 
   int stamp = 0;
 #define RECUR_STAMP()                                                                                  \
@@ -408,6 +473,15 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
     const int n = __popc(__ballot_sync(0xffffffffu, lane < GR && row0 + lane < B && lens[min(row0 + lane, B - 1)] > t));
     if (n == 0) break;
     const int64_t tb = (int64_t)t * B;
+    float* const sc_t = p.scores + tb * Ppad;
+    // scores: this group's share of the (b, px) items of its rows = consecutive att1 rows = ONE bulk copy; att1 does
+    // not depend on the step, so the copy is issued NOW and lands while G1 waits for h_{t-1} and multiplies
+    const int items = ATT ? n * P : 0;
+    const int per = (items + nctas - 1) / nctas;
+    const int i0 = G.vcta * per, i1 = min(items, i0 + per);
+    const int sci = min(SCI, P > 0 ? P : 1);           // items per fill: never more than one row's worth
+    if (ATT && (p.mask & 2) && i0 < i1)
+      stage_fill(G, 0, p.att1 + ((int64_t)row0 * P + i0) * A, (uint32_t)min(sci, i1 - i0) * A * 2);
     // ================= G1: [att2 | beta_pre | p] = h_{t-1} W_cat1^T + b, and p*q -> m =================
     if (has1 && (p.mask & 1)) {
       const bf16* hprev = (t == 0 ? p.H0 : p.Ht + (tb - B) * D) + (int64_t)row0 * D;
@@ -419,7 +493,7 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
         q1[i] = (!LSTM && lrow < n && nf >= col0 && nf < NG1) ? __ldg(p.q + (int64_t)erow * NQ + (nf - col0)) : 0.f;
       }
       float out[NT1 / 2];
-      gemm_job<NT1 / 2, 2>(G, hprev, 0, n, W1s, w1s, 1, out);
+      gemm_job_df<NT1 / 2, 2, 1>(G, hprev, 0, n, W1s, w1s, out);
       if (lrow < n) {
         float* g1 = p.g1 + (tb + erow) * NG1;
 #pragma unroll
@@ -427,11 +501,11 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
           const int nf = f1 + i * 16 + ej;
           if (nf < NG1) {
             const float val = out[i] + bias1[i];
-            g1[nf] = val;
+            stx4f(g1 + nf, val);
             if (!LSTM && nf >= col0) {
               const int nn = nf - col0;
               const int gg = nn / F, f = nn - gg * F;
-              p.m[((int64_t)gg * p.R + tb + erow) * 2 * F + F + f] = __float2bfloat16_rn(val * q1[i]);
+              stx2(p.m + ((int64_t)gg * p.R + tb + erow) * 2 * F + F + f, __float2bfloat16_rn(val * q1[i]));
             }
           }
         }
@@ -446,44 +520,32 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
         const int b = row0 + bl;
         const int gg = nf / F, f = nf - gg * F;
         const float u = __ldg(p.U + (tb + b) * NQ + nf);
-        p.m[((int64_t)gg * p.R + tb + b) * 2 * F + f] = __float2bfloat16_rn(u * __ldg(p.v + (int64_t)b * NQ + nf));
+        stx2(p.m + ((int64_t)gg * p.R + tb + b) * 2 * F + f, __float2bfloat16_rn(u * __ldg(p.v + (int64_t)b * NQ + nf)));
       }
     }
     RECUR_STAMP();
     if (ATT) {
       // ================= scores e[b, px] = w_f . relu(att1[b, px, :] + att2[b, :]) + b_f =================
-      // this group's share of the (b, px) items of its rows = consecutive att1 rows: ONE bulk copy, issued
-      // while the grid barrier is crossed -- att1 does not depend on this step
-      const int items = n * P;
-      const int per = (items + nctas - 1) / nctas;
-      const int i0 = G.vcta * per, i1 = min(items, i0 + per);
-      grid_arrive(G);
-      // step-independent operands (score weights) are requested before the barrier is crossed
-      float wf[2][8];
+      if ((p.mask & 2) && i0 < i1) {
+        float wf[2][8];
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int a = cc * 256 + a_lane;
-        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-        if (a < A) {
-          w0 = __ldg(reinterpret_cast<const float4*>(p.w_f + a));
-          w1 = __ldg(reinterpret_cast<const float4*>(p.w_f + a + 4));
+        for (int cc = 0; cc < 2; ++cc) {
+          const int a = cc * 256 + a_lane;
+          float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+          if (a < A) {
+            w0 = __ldg(reinterpret_cast<const float4*>(p.w_f + a));
+            w1 = __ldg(reinterpret_cast<const float4*>(p.w_f + a + 4));
+          }
+          wf[cc][0] = w0.x; wf[cc][1] = w0.y; wf[cc][2] = w0.z; wf[cc][3] = w0.w;
+          wf[cc][4] = w1.x; wf[cc][5] = w1.y; wf[cc][6] = w1.z; wf[cc][7] = w1.w;
         }
-        wf[cc][0] = w0.x; wf[cc][1] = w0.y; wf[cc][2] = w0.z; wf[cc][3] = w0.w;
-        wf[cc][4] = w1.x; wf[cc][5] = w1.y; wf[cc][6] = w1.z; wf[cc][7] = w1.w;
-      }
-      const float bfv = __ldg(p.b_f);
-      const int sci = min(SCI, P);                     // items per fill: never more than one row's worth
+        const float bfv = __ldg(p.b_f);
 #pragma unroll 1
-      for (int base = i0; base < i1 || base == i0; base += sci) {
-        const int cnt = (p.mask & 2) ? max(0, min(sci, i1 - base)) : 0;
-        if (cnt > 0) stage_fill(G, 0, p.att1 + ((int64_t)row0 * P + base) * A, (uint32_t)cnt * A * 2);
-        if (base == i0) {
-          grid_wait(G);
-          RECUR_STAMP();
-        }
-        if (cnt > 0) {
-          // a fill's items lie in at most two consecutive rows (sci <= P): both att2 rows are requested at once,
-          // ONE L2 round trip per fill instead of one per item
+        for (int base = i0; base < i1; base += sci) {
+          const int cnt = min(sci, i1 - base);
+          if (base != i0) stage_fill(G, 0, p.att1 + ((int64_t)row0 * P + base) * A, (uint32_t)cnt * A * 2);
+          // a fill's items lie in at most two consecutive rows (sci <= P): both att2 rows (written by the G1 phase of
+          // other CTAs: polled) are requested at once
           const int bl0 = base / P;
           const int px_split = (bl0 + 1) * P - base;     // items at or beyond this index belong to row bl0 + 1
           float x2[2][2][8];
@@ -491,16 +553,27 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
           for (int r = 0; r < 2; ++r) {
             const bool need = r == 0 || px_split < cnt;
             const float* g1 = p.g1 + (tb + row0 + bl0 + r) * NG1;
+            uint4 raw[2][2];
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
               const int a = cc * 256 + a_lane;
-              float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+              raw[cc][0] = raw[cc][1] = make_uint4(0, 0, 0, 0);
               if (need && a < A) {
-                x0 = __ldcg(reinterpret_cast<const float4*>(g1 + a));
-                x1 = __ldcg(reinterpret_cast<const float4*>(g1 + a + 4));
+                raw[cc][0] = ldx16(g1 + a);
+                raw[cc][1] = ldx16(g1 + a + 4);
               }
-              x2[r][cc][0] = x0.x; x2[r][cc][1] = x0.y; x2[r][cc][2] = x0.z; x2[r][cc][3] = x0.w;
-              x2[r][cc][4] = x1.x; x2[r][cc][5] = x1.y; x2[r][cc][6] = x1.z; x2[r][cc][7] = x1.w;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int a = cc * 256 + a_lane;
+              if (need && a < A) {
+                raw[cc][0] = poll16<true>(G, g1 + a, raw[cc][0]);
+                raw[cc][1] = poll16<true>(G, g1 + a + 4, raw[cc][1]);
+              }
+              x2[r][cc][0] = __uint_as_float(raw[cc][0].x); x2[r][cc][1] = __uint_as_float(raw[cc][0].y);
+              x2[r][cc][2] = __uint_as_float(raw[cc][0].z); x2[r][cc][3] = __uint_as_float(raw[cc][0].w);
+              x2[r][cc][4] = __uint_as_float(raw[cc][1].x); x2[r][cc][5] = __uint_as_float(raw[cc][1].y);
+              x2[r][cc][6] = __uint_as_float(raw[cc][1].z); x2[r][cc][7] = __uint_as_float(raw[cc][1].w);
             }
           }
           pipe_wait(G.pp, 0);
@@ -510,7 +583,7 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
             const bool second = i >= px_split;
             const int bl = bl0 + (second ? 1 : 0);
             const int px = base + i - bl * P;
-            float s = 0.f;
+            float sacc = 0.f;
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
               const int a = cc * 256 + a_lane;
@@ -520,51 +593,40 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
                 unpack16(raw, f, bf16());
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                  s = fmaf(wf[cc][k], fmaxf(f[k] + (second ? x2[1][cc][k] : x2[0][cc][k]), 0.f), s);
+                  sacc = fmaf(wf[cc][k], fmaxf(f[k] + (second ? x2[1][cc][k] : x2[0][cc][k]), 0.f), sacc);
               }
             }
-            s = warp_sum(s);
-            if (lane == 0) p.scores[(int64_t)(row0 + bl) * Ppad + px] = s + bfv;
+            sacc = warp_sum(sacc);
+            if (lane == 0) stx4f(sc_t + (int64_t)(row0 + bl) * Ppad + px, sacc + bfv);
           }
-          if (base + sci < i1) gsync(G);
+          gsync(G);                                    // every warp is done with the staged att1 rows
         }
       }
       RECUR_STAMP();
       // ================= softmax + weighted sum over a 256-channel chunk + gate -> z =================
-      // item = (row, chunk); its pixels stream through the two stages, 32 pixels (16 KB, one bulk copy
-      // from the chunk-major feature copy) per fill; the first two fills are in flight during the barrier
-      grid_arrive(G);
+      // item = (row, chunk); its pixels stream through the two stages, 32 pixels (16 KB, one bulk copy from the
+      // chunk-major feature copy) per fill; the first two fills are in flight while the row's scores are polled
       {
         const int items_w = (p.mask & 4) ? n * chunks : 0;
         const int nfill = (P + WPXS - 1) / WPXS;
-        bool first = true;
 #pragma unroll 1
-        for (int item = G.vcta; item < items_w || first; item += nctas) {
-          const bool live = item < items_w;
-          const int rl = live ? item / chunks : 0, chunk = live ? item - rl * chunks : 0;
+        for (int item = G.vcta; item < items_w; item += nctas) {
+          const int rl = item / chunks, chunk = item - rl * chunks;
           const int row = row0 + rl;
           const bf16* src = p.enc_cm + ((int64_t)row * chunks + chunk) * P * CHUNK;
-          if (live) {
-            stage_fill(G, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
-            if (nfill > 1) stage_fill(G, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
+          stage_fill(G, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
+          if (nfill > 1) stage_fill(G, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
+          // the gate pre-activation comes from this step's G1 phase: requested now, checked in the epilogue
+          const float* g1b = p.g1 + (tb + row) * NG1 + A + chunk * CHUNK + col * 8;
+          uint4 braw0 = make_uint4(0, 0, 0, 0), braw1 = braw0;
+          if (grp == 0) {
+            braw0 = ldx16(g1b);
+            braw1 = ldx16(g1b + 4);
           }
-          // the gate pre-activation comes from this step's G1 phase (two barriers ago): requested now, used in
-          // the epilogue
-          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-          if (live && grp == 0) {
-            const float* g1 = p.g1 + (tb + row) * NG1 + A + chunk * CHUNK + col * 8;
-            b0 = __ldcg(reinterpret_cast<const float4*>(g1));
-            b1 = __ldcg(reinterpret_cast<const float4*>(g1 + 4));
-          }
-          if (first) {
-            grid_wait(G);
-            RECUR_STAMP();
-            first = false;
-          }
-          if (!live) break;
-          // softmax (every group working on the row recomputes it: P <= GT values, one per thread)
+          // softmax (every item of the row recomputes it: P <= GT values, one per thread); the scores of the row
+          // come from up to ~9 other CTAs: polled
           float sv = -INFINITY;
-          if (tid < P) sv = __ldcg(p.scores + (int64_t)row * Ppad + tid);
+          if (tid < P) sv = poll4f(G, sc_t + (int64_t)row * Ppad + tid);
           float mx = warp_max(sv);
           if (lane == 0) G.red[warp] = mx;
           gsync(G);
@@ -630,25 +692,26 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
               acc[4] += s1.x; acc[5] += s1.y; acc[6] += s1.z; acc[7] += s1.w;
             }
             const int e0 = chunk * CHUNK + col * 8;
-            const float bp[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            braw0 = poll16<true>(G, g1b, braw0);
+            braw1 = poll16<true>(G, g1b + 4, braw1);
+            const float bp[8] = {__uint_as_float(braw0.x), __uint_as_float(braw0.y), __uint_as_float(braw0.z),
+                                 __uint_as_float(braw0.w), __uint_as_float(braw1.x), __uint_as_float(braw1.y),
+                                 __uint_as_float(braw1.z), __uint_as_float(braw1.w)};
             float zv[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) zv[k] = fsigmoid(bp[k]) * acc[k];
+            const uint4 zp = pack16(zv, bf16());
+            stx16(p.zk + (((int64_t)t * (E / KC) + e0 / KC) * B + row) * KC + (e0 % KC), zp);
+            *reinterpret_cast<uint4*>(p.z + (tb + row) * E + e0) = zp;
             if (p.awe) {
               float* dst = p.awe + (tb + row) * E + e0;
               *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
               *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
             }
-            const uint4 zp = pack16(zv, bf16());
-            *reinterpret_cast<uint4*>(p.z + (tb + row) * E + e0) = zp;
-            *reinterpret_cast<uint4*>(p.zk + (((int64_t)t * (E / KC) + e0 / KC) * B + row) * KC + (e0 % KC)) = zp;
           }
           gsync(G);
         }
       }
-      RECUR_STAMP();
-      grid_arrive(G);
-      grid_wait(G);
       RECUR_STAMP();
       // ================= P3: u = Emb W_ia[:M] + z W_ia[M:], and u*v -> m =================
       if (has3 && (p.mask & 8)) {
@@ -658,77 +721,79 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
         float* U = p.U + (tb + erow) * NQ;
         const float u_emb = ok3 ? __ldg(U + nf) : 0.f;           // written by the batched GEMM before this kernel
         const float v3 = (!LSTM && ok3) ? __ldg(p.v + (int64_t)erow * NQ + nf) : 0.f;
-        float out[1];
-        gemm_job<1, 2>(G, p.zk + ((int64_t)t * (E / KC) * B + row0) * KC, (int64_t)B * KC, n, W3s, w3s, E / KC, out);
+        float out[1] = {0.f};
+        const bf16* zsrc = p.zk + ((int64_t)t * nfill3 * B + row0) * KC;
+        if (nfill3 == 4) {
+          gemm_job_df<1, 2, 4>(G, zsrc, (int64_t)B * KC, n, W3s, w3s, out);
+        } else {
+#pragma unroll 1
+          for (int kf = 0; kf < nfill3; ++kf) {
+            float part[1];
+            gemm_job_df<1, 2, 1>(G, zsrc + (int64_t)kf * B * KC, 0, n, W3s + (size_t)kf * KC * 2, w3s, part);
+            out[0] += part[0];
+          }
+        }
         if (ok3) {
           const float val = out[0] + u_emb;
-          U[nf] = val;
-          if (!LSTM) {
+          if (LSTM) {
+            stx4f(p.pre + (tb + erow) * NQ + nf, val);           // the cell phase of other CTAs reads it
+          } else {
+            U[nf] = val;                                         // kept for the backward (read by this thread only)
             const int gg = nf / F, f = nf - gg * F;
-            p.m[((int64_t)gg * p.R + tb + erow) * 2 * F + f] = __float2bfloat16_rn(val * v3);
+            stx2(p.m + ((int64_t)gg * p.R + tb + erow) * 2 * F + f, __float2bfloat16_rn(val * v3));
           }
         }
       }
       RECUR_STAMP();
     }
-    grid_arrive(G);
-    grid_wait(G);
-    RECUR_STAMP();
     if (!LSTM) {
-      // ================= P4: pre_g = m_g [W_ic_g | W_hc_g]^T  (the n x 2F operand is one bulk copy) =========
+      // ================= P4: pre_g = m_g [W_ic_g | W_hc_g]^T  (the n x 2F operand: both halves polled) =========
       if (has4 && (p.mask & 16)) {
         float out[1];
-        gemm_job<1, 4>(G, p.m + ((int64_t)gate4 * p.R + tb + row0) * 2 * F, 0, n, W4s, w4s, 1, out);
+        gemm_job_df<1, 4, 1>(G, p.m + ((int64_t)gate4 * p.R + tb + row0) * 2 * F, 0, n, W4s, w4s, out);
         const int d = d4 + ej;
-        if (lrow < n && d < D) p.pre[(tb + erow) * 4 * D + (int64_t)gate4 * D + d] = out[0];
+        if (lrow < n && d < D) stx4f(p.pre + (tb + erow) * 4 * D + (int64_t)gate4 * D + d, out[0]);
       }
-      RECUR_STAMP();
-      grid_arrive(G);
-      grid_wait(G);
       RECUR_STAMP();
     }
     // ================= LSTM pointwise (scn_cell.py:146-152), gate order i,f,o,c =================
-    {
-      const int total = (p.mask & 32) ? n * D : 0;
-      const float* c_prev = p.C + (tb + row0) * D;
-      float* c_new = p.C + (tb + B + row0) * D;
-#pragma unroll 1
-      for (int i = G.vcta * GT + tid; i < total; i += nctas * GT) {
-        const int bl = i / D, d = i - bl * D;
-        const int b = row0 + bl;
-        float x[4];
-        if (LSTM) {
-          // pre = (Emb W_ih[:M] + z W_ih[M:]) + h W_hh + b_ih + b_hh, torch gate order i,f,g,o
-          const float* ua = p.U + (tb + b) * NQ + d;
-          const float* hb = p.g1 + (tb + b) * NG1 + col0 + d;
+    if ((p.mask & 32) && cbl < n) {
+      const int b = row0 + cbl, d = cd;
+      float x[4];
+      if (LSTM) {
+        // pre = (Emb W_ih[:M] + z W_ih[M:]) + h W_hh + b_ih + b_hh, torch gate order i,f,g,o
+        const float* ua = (ATT ? p.pre : p.U) + (tb + b) * NQ + d;
+        const float* hb = p.g1 + (tb + b) * NG1 + col0 + d;
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq)
-            x[gq] = __ldcg(ua + gq * D) + __ldcg(hb + gq * D) + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
-          const float t2 = x[2]; x[2] = x[3]; x[3] = t2;        // -> i, f, o, g
-        } else {
-          const float* pre = p.pre + (tb + b) * 4 * D + d;
+        for (int gq = 0; gq < 4; ++gq)
+          x[gq] = poll4f(G, ua + gq * D) + poll4f(G, hb + gq * D) + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
+        const float t2 = x[2]; x[2] = x[3]; x[3] = t2;        // -> i, f, o, g
+      } else {
+        const float* pre = p.pre + (tb + b) * 4 * D + d;
+        uint32_t raw[4];
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq)
-            x[gq] = __ldcg(pre + gq * D) + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
+        for (int gq = 0; gq < 4; ++gq) raw[gq] = ldx4(pre + gq * D);
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          const float v = raw[gq] != SENT ? __uint_as_float(raw[gq]) : poll4f(G, pre + gq * D);
+          x[gq] = v + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
         }
-        const float ig = fsigmoid(x[0]), fg = fsigmoid(x[1]), og = fsigmoid(x[2]);
-        const float gg = ftanh(x[3]);
-        const float c = fg * __ldcg(c_prev + i) + ig * gg;
-        const float h = og * ftanh(c);
-        c_new[i] = c;
-        float* gp = p.gates + (tb + b) * 4 * D + d;
-        gp[0] = ig; gp[D] = fg; gp[2 * D] = og; gp[3 * D] = gg;
-        const int64_t ho = ((int64_t)b * T + t) * D + d;
-        const bf16 hb = __float2bfloat16_rn(h);
-        p.Hall[ho] = hb;
-        p.Ht[(tb + row0) * D + i] = hb;
-        if (drop_p > 0.f)
-          p.Hd[ho] = __float2bfloat16_rn(h * dropout_scale(seed, ((uint64_t)b * T + t) * D + d, drop_p));
       }
+      const float ig = fsigmoid(x[0]), fg = fsigmoid(x[1]), og = fsigmoid(x[2]);
+      const float gg = ftanh(x[3]);
+      const float c = fg * c_reg + ig * gg;
+      const float h = og * ftanh(c);
+      c_reg = c;
+      const bf16 hb16 = __float2bfloat16_rn(h);
+      stx2(p.Ht + (tb + b) * D + d, hb16);                    // the next step's G1 operand first
+      p.C[(tb + B + b) * D + d] = c;
+      float* gp = p.gates + (tb + b) * 4 * D + d;
+      gp[0] = ig; gp[D] = fg; gp[2 * D] = og; gp[3 * D] = gg;
+      const int64_t ho = ((int64_t)b * T + t) * D + d;
+      p.Hall[ho] = hb16;
+      if (drop_p > 0.f)
+        p.Hd[ho] = __float2bfloat16_rn(h * dropout_scale(seed, ((uint64_t)b * T + t) * D + d, drop_p));
     }
-    RECUR_STAMP();
-    grid_arrive(G);
-    grid_wait(G);
     RECUR_STAMP();
   }
   FSTAMP_FLUSH();
@@ -764,7 +829,8 @@ struct BwdP {
   const float* dHfc;                  // (B, T, D) fp32: d loss / d h_t through the vocabulary projection
   const float* gates; const float* C;
   float* dc;                          // [B][D]
-  float* dh_rec;                      // [T+1][B][D], zero on entry
+  float* dh_rec;                      // [B][D]: out, dh_0
+  float* dhp;                         // [T][KH/512][B][D] K-chunk partials of the recurrent gradient (exchange)
   bf16* dpre;                         // [T][B][4D]
   bf16* dpre_gm;                      // [T][4][B][D]
   const float* U; const float* g1; const float* v; const float* q;
@@ -777,7 +843,7 @@ struct BwdP {
   const float* awe; const float* alphas; const float* d_alphas;
   const bf16* enc_cm; const float* w_f;   // enc_cm [B][E/256][P][256]
   const bf16* att1_cm;                // [B][A/64][P][64]   eighth-major copy of att1
-  float* part;                        // [B][E/256][pad4(P)]
+  float* part;                        // [T][B][E/256][pad4(P)] (exchange)
   float* de; float* dwf; float* dbf;  // [T][B][pad4(P)], [T][B][A], [T][B]
   unsigned* bar;
   float dropout_p; const uint64_t* seed;
@@ -851,6 +917,11 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
   const int nfillP = (P + WPXS - 1) / WPXS;
   bf16* const dwv = reinterpret_cast<bf16*>(G.red);        // phase A: dawe of the item, bf16 [CHUNK]
   float* const psum = G.red + CHUNK / 2;                   // phase A: [4 K quarters][pad4(P)] partial dalpha
+  // cell element (row, d) of this thread: the same at every step, so dc never leaves its register
+  const int ci = G.vcta * GT + tid;
+  const int cbl = ci / D, cd = ci - cbl * D;
+  const bool cell_mine = cbl < GR && row0 + cbl < B;
+  float dc_reg = 0.f;
   int stamp = 0;
 #define BSTAMP() do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[t * 16 + (stamp & 15)] = clock64(); FSTAMP(stamp); ++stamp; } while (0)
 
@@ -863,42 +934,42 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
     if (n == 0) continue;
     const int64_t tb = (int64_t)t * B;
     // ================= C: LSTM pointwise backward =================
-    {
-      const int total = n * D;
-      const float* dh_in = p.dh_rec + (tb + B + row0) * D;
-      const float* c_prev = p.C + (tb + row0) * D;
-      const float* c_new = p.C + (tb + B + row0) * D;
-      float* dcp = p.dc + (int64_t)row0 * D;
-#pragma unroll 1
-      for (int i = G.vcta * GT + tid; i < total; i += nctas * GT) {
-        const int bl = i / D, d = i - bl * D;
-        const int b = row0 + bl;
-        float dh = __ldcg(dh_in + i);
-        {
-          float g = __ldg(p.dHfc + ((int64_t)b * T + t) * D + d);
-          if (drop_p > 0.f) g *= dropout_scale(seed, ((uint64_t)b * T + t) * D + d, drop_p);
-          dh += g;
-        }
-        const float* gp = p.gates + (tb + b) * 4 * D + d;
-        const float ig = __ldg(gp), fg = __ldg(gp + D), og = __ldg(gp + 2 * D), gg = __ldg(gp + 3 * D);
-        const float tc = ftanh(__ldg(c_new + i));
-        const float dcn = dcp[i] + dh * og * (1.f - tc * tc);
-        const float dpo = dh * tc * og * (1.f - og), dpg = dcn * ig * (1.f - gg * gg);
-        // pre-activation slots: i, f, o, c (SCN cell) or i, f, g, o (nn.LSTMCell)
-        const float dpv[4] = {dcn * gg * ig * (1.f - ig), dcn * __ldg(c_prev + i) * fg * (1.f - fg),
-                              LSTM ? dpg : dpo, LSTM ? dpo : dpg};
-        dcp[i] = dcn * fg;
+    // dh_t = fc gradient + the recurrent gradient of step t+1 = sum of the nkc K-chunk partials its H phase left in
+    // dhp[t+1] (polled; a row that was not live at t+1 gets none)
+    if (cell_mine && cbl < n) {
+      const int b = row0 + cbl, d = cd;
+      float dh = 0.f;
+      if (t + 1 < T && lens[b] > t + 1) {
+        const float* dp = p.dhp + (((int64_t)(t + 1) * nkc) * B + b) * D + d;
+        uint32_t raw[16];
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          const bf16 x = __float2bfloat16_rn(dpv[gq]);
-          p.dpre[(tb + b) * 4 * D + gq * D + d] = x;
-          p.dpre_gm[(((int64_t)t * 4 + gq) * B + b) * D + d] = x;
-        }
+        for (int k = 0; k < 16; ++k) raw[k] = k < nkc ? ldx4(dp + (int64_t)k * B * D) : 0u;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (k < nkc) dh += raw[k] != SENT ? __uint_as_float(raw[k]) : poll4f(G, dp + (int64_t)k * B * D);
+      }
+      {
+        float g = __ldg(p.dHfc + ((int64_t)b * T + t) * D + d);
+        if (drop_p > 0.f) g *= dropout_scale(seed, ((uint64_t)b * T + t) * D + d, drop_p);
+        dh += g;
+      }
+      const int64_t i = (int64_t)cbl * D + d;
+      const float* gp = p.gates + (tb + b) * 4 * D + d;
+      const float ig = __ldg(gp), fg = __ldg(gp + D), og = __ldg(gp + 2 * D), gg = __ldg(gp + 3 * D);
+      const float tc = ftanh(__ldg(p.C + (tb + B + row0) * D + i));
+      const float dcn = dc_reg + dh * og * (1.f - tc * tc);
+      const float dpo = dh * tc * og * (1.f - og), dpg = dcn * ig * (1.f - gg * gg);
+      // pre-activation slots: i, f, o, c (SCN cell) or i, f, g, o (nn.LSTMCell)
+      const float dpv[4] = {dcn * gg * ig * (1.f - ig), dcn * __ldg(p.C + (tb + row0) * D + i) * fg * (1.f - fg),
+                            LSTM ? dpg : dpo, LSTM ? dpo : dpg};
+      dc_reg = dcn * fg;
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        const bf16 x = __float2bfloat16_rn(dpv[gq]);
+        stx2(p.dpre_gm + (((int64_t)t * 4 + gq) * B + b) * D + d, x);      // the W / Z / H operand of other CTAs
+        p.dpre[(tb + b) * 4 * D + gq * D + d] = x;
       }
     }
-    BSTAMP();
-    grid_arrive(G);
-    grid_wait(G);
     BSTAMP();
     // ================= W: [w | r] = dpre_g [W_ic_g | W_hc_g] and the factor products =================
     if (hasW) {
@@ -918,7 +989,7 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
         }
       }
       float out[2];
-      gemm_job<2, 2>(G, p.dpre_gm + (((int64_t)t * 4 + gateW) * B + row0) * D, 0, n, WWs, wWs, 1, out);
+      gemm_job_df<2, 2, 1>(G, p.dpre_gm + (((int64_t)t * 4 + gateW) * B + row0) * D, 0, n, WWs, wWs, out);
       if (lrow < n) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -930,12 +1001,12 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             const float val = out[i];
             const bf16 x = __float2bfloat16_rn(val * fac[i]);
             if (is_w) {
+              stx2(p.duk + (((int64_t)t * nkq + n4 / KC) * B + erow) * KC + (n4 % KC), x);   // the Z operand
               p.du[(tb + erow) * NQ + n4] = x;
-              p.duk[(((int64_t)t * nkq + n4 / KC) * B + erow) * KC + (n4 % KC)] = x;
               p.dv_acc[k] = run[i] + val * act[i];
             } else {
+              stx2(p.dpxk + (((int64_t)t * nkc + n4 / KC) * B + erow) * KC + (n4 % KC), x);  // an H operand
               p.dpx[(tb + erow) * p.ldPX + n4] = x;
-              p.dpxk[(((int64_t)t * nkc + n4 / KC) * B + erow) * KC + (n4 % KC)] = x;
               p.dq_acc[k] = run[i] + val * act[i];
             }
           }
@@ -944,56 +1015,50 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
     }
     BSTAMP();
     if (ATT) {
-      if (!LSTM) {
-        grid_arrive(G);
-        grid_wait(G);
-      }
-      BSTAMP();
       // ================= Z: dz = du W_ia[M:]^T   (LSTM: dpre W_ih[:, M:]) =================
       if (hasZ) {
-        float out[1];
-        gemm_job<1, 2>(G, (LSTM ? p.dpre_gm + (int64_t)t * 4 * B * D : p.duk + (int64_t)t * nkq * B * KC) + (int64_t)row0 * KC,
-                       (int64_t)B * KC, n, WZs, wZs, nkq, out);
+        float out[1] = {0.f};
+        const bf16* zsrc = (LSTM ? p.dpre_gm + (int64_t)t * 4 * B * D : p.duk + (int64_t)t * nkq * B * KC) + (int64_t)row0 * KC;
+        if (nkq == 4) {
+          gemm_job_df<1, 2, 4>(G, zsrc, (int64_t)B * KC, n, WZs, wZs, out);
+        } else {
+#pragma unroll 1
+          for (int kf = 0; kf < nkq; ++kf) {
+            float part1[1];
+            gemm_job_df<1, 2, 1>(G, zsrc + (int64_t)kf * B * KC, 0, n, WZs + (size_t)kf * KC * 2, wZs, part1);
+            out[0] += part1[0];
+          }
+        }
         const int e = eZ0 + ej;
-        if (lrow < n && e < E) p.dz[(tb + erow) * E + e] = out[0];
+        if (lrow < n && e < E) stx4f(p.dz + (tb + erow) * E + e, out[0]);     // phase A of other CTAs polls it
       }
       BSTAMP();
       // ================= A: gate backward + partial dalpha over one 256-channel chunk =================
-      grid_arrive(G);
       {
         const int items = n * chunks;
-        bool first = true;
 #pragma unroll 1
-        for (int item = G.vcta; item < items || first; item += nctas) {
-          const bool live = item < items;
-          const int rl = live ? item / chunks : 0, chunk = live ? item - rl * chunks : 0;
+        for (int item = G.vcta; item < items; item += nctas) {
+          const int rl = item / chunks, chunk = item - rl * chunks;
           const int row = row0 + rl;
           const bf16* src = p.enc_cm + ((int64_t)row * chunks + chunk) * P * CHUNK;
-          if (live) {
-            stage_fill(G, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
-            if (nfillP > 1) stage_fill(G, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
-          }
-          // the saved forward activations (gate pre-activation, awe) do not depend on this step's barrier:
-          // requested before it is crossed
+          stage_fill(G, 0, src, (uint32_t)min(WPXS, P) * CHUNK * 2);
+          if (nfillP > 1) stage_fill(G, 1, src + (int64_t)WPXS * CHUNK, (uint32_t)min(WPXS, P - WPXS) * CHUNK * 2);
+          // the saved forward activations (gate pre-activation, awe) do not depend on this step: requested before
+          // dz is polled
           const int e0 = chunk * CHUNK + col * 8;
-          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0, a0 = b0, a1 = b0;
-          if (live) {
+          float4 b0, b1, a0, a1;
+          {
             const float* bpp = p.g1 + (tb + row) * NG1 + A + e0;
             const float* awp = p.awe + (tb + row) * E + e0;
             b0 = __ldg(reinterpret_cast<const float4*>(bpp)); b1 = __ldg(reinterpret_cast<const float4*>(bpp + 4));
             a0 = __ldg(reinterpret_cast<const float4*>(awp)); a1 = __ldg(reinterpret_cast<const float4*>(awp + 4));
           }
-          if (first) {
-            grid_wait(G);
-            BSTAMP();
-            first = false;
-          }
-          if (!live) break;
           float dawe[8];
           {
             const float* dzp = p.dz + (tb + row) * E + e0;
-            const float4 z0 = __ldcg(reinterpret_cast<const float4*>(dzp)), z1 = __ldcg(reinterpret_cast<const float4*>(dzp + 4));
-            const float dzv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+            const uint4 z0 = poll16<true>(G, dzp), z1 = poll16<true>(G, dzp + 4);
+            const float dzv[8] = {__uint_as_float(z0.x), __uint_as_float(z0.y), __uint_as_float(z0.z), __uint_as_float(z0.w),
+                                  __uint_as_float(z1.x), __uint_as_float(z1.y), __uint_as_float(z1.z), __uint_as_float(z1.w)};
             const float bp[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             const float aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             float db[8];
@@ -1005,8 +1070,8 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             }
             if (grp == 0) {
               const uint4 pk = pack16(db, bf16());
+              stx16(p.dpxk + (((int64_t)t * nkc + nkq + e0 / KC) * B + row) * KC + (e0 % KC), pk);   // an H operand
               *reinterpret_cast<uint4*>(p.dbx + (tb + row) * p.ldbx + p.dbx_off + e0) = pk;
-              *reinterpret_cast<uint4*>(p.dpxk + (((int64_t)t * nkc + nkq + e0 / KC) * B + row) * KC + (e0 % KC)) = pk;
               // dawe as the (single useful) column of the mma B operand
               *reinterpret_cast<uint4*>(dwv + col * 8) = pack16(dawe, bf16());
             }
@@ -1055,8 +1120,8 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
           }
           gsync(G);
           if (tid < P)
-            p.part[((int64_t)row * chunks + chunk) * Ppad + tid] =
-                (psum[tid] + psum[Ppad + tid]) + (psum[2 * Ppad + tid] + psum[3 * Ppad + tid]);
+            stx4f(p.part + (((int64_t)t * B + row) * chunks + chunk) * Ppad + tid,
+                  (psum[tid] + psum[Ppad + tid]) + (psum[2 * Ppad + tid] + psum[3 * Ppad + tid]));   // phase B polls it
           gsync(G);
         }
       }
@@ -1065,7 +1130,6 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
       // item = (row, 64 attention channels): the eighth-major copy att1_cm makes the item's P x 64 slab
       // contiguous (two bulk copies), datt2 / dw_f of different items are disjoint, and every item redoes the
       // row's tiny softmax backward
-      grid_arrive(G);
       {
         const int eighths = A / QW;
         const int items = n * eighths;
@@ -1091,21 +1155,24 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
           x2 = __ldg(reinterpret_cast<const float4*>(p.g1 + (tb + row) * NG1 + a0));
           w4 = __ldg(reinterpret_cast<const float4*>(p.w_f + a0));
         }
-        grid_wait(G);
-        BSTAMP();
         if (live) {
-          // dalpha = sum of the channel-chunk partials (+ external); de = alpha (dalpha - alpha . dalpha)
+          // dalpha = sum of the channel-chunk partials of phase A (other CTAs: polled) (+ external);
+          // de = alpha (dalpha - alpha . dalpha)
           if (tid < P) {
             // independent loads: all in flight together (a running sum would serialise 8 L2 round trips)
-            const float* pp0 = p.part + (int64_t)row * chunks * Ppad + tid;
+            const float* pp0 = p.part + ((int64_t)t * B + row) * chunks * Ppad + tid;
             int cc = 0;
             for (; cc + 8 <= chunks; cc += 8) {
+              uint32_t raw[8];
               float v[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) v[k] = __ldcg(pp0 + (int64_t)(cc + k) * Ppad);
+              for (int k = 0; k < 8; ++k) raw[k] = ldx4(pp0 + (int64_t)(cc + k) * Ppad);
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                v[k] = raw[k] != SENT ? __uint_as_float(raw[k]) : poll4f(G, pp0 + (int64_t)(cc + k) * Ppad);
               d += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
             }
-            for (; cc < chunks; ++cc) d += __ldcg(pp0 + (int64_t)cc * Ppad);
+            for (; cc < chunks; ++cc) d += poll4f(G, pp0 + (int64_t)cc * Ppad);
           }
           float dot = warp_sum(alp * d);
           if (lane == 0) G.red[warp] = dot;
@@ -1177,8 +1244,8 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             const int a = qa * QW + aa;
             if (which == 0) {
               const bf16 xb = __float2bfloat16_rn(sum);
+              stx2(p.dpxk + (((int64_t)t * nkc + nkq + E / KC) * B + row) * KC + a, xb);      // an H operand
               p.dbx[(tb + row) * p.ldbx + p.dbx_off + E + a] = xb;
-              p.dpxk[(((int64_t)t * nkc + nkq + E / KC) * B + row) * KC + a] = xb;
             } else {
               p.dwf[(tb + row) * A + a] = sum;
             }
@@ -1189,39 +1256,34 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
       }
     }
     BSTAMP();
-    grid_arrive(G);
-    grid_wait(G);
-    BSTAMP();
-    // ================= H: dh_{t-1} += [dp | dbeta_pre | datt2] chunk . W_hx chunk^T =================
-    // the CTA's (at most two) jobs use one staging buffer each: both operand copies are in flight at once
+    // ================= H: dh_{t-1} partial (chunk kc) = [dp | dbeta_pre | datt2] chunk . W_hx chunk^T =================
+    // K = KH is cut in 512-wide jobs (at most two per CTA); job (d-slice, kc) leaves its partial sum in dhp[t][kc],
+    // the C phase of step t-1 adds the nkc partials (no atomics, no zeroed accumulator)
     {
-      const bf16* srcH[2];
-      bool hasH[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int j = c + i * nctas;
-        hasH[i] = j < jobsH;
-        const int ds = j / nkc, kc = j - ds * nkc;
-        srcH[i] = ((LSTM && kc < nkq) ? p.dpre_gm + ((int64_t)t * 4 + kc) * B * D
-                                      : p.dpxk + ((int64_t)t * nkc + kc) * B * KC) + (int64_t)row0 * KC;
-        if (hasH[i]) stage_fill(G, i, srcH[i], (uint32_t)n * KC * 2);
-      }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        if (hasH[i]) {
-          const int j = c + i * nctas;
-          const int ds = j / nkc;
+        if (j < jobsH) {
+          const int ds = j / nkc, kc = j - ds * nkc;
+          const bf16* srcH = ((LSTM && kc < nkq) ? p.dpre_gm + ((int64_t)t * 4 + kc) * B * D
+                                                 : p.dpxk + ((int64_t)t * nkc + kc) * B * KC) + (int64_t)row0 * KC;
           float out[1];
-          gemm_job<1, 2, true>(G, srcH[i], 0, n, WHs + (size_t)i * 16 * wHs, wHs, 1, out, i);
+          gemm_job_df<1, 2, 1>(G, srcH, 0, n, WHs + (size_t)i * 16 * wHs, wHs, out);
           const int d = ds * 16 + ej;
-          if (lrow < n && d < D) atomicAdd(p.dh_rec + (tb + erow) * D + d, out[0]);
+          if (lrow < n && d < D) stx4f(p.dhp + (((int64_t)t * nkc + kc) * B + erow) * D + d, out[0]);
         }
       }
     }
     BSTAMP();
-    grid_arrive(G);
-    grid_wait(G);
-    BSTAMP();
+  }
+  // dh_0 (gradient of init_h's output) = sum of the partials of step 0; dc_0 is what is left in the register
+  if (cell_mine) {
+    const int b = row0 + cbl, d = cd;
+    float dh = 0.f;
+    const float* dp = p.dhp + (int64_t)b * D + d;
+    for (int k = 0; k < nkc; ++k) dh += poll4f(G, dp + (int64_t)k * B * D);
+    p.dh_rec[(int64_t)b * D + d] = dh;
+    p.dc[(int64_t)b * D + d] = dc_reg;
   }
   FSTAMP_FLUSH();
 #undef BSTAMP
@@ -1269,6 +1331,24 @@ void fine_dump(const char* name) {
 void fine_reset() {}
 void fine_dump(const char*) {}
 #endif
+
+// Rows (t, b) beyond a caption's length are never written inside the time loop, so in the exchange buffers they
+// keep the fill pattern (a NaN).  Two of those buffers are read over ALL rows afterwards -- m by the batched
+// weight-gradient GEMMs, g1 by the batched dAtt1 kernel -- and must hold zeros there (0 * NaN = NaN).
+__global__ void dead_rows_zero_kernel(const int32_t* __restrict__ len, int B, bf16* m, int64_t R, int twoF, float* g1,
+                                      int NG1) {
+  const int t = blockIdx.x / B, b = blockIdx.x - t * B;
+  if (t < __ldg(len + b)) return;
+  const int64_t r = (int64_t)t * B + b;
+  if (m) {
+    const int v = twoF / 8;
+    for (int i = threadIdx.x; i < 4 * v; i += blockDim.x) {
+      const int g = i / v, j = i - g * v;
+      reinterpret_cast<uint4*>(m + ((int64_t)g * R + r) * twoF)[j] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  for (int i = threadIdx.x; i < NG1 / 4; i += blockDim.x) reinterpret_cast<float4*>(g1 + r * NG1)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
 
 struct DevInfo { int sms = 0; int smem_optin = 0; bool coop = false; };
 DevInfo g_dev[64];
@@ -1378,7 +1458,21 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   CAPDEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RT, smem));
   CAPDEC_REQUIRE(per_sm >= 1, CAPDEC_ERR_CUDA, "recur_fwd: kernel does not fit one CTA per SM (smem %zu)", smem);
   CAPDEC_REQUIRE(a.ldH0 == a.D, CAPDEC_ERR_BAD_SHAPE, "recur_fwd: H0 must be dense");
+  CAPDEC_REQUIRE((int64_t)GR * a.D <= (int64_t)di->sms * GT, CAPDEC_ERR_BAD_SHAPE, "recur_fwd: one cell element per thread");
+  CAPDEC_REQUIRE(p.NG1 % 4 == 0 && (2 * a.F) % 8 == 0, CAPDEC_ERR_BAD_SHAPE, "recur_fwd: row widths");
   CAPDEC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, st));
+  // exchange buffers of the time loop: the all-ones fill pattern their consumers poll on (see "Dataflow exchange")
+  {
+    const size_t R = (size_t)p.R;
+    CAPDEC_CUDA_OK(cudaMemsetAsync(a.Ht, 0xFF, R * a.D * 2, st));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(a.g1, 0xFF, R * p.NG1 * 4, st));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(a.pre, 0xFF, R * p.NQ * 4, st));
+    if (!a.lstm) CAPDEC_CUDA_OK(cudaMemsetAsync(a.m, 0xFF, (size_t)4 * R * 2 * a.F * 2, st));
+    if (a.att) {
+      CAPDEC_CUDA_OK(cudaMemsetAsync(a.zk, 0xFF, R * a.E * 2, st));
+      CAPDEC_CUDA_OK(cudaMemsetAsync(a.scores, 0xFF, (size_t)a.T * a.B * pad4i(a.P) * 4, st));
+    }
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(di->sms, 1, 1);
@@ -1395,6 +1489,7 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   p.skew = a.att ? RECUR_SKEW_FWD : 0;
   if (const char* sk = getenv("CAPDEC_RECUR_SKEW")) p.skew = atoi(sk);
   if (const char* sk = getenv("CAPDEC_RECUR_SKEW_FWD")) p.skew = atoi(sk);
+
   const char* prof_env = getenv("CAPDEC_RECUR_PROF");
   const bool prof = prof_env && prof_env[0] == '1';
   if (prof) {
@@ -1413,6 +1508,10 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
     CAPDEC_CUDA_OK(cudaEventRecord(g_ev[1], st));
     g_timed[0] = true;
   }
+  if (a.ragged) {
+    dead_rows_zero_kernel<<<a.B * a.T, 128, 0, st>>>(a.len, a.B, a.lstm ? nullptr : (bf16*)a.m, p.R, 2 * a.F, a.g1, p.NG1);
+    CAPDEC_LAUNCH_OK();
+  }
   if (prof) {
     // debug only: synchronises.  Prints per-phase cycles of CTA 0 (work, barrier wait) for a few steps.
     std::vector<long long> h((size_t)a.T * 16 + 64);
@@ -1424,6 +1523,9 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
       for (int k = 1; k < 16 && h[t * 16 + k]; ++k) fprintf(stderr, " %lld", h[t * 16 + k] - h[t * 16 + k - 1]);
       fprintf(stderr, "\n");
     }
+    unsigned flag = 0;
+    cudaMemcpy(&flag, a.bar + 16, sizeof flag, cudaMemcpyDeviceToHost);
+    if (flag) fprintf(stderr, "recur_fwd: a dataflow poll TIMED OUT (abort flag set)\n");
     fine_dump("recur_fwd");
   }
   return CAPDEC_OK;
@@ -1478,7 +1580,7 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
   p.q = a.q; p.du = (bf16*)a.du; p.duk = (bf16*)a.duk; p.dpx = (bf16*)a.dpx; p.dpxk = (bf16*)a.dpxk;
   p.dv_acc = a.dv_acc; p.dq_acc = a.dq_acc; p.dz = a.dz; p.awe = a.awe; p.alphas = a.alphas; p.d_alphas = a.d_alphas;
   p.enc_cm = (const bf16*)a.enc_cm; p.att1_cm = (const bf16*)a.att1_cm; p.w_f = a.w_f; p.part = a.part; p.de = a.de;
-  p.dwf = a.dwf; p.dbf = a.dbf; p.bar = a.bar; p.dropout_p = a.dropout_p; p.seed = a.seed;
+  p.dwf = a.dwf; p.dbf = a.dbf; p.bar = a.bar; p.dropout_p = a.dropout_p; p.seed = a.seed; p.dhp = a.dhp;
   p.skew = a.att ? RECUR_SKEW_BWD : 0;
   if (const char* sk = getenv("CAPDEC_RECUR_SKEW")) p.skew = atoi(sk);
   if (const char* sk = getenv("CAPDEC_RECUR_SKEW_BWD")) p.skew = atoi(sk);
@@ -1495,7 +1597,22 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
     chunk_major_kernel<<<di->sms * 4, 256, 0, st>>>((const uint4*)a.att1, (uint4*)a.att1_cm, a.B, a.P, a.A, QW);
     CAPDEC_LAUNCH_OK();
   }
+  CAPDEC_REQUIRE((int64_t)GR * a.D <= (int64_t)di->sms * GT, CAPDEC_ERR_BAD_SHAPE, "recur_bwd: one cell element per thread");
   CAPDEC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, st));
+  // exchange buffers of the reverse loop: the all-ones fill pattern their consumers poll on (see "Dataflow exchange")
+  {
+    const size_t R = (size_t)p.R;
+    const int KH = p.NQ + (a.att ? a.E + a.A : 0);
+    CAPDEC_REQUIRE(KH / KC <= 16, CAPDEC_ERR_BAD_SHAPE, "recur_bwd: more than 16 K chunks of the recurrent gradient");
+    CAPDEC_CUDA_OK(cudaMemsetAsync(a.dpre_gm, 0xFF, R * 4 * a.D * 2, st));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(a.dpxk, 0xFF, R * (size_t)KH * 2, st));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(a.dhp, 0xFF, R * (size_t)(KH / KC) * a.D * 4, st));
+    if (!a.lstm) CAPDEC_CUDA_OK(cudaMemsetAsync(a.duk, 0xFF, R * p.NQ * 2, st));
+    if (a.att) {
+      CAPDEC_CUDA_OK(cudaMemsetAsync(a.dz, 0xFF, R * a.E * 4, st));
+      CAPDEC_CUDA_OK(cudaMemsetAsync(a.part, 0xFF, R * (size_t)(a.E / CHUNK) * pad4i(a.P) * 4, st));
+    }
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(di->sms, 1, 1);
@@ -1535,6 +1652,9 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
       for (int k = 1; k < 16 && h[t * 16 + k]; ++k) fprintf(stderr, " %lld", h[t * 16 + k] - h[t * 16 + k - 1]);
       fprintf(stderr, "\n");
     }
+    unsigned flag = 0;
+    cudaMemcpy(&flag, a.bar + 16, sizeof flag, cudaMemcpyDeviceToHost);
+    if (flag) fprintf(stderr, "recur_bwd: a dataflow poll TIMED OUT (abort flag set)\n");
     fine_dump("recur_bwd");
   }
   return CAPDEC_OK;
