@@ -1466,7 +1466,7 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
     const size_t R = (size_t)p.R;
     CAPDEC_CUDA_OK(cudaMemsetAsync(a.Ht, 0xFF, R * a.D * 2, st));
     CAPDEC_CUDA_OK(cudaMemsetAsync(a.g1, 0xFF, R * p.NG1 * 4, st));
-    CAPDEC_CUDA_OK(cudaMemsetAsync(a.pre, 0xFF, R * p.NQ * 4, st));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(a.pre, 0xFF, R * (size_t)4 * a.D * 4, st));     // [T][B][4D] (LSTM: NQ = 4D)
     if (!a.lstm) CAPDEC_CUDA_OK(cudaMemsetAsync(a.m, 0xFF, (size_t)4 * R * 2 * a.F * 2, st));
     if (a.att) {
       CAPDEC_CUDA_OK(cudaMemsetAsync(a.zk, 0xFF, R * a.E * 2, st));

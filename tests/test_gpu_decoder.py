@@ -429,3 +429,38 @@ def test_benchmarked_mode_matches_oracle(kind, lengths_kind, monkeypatch):
     with capdec.precision_scope("bf16"):
         s_eval = call_forward(dec, kind, *args)[0]
     assert rel_err(s_eval, ref["scores"]) > 10 * BF16_TOL
+
+
+@pytest.mark.parametrize("precision,tol,gtol", [("bf16", BF16_TOL, 8e-2), ("fp32", FP32_TOL, 4 * FP32_TOL)])
+def test_scaled_shape_matches_oracle(precision, tol, gtol):
+    """BASELINE config 5 dims (decoder / factor 1024, vocab 30k; attention / embedding 512) at a batch the CPU
+    oracle finishes in seconds, train mode with the decoder's own dropout mask fed to the oracle."""
+    from capdec import functional as CF
+    dims = dict(A=512, M=512, D=1024, F=1024, S=1000, V=30000, E=2048)
+    lengths = [9, 5, 12, 3]
+    enc, tags, caps, caplens = O.synthetic_batch(4, dims["V"], seed=31, lengths=lengths)
+    with capdec.precision_scope(precision):
+        torch.manual_seed(0)
+        dec = build_decoder(O.ATTENTION_SCN, dims).train()
+        sd = {k: v.detach().cpu() for k, v in dec.state_dict().items()}
+        torch.manual_seed(5)
+        scores, caps_sorted, dl, alphas, sort_ind = dec(enc.cuda(), tags.cuda(), caps.cuda(), caplens.cuda())
+        mask = CF.dropout_mask(scores._capdec_meta["seed"], 0.5, 4, max(dl), dims["D"])
+        ref = oracle_run(O.ATTENTION_SCN, sd, enc, tags, caps, caplens, sort_ind=sort_ind, dropout_masks=mask, hoist=True)
+        assert rel_err(scores, ref["scores"]) < tol
+        assert rel_err(alphas, ref["alphas"]) < tol
+        loss, _ = dec.loss(scores, caps_sorted, dl, alphas)
+        assert abs(loss.item() - ref["loss"].item()) < tol * abs(ref["loss"].item())
+        loss.backward()
+        bad = []
+        for n, p in dec.named_parameters():
+            g = ref["grads"][n]
+            if g.abs().max().item() < 1e-9:
+                continue
+            e = rel_err(p.grad, g)
+            lim = gtol
+            if n.startswith("attention.encoder_att") or n.startswith("attention.decoder_att"):
+                e, lim = rel_err_fro(p.grad, g), max(gtol, 1e-2)     # relu-kink flips (see the fp32 full-width test)
+            if e >= lim:
+                bad.append((n, e, lim))
+        assert not bad, bad

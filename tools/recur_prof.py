@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-phase clock stamps of the persistent recurrence kernels (debug): runs one eager
 attention_scn forward(+backward) at the config-3 shape with CAPDEC_RECUR_PROF=1; the library
-prints, for CTA 0 and a few steps, the cycles spent in each phase and in each grid barrier."""
+prints, for CTA 0 (row group 0) and a few steps, the cycles between the phase boundaries (wait for the inputs + work)."""
 import os
 import sys
 
@@ -15,6 +15,7 @@ import bench  # noqa: E402
 
 kind_name = sys.argv[1] if len(sys.argv) > 1 else "attention_scn"
 capdec.set_precision("bf16")
+capdec.set_graphs(False)          # the profiling path allocates and synchronises: never inside a capture
 kind, dims, B, _ = bench.WORKLOADS[kind_name + "_train"]
 torch.manual_seed(0)
 dec = bench.make_decoder(kind, dims).cuda().train()
