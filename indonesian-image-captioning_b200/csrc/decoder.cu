@@ -378,8 +378,10 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
     CAPDEC_CUDA_OK(cudaMemcpyAsync(c.at(o.seedD), &seed, 8, cudaMemcpyHostToDevice, st));
     CAPDEC_CUDA_OK(cudaMemcpyAsync(c.at(o.capsD), caps, (size_t)B * d.L * 8, cudaMemcpyDeviceToDevice, st));
     // sorted, converted features + pixel mean (attention_scn.py:113-120, :90)
+    // ... and, for the persistent kernels, the chunk-major copy of the features in the same pass
+    const bool want_cm = o.enc_cm != 0 && E % 256 == 0;
     CAPDEC_TRY(gather_features(pr, enc, sb, sp, se, sort_ind, c.at(o.enc_s), c.at<float>(o.mean),
-                               c.at(o.meanF), p.ldE, B, P, E, st));
+                               c.at(o.meanF), p.ldE, B, P, E, st, want_cm ? c.at(o.enc_cm) : nullptr, 256));
     if (p.scn)   // tags are NOT permuted (App. C-1): row i of the sorted batch uses tags[i]
       CAPDEC_TRY(copy_cast(pr, tags, 0, S, c.at(o.tagsF), 1, p.ldS, B, S, st));
   }
@@ -466,9 +468,7 @@ int forward_train(const CapdecDims& d, const CapdecParams& w, const float* enc, 
                   NQ, M));
   }
   if (alphas) CAPDEC_CUDA_OK(cudaMemsetAsync(alphas, 0, (size_t)R * P * 4, st));
-  if (persistent) {
-    CAPDEC_TRY(recur_fwd_prepare(ra, st));          // chunk-major feature copy
-  } else if (SK) {
+  if (!persistent && SK) {
     // split-K GEMMs of the tcgen05 engine accumulate with atomics into pre-zeroed buffers
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.g1), 0, (size_t)R * NG1 * 4, st));
     if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.pre), 0, (size_t)R * 4 * D * 4, st));
@@ -631,18 +631,30 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   const int Ppad = (P + 3) / 4 * 4;
   const int Ri = (int)R;
   if (phases & 2) {
-  CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dh_rec), 0, (size_t)(T + 1) * B * D * 4, st));
-  if (SK) {
-    if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.wr), 0, (size_t)R * 4 * 2 * F * 4, st));
-    if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dz), 0, (size_t)R * E * 4, st));
-    CAPDEC_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)GEMM_TC_MAX_TILE_COUNTERS * 4, st));
+  // will the reverse loop run as the persistent kernel?  It then needs none of the zeroed accumulators of the split-K
+  // kernel chains (it writes dh_0 / dc_0 itself and fills its exchange buffers in its launcher)
+  bool will_persist = false;
+  if (pr == CAPDEC_BF16 && (p.scn || p.att) && !fused && (!p.att || alphas)) {
+    RecurBwdArgs probe;
+    probe.att = p.att ? 1 : 0; probe.lstm = p.scn ? 0 : 1;
+    probe.B = B; probe.T = T; probe.P = P; probe.E = E; probe.A = A; probe.M = M; probe.D = D; probe.F = F;
+    will_persist = recur_bwd_supported(probe);
   }
-  CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dc), 0, (size_t)B * D * 4, st));
+  if (!will_persist) {
+    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dh_rec), 0, (size_t)(T + 1) * B * D * 4, st));
+    if (SK) {
+      if (p.scn) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.wr), 0, (size_t)R * 4 * 2 * F * 4, st));
+      if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dz), 0, (size_t)R * E * 4, st));
+      CAPDEC_CUDA_OK(cudaMemsetAsync(counters, 0, (size_t)GEMM_TC_MAX_TILE_COUNTERS * 4, st));
+    }
+    CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dc), 0, (size_t)B * D * 4, st));
+  }
   if (p.scn) {
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dv_acc), 0, (size_t)B * NQ * 4, st));
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dq_acc), 0, (size_t)B * NQ * 4, st));
   }
-  if (p.att) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.de), 0, (size_t)R * Ppad * 4, st));
+  // de feeds the batched dAtt1 kernel over ALL (t,b) rows: rows beyond a caption's length must be zero
+  if (p.att && (ragged || !will_persist)) CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.de), 0, (size_t)R * Ppad * 4, st));
   if (ragged) {
     CAPDEC_CUDA_OK(cudaMemsetAsync(c.at(o.dpre), 0, (size_t)R * 4 * D * p.fsz, st));
     if (p.scn) {
@@ -687,9 +699,7 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     if (p.att) {
       rb.dz = c.at<float>(o.dz); rb.awe = c.at<float>(o.awe); rb.alphas = alphas; rb.d_alphas = d_alphas;
       rb.enc_cm = c.at(o.enc_cm); rb.att1 = c.at(o.att1); rb.att1_cm = c.at(o.att1_cm); rb.w_f = w.full_att_w;
-      RecurFwdArgs fa;        // did the forward (same dims, same switches) build the chunk-major feature copy?
-      fa.att = 1; fa.lstm = p.scn ? 0 : 1; fa.B = B; fa.T = T; fa.P = P; fa.E = E; fa.A = A; fa.M = M; fa.D = D; fa.F = F;
-      rb.enc = c.at(o.enc_s); rb.build_enc_cm = recur_fwd_supported(fa) ? 0 : 1;
+      rb.enc = c.at(o.enc_s); rb.build_enc_cm = E % 256 == 0 ? 0 : 1;       // the forward's input phase wrote it
       rb.part = c.at<float>(o.part_t); rb.de = c.at<float>(o.de); rb.dwf = c.at<float>(o.dwf);
       rb.dbf = c.at<float>(o.dbf);
     }
@@ -1079,13 +1089,13 @@ int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, co
 
   CAPDEC_TRY(pack_weights(c, w));
   // ---- per-image prologue (attention_scn.py:176-214) ----
+  const bool have_cm = p.att && pr == CAPDEC_BF16 && E % 512 == 0;
   CAPDEC_TRY(gather_features(pr, enc, (int64_t)P * E, E, 1, nullptr, c.at(o.enc_f), c.at<float>(o.mean),
-                             c.at(o.meanF), p.ldE, G, P, E, st));
+                             c.at(o.meanF), p.ldE, G, P, E, st, have_cm ? c.at(o.enc_cm) : nullptr, 512));
   if (p.att)
     CAPDEC_TRY(G_(c, c.at(o.enc_f), E, c.at(p.o.Wp_e), p.ldE, c.at(o.att1), A, 1, w.enc_att_b, nullptr, 0,
                   G * P, A, E));
-  const bool have_cm = p.att && pr == CAPDEC_BF16 && E % 512 == 0;
-  if (have_cm) CAPDEC_TRY(chunk_major_copy(c.at(o.enc_f), c.at(o.enc_cm), G, P, E, 512, st));
+
   CAPDEC_TRY(expand_rows(pr, c.at(o.meanF), p.ldE, c.at(o.meanX), p.ldE, G, k, E, st));
   CAPDEC_TRY(G_(c, c.at(o.meanX), p.ldE, c.ft(p.o.Wp_init, 0), p.ldE, c.at(o.H), p.ldD, 1, w.init_h_b,
                 nullptr, 0, R, D, E));

@@ -55,7 +55,8 @@ int colsum(int precision, const void* X, int x_ft, int64_t ld, int R, int N, flo
 // gather rows by sort_ind, convert to the feature type, and mean over pixels
 int gather_features(int precision, const float* enc, int64_t sb, int64_t sp, int64_t se,
                     const int64_t* sort_ind, void* enc_s, float* mean_f32, void* mean_ft,
-                    int64_t ld_mean_ft, int B, int P, int E, cudaStream_t st);
+                    int64_t ld_mean_ft, int B, int P, int E, cudaStream_t st,
+                    void* enc_cm = nullptr, int cw = 0);   // optional chunk-major copy [B][E/cw][P][cw] in the same pass
 // Xe[(t*B + b)*ldx + :] = emb[caps[b*L + t]]
 int embedding_gather(int precision, const float* emb, const int64_t* caps, int L, void* Xe,
                      int64_t ldx, int B, int T, int M, int V, cudaStream_t st);
@@ -115,7 +116,6 @@ struct RecurFwdArgs {
   float dropout_p = 0.f; const uint64_t* seed = nullptr;
 };
 bool recur_fwd_supported(const RecurFwdArgs& a);     // shape / device / CAPDEC_PERSISTENT check
-int recur_fwd_prepare(const RecurFwdArgs& a, cudaStream_t st);   // chunk-major feature copy (once per batch)
 int recur_fwd(const RecurFwdArgs& a, cudaStream_t st);
 struct RecurBwdArgs {
   int att = 0, lstm = 0;

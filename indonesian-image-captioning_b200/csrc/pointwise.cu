@@ -140,13 +140,16 @@ __global__ void gather_features_kernel(const float* __restrict__ enc, int64_t sb
                                        int64_t se, const int64_t* __restrict__ sort_ind,
                                        FT* __restrict__ enc_s, float* __restrict__ mean_f32,
                                        FT* __restrict__ mean_ft, int64_t ld_mean_ft, int B, int P,
-                                       int E) {
+                                       int E, FT* __restrict__ enc_cm, int cw) {
   const int b = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   const int64_t src_b = sort_ind ? sort_ind[b] : b;
   const float* src = enc + src_b * sb + (int64_t)e * se;
   FT* dst = enc_s + (int64_t)b * P * E + e;
+  // optional second copy, chunk-major [B][E/cw][P][cw]: every (pixel range, cw-channel chunk) run is contiguous, so a
+  // staging fill of the persistent / streaming attention kernels is ONE bulk copy (was a separate pass over enc_s)
+  FT* dcm = enc_cm ? enc_cm + (((int64_t)b * (E / cw) + e / cw) * P) * cw + (e % cw) : nullptr;
   float s = 0.f;
   int p = 0;
   constexpr int U = 14;                         // pixels in flight per thread (196 = 14 * 14)
@@ -156,13 +159,17 @@ __global__ void gather_features_kernel(const float* __restrict__ enc, int64_t sb
     for (int i = 0; i < U; ++i) v[i] = src[(int64_t)(p + i) * sp];
 #pragma unroll
     for (int i = 0; i < U; ++i) {
-      dst[(int64_t)(p + i) * E] = from_f<FT>(v[i]);
+      const FT x = from_f<FT>(v[i]);
+      dst[(int64_t)(p + i) * E] = x;
+      if (dcm) dcm[(int64_t)(p + i) * cw] = x;
       s += v[i];
     }
   }
   for (; p < P; ++p) {
     const float v0 = src[(int64_t)p * sp];
-    dst[(int64_t)p * E] = from_f<FT>(v0);
+    const FT x = from_f<FT>(v0);
+    dst[(int64_t)p * E] = x;
+    if (dcm) dcm[(int64_t)p * cw] = x;
     s += v0;
   }
   const float m = s / (float)P;
@@ -485,14 +492,15 @@ int colsum(int precision, const void* X, int x_ft, int64_t ld, int R, int N, flo
 
 int gather_features(int precision, const float* enc, int64_t sb, int64_t sp, int64_t se,
                     const int64_t* sort_ind, void* enc_s, float* mean_f32, void* mean_ft,
-                    int64_t ld_mean_ft, int B, int P, int E, cudaStream_t st) {
+                    int64_t ld_mean_ft, int B, int P, int E, cudaStream_t st, void* enc_cm, int cw) {
+  CAPDEC_REQUIRE(!enc_cm || (cw > 0 && E % cw == 0), CAPDEC_ERR_BAD_SHAPE, "gather_features: E=%d cw=%d", E, cw);
   dim3 grid(ceil_div(E, 128), B);
   if (precision == CAPDEC_BF16)
     gather_features_kernel<bf16><<<grid, 128, 0, st>>>(enc, sb, sp, se, sort_ind, (bf16*)enc_s,
-                                                       mean_f32, (bf16*)mean_ft, ld_mean_ft, B, P, E);
+                                                       mean_f32, (bf16*)mean_ft, ld_mean_ft, B, P, E, (bf16*)enc_cm, cw);
   else
     gather_features_kernel<float><<<grid, 128, 0, st>>>(enc, sb, sp, se, sort_ind, (float*)enc_s,
-                                                        mean_f32, (float*)mean_ft, ld_mean_ft, B, P, E);
+                                                        mean_f32, (float*)mean_ft, ld_mean_ft, B, P, E, (float*)enc_cm, cw);
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }

@@ -1427,12 +1427,6 @@ bool recur_fwd_supported(const RecurFwdArgs& a) {
   return plan_fwd(a, dev_info(), &n1, &n3, &n4, &smem);
 }
 
-// once per batch, before recur_fwd: the chunk-major copy of the features ([B][E/256][P][256])
-int recur_fwd_prepare(const RecurFwdArgs& a, cudaStream_t st) {
-  if (!a.att) return CAPDEC_OK;
-  return chunk_major_copy(a.enc, a.enc_cm, a.B, a.P, a.E, CHUNK, st);
-}
-
 int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   const DevInfo* di = dev_info();
   int nt1, nt3, nt4;
