@@ -33,6 +33,7 @@
 // weight gradients) stay on the tcgen05 engine (gemm_tc.cu).
 #include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -97,6 +98,12 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1
       "{%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 
 // MUFU-based transcendentals (abs. error ~1e-6; the results are rounded to bf16 operands anyway)
@@ -168,12 +175,20 @@ constexpr long long POLL_LIMIT_CYCLES = 4000000000ll;
 
 __device__ __forceinline__ uint4 ldx16(const void* p) {
   uint4 r;
+#ifdef CAPDEC_POLL_VOLATILE
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+#else
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+#endif
   return r;
 }
 __device__ __forceinline__ uint32_t ldx4(const void* p) {
   uint32_t r;
+#ifdef CAPDEC_POLL_VOLATILE
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+#else
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+#endif
   return r;
 }
 __device__ __forceinline__ void stx16(void* p, const uint4& v) {
@@ -222,6 +237,26 @@ __device__ __forceinline__ float poll4f(const Grp& G, const float* p) {
   return __uint_as_float(v);
 }
 
+// N floats, `stride` elements apart, polled together in rounds
+template <int N>
+__device__ __forceinline__ void poll4f_n(const Grp& G, const float* p, int64_t stride, int n, float (&out)[N]) {
+  uint32_t raw[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) raw[k] = k < n ? ldx4(p + (int64_t)k * stride) : 0u;
+  for (unsigned spins = 0;;) {
+    bool pend = false;
+#pragma unroll
+    for (int k = 0; k < N; ++k) pend = pend || raw[k] == SENT;
+    if (!pend) break;
+    if ((++spins & 63u) == 0u && poll_stalled(G.abortp, G.t_end)) break;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (raw[k] == SENT) raw[k] = ldx4(p + (int64_t)k * stride);
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) out[k] = __uint_as_float(raw[k]);
+}
+
 // One GEMM job of a row group with the activation operand taken STRAIGHT FROM THE EXCHANGE BUFFER in global memory
 // (see above) into mma fragments: NH * 16 output features with the full K,
 //   out[h] = sum_k A[row, k] * W[h*16 + j, k]       (row = G.tid / 16, j = G.tid % 16)
@@ -242,8 +277,10 @@ __device__ __forceinline__ void gemm_job_df(Grp& G, const bf16* __restrict__ src
   const uint8_t* a_lo = reinterpret_cast<const uint8_t*>(src) + ((size_t)g * KF + ks * (BPW * 32)) * 2 + 16 * c;
   const uint8_t* a_hi = a_lo + (size_t)8 * KF * 2;
   FSTAMP(100);
+#ifndef CAPDEC_NO_PROBE
   if (lane == 0) (void)poll16<false>(G, a_lo);
   __syncwarp();
+#endif
   FSTAMP(101);
   uint4 alo[NF][BPW], ahi[NF][BPW];
 #pragma unroll
@@ -261,13 +298,29 @@ __device__ __forceinline__ void gemm_job_df(Grp& G, const bf16* __restrict__ src
 #pragma unroll
       for (int i = 0; i < 4; ++i) accb[nt][j][i] = 0.f;
   const uint8_t* w_base = Ws + (size_t)g * wstride + ks * (BPW * 64) + 16 * c;
+  // elements that had not arrived yet are re-requested IN ROUNDS, all pending ones of the lane together: one L2
+  // round trip per round whatever their number (one after the other, 16 late elements cost 16 round trips)
+  for (unsigned spins = 0;;) {
+    bool pend = false;
+#pragma unroll
+    for (int kf = 0; kf < NF; ++kf)
+#pragma unroll
+      for (int j = 0; j < BPW; ++j) pend = pend || (lo && sent16(alo[kf][j])) || (hi && sent16(ahi[kf][j]));
+    if (!pend) break;
+    if ((++spins & 63u) == 0u && poll_stalled(G.abortp, G.t_end)) break;
+#pragma unroll
+    for (int kf = 0; kf < NF; ++kf)
+#pragma unroll
+      for (int j = 0; j < BPW; ++j) {
+        if (lo && sent16(alo[kf][j])) alo[kf][j] = ldx16(a_lo + (size_t)kf * fill_stride * 2 + j * 64);
+        if (hi && sent16(ahi[kf][j])) ahi[kf][j] = ldx16(a_hi + (size_t)kf * fill_stride * 2 + j * 64);
+      }
+  }
 #pragma unroll
   for (int kf = 0; kf < NF; ++kf) {
     const uint8_t* wp = w_base + (size_t)kf * KF * 2;
 #pragma unroll
     for (int j = 0; j < BPW; ++j) {
-      if (lo) alo[kf][j] = poll16<false>(G, a_lo + (size_t)kf * fill_stride * 2 + j * 64, alo[kf][j]);
-      if (hi) ahi[kf][j] = poll16<false>(G, a_hi + (size_t)kf * fill_stride * 2 + j * 64, ahi[kf][j]);
       const uint4 x = alo[kf][j], y = ahi[kf][j];
 #pragma unroll
       for (int nt = 0; nt < 2 * NH; ++nt) {
@@ -462,6 +515,8 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
 #define RECUR_STAMP()                                                                                  \
   do {                                                                                                 \
     if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[t * 16 + (stamp & 15)] = clock64();      \
+    if (p.prof && t == T / 2 && G.tid == 0)                                                            \
+      p.prof[(int64_t)T * 16 + ((int64_t)(G.g * gridDim.x + blockIdx.x)) * 16 + (stamp & 15)] = gtime_ns(); \
     FSTAMP(stamp);                                                                                     \
     ++stamp;                                                                                           \
   } while (0)
@@ -563,13 +618,21 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
                 raw[cc][1] = ldx16(g1 + a + 4);
               }
             }
+            for (unsigned spins = 0;;) {                 // late elements: re-requested in rounds (see gemm_job_df)
+              bool pend = false;
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) pend = pend || sent32(raw[cc][0]) || sent32(raw[cc][1]);
+              if (!pend) break;
+              if ((++spins & 63u) == 0u && poll_stalled(G.abortp, G.t_end)) break;
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                const int a = cc * 256 + a_lane;
+                if (sent32(raw[cc][0])) raw[cc][0] = ldx16(g1 + a);
+                if (sent32(raw[cc][1])) raw[cc][1] = ldx16(g1 + a + 4);
+              }
+            }
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
-              const int a = cc * 256 + a_lane;
-              if (need && a < A) {
-                raw[cc][0] = poll16<true>(G, g1 + a, raw[cc][0]);
-                raw[cc][1] = poll16<true>(G, g1 + a + 4, raw[cc][1]);
-              }
               x2[r][cc][0] = __uint_as_float(raw[cc][0].x); x2[r][cc][1] = __uint_as_float(raw[cc][0].y);
               x2[r][cc][2] = __uint_as_float(raw[cc][0].z); x2[r][cc][3] = __uint_as_float(raw[cc][0].w);
               x2[r][cc][4] = __uint_as_float(raw[cc][1].x); x2[r][cc][5] = __uint_as_float(raw[cc][1].y);
@@ -764,20 +827,17 @@ __global__ void __launch_bounds__(RT, 1) recur_fwd_kernel(const __grid_constant_
         // pre = (Emb W_ih[:M] + z W_ih[M:]) + h W_hh + b_ih + b_hh, torch gate order i,f,g,o
         const float* ua = (ATT ? p.pre : p.U) + (tb + b) * NQ + d;
         const float* hb = p.g1 + (tb + b) * NG1 + col0 + d;
+        float uv[4], hv[4];
+        poll4f_n<4>(G, ua, D, 4, uv);
+        poll4f_n<4>(G, hb, D, 4, hv);
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq)
-          x[gq] = poll4f(G, ua + gq * D) + poll4f(G, hb + gq * D) + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
+        for (int gq = 0; gq < 4; ++gq) x[gq] = uv[gq] + hv[gq] + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
         const float t2 = x[2]; x[2] = x[3]; x[3] = t2;        // -> i, f, o, g
       } else {
-        const float* pre = p.pre + (tb + b) * 4 * D + d;
-        uint32_t raw[4];
+        float pv[4];
+        poll4f_n<4>(G, p.pre + (tb + b) * 4 * D + d, D, 4, pv);
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) raw[gq] = ldx4(pre + gq * D);
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          const float v = raw[gq] != SENT ? __uint_as_float(raw[gq]) : poll4f(G, pre + gq * D);
-          x[gq] = v + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
-        }
+        for (int gq = 0; gq < 4; ++gq) x[gq] = pv[gq] + __ldg(p.b_ih + gq * D + d) + __ldg(p.b_hh + gq * D + d);
       }
       const float ig = fsigmoid(x[0]), fg = fsigmoid(x[1]), og = fsigmoid(x[2]);
       const float gg = ftanh(x[3]);
@@ -923,7 +983,9 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
   const bool cell_mine = cbl < GR && row0 + cbl < B;
   float dc_reg = 0.f;
   int stamp = 0;
-#define BSTAMP() do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[t * 16 + (stamp & 15)] = clock64(); FSTAMP(stamp); ++stamp; } while (0)
+#define BSTAMP() do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[t * 16 + (stamp & 15)] = clock64(); \
+    if (p.prof && t == T / 2 && G.tid == 0) p.prof[(int64_t)T * 16 + ((int64_t)(G.g * gridDim.x + blockIdx.x)) * 16 + (stamp & 15)] = gtime_ns(); \
+    FSTAMP(stamp); ++stamp; } while (0)
 
 #pragma unroll 1
   for (int t = T - 1; t >= 0; --t) {
@@ -941,12 +1003,10 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
       float dh = 0.f;
       if (t + 1 < T && lens[b] > t + 1) {
         const float* dp = p.dhp + (((int64_t)(t + 1) * nkc) * B + b) * D + d;
-        uint32_t raw[16];
+        float pv[16];
+        poll4f_n<16>(G, dp, (int64_t)B * D, nkc, pv);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) raw[k] = k < nkc ? ldx4(dp + (int64_t)k * B * D) : 0u;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          if (k < nkc) dh += raw[k] != SENT ? __uint_as_float(raw[k]) : poll4f(G, dp + (int64_t)k * B * D);
+        for (int k = 0; k < 16; ++k) dh += pv[k];
       }
       {
         float g = __ldg(p.dHfc + ((int64_t)b * T + t) * D + d);
@@ -1056,7 +1116,12 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
           float dawe[8];
           {
             const float* dzp = p.dz + (tb + row) * E + e0;
-            const uint4 z0 = poll16<true>(G, dzp), z1 = poll16<true>(G, dzp + 4);
+            uint4 z0 = ldx16(dzp), z1 = ldx16(dzp + 4);
+            for (unsigned spins = 0; sent32(z0) || sent32(z1);) {          // late elements: re-requested together
+              if ((++spins & 63u) == 0u && poll_stalled(G.abortp, G.t_end)) break;
+              if (sent32(z0)) z0 = ldx16(dzp);
+              if (sent32(z1)) z1 = ldx16(dzp + 4);
+            }
             const float dzv[8] = {__uint_as_float(z0.x), __uint_as_float(z0.y), __uint_as_float(z0.z), __uint_as_float(z0.w),
                                   __uint_as_float(z1.x), __uint_as_float(z1.y), __uint_as_float(z1.z), __uint_as_float(z1.w)};
             const float bp[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -1163,13 +1228,8 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
             const float* pp0 = p.part + ((int64_t)t * B + row) * chunks * Ppad + tid;
             int cc = 0;
             for (; cc + 8 <= chunks; cc += 8) {
-              uint32_t raw[8];
               float v[8];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) raw[k] = ldx4(pp0 + (int64_t)(cc + k) * Ppad);
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                v[k] = raw[k] != SENT ? __uint_as_float(raw[k]) : poll4f(G, pp0 + (int64_t)(cc + k) * Ppad);
+              poll4f_n<8>(G, pp0 + (int64_t)cc * Ppad, Ppad, 8, v);
               d += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
             }
             for (; cc < chunks; ++cc) d += poll4f(G, pp0 + (int64_t)cc * Ppad);
@@ -1281,7 +1341,10 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
     const int b = row0 + cbl, d = cd;
     float dh = 0.f;
     const float* dp = p.dhp + (int64_t)b * D + d;
-    for (int k = 0; k < nkc; ++k) dh += poll4f(G, dp + (int64_t)k * B * D);
+    float pv[16];
+    poll4f_n<16>(G, dp, (int64_t)B * D, nkc, pv);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dh += pv[k];
     p.dh_rec[(int64_t)b * D + d] = dh;
     p.dc[(int64_t)b * D + d] = dc_reg;
   }
@@ -1348,6 +1411,30 @@ __global__ void dead_rows_zero_kernel(const int32_t* __restrict__ len, int B, bf
     }
   }
   for (int i = threadIdx.x; i < NG1 / 4; i += blockDim.x) reinterpret_cast<float4*>(g1 + r * NG1)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// debug: the phase boundaries of the middle step on EVERY CTA and both row groups (global timer, ns): per boundary the
+// earliest / median / latest arrival relative to the earliest step start of that row group
+void dump_all_cta_stamps(const char* name, const long long* h, int nctas) {
+  for (int g = 0; g < 2; ++g) {
+    long long t0 = 0;
+    for (int c = 0; c < nctas; ++c) {
+      const long long v = h[((int64_t)g * nctas + c) * 16];
+      if (v && (!t0 || v < t0)) t0 = v;
+    }
+    if (!t0) continue;
+    fprintf(stderr, "%s all-CTA stamps, row group %d (ns after the group's earliest step start; min / median / max):\n", name, g);
+    for (int k = 0; k < 16; ++k) {
+      std::vector<long long> v;
+      for (int c = 0; c < nctas; ++c) {
+        const long long x = h[((int64_t)g * nctas + c) * 16 + k];
+        if (x) v.push_back(x - t0);
+      }
+      if (v.empty()) break;
+      std::sort(v.begin(), v.end());
+      fprintf(stderr, "  boundary %d: %lld / %lld / %lld  (%zu CTAs)\n", k, v.front(), v[v.size() / 2], v.back(), v.size());
+    }
+  }
 }
 
 struct DevInfo { int sms = 0; int smem_optin = 0; bool coop = false; };
@@ -1488,8 +1575,8 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   const bool prof = prof_env && prof_env[0] == '1';
   if (prof) {
     fine_reset();
-    CAPDEC_CUDA_OK(cudaMalloc(&p.prof, (size_t)(a.T * 16 + 64) * sizeof(long long)));
-    CAPDEC_CUDA_OK(cudaMemsetAsync(p.prof, 0, (size_t)(a.T * 16 + 64) * sizeof(long long), st));
+    CAPDEC_CUDA_OK(cudaMalloc(&p.prof, (size_t)(a.T * 16 + 2 * di->sms * 16) * sizeof(long long)));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(p.prof, 0, (size_t)(a.T * 16 + 2 * di->sms * 16) * sizeof(long long), st));
   }
   if (g_timing) {
     for (int i = 0; i < 4; ++i)
@@ -1508,7 +1595,7 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
   }
   if (prof) {
     // debug only: synchronises.  Prints per-phase cycles of CTA 0 (work, barrier wait) for a few steps.
-    std::vector<long long> h((size_t)a.T * 16 + 64);
+    std::vector<long long> h((size_t)a.T * 16 + 2 * di->sms * 16);
     CAPDEC_CUDA_OK(cudaStreamSynchronize(st));
     CAPDEC_CUDA_OK(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.prof);
@@ -1520,6 +1607,7 @@ int recur_fwd(const RecurFwdArgs& a, cudaStream_t st) {
     unsigned flag = 0;
     cudaMemcpy(&flag, a.bar + 16, sizeof flag, cudaMemcpyDeviceToHost);
     if (flag) fprintf(stderr, "recur_fwd: a dataflow poll TIMED OUT (abort flag set)\n");
+    dump_all_cta_stamps("recur_fwd", h.data() + (size_t)a.T * 16, di->sms);
     fine_dump("recur_fwd");
   }
   return CAPDEC_OK;
@@ -1622,8 +1710,8 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
   const bool prof = prof_env && prof_env[0] == '1';
   if (prof) {
     fine_reset();
-    CAPDEC_CUDA_OK(cudaMalloc(&p.prof, (size_t)a.T * 16 * sizeof(long long)));
-    CAPDEC_CUDA_OK(cudaMemsetAsync(p.prof, 0, (size_t)a.T * 16 * sizeof(long long), st));
+    CAPDEC_CUDA_OK(cudaMalloc(&p.prof, (size_t)(a.T * 16 + 2 * di->sms * 16) * sizeof(long long)));
+    CAPDEC_CUDA_OK(cudaMemsetAsync(p.prof, 0, (size_t)(a.T * 16 + 2 * di->sms * 16) * sizeof(long long), st));
   }
   if (g_timing) {
     for (int i = 0; i < 4; ++i)
@@ -1637,7 +1725,7 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
     g_timed[1] = true;
   }
   if (prof) {
-    std::vector<long long> h((size_t)a.T * 16);
+    std::vector<long long> h((size_t)a.T * 16 + 2 * di->sms * 16);
     CAPDEC_CUDA_OK(cudaStreamSynchronize(st));
     CAPDEC_CUDA_OK(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.prof);
@@ -1649,6 +1737,7 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
     unsigned flag = 0;
     cudaMemcpy(&flag, a.bar + 16, sizeof flag, cudaMemcpyDeviceToHost);
     if (flag) fprintf(stderr, "recur_bwd: a dataflow poll TIMED OUT (abort flag set)\n");
+    dump_all_cta_stamps("recur_bwd", h.data() + (size_t)a.T * 16, di->sms);
     fine_dump("recur_bwd");
   }
   return CAPDEC_OK;
