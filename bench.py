@@ -32,6 +32,10 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# a process-wide NCCL_DEBUG=VERSION would put NCCL's banner on stdout next to the ONE JSON line of the contract
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch  # noqa: E402
 
 DIMS512 = dict(A=512, M=512, D=512, F=512, S=1000, V=10000, E=2048)

@@ -13,7 +13,9 @@ import capdec  # noqa: E402
 from oracle import capdec_oracle as O  # noqa: E402
 import bench  # noqa: E402
 
-name = sys.argv[1] if len(sys.argv) > 1 else "attention_scn_train"
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+summary = "--summary" in sys.argv          # aggregate by kernel name instead of listing every activity
+name = args[0] if args else "attention_scn_train"
 capdec.set_precision("bf16")
 capdec.set_graphs(True)
 kind, dims, B, _ = bench.WORKLOADS[name]
@@ -49,8 +51,27 @@ t0 = sel[0].time_range.start
 end_prev = t0
 busy = 0.0
 gaps = []
+if summary:
+    import collections
+    agg = collections.OrderedDict()
+    for e in sel:
+        k = e.name[:110]
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += e.time_range.end - e.time_range.start
+    print("%6s %10s %8s  %s" % ("count", "total_us", "avg_us", "name"))
+    for k, (n, tot) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("%6d %10.1f %8.2f  %s" % (n, tot, tot / n, k))
 print("%9s %8s %7s  %s" % ("start_us", "dur_us", "gap_us", "name"))
 for e in sel:
+    if summary:
+        st, du = e.time_range.start - t0, e.time_range.end - e.time_range.start
+        gap = e.time_range.start - end_prev
+        if gap > 0:
+            gaps.append(gap)
+        busy += du
+        end_prev = max(end_prev, e.time_range.end)
+        continue
     st, du = e.time_range.start - t0, e.time_range.end - e.time_range.start
     gap = e.time_range.start - end_prev
     if gap > 0:
