@@ -160,9 +160,11 @@ int capdec_dropout_mask(uint64_t dropout_seed, float dropout_p, int64_t n, float
  *   phases         0 = everything, else a bit set of the backward's stages IN PRODUCTION ORDER of the gradients,
  *                  so that a data-parallel caller can all-reduce one bucket of gradients while the next is being
  *                  computed (capdec/parallel.py):
- *                    1  fc.weight, fc.bias (and dH_fc)          2  the reverse-time recurrence
- *                    4  weight_ia / weight_ih, embedding.weight  8  the other cell weights, bias_ih, bias_hh
- *                    16 attention.*, f_beta.*, init_h.*, init_c.*
+ *                    1  fc.weight, fc.bias (and dH_fc)           2  the reverse-time recurrence
+ *                    4  weight_ia / weight_ih, embedding.weight  8  the other cell weights, bias_ih, bias_hh,
+ *                                                                   init_h.*, init_c.*
+ *                    16 f_beta.*, attention.decoder_att.*,       32 attention.encoder_att.* (the long dAtt1
+ *                       attention.full_att.*                        chain with the fewest bytes: last)
  *                  Stages must run in this order on one stream; each is graph-capturable on its own. */
 int capdec_backward(const CapdecDims* dims, const CapdecParams* params,
                     const int32_t* decode_len_h, float dropout_p,

@@ -45,19 +45,25 @@ PARAM_MAP = {
     "pure_attention": _ATT + [("embedding.weight", "emb")] + _LSTM + _COMMON_TAIL + _BETA + _FC,
 }
 
-# gradient buckets in PRODUCTION ORDER of capdec_backward (its `phases` 1|2, 4, 8, 16): the flat gradient buffer is
+# gradient buckets in PRODUCTION ORDER of capdec_backward (its `phases` 1|2, 4, 8, 16, 32): the flat gradient buffer is
 # laid out in this order, so every bucket is one contiguous slice that a data-parallel caller can all-reduce as
 # soon as its stage has been launched (capdec/parallel.py)
 _BUCKET_NAMES = [
     ("fc.weight", "fc.bias"),
     ("decode_step.weight_ia", "decode_step.weight_ih", "embedding.weight"),
     ("decode_step.weight_ic", "decode_step.weight_hc", "decode_step.weight_ha", "decode_step.weight_hh",
-     "decode_step.weight_ib", "decode_step.weight_hb", "decode_step.bias_ih", "decode_step.bias_hh"),
-    ("attention.encoder_att.weight", "attention.encoder_att.bias", "attention.decoder_att.weight",
-     "attention.decoder_att.bias", "attention.full_att.weight", "attention.full_att.bias", "f_beta.weight",
-     "f_beta.bias", "init_h.weight", "init_h.bias", "init_c.weight", "init_c.bias"),
+     "decode_step.weight_ib", "decode_step.weight_hb", "decode_step.bias_ih", "decode_step.bias_hh",
+     "init_h.weight", "init_h.bias", "init_c.weight", "init_c.bias"),
+    ("f_beta.weight", "f_beta.bias", "attention.decoder_att.weight", "attention.decoder_att.bias",
+     "attention.full_att.weight", "attention.full_att.bias"),
+    ("attention.encoder_att.weight", "attention.encoder_att.bias"),
 ]
-BUCKET_PHASES = (1 | 2, 4, 8, 16)
+# stage groups of capdec_backward after which bucket i is complete.  Default: the fc bucket is handed over after
+# the reverse loop (an all-reduce kernel issued before it would fight the persistent kernel for SMs); a hook
+# with `early_fc` (a communicator limited to a few CTAs, see capdec/parallel.py) gets it BEFORE the loop and
+# runs next to it.
+BUCKET_PHASES = (1 | 2, 4, 8, 16, 32)
+BUCKET_PHASES_EARLY_FC = (1, 2 | 4, 8, 16, 32)
 
 
 def grad_buckets(kind):
@@ -516,14 +522,15 @@ class DecoderTrainFn(torch.autograd.Function):
             else:
                 # stage by stage: the hook starts the all-reduce of a bucket while the next stage is being computed
                 flat = plan.flat_grads
-                nb = len(BUCKET_PHASES)
-                for i, ph in enumerate(BUCKET_PHASES):
+                stages = BUCKET_PHASES_EARLY_FC if getattr(hook, "early_fc", False) else BUCKET_PHASES
+                nb = len(stages)
+                for i, ph in enumerate(stages):
                     if ctx.use_graph:
                         plan.run("%s_%d" % (slot, ph), lambda ph=ph: call(ph))
                     else:
                         call(ph)
                     lo, hi = plan.gstore.bucket_slices[i]
-                    hook(i, nb, flat[lo:hi])
+                    hook(i, nb, flat[lo:hi])            # an empty slice (pure_scn: no attention) still closes the bucket
         meta["flat_grads"] = plan.flat_grads
         if ctx.family is not None:
             ctx.token = None                                   # this forward's saved state is no longer needed

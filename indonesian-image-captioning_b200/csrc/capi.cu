@@ -122,7 +122,7 @@ int capdec_backward(const CapdecDims* dims, const CapdecParams* params,
                     const float* d_alphas, const float* alphas, const CapdecParams* grads,
                     void* workspace, size_t workspace_bytes, int phases, void* stream) {
   CAPDEC_REQUIRE(dims && params && grads && workspace, CAPDEC_ERR_BAD_ARG, "capdec_backward: null argument");
-  CAPDEC_REQUIRE(phases >= 0 && phases <= 31, CAPDEC_ERR_BAD_ARG, "capdec_backward: bad phases");
+  CAPDEC_REQUIRE(phases >= 0 && phases <= 63, CAPDEC_ERR_BAD_ARG, "capdec_backward: bad phases");
   CAPDEC_REQUIRE(dims->kind == CAPDEC_PURE_SCN || alphas, CAPDEC_ERR_BAD_ARG, "alphas is NULL");
   CAPDEC_TRY(capdec_init());
   return backward(*dims, *params, decode_len_h, dropout_p,

@@ -561,10 +561,10 @@ int backward(const CapdecDims& d, const CapdecParams& w,
   //   1  fc.weight / fc.bias and dH_fc                 (before the reverse loop)
   //   2  the reverse-time recurrence
   //   4  weight_ia (weight_ih) and embedding.weight    (the two largest gradients after fc)
-  //   8  the other cell weights and both cell biases
-  //   16 attention, f_beta, init_h / init_c
+  //   8  the other cell weights, both cell biases, init_h / init_c
+  //   16 f_beta, decoder_att, full_att            32 encoder_att (the long dAtt1 chain, the smallest bucket: last)
   // Every phase reads only params, workspace, alphas and the d_* inputs -> each is graph-capturable on its own.
-  if (phases == 0) phases = 31;
+  if (phases == 0) phases = 63;
   const bool len_free = len_h == nullptr;   // lengths only on the device: persistent recurrence kernels required
   Ctx c;
   CAPDEC_TRY(make_plan(d, true, &c.p));
@@ -925,6 +925,14 @@ int backward(const CapdecDims& d, const CapdecParams& w,
       CAPDEC_TRY(transpose_cast(pr, c.at(o.dq_acc), 0, c.at(o.tB), 1, 1, B, NQ, 0, NQ, p.ldB, 0, 1, st));
       CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.w_hb, NQ, 0, nullptr, nullptr, 0, S, NQ, B));
     }
+    // init_h / init_c: dh0 = dh_rec, dc0 = dc after the last reverse step
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.mean), 0, c.at(o.tB), 1, 1, B, E, 0, E, p.ldB, 0, 1, st));
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.dh_rec), 0, c.at(o.tA), 1, 1, B, D, 0, D, p.ldB, 0, 1, st));
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.init_h_w, E, 0, nullptr, nullptr, 0, D, E, B));
+    CAPDEC_TRY(colsum(pr, c.at(o.dh_rec), 0, D, B, D, g.init_h_b, 0, st));
+    CAPDEC_TRY(transpose_cast(pr, c.at(o.dc), 0, c.at(o.tA), 1, 1, B, D, 0, D, p.ldB, 0, 1, st));
+    CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.init_c_w, E, 0, nullptr, nullptr, 0, D, E, B));
+    CAPDEC_TRY(colsum(pr, c.at(o.dc), 0, D, B, D, g.init_c_b, 0, st));
   }   // phase 8
 
   if (phases & 16) {
@@ -944,6 +952,11 @@ int backward(const CapdecDims& d, const CapdecParams& w,
     // full_att: per-row partials reduced over all (t,b)
     CAPDEC_TRY(colsum(pr, c.at(o.dwf), 0, A, Ri, A, g.full_att_w, 0, st));
     CAPDEC_TRY(colsum(pr, c.at(o.dbf), 0, 1, Ri, 1, g.full_att_b, 0, st));
+  }
+  }   // phase 16
+
+  if (phases & 32) {
+  if (p.att) {
     // dAtt1[b,p,:] = w_f * sum_t de[t,b,p] 1[att1[b,p,:] + att2_t[b,:] > 0]  (masks rebuilt, not stored)
     CAPDEC_TRY(attention_datt1(pr, c.at(o.att1), c.at<float>(o.g1), NG1, (int64_t)B * NG1, c.at<float>(o.de),
                                (int64_t)B * Ppad, w.full_att_w, c.at<float>(o.dAtt1), 0, B, T, P, A, st));
@@ -959,15 +972,7 @@ int backward(const CapdecDims& d, const CapdecParams& w,
       CAPDEC_TRY(G_(c, c.at(o.tA), p.ldBP, c.at(o.tB), p.ldBP, g.enc_att_w, E, 0, nullptr, nullptr, 0, A, E, BP));
     }
   }
-  // init_h / init_c: dh0 = dh_rec, dc0 = dc after the last reverse step
-  CAPDEC_TRY(transpose_cast(pr, c.at(o.mean), 0, c.at(o.tB), 1, 1, B, E, 0, E, p.ldB, 0, 1, st));
-  CAPDEC_TRY(transpose_cast(pr, c.at(o.dh_rec), 0, c.at(o.tA), 1, 1, B, D, 0, D, p.ldB, 0, 1, st));
-  CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.init_h_w, E, 0, nullptr, nullptr, 0, D, E, B));
-  CAPDEC_TRY(colsum(pr, c.at(o.dh_rec), 0, D, B, D, g.init_h_b, 0, st));
-  CAPDEC_TRY(transpose_cast(pr, c.at(o.dc), 0, c.at(o.tA), 1, 1, B, D, 0, D, p.ldB, 0, 1, st));
-  CAPDEC_TRY(G_(c, c.at(o.tA), p.ldB, c.at(o.tB), p.ldB, g.init_c_w, E, 0, nullptr, nullptr, 0, D, E, B));
-  CAPDEC_TRY(colsum(pr, c.at(o.dc), 0, D, B, D, g.init_c_b, 0, st));
-  }   // phase 16
+  }   // phase 32
   return CAPDEC_OK;
 }
 

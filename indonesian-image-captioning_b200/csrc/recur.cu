@@ -1679,7 +1679,7 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
     chunk_major_kernel<<<di->sms * 4, 256, 0, st>>>((const uint4*)a.att1, (uint4*)a.att1_cm, a.B, a.P, a.A, QW);
     CAPDEC_LAUNCH_OK();
   }
-  CAPDEC_REQUIRE((int64_t)GR * a.D <= (int64_t)di->sms * GT, CAPDEC_ERR_BAD_SHAPE, "recur_bwd: one cell element per thread");
+  CAPDEC_REQUIRE((int64_t)GR * a.D <= (int64_t)(di->sms - 8) * GT, CAPDEC_ERR_BAD_SHAPE, "recur_bwd: one cell element per thread");
   CAPDEC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, st));
   // exchange buffers of the reverse loop: the all-ones fill pattern their consumers poll on (see "Dataflow exchange")
   {
@@ -1697,7 +1697,18 @@ int recur_bwd(const RecurBwdArgs& a, cudaStream_t st) {
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(di->sms, 1, 1);
+  // CAPDEC_RECUR_BWD_CTAS: launch on fewer SMs than the device has, so that a small NCCL kernel (the all-reduce of the
+  // fc gradients, capdec/parallel.py) runs NEXT TO the reverse loop instead of waiting for it.  Every role mapping of
+  // the kernel only needs >= 144 CTAs at the reference dims (plan_bwd's limits are re-checked for the reduced grid).
+  int nctas = di->sms;
+  if (const char* e = getenv("CAPDEC_RECUR_BWD_CTAS")) {
+    const int want = atoi(e);
+    DevInfo fewer = *di;
+    fewer.sms = want;
+    size_t smem2;
+    if (want >= 8 && want < di->sms && plan_bwd(a, &fewer, &smem2)) nctas = want;
+  }
+  cfg.gridDim = dim3(nctas, 1, 1);
   cfg.blockDim = dim3(RT, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;

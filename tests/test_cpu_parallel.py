@@ -124,9 +124,11 @@ def test_gradient_buckets_cover_every_parameter_in_production_order():
     for kind in ("attention_scn", "pure_scn", "pure_attention"):
         names = CF.param_names(kind)
         buckets = CF.grad_buckets(kind)
-        assert len(buckets) == len(CF.BUCKET_PHASES) == 4
+        assert len(buckets) == len(CF.BUCKET_PHASES) == len(CF.BUCKET_PHASES_EARLY_FC) == 5
         flat = [i for b in buckets for i in b]
         assert sorted(flat) == list(range(len(names)))
         assert [names[i] for i in buckets[0]] == ["fc.weight", "fc.bias"]
         assert "embedding.weight" in [names[i] for i in buckets[1]]
-        assert all(names[i].startswith("decode_step.") for i in buckets[2])
+        assert all(names[i].startswith(("decode_step.", "init_h.", "init_c.")) for i in buckets[2])
+        assert [names[i] for i in buckets[4]] == (["attention.encoder_att.weight", "attention.encoder_att.bias"]
+                                                  if kind != "pure_scn" else [])
