@@ -85,8 +85,11 @@ class GradReducer:
             if flat_slice.is_cuda:
                 small = index == 0 and self.early_fc
                 if self._side is None:
-                    self._side = torch.cuda.Stream(device=flat_slice.device)
-                    self._side_small = torch.cuda.Stream(device=flat_slice.device)
+                    # high-priority streams: the all-reduce kernels get free SM slots ahead of the queued GEMM tiles
+                    # of the compute stream (the exchange, not the GEMMs, is what the step ends on)
+                    prio = -1 if os.environ.get("CAPDEC_AR_PRIORITY", "1") != "0" else 0
+                    self._side = torch.cuda.Stream(device=flat_slice.device, priority=prio)
+                    self._side_small = torch.cuda.Stream(device=flat_slice.device, priority=prio)
                 side = self._side_small if small else self._side
                 ev = torch.cuda.Event()
                 ev.record()               # on the compute stream, after this bucket's last kernel
