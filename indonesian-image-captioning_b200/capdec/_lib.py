@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_ROOT, "libcapdec.so")
+# CAPDEC_LIB: another build of the same library (e.g. the -DCAPDEC_RECUR_FINE debug build of tools/recur_prof.py)
+LIB_PATH = os.environ.get("CAPDEC_LIB") or os.path.join(PKG_ROOT, "libcapdec.so")
 
 KIND = {"attention_scn": 0, "pure_scn": 1, "pure_attention": 2}
 

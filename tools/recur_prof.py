@@ -17,6 +17,7 @@ kind_name = sys.argv[1] if len(sys.argv) > 1 else "attention_scn"
 capdec.set_precision("bf16")
 capdec.set_graphs(False)          # the profiling path allocates and synchronises: never inside a capture
 kind, dims, B, _ = bench.WORKLOADS[kind_name + "_train"]
+B = int(os.environ.get("RECUR_PROF_BATCH", B))          # 16 = one row group alone
 torch.manual_seed(0)
 dec = bench.make_decoder(kind, dims).cuda().train()
 enc, tags, caps, caplens = [t.cuda() for t in O.synthetic_batch(B, dims["V"], seed=1, lengths=[51] * B)]
