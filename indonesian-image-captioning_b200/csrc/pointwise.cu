@@ -392,6 +392,186 @@ __global__ void scn_bwd_products_kernel(const float* __restrict__ wr, const floa
   }
 }
 
+// ---- four-features-per-thread versions of the four per-step pointwise kernels (beam search: 1 875 rows per step, the
+// per-step chains of the large shapes): 16-byte loads / stores and 32-bit index arithmetic.  The one-element-per-thread
+// kernels above ran at a third of their own HBM roofline (scn_form_m 22.7 us for 50 MB, cell_fwd 14.6 us for 25 MB:
+// profiles/r1g_decode_launches_summary.txt).  Launchers fall back to them when a row pitch or pointer is not 16-byte
+// friendly. ----
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void st4(bf16* p, float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 v;
+  v.x = *reinterpret_cast<const uint32_t*>(&lo);
+  v.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = v;
+}
+
+template <typename FT>
+__global__ void scn_form_m_v4_kernel(const float* __restrict__ u, int64_t ldu, const float* __restrict__ p, int64_t ldp,
+                                     const float* __restrict__ v, const float* __restrict__ q, FT* __restrict__ m,
+                                     int rows, int B, int F) {
+  pdl_prologue();
+  const int total = rows * F;                       // groups of 4 features: (row, n / 4), n = g*F + f
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / F, n = (i - b * F) * 4;
+    const int g = n / F, f = n - g * F;
+    const float4 uu = ld4(u + (int64_t)b * ldu + n), vv = ld4(v + (int64_t)b * 4 * F + n);
+    const float4 pp = ld4(p + (int64_t)b * ldp + n), qq = ld4(q + (int64_t)b * 4 * F + n);
+    FT* dst = m + ((int64_t)g * B + b) * 2 * F + f;
+    st4(dst, uu.x * vv.x, uu.y * vv.y, uu.z * vv.z, uu.w * vv.w);
+    st4(dst + F, pp.x * qq.x, pp.y * qq.y, pp.z * qq.z, pp.w * qq.w);
+  }
+}
+
+template <typename FT>
+__global__ void cell_fwd_v4_kernel(const float* __restrict__ preA, int64_t ldA, const float* __restrict__ preB, int64_t ldB,
+                                   const float* __restrict__ b1, const float* __restrict__ b2, int lstm_order,
+                                   const float* __restrict__ c_prev, float* __restrict__ c_new, float* __restrict__ gates,
+                                   FT* __restrict__ h_out, int64_t ldh, FT* __restrict__ hd_out, float dropout_p,
+                                   const uint64_t* __restrict__ seed_dev, int t, int T, int rows, int D) {
+  pdl_prologue();
+  int si, sf, so, sg;
+  gate_slots(lstm_order, si, sf, so, sg);
+  const int D4 = D / 4, total = rows * D4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / D4, d = (i - b * D4) * 4;
+    float pre[4][4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float4 x = ld4(preA + (int64_t)b * ldA + g * D + d);
+      if (preB) { const float4 y = ld4(preB + (int64_t)b * ldB + g * D + d); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+      if (b1) { const float4 y = ld4(b1 + g * D + d); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+      if (b2) { const float4 y = ld4(b2 + g * D + d); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+      pre[g][0] = x.x; pre[g][1] = x.y; pre[g][2] = x.z; pre[g][3] = x.w;
+    }
+    const float4 cp4 = ld4(c_prev + (int64_t)b * D + d);
+    const float cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+    float ig[4], fg[4], og[4], gg[4], c[4], h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ig[k] = sigmoidf_(pre[si][k]); fg[k] = sigmoidf_(pre[sf][k]); og[k] = sigmoidf_(pre[so][k]);
+      gg[k] = tanhf(pre[sg][k]);
+      c[k] = fg[k] * cp[k] + ig[k] * gg[k];
+      h[k] = og[k] * tanhf(c[k]);
+    }
+    st4(c_new + (int64_t)b * D + d, c[0], c[1], c[2], c[3]);
+    if (gates) {
+      float* gp = gates + (int64_t)b * 4 * D + d;       // stored as [i | f | o | g~]
+      st4(gp, ig[0], ig[1], ig[2], ig[3]);
+      st4(gp + D, fg[0], fg[1], fg[2], fg[3]);
+      st4(gp + 2 * D, og[0], og[1], og[2], og[3]);
+      st4(gp + 3 * D, gg[0], gg[1], gg[2], gg[3]);
+    }
+    st4(h_out + (int64_t)b * ldh + d, h[0], h[1], h[2], h[3]);
+    if (hd_out) {
+      const uint64_t seed = seed_dev[0];
+      float hs[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hs[k] = h[k] * dropout_scale(seed, ((uint64_t)b * T + t) * D + d + k, dropout_p);
+      st4(hd_out + (int64_t)b * ldh + d, hs[0], hs[1], hs[2], hs[3]);
+    }
+  }
+}
+
+template <typename FT>
+__global__ void cell_bwd_v4_kernel(const float* __restrict__ dh_fc, int64_t ld_dhfc, const float* __restrict__ dh_rec,
+                                   float* __restrict__ dc, const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                   const float* __restrict__ c_new, int lstm_order, float dropout_p,
+                                   const uint64_t* __restrict__ seed_dev, int t, int T, FT* __restrict__ dpre,
+                                   float* __restrict__ dpre_f32, int rows, int D) {
+  pdl_prologue();
+  int si, sf, so, sg;
+  gate_slots(lstm_order, si, sf, so, sg);
+  const int D4 = D / 4, total = rows * D4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / D4, d = (i - b * D4) * 4;
+    const int64_t e = (int64_t)b * D + d;
+    const float4 r4 = ld4(dh_rec + e);
+    float dh[4] = {r4.x, r4.y, r4.z, r4.w};
+    if (dh_fc) {
+      const float4 g4 = ld4(dh_fc + (int64_t)b * ld_dhfc + d);
+      float g[4] = {g4.x, g4.y, g4.z, g4.w};
+      if (dropout_p > 0.f) {
+        const uint64_t seed = seed_dev[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g[k] *= dropout_scale(seed, ((uint64_t)b * T + t) * D + d + k, dropout_p);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dh[k] += g[k];
+    }
+    const float* gp = gates + (int64_t)b * 4 * D + d;
+    const float4 i4 = ld4(gp), f4 = ld4(gp + D), o4 = ld4(gp + 2 * D), g4 = ld4(gp + 3 * D);
+    const float4 cn4 = ld4(c_new + e), cp4 = ld4(c_prev + e), dc4 = ld4(dc + e);
+    const float ig[4] = {i4.x, i4.y, i4.z, i4.w}, fg[4] = {f4.x, f4.y, f4.z, f4.w}, og[4] = {o4.x, o4.y, o4.z, o4.w},
+                gg[4] = {g4.x, g4.y, g4.z, g4.w}, cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w}, cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w},
+                dcv[4] = {dc4.x, dc4.y, dc4.z, dc4.w};
+    float dpi[4], dpf[4], dpo[4], dpg[4], dco[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float tc = tanhf(cn[k]);
+      const float dcn = dcv[k] + dh[k] * og[k] * (1.f - tc * tc);
+      dpo[k] = dh[k] * tc * og[k] * (1.f - og[k]);
+      dpi[k] = dcn * gg[k] * ig[k] * (1.f - ig[k]);
+      dpf[k] = dcn * cp[k] * fg[k] * (1.f - fg[k]);
+      dpg[k] = dcn * ig[k] * (1.f - gg[k] * gg[k]);
+      dco[k] = dcn * fg[k];
+    }
+    st4(dc + e, dco[0], dco[1], dco[2], dco[3]);
+    const int64_t o = (int64_t)b * 4 * D + d;
+    st4(dpre + o + (int64_t)si * D, dpi[0], dpi[1], dpi[2], dpi[3]);
+    st4(dpre + o + (int64_t)sf * D, dpf[0], dpf[1], dpf[2], dpf[3]);
+    st4(dpre + o + (int64_t)so * D, dpo[0], dpo[1], dpo[2], dpo[3]);
+    st4(dpre + o + (int64_t)sg * D, dpg[0], dpg[1], dpg[2], dpg[3]);
+    if (dpre_f32) {
+      st4(dpre_f32 + o + (int64_t)si * D, dpi[0], dpi[1], dpi[2], dpi[3]);
+      st4(dpre_f32 + o + (int64_t)sf * D, dpf[0], dpf[1], dpf[2], dpf[3]);
+      st4(dpre_f32 + o + (int64_t)so * D, dpo[0], dpo[1], dpo[2], dpo[3]);
+      st4(dpre_f32 + o + (int64_t)sg * D, dpg[0], dpg[1], dpg[2], dpg[3]);
+    }
+  }
+}
+
+template <typename FT>
+__global__ void scn_bwd_products_v4_kernel(const float* __restrict__ wr, const float* __restrict__ u, int64_t ldu,
+                                           const float* __restrict__ p, int64_t ldp, const float* __restrict__ v,
+                                           const float* __restrict__ q, FT* __restrict__ du, FT* __restrict__ dp,
+                                           float* __restrict__ dv_acc, float* __restrict__ dq_acc, int rows, int B, int F,
+                                           int64_t lddp) {
+  pdl_prologue();
+  const int total = rows * F;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / F, n = (i - b * F) * 4;
+    const int g = n / F, f = n - g * F;
+    const float* src = wr + ((int64_t)g * B + b) * 2 * F + f;
+    const float4 w = ld4(src), r = ld4(src + F);
+    const int64_t k = (int64_t)b * 4 * F + n;
+    const float4 vv = ld4(v + k), qq = ld4(q + k);
+    const float4 uu = ld4(u + (int64_t)b * ldu + n), pp = ld4(p + (int64_t)b * ldp + n);
+    const float4 av = ld4(dv_acc + k), aq = ld4(dq_acc + k);
+    st4(du + k, w.x * vv.x, w.y * vv.y, w.z * vv.z, w.w * vv.w);
+    st4(dp + (int64_t)b * lddp + n, r.x * qq.x, r.y * qq.y, r.z * qq.z, r.w * qq.w);
+    st4(dv_acc + k, av.x + w.x * uu.x, av.y + w.y * uu.y, av.z + w.z * uu.z, av.w + w.w * uu.w);
+    st4(dq_acc + k, aq.x + r.x * pp.x, aq.y + r.y * pp.y, aq.z + r.z * pp.z, aq.w + r.w * pp.w);
+  }
+}
+
+// all pointers 16-byte aligned and all pitches multiples of 4 elements?
+template <typename... P>
+inline bool aligned16(P... ptrs) {
+  uintptr_t acc = 0;
+  const uintptr_t v[] = {(uintptr_t)ptrs...};
+  for (uintptr_t x : v) acc |= x;
+  return (acc & 15u) == 0;
+}
+inline bool mult4(std::initializer_list<int64_t> v) {
+  for (int64_t x : v)
+    if (x % 4) return false;
+  return true;
+}
+
 __global__ void concat_bias_kernel(float* dst, const float* a, int na, const float* b, int nb,
                                    int nzero) {
   const int n = na + nb + nzero;
@@ -548,6 +728,15 @@ int expand_rows(int precision, const void* src, int64_t lds, void* dst, int64_t 
 int scn_form_m(int precision, const float* u, int64_t ldu, const float* p, int64_t ldp,
                const float* v, const float* q, void* m, int rows, int B, int F, cudaStream_t st) {
   if (rows <= 0) return CAPDEC_OK;
+  if (aligned16(u, p, v, q, m) && mult4({ldu, ldp, F}) && (int64_t)rows * F < (1ll << 30)) {
+    const int g4 = grid_for((int64_t)rows * F, 256);
+    if (precision == CAPDEC_BF16)
+      CAPDEC_CUDA_OK(launch_pdl(scn_form_m_v4_kernel<bf16>, dim3(g4), dim3(256), 0, st, 1, u, ldu, p, ldp, v, q, (bf16*)m, rows, B, F));
+    else
+      CAPDEC_CUDA_OK(launch_pdl(scn_form_m_v4_kernel<float>, dim3(g4), dim3(256), 0, st, 1, u, ldu, p, ldp, v, q, (float*)m, rows, B, F));
+    CAPDEC_LAUNCH_OK();
+    return CAPDEC_OK;
+  }
   const int g = grid_for((int64_t)rows * 4 * F, 256);
   if (precision == CAPDEC_BF16)
     CAPDEC_CUDA_OK(launch_pdl(scn_form_m_kernel<bf16>, dim3(g), dim3(256), 0, st, 1, u, ldu, p, ldp, v, q, (bf16*)m, rows, B, F));
@@ -562,6 +751,18 @@ int cell_fwd(int precision, const float* preA, int64_t ldA, const float* preB, i
              float* gates, void* h_out, int64_t ldh, void* hd_out, float dropout_p, const uint64_t* seed,
              int t, int T, int rows, int D, cudaStream_t st) {
   if (rows <= 0) return CAPDEC_OK;
+  if (aligned16(preA, preB, b1, b2, c_prev, c_new, gates, h_out, hd_out) && mult4({ldA, ldB, ldh, D}) &&
+      (int64_t)rows * D < (1ll << 31)) {
+    const int g4 = grid_for((int64_t)rows * D / 4, 128);
+    if (precision == CAPDEC_BF16)
+      CAPDEC_CUDA_OK(launch_pdl(cell_fwd_v4_kernel<bf16>, dim3(g4), dim3(128), 0, st, 1, preA, ldA, preB, ldB, b1, b2, lstm_order, c_prev,
+                                c_new, gates, (bf16*)h_out, ldh, (bf16*)hd_out, dropout_p, seed, t, T, rows, D));
+    else
+      CAPDEC_CUDA_OK(launch_pdl(cell_fwd_v4_kernel<float>, dim3(g4), dim3(128), 0, st, 1, preA, ldA, preB, ldB, b1, b2, lstm_order, c_prev,
+                                c_new, gates, (float*)h_out, ldh, (float*)hd_out, dropout_p, seed, t, T, rows, D));
+    CAPDEC_LAUNCH_OK();
+    return CAPDEC_OK;
+  }
   const int g = grid_for((int64_t)rows * D, 128);
   if (precision == CAPDEC_BF16)
     CAPDEC_CUDA_OK(launch_pdl(cell_fwd_kernel<bf16>, dim3(g), dim3(128), 0, st, 1, preA, ldA, preB, ldB, b1, b2, lstm_order, c_prev, c_new,
@@ -580,6 +781,18 @@ int cell_bwd(int precision, const float* dh_fc, int64_t ld_dhfc, const float* dh
              float dropout_p, const uint64_t* seed, int t, int T, void* dpre, float* dpre_f32, int rows,
              int D, cudaStream_t st) {
   if (rows <= 0) return CAPDEC_OK;
+  if (aligned16(dh_fc, dh_rec, dc, gates, c_prev, c_new, dpre, dpre_f32) && mult4({ld_dhfc, D}) &&
+      (int64_t)rows * D < (1ll << 31)) {
+    const int g4 = grid_for((int64_t)rows * D / 4, 128);
+    if (precision == CAPDEC_BF16)
+      CAPDEC_CUDA_OK(launch_pdl(cell_bwd_v4_kernel<bf16>, dim3(g4), dim3(128), 0, st, 1, dh_fc, ld_dhfc, dh_rec, dc, gates, c_prev, c_new,
+                                lstm_order, dropout_p, seed, t, T, (bf16*)dpre, dpre_f32, rows, D));
+    else
+      CAPDEC_CUDA_OK(launch_pdl(cell_bwd_v4_kernel<float>, dim3(g4), dim3(128), 0, st, 1, dh_fc, ld_dhfc, dh_rec, dc, gates, c_prev, c_new,
+                                lstm_order, dropout_p, seed, t, T, (float*)dpre, dpre_f32, rows, D));
+    CAPDEC_LAUNCH_OK();
+    return CAPDEC_OK;
+  }
   const int g = grid_for((int64_t)rows * D, 128);
   if (precision == CAPDEC_BF16)
     CAPDEC_CUDA_OK(launch_pdl(cell_bwd_kernel<bf16>, dim3(g), dim3(128), 0, st, 1, dh_fc, ld_dhfc, dh_rec, dc, gates, c_prev, c_new,
@@ -597,6 +810,17 @@ int scn_bwd_products(int precision, const float* wr, const float* u, int64_t ldu
                      int64_t ldp, const float* v, const float* q, void* du, void* dp,
                      float* dv_acc, float* dq_acc, int rows, int B, int F, int64_t lddp, cudaStream_t st) {
   if (rows <= 0) return CAPDEC_OK;
+  if (aligned16(wr, u, p, v, q, du, dp, dv_acc, dq_acc) && mult4({ldu, ldp, lddp, F}) && (int64_t)rows * F < (1ll << 30)) {
+    const int g4 = grid_for((int64_t)rows * F, 256);
+    if (precision == CAPDEC_BF16)
+      CAPDEC_CUDA_OK(launch_pdl(scn_bwd_products_v4_kernel<bf16>, dim3(g4), dim3(256), 0, st, 1, wr, u, ldu, p, ldp, v, q, (bf16*)du,
+                                (bf16*)dp, dv_acc, dq_acc, rows, B, F, lddp));
+    else
+      CAPDEC_CUDA_OK(launch_pdl(scn_bwd_products_v4_kernel<float>, dim3(g4), dim3(256), 0, st, 1, wr, u, ldu, p, ldp, v, q, (float*)du,
+                                (float*)dp, dv_acc, dq_acc, rows, B, F, lddp));
+    CAPDEC_LAUNCH_OK();
+    return CAPDEC_OK;
+  }
   const int g = grid_for((int64_t)rows * 4 * F, 256);
   if (precision == CAPDEC_BF16)
     CAPDEC_CUDA_OK(launch_pdl(scn_bwd_products_kernel<bf16>, dim3(g), dim3(256), 0, st, 1, wr, u, ldu, p, ldp, v, q, (bf16*)du, (bf16*)dp,
