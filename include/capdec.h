@@ -211,6 +211,18 @@ int capdec_beam_search(const CapdecDims* dims, const CapdecParams* params,
                        float* out_alpha, int32_t* trace_parent, int32_t* trace_word,
                        float* trace_score,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* The same with STRIDED encoder features: element (g, p, e) at enc[g * enc_sb + p * enc_sp + e * enc_se].  The
+ * reference's EncoderCaption returns a permuted view that is physically NCHW (models/encoders/caption.py:43; SURVEY.md
+ * App. C-22): the prologue's gather casts / reorders it in its one pass instead of a dense fp32 copy being made first
+ * (the `encoder_out.view(1, -1, encoder_dim)` + `expand` of attention_scn.py:176-189 never copies either). */
+int capdec_beam_search_strided(const CapdecDims* dims, const CapdecParams* params,
+                               const float* enc, int64_t enc_sb, int64_t enc_sp, int64_t enc_se,
+                               const float* tags, int G, int k, int n_steps,
+                               int32_t start_id, int32_t end_id,
+                               int32_t* out_seq, int32_t* out_len, float* out_score, int32_t* out_completed,
+                               float* out_alpha, int32_t* trace_parent, int32_t* trace_word,
+                               float* trace_score,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* Top-k accuracy count (reference utils/metric.py:25-39 `accuracy(scores, targets, k)` as
  * called on the packed scores in trains/attention_scn.py:255, 338).  hits_out[0] = number of rows whose target

@@ -58,6 +58,8 @@ SIGNATURES = {
     "capdec_beam_workspace_bytes": (_sz, [C.POINTER(Dims), _i, _i, _i]),
     "capdec_beam_search": (_i, [C.POINTER(Dims), C.POINTER(Params), _vp, _vp, _i, _i, _i, C.c_int32,
                                 C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "capdec_beam_search_strided": (_i, [C.POINTER(Dims), C.POINTER(Params), _vp, _i64, _i64, _i64, _vp, _i, _i, _i,
+                                        C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "capdec_gemm": (_i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i64,
                          _i64, _i64, _i, _vp]),
     "capdec_gemm_tn": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i64, _i64, _i64, _vp]),

@@ -28,7 +28,11 @@ def beam_search_batch(dec, beam_size, start_id, end_id, encoder_out, tag_out=Non
     E = encoder_out.size(-1)
     enc = encoder_out.reshape(G_, -1, E)
     CF._require_cuda(enc, tag_out)
-    enc = enc.detach().float().contiguous()
+    enc = enc.detach()
+    if enc.dtype != torch.float32:
+        enc = enc.float()
+    # strided views (the encoder's permuted NCHW output) go to the library as they are: its gather reorders and
+    # casts in one pass (never .contiguous() in Python)
     P = enc.size(1)
     tags = None
     if kind != "pure_attention":
@@ -66,10 +70,11 @@ def beam_search_batch(dec, beam_size, start_id, end_id, encoder_out, tag_out=Non
               torch.empty(G_, n_steps, k, dtype=torch.int32, device=dev),
               torch.empty(G_, n_steps, k, dtype=torch.float32, device=dev))
     with torch.cuda.device(dev):
-        rc = lib.capdec_beam_search(C.byref(dims), C.byref(pstruct), _lib.ptr(enc), _lib.ptr(tags), G_, k,
-                                    n_steps, int(start_id), int(end_id), _lib.ptr(seq), _lib.ptr(length),
-                                    _lib.ptr(score), _lib.ptr(completed), _lib.ptr(alpha), _lib.ptr(tr[0]),
-                                    _lib.ptr(tr[1]), _lib.ptr(tr[2]), _lib.ptr(ws), ws_bytes, CF._stream())
+        rc = lib.capdec_beam_search_strided(C.byref(dims), C.byref(pstruct), _lib.ptr(enc), enc.stride(0),
+                                            enc.stride(1), enc.stride(2), _lib.ptr(tags), G_, k, n_steps,
+                                            int(start_id), int(end_id), _lib.ptr(seq), _lib.ptr(length),
+                                            _lib.ptr(score), _lib.ptr(completed), _lib.ptr(alpha), _lib.ptr(tr[0]),
+                                            _lib.ptr(tr[1]), _lib.ptr(tr[2]), _lib.ptr(ws), ws_bytes, CF._stream())
     _lib.check(rc, "capdec_beam_search")
     return {"seq": seq, "len": length, "score": score, "completed": completed, "alpha": alpha,
             "trace": tr if want_trace else None}

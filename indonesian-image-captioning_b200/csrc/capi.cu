@@ -46,7 +46,8 @@ static int do_init() {
   return CAPDEC_OK;
 }
 
-int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, const float* tags, int G,
+int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, int64_t enc_sb, int64_t enc_sp,
+                int64_t enc_se, const float* tags, int G,
                 int k, int max_steps, int32_t start_id, int32_t end_id, int32_t* out_seq,
                 int32_t* out_len, float* out_score, int32_t* out_completed, float* out_alpha,
                 int32_t* trace_parent, int32_t* trace_word, float* trace_score, void* workspace,
@@ -155,18 +156,31 @@ size_t capdec_beam_workspace_bytes(const CapdecDims* dims, int G, int k, int max
   return beam_workspace_bytes(*dims, G, k, max_steps);
 }
 
+int capdec_beam_search_strided(const CapdecDims* dims, const CapdecParams* params, const float* enc,
+                               int64_t enc_sb, int64_t enc_sp, int64_t enc_se,
+                               const float* tags, int G, int k, int max_steps, int32_t start_id,
+                               int32_t end_id, int32_t* out_seq, int32_t* out_len, float* out_score,
+                               int32_t* out_completed, float* out_alpha, int32_t* trace_parent,
+                               int32_t* trace_word, float* trace_score, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  CAPDEC_REQUIRE(dims && params && enc && out_seq && out_len && out_score && out_completed && workspace,
+                 CAPDEC_ERR_BAD_ARG, "capdec_beam_search: null argument");
+  CAPDEC_TRY(capdec_init());
+  return beam_search(*dims, *params, enc, enc_sb, enc_sp, enc_se, tags, G, k, max_steps, start_id, end_id, out_seq,
+                     out_len, out_score, out_completed, out_alpha, trace_parent, trace_word, trace_score,
+                     workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int capdec_beam_search(const CapdecDims* dims, const CapdecParams* params, const float* enc,
                        const float* tags, int G, int k, int max_steps, int32_t start_id,
                        int32_t end_id, int32_t* out_seq, int32_t* out_len, float* out_score,
                        int32_t* out_completed, float* out_alpha, int32_t* trace_parent,
                        int32_t* trace_word, float* trace_score, void* workspace,
                        size_t workspace_bytes, void* stream) {
-  CAPDEC_REQUIRE(dims && params && enc && out_seq && out_len && out_score && out_completed && workspace,
-                 CAPDEC_ERR_BAD_ARG, "capdec_beam_search: null argument");
-  CAPDEC_TRY(capdec_init());
-  return beam_search(*dims, *params, enc, tags, G, k, max_steps, start_id, end_id, out_seq, out_len,
-                     out_score, out_completed, out_alpha, trace_parent, trace_word, trace_score,
-                     workspace, workspace_bytes, (cudaStream_t)stream);
+  CAPDEC_REQUIRE(dims, CAPDEC_ERR_BAD_ARG, "capdec_beam_search: null argument");
+  return capdec_beam_search_strided(dims, params, enc, (int64_t)dims->P * dims->E, dims->E, 1, tags, G, k, max_steps,
+                                    start_id, end_id, out_seq, out_len, out_score, out_completed, out_alpha,
+                                    trace_parent, trace_word, trace_score, workspace, workspace_bytes, stream);
 }
 
 int capdec_gemm(int precision, const void* X, int64_t ldx, const void* W, int64_t ldw, void* out,

@@ -1067,8 +1067,8 @@ size_t beam_workspace_bytes(const CapdecDims& d, int G, int k, int n_steps) {
   return bp.o.total;
 }
 
-int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, const float* tags, int G,
-                int k, int n_steps, int32_t start_id, int32_t end_id, int32_t* out_seq,
+int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, int64_t enc_sb, int64_t enc_sp,
+                int64_t enc_se, const float* tags, int G, int k, int n_steps, int32_t start_id, int32_t end_id, int32_t* out_seq,
                 int32_t* out_len, float* out_score, int32_t* out_completed, float* out_alpha,
                 int32_t* trace_parent, int32_t* trace_word, float* trace_score, void* workspace,
                 size_t ws_bytes, cudaStream_t st) {
@@ -1095,7 +1095,9 @@ int beam_search(const CapdecDims& d, const CapdecParams& w, const float* enc, co
   CAPDEC_TRY(pack_weights(c, w));
   // ---- per-image prologue (attention_scn.py:176-214) ----
   const bool have_cm = p.att && pr == CAPDEC_BF16 && E % 512 == 0;
-  CAPDEC_TRY(gather_features(pr, enc, (int64_t)P * E, E, 1, nullptr, c.at(o.enc_f), c.at<float>(o.mean),
+  // strided views accepted (the real encoder output is physically NCHW): the gather casts /
+  // reorders in its one pass, no dense fp32 copy is made first
+  CAPDEC_TRY(gather_features(pr, enc, enc_sb, enc_sp, enc_se, nullptr, c.at(o.enc_f), c.at<float>(o.mean),
                              c.at(o.meanF), p.ldE, G, P, E, st, have_cm ? c.at(o.enc_cm) : nullptr, 512));
   if (p.att)
     CAPDEC_TRY(G_(c, c.at(o.enc_f), E, c.at(p.o.Wp_e), p.ldE, c.at(o.att1), A, 1, w.enc_att_b, nullptr, 0,

@@ -820,7 +820,12 @@ int launch(const GemmArgs& a, cudaStream_t st) {
   const int tiles = ceil_div(a.N, BM) * row_tiles * zb;
   int splits = 1;
   if (a.splitk != 0 && !(EPI == EPI_PLAIN && a.out_ft)) {
-    splits = a.splitk > 0 ? a.splitk : (148 + tiles - 1) / tiles;     // auto: about one CTA per SM
+    int target = 148;                                                  // auto: about one CTA per SM
+    if (const char* e = getenv("CAPDEC_GEMM_TARGET")) target = atoi(e);   // experiments
+    splits = a.splitk > 0 ? a.splitk : (target + tiles - 1) / tiles;
+    if (a.splitk < 0) {
+      if (const char* e = getenv("CAPDEC_GEMM_SPLITK")) splits = atoi(e);   // experiments: fixed split count
+    }
     if (splits > nkb / 2) splits = nkb / 2;                            // >= 2 k-blocks per CTA
     if (splits > 16) splits = 16;
     if (splits < 1) splits = 1;
@@ -916,8 +921,19 @@ bool persist_enabled() {
 template <int NACC, int EPI>
 int launch_rows(const GemmArgs& a, cudaStream_t st) {
   const int rows = (EPI == EPI_DHCELL && a.e.rows_epi > a.rows) ? a.e.rows_epi : a.rows;
-  if (rows <= 32) return launch<32, NACC, EPI>(a, st);
-  if (rows <= 64 || NACC > 1) return launch<64, NACC, EPI>(a, st);
+  // batch-side tile: with few output tiles (one 128-row batch tile x N/128 weight tiles < one wave of CTAs) the K loop
+  // had to be cut in 3..16 slices that meet in fp32 atomics -- at 128 captions per GPU and D = F = 1024 every in-loop GEMM
+  // of the per-step chains took ~15 us whatever its size.  Narrower batch tiles make the wave out of TILES first (the
+  // weight tile is re-read from L2 once per batch tile) and leave split-K for the long-K / few-tile products:
+  // 13.2 -> 12.4 ms per step at the config-5 shape (profiles/r2b_scaled_gemm_sweep.txt).
+  int cap = 128;
+  if (a.splitk < 0 && rows > 32) {
+    const int64_t wt = (int64_t)ceil_div(a.N, BM) * (NACC > 1 ? 1 : a.batch);
+    if (wt * ceil_div(rows, 128) < 148) cap = wt * ceil_div(rows, 64) >= 148 ? 64 : 32;
+  }
+  if (const char* e = getenv("CAPDEC_GEMM_ROWTILE")) cap = atoi(e);        // experiments: forced batch-side tile
+  if (rows <= 32 || cap <= 32) return launch<32, NACC, EPI>(a, st);
+  if (rows <= 64 || NACC > 1 || cap <= 64) return launch<64, NACC, EPI>(a, st);
   return launch<128, NACC, EPI>(a, st);
 }
 

@@ -1502,7 +1502,8 @@ bool plan_fwd(const RecurFwdArgs& a, const DevInfo* di, int* nt1, int* nt3, int*
 
 int chunk_major_copy(const void* src, void* dst, int B, int P, int E, int cw, cudaStream_t st) {
   CAPDEC_REQUIRE(E % cw == 0 && cw % 8 == 0, CAPDEC_ERR_BAD_SHAPE, "chunk_major_copy: E=%d cw=%d", E, cw);
-  chunk_major_kernel<<<148 * 8, 256, 0, st>>>((const uint4*)src, (uint4*)dst, B, P, E, cw);
+  const DevInfo* di = dev_info();
+  chunk_major_kernel<<<(di && di->sms > 0 ? di->sms : 148) * 8, 256, 0, st>>>((const uint4*)src, (uint4*)dst, B, P, E, cw);
   CAPDEC_LAUNCH_OK();
   return CAPDEC_OK;
 }

@@ -180,3 +180,73 @@ def test_evalcap_driver_with_a_stub_decoder():
         raise AssertionError("expected ValueError")
     except ValueError:
         pass
+
+
+def test_eval_caption_overlay_runs_the_reference_loop_in_batches(tmp_path):
+    """The overlay eval_caption.py: the reference's `evaluate(args)` with its per-image loop
+    (eval_caption.py:96-131) replaced by the batched driver -- same CLI arguments, same reference / hypothesis
+    strings, same nlg-eval layout and JSON files.  Stubs stand in for the dataset, the encoders and the CUDA decoder."""
+    import importlib.util
+    import json
+    import torch
+
+    spec = importlib.util.spec_from_file_location(
+        "capdec_eval_caption", os.path.join(ROOT, "indonesian-image-captioning_b200", "eval_caption.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    # every option of the reference's parser (eval_caption.py:171-185) is still there
+    args = mod.build_parser().parse_args(["-t", "attention_scn", "-mc", "c.pth", "-mt", "t.pth", "-df", "d", "-dn", "n",
+                                          "-tm", "tm.json", "-wm", "wm.json", "-bs", "3", "--output_dir", str(tmp_path)])
+    assert (args.type, args.model_caption, args.beam_size, args.batch_size) == ("attention_scn", "c.pth", 3, 32)
+
+    word_map = {"<pad>": 0, "a": 1, "b": 2, "c": 3, "<unk>": 4, "<start>": 5, "<end>": 6}
+
+    class Enc(torch.nn.Module):
+        def forward(self, image):                      # (G, 3, H, W) -> (G, 1, 1, 1) "features"
+            return image[:, :1, :1, :1].permute(0, 2, 3, 1)
+
+    class Tagger(torch.nn.Module):
+        def forward(self, image):
+            return torch.zeros(image.size(0), 4)
+
+    class Dec(torch.nn.Module):
+        kind = "attention_scn"
+
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self.calls = []
+
+        def sample_batch(self, beam, start, end, enc, tags, max_steps=50, want_alphas=True):
+            G = enc.size(0)
+            self.calls.append((G, beam, tuple(tags.shape)))
+            seq = torch.zeros(G, 5, dtype=torch.int32)
+            seq[:, 0] = start
+            seq[:, 1] = 1 + (enc.reshape(G, -1)[:, 0].long() % 3).int()
+            seq[:, 2] = end
+            return {"seq": seq, "len": torch.full((G,), 3, dtype=torch.int32),
+                    "completed": torch.tensor([1] * (G - 1) + [0], dtype=torch.int32)}
+
+    images = torch.arange(5, dtype=torch.float32).view(5, 1, 1, 1).expand(5, 3, 2, 2).contiguous()
+    allcaps = torch.tensor([[[5, 1, 2, 6, 0], [5, 3, 6, 0, 0]]] * 5)
+    loader = [(images[:3], None, None, allcaps[:3]), (images[3:], None, None, allcaps[3:])]
+    dec = Dec()
+    seen = {}
+
+    def metrics(references, hypotheses):
+        seen["refs"], seen["hyps"] = references, hypotheses
+        return {"Bleu_4": 0.5}
+
+    scores = mod.evaluate(args, loader=loader, models=(Enc(), Tagger(), dec), word_map=word_map, metrics=metrics)
+    assert scores == {"Bleu_4": 0.5}
+    assert dec.calls == [(3, 3, (3, 4)), (2, 3, (2, 4))]
+    assert seen["hyps"] == ["a", "b", "c", "a", "b"]
+    assert seen["refs"] == [["a b"] * 5, ["c"] * 5]                  # [caption][image], eval_caption.py:135-141
+    out = [os.path.join(dp, f) for dp, _, fs in os.walk(tmp_path) for f in fs]
+    names = sorted(os.path.basename(f) for f in out)
+    assert names == ["attention_scn_beam_3_hypotheses.json", "attention_scn_beam_3_incomplete.json",
+                     "attention_scn_beam_3_references.json", "attention_scn_beam_3_scores.json"]
+    by = {os.path.basename(f): json.load(open(f)) for f in out}
+    assert by["attention_scn_beam_3_hypotheses.json"] == seen["hyps"]
+    assert by["attention_scn_beam_3_incomplete.json"] == [2, 4]

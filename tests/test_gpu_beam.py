@@ -214,3 +214,26 @@ def test_beam_fused_vocabulary_kernel_large_batch(monkeypatch):
     assert torch.equal(a["trace"][0], b["trace"][0]) and torch.equal(a["trace"][1], b["trace"][1])
     assert torch.equal(a["seq"], b["seq"])
     assert (a["trace"][2] - b["trace"][2]).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("kind", [O.ATTENTION_SCN, O.PURE_ATTENTION])
+def test_beam_strided_encoder_features(kind):
+    """The reference encoder hands `sample` a permuted view that is physically NCHW (models/encoders/caption.py:43,
+    SURVEY App. C-22): capdec_beam_search_strided takes it as it is -- same tokens, parents and scores as with the
+    dense copy, in the token-exact fp32 mode."""
+    blob = load_golden("beam_" + kind)
+    start, end = blob["start_id"], blob["end_id"]
+    with capdec.precision_scope("fp32"):
+        dec = _decoder(blob)
+        enc = torch.cat([im["encoder_out"] for im in blob["images"]]).cuda()          # (G, 14, 14, E) or (G, P, E)
+        G = enc.size(0)
+        enc4 = enc.reshape(G, 14, 14, -1)
+        view = enc4.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)              # NHWC view of NCHW memory
+        assert not view.is_contiguous() and torch.equal(view, enc4)
+        tags = None if kind == O.PURE_ATTENTION else torch.cat([im["tags"] for im in blob["images"]]).cuda()
+        with torch.no_grad():
+            a = dec.sample_batch(3, start, end, enc4, tags, want_trace=True)
+            b = dec.sample_batch(3, start, end, view, tags, want_trace=True)
+        assert torch.equal(a["seq"], b["seq"]) and torch.equal(a["len"], b["len"])
+        assert torch.equal(a["trace"][0], b["trace"][0]) and torch.equal(a["trace"][1], b["trace"][1])
+        assert torch.equal(a["score"], b["score"])
