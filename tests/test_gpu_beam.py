@@ -225,9 +225,10 @@ def test_beam_strided_encoder_features(kind):
     start, end = blob["start_id"], blob["end_id"]
     with capdec.precision_scope("fp32"):
         dec = _decoder(blob)
-        enc = torch.cat([im["encoder_out"] for im in blob["images"]]).cuda()          # (G, 14, 14, E) or (G, P, E)
+        enc = torch.cat([im["encoder_out"] for im in blob["images"]]).cuda()
         G = enc.size(0)
-        enc4 = enc.reshape(G, 14, 14, -1)
+        assert enc.dim() == 4                                                          # (G, side, side, E)
+        enc4 = enc
         view = enc4.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)              # NHWC view of NCHW memory
         assert not view.is_contiguous() and torch.equal(view, enc4)
         tags = None if kind == O.PURE_ATTENTION else torch.cat([im["tags"] for im in blob["images"]]).cuda()
