@@ -18,6 +18,7 @@ Two execution modes for the training step:
 import collections
 import ctypes as C
 import os
+import warnings
 import weakref
 
 import torch
@@ -258,8 +259,12 @@ class _Plan:
             lib = _lib.load()
             before = lib.capdec_launch_count()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                launch()
+            with warnings.catch_warnings():
+                # a backward stage that queues nothing for this decoder (pure_scn has no attention gradients) is a
+                # legitimately empty graph: replaying it is a no-op, torch's warning about it is noise on every rank
+                warnings.filterwarnings("ignore", message="The CUDA Graph is empty")
+                with torch.cuda.graph(g):
+                    launch()
             # the capture call counted the kernels once without running them; this replay runs them
             self.graph_nodes[slot] = lib.capdec_launch_count() - before
             g.replay()
