@@ -52,7 +52,6 @@ WORKLOADS = {
 SECONDARY = [
     ("attention_scn_train_ragged", "attention_scn_train", True, True),
     ("attention_scn_train_ragged_eager", "attention_scn_train", True, False),
-    ("attention_scn_train_eager", "attention_scn_train", False, False),
     ("pure_scn_train", "pure_scn_train", False, True),
     ("pure_attention_train", "pure_attention_train", False, True),
     ("attention_scn_train_scaled", "attention_scn_train_scaled", False, True),
