@@ -361,6 +361,91 @@ __device__ __forceinline__ void gemm_job_df(Grp& G, const bf16* __restrict__ src
   FSTAMP(104);
 }
 
+// Two GEMM jobs of a row group AT ONCE (backward phase H: the CTA's two (d-slice, K-chunk) jobs): different activation
+// operands (n rows x 512 each), adjacent 16-row weight blocks in shared memory (job h = rows [16 h, 16 h + 16) of Ws).
+// The operand loads of BOTH jobs are in flight together and share one poll phase -- run one after the other, the second
+// job paid a second probe + load round trip (~600 cycles) on the CTAs that are last to finish the step.
+__device__ __forceinline__ void gemm_job_df_pair(Grp& G, const bf16* __restrict__ src0, const bf16* __restrict__ src1, int n,
+                                                 const uint8_t* Ws, int wstride, float (&out)[2]) {
+  constexpr int BPW = 2, KF = 64 * BPW * 4;
+  const int lane = G.tid & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int ks = G.warp;
+  const bool lo = g < n, hi = g + 8 < n;
+  const size_t off_lo = ((size_t)g * KF + ks * (BPW * 32)) * 2 + 16 * c, off_hi = off_lo + (size_t)8 * KF * 2;
+  const uint8_t* a0 = reinterpret_cast<const uint8_t*>(src0);
+  const uint8_t* a1 = reinterpret_cast<const uint8_t*>(src1);
+#ifndef CAPDEC_NO_PROBE
+  if (lane == 0) (void)poll16<false>(G, a0 + off_lo);
+  __syncwarp();
+#endif
+  uint4 alo[2][BPW], ahi[2][BPW];
+#pragma unroll
+  for (int j = 0; j < BPW; ++j) {
+    alo[0][j] = lo ? ldx16(a0 + off_lo + j * 64) : make_uint4(0, 0, 0, 0);
+    ahi[0][j] = hi ? ldx16(a0 + off_hi + j * 64) : make_uint4(0, 0, 0, 0);
+    alo[1][j] = lo ? ldx16(a1 + off_lo + j * 64) : make_uint4(0, 0, 0, 0);
+    ahi[1][j] = hi ? ldx16(a1 + off_hi + j * 64) : make_uint4(0, 0, 0, 0);
+  }
+  float accb[4][BPW][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int j = 0; j < BPW; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) accb[nt][j][i] = 0.f;
+  for (unsigned spins = 0;;) {                   // late elements: re-requested in rounds (see gemm_job_df)
+    bool pend = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int j = 0; j < BPW; ++j) pend = pend || (lo && sent16(alo[h][j])) || (hi && sent16(ahi[h][j]));
+    if (!pend) break;
+    if ((++spins & 63u) == 0u && poll_stalled(G.abortp, G.t_end)) break;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint8_t* ap = h ? a1 : a0;
+#pragma unroll
+      for (int j = 0; j < BPW; ++j) {
+        if (lo && sent16(alo[h][j])) alo[h][j] = ldx16(ap + off_lo + j * 64);
+        if (hi && sent16(ahi[h][j])) ahi[h][j] = ldx16(ap + off_hi + j * 64);
+      }
+    }
+  }
+  const uint8_t* w_base = Ws + (size_t)g * wstride + ks * (BPW * 64) + 16 * c;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int j = 0; j < BPW; ++j) {
+      const uint4 x = alo[h][j], y = ahi[h][j];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int nt = 2 * h + q;
+        const uint4 b = *reinterpret_cast<const uint4*>(w_base + (size_t)nt * 8 * wstride + j * 64);
+        mma_bf16(accb[nt][j], x.x, y.x, x.y, y.y, b.x, b.y);
+        mma_bf16(accb[nt][j], x.z, y.z, x.w, y.w, b.z, b.w);
+      }
+    }
+  const int row = G.tid >> 4, jj = G.tid & 15;
+  float* mine = G.red + (ks * GR + g) * REDLD + 2 * c;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (h > 0) gsync(G);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int nt = 2 * h + q;
+      *reinterpret_cast<float2*>(mine + q * 8) = make_float2(accb[nt][0][0] + accb[nt][1][0], accb[nt][0][1] + accb[nt][1][1]);
+      *reinterpret_cast<float2*>(mine + 8 * REDLD + q * 8) = make_float2(accb[nt][0][2] + accb[nt][1][2], accb[nt][0][3] + accb[nt][1][3]);
+    }
+    gsync(G);
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < KSL; ++w) sum += G.red[(w * GR + row) * REDLD + jj];
+    out[h] = sum;
+  }
+  gsync(G);                                  // `red` is free again
+}
+
 // copy `nrows` weight rows (K bf16 each, global pitch ldw elements) into shared memory rows of
 // K*2 + WPAD bytes; rows at or beyond `valid` are zero-filled.  Whole CTA.
 __device__ __noinline__ void load_weight_rows(uint8_t* Ws, const bf16* Wg, int64_t ldw, int K, int nrows,
@@ -1320,18 +1405,30 @@ __global__ void __launch_bounds__(RT, 1) recur_bwd_kernel(const __grid_constant_
     // K = KH is cut in 512-wide jobs (at most two per CTA); job (d-slice, kc) leaves its partial sum in dhp[t][kc],
     // the C phase of step t-1 adds the nkc partials (no atomics, no zeroed accumulator)
     {
+      const bf16* srcH[2] = {nullptr, nullptr};
+      int dsH[2] = {0, 0}, kcH[2] = {0, 0};
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int j = c + i * nctas;
         if (j < jobsH) {
-          const int ds = j / nkc, kc = j - ds * nkc;
-          const bf16* srcH = ((LSTM && kc < nkq) ? p.dpre_gm + ((int64_t)t * 4 + kc) * B * D
-                                                 : p.dpxk + ((int64_t)t * nkc + kc) * B * KC) + (int64_t)row0 * KC;
-          float out[1];
-          gemm_job_df<1, 2, 1>(G, srcH, 0, n, WHs + (size_t)i * 16 * wHs, wHs, out);
-          const int d = ds * 16 + ej;
-          if (lrow < n && d < D) stx4f(p.dhp + (((int64_t)t * nkc + kc) * B + erow) * D + d, out[0]);
+          dsH[i] = j / nkc;
+          kcH[i] = j - dsH[i] * nkc;
+          srcH[i] = ((LSTM && kcH[i] < nkq) ? p.dpre_gm + ((int64_t)t * 4 + kcH[i]) * B * D
+                                            : p.dpxk + ((int64_t)t * nkc + kcH[i]) * B * KC) + (int64_t)row0 * KC;
         }
+      }
+      float outH[2] = {0.f, 0.f};
+      if (srcH[0] && srcH[1]) {                  // both jobs: operand loads in flight together (CTA-uniform)
+        gemm_job_df_pair(G, srcH[0], srcH[1], n, WHs, wHs, outH);
+      } else if (srcH[0]) {
+        float o1[1];
+        gemm_job_df<1, 2, 1>(G, srcH[0], 0, n, WHs, wHs, o1);
+        outH[0] = o1[0];
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int d = dsH[i] * 16 + ej;
+        if (srcH[i] && lrow < n && d < D) stx4f(p.dhp + (((int64_t)t * nkc + kcH[i]) * B + erow) * D + d, outH[i]);
       }
     }
     BSTAMP();
