@@ -250,3 +250,33 @@ def test_eval_caption_overlay_runs_the_reference_loop_in_batches(tmp_path):
     by = {os.path.basename(f): json.load(open(f)) for f in out}
     assert by["attention_scn_beam_3_hypotheses.json"] == seen["hyps"]
     assert by["attention_scn_beam_3_incomplete.json"] == [2, 4]
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference: ONE JSON line with the B200 arm's metric / unit / config, `impl: reference`, a
+    cpu_baseline describing the run (kind = the unmodified reference modules of oracle/_ref) and an e2e block with no
+    copies; ranks other than 0 of a torchrun launch exit 0 without printing."""
+    import json
+    import subprocess
+    import sys
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref")) and not os.path.isdir("/root/reference"):
+        import pytest
+        pytest.skip("neither oracle/_ref nor the reference tree is present")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--batch", "2"]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "captions/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("captions/sec") and d["config"]["workload"] == "attention_scn_train"
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert abs(d["cpu_baseline"]["value"] - d["value"]) < 1e-9 * max(1.0, d["value"])
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0
+    env.update(RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
