@@ -1,5 +1,5 @@
 #!/bin/bash
-# fine-grained phase stamps of the persistent kernels (debug build libcapdec_fine.so) + one-row-group comparison
+# fine-grained phase stamps of the persistent kernels (debug build libcapdec_fine.so: tools/build_fine.sh first) + one-row-group comparison
 TAG=${1:-r2b}
 OUT=gpurun_out
 mkdir -p $OUT
