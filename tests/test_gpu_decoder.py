@@ -464,3 +464,41 @@ def test_scaled_shape_matches_oracle(precision, tol, gtol):
             if e >= lim:
                 bad.append((n, e, lim))
         assert not bad, bad
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: never run on a B200 yet "
+                                        "(expected to pass: every role mapping of recur_bwd_kernel is grid-size generic)")
+def test_persistent_backward_on_fewer_sms_gives_the_same_gradients(monkeypatch):
+    """Data-parallel runs launch recur_bwd_kernel on 144 instead of 148 SMs (CAPDEC_RECUR_BWD_CTAS, set by
+    capdec.parallel.GradReducer so that the fc bucket's all-reduce runs next to the reverse loop): the work items
+    are dealt to other CTAs but every item's arithmetic is unchanged, so the gradients agree with the full-grid
+    launch.  Eager launches: a captured graph keeps the grid it was captured with."""
+    dims = dict(A=512, M=512, D=512, F=512, S=1000, V=10000, E=2048)
+    B = 32
+    enc, tags, caps, caplens = O.synthetic_batch(B, dims["V"], seed=9, lengths=O.tie_free_lengths(B))
+    args = [t.cuda() for t in (enc, tags, caps, caplens)]
+    was = capdec.graphs_enabled() if hasattr(capdec, "graphs_enabled") else True
+    capdec.set_graphs(False)
+    try:
+        with capdec.precision_scope("bf16"):
+            torch.manual_seed(0)
+            dec = build_decoder(O.ATTENTION_SCN, dims).train()
+            grads = {}
+            for ctas in (None, "144"):
+                if ctas is None:
+                    monkeypatch.delenv("CAPDEC_RECUR_BWD_CTAS", raising=False)
+                else:
+                    monkeypatch.setenv("CAPDEC_RECUR_BWD_CTAS", ctas)
+                torch.manual_seed(11)
+                dec.zero_grad(set_to_none=True)
+                scores, caps_sorted, dl, alphas, sort_ind = call_forward(dec, O.ATTENTION_SCN, *args)
+                loss, _ = dec.loss(scores, caps_sorted, dl, alphas)
+                loss.backward()
+                grads[ctas] = {n: p.grad.clone() for n, p in dec.named_parameters()}
+        for n, g in grads[None].items():
+            assert torch.isfinite(grads["144"][n]).all(), n
+            if g.abs().max().item() < 1e-9:
+                continue
+            assert rel_err_fro(grads["144"][n], g) < 1e-5, n
+    finally:
+        capdec.set_graphs(was)
